@@ -1,0 +1,241 @@
+"""Snapshot packer: a plain-Python model of the informer cache + listed AWS resources -> the SoA tables of
+include/garecon.h.
+
+This is the small-case twin of the Go-side packer a maintainer would write: it walks
+objects exactly the way the reference reads them and lays strings out row-major in one byte slab per
+table group, so that consecutive rows are consecutive bytes.
+
+Model (all plain dicts / lists; order is preserved and meaningful):
+
+  objects: [ {kind: "service"|"ingress", ns, name,
+              spec_type: "ClusterIP"|"NodePort"|"LoadBalancer"|"ExternalName",   # Service only
+              lb_class: bool,                                                    # spec.loadBalancerClass != nil
+              ingress_class: None|str,                                           # *spec.ingressClassName
+              annotations: {k: v} | [(k, v)...],
+              lb_ingress: [hostname...],
+              ports: [(number, protocol_str)...] | [number...] } ]
+  actual:  {lbs: [{region, name, dns, arn, state}],
+            accelerators: [{arn, name, dns, enabled, tags: [(k, v)...],
+                            listeners: [{arn, proto: "TCP"|"UDP", ports: [from...],
+                                         egs: [{arn, endpoints: [id...]}]}]}],
+            zones: [{id, name, records: [{name, type: "A"|"TXT"|"CNAME"|"AAAA"|..., alias: None|str, values: [str...]}]}]}
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+
+_SPEC = {"ClusterIP": 0, "NodePort": 1, "LoadBalancer": 2, "ExternalName": 3, "": 0}
+_LBSTATE = {"active": 0, "provisioning": 1, "active_impaired": 2, "failed": 3}
+_RR = {"A": abi.RR_A, "TXT": abi.RR_TXT, "CNAME": abi.RR_CNAME, "AAAA": abi.RR_AAAA}
+
+
+class _Slab:
+    def __init__(self):
+        self.buf = bytearray()
+
+    def put(self, s) -> int:
+        b = s if isinstance(s, (bytes, bytearray)) else str(s).encode("utf-8", "surrogatepass")
+        off = len(self.buf)
+        self.buf += b
+        return (len(b) << abi.OFF_BITS) | off
+
+
+def _ptr(arr: np.ndarray, ctype):
+    return arr.ctypes.data_as(C.POINTER(ctype))
+
+
+class Snapshot:
+    """Owns the numpy buffers behind a GarObjects / GarActual pair."""
+
+    def __init__(self):
+        self.objects = abi.GarObjects()
+        self.actual = abi.GarActual()
+        self.arrays: dict[str, np.ndarray] = {}
+
+    def _set(self, struct, name, values, dtype, ctype):
+        arr = np.ascontiguousarray(np.asarray(values, dtype=dtype))
+        if arr.size == 0:
+            arr = np.zeros(1, dtype=dtype)[:0].copy()
+        self.arrays[name] = arr
+        # keep a 1-element backing store for empty arrays so the pointer is never NULL
+        if arr.size == 0:
+            backing = np.zeros(1, dtype=dtype)
+            self.arrays[name + "#backing"] = backing
+            setattr(struct, name, _ptr(backing, ctype))
+        else:
+            setattr(struct, name, _ptr(arr, ctype))
+
+    def obj_str(self, ref: int) -> bytes:
+        ref = int(ref)
+        off, ln = ref & abi.OFF_MASK, ref >> abi.OFF_BITS
+        return bytes(self.arrays["o.slab"][off:off + ln])
+
+    def act_str(self, ref: int) -> bytes:
+        ref = int(ref)
+        off, ln = ref & abi.OFF_MASK, ref >> abi.OFF_BITS
+        return bytes(self.arrays["a.slab"][off:off + ln])
+
+    def input_bytes(self) -> int:
+        return sum(a.nbytes for k, a in self.arrays.items() if not k.endswith("#backing"))
+
+
+def pack(objects: list[dict], actual: dict | None = None) -> Snapshot:
+    actual = actual or {}
+    snap = Snapshot()
+    o = snap.objects
+    sl = _Slab()
+    kind, spec, flags, ns, name, icls = [], [], [], [], [], []
+    ann_b, lbi_b, port_b = [0], [0], [0]
+    ann_k, ann_v, lbi_h, port_n, port_p = [], [], [], [], []
+    for ob in objects:
+        k = abi.KIND_SERVICE if ob.get("kind", "service") == "service" else abi.KIND_INGRESS
+        kind.append(k)
+        spec.append(_SPEC[ob.get("spec_type", "LoadBalancer" if k == abi.KIND_SERVICE else "")] if k == abi.KIND_SERVICE else 0)
+        f = 0
+        if ob.get("lb_class"):
+            f |= abi.OBJ_HAS_LB_CLASS
+        if ob.get("ingress_class") is not None:
+            f |= abi.OBJ_HAS_INGRESS_CLASS
+        flags.append(f)
+        ns.append(sl.put(ob.get("ns", "default")))
+        name.append(sl.put(ob["name"]))
+        icls.append(sl.put(ob["ingress_class"]) if ob.get("ingress_class") is not None else 0)
+        anns = ob.get("annotations", {})
+        items = list(anns.items()) if isinstance(anns, dict) else list(anns)
+        for ak, av in items:
+            ann_k.append(sl.put(ak))
+            ann_v.append(sl.put(av))
+        ann_b.append(len(ann_k))
+        for h in ob.get("lb_ingress", []):
+            lbi_h.append(sl.put(h))
+        lbi_b.append(len(lbi_h))
+        for p in ob.get("ports", []):
+            if isinstance(p, (tuple, list)):
+                port_n.append(int(p[0]))
+                port_p.append(sl.put(p[1]) if k == abi.KIND_SERVICE else 0)
+            else:
+                port_n.append(int(p))
+                port_p.append(sl.put("TCP") if k == abi.KIND_SERVICE else 0)
+        port_b.append(len(port_n))
+    u8, u32, u64, i32 = np.uint8, np.uint32, np.uint64, np.int32
+    o.n_objects = len(objects)
+    snap._set(o, "obj_kind", kind, u8, C.c_uint8)
+    snap._set(o, "obj_spec_type", spec, u8, C.c_uint8)
+    snap._set(o, "obj_flags", flags, u8, C.c_uint8)
+    snap._set(o, "obj_ns", ns, u64, C.c_uint64)
+    snap._set(o, "obj_name", name, u64, C.c_uint64)
+    snap._set(o, "obj_ingress_class", icls, u64, C.c_uint64)
+    snap._set(o, "obj_ann_begin", ann_b, u32, C.c_uint32)
+    snap._set(o, "obj_lbi_begin", lbi_b, u32, C.c_uint32)
+    snap._set(o, "obj_port_begin", port_b, u32, C.c_uint32)
+    o.n_ann = len(ann_k)
+    snap._set(o, "ann_key", ann_k, u64, C.c_uint64)
+    snap._set(o, "ann_val", ann_v, u64, C.c_uint64)
+    o.n_lbi = len(lbi_h)
+    snap._set(o, "lbi_hostname", lbi_h, u64, C.c_uint64)
+    o.n_ports = len(port_n)
+    snap._set(o, "port_number", port_n, i32, C.c_int32)
+    snap._set(o, "port_proto", port_p, u64, C.c_uint64)
+    slab = np.frombuffer(bytes(sl.buf) + b"\0" * 16, dtype=np.uint8).copy()
+    snap.arrays["o.slab"] = slab
+    o.slab = _ptr(slab, C.c_uint8)
+    o.slab_len = len(sl.buf)
+
+    a = snap.actual
+    sl = _Slab()
+    lbs = actual.get("lbs", [])
+    a.n_lbs = len(lbs)
+    snap._set(a, "lb_region", [sl.put(x["region"]) for x in lbs], u64, C.c_uint64)
+    snap._set(a, "lb_name", [sl.put(x["name"]) for x in lbs], u64, C.c_uint64)
+    snap._set(a, "lb_dns", [sl.put(x["dns"]) for x in lbs], u64, C.c_uint64)
+    snap._set(a, "lb_arn", [sl.put(x["arn"]) for x in lbs], u64, C.c_uint64)
+    snap._set(a, "lb_state", [_LBSTATE[x.get("state", "active")] for x in lbs], u8, C.c_uint8)
+
+    accs = actual.get("accelerators", [])
+    acc_arn, acc_name, acc_dns, acc_en = [], [], [], []
+    tag_b, lis_b, tag_k, tag_v = [0], [0], [], []
+    lis_arn, lis_proto, pr_b, eg_b, pr_from = [], [], [0], [0], []
+    eg_arn, ep_b, ep_id = [], [0], []
+    # strings are laid out accelerator-row-major: accelerator, its tags, its listeners, their egs
+    for x in accs:
+        acc_arn.append(sl.put(x["arn"]))
+        acc_name.append(sl.put(x.get("name", "")))
+        acc_dns.append(sl.put(x.get("dns", "")))
+        acc_en.append(1 if x.get("enabled", True) else 0)
+        for tk, tv in x.get("tags", []):
+            tag_k.append(sl.put(tk))
+            tag_v.append(sl.put(tv))
+        tag_b.append(len(tag_k))
+        for li in x.get("listeners", []):
+            lis_arn.append(sl.put(li["arn"]))
+            lis_proto.append(abi.PROTO_UDP if li.get("proto", "TCP") == "UDP" else abi.PROTO_TCP)
+            pr_from.extend(int(p) for p in li.get("ports", []))
+            pr_b.append(len(pr_from))
+            for eg in li.get("egs", []):
+                eg_arn.append(sl.put(eg["arn"]))
+                for e in eg.get("endpoints", []):
+                    ep_id.append(sl.put(e))
+                ep_b.append(len(ep_id))
+            eg_b.append(len(eg_arn))
+        lis_b.append(len(lis_arn))
+    a.n_accels = len(accs)
+    snap._set(a, "acc_arn", acc_arn, u64, C.c_uint64)
+    snap._set(a, "acc_name", acc_name, u64, C.c_uint64)
+    snap._set(a, "acc_dns", acc_dns, u64, C.c_uint64)
+    snap._set(a, "acc_enabled", acc_en, u8, C.c_uint8)
+    snap._set(a, "acc_tag_begin", tag_b, u32, C.c_uint32)
+    snap._set(a, "acc_lis_begin", lis_b, u32, C.c_uint32)
+    a.n_tags = len(tag_k)
+    snap._set(a, "tag_key", tag_k, u64, C.c_uint64)
+    snap._set(a, "tag_val", tag_v, u64, C.c_uint64)
+    a.n_listeners = len(lis_arn)
+    snap._set(a, "lis_arn", lis_arn, u64, C.c_uint64)
+    snap._set(a, "lis_proto", lis_proto, u8, C.c_uint8)
+    snap._set(a, "lis_pr_begin", pr_b, u32, C.c_uint32)
+    snap._set(a, "lis_eg_begin", eg_b, u32, C.c_uint32)
+    a.n_port_ranges = len(pr_from)
+    snap._set(a, "pr_from", pr_from, i32, C.c_int32)
+    a.n_egs = len(eg_arn)
+    snap._set(a, "eg_arn", eg_arn, u64, C.c_uint64)
+    snap._set(a, "eg_ep_begin", ep_b, u32, C.c_uint32)
+    a.n_endpoints = len(ep_id)
+    snap._set(a, "ep_id", ep_id, u64, C.c_uint64)
+
+    zones = actual.get("zones", [])
+    z_id, z_name, rec_b = [], [], [0]
+    r_name, r_type, r_has, r_alias, val_b, v_val = [], [], [], [], [0], []
+    for z in zones:
+        z_id.append(sl.put(z.get("id", "")))
+        z_name.append(sl.put(z["name"]))
+        for r in z.get("records", []):
+            r_name.append(sl.put(r["name"]))
+            r_type.append(_RR.get(r.get("type", "A"), abi.RR_OTHER))
+            alias = r.get("alias")
+            r_has.append(1 if alias is not None else 0)
+            r_alias.append(sl.put(alias) if alias is not None else 0)
+            for v in r.get("values", []):
+                v_val.append(sl.put(v))
+            val_b.append(len(v_val))
+        rec_b.append(len(r_name))
+    a.n_zones = len(zones)
+    snap._set(a, "zone_id", z_id, u64, C.c_uint64)
+    snap._set(a, "zone_name", z_name, u64, C.c_uint64)
+    snap._set(a, "zone_rec_begin", rec_b, u32, C.c_uint32)
+    a.n_records = len(r_name)
+    snap._set(a, "rec_name", r_name, u64, C.c_uint64)
+    snap._set(a, "rec_type", r_type, u8, C.c_uint8)
+    snap._set(a, "rec_has_alias", r_has, u8, C.c_uint8)
+    snap._set(a, "rec_alias_dns", r_alias, u64, C.c_uint64)
+    snap._set(a, "rec_val_begin", val_b, u32, C.c_uint32)
+    a.n_values = len(v_val)
+    snap._set(a, "val_value", v_val, u64, C.c_uint64)
+    slab = np.frombuffer(bytes(sl.buf) + b"\0" * 16, dtype=np.uint8).copy()
+    snap.arrays["a.slab"] = slab
+    a.slab = _ptr(slab, C.c_uint8)
+    a.slab_len = len(sl.buf)
+    snap.model = (objects, actual)
+    return snap

@@ -1,0 +1,1417 @@
+// oracle.cpp — CPU restatement of the reference's desired-vs-actual decision logic.
+//
+// TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product: only tests/,
+// __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it, and only as the
+// checker / CPU baseline.  The product path (libgarecon.so) never links or calls this file.
+//
+// Why a restatement: the reference is pure Go (CGO_ENABLED=0) and there is no Go toolchain in this image,
+// so it cannot be compiled or run here.  Every function below names the reference file:line it follows
+// (paths relative to the reference root).  Parity status:
+//   pinned by the reference's own test vectors (tests/test_oracle_golden.py):
+//     GetLBNameFromHostname, DetectCloudProvider, listenerProtocolChangedFromService,
+//     listenerPortChangedFromService, listenerForIngress, findARecord, needRecordsUpdate, parentDomain
+//   parity unpinned (no reference test exists; follows the source text only, cross-checked against an
+//   independent Python restatement, oracle/pyref.py):
+//     tagsContainsAllValues, acceleratorChanged, endpointContainsLB, list-by-owner / by-hostname,
+//     update sequencing and cardinality rules, cleanup, FindOwneredARecordSets, GetHostedZone,
+//     Route53OwnerValue, and the batch/ordering semantics (which the reference does not have).
+//
+// Two evaluation modes produce the same change set:
+//   mode 0 "faithful": per object, the reference's own linear scans (O(N*A), O(N*H*R)).
+//   mode 1 "indexed" : same decision functions over unordered_map indexes built once; optionally
+//                      multi-threaded over object ranges.  This is the fair CPU batch baseline.
+
+#include "../include/garecon.h"
+
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <string>
+#include <string_view>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+namespace {
+
+using sv = std::string_view;
+
+// ------------------------------------------------------------------ Go stdlib helpers
+
+// strings.Split(s, sep) for a one-byte separator.
+std::vector<sv> goSplit(sv s, char sep) {
+  std::vector<sv> out;
+  size_t start = 0;
+  for (size_t i = 0; i < s.size(); i++) {
+    if (s[i] == sep) {
+      out.push_back(s.substr(start, i - start));
+      start = i + 1;
+    }
+  }
+  out.push_back(s.substr(start));
+  return out;
+}
+
+bool hasSuffix(sv s, sv suf) { return s.size() >= suf.size() && s.substr(s.size() - suf.size()) == suf; }
+bool hasPrefix(sv s, sv pre) { return s.size() >= pre.size() && s.substr(0, pre.size()) == pre; }
+
+// RE2 \w : [0-9A-Za-z_]
+bool isWord(char c) { return (c >= '0' && c <= '9') || (c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z') || c == '_'; }
+
+// strings.ToLower restricted to what the comparison needs: the result is compared with "udp"/"tcp", so only
+// ASCII letters can matter (global_accelerator.go:442-446).  Non-ASCII runes that lower-case INTO ascii
+// (U+212A KELVIN SIGN -> 'k') are irrelevant for "udp"/"tcp".
+std::string asciiLower(sv s) {
+  std::string r(s);
+  for (auto &c : r)
+    if (c >= 'A' && c <= 'Z') c = char(c - 'A' + 'a');
+  return r;
+}
+
+// ------------------------------------------------------------------ pkg/cloudprovider/provider.go:8-17
+
+enum { DCP_AWS = 0, DCP_ERR = 1, DCP_PANIC = 2 };
+int detectCloudProvider(sv hostname) {
+  auto parts = goSplit(hostname, '.');
+  if (parts.size() < 2) return DCP_PANIC;  // parts[len(parts)-2] out of range
+  std::string domain = std::string(parts[parts.size() - 2]) + "." + std::string(parts[parts.size() - 1]);
+  if (domain == "amazonaws.com") return DCP_AWS;
+  return DCP_ERR;
+}
+
+// ------------------------------------------------------------------ pkg/cloudprovider/aws/load_balancer.go:32-93
+
+// `^([\w\-]+)\-[\w]+$` with Perl-like greedy semantics: group 1 is the longest prefix that lets the rest match.
+bool matchNameDashId(sv sub, sv *group1) {
+  if (sub.size() < 3) return false;
+  for (size_t p = sub.size() - 2; p >= 1; p--) {  // p = index of the separating '-'
+    if (sub[p] != '-') continue;
+    bool ok = true;
+    for (size_t i = 0; i < p && ok; i++) ok = isWord(sub[i]) || sub[i] == '-';
+    for (size_t i = p + 1; i < sub.size() && ok; i++) ok = isWord(sub[i]);
+    if (ok) {
+      *group1 = sub.substr(0, p);
+      return true;
+    }
+  }
+  return false;
+}
+
+struct Tok {
+  int code;
+  sv name, region;
+};
+
+Tok getLBNameFromHostname(sv h) {
+  // albReg `\.elb\.amazonaws\.com$`  (:33)
+  bool alb = hasSuffix(h, ".elb.amazonaws.com");
+  // nlbReg `\.elb\..+\.amazonaws\.com$`  (:34)  '.' does not match '\n' in Go regexp
+  bool nlb = false;
+  const sv tail = ".amazonaws.com";
+  if (hasSuffix(h, tail)) {
+    for (size_t i = 0; i + 5 <= h.size() && !nlb; i++) {
+      if (h.substr(i, 5) != ".elb.") continue;
+      size_t mbeg = i + 5;
+      if (h.size() < tail.size() || mbeg >= h.size() - tail.size()) continue;  // .+ needs >= 1 char
+      sv mid = h.substr(mbeg, h.size() - tail.size() - mbeg);
+      if (mid.find('\n') == sv::npos) nlb = true;
+    }
+  }
+  if (alb) {  // matchALBHostname (:46-59)
+    auto slice = goSplit(h, '.');
+    sv sub = slice[0], region = slice[1];
+    if (hasPrefix(sub, "internal-")) {  // internalALBName (:61-68)
+      sv g;
+      if (!matchNameDashId(sub.substr(9), &g)) return {GAR_TOK_ERR_INTERNAL_ALB, {}, {}};
+      return {GAR_TOK_ALB_INTERNAL, g, region};
+    }
+    sv g;  // publicALBName (:70-77)
+    if (!matchNameDashId(sub, &g)) return {GAR_TOK_ERR_PUBLIC_ALB, {}, {}};
+    return {GAR_TOK_ALB_PUBLIC, g, region};
+  }
+  if (nlb) {  // matchNLBHostname (:79-85), nlbName (:87-93)
+    auto slice = goSplit(h, '.');
+    sv sub = slice[0], region = slice[2];
+    sv g;
+    if (!matchNameDashId(sub, &g)) return {GAR_TOK_ERR_NLB, {}, {}};
+    return {GAR_TOK_NLB, g, region};
+  }
+  return {GAR_TOK_ERR_NOT_ELB, {}, {}};
+}
+
+// provider + name in one step, as the controllers sequence them (globalaccelerator/service.go:88-100)
+Tok tokenise(sv hostname) {
+  int p = detectCloudProvider(hostname);
+  if (p == DCP_PANIC) return {GAR_TOK_PANIC, {}, {}};
+  if (p == DCP_ERR) return {GAR_TOK_NOT_AWS, {}, {}};
+  return getLBNameFromHostname(hostname);
+}
+
+// ------------------------------------------------------------------ encoding/json, as used at global_accelerator.go:526-542
+//
+// json.Unmarshal([]byte(val), &[]IngressPort{}) where IngressPort{HTTP int64 `json:"HTTP,omitempty"`;
+// HTTPS int64 `json:"HTTPS,omitempty"`}.  Go (1.25, go.mod:3) first runs checkValid over the whole input
+// (encoding/json/scanner.go), then decodes; type mismatches are recorded (first one wins) and decoding goes
+// on, the error is returned at the end.  The caller maps ANY error to "no ports".
+//
+// Part 1 restates the scanner as the same step-function state machine.  Part 2 decodes the (now known
+// valid) text with a small recursive walker.
+
+struct Scanner {
+  enum { parseObjectKey, parseObjectValue, parseArrayValue };
+  enum Op { scanContinue, scanBeginLiteral, scanBeginObject, scanObjectKey, scanObjectValue, scanEndObject, scanBeginArray,
+            scanArrayValue, scanEndArray, scanSkipSpace, scanEnd, scanError };
+  typedef Op (Scanner::*Step)(unsigned char);
+  Step step;
+  bool endTop = false;
+  std::vector<int> parseState;
+  static constexpr size_t maxNestingDepth = 10000;
+
+  static bool isSpace(unsigned char c) { return c <= ' ' && (c == ' ' || c == '\t' || c == '\r' || c == '\n'); }
+  void reset() {
+    step = &Scanner::stateBeginValue;
+    parseState.clear();
+    endTop = false;
+  }
+  Op error() {
+    step = &Scanner::stateError;
+    return scanError;
+  }
+  Op pushParseState(int st, Op success) {
+    parseState.push_back(st);
+    if (parseState.size() <= maxNestingDepth) return success;
+    return error();
+  }
+  void popParseState() {
+    parseState.pop_back();
+    if (parseState.empty()) {
+      step = &Scanner::stateEndTop;
+      endTop = true;
+    } else {
+      step = &Scanner::stateEndValue;
+    }
+  }
+  Op stateBeginValueOrEmpty(unsigned char c) {
+    if (isSpace(c)) return scanSkipSpace;
+    if (c == ']') return stateEndValue(c);
+    return stateBeginValue(c);
+  }
+  Op stateBeginValue(unsigned char c) {
+    if (isSpace(c)) return scanSkipSpace;
+    switch (c) {
+      case '{': step = &Scanner::stateBeginStringOrEmpty; return pushParseState(parseObjectKey, scanBeginObject);
+      case '[': step = &Scanner::stateBeginValueOrEmpty; return pushParseState(parseArrayValue, scanBeginArray);
+      case '"': step = &Scanner::stateInString; return scanBeginLiteral;
+      case '-': step = &Scanner::stateNeg; return scanBeginLiteral;
+      case '0': step = &Scanner::state0; return scanBeginLiteral;
+      case 't': step = &Scanner::stateT; return scanBeginLiteral;
+      case 'f': step = &Scanner::stateF; return scanBeginLiteral;
+      case 'n': step = &Scanner::stateN; return scanBeginLiteral;
+    }
+    if ('1' <= c && c <= '9') {
+      step = &Scanner::state1;
+      return scanBeginLiteral;
+    }
+    return error();
+  }
+  Op stateBeginStringOrEmpty(unsigned char c) {
+    if (isSpace(c)) return scanSkipSpace;
+    if (c == '}') {
+      parseState.back() = parseObjectValue;
+      return stateEndValue(c);
+    }
+    return stateBeginString(c);
+  }
+  Op stateBeginString(unsigned char c) {
+    if (isSpace(c)) return scanSkipSpace;
+    if (c == '"') {
+      step = &Scanner::stateInString;
+      return scanBeginLiteral;
+    }
+    return error();
+  }
+  Op stateEndValue(unsigned char c) {
+    size_t n = parseState.size();
+    if (n == 0) {
+      step = &Scanner::stateEndTop;
+      endTop = true;
+      return stateEndTop(c);
+    }
+    if (isSpace(c)) {
+      step = &Scanner::stateEndValue;
+      return scanSkipSpace;
+    }
+    int ps = parseState[n - 1];
+    switch (ps) {
+      case parseObjectKey:
+        if (c == ':') {
+          parseState[n - 1] = parseObjectValue;
+          step = &Scanner::stateBeginValue;
+          return scanObjectKey;
+        }
+        return error();
+      case parseObjectValue:
+        if (c == ',') {
+          parseState[n - 1] = parseObjectKey;
+          step = &Scanner::stateBeginString;
+          return scanObjectValue;
+        }
+        if (c == '}') {
+          popParseState();
+          return scanEndObject;
+        }
+        return error();
+      case parseArrayValue:
+        if (c == ',') {
+          step = &Scanner::stateBeginValue;
+          return scanArrayValue;
+        }
+        if (c == ']') {
+          popParseState();
+          return scanEndArray;
+        }
+        return error();
+    }
+    return error();
+  }
+  Op stateEndTop(unsigned char c) {
+    if (!isSpace(c)) error();
+    return scanEnd;
+  }
+  Op stateInString(unsigned char c) {
+    if (c == '"') {
+      step = &Scanner::stateEndValue;
+      return scanContinue;
+    }
+    if (c == '\\') {
+      step = &Scanner::stateInStringEsc;
+      return scanContinue;
+    }
+    if (c < 0x20) return error();
+    return scanContinue;
+  }
+  Op stateInStringEsc(unsigned char c) {
+    switch (c) {
+      case 'b': case 'f': case 'n': case 'r': case 't': case '\\': case '/': case '"':
+        step = &Scanner::stateInString;
+        return scanContinue;
+      case 'u':
+        step = &Scanner::stateInStringEscU;
+        return scanContinue;
+    }
+    return error();
+  }
+  static bool isHex(unsigned char c) { return ('0' <= c && c <= '9') || ('a' <= c && c <= 'f') || ('A' <= c && c <= 'F'); }
+  Op stateInStringEscU(unsigned char c) {
+    if (isHex(c)) { step = &Scanner::stateInStringEscU1; return scanContinue; }
+    return error();
+  }
+  Op stateInStringEscU1(unsigned char c) {
+    if (isHex(c)) { step = &Scanner::stateInStringEscU12; return scanContinue; }
+    return error();
+  }
+  Op stateInStringEscU12(unsigned char c) {
+    if (isHex(c)) { step = &Scanner::stateInStringEscU123; return scanContinue; }
+    return error();
+  }
+  Op stateInStringEscU123(unsigned char c) {
+    if (isHex(c)) { step = &Scanner::stateInString; return scanContinue; }
+    return error();
+  }
+  Op stateNeg(unsigned char c) {
+    if (c == '0') { step = &Scanner::state0; return scanContinue; }
+    if ('1' <= c && c <= '9') { step = &Scanner::state1; return scanContinue; }
+    return error();
+  }
+  Op state1(unsigned char c) {
+    if ('0' <= c && c <= '9') { step = &Scanner::state1; return scanContinue; }
+    return state0(c);
+  }
+  Op state0(unsigned char c) {
+    if (c == '.') { step = &Scanner::stateDot; return scanContinue; }
+    if (c == 'e' || c == 'E') { step = &Scanner::stateE; return scanContinue; }
+    return stateEndValue(c);
+  }
+  Op stateDot(unsigned char c) {
+    if ('0' <= c && c <= '9') { step = &Scanner::stateDot0; return scanContinue; }
+    return error();
+  }
+  Op stateDot0(unsigned char c) {
+    if ('0' <= c && c <= '9') return scanContinue;
+    if (c == 'e' || c == 'E') { step = &Scanner::stateE; return scanContinue; }
+    return stateEndValue(c);
+  }
+  Op stateE(unsigned char c) {
+    if (c == '+' || c == '-') { step = &Scanner::stateESign; return scanContinue; }
+    return stateESign(c);
+  }
+  Op stateESign(unsigned char c) {
+    if ('0' <= c && c <= '9') { step = &Scanner::stateE0; return scanContinue; }
+    return error();
+  }
+  Op stateE0(unsigned char c) {
+    if ('0' <= c && c <= '9') return scanContinue;
+    return stateEndValue(c);
+  }
+  Op lit(unsigned char c, unsigned char want, Step next) {
+    if (c == want) { step = next; return scanContinue; }
+    return error();
+  }
+  Op stateT(unsigned char c) { return lit(c, 'r', &Scanner::stateTr); }
+  Op stateTr(unsigned char c) { return lit(c, 'u', &Scanner::stateTru); }
+  Op stateTru(unsigned char c) { return lit(c, 'e', &Scanner::stateEndValue); }
+  Op stateF(unsigned char c) { return lit(c, 'a', &Scanner::stateFa); }
+  Op stateFa(unsigned char c) { return lit(c, 'l', &Scanner::stateFal); }
+  Op stateFal(unsigned char c) { return lit(c, 's', &Scanner::stateFals); }
+  Op stateFals(unsigned char c) { return lit(c, 'e', &Scanner::stateEndValue); }
+  Op stateN(unsigned char c) { return lit(c, 'u', &Scanner::stateNu); }
+  Op stateNu(unsigned char c) { return lit(c, 'l', &Scanner::stateNul); }
+  Op stateNul(unsigned char c) { return lit(c, 'l', &Scanner::stateEndValue); }
+  Op stateError(unsigned char) { return scanError; }
+
+  // scanner.eof()
+  bool eofOk() {
+    if (step == &Scanner::stateError) return false;
+    if (endTop) return true;
+    (this->*step)(' ');
+    if (endTop) return true;
+    return false;
+  }
+};
+
+// checkValid (scanner.go)
+bool jsonValid(sv data) {
+  Scanner s;
+  s.reset();
+  for (unsigned char c : data)
+    if ((s.*(s.step))(c) == Scanner::scanError) return false;
+  return s.eofOk();
+}
+
+// --- decode phase (input is syntactically valid) ---
+
+struct JDec {
+  sv d;
+  size_t p = 0;
+  bool typeErr = false;
+  void ws() {
+    while (p < d.size() && Scanner::isSpace((unsigned char)d[p])) p++;
+  }
+  // skip any value
+  void skipValue() {
+    ws();
+    char c = d[p];
+    if (c == '"') {
+      skipString();
+    } else if (c == '{') {
+      p++;
+      ws();
+      if (d[p] == '}') { p++; return; }
+      for (;;) {
+        ws();
+        skipString();
+        ws();
+        p++;  // ':'
+        skipValue();
+        ws();
+        if (d[p] == ',') { p++; continue; }
+        p++;  // '}'
+        return;
+      }
+    } else if (c == '[') {
+      p++;
+      ws();
+      if (d[p] == ']') { p++; return; }
+      for (;;) {
+        skipValue();
+        ws();
+        if (d[p] == ',') { p++; continue; }
+        p++;  // ']'
+        return;
+      }
+    } else {
+      while (p < d.size()) {
+        char ch = d[p];
+        if (ch == ',' || ch == ']' || ch == '}' || Scanner::isSpace((unsigned char)ch)) break;
+        p++;
+      }
+    }
+  }
+  void skipString() {
+    p++;  // opening quote
+    while (d[p] != '"') {
+      if (d[p] == '\\') p++;
+      p++;
+    }
+    p++;
+  }
+  static int hexv(char c) {
+    if (c >= '0' && c <= '9') return c - '0';
+    if (c >= 'a' && c <= 'f') return c - 'a' + 10;
+    return c - 'A' + 10;
+  }
+  // unquote (decode.go unquoteBytes) into a rune sequence; invalid UTF-8 -> U+FFFD per byte as Go does.
+  std::vector<uint32_t> stringRunes() {
+    std::vector<uint32_t> out;
+    p++;
+    while (d[p] != '"') {
+      unsigned char c = (unsigned char)d[p];
+      if (c == '\\') {
+        char e = d[p + 1];
+        p += 2;
+        switch (e) {
+          case '"': out.push_back('"'); break;
+          case '\\': out.push_back('\\'); break;
+          case '/': out.push_back('/'); break;
+          case 'b': out.push_back('\b'); break;
+          case 'f': out.push_back('\f'); break;
+          case 'n': out.push_back('\n'); break;
+          case 'r': out.push_back('\r'); break;
+          case 't': out.push_back('\t'); break;
+          case 'u': {
+            uint32_t rr = hexv(d[p]) << 12 | hexv(d[p + 1]) << 8 | hexv(d[p + 2]) << 4 | hexv(d[p + 3]);
+            p += 4;
+            if (rr >= 0xD800 && rr < 0xE000) {  // utf16.IsSurrogate
+              bool paired = false;
+              if (p + 6 <= d.size() && d[p] == '\\' && d[p + 1] == 'u') {
+                // getu4 on the next 6 bytes; validity of hex digits is guaranteed by the scanner only if it IS an escape
+                uint32_t r2 = hexv(d[p + 2]) << 12 | hexv(d[p + 3]) << 8 | hexv(d[p + 4]) << 4 | hexv(d[p + 5]);
+                if (rr < 0xDC00 && r2 >= 0xDC00 && r2 < 0xE000) {  // utf16.DecodeRune valid pair
+                  out.push_back(0x10000 + ((rr - 0xD800) << 10) + (r2 - 0xDC00));
+                  p += 6;
+                  paired = true;
+                }
+              }
+              if (!paired) out.push_back(0xFFFD);
+            } else {
+              out.push_back(rr);
+            }
+            break;
+          }
+        }
+        continue;
+      }
+      if (c < 0x80) {
+        out.push_back(c);
+        p++;
+        continue;
+      }
+      // utf8.DecodeRune
+      size_t rem = 0;
+      for (size_t q = p; d[q] != '"' && rem < 4; q++) rem++;  // bytes available before the closing quote (>=1)
+      uint32_t r = 0xFFFD;
+      size_t sz = 1;
+      auto cont = [&](size_t k) { return k < rem && ((unsigned char)d[p + k] & 0xC0) == 0x80; };
+      unsigned char b1 = rem > 1 ? (unsigned char)d[p + 1] : 0;
+      if (c >= 0xC2 && c <= 0xDF) {
+        if (cont(1)) { r = (c & 0x1F) << 6 | (b1 & 0x3F); sz = 2; }
+      } else if (c >= 0xE0 && c <= 0xEF) {
+        unsigned char lo = c == 0xE0 ? 0xA0 : 0x80, hi = c == 0xED ? 0x9F : 0xBF;
+        if (rem > 1 && b1 >= lo && b1 <= hi && cont(2)) {
+          r = (c & 0x0F) << 12 | (b1 & 0x3F) << 6 | ((unsigned char)d[p + 2] & 0x3F);
+          sz = 3;
+        }
+      } else if (c >= 0xF0 && c <= 0xF4) {
+        unsigned char lo = c == 0xF0 ? 0x90 : 0x80, hi = c == 0xF4 ? 0x8F : 0xBF;
+        if (rem > 1 && b1 >= lo && b1 <= hi && cont(2) && cont(3)) {
+          r = (c & 0x07) << 18 | (b1 & 0x3F) << 12 | ((unsigned char)d[p + 2] & 0x3F) << 6 | ((unsigned char)d[p + 3] & 0x3F);
+          sz = 4;
+        }
+      }
+      out.push_back(r);
+      p += sz;
+    }
+    p++;
+    return out;
+  }
+  // encoding/json foldName: ASCII lower->upper; other runes -> smallest rune of the simple-fold orbit.
+  // Only orbits that contain an ASCII letter can influence a match against "HTTP"/"HTTPS":
+  // {K,k,U+212A} and {S,s,U+017F}.
+  static uint32_t foldRune(uint32_t r) {
+    if (r >= 'a' && r <= 'z') return r - 'a' + 'A';
+    if (r == 0x017F) return 'S';
+    if (r == 0x212A) return 'K';
+    return r;
+  }
+  static bool foldEq(const std::vector<uint32_t> &k, const char *name) {
+    size_t n = strlen(name);
+    if (k.size() != n) return false;
+    for (size_t i = 0; i < n; i++)
+      if (foldRune(k[i]) != (uint32_t)(unsigned char)name[i]) return false;
+    return true;
+  }
+  // literalStore of a value into an int64 field
+  void intField(int64_t *dst) {
+    ws();
+    char c = d[p];
+    if (c == 'n') {  // null: no-op for int kinds
+      p += 4;
+      return;
+    }
+    if (c == '-' || (c >= '0' && c <= '9')) {
+      size_t b = p;
+      skipValue();
+      sv lit = d.substr(b, p - b);
+      // strconv.ParseInt(lit, 10, 64)
+      bool neg = false;
+      size_t i = 0;
+      if (lit[0] == '-') { neg = true; i = 1; }
+      unsigned __int128 acc = 0;
+      bool bad = i >= lit.size();
+      for (; i < lit.size() && !bad; i++) {
+        if (lit[i] < '0' || lit[i] > '9') { bad = true; break; }
+        acc = acc * 10 + (unsigned)(lit[i] - '0');
+        if (acc > ((unsigned __int128)1 << 64)) bad = true;
+      }
+      if (!bad) {
+        unsigned __int128 lim = neg ? ((unsigned __int128)1 << 63) : (((unsigned __int128)1 << 63) - 1);
+        if (acc > lim) bad = true;
+      }
+      if (bad) {
+        typeErr = true;
+        return;
+      }
+      *dst = neg ? (int64_t)(0 - (uint64_t)acc) : (int64_t)(uint64_t)acc;
+      return;
+    }
+    // string, bool, object, array -> UnmarshalTypeError
+    typeErr = true;
+    skipValue();
+  }
+  // object into IngressPort
+  void ingressPort(int64_t *http, int64_t *https) {
+    ws();
+    char c = d[p];
+    if (c == 'n') { p += 4; return; }  // null leaves the zero struct
+    if (c != '{') {                    // array / string / number / bool into a struct
+      typeErr = true;
+      skipValue();
+      return;
+    }
+    p++;
+    ws();
+    if (d[p] == '}') { p++; return; }
+    for (;;) {
+      ws();
+      auto key = stringRunes();
+      ws();
+      p++;  // ':'
+      // exact match first, then case-insensitive (decode.go object()); both resolve to the same field here
+      if (foldEq(key, "HTTP")) intField(http);
+      else if (foldEq(key, "HTTPS")) intField(https);
+      else skipValue();
+      ws();
+      if (d[p] == ',') { p++; continue; }
+      p++;  // '}'
+      return;
+    }
+  }
+};
+
+// listenerForIngress' annotation branch (global_accelerator.go:526-542).  Returns false on any json error
+// (caller then uses an empty list).
+bool parseListenPorts(sv val, std::vector<int32_t> *ports) {
+  ports->clear();
+  if (!jsonValid(val)) return false;
+  JDec j{val};
+  j.ws();
+  char c = val[j.p];
+  if (c == 'n') return true;  // null -> nil slice, no error
+  if (c != '[') return false; // object / string / number / bool into a slice: UnmarshalTypeError
+  j.p++;
+  j.ws();
+  std::vector<std::pair<int64_t, int64_t>> elems;
+  if (val[j.p] == ']') {
+    j.p++;
+  } else {
+    for (;;) {
+      int64_t http = 0, https = 0;
+      j.ingressPort(&http, &https);
+      elems.push_back({http, https});
+      j.ws();
+      if (val[j.p] == ',') { j.p++; continue; }
+      j.p++;
+      break;
+    }
+  }
+  if (j.typeErr) return false;
+  for (auto &e : elems) {
+    if (e.first != 0) ports->push_back((int32_t)e.first);    // int32(i.HTTP): truncating conversion
+    if (e.second != 0) ports->push_back((int32_t)e.second);
+  }
+  return true;
+}
+
+// ------------------------------------------------------------------ port / protocol predicates
+
+// listenerPortChangedFrom{Service,Ingress} (global_accelerator.go:458-492)
+bool listenerPortChanged(const int32_t *lis, size_t nl, const int32_t *des, size_t nd) {
+  std::map<int, int> portCount;
+  for (size_t i = 0; i < nl; i++) portCount[lis[i]]++;
+  for (size_t i = 0; i < nd; i++) portCount[des[i]]++;
+  for (auto &kv : portCount)
+    if (kv.second <= 1) return true;
+  return false;
+}
+
+// listenerForService protocol half / listenerProtocolChangedFromService (:439-450, :503-515)
+int serviceProtocol(const std::vector<sv> &protos) {
+  int protocol = GAR_PROTO_TCP;
+  for (auto p : protos) {
+    std::string l = asciiLower(p);
+    if (l == "udp") protocol = GAR_PROTO_UDP;
+    else if (l == "tcp") protocol = GAR_PROTO_TCP;
+  }
+  return protocol;
+}
+
+// ------------------------------------------------------------------ route53.go helpers
+
+// parentDomain (route53.go:383-386)
+std::string parentDomain(sv hostname) {
+  auto slice = goSplit(hostname, '.');
+  std::string out;
+  for (size_t i = 1; i < slice.size(); i++) {
+    if (i > 1) out += ".";
+    out += std::string(slice[i]);
+  }
+  return out;
+}
+
+// replaceWildcards (route53.go:369-371): strings.Replace(s, "\\052", "*", 1)
+std::string replaceWildcards(sv s) {
+  size_t p = s.find("\\052");
+  if (p == sv::npos) return std::string(s);
+  return std::string(s.substr(0, p)) + "*" + std::string(s.substr(p + 4));
+}
+
+// Route53OwnerValue (route53.go:18-20)
+std::string route53OwnerValue(sv cluster, sv resource, sv ns, sv name) {
+  return "\"heritage=aws-global-accelerator-controller,cluster=" + std::string(cluster) + "," + std::string(resource) + "/" +
+         std::string(ns) + "/" + std::string(name) + "\"";
+}
+
+// ------------------------------------------------------------------ constants
+
+const char *kAnnManaged = "aws-global-accelerator-controller.h3poteto.dev/global-accelerator-managed";  // pkg/apis/type.go:4
+const char *kAnnR53Host = "aws-global-accelerator-controller.h3poteto.dev/route53-hostname";            // :5
+const char *kAnnIPPreserve = "aws-global-accelerator-controller.h3poteto.dev/client-ip-preservation";   // :6
+const char *kAnnName = "aws-global-accelerator-controller.h3poteto.dev/global-accelerator-name";        // :7
+const char *kAnnTags = "aws-global-accelerator-controller.h3poteto.dev/global-accelerator-tags";        // :8
+const char *kAnnIPType = "aws-global-accelerator-controller.h3poteto.dev/ip-address-type";              // :9
+const char *kAnnLBType = "service.beta.kubernetes.io/aws-load-balancer-type";                           // :11
+const char *kAnnIngressClass = "kubernetes.io/ingress.class";                                           // :12
+const char *kAnnListenPorts = "alb.ingress.kubernetes.io/listen-ports";  // global_accelerator.go:526
+
+const char *kTagManaged = "aws-global-accelerator-controller-managed";  // global_accelerator.go:24
+const char *kTagOwner = "aws-global-accelerator-owner";                 // :25
+const char *kTagTargetHostname = "aws-global-accelerator-target-hostname";  // :26
+const char *kTagCluster = "aws-global-accelerator-cluster";             // :27
+
+// ------------------------------------------------------------------ snapshot view
+
+struct Snap {
+  const gar_objects *o;
+  const gar_actual *a;
+  std::string cluster;
+  sv os(gar_str s) const { return sv((const char *)o->slab + GAR_STR_OFF(s), GAR_STR_LEN(s)); }
+  sv as(gar_str s) const { return sv((const char *)a->slab + GAR_STR_OFF(s), GAR_STR_LEN(s)); }
+};
+
+// indexes for mode 1
+struct Index {
+  std::unordered_map<std::string, std::vector<uint32_t>> byOwner;     // owner tag value -> accelerators (managed, cluster)
+  std::unordered_map<std::string, std::vector<uint32_t>> byHostname;  // target hostname -> accelerators (managed, cluster)
+  std::unordered_map<std::string, uint32_t> lbByRegionName;           // region + '\0' + name -> first LB row
+  std::unordered_map<std::string, uint32_t> zoneByName;               // zone name -> first zone row
+  std::unordered_map<std::string, std::vector<uint32_t>> valByValue;  // value string -> value rows (ascending)
+  std::unordered_map<std::string, std::vector<uint32_t>> aliasByZoneName;  // zone(4 bytes) + name -> alias record rows
+  std::vector<uint32_t> recZone, valRec;
+};
+
+std::string zkey(uint32_t z, sv name) {
+  std::string k((const char *)&z, 4);
+  k += std::string(name);
+  return k;
+}
+
+struct Out {
+  std::vector<gar_op> ops;
+};
+
+struct Object {
+  uint32_t row;
+  int kind;
+  sv ns, name;
+  std::map<sv, sv> ann;  // metadata.annotations as a map (later duplicate wins, like a map literal built in order)
+  bool has(const char *k) const { return ann.count(sv(k)) != 0; }
+  sv get(const char *k) const {
+    auto it = ann.find(sv(k));
+    return it == ann.end() ? sv() : it->second;
+  }
+};
+
+class Engine {
+ public:
+  Snap S;
+  int mode;
+  Index ix;
+  std::vector<uint32_t> recZone, valRec, lisAcc;
+
+  Engine(const gar_objects *o, const gar_actual *a, const char *cluster, int mode_) : S{o, a, cluster}, mode(mode_) {
+    recZone.resize(a->n_records);
+    for (uint32_t z = 0; z < a->n_zones; z++)
+      for (uint32_t r = a->zone_rec_begin[z]; r < a->zone_rec_begin[z + 1]; r++) recZone[r] = z;
+    valRec.resize(a->n_values);
+    for (uint32_t r = 0; r < a->n_records; r++)
+      for (uint32_t v = a->rec_val_begin[r]; v < a->rec_val_begin[r + 1]; v++) valRec[v] = r;
+    if (mode == 1) buildIndex();
+  }
+
+  // ---- tags
+  std::map<sv, sv> tagMap(uint32_t acc) const {  // tagsContainsAllValues' `actual` map (:560-563)
+    std::map<sv, sv> m;
+    for (uint32_t t = S.a->acc_tag_begin[acc]; t < S.a->acc_tag_begin[acc + 1]; t++) m[S.as(S.a->tag_key[t])] = S.as(S.a->tag_val[t]);
+    return m;
+  }
+  static sv mget(const std::map<sv, sv> &m, sv k) {
+    auto it = m.find(k);
+    return it == m.end() ? sv() : it->second;  // Go: missing key reads as ""
+  }
+  // tagsContainsAllValues (:559-570)
+  static bool tagsContainsAllValues(const std::map<sv, sv> &actual, const std::map<std::string, std::string> &target) {
+    for (auto &kv : target)
+      if (mget(actual, kv.first) != sv(kv.second)) return false;
+    return true;
+  }
+
+  void buildIndex() {
+    const gar_actual *a = S.a;
+    for (uint32_t i = 0; i < a->n_accels; i++) {
+      auto m = tagMap(i);
+      if (mget(m, kTagManaged) != "true") continue;
+      if (mget(m, kTagCluster) != sv(S.cluster)) continue;
+      ix.byOwner[std::string(mget(m, kTagOwner))].push_back(i);
+      ix.byHostname[std::string(mget(m, kTagTargetHostname))].push_back(i);
+    }
+    for (uint32_t i = 0; i < a->n_lbs; i++) {
+      std::string k = std::string(S.as(a->lb_region[i])) + '\0' + std::string(S.as(a->lb_name[i]));
+      ix.lbByRegionName.emplace(k, i);  // first wins
+    }
+    for (uint32_t z = 0; z < a->n_zones; z++) ix.zoneByName.emplace(std::string(S.as(a->zone_name[z])), z);
+    for (uint32_t v = 0; v < a->n_values; v++) ix.valByValue[std::string(S.as(a->val_value[v]))].push_back(v);
+    for (uint32_t r = 0; r < a->n_records; r++)
+      if (a->rec_has_alias[r]) ix.aliasByZoneName[zkey(recZone[r], S.as(a->rec_name[r]))].push_back(r);
+  }
+
+  // ---- object view
+  Object object(uint32_t i) const {
+    Object ob;
+    ob.row = i;
+    ob.kind = S.o->obj_kind[i];
+    ob.ns = S.os(S.o->obj_ns[i]);
+    ob.name = S.os(S.o->obj_name[i]);
+    for (uint32_t k = S.o->obj_ann_begin[i]; k < S.o->obj_ann_begin[i + 1]; k++) ob.ann[S.os(S.o->ann_key[k])] = S.os(S.o->ann_val[k]);
+    return ob;
+  }
+  static const char *resourceOf(int kind) { return kind == GAR_KIND_SERVICE ? "service" : "ingress"; }
+
+  // wasLoadBalancerService (globalaccelerator/service.go:18-26 == route53/service.go:19-27)
+  bool wasLoadBalancerService(const Object &ob) const {
+    if (S.o->obj_spec_type[ob.row] == GAR_SVC_LOADBALANCER) {
+      if (ob.has(kAnnLBType) || (S.o->obj_flags[ob.row] & GAR_OBJ_HAS_LB_CLASS)) return true;
+    }
+    return false;
+  }
+  // wasALBIngress (globalaccelerator/ingress.go:19-27)
+  bool wasALBIngress(const Object &ob) const {
+    if ((S.o->obj_flags[ob.row] & GAR_OBJ_HAS_INGRESS_CLASS) && S.os(S.o->obj_ingress_class[ob.row]) == "alb") return true;
+    if (ob.has(kAnnIngressClass)) return true;
+    return false;
+  }
+
+  // acceleratorOwnerTagValue (global_accelerator.go:31-33)
+  static std::string ownerTagValue(sv resource, sv ns, sv name) { return std::string(resource) + "/" + std::string(ns) + "/" + std::string(name); }
+  // acceleratorName (:53-60)
+  static std::string acceleratorName(sv resource, const Object &ob) {
+    sv n = ob.get(kAnnName);
+    if (!n.empty()) return std::string(n);
+    return std::string(resource) + "-" + std::string(ob.ns) + "-" + std::string(ob.name);
+  }
+  // acceleratorTags (:35-51)
+  static std::vector<std::pair<sv, sv>> acceleratorTags(const Object &ob) {
+    std::vector<std::pair<sv, sv>> res;
+    for (sv tag : goSplit(ob.get(kAnnTags), ',')) {
+      auto t = goSplit(tag, '=');
+      if (t.size() != 2) continue;
+      res.push_back({t[0], t[1]});
+    }
+    return res;
+  }
+
+  // desired ports and protocol: listenerForService (:503-515) / listenerForIngress (:522-557)
+  void desiredListener(const Object &ob, std::vector<int32_t> *ports, int *proto, bool *fromAnn) const {
+    ports->clear();
+    *proto = GAR_PROTO_TCP;
+    *fromAnn = false;
+    uint32_t b = S.o->obj_port_begin[ob.row], e = S.o->obj_port_begin[ob.row + 1];
+    if (ob.kind == GAR_KIND_SERVICE) {
+      std::vector<sv> protos;
+      for (uint32_t p = b; p < e; p++) {
+        ports->push_back(S.o->port_number[p]);
+        protos.push_back(S.os(S.o->port_proto[p]));
+      }
+      *proto = serviceProtocol(protos);
+      return;
+    }
+    if (ob.has(kAnnListenPorts)) {
+      *fromAnn = true;
+      std::vector<int32_t> parsed;
+      if (parseListenPorts(ob.get(kAnnListenPorts), &parsed)) *ports = parsed;
+      return;
+    }
+    for (uint32_t p = b; p < e; p++) ports->push_back(S.o->port_number[p]);
+  }
+
+  // ListGlobalAcceleratorByResource (:87-110)
+  std::vector<uint32_t> listByResource(sv resource, sv ns, sv name) const {
+    std::string owner = ownerTagValue(resource, ns, name);
+    if (mode == 1) {
+      auto it = ix.byOwner.find(owner);
+      return it == ix.byOwner.end() ? std::vector<uint32_t>() : it->second;
+    }
+    std::vector<uint32_t> res;
+    std::map<std::string, std::string> target = {{kTagManaged, "true"}, {kTagOwner, owner}, {kTagCluster, S.cluster}};
+    for (uint32_t i = 0; i < S.a->n_accels; i++)
+      if (tagsContainsAllValues(tagMap(i), target)) res.push_back(i);
+    return res;
+  }
+  // ListGlobalAcceleratorByHostname (:62-85)
+  std::vector<uint32_t> listByHostname(sv hostname) const {
+    if (mode == 1) {
+      auto it = ix.byHostname.find(std::string(hostname));
+      return it == ix.byHostname.end() ? std::vector<uint32_t>() : it->second;
+    }
+    std::vector<uint32_t> res;
+    std::map<std::string, std::string> target = {{kTagManaged, "true"}, {kTagTargetHostname, std::string(hostname)}, {kTagCluster, S.cluster}};
+    for (uint32_t i = 0; i < S.a->n_accels; i++)
+      if (tagsContainsAllValues(tagMap(i), target)) res.push_back(i);
+    return res;
+  }
+  // GetLoadBalancer (load_balancer.go:13-30), client bound to `region` (aws.go:23-25)
+  int64_t getLoadBalancer(sv region, sv name) const {
+    if (mode == 1) {
+      auto it = ix.lbByRegionName.find(std::string(region) + '\0' + std::string(name));
+      return it == ix.lbByRegionName.end() ? -1 : (int64_t)it->second;
+    }
+    for (uint32_t i = 0; i < S.a->n_lbs; i++)
+      if (S.as(S.a->lb_region[i]) == region && S.as(S.a->lb_name[i]) == name) return i;
+    return -1;
+  }
+
+  // acceleratorChanged (:412-437)
+  bool acceleratorChanged(uint32_t acc, sv lbDns, sv resource, const Object &ob) const {
+    if (!S.a->acc_enabled[acc]) return true;
+    if (S.as(S.a->acc_name[acc]) != sv(acceleratorName(resource, ob))) return true;
+    std::map<std::string, std::string> target = {
+        {kTagManaged, "true"}, {kTagOwner, ownerTagValue(resource, ob.ns, ob.name)}, {kTagTargetHostname, std::string(lbDns)}};
+    for (auto &t : acceleratorTags(ob)) target[std::string(t.first)] = std::string(t.second);
+    return !tagsContainsAllValues(tagMap(acc), target);
+  }
+
+  // CleanupGlobalAccelerator + listRelatedGlobalAccelerator (:254-288): what gets deleted for one accelerator
+  void emitDeleteChain(std::vector<gar_op> &ops, uint32_t objRow, int kind, uint32_t acc) const {
+    uint32_t lb = S.a->acc_lis_begin[acc], le = S.a->acc_lis_begin[acc + 1];
+    uint32_t lis = GAR_NONE, eg = GAR_NONE;
+    if (le - lb == 1) {  // GetListener succeeds only with exactly one (:806-812)
+      lis = lb;
+      uint32_t eb = S.a->lis_eg_begin[lis], ee = S.a->lis_eg_begin[lis + 1];
+      if (ee - eb == 1) eg = eb;  // GetEndpointGroup likewise (:900-906)
+    }
+    ops.push_back({GAR_OP_HEAD(GAR_OP_GA_DELETE_CHAIN, GAR_CTRL_GA, objRow == GAR_NONE ? 0 : kind), objRow, 0, acc, lis, eg});
+  }
+
+  // updateGlobalAcceleratorFor{Service,Ingress} (:290-410).  Returns 0 or a gar_detail error.
+  int updateAccelerator(std::vector<gar_op> &ops, const Object &ob, uint32_t j, uint32_t acc, uint32_t lb) const {
+    const gar_actual *a = S.a;
+    sv resource = resourceOf(ob.kind);
+    uint32_t head = 0;
+    auto H = [&](int op) { return GAR_OP_HEAD(op, GAR_CTRL_GA, ob.kind); };
+    (void)head;
+    if (acceleratorChanged(acc, S.as(a->lb_dns[lb]), resource, ob)) ops.push_back({H(GAR_OP_GA_UPDATE_ACCEL), ob.row, j, acc, lb, GAR_NONE});
+    std::vector<int32_t> dports;
+    int dproto;
+    bool fromAnn;
+    desiredListener(ob, &dports, &dproto, &fromAnn);
+    uint32_t lbeg = a->acc_lis_begin[acc], lend = a->acc_lis_begin[acc + 1];
+    if (lend - lbeg > 1) return GAR_D_TOO_MANY_LISTENERS;
+    if (lend == lbeg) {
+      // listener created from the desired state: the two change predicates are false on it, it has no
+      // endpoint group, and the endpoint group created for it contains the LB (:298-345)
+      ops.push_back({H(GAR_OP_GA_CREATE_LISTENER), ob.row, j, acc, GAR_NONE, GAR_NONE});
+      ops.push_back({H(GAR_OP_GA_CREATE_EG), ob.row, j, acc, GAR_NONE, lb});
+      return 0;
+    }
+    uint32_t lis = lbeg;
+    bool protoChanged = ob.kind == GAR_KIND_SERVICE ? (a->lis_proto[lis] != dproto)      // :439-450
+                                                    : (a->lis_proto[lis] != GAR_PROTO_TCP);  // :452-456
+    uint32_t pb = a->lis_pr_begin[lis], pe = a->lis_pr_begin[lis + 1];
+    bool portChanged = listenerPortChanged(a->pr_from + pb, pe - pb, dports.data(), dports.size());
+    if (protoChanged || portChanged) ops.push_back({H(GAR_OP_GA_UPDATE_LISTENER), ob.row, j, acc, lis, GAR_NONE});
+    uint32_t eb = a->lis_eg_begin[lis], ee = a->lis_eg_begin[lis + 1];
+    if (ee - eb > 1) return GAR_D_TOO_MANY_EGS;
+    if (ee == eb) {
+      ops.push_back({H(GAR_OP_GA_CREATE_EG), ob.row, j, acc, lis, lb});
+      return 0;
+    }
+    uint32_t eg = eb;
+    bool contains = false;  // endpointContainsLB (:494-501)
+    for (uint32_t d = a->eg_ep_begin[eg]; d < a->eg_ep_begin[eg + 1]; d++)
+      if (S.as(a->ep_id[d]) == S.as(a->lb_arn[lb])) contains = true;
+    if (!contains) ops.push_back({H(GAR_OP_GA_UPDATE_EG), ob.row, j, acc, eg, lb});
+    return 0;
+  }
+
+  // process{Service,Ingress}CreateOrUpdate of the globalaccelerator controller (service.go:54-126, ingress.go:56-130)
+  uint32_t gaReconcile(std::vector<gar_op> &ops, const Object &ob) const {
+    const gar_objects *o = S.o;
+    bool eligible = ob.kind == GAR_KIND_SERVICE ? wasLoadBalancerService(ob) : wasALBIngress(ob);
+    if (!eligible) return GAR_STATUS(GAR_ST_IGNORED, 0, 0);
+    uint32_t jb = o->obj_lbi_begin[ob.row], je = o->obj_lbi_begin[ob.row + 1];
+    if (je - jb < 1) return GAR_STATUS(GAR_ST_SKIP_NO_LB, 0, 0);
+    sv resource = resourceOf(ob.kind);
+    if (!ob.has(kAnnManaged)) {
+      for (uint32_t acc : listByResource(resource, ob.ns, ob.name)) emitDeleteChain(ops, ob.row, ob.kind, acc);
+      return GAR_STATUS(GAR_ST_OK, 0, GAR_EV_DELETED);
+    }
+    uint32_t ev = 0;
+    for (uint32_t j = 0; j < je - jb; j++) {
+      sv hostname = S.os(o->lbi_hostname[jb + j]);
+      int prov = detectCloudProvider(hostname);
+      if (prov == DCP_PANIC) return GAR_STATUS(GAR_ST_PANIC, 0, ev);
+      if (prov == DCP_ERR) continue;
+      Tok t = getLBNameFromHostname(hostname);
+      if (t.code >= GAR_TOK_ERR_NOT_ELB) return GAR_STATUS(GAR_ST_ERR_RETRY, GAR_D_NOT_ELB + (t.code - GAR_TOK_ERR_NOT_ELB), ev);
+      // EnsureGlobalAcceleratorFor{Service,Ingress} (global_accelerator.go:112-211)
+      int64_t lb = getLoadBalancer(t.region, t.name);
+      if (lb < 0) return GAR_STATUS(GAR_ST_ERR_RETRY, GAR_D_LB_NOT_FOUND, ev);
+      if (S.as(S.a->lb_dns[lb]) != hostname) return GAR_STATUS(GAR_ST_ERR_RETRY, GAR_D_LB_DNS_MISMATCH, ev);
+      if (S.a->lb_state[lb] != GAR_LB_ACTIVE) return GAR_STATUS(GAR_ST_REQUEUE_30S, 0, ev);
+      auto accs = listByResource(resource, ob.ns, ob.name);
+      if (accs.empty()) {
+        ops.push_back({GAR_OP_HEAD(GAR_OP_GA_CREATE_CHAIN, GAR_CTRL_GA, ob.kind), ob.row, j, (uint32_t)lb, GAR_NONE, GAR_NONE});
+        ev |= GAR_EV_CREATED;
+        continue;
+      }
+      for (uint32_t acc : accs) {
+        int err = updateAccelerator(ops, ob, j, acc, (uint32_t)lb);
+        if (err) return GAR_STATUS(GAR_ST_ERR_RETRY, err, ev);
+      }
+    }
+    return GAR_STATUS(GAR_ST_OK, 0, ev);
+  }
+
+  // ---- route53
+
+  // GetHostedZone (route53.go:335-358)
+  int64_t getHostedZone(sv original) const {
+    std::string target(original);
+    for (;;) {
+      if (target.empty()) return -1;
+      std::string want = target + ".";
+      if (mode == 1) {
+        auto it = ix.zoneByName.find(want);
+        if (it != ix.zoneByName.end()) return it->second;
+      } else {
+        for (uint32_t z = 0; z < S.a->n_zones; z++)
+          if (S.as(S.a->zone_name[z]) == sv(want)) return z;
+      }
+      target = parentDomain(target);
+    }
+  }
+
+  struct Owned {
+    uint32_t rec;  // alias record row
+    uint32_t val;  // first value row of the zone that carries the owner value under the same name
+  };
+  // FindOwneredARecordSets (route53.go:216-238) for one zone
+  std::vector<Owned> findOwneredARecordSets(uint32_t z, sv ownerValue) const {
+    const gar_actual *a = S.a;
+    std::vector<Owned> res;
+    if (mode == 1) {
+      auto it = ix.valByValue.find(std::string(ownerValue));
+      if (it == ix.valByValue.end()) return res;
+      std::vector<std::pair<sv, uint32_t>> names;  // distinct names in first-seen order, with first value row
+      for (uint32_t v : it->second) {
+        if (recZone[valRec[v]] != z) continue;
+        sv n = S.as(a->rec_name[valRec[v]]);
+        bool seen = false;
+        for (auto &p : names) seen |= (p.first == n);
+        if (!seen) names.push_back({n, v});
+      }
+      for (auto &p : names) {
+        auto at = ix.aliasByZoneName.find(zkey(z, p.first));
+        if (at == ix.aliasByZoneName.end()) continue;
+        for (uint32_t r : at->second) res.push_back({r, p.second});
+      }
+      std::sort(res.begin(), res.end(), [](const Owned &x, const Owned &y) { return x.rec < y.rec; });
+      return res;
+    }
+    std::vector<std::pair<sv, uint32_t>> hostnames;
+    for (uint32_t r = a->zone_rec_begin[z]; r < a->zone_rec_begin[z + 1]; r++)
+      for (uint32_t v = a->rec_val_begin[r]; v < a->rec_val_begin[r + 1]; v++)
+        if (S.as(a->val_value[v]) == ownerValue) hostnames.push_back({S.as(a->rec_name[r]), v});
+    for (uint32_t r = a->zone_rec_begin[z]; r < a->zone_rec_begin[z + 1]; r++) {
+      if (!a->rec_has_alias[r]) continue;
+      for (auto &h : hostnames)  // hostnameContains (:388-395): first equal name
+        if (h.first == S.as(a->rec_name[r])) {
+          res.push_back({r, h.second});
+          break;
+        }
+    }
+    return res;
+  }
+  // findOwneredMetadataRecordSets (route53.go:167-181): (record, value) once per matching value
+  std::vector<Owned> findOwneredMetadataRecordSets(uint32_t z, sv ownerValue) const {
+    const gar_actual *a = S.a;
+    std::vector<Owned> res;
+    if (mode == 1) {
+      auto it = ix.valByValue.find(std::string(ownerValue));
+      if (it == ix.valByValue.end()) return res;
+      for (uint32_t v : it->second)
+        if (recZone[valRec[v]] == z) res.push_back({valRec[v], v});
+      return res;
+    }
+    for (uint32_t r = a->zone_rec_begin[z]; r < a->zone_rec_begin[z + 1]; r++)
+      for (uint32_t v = a->rec_val_begin[r]; v < a->rec_val_begin[r + 1]; v++)
+        if (S.as(a->val_value[v]) == ownerValue) res.push_back({r, v});
+    return res;
+  }
+  // findARecord (route53.go:360-367)
+  int64_t findARecord(const std::vector<Owned> &records, sv hostname) const {
+    std::string want = std::string(hostname) + ".";
+    for (auto &rec : records)
+      if (S.a->rec_type[rec.rec] == GAR_RR_A && replaceWildcards(S.as(S.a->rec_name[rec.rec])) == want) return rec.rec;
+    return -1;
+  }
+  // needRecordsUpdate (route53.go:373-381)
+  bool needRecordsUpdate(uint32_t rec, uint32_t acc) const {
+    if (!S.a->rec_has_alias[rec]) return true;
+    return S.as(S.a->rec_alias_dns[rec]) != sv(std::string(S.as(S.a->acc_dns[acc])) + ".");
+  }
+  // CleanupRecordSet (route53.go:132-165)
+  void cleanupRecordSet(std::vector<gar_op> &ops, uint32_t objRow, int kind, sv ownerValue) const {
+    uint32_t head = GAR_OP_HEAD(GAR_OP_R53_DELETE_RECORD, GAR_CTRL_R53, objRow == GAR_NONE ? 0 : kind);
+    if (mode == 1 && ix.valByValue.find(std::string(ownerValue)) == ix.valByValue.end()) return;
+    for (uint32_t z = 0; z < S.a->n_zones; z++) {
+      for (auto &r : findOwneredARecordSets(z, ownerValue)) ops.push_back({head, objRow, 0, z, r.rec, r.val});
+      for (auto &r : findOwneredMetadataRecordSets(z, ownerValue)) ops.push_back({head, objRow, 1, z, r.rec, r.val});
+    }
+  }
+
+  // process{Service,Ingress}CreateOrUpdate of the route53 controller (route53/service.go:48-111, ingress.go:40-104)
+  uint32_t r53Reconcile(std::vector<gar_op> &ops, const Object &ob) const {
+    const gar_objects *o = S.o;
+    bool eligible = ob.kind == GAR_KIND_SERVICE ? wasLoadBalancerService(ob) : true;  // route53/controller.go:87-148
+    if (!eligible) return GAR_STATUS(GAR_ST_IGNORED, 0, 0);
+    sv resource = resourceOf(ob.kind);
+    std::string ownerValue = route53OwnerValue(S.cluster, resource, ob.ns, ob.name);
+    if (!ob.has(kAnnR53Host)) {
+      cleanupRecordSet(ops, ob.row, ob.kind, ownerValue);
+      return GAR_STATUS(GAR_ST_OK, 0, GAR_EV_DELETED);
+    }
+    auto hostnames = goSplit(ob.get(kAnnR53Host), ',');  // route53/service.go:71
+    uint32_t jb = o->obj_lbi_begin[ob.row], je = o->obj_lbi_begin[ob.row + 1];
+    uint32_t ev = 0;
+    for (uint32_t j = 0; j < je - jb; j++) {
+      sv lbHostname = S.os(o->lbi_hostname[jb + j]);
+      int prov = detectCloudProvider(lbHostname);
+      if (prov == DCP_PANIC) return GAR_STATUS(GAR_ST_PANIC, 0, ev);
+      if (prov == DCP_ERR) continue;
+      Tok t = getLBNameFromHostname(lbHostname);
+      if (t.code >= GAR_TOK_ERR_NOT_ELB) return GAR_STATUS(GAR_ST_ERR_RETRY, GAR_D_NOT_ELB + (t.code - GAR_TOK_ERR_NOT_ELB), ev);
+      // ensureRoute53 (route53.go:56-130)
+      auto accs = listByHostname(lbHostname);
+      if (accs.size() > 1) return GAR_STATUS(GAR_ST_REQUEUE_60S, GAR_D_ACCEL_MANY, ev);
+      if (accs.empty()) return GAR_STATUS(GAR_ST_REQUEUE_60S, GAR_D_ACCEL_NONE, ev);
+      uint32_t acc = accs[0];
+      bool created = false;
+      for (uint32_t k = 0; k < hostnames.size(); k++) {
+        sv hostname = hostnames[k];
+        int64_t z = getHostedZone(hostname);
+        if (z < 0) return GAR_STATUS(GAR_ST_ERR_RETRY, GAR_D_NO_HOSTED_ZONE, ev);
+        auto records = findOwneredARecordSets((uint32_t)z, ownerValue);
+        int64_t rec = findARecord(records, hostname);
+        if (rec < 0) {
+          ops.push_back({GAR_OP_HEAD(GAR_OP_R53_CREATE, GAR_CTRL_R53, ob.kind), ob.row, GAR_R53_SUB(j, k), (uint32_t)z, acc, GAR_NONE});
+          created = true;
+        } else if (needRecordsUpdate((uint32_t)rec, acc)) {
+          ops.push_back({GAR_OP_HEAD(GAR_OP_R53_UPSERT_A, GAR_CTRL_R53, ob.kind), ob.row, GAR_R53_SUB(j, k), (uint32_t)z, acc, (uint32_t)rec});
+        }
+      }
+      if (created) ev |= GAR_EV_CREATED;
+    }
+    return GAR_STATUS(GAR_ST_OK, 0, ev);
+  }
+};
+
+// ------------------------------------------------------------------ result container
+
+struct Result {
+  gar_changeset cs{};
+  std::vector<uint32_t> stGa, stR53, derived, dportBegin;
+  std::vector<gar_op> ops;
+  std::vector<uint8_t> tokCode;
+  std::vector<gar_str> tokName, tokRegion;
+  std::vector<int32_t> dports;
+};
+
+struct ObjKey {
+  int kind;
+  sv ns, name;
+  bool operator==(const ObjKey &o) const { return kind == o.kind && ns == o.ns && name == o.name; }
+};
+struct ObjKeyHash {
+  size_t operator()(const ObjKey &k) const { return std::hash<sv>()(k.ns) * 1315423911u ^ std::hash<sv>()(k.name) ^ (size_t)k.kind; }
+};
+
+// owner "resource/ns/name" -> (kind, ns, name); false if it is not a key this controller could have written
+bool parseOwner(sv owner, ObjKey *k) {
+  auto parts = goSplit(owner, '/');
+  if (parts.size() != 3) return false;
+  if (parts[0] == "service") k->kind = GAR_KIND_SERVICE;
+  else if (parts[0] == "ingress") k->kind = GAR_KIND_INGRESS;
+  else return false;
+  k->ns = parts[1];
+  k->name = parts[2];
+  return true;
+}
+
+}  // namespace
+
+// ==================================================================== exported C interface
+
+extern "C" {
+
+// Full batch diff.  mode: 0 faithful, 1 indexed.  threads only used in mode 1.
+int orc_diff(const gar_objects *o, const gar_actual *a, const char *cluster, int mode, int threads, gar_changeset **out) {
+  Engine E(o, a, cluster, mode);
+  auto *R = new Result();
+  uint32_t n = o->n_objects;
+  R->stGa.assign(n, 0);
+  R->stR53.assign(n, 0);
+  R->derived.assign(n, 0);
+  R->dportBegin.assign(n + 1, 0);
+  R->tokCode.resize(o->n_lbi);
+  R->tokName.assign(o->n_lbi, 0);
+  R->tokRegion.assign(o->n_lbi, 0);
+
+  // tokeniser results per lbIngress row
+  for (uint32_t i = 0; i < o->n_lbi; i++) {
+    sv h = E.S.os(o->lbi_hostname[i]);
+    Tok t = tokenise(h);
+    R->tokCode[i] = (uint8_t)t.code;
+    if (t.code <= GAR_TOK_NLB) {
+      uint64_t base = GAR_STR_OFF(o->lbi_hostname[i]);
+      R->tokName[i] = GAR_STR(base + (uint64_t)(t.name.data() - h.data()), t.name.size());
+      R->tokRegion[i] = GAR_STR(base + (uint64_t)(t.region.data() - h.data()), t.region.size());
+    }
+  }
+
+  if (threads < 1 || mode == 0) threads = 1;
+  std::vector<std::vector<gar_op>> gaOps(threads), r53Ops(threads);
+  std::vector<std::vector<std::vector<int32_t>>> dps(threads);
+  auto work = [&](int t) {
+    uint32_t lo = (uint64_t)n * t / threads, hi = (uint64_t)n * (t + 1) / threads;
+    for (uint32_t i = lo; i < hi; i++) {
+      Object ob = E.object(i);
+      // derived desired state
+      uint32_t dv = 0;
+      std::vector<int32_t> ports;
+      int proto;
+      bool fromAnn;
+      E.desiredListener(ob, &ports, &proto, &fromAnn);
+      if (proto == GAR_PROTO_UDP) dv |= GAR_DV_PROTO_UDP;
+      if (ob.get(kAnnIPPreserve) == "true") dv |= GAR_DV_IP_PRESERVE;
+      sv ipt = ob.get(kAnnIPType);
+      if (ipt == "ipv4" || ipt == "IPV4") dv |= GAR_DV_IPV4;  // createAccelerator switch (:686-695)
+      if (fromAnn) {
+        dv |= GAR_DV_PORTS_FROM_ANN;
+        R->dportBegin[i + 1] = (uint32_t)ports.size();
+        dps[t].push_back(ports);
+      }
+      bool gaEl = ob.kind == GAR_KIND_SERVICE ? E.wasLoadBalancerService(ob) : E.wasALBIngress(ob);
+      bool r53El = ob.kind == GAR_KIND_SERVICE ? E.wasLoadBalancerService(ob) : true;
+      if (gaEl) dv |= GAR_DV_GA_ELIGIBLE;
+      if (ob.has(kAnnManaged)) dv |= GAR_DV_GA_MANAGED;
+      if (r53El) dv |= GAR_DV_R53_ELIGIBLE;
+      if (ob.has(kAnnR53Host)) dv |= GAR_DV_R53_ANNOTATED;
+      R->derived[i] = dv;
+      R->stGa[i] = E.gaReconcile(gaOps[t], ob);
+      R->stR53[i] = E.r53Reconcile(r53Ops[t], ob);
+    }
+  };
+  if (threads == 1) {
+    work(0);
+  } else {
+    std::vector<std::thread> th;
+    for (int t = 0; t < threads; t++) th.emplace_back(work, t);
+    for (auto &x : th) x.join();
+  }
+  // dports CSR
+  for (uint32_t i = 0; i < n; i++) R->dportBegin[i + 1] += R->dportBegin[i];
+  for (auto &v : dps)
+    for (auto &p : v) R->dports.insert(R->dports.end(), p.begin(), p.end());
+
+  // cache membership for orphan detection
+  std::unordered_map<ObjKey, uint32_t, ObjKeyHash> cache;
+  for (uint32_t i = 0; i < n; i++) cache.emplace(ObjKey{o->obj_kind[i], E.S.os(o->obj_ns[i]), E.S.os(o->obj_name[i])}, i);
+
+  // section 0: GA ops of cached objects
+  R->cs.section_begin[0] = 0;
+  for (auto &v : gaOps) R->ops.insert(R->ops.end(), v.begin(), v.end());
+  R->cs.section_begin[1] = R->ops.size();
+  // section 1: GA orphans = what process{Service,Ingress}Delete (service.go:28-52, ingress.go:29-54) would clean
+  // for every owner key of this cluster that has no object in the cache
+  for (uint32_t acc = 0; acc < a->n_accels; acc++) {
+    auto m = E.tagMap(acc);
+    if (Engine::mget(m, kTagManaged) != "true") continue;
+    if (Engine::mget(m, kTagCluster) != sv(E.S.cluster)) continue;
+    ObjKey k;
+    if (!parseOwner(Engine::mget(m, kTagOwner), &k)) continue;
+    if (cache.count(k)) continue;
+    E.emitDeleteChain(R->ops, GAR_NONE, 0, acc);
+  }
+  R->cs.section_begin[2] = R->ops.size();
+  // section 2: R53 ops of cached objects
+  for (auto &v : r53Ops) R->ops.insert(R->ops.end(), v.begin(), v.end());
+  R->cs.section_begin[3] = R->ops.size();
+  // section 3: R53 orphans = CleanupRecordSet (route53/service.go:29-46) for every owner value of this cluster
+  // with no object in the cache; order (zone, phase, record row, value row)
+  {
+    std::string prefix = "\"heritage=aws-global-accelerator-controller,cluster=" + E.S.cluster + ",";
+    auto orphanKey = [&](sv value, ObjKey *k) {
+      if (!hasPrefix(value, prefix) || value.size() < prefix.size() + 1 || value.back() != '"') return false;
+      sv mid = value.substr(prefix.size(), value.size() - prefix.size() - 1);
+      if (!parseOwner(mid, k)) return false;
+      return cache.count(*k) == 0;
+    };
+    uint32_t head = GAR_OP_HEAD(GAR_OP_R53_DELETE_RECORD, GAR_CTRL_R53, 0);
+    for (uint32_t z = 0; z < a->n_zones; z++) {
+      uint32_t rb = a->zone_rec_begin[z], re = a->zone_rec_begin[z + 1];
+      // orphan value rows of this zone, ascending
+      std::vector<uint32_t> ov;
+      for (uint32_t r = rb; r < re; r++)
+        for (uint32_t v = a->rec_val_begin[r]; v < a->rec_val_begin[r + 1]; v++) {
+          ObjKey k;
+          if (orphanKey(E.S.as(a->val_value[v]), &k)) ov.push_back(v);
+        }
+      // phase 0: alias set r x orphan owner value (represented by its first value row under that name)
+      for (uint32_t r = rb; r < re; r++) {
+        if (!a->rec_has_alias[r]) continue;
+        std::vector<sv> seen;
+        for (uint32_t v : ov) {
+          if (E.S.as(a->rec_name[E.valRec[v]]) != E.S.as(a->rec_name[r])) continue;
+          sv val = E.S.as(a->val_value[v]);
+          if (std::find(seen.begin(), seen.end(), val) != seen.end()) continue;
+          seen.push_back(val);
+          R->ops.push_back({head, GAR_NONE, 0, z, r, v});
+        }
+      }
+      // phase 1: owner metadata sets
+      for (uint32_t v : ov) R->ops.push_back({head, GAR_NONE, 1, z, E.valRec[v], v});
+    }
+  }
+  R->cs.section_begin[4] = R->ops.size();
+
+  gar_changeset &cs = R->cs;
+  cs.n_objects = n;
+  cs.status_ga = R->stGa.data();
+  cs.status_r53 = R->stR53.data();
+  cs.derived = R->derived.data();
+  cs.n_ops = R->ops.size();
+  cs.ops = R->ops.data();
+  cs.n_lbi = o->n_lbi;
+  cs.tok_code = R->tokCode.data();
+  cs.tok_name = R->tokName.data();
+  cs.tok_region = R->tokRegion.data();
+  cs.dport_begin = R->dportBegin.data();
+  cs.n_dports = R->dports.size();
+  cs.dports = R->dports.data();
+  cs.opaque = R;
+  *out = &R->cs;
+  return 0;
+}
+
+void orc_free(gar_changeset *cs) {
+  if (cs) delete (Result *)cs->opaque;
+}
+
+// ---- unit entry points, used by the golden-vector tests
+
+// DetectCloudProvider: 0 "aws", 1 error, 2 panic
+int orc_detect_cloud_provider(const char *h, uint32_t len) { return detectCloudProvider(sv(h, len)); }
+
+// GetLBNameFromHostname: returns gar_tok_code (>= GAR_TOK_ERR_NOT_ELB on error); offsets relative to h
+int orc_get_lb_name_from_hostname(const char *h, uint32_t len, uint32_t *name_off, uint32_t *name_len, uint32_t *region_off, uint32_t *region_len) {
+  sv s(h, len);
+  Tok t = getLBNameFromHostname(s);
+  if (t.code <= GAR_TOK_NLB) {
+    *name_off = (uint32_t)(t.name.data() - h);
+    *name_len = (uint32_t)t.name.size();
+    *region_off = (uint32_t)(t.region.data() - h);
+    *region_len = (uint32_t)t.region.size();
+  }
+  return t.code;
+}
+
+// listenerForIngress annotation branch: returns number of ports, or -1 on json error
+int orc_parse_listen_ports(const char *val, uint32_t len, int32_t *out, int cap) {
+  std::vector<int32_t> p;
+  if (!parseListenPorts(sv(val, len), &p)) return -1;
+  for (size_t i = 0; i < p.size() && (int)i < cap; i++) out[i] = p[i];
+  return (int)p.size();
+}
+
+int orc_json_valid(const char *val, uint32_t len) { return jsonValid(sv(val, len)) ? 1 : 0; }
+
+int orc_listener_port_changed(const int32_t *lis, uint32_t nl, const int32_t *des, uint32_t nd) { return listenerPortChanged(lis, nl, des, nd) ? 1 : 0; }
+
+// protocol selected by listenerForService over `n` NUL-terminated protocol strings
+int orc_service_protocol(const char *const *protos, uint32_t n) {
+  std::vector<sv> v;
+  for (uint32_t i = 0; i < n; i++) v.push_back(sv(protos[i]));
+  return serviceProtocol(v);
+}
+
+// parentDomain: writes into out (cap bytes), returns length
+int orc_parent_domain(const char *h, uint32_t len, char *out, int cap) {
+  std::string p = parentDomain(sv(h, len));
+  int n = (int)p.size() < cap ? (int)p.size() : cap;
+  memcpy(out, p.data(), n);
+  return (int)p.size();
+}
+
+// findARecord over parallel arrays (names NUL-terminated, types GAR_RR_*): returns index or -1
+int orc_find_a_record(const char *const *names, const uint8_t *types, uint32_t n, const char *hostname) {
+  std::string want = std::string(hostname) + ".";
+  for (uint32_t i = 0; i < n; i++)
+    if (types[i] == GAR_RR_A && replaceWildcards(sv(names[i])) == want) return (int)i;
+  return -1;
+}
+
+// needRecordsUpdate
+int orc_need_records_update(int has_alias, const char *alias_dns, const char *accel_dns) {
+  if (!has_alias) return 1;
+  return sv(alias_dns) != sv(std::string(accel_dns) + ".") ? 1 : 0;
+}
+
+int orc_route53_owner_value(const char *cluster, const char *resource, const char *ns, const char *name, char *out, int cap) {
+  std::string v = route53OwnerValue(cluster, resource, ns, name);
+  int n = (int)v.size() < cap ? (int)v.size() : cap;
+  memcpy(out, v.data(), n);
+  return (int)v.size();
+}
+
+}  // extern "C"
