@@ -1,0 +1,693 @@
+// gar_engine.cu — CUDA backend (sm_100a) and C ABI of the reconcile-diff engine.
+//
+// Implements include/garecon.h.  Stage logic lives in gar_rows.h / gar_pipeline.h; this file supplies what
+// is specific to the GPU: kernels for the data-parallel stages, the device-wide exclusive scan, the stable LSD
+// radix sort that orders hash-index buckets, device/pinned memory management, stream + event timing.
+//
+// There is deliberately no CPU path in this library: every entry point needs a live sm_100 device.
+
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+#include <utility>
+
+#include "gar_pipeline.h"
+
+#define GAR_VERSION_STRING "garecon 0.1.0 (sm_100a)"
+
+// ------------------------------------------------------------------ kernels
+
+template <class F>
+__global__ void __launch_bounds__(256) k_for_each(const __grid_constant__ F f, u32 n) {
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) f(i);
+}
+
+__global__ void k_fill32(u32 *p, u32 v, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) p[i] = v;
+}
+
+// ---- exclusive scan (u32): per-tile reduce, single-block scan of tile sums, per-tile scan + offset
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ u32 warp_incl_scan(u32 v) {
+  const unsigned lane = threadIdx.x & 31;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    u32 t = __shfl_up_sync(0xffffffffu, v, d);
+    if (lane >= (unsigned)d) v += t;
+  }
+  return v;
+}
+// exclusive scan of one value per thread across the block; returns the exclusive prefix, *total = block sum
+__device__ __forceinline__ u32 block_excl_scan(u32 v, u32 *total) {
+  __shared__ u32 wsum[SCAN_THREADS / 32];
+  __shared__ u32 wtot;
+  const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  u32 inc = warp_incl_scan(v);
+  if (lane == 31) wsum[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    u32 s = lane < SCAN_THREADS / 32 ? wsum[lane] : 0;
+    u32 si = warp_incl_scan(s);
+    if (lane < SCAN_THREADS / 32) wsum[lane] = si - s;
+    if (lane == SCAN_THREADS / 32 - 1) wtot = si;
+  }
+  __syncthreads();
+  u32 r = wsum[w] + inc - v;
+  *total = wtot;
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const u32 *in, u32 *tile_sums, u32 n) {
+  u32 base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  u32 s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++)
+    if (base + k < n) s += in[base + k];
+  u32 tot;
+  block_excl_scan(s, &tot);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
+}
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(u32 *tile_sums, u32 ntiles) {
+  u32 carry = 0;
+  for (u32 b = 0; b < ntiles; b += SCAN_THREADS) {
+    u32 i = b + threadIdx.x;
+    u32 v = i < ntiles ? tile_sums[i] : 0;
+    u32 tot;
+    u32 ex = block_excl_scan(v, &tot);
+    if (i < ntiles) tile_sums[i] = carry + ex;
+    carry += tot;
+  }
+}
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(u32 *data, const u32 *tile_sums, u32 n) {
+  u32 base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+  u32 v[SCAN_ITEMS];
+  u32 s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    v[k] = base + k < n ? data[base + k] : 0;
+    s += v[k];
+  }
+  u32 tot;
+  u32 ex = block_excl_scan(s, &tot) + tile_sums[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) {
+    if (base + k < n) data[base + k] = ex;
+    ex += v[k];
+  }
+}
+
+// ---- stable LSD radix sort of (u32 key, u32 value) pairs, 8 bits per pass.
+// Tile = 256 threads x 8 items; inside a tile item order is (warp, round, lane) = ascending index, and the
+// per-digit rank is built with match_any so equal keys keep their input order.
+constexpr int RS_THREADS = 256;
+constexpr int RS_ITEMS = 8;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
+constexpr int RS_WARPS = RS_THREADS / 32;
+
+__global__ void __launch_bounds__(RS_THREADS) k_radix_hist(const u32 *keys, u32 n, int shift, u32 *hist /* [256][ntiles] */, u32 ntiles) {
+  __shared__ u32 h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  u32 base = blockIdx.x * RS_TILE;
+#pragma unroll
+  for (int k = 0; k < RS_ITEMS; k++) {
+    u32 i = base + k * RS_THREADS + threadIdx.x;
+    if (i < n) atomicAdd(&h[(keys[i] >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  hist[(size_t)threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const u32 *keys, const u32 *vals, u32 *keys_out, u32 *vals_out, u32 n, int shift,
+                                                              const u32 *hist_scanned, u32 ntiles) {
+  __shared__ u32 wcnt[RS_WARPS][256];
+  __shared__ u32 dbase[256];
+  const unsigned lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int k = threadIdx.x; k < RS_WARPS * 256; k += RS_THREADS) (&wcnt[0][0])[k] = 0;
+  dbase[threadIdx.x] = hist_scanned[(size_t)threadIdx.x * ntiles + blockIdx.x];
+  __syncthreads();
+  const u32 wbase = blockIdx.x * RS_TILE + w * (32 * RS_ITEMS);
+  u32 key[RS_ITEMS], val[RS_ITEMS], rank[RS_ITEMS];
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; r++) {
+    u32 i = wbase + r * 32 + lane;
+    bool ok = i < n;
+    key[r] = ok ? keys[i] : 0;
+    val[r] = ok ? vals[i] : 0;
+    u32 d = ok ? ((key[r] >> shift) & 255u) : 256u;  // 256 = out-of-range items group together and are dropped
+    unsigned peers = __match_any_sync(0xffffffffu, d);
+    unsigned leader = __ffs(peers) - 1;
+    u32 before = __popc(peers & ((1u << lane) - 1));
+    u32 prev = 0;
+    if (lane == leader && d < 256u) {
+      prev = wcnt[w][d];
+      wcnt[w][d] = prev + __popc(peers);
+    }
+    prev = __shfl_sync(0xffffffffu, prev, leader);
+    rank[r] = prev + before;
+    __syncwarp();
+  }
+  __syncthreads();
+  {  // exclusive prefix over warps for digit = threadIdx.x
+    u32 run = 0;
+#pragma unroll
+    for (int ww = 0; ww < RS_WARPS; ww++) {
+      u32 c = wcnt[ww][threadIdx.x];
+      wcnt[ww][threadIdx.x] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; r++) {
+    u32 i = wbase + r * 32 + lane;
+    if (i < n) {
+      u32 d = (key[r] >> shift) & 255u;
+      u32 dst = dbase[d] + wcnt[w][d] + rank[r];
+      keys_out[dst] = key[r];
+      vals_out[dst] = val[r];
+    }
+  }
+}
+
+// ------------------------------------------------------------------ engine
+
+struct DBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+};
+
+struct HostResult {  // pinned host buffers of one change set
+  DBuf status_ga, status_r53, derived, ops, tok_code, tok_name, tok_region, dport_begin, dports;
+};
+
+#define CK(call)                                                                                             \
+  do {                                                                                                       \
+    cudaError_t _e = (call);                                                                                 \
+    if (_e != cudaSuccess) {                                                                                 \
+      char _b[512];                                                                                          \
+      snprintf(_b, sizeof(_b), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      throw CudaError{std::string(_b)};                                                                      \
+    }                                                                                                        \
+  } while (0)
+
+struct CudaError {
+  std::string msg;
+};
+struct InvalidError {
+  std::string msg;
+};
+
+static std::string g_create_error = "";
+
+struct gar_engine {
+  int device = 0;
+  std::string cluster;
+  std::string err;
+  std::mutex mu;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[6] = {};
+  bool loaded = false, attached = false;
+  DevTables T{};
+  std::vector<DBuf> in;        // device copies of the input arrays (copy mode)
+  size_t in_used = 0;
+  DBuf cluster_dev;
+  DBuf slot[S_NSLOTS];
+  DBuf d_status_ga, d_status_r53, d_derived, d_ops, d_tok_code, d_tok_name, d_tok_region, d_dport_begin, d_dports, d_scan_tiles, d_hist;
+  std::vector<HostResult *> free_results;
+  float ms_h2d = 0;
+  u32 launches = 0;
+  u64 input_bytes = 0;  // slabs + fixed-width columns, each once
+
+  // ---- memory
+  void *dev_ensure(DBuf &b, size_t bytes) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (b.cap < bytes) {
+      if (b.p) CK(cudaFree(b.p));
+      b.p = nullptr;
+      b.cap = 0;
+      size_t want = bytes + bytes / 4;
+      CK(cudaMalloc(&b.p, want));
+      b.cap = want;
+    }
+    return b.p;
+  }
+  void *pin_ensure(DBuf &b, size_t bytes) {
+    if (bytes < 64) bytes = 64;
+    if (b.cap < bytes) {
+      if (b.p) CK(cudaFreeHost(b.p));
+      b.p = nullptr;
+      b.cap = 0;
+      size_t want = bytes + bytes / 4;
+      CK(cudaMallocHost(&b.p, want));
+      b.cap = want;
+    }
+    return b.p;
+  }
+
+  // ---- Backend interface (gar_pipeline.h)
+  template <class F>
+  void for_each(const char *, u32 n, const F &f) {
+    if (!n) return;
+    k_for_each<F><<<(n + 255) / 256, 256, 0, stream>>>(f, n);
+    launches++;
+  }
+  void fill32(u32 *p, u32 v, size_t n) {
+    if (!n) return;
+    if (v == 0) {
+      CK(cudaMemsetAsync(p, 0, n * 4, stream));
+      return;
+    }
+    size_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_fill32<<<(unsigned)blocks, 256, 0, stream>>>(p, v, n);
+    launches++;
+  }
+  void copy32(u32 *dst, const u32 *src, size_t n) {
+    if (n) CK(cudaMemcpyAsync(dst, src, n * 4, cudaMemcpyDeviceToDevice, stream));
+  }
+  void exclusive_scan(u32 *data, u32 n) {
+    if (!n) return;
+    u32 ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    u32 *tiles = (u32 *)dev_ensure(d_scan_tiles, 4 * (size_t)(ntiles + 1));
+    k_scan_reduce<<<ntiles, SCAN_THREADS, 0, stream>>>(data, tiles, n);
+    k_scan_tiles<<<1, SCAN_THREADS, 0, stream>>>(tiles, ntiles);
+    k_scan_apply<<<ntiles, SCAN_THREADS, 0, stream>>>(data, tiles, n);
+    launches += 3;
+  }
+  void sort_pairs(u32 *keys, u32 *vals, u32 *keys_alt, u32 *vals_alt, u32 n, int bits) {
+    if (!n) return;
+    u32 ntiles = (n + RS_TILE - 1) / RS_TILE;
+    u32 *hist = (u32 *)dev_ensure(d_hist, 4 * (size_t)256 * ntiles + 16);
+    u32 *ka = keys, *va = vals, *kb = keys_alt, *vb = vals_alt;
+    int passes = (bits + 7) / 8;
+    for (int p = 0; p < passes; p++) {
+      k_radix_hist<<<ntiles, RS_THREADS, 0, stream>>>(ka, n, p * 8, hist, ntiles);
+      launches++;
+      exclusive_scan(hist, 256 * ntiles);
+      k_radix_scatter<<<ntiles, RS_THREADS, 0, stream>>>(ka, va, kb, vb, n, p * 8, hist, ntiles);
+      launches++;
+      std::swap(ka, kb);
+      std::swap(va, vb);
+    }
+    if (ka != keys) {  // odd number of passes: bring the result back
+      CK(cudaMemcpyAsync(keys, ka, 4 * (size_t)n, cudaMemcpyDeviceToDevice, stream));
+      CK(cudaMemcpyAsync(vals, va, 4 * (size_t)n, cudaMemcpyDeviceToDevice, stream));
+    }
+  }
+  void *ensure(int s, size_t bytes) { return dev_ensure(slot[s], bytes); }
+  void download(void *dst, const void *src, size_t bytes) {
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+  }
+  void *out_derived(u32 n) { return dev_ensure(d_derived, 4 * (size_t)(n + 1)); }
+  void *out_dport_begin(u32 n) { return dev_ensure(d_dport_begin, 4 * (size_t)(n + 2)); }
+  void *out_tok_code(u32 n) { return dev_ensure(d_tok_code, (size_t)n + 1); }
+  void *out_tok_name(u32 n) { return dev_ensure(d_tok_name, 8 * (size_t)(n + 1)); }
+  void *out_tok_region(u32 n) { return dev_ensure(d_tok_region, 8 * (size_t)(n + 1)); }
+  void *out_dports(u64 n) { return dev_ensure(d_dports, 4 * (size_t)(n + 1)); }
+  void *out_status_ga(u32 n) { return dev_ensure(d_status_ga, 4 * (size_t)(n + 1)); }
+  void *out_status_r53(u32 n) { return dev_ensure(d_status_r53, 4 * (size_t)(n + 1)); }
+};
+
+// ------------------------------------------------------------------ snapshot validation (host, copy mode only)
+
+static void check_str_col(const char *name, const gar_str *col, size_t n, u64 slab_len) {
+  if (n && !col) throw InvalidError{std::string(name) + " is NULL"};
+  for (size_t i = 0; i < n; i++) {
+    u64 off = GAR_STR_OFF(col[i]), len = GAR_STR_LEN(col[i]);
+    if (off + len > slab_len) throw InvalidError{std::string(name) + ": string reference outside the slab"};
+  }
+}
+static void check_csr(const char *name, const u32 *b, size_t nparents, size_t nchildren) {
+  if (!b) throw InvalidError{std::string(name) + " is NULL"};
+  if (b[0] != 0) throw InvalidError{std::string(name) + "[0] != 0"};
+  for (size_t i = 0; i < nparents; i++)
+    if (b[i + 1] < b[i]) throw InvalidError{std::string(name) + " is not monotone"};
+  if (b[nparents] != nchildren) throw InvalidError{std::string(name) + " does not end at the child count"};
+}
+static void check_ptr(const char *name, const void *p, size_t n) {
+  if (n && !p) throw InvalidError{std::string(name) + " is NULL"};
+}
+
+static void validate(const gar_objects *o, const gar_actual *a) {
+  if (!o || !a) throw InvalidError{"NULL table struct"};
+  size_t n = o->n_objects;
+  check_ptr("obj_kind", o->obj_kind, n);
+  check_ptr("obj_spec_type", o->obj_spec_type, n);
+  check_ptr("obj_flags", o->obj_flags, n);
+  check_ptr("objects.slab", o->slab, o->slab_len);
+  check_str_col("obj_ns", o->obj_ns, n, o->slab_len);
+  check_str_col("obj_name", o->obj_name, n, o->slab_len);
+  check_str_col("obj_ingress_class", o->obj_ingress_class, n, o->slab_len);
+  check_csr("obj_ann_begin", o->obj_ann_begin, n, o->n_ann);
+  check_csr("obj_lbi_begin", o->obj_lbi_begin, n, o->n_lbi);
+  check_csr("obj_port_begin", o->obj_port_begin, n, o->n_ports);
+  check_str_col("ann_key", o->ann_key, o->n_ann, o->slab_len);
+  check_str_col("ann_val", o->ann_val, o->n_ann, o->slab_len);
+  check_str_col("lbi_hostname", o->lbi_hostname, o->n_lbi, o->slab_len);
+  check_ptr("port_number", o->port_number, o->n_ports);
+  check_str_col("port_proto", o->port_proto, o->n_ports, o->slab_len);
+  for (size_t i = 0; i < n; i++) {
+    if (o->obj_kind[i] > GAR_KIND_INGRESS) throw InvalidError{"obj_kind out of range"};
+    u64 sep = GAR_STR_OFF(o->obj_ns[i]) + GAR_STR_LEN(o->obj_ns[i]);
+    if (GAR_STR_OFF(o->obj_name[i]) != sep + 1 || sep >= o->slab_len || o->slab[sep] != '/')
+      throw InvalidError{"objects layout rule violated: obj_ns and obj_name must be slices of one \"ns/name\" key string"};
+  }
+  check_ptr("actual.slab", a->slab, a->slab_len);
+  check_str_col("lb_region", a->lb_region, a->n_lbs, a->slab_len);
+  check_str_col("lb_name", a->lb_name, a->n_lbs, a->slab_len);
+  check_str_col("lb_dns", a->lb_dns, a->n_lbs, a->slab_len);
+  check_str_col("lb_arn", a->lb_arn, a->n_lbs, a->slab_len);
+  check_ptr("lb_state", a->lb_state, a->n_lbs);
+  check_str_col("acc_arn", a->acc_arn, a->n_accels, a->slab_len);
+  check_str_col("acc_name", a->acc_name, a->n_accels, a->slab_len);
+  check_str_col("acc_dns", a->acc_dns, a->n_accels, a->slab_len);
+  check_ptr("acc_enabled", a->acc_enabled, a->n_accels);
+  check_csr("acc_tag_begin", a->acc_tag_begin, a->n_accels, a->n_tags);
+  check_csr("acc_lis_begin", a->acc_lis_begin, a->n_accels, a->n_listeners);
+  check_str_col("tag_key", a->tag_key, a->n_tags, a->slab_len);
+  check_str_col("tag_val", a->tag_val, a->n_tags, a->slab_len);
+  check_str_col("lis_arn", a->lis_arn, a->n_listeners, a->slab_len);
+  check_ptr("lis_proto", a->lis_proto, a->n_listeners);
+  check_csr("lis_pr_begin", a->lis_pr_begin, a->n_listeners, a->n_port_ranges);
+  check_csr("lis_eg_begin", a->lis_eg_begin, a->n_listeners, a->n_egs);
+  check_ptr("pr_from", a->pr_from, a->n_port_ranges);
+  check_str_col("eg_arn", a->eg_arn, a->n_egs, a->slab_len);
+  check_csr("eg_ep_begin", a->eg_ep_begin, a->n_egs, a->n_endpoints);
+  check_str_col("ep_id", a->ep_id, a->n_endpoints, a->slab_len);
+  check_str_col("zone_id", a->zone_id, a->n_zones, a->slab_len);
+  check_str_col("zone_name", a->zone_name, a->n_zones, a->slab_len);
+  check_csr("zone_rec_begin", a->zone_rec_begin, a->n_zones, a->n_records);
+  check_str_col("rec_name", a->rec_name, a->n_records, a->slab_len);
+  check_ptr("rec_type", a->rec_type, a->n_records);
+  check_ptr("rec_has_alias", a->rec_has_alias, a->n_records);
+  check_str_col("rec_alias_dns", a->rec_alias_dns, a->n_records, a->slab_len);
+  check_csr("rec_val_begin", a->rec_val_begin, a->n_records, a->n_values);
+  check_str_col("val_value", a->val_value, a->n_values, a->slab_len);
+}
+
+// bytes of the input tables, each array counted once (roofline numerator)
+static u64 table_bytes(const gar_objects *o, const gar_actual *a) {
+  u64 n = o->n_objects, b = 0;
+  b += o->slab_len + a->slab_len;
+  b += n * (3 + 8 * 3) + 4 * (n + 1) * 3;
+  b += (u64)o->n_ann * 16 + (u64)o->n_lbi * 8 + (u64)o->n_ports * 12;
+  b += (u64)a->n_lbs * (8 * 4 + 1);
+  b += (u64)a->n_accels * (8 * 3 + 1) + 4 * ((u64)a->n_accels + 1) * 2;
+  b += (u64)a->n_tags * 16;
+  b += (u64)a->n_listeners * (8 + 1) + 4 * ((u64)a->n_listeners + 1) * 2;
+  b += (u64)a->n_port_ranges * 4;
+  b += (u64)a->n_egs * 8 + 4 * ((u64)a->n_egs + 1);
+  b += (u64)a->n_endpoints * 8;
+  b += (u64)a->n_zones * 16 + 4 * ((u64)a->n_zones + 1);
+  b += (u64)a->n_records * (8 + 1 + 1 + 8) + 4 * ((u64)a->n_records + 1);
+  b += (u64)a->n_values * 8;
+  return b;
+}
+
+// ------------------------------------------------------------------ load
+
+template <class Tp>
+static const Tp *upload(gar_engine *e, const Tp *host, size_t count, size_t pad_bytes = 0) {
+  if (e->in_used >= e->in.size()) e->in.emplace_back();
+  DBuf &b = e->in[e->in_used++];
+  size_t bytes = count * sizeof(Tp);
+  e->dev_ensure(b, bytes + pad_bytes + 16);
+  if (bytes) CK(cudaMemcpyAsync(b.p, host, bytes, cudaMemcpyHostToDevice, e->stream));
+  if (pad_bytes) CK(cudaMemsetAsync((char *)b.p + bytes, 0, pad_bytes, e->stream));
+  return (const Tp *)b.p;
+}
+
+static void do_load(gar_engine *e, const gar_objects *o, const gar_actual *a) {
+  validate(o, a);
+  CK(cudaSetDevice(e->device));
+  e->in_used = 0;
+  DevTables &T = e->T;
+  CK(cudaEventRecord(e->ev[0], e->stream));
+  T.o = *o;
+  T.a = *a;
+  size_t n = o->n_objects;
+  T.o.obj_kind = upload(e, o->obj_kind, n);
+  T.o.obj_spec_type = upload(e, o->obj_spec_type, n);
+  T.o.obj_flags = upload(e, o->obj_flags, n);
+  T.o.obj_ns = upload(e, o->obj_ns, n);
+  T.o.obj_name = upload(e, o->obj_name, n);
+  T.o.obj_ingress_class = upload(e, o->obj_ingress_class, n);
+  T.o.obj_ann_begin = upload(e, o->obj_ann_begin, n + 1);
+  T.o.obj_lbi_begin = upload(e, o->obj_lbi_begin, n + 1);
+  T.o.obj_port_begin = upload(e, o->obj_port_begin, n + 1);
+  T.o.ann_key = upload(e, o->ann_key, o->n_ann);
+  T.o.ann_val = upload(e, o->ann_val, o->n_ann);
+  T.o.lbi_hostname = upload(e, o->lbi_hostname, o->n_lbi);
+  T.o.port_number = upload(e, o->port_number, o->n_ports);
+  T.o.port_proto = upload(e, o->port_proto, o->n_ports);
+  T.o.slab = upload(e, o->slab, o->slab_len, GAR_SLAB_PAD);
+  T.a.lb_region = upload(e, a->lb_region, a->n_lbs);
+  T.a.lb_name = upload(e, a->lb_name, a->n_lbs);
+  T.a.lb_dns = upload(e, a->lb_dns, a->n_lbs);
+  T.a.lb_arn = upload(e, a->lb_arn, a->n_lbs);
+  T.a.lb_state = upload(e, a->lb_state, a->n_lbs);
+  T.a.acc_arn = upload(e, a->acc_arn, a->n_accels);
+  T.a.acc_name = upload(e, a->acc_name, a->n_accels);
+  T.a.acc_dns = upload(e, a->acc_dns, a->n_accels);
+  T.a.acc_enabled = upload(e, a->acc_enabled, a->n_accels);
+  T.a.acc_tag_begin = upload(e, a->acc_tag_begin, (size_t)a->n_accels + 1);
+  T.a.acc_lis_begin = upload(e, a->acc_lis_begin, (size_t)a->n_accels + 1);
+  T.a.tag_key = upload(e, a->tag_key, a->n_tags);
+  T.a.tag_val = upload(e, a->tag_val, a->n_tags);
+  T.a.lis_arn = upload(e, a->lis_arn, a->n_listeners);
+  T.a.lis_proto = upload(e, a->lis_proto, a->n_listeners);
+  T.a.lis_pr_begin = upload(e, a->lis_pr_begin, (size_t)a->n_listeners + 1);
+  T.a.lis_eg_begin = upload(e, a->lis_eg_begin, (size_t)a->n_listeners + 1);
+  T.a.pr_from = upload(e, a->pr_from, a->n_port_ranges);
+  T.a.eg_arn = upload(e, a->eg_arn, a->n_egs);
+  T.a.eg_ep_begin = upload(e, a->eg_ep_begin, (size_t)a->n_egs + 1);
+  T.a.ep_id = upload(e, a->ep_id, a->n_endpoints);
+  T.a.zone_id = upload(e, a->zone_id, a->n_zones);
+  T.a.zone_name = upload(e, a->zone_name, a->n_zones);
+  T.a.zone_rec_begin = upload(e, a->zone_rec_begin, (size_t)a->n_zones + 1);
+  T.a.rec_name = upload(e, a->rec_name, a->n_records);
+  T.a.rec_type = upload(e, a->rec_type, a->n_records);
+  T.a.rec_has_alias = upload(e, a->rec_has_alias, a->n_records);
+  T.a.rec_alias_dns = upload(e, a->rec_alias_dns, a->n_records);
+  T.a.rec_val_begin = upload(e, a->rec_val_begin, (size_t)a->n_records + 1);
+  T.a.val_value = upload(e, a->val_value, a->n_values);
+  T.a.slab = upload(e, a->slab, a->slab_len, GAR_SLAB_PAD);
+  CK(cudaEventRecord(e->ev[1], e->stream));
+  CK(cudaStreamSynchronize(e->stream));  // caller may free its buffers when we return
+  CK(cudaEventElapsedTime(&e->ms_h2d, e->ev[0], e->ev[1]));
+  e->input_bytes = table_bytes(o, a);
+  e->loaded = true;
+  e->attached = false;
+}
+
+// ------------------------------------------------------------------ diff
+
+static void do_diff(gar_engine *e, gar_changeset *out, bool to_host) {
+  if (!e->loaded) throw InvalidError{"no snapshot loaded"};
+  CK(cudaSetDevice(e->device));
+  memset(out, 0, sizeof(*out));
+  e->launches = 0;
+  Pipeline<gar_engine> P(*e, e->T);
+  DiffCounts dc{};
+  CK(cudaEventRecord(e->ev[2], e->stream));
+  int rc = P.run(&dc, [&](u64 nops) { return e->dev_ensure(e->d_ops, sizeof(gar_op) * (size_t)(nops + 1)); });
+  CK(cudaEventRecord(e->ev[3], e->stream));
+  if (rc == GAR_E_INVALID) {
+    CK(cudaStreamSynchronize(e->stream));
+    throw InvalidError{"objects layout rule violated: obj_ns and obj_name must be slices of one \"ns/name\" key string"};
+  }
+  const u32 n = e->T.o.n_objects, nlbi = e->T.o.n_lbi;
+  out->n_objects = n;
+  out->n_ops = dc.n_ops;
+  for (int k = 0; k <= GAR_N_SECTIONS; k++) out->section_begin[k] = dc.section_begin[k];
+  out->n_lbi = nlbi;
+  out->n_dports = dc.n_dports;
+  if (to_host) {
+    HostResult *h;
+    if (!e->free_results.empty()) {
+      h = e->free_results.back();
+      e->free_results.pop_back();
+    } else {
+      h = new HostResult();
+    }
+    out->opaque = h;
+    auto pull = [&](DBuf &hb, const DBuf &db, size_t bytes) -> void * {
+      void *p = e->pin_ensure(hb, bytes);
+      if (bytes) CK(cudaMemcpyAsync(p, db.p, bytes, cudaMemcpyDeviceToHost, e->stream));
+      return p;
+    };
+    out->status_ga = (const u32 *)pull(h->status_ga, e->d_status_ga, 4 * (size_t)n);
+    out->status_r53 = (const u32 *)pull(h->status_r53, e->d_status_r53, 4 * (size_t)n);
+    out->derived = (const u32 *)pull(h->derived, e->d_derived, 4 * (size_t)n);
+    out->ops = (const gar_op *)pull(h->ops, e->d_ops, sizeof(gar_op) * (size_t)dc.n_ops);
+    out->tok_code = (const u8 *)pull(h->tok_code, e->d_tok_code, nlbi);
+    out->tok_name = (const gar_str *)pull(h->tok_name, e->d_tok_name, 8 * (size_t)nlbi);
+    out->tok_region = (const gar_str *)pull(h->tok_region, e->d_tok_region, 8 * (size_t)nlbi);
+    out->dport_begin = (const u32 *)pull(h->dport_begin, e->d_dport_begin, 4 * (size_t)(n + 1));
+    out->dports = (const i32 *)pull(h->dports, e->d_dports, 4 * (size_t)dc.n_dports);
+  } else {
+    out->status_ga = (const u32 *)e->d_status_ga.p;
+    out->status_r53 = (const u32 *)e->d_status_r53.p;
+    out->derived = (const u32 *)e->d_derived.p;
+    out->ops = (const gar_op *)e->d_ops.p;
+    out->tok_code = (const u8 *)e->d_tok_code.p;
+    out->tok_name = (const gar_str *)e->d_tok_name.p;
+    out->tok_region = (const gar_str *)e->d_tok_region.p;
+    out->dport_begin = (const u32 *)e->d_dport_begin.p;
+    out->dports = (const i32 *)e->d_dports.p;
+  }
+  CK(cudaEventRecord(e->ev[4], e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  CK(cudaGetLastError());
+  CK(cudaEventElapsedTime(&out->ms_kernels, e->ev[2], e->ev[3]));
+  CK(cudaEventElapsedTime(&out->ms_d2h, e->ev[3], e->ev[4]));
+  out->ms_h2d = e->ms_h2d;
+  out->kernel_launches = e->launches;
+}
+
+// ------------------------------------------------------------------ C ABI
+
+template <class Fn>
+static int guarded(gar_engine *e, Fn fn) {
+  if (!e) return GAR_E_INVALID;
+  std::lock_guard<std::mutex> lk(e->mu);
+  try {
+    fn();
+    e->err.clear();
+    return GAR_OK;
+  } catch (const CudaError &ce) {
+    e->err = ce.msg;
+    cudaGetLastError();
+    return GAR_E_CUDA;
+  } catch (const InvalidError &ie) {
+    e->err = ie.msg;
+    return GAR_E_INVALID;
+  } catch (const std::bad_alloc &) {
+    e->err = "out of host memory";
+    return GAR_E_NOMEM;
+  }
+}
+
+extern "C" {
+
+int gar_engine_create(const gar_config *cfg, gar_engine **out) {
+  if (out) *out = nullptr;
+  if (!cfg || !out || cfg->abi_version != GAR_ABI_VERSION) {
+    g_create_error = "bad config or ABI version mismatch";
+    return GAR_E_INVALID;
+  }
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0 || cfg->device < 0 || cfg->device >= ndev) {
+    g_create_error = std::string("no usable CUDA device: ") + (ce != cudaSuccess ? cudaGetErrorString(ce) : "device ordinal out of range");
+    cudaGetLastError();
+    return GAR_E_NO_DEVICE;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess || prop.major != 10) {
+    g_create_error = "device is not sm_100 (this library ships sm_100a code only)";
+    cudaGetLastError();
+    return GAR_E_NO_DEVICE;
+  }
+  gar_engine *e = new gar_engine();
+  e->device = cfg->device;
+  e->cluster = cfg->cluster_name ? cfg->cluster_name : "";
+  try {
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    for (auto &ev : e->ev) CK(cudaEventCreate(&ev));
+    e->dev_ensure(e->cluster_dev, e->cluster.size() + GAR_SLAB_PAD);
+    CK(cudaMemsetAsync(e->cluster_dev.p, 0, e->cluster.size() + GAR_SLAB_PAD, e->stream));
+    if (!e->cluster.empty()) CK(cudaMemcpyAsync(e->cluster_dev.p, e->cluster.data(), e->cluster.size(), cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+  } catch (const CudaError &err) {
+    g_create_error = err.msg;
+    delete e;
+    return GAR_E_CUDA;
+  }
+  *out = e;
+  return GAR_OK;
+}
+
+void gar_engine_destroy(gar_engine *e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  for (auto &b : e->in) cudaFree(b.p);
+  for (auto &b : e->slot) cudaFree(b.p);
+  for (DBuf *b : {&e->cluster_dev, &e->d_status_ga, &e->d_status_r53, &e->d_derived, &e->d_ops, &e->d_tok_code, &e->d_tok_name, &e->d_tok_region,
+                  &e->d_dport_begin, &e->d_dports, &e->d_scan_tiles, &e->d_hist})
+    cudaFree(b->p);
+  for (HostResult *h : e->free_results) {
+    for (DBuf *b : {&h->status_ga, &h->status_r53, &h->derived, &h->ops, &h->tok_code, &h->tok_name, &h->tok_region, &h->dport_begin, &h->dports}) cudaFreeHost(b->p);
+    delete h;
+  }
+  for (auto &ev : e->ev)
+    if (ev) cudaEventDestroy(ev);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+int gar_snapshot_load(gar_engine *e, const gar_objects *desired, const gar_actual *actual) {
+  return guarded(e, [&] {
+    do_load(e, desired, actual);
+    e->T.cluster = (const u8 *)e->cluster_dev.p;
+    e->T.cluster_len = (u32)e->cluster.size();
+  });
+}
+
+int gar_snapshot_attach_device(gar_engine *e, const gar_objects *desired, const gar_actual *actual) {
+  return guarded(e, [&] {
+    if (!desired || !actual) throw InvalidError{"NULL table struct"};
+    e->T.o = *desired;
+    e->T.a = *actual;
+    e->T.cluster = (const u8 *)e->cluster_dev.p;
+    e->T.cluster_len = (u32)e->cluster.size();
+    e->input_bytes = table_bytes(desired, actual);
+    e->ms_h2d = 0;
+    e->loaded = true;
+    e->attached = true;
+  });
+}
+
+int gar_diff(gar_engine *e, gar_changeset *out) {
+  if (!out) return GAR_E_INVALID;
+  return guarded(e, [&] { do_diff(e, out, true); });
+}
+
+int gar_diff_device(gar_engine *e, gar_changeset *out) {
+  if (!out) return GAR_E_INVALID;
+  return guarded(e, [&] { do_diff(e, out, false); });
+}
+
+void gar_changeset_free(gar_engine *e, gar_changeset *cs) {
+  if (!e || !cs) return;
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (cs->opaque) e->free_results.push_back((HostResult *)cs->opaque);
+  memset(cs, 0, sizeof(*cs));
+}
+
+const char *gar_last_error(const gar_engine *e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+const char *gar_version(void) { return GAR_VERSION_STRING; }
+
+uint64_t gar_algorithmic_bytes(const gar_engine *e, const gar_changeset *cs) {
+  if (!e || !cs) return 0;
+  return e->input_bytes + 2ull * 4 * cs->n_objects + sizeof(gar_op) * cs->n_ops;
+}
+
+}  // extern "C"

@@ -101,8 +101,13 @@ def pack(objects: list[dict], actual: dict | None = None) -> Snapshot:
         if ob.get("ingress_class") is not None:
             f |= abi.OBJ_HAS_INGRESS_CLASS
         flags.append(f)
-        ns.append(sl.put(ob.get("ns", "default")))
-        name.append(sl.put(ob["name"]))
+        # layout rule: ns and name are slices of one "ns/name" string (the workqueue key, reconcile.go:47)
+        nsb = str(ob.get("ns", "default")).encode("utf-8", "surrogatepass")
+        nmb = str(ob["name"]).encode("utf-8", "surrogatepass")
+        kref = sl.put(nsb + b"/" + nmb)
+        koff = kref & abi.OFF_MASK
+        ns.append((len(nsb) << abi.OFF_BITS) | koff)
+        name.append((len(nmb) << abi.OFF_BITS) | (koff + len(nsb) + 1))
         icls.append(sl.put(ob["ingress_class"]) if ob.get("ingress_class") is not None else 0)
         anns = ob.get("annotations", {})
         items = list(anns.items()) if isinstance(anns, dict) else list(anns)

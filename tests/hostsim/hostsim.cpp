@@ -1,0 +1,137 @@
+// hostsim.cpp — TEST BUILD ONLY: the engine's row logic and pipeline (csrc/gar_rows.h, gar_pipeline.h) compiled
+// for the host, with loops / std::stable_sort standing in for kernels.  It exists because the build container has
+// no GPU: it lets `pytest -m "not gpu"` run the very functions the sm_100a kernels are made of against the oracle.
+// It is never loaded by the package and is not a fallback: libgarecon.so has no CPU path.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../aws-global-accelerator-controller_b200/csrc/gar_pipeline.h"
+
+struct HBuf {
+  std::vector<uint64_t> mem;
+  void *ensure(size_t bytes) {
+    size_t w = (bytes + 7) / 8 + 8;
+    if (mem.size() < w) mem.assign(w, 0);
+    return mem.data();
+  }
+};
+
+struct gar_engine {
+  std::string cluster, err;
+  std::vector<uint8_t> cluster_pad;
+  DevTables T{};
+  bool loaded = false;
+  std::vector<std::vector<uint8_t>> slabs;
+  HBuf slot[S_NSLOTS];
+  HBuf o_status_ga, o_status_r53, o_derived, o_ops, o_tok_code, o_tok_name, o_tok_region, o_dport_begin, o_dports;
+  u64 input_bytes = 0;
+  u32 launches = 0;
+
+  template <class F>
+  void for_each(const char *, u32 n, const F &f) {
+    launches++;
+    for (u32 i = 0; i < n; i++) f(i);
+  }
+  void fill32(u32 *p, u32 v, size_t n) { std::fill(p, p + n, v); }
+  void copy32(u32 *d, const u32 *s, size_t n) { memcpy(d, s, n * 4); }
+  void exclusive_scan(u32 *d, u32 n) {
+    u32 run = 0;
+    for (u32 i = 0; i < n; i++) {
+      u32 v = d[i];
+      d[i] = run;
+      run += v;
+    }
+  }
+  void sort_pairs(u32 *keys, u32 *vals, u32 *, u32 *, u32 n, int) {
+    std::vector<u32> idx(n);
+    std::iota(idx.begin(), idx.end(), 0u);
+    std::stable_sort(idx.begin(), idx.end(), [&](u32 a, u32 b) { return keys[a] < keys[b]; });
+    std::vector<u32> k(n), v(n);
+    for (u32 i = 0; i < n; i++) {
+      k[i] = keys[idx[i]];
+      v[i] = vals[idx[i]];
+    }
+    memcpy(keys, k.data(), n * 4);
+    memcpy(vals, v.data(), n * 4);
+  }
+  void *ensure(int s, size_t bytes) { return slot[s].ensure(bytes); }
+  void download(void *dst, const void *src, size_t bytes) { memcpy(dst, src, bytes); }
+  void *out_derived(u32 n) { return o_derived.ensure(4 * (size_t)(n + 1)); }
+  void *out_dport_begin(u32 n) { return o_dport_begin.ensure(4 * (size_t)(n + 2)); }
+  void *out_tok_code(u32 n) { return o_tok_code.ensure(n + 1); }
+  void *out_tok_name(u32 n) { return o_tok_name.ensure(8 * (size_t)(n + 1)); }
+  void *out_tok_region(u32 n) { return o_tok_region.ensure(8 * (size_t)(n + 1)); }
+  void *out_dports(u64 n) { return o_dports.ensure(4 * (size_t)(n + 1)); }
+  void *out_status_ga(u32 n) { return o_status_ga.ensure(4 * (size_t)(n + 1)); }
+  void *out_status_r53(u32 n) { return o_status_r53.ensure(4 * (size_t)(n + 1)); }
+};
+
+static std::string g_err;
+
+extern "C" {
+
+int gar_engine_create(const gar_config *cfg, gar_engine **out) {
+  auto *e = new gar_engine();
+  e->cluster = cfg->cluster_name ? cfg->cluster_name : "";
+  e->cluster_pad.assign(e->cluster.size() + 64, 0);
+  memcpy(e->cluster_pad.data(), e->cluster.data(), e->cluster.size());
+  *out = e;
+  return GAR_OK;
+}
+void gar_engine_destroy(gar_engine *e) { delete e; }
+
+int gar_snapshot_load(gar_engine *e, const gar_objects *o, const gar_actual *a) {
+  // copy only the slabs (for padding); columns are read in place (the caller keeps them alive in tests)
+  e->slabs.clear();
+  e->slabs.emplace_back(o->slab_len + 64, 0);
+  if (o->slab_len) memcpy(e->slabs[0].data(), o->slab, o->slab_len);
+  e->slabs.emplace_back(a->slab_len + 64, 0);
+  if (a->slab_len) memcpy(e->slabs[1].data(), a->slab, a->slab_len);
+  e->T.o = *o;
+  e->T.a = *a;
+  e->T.o.slab = e->slabs[0].data();
+  e->T.a.slab = e->slabs[1].data();
+  e->T.cluster = e->cluster_pad.data();
+  e->T.cluster_len = (u32)e->cluster.size();
+  e->loaded = true;
+  return GAR_OK;
+}
+int gar_snapshot_attach_device(gar_engine *e, const gar_objects *o, const gar_actual *a) { return gar_snapshot_load(e, o, a); }
+
+int gar_diff(gar_engine *e, gar_changeset *out) {
+  memset(out, 0, sizeof(*out));
+  e->launches = 0;
+  Pipeline<gar_engine> P(*e, e->T);
+  DiffCounts dc{};
+  int rc = P.run(&dc, [&](u64 nops) { return e->o_ops.ensure(sizeof(gar_op) * (size_t)(nops + 1)); });
+  if (rc != GAR_OK) {
+    e->err = "objects layout rule violated";
+    return rc;
+  }
+  out->n_objects = e->T.o.n_objects;
+  out->status_ga = (const u32 *)e->o_status_ga.mem.data();
+  out->status_r53 = (const u32 *)e->o_status_r53.mem.data();
+  out->derived = (const u32 *)e->o_derived.mem.data();
+  out->n_ops = dc.n_ops;
+  out->ops = (const gar_op *)e->o_ops.mem.data();
+  for (int k = 0; k <= GAR_N_SECTIONS; k++) out->section_begin[k] = dc.section_begin[k];
+  out->n_lbi = e->T.o.n_lbi;
+  out->tok_code = (const u8 *)e->o_tok_code.mem.data();
+  out->tok_name = (const gar_str *)e->o_tok_name.mem.data();
+  out->tok_region = (const gar_str *)e->o_tok_region.mem.data();
+  out->dport_begin = (const u32 *)e->o_dport_begin.mem.data();
+  out->n_dports = dc.n_dports;
+  out->dports = (const i32 *)e->o_dports.mem.data();
+  out->kernel_launches = e->launches;
+  return GAR_OK;
+}
+int gar_diff_device(gar_engine *e, gar_changeset *out) { return gar_diff(e, out); }
+void gar_changeset_free(gar_engine *, gar_changeset *cs) { memset(cs, 0, sizeof(*cs)); }
+const char *gar_last_error(const gar_engine *e) { return e ? e->err.c_str() : g_err.c_str(); }
+const char *gar_version(void) { return "garecon hostsim (test build)"; }
+uint64_t gar_algorithmic_bytes(const gar_engine *, const gar_changeset *) { return 0; }
+}

@@ -1,0 +1,85 @@
+"""GPU tier: the sm_100a library, called through the C ABI (ctypes), must produce the oracle's change set
+bit for bit (integer/index work: no tolerance)."""
+import numpy as np
+import pytest
+
+import randmodel
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_snapshots_match_oracle(garecon, oracle, engine, seed):
+    objects, actual = randmodel.make(seed, n_objects=60)
+    snap = garecon.pack(objects, actual)
+    engine.load(snap)
+    got = engine.diff()
+    want = oracle.diff(snap, "default", mode=1)
+    assert got.diff(want) == [], got.describe_first_mismatch(want)
+    assert got.kernel_launches > 0
+
+
+def test_empty_snapshot(garecon, oracle, engine):
+    snap = garecon.pack([], {})
+    engine.load(snap)
+    got = engine.diff()
+    assert got.diff(oracle.diff(snap, "default", mode=1)) == []
+
+
+def test_objects_without_any_actual_state(garecon, oracle, engine):
+    objects, _ = randmodel.make(5, n_objects=50)
+    snap = garecon.pack(objects, {})
+    engine.load(snap)
+    got = engine.diff()
+    want = oracle.diff(snap, "default", mode=1)
+    assert got.diff(want) == [], got.describe_first_mismatch(want)
+
+
+def test_orphans_only(garecon, oracle, engine):
+    _, actual = randmodel.make(9, n_objects=50)
+    snap = garecon.pack([], actual)
+    engine.load(snap)
+    got = engine.diff()
+    want = oracle.diff(snap, "default", mode=1)
+    assert got.diff(want) == [], got.describe_first_mismatch(want)
+    assert len(got.ops) > 0
+
+
+def test_golden_hostnames_through_the_abi(garecon, engine):
+    """reference load_balancer_test.go:17-40 through the tokeniser kernel."""
+    from test_oracle_golden import LB_HOSTNAMES
+    objects = [dict(kind="service", ns="default", name=f"s{i}", annotations={}, lb_ingress=[h]) for i, (h, *_r) in enumerate(LB_HOSTNAMES)]
+    snap = garecon.pack(objects, {})
+    engine.load(snap)
+    cs = engine.diff()
+    for i, (h, name, region, code) in enumerate(LB_HOSTNAMES):
+        assert cs.tok_code[i] == code
+        assert snap.obj_str(cs.tok_name[i]).decode() == name
+        assert snap.obj_str(cs.tok_region[i]).decode() == region
+
+
+def test_golden_listen_ports_through_the_abi(garecon, engine):
+    """reference global_accelerator_test.go:354-480 + local_e2e fixture through the JSON kernel."""
+    anns = ['[{"HTTP": 80}, {"HTTPS": 443}]', '[{"HTTPS":443}]']
+    objects = [dict(kind="ingress", ns="default", name=f"i{i}", ingress_class="alb", annotations={"alb.ingress.kubernetes.io/listen-ports": a}, ports=[8080, 80])
+               for i, a in enumerate(anns)]
+    snap = garecon.pack(objects, {})
+    engine.load(snap)
+    cs = engine.diff()
+    assert list(cs.dport_begin) == [0, 2, 3]
+    assert list(cs.dports) == [80, 443, 443]
+
+
+def test_layout_rule_violation_is_an_error(garecon, engine):
+    snap = garecon.pack([dict(kind="service", ns="a", name="b")], {})
+    snap.arrays["obj_name"][0] = (1 << garecon.abi.OFF_BITS) | 0  # name no longer follows "ns/"
+    with pytest.raises(garecon.GarError) as ei:
+        engine.load(snap)
+    assert ei.value.rc == garecon.abi.GAR_E_INVALID
+
+
+def test_bad_string_reference_is_an_error(garecon, engine):
+    snap = garecon.pack([dict(kind="service", ns="a", name="b", annotations={"k": "v"})], {})
+    snap.arrays["ann_val"][0] = (100 << garecon.abi.OFF_BITS) | 5
+    with pytest.raises(garecon.GarError):
+        engine.load(snap)
