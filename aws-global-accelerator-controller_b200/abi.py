@@ -95,6 +95,13 @@ class GarConfig(C.Structure):
     _fields_ = [("abi_version", C.c_uint32), ("device", C.c_int32), ("cluster_name", C.c_char_p), ("flags", C.c_uint32)]
 
 
+class GarStageTiming(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("ms", C.c_float), ("launches", C.c_uint32), ("bytes", C.c_uint64)]
+
+
+FLAG_STAGE_TIMING = 1
+
+
 class GarOp(C.Structure):
     _fields_ = [("head", C.c_uint32), ("obj", C.c_uint32), ("sub", C.c_uint32), ("a0", C.c_uint32), ("a1", C.c_uint32), ("a2", C.c_uint32)]
 
@@ -207,6 +214,8 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
     lib.gar_version.restype = C.c_char_p
     lib.gar_algorithmic_bytes.argtypes = [C.c_void_p, C.POINTER(GarChangeset)]
     lib.gar_algorithmic_bytes.restype = C.c_uint64
+    lib.gar_last_stage_timings.argtypes = [C.c_void_p, C.POINTER(GarStageTiming), C.c_uint32]
+    lib.gar_last_stage_timings.restype = C.c_uint32
     if path is None:
         _lib = lib
     return lib
@@ -215,6 +224,7 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
 EXPORTED_SYMBOLS = (
     "gar_engine_create", "gar_engine_destroy", "gar_snapshot_load", "gar_snapshot_attach_device", "gar_diff",
     "gar_diff_device", "gar_changeset_free", "gar_last_error", "gar_version", "gar_algorithmic_bytes",
+    "gar_last_stage_timings",
 )
 
 
@@ -227,11 +237,11 @@ class GarError(RuntimeError):
 class Engine:
     """Thin RAII wrapper over gar_engine_* (one engine per process per device)."""
 
-    def __init__(self, cluster_name: str = "default", device: int = 0, lib: C.CDLL | None = None):
+    def __init__(self, cluster_name: str = "default", device: int = 0, lib: C.CDLL | None = None, stage_timing: bool = False):
         self.lib = lib or load_library()
         self._h = C.c_void_p()
         self._cluster = cluster_name.encode()
-        cfg = GarConfig(GAR_ABI_VERSION, device, self._cluster, 0)
+        cfg = GarConfig(GAR_ABI_VERSION, device, self._cluster, FLAG_STAGE_TIMING if stage_timing else 0)
         rc = self.lib.gar_engine_create(C.byref(cfg), C.byref(self._h))
         if rc != GAR_OK:
             msg = self.lib.gar_last_error(self._h).decode(errors="replace") if self._h else self.lib.gar_last_error(None).decode(errors="replace")
@@ -264,6 +274,12 @@ class Engine:
         cs = GarChangeset()
         self._check(self.lib.gar_diff_device(self._h, C.byref(cs)))
         return cs
+
+    def stage_timings(self) -> list[tuple[str, float, int]]:
+        """(name, ms, launches) per stage of the last diff (engine created with stage_timing=True)."""
+        arr = (GarStageTiming * 128)()
+        n = self.lib.gar_last_stage_timings(self._h, arr, 128)
+        return [(arr[i].name.decode(), float(arr[i].ms), int(arr[i].launches)) for i in range(min(n, 128))]
 
     def algorithmic_bytes(self, cs: GarChangeset) -> int:
         return int(self.lib.gar_algorithmic_bytes(self._h, C.byref(cs)))

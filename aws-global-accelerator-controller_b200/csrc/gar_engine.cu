@@ -230,6 +230,39 @@ struct gar_engine {
   float ms_h2d = 0;
   u32 launches = 0;
   u64 input_bytes = 0;  // slabs + fixed-width columns, each once
+  // stage timing (GAR_FLAG_STAGE_TIMING)
+  bool timing = false;
+  struct Mark {
+    const char *name;
+    cudaEvent_t a, b;
+    u32 launches;
+  };
+  std::vector<Mark> marks;
+  std::vector<cudaEvent_t> event_pool;
+  size_t events_used = 0;
+  int stage_depth = 0;
+  u32 stage_launch0 = 0;
+  std::vector<gar_stage_timing> last_timings;
+  cudaEvent_t new_event() {
+    if (events_used == event_pool.size()) {
+      cudaEvent_t ev;
+      CK(cudaEventCreate(&ev));
+      event_pool.push_back(ev);
+    }
+    return event_pool[events_used++];
+  }
+  void stage_begin(const char *name) {
+    if (!timing || stage_depth++ > 0) return;
+    Mark m{name, new_event(), new_event(), 0};
+    CK(cudaEventRecord(m.a, stream));
+    stage_launch0 = launches;
+    marks.push_back(m);
+  }
+  void stage_end() {
+    if (!timing || --stage_depth > 0) return;
+    marks.back().launches = launches - stage_launch0;
+    CK(cudaEventRecord(marks.back().b, stream));
+  }
 
   // ---- memory
   void *dev_ensure(DBuf &b, size_t bytes) {
@@ -259,10 +292,12 @@ struct gar_engine {
 
   // ---- Backend interface (gar_pipeline.h)
   template <class F>
-  void for_each(const char *, u32 n, const F &f) {
+  void for_each(const char *name, u32 n, const F &f) {
     if (!n) return;
+    stage_begin(name);
     k_for_each<F><<<(n + 255) / 256, 256, 0, stream>>>(f, n);
     launches++;
+    stage_end();
   }
   void fill32(u32 *p, u32 v, size_t n) {
     if (!n) return;
@@ -280,15 +315,18 @@ struct gar_engine {
   }
   void exclusive_scan(u32 *data, u32 n) {
     if (!n) return;
+    stage_begin("exclusive_scan");
     u32 ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     u32 *tiles = (u32 *)dev_ensure(d_scan_tiles, 4 * (size_t)(ntiles + 1));
     k_scan_reduce<<<ntiles, SCAN_THREADS, 0, stream>>>(data, tiles, n);
     k_scan_tiles<<<1, SCAN_THREADS, 0, stream>>>(tiles, ntiles);
     k_scan_apply<<<ntiles, SCAN_THREADS, 0, stream>>>(data, tiles, n);
     launches += 3;
+    stage_end();
   }
   void sort_pairs(u32 *keys, u32 *vals, u32 *keys_alt, u32 *vals_alt, u32 n, int bits) {
     if (!n) return;
+    stage_begin("radix_sort_pairs");
     u32 ntiles = (n + RS_TILE - 1) / RS_TILE;
     u32 *hist = (u32 *)dev_ensure(d_hist, 4 * (size_t)256 * ntiles + 16);
     u32 *ka = keys, *va = vals, *kb = keys_alt, *vb = vals_alt;
@@ -306,6 +344,7 @@ struct gar_engine {
       CK(cudaMemcpyAsync(keys, ka, 4 * (size_t)n, cudaMemcpyDeviceToDevice, stream));
       CK(cudaMemcpyAsync(vals, va, 4 * (size_t)n, cudaMemcpyDeviceToDevice, stream));
     }
+    stage_end();
   }
   void *ensure(int s, size_t bytes) { return dev_ensure(slot[s], bytes); }
   void download(void *dst, const void *src, size_t bytes) {
@@ -501,6 +540,9 @@ static void do_diff(gar_engine *e, gar_changeset *out, bool to_host) {
   CK(cudaSetDevice(e->device));
   memset(out, 0, sizeof(*out));
   e->launches = 0;
+  e->marks.clear();
+  e->events_used = 0;
+  e->stage_depth = 0;
   Pipeline<gar_engine> P(*e, e->T);
   DiffCounts dc{};
   CK(cudaEventRecord(e->ev[2], e->stream));
@@ -557,6 +599,19 @@ static void do_diff(gar_engine *e, gar_changeset *out, bool to_host) {
   CK(cudaEventElapsedTime(&out->ms_d2h, e->ev[3], e->ev[4]));
   out->ms_h2d = e->ms_h2d;
   out->kernel_launches = e->launches;
+  e->last_timings.clear();
+  for (auto &m : e->marks) {
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, m.a, m.b));
+    bool found = false;
+    for (auto &t : e->last_timings)
+      if (!strcmp(t.name, m.name)) {
+        t.ms += ms;
+        t.launches += m.launches;
+        found = true;
+      }
+    if (!found) e->last_timings.push_back(gar_stage_timing{m.name, ms, m.launches, 0});
+  }
 }
 
 // ------------------------------------------------------------------ C ABI
@@ -606,6 +661,7 @@ int gar_engine_create(const gar_config *cfg, gar_engine **out) {
   gar_engine *e = new gar_engine();
   e->device = cfg->device;
   e->cluster = cfg->cluster_name ? cfg->cluster_name : "";
+  e->timing = (cfg->flags & GAR_FLAG_STAGE_TIMING) != 0;
   try {
     CK(cudaSetDevice(e->device));
     CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
@@ -638,6 +694,7 @@ void gar_engine_destroy(gar_engine *e) {
   }
   for (auto &ev : e->ev)
     if (ev) cudaEventDestroy(ev);
+  for (auto &ev : e->event_pool) cudaEventDestroy(ev);
   if (e->stream) cudaStreamDestroy(e->stream);
   delete e;
 }
@@ -688,6 +745,14 @@ const char *gar_version(void) { return GAR_VERSION_STRING; }
 uint64_t gar_algorithmic_bytes(const gar_engine *e, const gar_changeset *cs) {
   if (!e || !cs) return 0;
   return e->input_bytes + 2ull * 4 * cs->n_objects + sizeof(gar_op) * cs->n_ops;
+}
+
+uint32_t gar_last_stage_timings(gar_engine *e, gar_stage_timing *out, uint32_t cap) {
+  if (!e) return 0;
+  std::lock_guard<std::mutex> lk(e->mu);
+  uint32_t n = (uint32_t)e->last_timings.size();
+  for (uint32_t i = 0; i < n && i < cap; i++) out[i] = e->last_timings[i];
+  return n;
 }
 
 }  // extern "C"

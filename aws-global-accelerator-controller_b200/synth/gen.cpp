@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/garecon.h"
@@ -340,9 +341,22 @@ Snapshot *generate(const gsyn_config &cfg) {
     S.ann_val.push_back(S.os.put(v));
   };
   gar_str tcp = 0, udp = 0;
+  // every object's spec, computed once (in parallel: it is a pure function of (seed, i))
+  std::vector<ObjSpec> specs(n);
+  {
+    unsigned nt = std::thread::hardware_concurrency();
+    if (nt < 1) nt = 1;
+    if (nt > 32) nt = 32;
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; t++)
+      th.emplace_back([&, t] {
+        for (uint64_t i = (uint64_t)n * t / nt; i < (uint64_t)n * (t + 1) / nt; i++) specs[i] = G.spec((uint32_t)i);
+      });
+    for (auto &x : th) x.join();
+  }
   // ---------------- objects (informer cache order)
   for (uint32_t i = 0; i < n; i++) {
-    ObjSpec s = G.spec(i);
+    const ObjSpec &s = specs[i];
     S.obj_kind.push_back(s.ingress ? GAR_KIND_INGRESS : GAR_KIND_SERVICE);
     S.obj_spec.push_back(s.ingress ? 0 : (s.eligible ? GAR_SVC_LOADBALANCER : GAR_SVC_CLUSTERIP));
     S.obj_flags.push_back(s.ingress ? GAR_OBJ_HAS_INGRESS_CLASS : 0);
@@ -394,7 +408,7 @@ Snapshot *generate(const gsyn_config &cfg) {
   {
     Perm pi(n, cfg.seed ^ 0x1B);
     for (uint32_t r = 0; r < n; r++) {
-      ObjSpec s = G.spec(pi(r));
+      const ObjSpec &s = specs[pi(r)];
       S.lb_region.push_back(S.as.put(s.region));
       S.lb_name.push_back(S.as.put(s.lb_name));
       S.lb_dns.push_back(S.as.put(s.hostname));
@@ -412,7 +426,7 @@ Snapshot *generate(const gsyn_config &cfg) {
     Perm pi(n, cfg.seed ^ 0xACC);
     for (uint32_t r = 0; r < n; r++) {
       uint32_t i = pi(r);
-      ObjSpec s = G.spec(i);
+      const ObjSpec &s = specs[i];
       Rng rr(mix(s.r, 31));
       bool has = s.eligible && s.sc != MISSING_ACC;
       if (!s.managed) has = rr.uni() < 0.5;  // unmanaged objects sometimes still own one: the cleanup path
@@ -480,7 +494,7 @@ Snapshot *generate(const gsyn_config &cfg) {
     Perm pi(n, cfg.seed ^ 0x53);
     for (uint32_t r = 0; r < n; r++) {
       uint32_t i = pi(r);
-      ObjSpec s = G.spec(i);
+      const ObjSpec &s = specs[i];
       if (!s.eligible && !s.ingress) continue;
       std::string ov = G.owner_value(s);
       std::string adns = G.acc_dns(i) + ".";

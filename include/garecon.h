@@ -161,8 +161,9 @@ typedef struct gar_config {
   uint32_t abi_version;      /* GAR_ABI_VERSION */
   int32_t device;            /* CUDA device ordinal */
   const char *cluster_name;  /* --cluster-name (cmd/controller/controller.go:33); NUL-terminated, copied */
-  uint32_t flags;            /* reserved, 0 */
+  uint32_t flags;            /* GAR_FLAG_* */
 } gar_config;
+#define GAR_FLAG_STAGE_TIMING 1u /* bracket every stage with CUDA events; read them with gar_last_stage_timings */
 
 /* ---------------------------------------------------------------- output: the change set */
 
@@ -339,6 +340,16 @@ const char *gar_version(void);
 /* Bytes the diff must touch at least once: input slabs + fixed-width columns (each once)
    + 4 B per (controller, object) status + 24 B per op.  The roofline numerator. */
 uint64_t gar_algorithmic_bytes(const gar_engine *e, const gar_changeset *cs);
+
+/* Per-stage device times of the last gar_diff / gar_diff_device (engine created with GAR_FLAG_STAGE_TIMING).
+   Stages launched several times (index builds) are summed under one name.  Returns the number of stages. */
+typedef struct gar_stage_timing {
+  const char *name; /* static string */
+  float ms;         /* CUDA-event time on the engine's stream */
+  uint32_t launches;
+  uint64_t bytes;   /* algorithmic bytes of the stage (DESIGN.md "Per-kernel byte model"), 0 if not modelled */
+} gar_stage_timing;
+uint32_t gar_last_stage_timings(gar_engine *e, gar_stage_timing *out, uint32_t cap);
 
 #ifdef __cplusplus
 }

@@ -134,4 +134,5 @@ void gar_changeset_free(gar_engine *, gar_changeset *cs) { memset(cs, 0, sizeof(
 const char *gar_last_error(const gar_engine *e) { return e ? e->err.c_str() : g_err.c_str(); }
 const char *gar_version(void) { return "garecon hostsim (test build)"; }
 uint64_t gar_algorithmic_bytes(const gar_engine *, const gar_changeset *) { return 0; }
+uint32_t gar_last_stage_timings(gar_engine *, gar_stage_timing *, uint32_t) { return 0; }
 }

@@ -1,0 +1,82 @@
+"""GPU tier at BASELINE sizes: bit-exact against the indexed oracle (itself proven equal to the faithful
+restatement at small sizes in test_synth_configs.py), plus size-independent properties of the change set."""
+import importlib
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def synth(garecon):
+    import __graft_entry__ as ge
+    ge.build_synth()
+    return importlib.import_module("aws-global-accelerator-controller_b200.synth")
+
+
+def _check_properties(cs, snap):
+    sb = cs.section_begin.astype(np.int64)
+    assert sb[0] == 0 and (np.diff(sb) >= 0).all() and sb[-1] == len(cs.ops)
+    ops = cs.ops
+    for s in (0, 2):  # object sections are ordered by object row
+        part = ops[sb[s]:sb[s + 1]]
+        assert (np.diff(part["obj"].astype(np.int64)) >= 0).all()
+    assert (ops[sb[1]:sb[2]]["obj"] == 0xFFFFFFFF).all() and (ops[sb[3]:sb[4]]["obj"] == 0xFFFFFFFF).all()
+    ga = ops[sb[1]:sb[2]]
+    assert (np.diff(ga["a0"].astype(np.int64)) > 0).all()  # GA orphans: strictly ascending accelerator rows
+    r53o = ops[sb[3]:sb[4]]
+    key = r53o["a0"].astype(np.int64) * 2 + r53o["sub"]
+    assert (np.diff(key) >= 0).all()  # R53 orphans: (zone, phase) ascending
+    codes = ops["head"] & 0xFF
+    assert ((codes >= 1) & (codes <= 10)).all()
+    ctrl = (ops["head"] >> 8) & 0xFF
+    assert (ctrl[:sb[2]] == 0).all() and (ctrl[sb[2]:] == 1).all()
+    # ignored objects never produce ops; every op's object is eligible
+    st_ga = cs.status_ga & 0xFF
+    objs = ops[sb[0]:sb[1]]["obj"]
+    assert (st_ga[objs] != 0).all()
+
+
+@pytest.mark.parametrize("cfg,n", [(2, 100_000), (3, 100_000), (5, 100_000)])
+def test_baseline_configs_1e5_bit_exact(garecon, oracle, engine, synth, cfg, n):
+    snap = synth.generate(cfg, n)
+    engine.load(snap)
+    got = engine.diff()
+    want = oracle.diff(snap, "default", mode=1, threads=os.cpu_count() or 4)
+    assert got.diff(want) == [], got.describe_first_mismatch(want)
+    _check_properties(got, snap)
+
+
+def test_config3_1e6_bit_exact_and_idempotent(garecon, oracle, engine, synth):
+    """BASELINE configs[2] at full size (the bench workload)."""
+    snap = synth.generate(3, 1_000_000)
+    engine.load(snap)
+    got = engine.diff()
+    again = engine.diff()
+    assert got.diff(again) == []  # a diff does not disturb the loaded snapshot
+    _check_properties(got, snap)
+    want = oracle.diff(snap, "default", mode=1, threads=os.cpu_count() or 4)
+    assert got.diff(want) == [], got.describe_first_mismatch(want)
+    assert got.checksum() == want.checksum()
+
+
+def test_adversarial_1e6_properties_and_sampled_parity(garecon, oracle, engine, synth):
+    """BASELINE configs[4]: 90% colliding hostnames + 64-port listeners at 10^6; full oracle comparison."""
+    snap = synth.generate(5, 1_000_000)
+    engine.load(snap)
+    got = engine.diff()
+    _check_properties(got, snap)
+    want = oracle.diff(snap, "default", mode=1, threads=os.cpu_count() or 4)
+    assert got.diff(want) == [], got.describe_first_mismatch(want)
+
+
+def test_device_resident_path_matches_host_path(garecon, engine, synth):
+    snap = synth.generate(2, 50_000)
+    engine.load(snap)
+    full = engine.diff()
+    cs = engine.diff_device()
+    assert int(cs.n_ops) == len(full.ops)
+    assert list(cs.section_begin) == list(full.section_begin)
+    assert cs.kernel_launches == full.kernel_launches
