@@ -75,15 +75,15 @@ class GarActual(C.Structure):
         ("n_lbs", C.c_uint32),
         ("lb_region", _u64p), ("lb_name", _u64p), ("lb_dns", _u64p), ("lb_arn", _u64p), ("lb_state", _u8p),
         ("n_accels", C.c_uint32),
-        ("acc_arn", _u64p), ("acc_name", _u64p), ("acc_dns", _u64p), ("acc_enabled", _u8p),
+        ("acc_name", _u64p), ("acc_dns", _u64p), ("acc_enabled", _u8p),
         ("acc_tag_begin", _u32p), ("acc_lis_begin", _u32p),
         ("n_tags", C.c_uint32), ("tag_key", _u64p), ("tag_val", _u64p),
-        ("n_listeners", C.c_uint32), ("lis_arn", _u64p), ("lis_proto", _u8p),
+        ("n_listeners", C.c_uint32), ("lis_proto", _u8p),
         ("lis_pr_begin", _u32p), ("lis_eg_begin", _u32p),
         ("n_port_ranges", C.c_uint32), ("pr_from", _i32p),
-        ("n_egs", C.c_uint32), ("eg_arn", _u64p), ("eg_ep_begin", _u32p),
+        ("n_egs", C.c_uint32), ("eg_ep_begin", _u32p),
         ("n_endpoints", C.c_uint32), ("ep_id", _u64p),
-        ("n_zones", C.c_uint32), ("zone_id", _u64p), ("zone_name", _u64p), ("zone_rec_begin", _u32p),
+        ("n_zones", C.c_uint32), ("zone_name", _u64p), ("zone_rec_begin", _u32p),
         ("n_records", C.c_uint32), ("rec_name", _u64p), ("rec_type", _u8p), ("rec_has_alias", _u8p),
         ("rec_alias_dns", _u64p), ("rec_val_begin", _u32p),
         ("n_values", C.c_uint32), ("val_value", _u64p),

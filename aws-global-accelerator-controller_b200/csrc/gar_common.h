@@ -18,6 +18,15 @@
 #define GAR_D inline
 #endif
 
+// Warp vote used to keep the outer loops of the decide kernels warp-uniform (and to force reconvergence at
+// every iteration).  Only valid in kernels where all 32 lanes of every warp stay alive (for_each_warp).
+#if defined(__CUDA_ARCH__)
+#define GAR_ANY(p) __any_sync(0xffffffffu, (p))
+#else
+bool gar_host_vote(bool p);  // tests/hostsim: 32 host threads emulate a warp; a vote that not all lanes reach is an error
+#define GAR_ANY(p) gar_host_vote((p))
+#endif
+
 typedef uint8_t u8;
 typedef uint32_t u32;
 typedef uint64_t u64;
@@ -88,6 +97,34 @@ GAR_HD bool has_suffix_lit(Str a, const char *lit, u32 n) {
 }
 #define HAS_SUFFIX_LIT(s, lit) has_suffix_lit((s), (lit), (u32)(sizeof(lit) - 1))
 
+// ------------------------------------------------------------------ SWAR byte search (8 bytes per step)
+
+GAR_HD u64 swar_eq_mask(u64 w, u8 c) {  // 0x80 in every byte of w that equals c (exact: no false positives below the first hit)
+  u64 x = w ^ (0x0101010101010101ull * c);
+  return (x - 0x0101010101010101ull) & ~x & 0x8080808080808080ull;
+}
+GAR_HD u32 ctz64(u64 x) {
+#if defined(__CUDA_ARCH__)
+  return (u32)(__ffsll((long long)x) - 1);
+#else
+  return (u32)__builtin_ctzll(x);
+#endif
+}
+// index of the first byte == c in s[from..), or s.n
+GAR_HD u32 find_byte(Str s, u32 from, u8 c) {
+  for (u32 i = from; i < s.n; i += 8) {
+    u64 m = swar_eq_mask(ld64u(s.p + i), c);
+    if (s.n - i < 8) m &= lowmask(s.n - i);
+    if (m) return i + (ctz64(m) >> 3);
+  }
+  return s.n;
+}
+GAR_HD u32 count_byte(Str s, u8 c) {  // byte-exact count (the SWAR mask can over-report bytes above the first hit, so count per byte)
+  u32 n = 0;
+  for (u32 i = find_byte(s, 0, c); i < s.n; i = find_byte(s, i + 1, c)) n++;
+  return n;
+}
+
 // ------------------------------------------------------------------ xxHash64 (XXH64, seed 0) over contiguous bytes
 
 #define XXP1 0x9E3779B185EBCA87ull
@@ -108,45 +145,57 @@ GAR_HD u64 xx_avalanche(u64 h) {
   return h;
 }
 
-GAR_HD u64 xxh64(Str s, u64 seed) {
-  const u8 *p = s.p;
-  u32 n = s.n, i = 0;
-  u64 h;
-  if (n >= 32) {
-    u64 v1 = seed + XXP1 + XXP2, v2 = seed + XXP2, v3 = seed, v4 = seed - XXP1;
-    for (; i + 32 <= n; i += 32) {
-      v1 = xx_round(v1, ld64u(p + i));
-      v2 = xx_round(v2, ld64u(p + i + 8));
-      v3 = xx_round(v3, ld64u(p + i + 16));
-      v4 = xx_round(v4, ld64u(p + i + 24));
-    }
-    h = rotl64(v1, 1) + rotl64(v2, 7) + rotl64(v3, 12) + rotl64(v4, 18);
-    h = xx_merge(h, v1);
-    h = xx_merge(h, v2);
-    h = xx_merge(h, v3);
-    h = xx_merge(h, v4);
-  } else {
-    h = seed + XXP5;
-  }
-  h += (u64)n;
-  for (; i + 8 <= n; i += 8) {
-    h ^= xx_round(0, ld64u(p + i));
-    h = rotl64(h, 27) * XXP1 + XXP4;
-  }
-  if (i + 4 <= n) {
-    h ^= (ld64u(p + i) & 0xFFFFFFFFull) * XXP1;
-    h = rotl64(h, 23) * XXP2 + XXP3;
-    i += 4;
-  }
-  if (i < n) {
-    u64 w = ld64u(p + i);
-    for (; i < n; i++) {
-      h ^= (w & 0xFF) * XXP5;
-      h = rotl64(h, 11) * XXP1;
-      w >>= 8;
-    }
+// Key hash: xxHash64's round/avalanche applied to one 8-byte word per step (tail masked), so that the scalar
+// form (index build, one thread per row) and the warp-uniform form (probes: all 32 lanes step together under a
+// vote, gar_rows.h) walk a key in exactly the same number of equal steps.  Both sides of every join use it.
+GAR_HD u64 hash_init(u32 n) { return XXP5 ^ ((u64)n * XXP3); }
+GAR_HD u64 hash_word(u64 h, u64 w) { return rotl64(h ^ (w * XXP2), 31) * XXP1 + XXP4; }
+GAR_HD u64 load_word(Str s, u32 i) {  // bytes [i, i+8) of s, zero beyond the end
+  u64 w = ld64u(s.p + i);
+  if (s.n - i < 8) w &= lowmask(s.n - i);
+  return w;
+}
+GAR_HD u64 gar_hash(Str s) {
+  u64 h = hash_init(s.n);
+  for (u32 i = 0; i < s.n; i += 8) h = hash_word(h, load_word(s, i));
+  return xx_avalanche(h);
+}
+
+// ---- warp-uniform string primitives: EVERY lane of the warp must call them (lanes without work pass act = false);
+// each loop iteration is one GAR_ANY vote, so the lanes' loads issue together.
+GAR_HD u64 u_hash(bool act, Str s) {
+  u64 h = hash_init(s.n);
+  for (u32 i = 0;; i += 8) {
+    bool step = act && i < s.n;
+    if (!GAR_ANY(step)) break;
+    if (step) h = hash_word(h, load_word(s, i));
   }
   return xx_avalanche(h);
+}
+GAR_HD bool u_streq(bool act, Str a, Str b) {
+  bool eq = act && a.n == b.n;
+  for (u32 i = 0;; i += 8) {
+    bool step = eq && i < a.n;
+    if (!GAR_ANY(step)) break;
+    if (step && load_word(a, i) != load_word(b, i)) eq = false;
+  }
+  return eq;
+}
+GAR_HD u32 u_find_byte(bool act, Str s, u32 from, u8 c) {
+  u32 found = s.n;
+  bool done = !act;
+  for (u32 i = from;; i += 8) {
+    bool step = !done && i < s.n;
+    if (!GAR_ANY(step)) break;
+    if (!step) continue;
+    u64 m = swar_eq_mask(ld64u(s.p + i), c);
+    if (s.n - i < 8) m &= lowmask(s.n - i);
+    if (m) {
+      found = i + (ctz64(m) >> 3);
+      done = true;
+    }
+  }
+  return found;
 }
 
 // combine a small integer (kind, zone row ...) or a second hash into a key hash
@@ -156,14 +205,20 @@ GAR_HD u64 hmix(u64 a, u64 b) { return xx_avalanche(a * XXP1 + rotl64(b, 29) * X
 //
 // An index is a CSR of buckets: bucket b owns entries [begin[b], begin[b+1]).  Entries of a bucket are
 // sorted by build-side row, so walking a bucket yields matching rows in table order — which the change
-// set's canonical order needs (duplicates are legal and ordered).  `tag` is the upper half of the 64-bit
-// key hash; a full key comparison by the caller always follows a tag hit.
+// set's canonical order needs (duplicates are legal and ordered).  An entry is one 32-byte sector: the tag
+// (upper half of the 64-bit key hash), the row, and a denormalised copy of what the probe needs next (string
+// refs, parent rows, small enums), so a probe touches the entry and then the key bytes — no column chasing.
+// A tag hit is always followed by a full key comparison by the caller: hash equality is never trusted.
+
+struct alignas(32) IdxEntry {
+  u32 tag, row, a0, a1;
+  u64 s0, s1;
+};
 
 struct HashIdx {
-  const u32 *begin;  // [nbuckets + 1]
-  const u32 *row;    // [n_entries]
-  const u32 *tag;    // [n_entries]
-  u32 mask;          // nbuckets - 1 (nbuckets is a power of two)
+  const u32 *begin;     // [nbuckets + 1]
+  const IdxEntry *ent;  // [n_entries]
+  u32 mask;             // nbuckets - 1 (nbuckets is a power of two)
 };
 
 struct Cursor {
@@ -173,6 +228,23 @@ struct Cursor {
 GAR_HD u32 hash_bucket(u64 h, u32 mask) { return (u32)h & mask; }
 GAR_HD u32 hash_tag(u64 h) { return (u32)(h >> 32); }
 
+GAR_HD IdxEntry load_entry(const IdxEntry *p) {
+#if defined(__CUDA_ARCH__)
+  const uint4 *q = reinterpret_cast<const uint4 *>(p);
+  uint4 lo = __ldg(q), hi = __ldg(q + 1);
+  IdxEntry e;
+  e.tag = lo.x;
+  e.row = lo.y;
+  e.a0 = lo.z;
+  e.a1 = lo.w;
+  e.s0 = (u64)hi.x | ((u64)hi.y << 32);
+  e.s1 = (u64)hi.z | ((u64)hi.w << 32);
+  return e;
+#else
+  return *p;
+#endif
+}
+
 GAR_HD Cursor idx_open(const HashIdx &ix, u64 h) {
   u32 b = hash_bucket(h, ix.mask);
   Cursor c;
@@ -181,11 +253,14 @@ GAR_HD Cursor idx_open(const HashIdx &ix, u64 h) {
   c.tag = hash_tag(h);
   return c;
 }
-// next candidate row whose tag matches, or GAR_NONE
-GAR_HD u32 idx_next(const HashIdx &ix, Cursor &c) {
+// next entry whose tag matches; false when the bucket is exhausted
+GAR_HD bool idx_next(const HashIdx &ix, Cursor &c, IdxEntry *out) {
   while (c.pos < c.end) {
-    u32 p = c.pos++;
-    if (ix.tag[p] == c.tag) return ix.row[p];
+    IdxEntry e = load_entry(ix.ent + c.pos++);
+    if (e.tag == c.tag) {
+      *out = e;
+      return true;
+    }
   }
-  return GAR_NONE;
+  return false;
 }

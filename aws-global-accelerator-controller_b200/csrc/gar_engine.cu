@@ -28,6 +28,13 @@ __global__ void __launch_bounds__(256) k_for_each(const __grid_constant__ F f, u
   if (i < n) f(i);
 }
 
+// Warp-synchronous variant: every lane of every warp calls f (padding lanes with valid = false), so f may vote.
+template <class F>
+__global__ void __launch_bounds__(256) k_for_each_warp(const __grid_constant__ F f, u32 n) {
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  f(i, i < n);
+}
+
 __global__ void k_fill32(u32 *p, u32 v, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -299,6 +306,14 @@ struct gar_engine {
     launches++;
     stage_end();
   }
+  template <class F>
+  void for_each_warp(const char *name, u32 n, const F &f) {
+    if (!n) return;
+    stage_begin(name);
+    k_for_each_warp<F><<<(n + 255) / 256, 256, 0, stream>>>(f, n);
+    launches++;
+    stage_end();
+  }
   void fill32(u32 *p, u32 v, size_t n) {
     if (!n) return;
     if (v == 0) {
@@ -411,7 +426,6 @@ static void validate(const gar_objects *o, const gar_actual *a) {
   check_str_col("lb_dns", a->lb_dns, a->n_lbs, a->slab_len);
   check_str_col("lb_arn", a->lb_arn, a->n_lbs, a->slab_len);
   check_ptr("lb_state", a->lb_state, a->n_lbs);
-  check_str_col("acc_arn", a->acc_arn, a->n_accels, a->slab_len);
   check_str_col("acc_name", a->acc_name, a->n_accels, a->slab_len);
   check_str_col("acc_dns", a->acc_dns, a->n_accels, a->slab_len);
   check_ptr("acc_enabled", a->acc_enabled, a->n_accels);
@@ -419,15 +433,12 @@ static void validate(const gar_objects *o, const gar_actual *a) {
   check_csr("acc_lis_begin", a->acc_lis_begin, a->n_accels, a->n_listeners);
   check_str_col("tag_key", a->tag_key, a->n_tags, a->slab_len);
   check_str_col("tag_val", a->tag_val, a->n_tags, a->slab_len);
-  check_str_col("lis_arn", a->lis_arn, a->n_listeners, a->slab_len);
   check_ptr("lis_proto", a->lis_proto, a->n_listeners);
   check_csr("lis_pr_begin", a->lis_pr_begin, a->n_listeners, a->n_port_ranges);
   check_csr("lis_eg_begin", a->lis_eg_begin, a->n_listeners, a->n_egs);
   check_ptr("pr_from", a->pr_from, a->n_port_ranges);
-  check_str_col("eg_arn", a->eg_arn, a->n_egs, a->slab_len);
   check_csr("eg_ep_begin", a->eg_ep_begin, a->n_egs, a->n_endpoints);
   check_str_col("ep_id", a->ep_id, a->n_endpoints, a->slab_len);
-  check_str_col("zone_id", a->zone_id, a->n_zones, a->slab_len);
   check_str_col("zone_name", a->zone_name, a->n_zones, a->slab_len);
   check_csr("zone_rec_begin", a->zone_rec_begin, a->n_zones, a->n_records);
   check_str_col("rec_name", a->rec_name, a->n_records, a->slab_len);
@@ -445,13 +456,13 @@ static u64 table_bytes(const gar_objects *o, const gar_actual *a) {
   b += n * (3 + 8 * 3) + 4 * (n + 1) * 3;
   b += (u64)o->n_ann * 16 + (u64)o->n_lbi * 8 + (u64)o->n_ports * 12;
   b += (u64)a->n_lbs * (8 * 4 + 1);
-  b += (u64)a->n_accels * (8 * 3 + 1) + 4 * ((u64)a->n_accels + 1) * 2;
+  b += (u64)a->n_accels * (8 * 2 + 1) + 4 * ((u64)a->n_accels + 1) * 2;
   b += (u64)a->n_tags * 16;
-  b += (u64)a->n_listeners * (8 + 1) + 4 * ((u64)a->n_listeners + 1) * 2;
+  b += (u64)a->n_listeners * 1 + 4 * ((u64)a->n_listeners + 1) * 2;
   b += (u64)a->n_port_ranges * 4;
-  b += (u64)a->n_egs * 8 + 4 * ((u64)a->n_egs + 1);
+  b += 4 * ((u64)a->n_egs + 1);
   b += (u64)a->n_endpoints * 8;
-  b += (u64)a->n_zones * 16 + 4 * ((u64)a->n_zones + 1);
+  b += (u64)a->n_zones * 8 + 4 * ((u64)a->n_zones + 1);
   b += (u64)a->n_records * (8 + 1 + 1 + 8) + 4 * ((u64)a->n_records + 1);
   b += (u64)a->n_values * 8;
   return b;
@@ -471,7 +482,8 @@ static const Tp *upload(gar_engine *e, const Tp *host, size_t count, size_t pad_
 }
 
 static void do_load(gar_engine *e, const gar_objects *o, const gar_actual *a) {
-  validate(o, a);
+  if (!o || !a) throw InvalidError{"NULL table struct"};
+  e->loaded = false;
   CK(cudaSetDevice(e->device));
   e->in_used = 0;
   DevTables &T = e->T;
@@ -499,7 +511,6 @@ static void do_load(gar_engine *e, const gar_objects *o, const gar_actual *a) {
   T.a.lb_dns = upload(e, a->lb_dns, a->n_lbs);
   T.a.lb_arn = upload(e, a->lb_arn, a->n_lbs);
   T.a.lb_state = upload(e, a->lb_state, a->n_lbs);
-  T.a.acc_arn = upload(e, a->acc_arn, a->n_accels);
   T.a.acc_name = upload(e, a->acc_name, a->n_accels);
   T.a.acc_dns = upload(e, a->acc_dns, a->n_accels);
   T.a.acc_enabled = upload(e, a->acc_enabled, a->n_accels);
@@ -507,15 +518,12 @@ static void do_load(gar_engine *e, const gar_objects *o, const gar_actual *a) {
   T.a.acc_lis_begin = upload(e, a->acc_lis_begin, (size_t)a->n_accels + 1);
   T.a.tag_key = upload(e, a->tag_key, a->n_tags);
   T.a.tag_val = upload(e, a->tag_val, a->n_tags);
-  T.a.lis_arn = upload(e, a->lis_arn, a->n_listeners);
   T.a.lis_proto = upload(e, a->lis_proto, a->n_listeners);
   T.a.lis_pr_begin = upload(e, a->lis_pr_begin, (size_t)a->n_listeners + 1);
   T.a.lis_eg_begin = upload(e, a->lis_eg_begin, (size_t)a->n_listeners + 1);
   T.a.pr_from = upload(e, a->pr_from, a->n_port_ranges);
-  T.a.eg_arn = upload(e, a->eg_arn, a->n_egs);
   T.a.eg_ep_begin = upload(e, a->eg_ep_begin, (size_t)a->n_egs + 1);
   T.a.ep_id = upload(e, a->ep_id, a->n_endpoints);
-  T.a.zone_id = upload(e, a->zone_id, a->n_zones);
   T.a.zone_name = upload(e, a->zone_name, a->n_zones);
   T.a.zone_rec_begin = upload(e, a->zone_rec_begin, (size_t)a->n_zones + 1);
   T.a.rec_name = upload(e, a->rec_name, a->n_records);
@@ -526,6 +534,14 @@ static void do_load(gar_engine *e, const gar_objects *o, const gar_actual *a) {
   T.a.val_value = upload(e, a->val_value, a->n_values);
   T.a.slab = upload(e, a->slab, a->slab_len, GAR_SLAB_PAD);
   CK(cudaEventRecord(e->ev[1], e->stream));
+  // Host-side validation of every reference and CSR runs while the copies are in flight (they are asynchronous
+  // when the caller's buffers are pinned); a malformed snapshot is rejected before any kernel can see it.
+  try {
+    validate(o, a);
+  } catch (...) {
+    cudaStreamSynchronize(e->stream);
+    throw;
+  }
   CK(cudaStreamSynchronize(e->stream));  // caller may free its buffers when we return
   CK(cudaEventElapsedTime(&e->ms_h2d, e->ev[0], e->ev[1]));
   e->input_bytes = table_bytes(o, a);

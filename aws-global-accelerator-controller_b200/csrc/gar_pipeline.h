@@ -6,6 +6,8 @@
 //
 // Backend interface:
 //   template <class F> void for_each(const char *name, u32 n, const F &f);  // f(i) for i in [0, n)
+//   template <class F> void for_each_warp(const char *name, u32 n, const F &f);  // f(i, i < n) for i in [0, roundup(n, 32)):
+//                                                                                // full warps, f may use GAR_ANY votes
 //   void exclusive_scan(u32 *data, u32 n);                                  // in place
 //   void sort_pairs(u32 *keys, u32 *vals, u32 *keys_alt, u32 *vals_alt, u32 n, int bits);  // stable, result in keys/vals
 //   void fill32(u32 *p, u32 value, size_t n);
@@ -24,7 +26,7 @@
 // ------------------------------------------------------------------ scratch slots
 
 enum Slot {
-  S_DERIVED, S_OFLAGS, S_ANN_R53, S_ANN_NAME, S_ANN_TAGS, S_ANN_LISTEN, S_DPORT_BEGIN, S_DPORTS,
+  S_DERIVED, S_OFLAGS, S_OKEY_HASH, S_STAGE_GA, S_STAGE_R53, S_ANN_R53, S_ANN_NAME, S_ANN_TAGS, S_ANN_LISTEN, S_DPORT_BEGIN, S_DPORTS,
   S_TOK_CODE, S_TOK_NAME, S_TOK_REGION,
   S_ACC_FLAGS, S_ACC_OWNER_KEY, S_ACC_OWNER, S_ACC_THOST, S_ACC_MANAGED,
   S_REC_ZONE, S_VAL_REC, S_VAL_CLS, S_VAL_KEY, S_VAL_ORPHAN,
@@ -173,7 +175,7 @@ struct FKeyObj {
   IdxOut o;
   GAR_HD void operator()(u32 i) const {
     bool valid = !(W.derived[i] & OBJ_KEY_BAD);
-    o.put(i, valid, valid ? key_hash_kinded(T.o.obj_kind[i], object_key(T, i)) : 0);
+    o.put(i, valid, W.okey_hash[i]);
   }
 };
 struct FKeyOvn {
@@ -189,12 +191,123 @@ struct FKeyOvn {
 struct FHistogram {
   const u32 *keys;
   u32 *counts;
-  GAR_HD void operator()(u32 i) const { GAR_ATOMIC_ADD(&counts[keys[i]], 1u); }
+  u32 nb;  // rows that are not indexed carry the sentinel key nb: not counted (they would all hit one counter)
+  GAR_HD void operator()(u32 i) const {
+    u32 k = keys[i];
+    if (k != nb) GAR_ATOMIC_ADD(&counts[k], 1u);
+  }
 };
-struct FGatherTags {
-  const u32 *vals, *tags_in;
-  u32 *tags_out;
-  GAR_HD void operator()(u32 p) const { tags_out[p] = tags_in[vals[p]]; }
+// --- entry fill: position p of the sorted order -> 32-byte entry (payload conventions: gar_rows.h "index probes")
+struct EntOut {
+  const u32 *vals, *tags;
+  IdxEntry *ent;
+  const u32 *nvalid;  // device: number of indexed rows (sorted positions beyond it hold rows that are not indexed)
+  GAR_HD bool live(u32 p) const { return p < *nvalid; }
+  GAR_HD void put(u32 p, u32 row, u32 a0, u32 a1, u64 s0, u64 s1) const {
+    IdxEntry e;
+    e.tag = tags[row];
+    e.row = row;
+    e.a0 = a0;
+    e.a1 = a1;
+    e.s0 = s0;
+    e.s1 = s1;
+    ent[p] = e;
+  }
+};
+struct FEntLb {
+  DevTables T;
+  EntOut o;
+  GAR_HD void operator()(u32 p) const {
+    if (!o.live(p)) return;
+    u32 r = o.vals[p];
+    o.put(p, r, T.a.lb_state[r], 0, T.a.lb_name[r], T.a.lb_region[r]);
+  }
+};
+struct FEntOwner {
+  DevTables T;
+  Work W;
+  EntOut o;
+  GAR_HD void operator()(u32 p) const {
+    if (!o.live(p)) return;
+    u32 r = o.vals[p];
+    o.put(p, r, W.acc_flags[r], 0, W.acc_owner_key[r], 0);
+  }
+};
+struct FEntThost {
+  DevTables T;
+  Work W;
+  EntOut o;
+  GAR_HD void operator()(u32 p) const {
+    if (!o.live(p)) return;
+    u32 r = o.vals[p];
+    o.put(p, r, 0, 0, W.acc_thost[r], T.a.acc_dns[r]);
+  }
+};
+struct FEntZone {
+  DevTables T;
+  EntOut o;
+  GAR_HD void operator()(u32 p) const {
+    if (!o.live(p)) return;
+    u32 r = o.vals[p];
+    o.put(p, r, 0, 0, T.a.zone_name[r], 0);
+  }
+};
+struct FEntVal {
+  DevTables T;
+  Work W;
+  EntOut o;
+  GAR_HD void operator()(u32 p) const {
+    if (!o.live(p)) return;
+    u32 v = o.vals[p];
+    u32 rec = W.val_rec[v];
+    u32 kind = (W.val_cls[v] & VAL_OWNER_INGRESS) ? 1u : 0u;
+    o.put(p, v, rec, W.rec_zone[rec] | (kind << 31), W.val_key[v], T.a.rec_name[rec]);
+  }
+};
+struct FEntAlias {
+  DevTables T;
+  Work W;
+  EntOut o;
+  GAR_HD void operator()(u32 p) const {
+    if (!o.live(p)) return;
+    u32 r = o.vals[p];
+    o.put(p, r, W.rec_zone[r], T.a.rec_type[r], T.a.rec_name[r], T.a.rec_alias_dns[r]);
+  }
+};
+struct FEntObj {
+  DevTables T;
+  EntOut o;
+  GAR_HD void operator()(u32 p) const {
+    if (!o.live(p)) return;
+    u32 i = o.vals[p];
+    gar_str ns = T.o.obj_ns[i];
+    o.put(p, i, T.o.obj_kind[i], 0, GAR_STR(GAR_STR_OFF(ns), GAR_STR_LEN(ns) + 1 + GAR_STR_LEN(T.o.obj_name[i])), 0);
+  }
+};
+struct FEntOvn {
+  DevTables T;
+  Work W;
+  EntOut o;
+  GAR_HD void operator()(u32 p) const {
+    if (!o.live(p)) return;
+    u32 v = o.vals[p];
+    u32 rec = W.val_rec[v];
+    o.put(p, v, rec, W.rec_zone[rec], T.a.rec_name[rec], T.a.val_value[v]);
+  }
+};
+struct FGather5 {
+  const u32 *src;
+  u32 idx[5];
+  u32 *dst;
+  GAR_HD void operator()(u32 k) const { dst[k] = src[idx[k]]; }
+};
+struct FGatherHeader {
+  const u32 *ndports, *errflag;
+  u32 *dst;
+  GAR_HD void operator()(u32) const {
+    dst[0] = *ndports;
+    dst[1] = *errflag;
+  }
 };
 struct FMarkOrphanValue {
   DevTables T;
@@ -212,18 +325,65 @@ struct CountLayout {
   GAR_HD u32 base1() const { return 2 * n + nacc + nrec; }
   GAR_HD u32 total() const { return 2 * n + nacc + nrec + nval; }
 };
+// Object sections: every object is evaluated ONCE.  The evaluation writes the status word, the op count and
+// up to OPS_STAGE_CAP ops into the object's staging slot; after the scan FCompactOps moves staged ops to their
+// final position (objects with more ops than the slot holds are re-evaluated straight into the output).
+constexpr u32 OPS_STAGE_CAP = 4;
 struct FGaObj {
   DevTables T;
   Work W;
   CountLayout L;
-  u32 *counts;     // count pass: written; emit pass: scanned offsets
-  gar_op *ops;     // nullptr in the count pass
+  u32 *counts;
+  gar_op *stage;  // [n * OPS_STAGE_CAP]
   u32 *status;
-  GAR_HD void operator()(u32 i) const {
-    OpSink s{ops ? ops + counts[L.ga_obj(i)] : nullptr, 0};
-    u32 st = ga_reconcile(T, W, i, s);
-    if (ops) status[i] = st;
-    else counts[L.ga_obj(i)] = s.n;
+  GAR_HD void operator()(u32 i, bool valid) const {
+    OpSink s{stage + (size_t)i * OPS_STAGE_CAP, 0, OPS_STAGE_CAP};
+    u32 st = ga_reconcile(T, W, i, valid, s);
+    if (valid) {
+      status[i] = st;
+      counts[L.ga_obj(i)] = s.n;
+    }
+  }
+};
+struct FR53Obj {
+  DevTables T;
+  Work W;
+  CountLayout L;
+  u32 *counts;
+  gar_op *stage;
+  u32 *status;
+  GAR_HD void operator()(u32 i, bool valid) const {
+    OpSink s{stage + (size_t)i * OPS_STAGE_CAP, 0, OPS_STAGE_CAP};
+    u32 st = r53_reconcile(T, W, i, valid, s);
+    if (valid) {
+      status[i] = st;
+      counts[L.r53_obj(i)] = s.n;
+    }
+  }
+};
+struct FCompactOps {
+  DevTables T;
+  Work W;
+  const u32 *scanned;  // exclusive-scanned counts of this section (entry i+1 exists: the layout is contiguous)
+  const gar_op *stage;
+  gar_op *ops;
+  u32 ctrl;
+  GAR_HD void operator()(u32 i, bool valid) const {
+    u32 off = 0, c = 0;
+    if (valid) {
+      off = scanned[i];
+      c = scanned[i + 1] - off;
+      if (c <= OPS_STAGE_CAP)
+        for (u32 k = 0; k < c; k++) ops[off + k] = stage[(size_t)i * OPS_STAGE_CAP + k];
+    }
+    // objects with more ops than a staging slot holds are re-evaluated straight into the output (warp-uniform:
+    // the decide functions vote, so the whole warp enters when any lane needs it)
+    bool redo = valid && c > OPS_STAGE_CAP;
+    if (GAR_ANY(redo)) {
+      OpSink s{ops + off, 0, redo ? 0xFFFFFFFFu : 0u};
+      if (ctrl == GAR_CTRL_GA) ga_reconcile(T, W, i, redo, s);
+      else r53_reconcile(T, W, i, redo, s);
+    }
   }
 };
 struct FGaOrphan {
@@ -233,23 +393,10 @@ struct FGaOrphan {
   u32 *counts;
   gar_op *ops;
   GAR_HD void operator()(u32 a) const {
-    OpSink s{ops ? ops + counts[L.ga_orph(a)] : nullptr, 0};
+    if (ops && counts[L.ga_orph(a) + 1] == counts[L.ga_orph(a)]) return;  // emit pass: nothing to write
+    OpSink s{ops ? ops + counts[L.ga_orph(a)] : nullptr, 0, 0xFFFFFFFFu};
     ga_orphan(T, W, a, s);
     if (!ops) counts[L.ga_orph(a)] = s.n;
-  }
-};
-struct FR53Obj {
-  DevTables T;
-  Work W;
-  CountLayout L;
-  u32 *counts;
-  gar_op *ops;
-  u32 *status;
-  GAR_HD void operator()(u32 i) const {
-    OpSink s{ops ? ops + counts[L.r53_obj(i)] : nullptr, 0};
-    u32 st = r53_reconcile(T, W, i, s);
-    if (ops) status[i] = st;
-    else counts[L.r53_obj(i)] = s.n;
   }
 };
 // orphan section order: per zone, alias phase (by record row) then metadata phase (by value row)
@@ -261,15 +408,16 @@ struct FR53OrphanAlias {
   gar_op *ops;
   GAR_HD void operator()(u32 r) const {
     if (!ops) {
-      OpSink s{nullptr, 0};
+      OpSink s{nullptr, 0, 0};
       r53_orphan_alias(T, W, r, s);
       counts[L.base0() + r] = s.n;
       return;
     }
+    if (counts[L.base0() + r + 1] == counts[L.base0() + r]) return;
     u32 z = W.rec_zone[r];
     u32 zv = T.a.rec_val_begin[T.a.zone_rec_begin[z]];  // first value row of the zone
     u32 off = counts[L.base0()] + (counts[L.base1() + zv] - counts[L.base1()]) + (counts[L.base0() + r] - counts[L.base0()]);
-    OpSink s{ops + off, 0};
+    OpSink s{ops + off, 0, 0xFFFFFFFFu};
     r53_orphan_alias(T, W, r, s);
   }
 };
@@ -327,8 +475,8 @@ struct Pipeline {
   Work W{};
   explicit Pipeline(B &b, const DevTables &t) : be(b), T(t) {}
 
-  template <class KeyF>
-  HashIdx build_index(int slot, u32 nrows, KeyF keyf) {
+  template <class KeyF, class EntF>
+  HashIdx build_index(int slot, u32 nrows, KeyF keyf, EntF entf) {
     u32 nb = next_pow2(nrows < 16 ? 16 : nrows);
     u32 *keys = (u32 *)be.ensure(S_SORT_KEYS, sizeof(u32) * (size_t)(nrows + 1));
     u32 *vals = (u32 *)be.ensure(S_SORT_VALS, sizeof(u32) * (size_t)(nrows + 1));
@@ -336,21 +484,20 @@ struct Pipeline {
     u32 *vals2 = (u32 *)be.ensure(S_SORT_VALS_ALT, sizeof(u32) * (size_t)(nrows + 1));
     u32 *tags = (u32 *)be.ensure(S_SORT_TAGS, sizeof(u32) * (size_t)(nrows + 1));
     u32 *begin = (u32 *)be.ensure(slot + 0, sizeof(u32) * (size_t)(nb + 2));
-    u32 *row = (u32 *)be.ensure(slot + 1, sizeof(u32) * (size_t)(nrows + 1));
-    u32 *tag = (u32 *)be.ensure(slot + 2, sizeof(u32) * (size_t)(nrows + 1));
+    IdxEntry *ent = (IdxEntry *)be.ensure(slot + 1, sizeof(IdxEntry) * (size_t)(nrows + 1));
     keyf.o = IdxOut{keys, vals, tags, nb - 1, nb};
     be.fill32(begin, 0, nb + 2);
     if (nrows) {
       be.for_each("idx_keys", nrows, keyf);
-      be.for_each("idx_histogram", nrows, FHistogram{keys, begin});
+      be.for_each("idx_histogram", nrows, FHistogram{keys, begin, nb});
     }
     be.exclusive_scan(begin, nb + 2);  // begin[b] = #rows with key < b; begin[nb] = #indexed rows
     if (nrows) {
       be.sort_pairs(keys, vals, keys2, vals2, nrows, ilog2(nb) + 1);
-      be.for_each("idx_gather", nrows, FGatherTags{vals, tags, tag});
-      be.copy32(row, vals, nrows);
+      entf.o = EntOut{vals, tags, ent, begin + nb};
+      be.for_each("idx_entries", nrows, entf);
     }
-    return HashIdx{begin, row, tag, nb - 1};
+    return HashIdx{begin, ent, nb - 1};
   }
 
   // Runs every stage.  `ops_out` is called once the op count is known and must return the device buffer the
@@ -361,6 +508,7 @@ struct Pipeline {
     W.derived = (u32 *)be.ensure(S_DERIVED, 4 * (size_t)(n + 1));
     u32 *derived_public = (u32 *)be.out_derived(n);
     u8 *oflags = (u8 *)be.ensure(S_OFLAGS, n + 1);
+    W.okey_hash = (u64 *)be.ensure(S_OKEY_HASH, 8 * (size_t)(n + 1));
     W.ann_r53 = (gar_str *)be.ensure(S_ANN_R53, 8 * (size_t)(n + 1));
     W.ann_name = (gar_str *)be.ensure(S_ANN_NAME, 8 * (size_t)(n + 1));
     W.ann_tags = (gar_str *)be.ensure(S_ANN_TAGS, 8 * (size_t)(n + 1));
@@ -379,7 +527,7 @@ struct Pipeline {
     W.val_cls = (u8 *)be.ensure(S_VAL_CLS, nval + 1);
     W.val_key = (gar_str *)be.ensure(S_VAL_KEY, 8 * (size_t)(nval + 1));
     W.val_orphan = (u8 *)be.ensure(S_VAL_ORPHAN, nval + 1);
-    u32 *errflag = (u32 *)be.ensure(S_ERRFLAG, 16);
+    u32 *errflag = (u32 *)be.ensure(S_ERRFLAG, 64);
     be.fill32(errflag, 0, 4);
 
     // stage 1: row-local preprocessing
@@ -395,8 +543,8 @@ struct Pipeline {
     if (n) be.for_each("listen_ports_count", n, FJsonCount{T, W});
     be.exclusive_scan(W.dport_begin, n + 1);
     u32 hdr[2] = {0, 0};
-    be.download(&hdr[0], W.dport_begin + n, 4);
-    be.download(&hdr[1], errflag, 4);
+    be.for_each("gather_header", 1, FGatherHeader{W.dport_begin + n, errflag, errflag + 4});
+    be.download(hdr, errflag + 4, sizeof(hdr));
     dc->n_dports = hdr[0];
     dc->bad_keys = hdr[1];
     if (hdr[1]) return GAR_E_INVALID;
@@ -404,42 +552,42 @@ struct Pipeline {
     if (n && hdr[0]) be.for_each("listen_ports_write", n, FJsonWrite{T, W});
 
     // stage 3: hash indexes
-    W.ix_lb = build_index(S_IX_LB, T.a.n_lbs, FKeyLb{T, {}});
-    W.ix_owner = build_index(S_IX_OWNER, nacc, FKeyOwner{T, W, {}});
-    W.ix_thost = build_index(S_IX_THOST, nacc, FKeyThost{T, W, {}});
-    W.ix_zone = build_index(S_IX_ZONE, nzone, FKeyZone{T, {}});
-    W.ix_val = build_index(S_IX_VAL, nval, FKeyVal{T, W, {}});
-    W.ix_alias = build_index(S_IX_ALIAS, nrec, FKeyAlias{T, W, {}});
-    W.ix_obj = build_index(S_IX_OBJ, n, FKeyObj{T, W, {}});
+    W.ix_lb = build_index(S_IX_LB, T.a.n_lbs, FKeyLb{T, {}}, FEntLb{T, {}});
+    W.ix_owner = build_index(S_IX_OWNER, nacc, FKeyOwner{T, W, {}}, FEntOwner{T, W, {}});
+    W.ix_thost = build_index(S_IX_THOST, nacc, FKeyThost{T, W, {}}, FEntThost{T, W, {}});
+    W.ix_zone = build_index(S_IX_ZONE, nzone, FKeyZone{T, {}}, FEntZone{T, {}});
+    W.ix_val = build_index(S_IX_VAL, nval, FKeyVal{T, W, {}}, FEntVal{T, W, {}});
+    W.ix_alias = build_index(S_IX_ALIAS, nrec, FKeyAlias{T, W, {}}, FEntAlias{T, W, {}});
+    W.ix_obj = build_index(S_IX_OBJ, n, FKeyObj{T, W, {}}, FEntObj{T, {}});
     if (nval) be.for_each("mark_orphan_values", nval, FMarkOrphanValue{T, W});
-    W.ix_ovn = build_index(S_IX_OVN, nval, FKeyOvn{T, W, {}});
+    W.ix_ovn = build_index(S_IX_OVN, nval, FKeyOvn{T, W, {}}, FEntOvn{T, W, {}});
 
-    // stage 4: count ops
+    // stage 4: evaluate every object once (status + count + staged ops); count the orphan sections
     CountLayout L{n, nacc, nrec, nval};
     u32 *counts = (u32 *)be.ensure(S_COUNTS, 4 * (size_t)(L.total() + 2));
     be.fill32(counts, 0, (size_t)L.total() + 1);
-    if (n) be.for_each("ga_objects_count", n, FGaObj{T, W, L, counts, nullptr, nullptr});
+    gar_op *stage_ga = (gar_op *)be.ensure(S_STAGE_GA, sizeof(gar_op) * ((size_t)n * OPS_STAGE_CAP + 1));
+    gar_op *stage_r53 = (gar_op *)be.ensure(S_STAGE_R53, sizeof(gar_op) * ((size_t)n * OPS_STAGE_CAP + 1));
+    u32 *st_ga = (u32 *)be.out_status_ga(n);
+    u32 *st_r53 = (u32 *)be.out_status_r53(n);
+    if (n) be.for_each_warp("ga_objects", n, FGaObj{T, W, L, counts, stage_ga, st_ga});
     if (nacc) be.for_each("ga_orphans_count", nacc, FGaOrphan{T, W, L, counts, nullptr});
-    if (n) be.for_each("r53_objects_count", n, FR53Obj{T, W, L, counts, nullptr, nullptr});
+    if (n) be.for_each_warp("r53_objects", n, FR53Obj{T, W, L, counts, stage_r53, st_r53});
     if (nrec) be.for_each("r53_orphan_alias_count", nrec, FR53OrphanAlias{T, W, L, counts, nullptr});
     if (nval) be.for_each("r53_orphan_value_count", nval, FR53OrphanValue{T, W, L, counts, nullptr});
     be.exclusive_scan(counts, L.total() + 1);
     u32 sec[5];
-    be.download(&sec[0], counts + 0, 4);
-    be.download(&sec[1], counts + L.ga_orph(0), 4);
-    be.download(&sec[2], counts + L.r53_obj(0), 4);
-    be.download(&sec[3], counts + L.base0(), 4);
-    be.download(&sec[4], counts + L.total(), 4);
+    u32 *secdev = errflag + 8;  // same small scratch buffer
+    be.for_each("gather_section_begins", 5, FGather5{counts, {0, L.ga_orph(0), L.r53_obj(0), L.base0(), L.total()}, secdev});
+    be.download(sec, secdev, sizeof(sec));
     for (int k = 0; k < 5; k++) dc->section_begin[k] = sec[k];
     dc->n_ops = sec[4];
 
-    // stage 5: emit
+    // stage 5: move ops to their final, canonical positions
     gar_op *ops = (gar_op *)ops_alloc(dc->n_ops);
-    u32 *st_ga = (u32 *)be.out_status_ga(n);
-    u32 *st_r53 = (u32 *)be.out_status_r53(n);
-    if (n) be.for_each("ga_objects_emit", n, FGaObj{T, W, L, counts, ops, st_ga});
+    if (n) be.for_each_warp("ga_objects_compact", n, FCompactOps{T, W, counts + L.ga_obj(0), stage_ga, ops, GAR_CTRL_GA});
     if (nacc) be.for_each("ga_orphans_emit", nacc, FGaOrphan{T, W, L, counts, ops});
-    if (n) be.for_each("r53_objects_emit", n, FR53Obj{T, W, L, counts, ops, st_r53});
+    if (n) be.for_each_warp("r53_objects_compact", n, FCompactOps{T, W, counts + L.r53_obj(0), stage_r53, ops, GAR_CTRL_R53});
     if (nrec) be.for_each("r53_orphan_alias_emit", nrec, FR53OrphanAlias{T, W, L, counts, ops});
     if (nval) be.for_each("r53_orphan_value_emit", nval, FR53OrphanValue{T, W, L, counts, ops});
     return GAR_OK;

@@ -39,6 +39,7 @@ enum { VAL_NOT_OWNER = 0, VAL_OWNER_SERVICE = 1, VAL_OWNER_INGRESS = 2, VAL_OWNE
 struct Work {
   // objects
   u32 *derived;        // [n] GAR_DV_* | OBJ_*
+  u64 *okey_hash;      // [n] key_hash_kinded(kind, "ns/name"): probes ix_owner / ix_val, builds ix_obj
   gar_str *ann_r53;    // [n] value of the route53-hostname annotation
   gar_str *ann_name;   // [n] value of global-accelerator-name
   gar_str *ann_tags;   // [n] value of global-accelerator-tags
@@ -73,10 +74,10 @@ struct Work {
 
 // ------------------------------------------------------------------ key hashes (build and probe sides must agree)
 
-GAR_HD u64 key_hash_kinded(u32 kind, Str nsname) { return hmix(kind + 1, xxh64(nsname, 0)); }
-GAR_HD u64 key_hash_lb(Str region, Str name) { return hmix(xxh64(region, 0), xxh64(name, 0)); }
-GAR_HD u64 key_hash_zoned(u32 zone, Str name) { return hmix((u64)zone + 0x100, xxh64(name, 0)); }
-GAR_HD u64 key_hash_str(Str s) { return xxh64(s, 0); }
+GAR_HD u64 key_hash_kinded(u32 kind, Str nsname) { return hmix(kind + 1, gar_hash(nsname)); }
+GAR_HD u64 key_hash_lb(Str region, Str name) { return hmix(gar_hash(region), gar_hash(name)); }
+GAR_HD u64 key_hash_zoned(u32 zone, Str name) { return hmix((u64)zone + 0x100, gar_hash(name)); }
+GAR_HD u64 key_hash_str(Str s) { return gar_hash(s); }
 
 // the workqueue key "ns/name" of an object row (cache.MetaNamespaceKeyFunc; reconcile.go:47).  Layout rule of
 // gar_objects: name starts one byte after ns ends and that byte is '/'.
@@ -161,6 +162,7 @@ GAR_HD void classify_object(const DevTables &T, const Work &W, u32 i) {
     if (has_listen) dv |= GAR_DV_PORTS_FROM_ANN;
   }
   if (!object_key_ok(T, i)) dv |= OBJ_KEY_BAD;
+  W.okey_hash[i] = (dv & OBJ_KEY_BAD) ? 0 : key_hash_kinded(kind, object_key(T, i));
   W.derived[i] = dv;
   W.ann_r53[i] = r53;
   W.ann_name[i] = name;
@@ -275,11 +277,7 @@ GAR_HD void tokenise_hostname(const DevTables &T, const Work &W, u32 row) {
 #define TAG_THOST "aws-global-accelerator-target-hostname"
 #define TAG_CLUSTER "aws-global-accelerator-cluster"
 
-GAR_HD u32 count_slashes(Str s) {
-  u32 c = 0;
-  for (u32 k = 0; k < s.n; k++) c += s.p[k] == '/';
-  return c;
-}
+GAR_HD u32 count_slashes(Str s) { return count_byte(s, '/'); }
 
 GAR_HD void digest_accelerator(const DevTables &T, const Work &W, u32 a) {
   const gar_actual &A = T.a;
@@ -351,12 +349,26 @@ GAR_HD void classify_value(const DevTables &T, const Work &W, u32 v) {
 }
 
 // ------------------------------------------------------------------ index probes
+//
+// Entry payloads (IdxEntry.a0/a1/s0/s1), filled by the FEnt* functors of gar_pipeline.h:
+//   ix_lb     row=lb    a0=lb_state                 s0=lb_name ref     s1=lb_region ref
+//   ix_owner  row=accel a0=acc_flags                s0=owner key ref
+//   ix_thost  row=accel                             s0=target-hostname ref  s1=acc_dns ref
+//   ix_zone   row=zone                              s0=zone_name ref
+//   ix_val    row=value a0=record  a1=zone|kind<<31 s0=owner key ref   s1=record name ref
+//   ix_alias  row=record a0=zone   a1=rec_type      s0=record name ref s1=alias dns ref
+//   ix_obj    row=object a0=kind                    s0="ns/name" ref
+//   ix_ovn    row=value a0=record  a1=zone          s0=record name ref s1=value ref
 
 // GetLoadBalancer (load_balancer.go:13-30) on a client bound to `region` (aws.go:23-25): first row wins
-GAR_HD u32 find_lb(const DevTables &T, const Work &W, Str region, Str name) {
+GAR_HD u32 find_lb(const DevTables &T, const Work &W, Str region, Str name, u32 *state) {
   Cursor c = idx_open(W.ix_lb, key_hash_lb(region, name));
-  for (u32 r; (r = idx_next(W.ix_lb, c)) != GAR_NONE;)
-    if (streq(mkstr(T.a.slab, T.a.lb_name[r]), name) && streq(mkstr(T.a.slab, T.a.lb_region[r]), region)) return r;
+  IdxEntry e;
+  while (idx_next(W.ix_lb, c, &e))
+    if (streq(mkstr(T.a.slab, e.s0), name) && streq(mkstr(T.a.slab, e.s1), region)) {
+      *state = e.a0;
+      return e.row;
+    }
   return GAR_NONE;
 }
 
@@ -365,24 +377,29 @@ struct OwnerIter {
   Cursor c;
   Str key;
 };
-GAR_HD OwnerIter owner_open(const Work &W, u32 kind, Str key) { return OwnerIter{idx_open(W.ix_owner, key_hash_kinded(kind, key)), key}; }
+GAR_HD OwnerIter owner_open(const Work &W, u64 key_hash, Str key) { return OwnerIter{idx_open(W.ix_owner, key_hash), key}; }
 GAR_HD u32 owner_next(const DevTables &T, const Work &W, u32 kind, OwnerIter &it) {
-  for (u32 r; (r = idx_next(W.ix_owner, it.c)) != GAR_NONE;) {
-    u32 fl = W.acc_flags[r];
-    if ((((fl & ACC_OWNER_INGRESS) != 0) ? 1u : 0u) != kind) continue;
-    if (streq(mkstr(T.a.slab, W.acc_owner_key[r]), it.key)) return r;
+  IdxEntry e;
+  while (idx_next(W.ix_owner, it.c, &e)) {
+    if ((((e.a0 & ACC_OWNER_INGRESS) != 0) ? 1u : 0u) != kind) continue;
+    if (streq(mkstr(T.a.slab, e.s0), it.key)) return e.row;
   }
   return GAR_NONE;
 }
 
-// ListGlobalAcceleratorByHostname (global_accelerator.go:62-85): number of matches (saturating at 2) and the first
-GAR_HD u32 find_by_hostname(const DevTables &T, const Work &W, Str hostname, u32 *first) {
+// ListGlobalAcceleratorByHostname (global_accelerator.go:62-85): number of matches (saturating at 2), the first
+// match and its DnsName ref
+GAR_HD u32 find_by_hostname(const DevTables &T, const Work &W, Str hostname, u32 *first, gar_str *first_dns) {
   Cursor c = idx_open(W.ix_thost, key_hash_str(hostname));
   u32 n = 0;
   *first = GAR_NONE;
-  for (u32 r; (r = idx_next(W.ix_thost, c)) != GAR_NONE;) {
-    if (!streq(mkstr(T.a.slab, W.acc_thost[r]), hostname)) continue;
-    if (n == 0) *first = r;
+  IdxEntry e;
+  while (idx_next(W.ix_thost, c, &e)) {
+    if (!streq(mkstr(T.a.slab, e.s0), hostname)) continue;
+    if (n == 0) {
+      *first = e.row;
+      *first_dns = e.s1;
+    }
     if (++n >= 2) break;
   }
   return n;
@@ -394,12 +411,12 @@ GAR_HD u32 find_hosted_zone(const DevTables &T, const Work &W, Str hostname) {
   for (;;) {
     if (t.n == 0) return GAR_NONE;
     Cursor c = idx_open(W.ix_zone, key_hash_str(t));
-    for (u32 z; (z = idx_next(W.ix_zone, c)) != GAR_NONE;) {
-      Str zn = mkstr(T.a.slab, T.a.zone_name[z]);
-      if (zn.n == t.n + 1 && streq(substr(zn, 0, t.n), t)) return z;  // zone.Name == target + "."
+    IdxEntry e;
+    while (idx_next(W.ix_zone, c, &e)) {
+      Str zn = mkstr(T.a.slab, e.s0);
+      if (zn.n == t.n + 1 && streq(substr(zn, 0, t.n), t)) return e.row;  // zone.Name == target + "." (index holds dotted names only)
     }
-    u32 k = 0;
-    while (k < t.n && t.p[k] != '.') k++;
+    u32 k = find_byte(t, 0, '.');
     if (k >= t.n) return GAR_NONE;  // single label: parent is ""
     t = substr(t, k + 1, t.n - k - 1);
   }
@@ -409,30 +426,154 @@ GAR_HD u32 find_hosted_zone(const DevTables &T, const Work &W, Str hostname) {
 GAR_HD bool record_name_matches(Str name, Str hostname) {
   // first occurrence of \052 in name
   u32 w = GAR_NONE;
-  for (u32 k = 0; k + 4 <= name.n; k++)
-    if (name.p[k] == '\\' && name.p[k + 1] == '0' && name.p[k + 2] == '5' && name.p[k + 3] == '2') {
+  for (u32 k = find_byte(name, 0, '\\'); k + 4 <= name.n; k = find_byte(name, k + 1, '\\'))
+    if (name.p[k + 1] == '0' && name.p[k + 2] == '5' && name.p[k + 3] == '2') {
       w = k;
       break;
     }
-  if (w == GAR_NONE) {
-    return name.n == hostname.n + 1 && name.p[name.n - 1] == '.' && streq(substr(name, 0, hostname.n), hostname);
-  }
+  if (w == GAR_NONE) return name.n == hostname.n + 1 && name.p[name.n - 1] == '.' && streq(substr(name, 0, hostname.n), hostname);
   // unescaped = name[:w] + "*" + name[w+4:]; compare with hostname + "."
   if (name.n - 3 != hostname.n + 1) return false;
-  if (name.p[name.n - 1] != '.') return false;  // note: name[w+4:] is never empty when this holds... checked below
+  if (name.p[name.n - 1] != '.') return false;
   if (w >= hostname.n || hostname.p[w] != '*') return false;
   if (!streq(substr(name, 0, w), substr(hostname, 0, w))) return false;
   u32 tail = hostname.n - w - 1;  // bytes of hostname after '*'
   return streq(substr(name, w + 4, tail), substr(hostname, w + 1, tail));
 }
 
+// ------------------------------------------------------------------ warp-uniform probes
+//
+// The lookups above, written so that ALL lanes of a warp call them together (lanes without work pass
+// active = false).  Every loop — hashing the key, walking the bucket, comparing key bytes — advances under one
+// GAR_ANY vote per step, so the 32 lanes issue their loads in the same instruction (32 misses in flight per
+// warp instead of one after another) and re-converge at every step.  Only valid inside for_each_warp kernels.
+
+GAR_HD Cursor cursor_none() { return Cursor{0, 0, 0}; }
+GAR_HD Cursor u_open(const HashIdx &ix, bool active, u64 h) { return active ? idx_open(ix, h) : cursor_none(); }
+
+// One voted bucket step: loads the next entry of the lanes that are still searching.  Returns whether this lane
+// got an entry whose tag matches (the caller then compares keys with u_streq, again all lanes together).
+GAR_HD bool u_bucket_step(const HashIdx &ix, bool searching, Cursor &c, IdxEntry *e) {
+  bool step = searching && c.pos < c.end;
+  if (step) {
+    *e = load_entry(ix.ent + c.pos++);
+    return e->tag == c.tag;
+  }
+  return false;
+}
+#define U_BUCKET_LOOP(searching_expr, cur) for (; GAR_ANY((searching_expr) && (cur).pos < (cur).end);)
+
+// first LB row matching (region, name)  (GetLoadBalancer, load_balancer.go:13-30)
+GAR_HD u32 u_find_lb(const DevTables &T, const Work &W, bool active, Str region, Str name, u32 *state) {
+  u64 h = hmix(u_hash(active, region), u_hash(active, name));
+  Cursor c = u_open(W.ix_lb, active, h);
+  u32 found = GAR_NONE;
+  U_BUCKET_LOOP(found == GAR_NONE, c) {
+    IdxEntry e;
+    bool hit = u_bucket_step(W.ix_lb, found == GAR_NONE, c, &e);
+    bool eq = u_streq(hit, mkstr(T.a.slab, e.s0), name);
+    eq = u_streq(eq, mkstr(T.a.slab, e.s1), region);
+    if (eq) {
+      found = e.row;
+      *state = e.a0;
+    }
+  }
+  return found;
+}
+
+// next accelerator of the owner key (ListGlobalAcceleratorByResource, global_accelerator.go:87-110); the cursor
+// lives in the caller: one call = one accelerator, all lanes together
+GAR_HD u32 u_owner_next(const DevTables &T, const Work &W, bool active, u32 kind, Str key, Cursor &c) {
+  u32 found = GAR_NONE;
+  U_BUCKET_LOOP(active && found == GAR_NONE, c) {
+    IdxEntry e;
+    bool hit = u_bucket_step(W.ix_owner, active && found == GAR_NONE, c, &e);
+    hit = hit && (((e.a0 & ACC_OWNER_INGRESS) != 0) ? 1u : 0u) == kind;
+    if (u_streq(hit, mkstr(T.a.slab, e.s0), key)) found = e.row;
+  }
+  return found;
+}
+
+// accelerators whose target-hostname tag equals `hostname` (ListGlobalAcceleratorByHostname, :62-85):
+// count (saturating at 2), first row, its DnsName
+GAR_HD u32 u_find_by_hostname(const DevTables &T, const Work &W, bool active, Str hostname, u32 *first, gar_str *first_dns) {
+  Cursor c = u_open(W.ix_thost, active, u_hash(active, hostname));
+  u32 n = 0;
+  *first = GAR_NONE;
+  U_BUCKET_LOOP(n < 2, c) {
+    IdxEntry e;
+    bool hit = u_bucket_step(W.ix_thost, n < 2, c, &e);
+    if (u_streq(hit, mkstr(T.a.slab, e.s0), hostname)) {
+      if (n == 0) {
+        *first = e.row;
+        *first_dns = e.s1;
+      }
+      n++;
+    }
+  }
+  return n;
+}
+
+// GetHostedZone (route53.go:335-358): one voted round per candidate suffix
+GAR_HD u32 u_find_hosted_zone(const DevTables &T, const Work &W, bool active, Str hostname) {
+  Str t = hostname;
+  u32 zone = GAR_NONE;
+  bool walking = active;
+  for (;;) {
+    bool round = walking && t.n != 0;
+    if (!GAR_ANY(round)) break;
+    Cursor c = u_open(W.ix_zone, round, u_hash(round, t));
+    U_BUCKET_LOOP(zone == GAR_NONE, c) {
+      IdxEntry e;
+      bool hit = u_bucket_step(W.ix_zone, zone == GAR_NONE, c, &e);
+      Str zn = mkstr(T.a.slab, e.s0);
+      hit = hit && zn.n == t.n + 1;  // zone.Name == target + "." (the index holds dotted names only)
+      if (u_streq(hit, substr(zn, 0, hit ? t.n : 0), t)) zone = e.row;
+    }
+    u32 k = u_find_byte(round && zone == GAR_NONE, t, 0, '.');
+    if (round) {
+      if (zone != GAR_NONE || k >= t.n) walking = false;  // found, or single label left: parent is ""
+      else t = substr(t, k + 1, t.n - k - 1);
+    }
+  }
+  return zone;
+}
+
+// first alias record with type A under (zone, name)
+GAR_HD u32 u_first_alias_a(const DevTables &T, const Work &W, bool active, u32 zone, Str name, gar_str *alias_dns) {
+  Cursor c = u_open(W.ix_alias, active, hmix((u64)zone + 0x100, u_hash(active, name)));
+  u32 found = GAR_NONE;
+  U_BUCKET_LOOP(found == GAR_NONE, c) {
+    IdxEntry e;
+    bool hit = u_bucket_step(W.ix_alias, found == GAR_NONE, c, &e);
+    hit = hit && e.a0 == zone && e.a1 == GAR_RR_A;
+    if (u_streq(hit, mkstr(T.a.slab, e.s0), name)) {
+      found = e.row;
+      *alias_dns = e.s1;
+    }
+  }
+  return found;
+}
+
+// replaceWildcards(name) == hostname + "."  (route53.go:360-371), all lanes together.  Names without a backslash
+// (everything but wildcard records) take the voted compare; the \052 case falls back to the scalar routine.
+GAR_HD bool u_record_name_matches(bool active, Str name, Str hostname) {
+  u32 bs = u_find_byte(active, name, 0, '\\');
+  bool plain = active && bs >= name.n;
+  bool shape = plain && name.n == hostname.n + 1 && name.p[name.n - 1] == '.';
+  bool eq = u_streq(shape, substr(name, 0, shape ? hostname.n : 0), hostname);
+  if (active && !plain) eq = record_name_matches(name, hostname);
+  return eq;
+}
+
 // ------------------------------------------------------------------ op sink (count pass or write pass)
 
 struct OpSink {
-  gar_op *out;  // nullptr in the count pass
+  gar_op *out;  // nullptr: count only
   u32 n;
+  u32 cap;      // ops beyond cap are counted but not stored (staging slots are small; see FCompactOps)
   GAR_HD void put(u32 head, u32 obj, u32 sub, u32 a0, u32 a1, u32 a2) {
-    if (out) {
+    if (out && n < cap) {
       gar_op o;
       o.head = head;
       o.obj = obj;
@@ -463,6 +604,12 @@ GAR_HD PortList desired_ports(const DevTables &T, const Work &W, u32 i) {
 // listener FromPorts and desired ports; changed iff some port has count <= 1, i.e. occurs exactly once in
 // the concatenation of both lists.
 GAR_HD bool ports_changed(PortList l, PortList d) {
+  // fast paths for the common shapes (no duplicates inside a list): identical lists are unchanged
+  if (l.n == d.n) {
+    bool same = true;
+    for (u32 x = 0; x < l.n && same; x++) same = l.p[x] == d.p[x];
+    if (same) return false;  // every port occurs (at least) twice
+  }
   u32 n = l.n + d.n;
   for (u32 x = 0; x < n; x++) {
     i32 px = x < l.n ? l.p[x] : d.p[x - l.n];
@@ -485,10 +632,9 @@ GAR_HD bool accel_name_matches(const DevTables &T, const Work &W, u32 i, u32 kin
   // resource + "-" + ns + "-" + name
   Str ns = mkstr(T.o.slab, T.o.obj_ns[i]), nm = mkstr(T.o.slab, T.o.obj_name[i]);
   if (acc_name.n != 7 + 1 + ns.n + 1 + nm.n) return false;
-  const char *res = kind == GAR_KIND_SERVICE ? "service" : "ingress";
-  for (u32 k = 0; k < 7; k++)
-    if (acc_name.p[k] != (u8)res[k]) return false;
-  if (acc_name.p[7] != '-' || acc_name.p[8 + ns.n] != '-') return false;
+  const u64 res = kind == GAR_KIND_SERVICE ? 0x2d65636976726573ull /* "service-" */ : 0x2d73736572676e69ull /* "ingress-" */;
+  if (ld64u(acc_name.p) != res) return false;
+  if (acc_name.p[8 + ns.n] != '-') return false;
   return streq(substr(acc_name, 8, ns.n), ns) && streq(substr(acc_name, 9 + ns.n, nm.n), nm);
 }
 
@@ -506,14 +652,9 @@ struct TagPiece {
   bool ok;
 };
 GAR_HD TagPiece tag_piece(Str piece) {
-  u32 eq = GAR_NONE, neq = 0;
-  for (u32 k = 0; k < piece.n; k++)
-    if (piece.p[k] == '=') {
-      if (neq == 0) eq = k;
-      neq++;
-    }
+  u32 eq = find_byte(piece, 0, '=');
   TagPiece t;
-  t.ok = neq == 1;
+  t.ok = eq < piece.n && find_byte(piece, eq + 1, '=') >= piece.n;
   if (t.ok) {
     t.key = substr(piece, 0, eq);
     t.val = substr(piece, eq + 1, piece.n - eq - 1);
@@ -525,43 +666,43 @@ GAR_HD TagPiece tag_piece(Str piece) {
 // iterate the pieces of strings.Split(annotation, ",")
 GAR_HD bool next_piece(Str all, u32 *pos, Str *piece) {
   if (*pos > all.n) return false;
-  u32 b = *pos, k = b;
-  while (k < all.n && all.p[k] != ',') k++;
+  u32 b = *pos;
+  u32 k = find_byte(all, b, ',');
   *piece = substr(all, b, k - b);
   *pos = k + 1;
   return true;
 }
 
-// acceleratorChanged (global_accelerator.go:412-437)
-GAR_HD bool accelerator_changed(const DevTables &T, const Work &W, u32 i, u32 kind, u32 acc, Str lb_dns) {
+// tag half of acceleratorChanged (global_accelerator.go:420-436), scalar
+GAR_HD bool accelerator_tags_changed(const DevTables &T, const Work &W, u32 i, u32 kind, u32 acc, Str lb_dns) {
   const gar_actual &A = T.a;
-  if (!A.acc_enabled[acc]) return true;
-  if (!accel_name_matches(T, W, i, kind, mkstr(A.slab, A.acc_name[acc]))) return true;
   // targetTags = {managed:"true", owner:resource/ns/name, target-hostname:lb dns} overlaid by the user tags of
   // the annotation (later pieces overwrite earlier ones and the three system keys).
-  Str tags = (W.derived[i] & OBJ_HAS_TAGS_ANN) ? mkstr(T.o.slab, W.ann_tags[i]) : Str{T.o.slab, 0};
   bool user_managed = false, user_owner = false, user_thost = false;
-  u32 pos = 0;
-  Str piece;
-  while (next_piece(tags, &pos, &piece)) {
-    TagPiece tp = tag_piece(piece);
-    if (!tp.ok) continue;
-    if (STREQ_LIT(tp.key, TAG_MANAGED)) user_managed = true;
-    else if (STREQ_LIT(tp.key, TAG_OWNER)) user_owner = true;
-    else if (STREQ_LIT(tp.key, TAG_THOST)) user_thost = true;
-    // overridden by a later piece with the same key?
-    bool overridden = false;
-    u32 pos2 = pos;
-    Str piece2;
-    while (next_piece(tags, &pos2, &piece2)) {
-      TagPiece t2 = tag_piece(piece2);
-      if (t2.ok && streq(t2.key, tp.key)) {
-        overridden = true;
-        break;
+  if (W.derived[i] & OBJ_HAS_TAGS_ANN) {
+    Str tags = mkstr(T.o.slab, W.ann_tags[i]);
+    u32 pos = 0;
+    Str piece;
+    while (next_piece(tags, &pos, &piece)) {
+      TagPiece tp = tag_piece(piece);
+      if (!tp.ok) continue;
+      if (STREQ_LIT(tp.key, TAG_MANAGED)) user_managed = true;
+      else if (STREQ_LIT(tp.key, TAG_OWNER)) user_owner = true;
+      else if (STREQ_LIT(tp.key, TAG_THOST)) user_thost = true;
+      // overridden by a later piece with the same key?
+      bool overridden = false;
+      u32 pos2 = pos;
+      Str piece2;
+      while (next_piece(tags, &pos2, &piece2)) {
+        TagPiece t2 = tag_piece(piece2);
+        if (t2.ok && streq(t2.key, tp.key)) {
+          overridden = true;
+          break;
+        }
       }
+      if (overridden) continue;
+      if (!streq(actual_tag(T, acc, tp.key), tp.val)) return true;
     }
-    if (overridden) continue;
-    if (!streq(actual_tag(T, acc, tp.key), tp.val)) return true;
   }
   u32 fl = W.acc_flags[acc];
   if (!user_managed && !STREQ_LIT(mkstr(A.slab, W.acc_managed[acc]), "true")) return true;
@@ -592,73 +733,176 @@ GAR_HD void put_delete_chain(const DevTables &T, OpSink &s, u32 obj, u32 kind, u
 // process{Service,Ingress}CreateOrUpdate (globalaccelerator/service.go:54-126, ingress.go:56-130) with
 // EnsureGlobalAcceleratorFor* (global_accelerator.go:112-211) and updateGlobalAcceleratorFor* (:290-410) inlined.
 
-GAR_HD u32 ga_reconcile(const DevTables &T, const Work &W, u32 i, OpSink &s) {
+// acceleratorChanged (global_accelerator.go:412-437), all lanes together.  The rare tags-annotation overlay keeps the
+// scalar routine (divergent, no votes inside).
+GAR_HD bool u_accelerator_changed(const DevTables &T, const Work &W, bool act, u32 i, u32 dv, u32 kind, u32 acc, Str okey, Str lb_dns) {
+  const gar_actual &A = T.a;
+  bool ch = act && !A.acc_enabled[acc];
+  // name: the annotation when non-empty, else resource-ns-name
+  bool need = act && !ch;
+  Str an = need ? mkstr(A.slab, A.acc_name[acc]) : Str{A.slab, 0};
+  Str ann = (need && (dv & OBJ_HAS_NAME_ANN)) ? mkstr(T.o.slab, W.ann_name[i]) : Str{T.o.slab, 0};
+  bool by_ann = need && ann.n != 0;
+  bool eq_ann = u_streq(by_ann, ann, an);
+  Str ns = need ? mkstr(T.o.slab, T.o.obj_ns[i]) : Str{T.o.slab, 0};
+  Str nm = need ? mkstr(T.o.slab, T.o.obj_name[i]) : Str{T.o.slab, 0};
+  bool shape = need && !by_ann && an.n == 9 + ns.n + nm.n &&
+               ld64u(an.p) == (kind == GAR_KIND_SERVICE ? 0x2d65636976726573ull /* "service-" */ : 0x2d73736572676e69ull /* "ingress-" */) &&
+               an.p[8 + ns.n] == '-';
+  bool eq_def = u_streq(shape, substr(an, 8, shape ? ns.n : 0), ns);
+  eq_def = u_streq(eq_def, substr(an, 9 + ns.n, eq_def ? nm.n : 0), nm);
+  if (need && !(by_ann ? eq_ann : eq_def)) ch = true;
+  // tags: managed, owner, target-hostname (user tags from the annotation may override them)
+  bool tagcheck = act && !ch;
+  bool overlay = tagcheck && (dv & OBJ_HAS_TAGS_ANN);
+  if (overlay) ch = accelerator_tags_changed(T, W, i, kind, acc, lb_dns);
+  bool sys = tagcheck && !overlay;
+  u32 fl = sys ? W.acc_flags[acc] : 0;
+  if (sys && !STREQ_LIT(mkstr(A.slab, W.acc_managed[acc]), "true")) ch = true;
+  bool own_shape = sys && !ch && (fl & ACC_OWNER_KEYED) && (((fl & ACC_OWNER_INGRESS) ? 1u : 0u) == kind);
+  if (sys && !ch && !own_shape) ch = true;
+  bool own_eq = u_streq(own_shape, own_shape ? mkstr(A.slab, W.acc_owner_key[acc]) : Str{A.slab, 0}, okey);
+  if (own_shape && !own_eq) ch = true;
+  bool th = sys && !ch;
+  bool th_eq = u_streq(th, th ? mkstr(A.slab, W.acc_thost[acc]) : Str{A.slab, 0}, lb_dns);
+  if (th && !th_eq) ch = true;
+  return ch;
+}
+
+// Written warp-synchronously: every lane of the warp runs the same outer loops (lbIngress index, accelerator of the
+// owner) and the same probe / compare steps under GAR_ANY votes, carrying its own predicates; nothing returns from
+// inside a loop.  `valid` is false for padding lanes beyond the last object.
+GAR_HD u32 ga_reconcile(const DevTables &T, const Work &W, u32 i, bool valid, OpSink &s) {
   const gar_objects &o = T.o;
   const gar_actual &A = T.a;
-  u32 dv = W.derived[i];
-  if (!(dv & GAR_DV_GA_ELIGIBLE)) return GAR_STATUS(GAR_ST_IGNORED, 0, 0);
-  u32 jb = o.obj_lbi_begin[i], je = o.obj_lbi_begin[i + 1];
-  if (je - jb < 1) return GAR_STATUS(GAR_ST_SKIP_NO_LB, 0, 0);
-  u32 kind = o.obj_kind[i];
-  Str okey = object_key(T, i);
-  if (!(dv & GAR_DV_GA_MANAGED)) {
-    OwnerIter it = owner_open(W, kind, okey);
-    for (u32 acc; (acc = owner_next(T, W, kind, it)) != GAR_NONE;) put_delete_chain(T, s, i, kind, acc);
-    return GAR_STATUS(GAR_ST_OK, 0, GAR_EV_DELETED);
+  u32 result = GAR_STATUS(GAR_ST_IGNORED, 0, 0);
+  u32 dv = 0, kind = 0, jb = 0, nj = 0;
+  Str okey{T.o.slab, 0};
+  u64 okh = 0;
+  bool ensure = false;
+  if (valid) {
+    dv = W.derived[i];
+    if (dv & GAR_DV_GA_ELIGIBLE) {
+      jb = o.obj_lbi_begin[i];
+      nj = o.obj_lbi_begin[i + 1] - jb;
+      kind = o.obj_kind[i];
+      if (nj < 1) {
+        result = GAR_STATUS(GAR_ST_SKIP_NO_LB, 0, 0);
+      } else {
+        okey = object_key(T, i);
+        okh = W.okey_hash[i];
+        if (!(dv & GAR_DV_GA_MANAGED)) {  // cleanup path (rare): runs divergent, no votes inside
+          OwnerIter it = owner_open(W, okh, okey);
+          for (u32 acc; (acc = owner_next(T, W, kind, it)) != GAR_NONE;) put_delete_chain(T, s, i, kind, acc);
+          result = GAR_STATUS(GAR_ST_OK, 0, GAR_EV_DELETED);
+        } else {
+          ensure = true;
+        }
+      }
+    }
   }
   u32 ev = 0;
-  for (u32 j = 0; j < je - jb; j++) {
-    u32 code = W.tok_code[jb + j];
-    if (code == GAR_TOK_PANIC) return GAR_STATUS(GAR_ST_PANIC, 0, ev);
-    if (code == GAR_TOK_NOT_AWS) continue;
-    if (code >= GAR_TOK_ERR_NOT_ELB) return GAR_STATUS(GAR_ST_ERR_RETRY, GAR_D_NOT_ELB + (code - GAR_TOK_ERR_NOT_ELB), ev);
-    Str hostname = mkstr(o.slab, o.lbi_hostname[jb + j]);
-    u32 lb = find_lb(T, W, mkstr(o.slab, W.tok_region[jb + j]), mkstr(o.slab, W.tok_name[jb + j]));
-    if (lb == GAR_NONE) return GAR_STATUS(GAR_ST_ERR_RETRY, GAR_D_LB_NOT_FOUND, ev);
-    Str lb_dns = mkstr(A.slab, A.lb_dns[lb]);
-    if (!streq(lb_dns, hostname)) return GAR_STATUS(GAR_ST_ERR_RETRY, GAR_D_LB_DNS_MISMATCH, ev);
-    if (A.lb_state[lb] != GAR_LB_ACTIVE) return GAR_STATUS(GAR_ST_REQUEUE_30S, 0, ev);
-    OwnerIter it = owner_open(W, kind, okey);
-    u32 nacc = 0;
-    for (u32 acc; (acc = owner_next(T, W, kind, it)) != GAR_NONE;) {
-      nacc++;
-      // updateGlobalAcceleratorFor{Service,Ingress}
-      if (accelerator_changed(T, W, i, kind, acc, lb_dns)) s.put(GAR_OP_HEAD(GAR_OP_GA_UPDATE_ACCEL, GAR_CTRL_GA, kind), i, j, acc, lb, GAR_NONE);
-      u32 lbeg = A.acc_lis_begin[acc], lend = A.acc_lis_begin[acc + 1];
-      if (lend - lbeg > 1) return GAR_STATUS(GAR_ST_ERR_RETRY, GAR_D_TOO_MANY_LISTENERS, ev);
-      if (lend == lbeg) {
-        // the listener is created from the desired state, so neither change predicate fires on it; it has no
-        // endpoint group yet, and the one created for it contains the LB (:298-345)
-        s.put(GAR_OP_HEAD(GAR_OP_GA_CREATE_LISTENER, GAR_CTRL_GA, kind), i, j, acc, GAR_NONE, GAR_NONE);
-        s.put(GAR_OP_HEAD(GAR_OP_GA_CREATE_EG, GAR_CTRL_GA, kind), i, j, acc, GAR_NONE, lb);
-        continue;
+  bool stop = false;
+  for (u32 j = 0;; j++) {
+    bool act = ensure && !stop && j < nj;
+    if (!GAR_ANY(act)) break;
+    bool probe = false;
+    Str hostname{o.slab, 0}, tregion{o.slab, 0}, tname{o.slab, 0};
+    if (act) {
+      u32 code = W.tok_code[jb + j];
+      if (code == GAR_TOK_PANIC) {
+        result = GAR_STATUS(GAR_ST_PANIC, 0, ev);
+        stop = true;
+      } else if (code == GAR_TOK_NOT_AWS) {
+      } else if (code >= GAR_TOK_ERR_NOT_ELB) {
+        result = GAR_STATUS(GAR_ST_ERR_RETRY, GAR_D_NOT_ELB + (code - GAR_TOK_ERR_NOT_ELB), ev);
+        stop = true;
+      } else {
+        probe = true;
+        hostname = mkstr(o.slab, o.lbi_hostname[jb + j]);
+        tregion = mkstr(o.slab, W.tok_region[jb + j]);
+        tname = mkstr(o.slab, W.tok_name[jb + j]);
       }
-      u32 lis = lbeg;
-      u32 want_proto = kind == GAR_KIND_SERVICE ? ((dv & GAR_DV_PROTO_UDP) ? GAR_PROTO_UDP : GAR_PROTO_TCP) : GAR_PROTO_TCP;
-      bool changed = A.lis_proto[lis] != want_proto;  // :439-456
-      if (!changed) {
-        u32 pb = A.lis_pr_begin[lis];
-        changed = ports_changed(PortList{A.pr_from + pb, A.lis_pr_begin[lis + 1] - pb}, desired_ports(T, W, i));
-      }
-      if (changed) s.put(GAR_OP_HEAD(GAR_OP_GA_UPDATE_LISTENER, GAR_CTRL_GA, kind), i, j, acc, lis, GAR_NONE);
-      u32 eb = A.lis_eg_begin[lis], ee = A.lis_eg_begin[lis + 1];
-      if (ee - eb > 1) return GAR_STATUS(GAR_ST_ERR_RETRY, GAR_D_TOO_MANY_EGS, ev);
-      if (ee == eb) {
-        s.put(GAR_OP_HEAD(GAR_OP_GA_CREATE_EG, GAR_CTRL_GA, kind), i, j, acc, lis, lb);
-        continue;
-      }
-      u32 eg = eb;
-      Str lb_arn = mkstr(A.slab, A.lb_arn[lb]);
-      bool contains = false;  // endpointContainsLB (:494-501)
-      for (u32 d = A.eg_ep_begin[eg]; d < A.eg_ep_begin[eg + 1] && !contains; d++) contains = streq(mkstr(A.slab, A.ep_id[d]), lb_arn);
-      if (!contains) s.put(GAR_OP_HEAD(GAR_OP_GA_UPDATE_EG, GAR_CTRL_GA, kind), i, j, acc, eg, lb);
     }
-    if (nacc == 0) {
+    // EnsureGlobalAcceleratorFor* (global_accelerator.go:112-211)
+    u32 lb_state = 0;
+    u32 lb = u_find_lb(T, W, probe, tregion, tname, &lb_state);
+    bool have_lb = probe && lb != GAR_NONE;
+    Str lb_dns = have_lb ? mkstr(A.slab, A.lb_dns[lb]) : Str{A.slab, 0};
+    bool dns_eq = u_streq(have_lb, lb_dns, hostname);
+    bool go = false;
+    if (probe) {
+      if (!have_lb) {
+        result = GAR_STATUS(GAR_ST_ERR_RETRY, GAR_D_LB_NOT_FOUND, ev);
+        stop = true;
+      } else if (!dns_eq) {
+        result = GAR_STATUS(GAR_ST_ERR_RETRY, GAR_D_LB_DNS_MISMATCH, ev);
+        stop = true;
+      } else if (lb_state != GAR_LB_ACTIVE) {
+        result = GAR_STATUS(GAR_ST_REQUEUE_30S, 0, ev);
+        stop = true;
+      } else {
+        go = true;
+      }
+    }
+    Cursor oc = u_open(W.ix_owner, go, okh);
+    Str lb_arn = go ? mkstr(A.slab, A.lb_arn[lb]) : Str{A.slab, 0};
+    u32 nacc = 0;
+    for (;;) {  // accelerators of the owner, in ListAccelerators order
+      u32 acc = u_owner_next(T, W, go && !stop, kind, okey, oc);
+      bool a = acc != GAR_NONE;
+      if (!GAR_ANY(a)) break;
+      if (a) nacc++;
+      // updateGlobalAcceleratorFor{Service,Ingress} (:290-410)
+      if (u_accelerator_changed(T, W, a, i, dv, kind, acc, okey, lb_dns)) s.put(GAR_OP_HEAD(GAR_OP_GA_UPDATE_ACCEL, GAR_CTRL_GA, kind), i, j, acc, lb, GAR_NONE);
+      u32 eg = GAR_NONE;
+      if (a) {
+        u32 lbeg = A.acc_lis_begin[acc], lend = A.acc_lis_begin[acc + 1];
+        if (lend - lbeg > 1) {
+          result = GAR_STATUS(GAR_ST_ERR_RETRY, GAR_D_TOO_MANY_LISTENERS, ev);
+          stop = true;
+        } else if (lend == lbeg) {
+          // the listener is created from the desired state, so neither change predicate fires on it; it has no
+          // endpoint group yet, and the one created for it contains the LB (:298-345)
+          s.put(GAR_OP_HEAD(GAR_OP_GA_CREATE_LISTENER, GAR_CTRL_GA, kind), i, j, acc, GAR_NONE, GAR_NONE);
+          s.put(GAR_OP_HEAD(GAR_OP_GA_CREATE_EG, GAR_CTRL_GA, kind), i, j, acc, GAR_NONE, lb);
+        } else {
+          u32 lis = lbeg;
+          u32 want_proto = kind == GAR_KIND_SERVICE ? ((dv & GAR_DV_PROTO_UDP) ? GAR_PROTO_UDP : GAR_PROTO_TCP) : GAR_PROTO_TCP;
+          bool changed = A.lis_proto[lis] != want_proto;  // :439-456
+          if (!changed) {
+            u32 pb = A.lis_pr_begin[lis];
+            changed = ports_changed(PortList{A.pr_from + pb, A.lis_pr_begin[lis + 1] - pb}, desired_ports(T, W, i));
+          }
+          if (changed) s.put(GAR_OP_HEAD(GAR_OP_GA_UPDATE_LISTENER, GAR_CTRL_GA, kind), i, j, acc, lis, GAR_NONE);
+          u32 eb = A.lis_eg_begin[lis], ee = A.lis_eg_begin[lis + 1];
+          if (ee - eb > 1) {
+            result = GAR_STATUS(GAR_ST_ERR_RETRY, GAR_D_TOO_MANY_EGS, ev);
+            stop = true;
+          } else if (ee == eb) {
+            s.put(GAR_OP_HEAD(GAR_OP_GA_CREATE_EG, GAR_CTRL_GA, kind), i, j, acc, lis, lb);
+          } else {
+            eg = eb;
+          }
+        }
+      }
+      // endpointContainsLB (:494-501): one voted step per endpoint description
+      bool contains = false;
+      u32 d = eg != GAR_NONE ? A.eg_ep_begin[eg] : 0, dend = eg != GAR_NONE ? A.eg_ep_begin[eg + 1] : 0;
+      for (;; d++) {
+        bool more = !contains && d < dend;
+        if (!GAR_ANY(more)) break;
+        if (u_streq(more, more ? mkstr(A.slab, A.ep_id[d]) : Str{A.slab, 0}, lb_arn)) contains = true;
+      }
+      if (eg != GAR_NONE && !contains) s.put(GAR_OP_HEAD(GAR_OP_GA_UPDATE_EG, GAR_CTRL_GA, kind), i, j, acc, eg, lb);
+    }
+    if (go && !stop && nacc == 0) {
       s.put(GAR_OP_HEAD(GAR_OP_GA_CREATE_CHAIN, GAR_CTRL_GA, kind), i, j, lb, GAR_NONE, GAR_NONE);
       ev |= GAR_EV_CREATED;
     }
   }
-  return GAR_STATUS(GAR_ST_OK, 0, ev);
+  if (ensure && !stop) result = GAR_STATUS(GAR_ST_OK, 0, ev);
+  return result;
 }
 
 // ------------------------------------------------------------------ (a9)(a10) Route53 decisions of one object
@@ -666,66 +910,118 @@ GAR_HD u32 ga_reconcile(const DevTables &T, const Work &W, u32 i, OpSink &s) {
 // process{Service,Ingress}CreateOrUpdate of the route53 controller (route53/service.go:48-111, ingress.go:40-104),
 // ensureRoute53 (route53.go:56-130) and CleanupRecordSet (:132-165).
 
-// iterate the owner-value rows of one object key in ascending value-row order
-struct ValIter {
-  Cursor c;
-  Str key;
-  u32 kind;
+// The owner-value rows of one object key, ascending by value row (= zone-major), fetched ONCE per object.  The
+// first OWNED_CACHE rows are kept in registers/local memory; objects owning more fall back to re-walking the bucket.
+constexpr u32 OWNED_CACHE = 8;
+struct OwnedHit {
+  u32 v, rec, zone;
+  gar_str name;  // record name of the set that carries the value
 };
-GAR_HD ValIter val_open(const Work &W, u32 kind, Str key) { return ValIter{idx_open(W.ix_val, key_hash_kinded(kind, key)), key, kind}; }
-GAR_HD u32 val_next(const DevTables &T, const Work &W, ValIter &it) {
-  for (u32 v; (v = idx_next(W.ix_val, it.c)) != GAR_NONE;) {
-    u32 cls = W.val_cls[v];
-    if (((cls & VAL_OWNER_INGRESS) ? 1u : 0u) != it.kind) continue;
-    if (streq(mkstr(T.a.slab, W.val_key[v]), it.key)) return v;
+struct Owned {
+  OwnedHit hit[OWNED_CACHE];
+  u32 n;  // total number of owned value rows (may exceed OWNED_CACHE)
+  u64 okh;
+  u32 kind;
+  Str key;
+};
+GAR_HD bool owned_match(const DevTables &T, const IdxEntry &e, u32 kind, Str key) {
+  return (e.a1 >> 31) == kind && streq(mkstr(T.a.slab, e.s0), key);
+}
+GAR_HD void owned_collect(const DevTables &T, const Work &W, u64 okh, u32 kind, Str key, Owned &o) {
+  o.n = 0;
+  o.okh = okh;
+  o.kind = kind;
+  o.key = key;
+  Cursor c = idx_open(W.ix_val, okh);
+  IdxEntry e;
+  while (idx_next(W.ix_val, c, &e)) {
+    if (!owned_match(T, e, kind, key)) continue;
+    if (o.n < OWNED_CACHE) o.hit[o.n] = OwnedHit{e.row, e.a0, e.a1 & 0x7FFFFFFFu, e.s1};
+    o.n++;
   }
-  return GAR_NONE;
+}
+GAR_HD void u_owned_collect(const DevTables &T, const Work &W, bool active, u64 okh, u32 kind, Str key, Owned &o) {
+  if (active) {
+    o.n = 0;
+    o.okh = okh;
+    o.kind = kind;
+    o.key = key;
+  }
+  Cursor c = active ? idx_open(W.ix_val, okh) : Cursor{0, 0, 0};
+  for (; GAR_ANY(c.pos < c.end);) {
+    IdxEntry e;
+    bool hit = false;
+    if (c.pos < c.end) {
+      e = load_entry(W.ix_val.ent + c.pos++);
+      hit = e.tag == c.tag && (e.a1 >> 31) == kind;
+    }
+    if (u_streq(hit, hit ? mkstr(T.a.slab, e.s0) : Str{T.a.slab, 0}, key)) {
+      if (o.n < OWNED_CACHE) o.hit[o.n] = OwnedHit{e.row, e.a0, e.a1 & 0x7FFFFFFFu, e.s1};
+      o.n++;
+    }
+  }
+}
+GAR_HD OwnedHit owned_get(const DevTables &T, const Work &W, const Owned &o, u32 k) {
+  if (k < OWNED_CACHE) return o.hit[k];
+  Cursor c = idx_open(W.ix_val, o.okh);  // rare: re-walk the bucket to the k-th match
+  IdxEntry e;
+  u32 seen = 0;
+  OwnedHit h{GAR_NONE, GAR_NONE, GAR_NONE, 0};
+  while (idx_next(W.ix_val, c, &e)) {
+    if (!owned_match(T, e, o.kind, o.key)) continue;
+    if (seen++ == k) {
+      h = OwnedHit{e.row, e.a0, e.a1 & 0x7FFFFFFFu, e.s1};
+      break;
+    }
+  }
+  return h;
 }
 
-// first alias record with type A under (zone, name), or GAR_NONE  (rows of a bucket are ascending)
-GAR_HD u32 first_alias_a(const DevTables &T, const Work &W, u32 zone, Str name) {
+// first alias record with type A under (zone, name): row and its alias DNSName ref  (rows of a bucket are ascending)
+GAR_HD u32 first_alias_a(const DevTables &T, const Work &W, u32 zone, Str name, gar_str *alias_dns) {
   Cursor c = idx_open(W.ix_alias, key_hash_zoned(zone, name));
-  for (u32 r; (r = idx_next(W.ix_alias, c)) != GAR_NONE;) {
-    if (W.rec_zone[r] != zone || T.a.rec_type[r] != GAR_RR_A) continue;
-    if (streq(mkstr(T.a.slab, T.a.rec_name[r]), name)) return r;
+  IdxEntry e;
+  while (idx_next(W.ix_alias, c, &e)) {
+    if (e.a0 != zone || e.a1 != GAR_RR_A) continue;
+    if (streq(mkstr(T.a.slab, e.s0), name)) {
+      *alias_dns = e.s1;
+      return e.row;
+    }
   }
   return GAR_NONE;
 }
 // smallest alias record row > after under (zone, name), any type
 GAR_HD u32 next_alias_any(const DevTables &T, const Work &W, u32 zone, Str name, u32 after /* GAR_NONE = none yet */) {
   Cursor c = idx_open(W.ix_alias, key_hash_zoned(zone, name));
-  for (u32 r; (r = idx_next(W.ix_alias, c)) != GAR_NONE;) {
-    if (after != GAR_NONE && r <= after) continue;
-    if (W.rec_zone[r] != zone) continue;
-    if (streq(mkstr(T.a.slab, T.a.rec_name[r]), name)) return r;
+  IdxEntry e;
+  while (idx_next(W.ix_alias, c, &e)) {
+    if (after != GAR_NONE && e.row <= after) continue;
+    if (e.a0 != zone) continue;
+    if (streq(mkstr(T.a.slab, e.s0), name)) return e.row;
   }
   return GAR_NONE;
 }
 
 // CleanupRecordSet for one owner key: per zone, owned alias sets in record order, then owner metadata sets
-GAR_HD void r53_cleanup(const DevTables &T, const Work &W, u32 obj, u32 kind, Str okey, OpSink &s) {
+GAR_HD void r53_cleanup(const DevTables &T, const Work &W, u32 obj, u32 kind, const Owned &ow, OpSink &s) {
   const gar_actual &A = T.a;
   u32 head = GAR_OP_HEAD(GAR_OP_R53_DELETE_RECORD, GAR_CTRL_R53, obj == GAR_NONE ? 0 : kind);
-  // value rows come out ascending, i.e. grouped by zone in zone order
-  ValIter it = val_open(W, kind, okey);
-  u32 v = val_next(T, W, it);
-  while (v != GAR_NONE) {
-    u32 zone = W.rec_zone[W.val_rec[v]];
+  u32 k = 0;
+  while (k < ow.n) {  // value rows are ascending, i.e. grouped by zone in zone order
+    u32 zone = owned_get(T, W, ow, k).zone;
+    u32 kend = k;
+    while (kend < ow.n && owned_get(T, W, ow, kend).zone == zone) kend++;
     // phase 0: repeatedly take the smallest not-yet-emitted alias record whose name is one of the zone group's names
     u32 last = GAR_NONE;
     for (;;) {
       u32 best = GAR_NONE, best_v = GAR_NONE;
-      ValIter g = val_open(W, kind, okey);
-      for (u32 x; (x = val_next(T, W, g)) != GAR_NONE;) {
-        u32 zx = W.rec_zone[W.val_rec[x]];
-        if (zx < zone) continue;
-        if (zx > zone) break;
-        Str nm = mkstr(A.slab, A.rec_name[W.val_rec[x]]);
-        u32 r = next_alias_any(T, W, zone, nm, last);
+      for (u32 x = k; x < kend; x++) {
+        OwnedHit h = owned_get(T, W, ow, x);
+        u32 r = next_alias_any(T, W, zone, mkstr(A.slab, h.name), last);
         // x ascending: the first value row that reaches a record is the one hostnameContains would hit first
         if (r != GAR_NONE && (best == GAR_NONE || r < best)) {
           best = r;
-          best_v = x;
+          best_v = h.v;
         }
       }
       if (best == GAR_NONE) break;
@@ -733,82 +1029,150 @@ GAR_HD void r53_cleanup(const DevTables &T, const Work &W, u32 obj, u32 kind, St
       last = best;
     }
     // phase 1: one op per matching value of this zone
-    u32 x = v;
-    while (x != GAR_NONE && W.rec_zone[W.val_rec[x]] == zone) {
-      s.put(head, obj, 1, zone, W.val_rec[x], x);
-      x = val_next(T, W, it);
+    for (u32 x = k; x < kend; x++) {
+      OwnedHit h = owned_get(T, W, ow, x);
+      s.put(head, obj, 1, zone, h.rec, h.v);
     }
-    v = x;
+    k = kend;
   }
 }
 
-GAR_HD u32 r53_reconcile(const DevTables &T, const Work &W, u32 i, OpSink &s) {
+// Warp-synchronous like ga_reconcile: uniform loops over lbIngress index, hostname index and owned value rows; every
+// probe and compare is a voted step.
+GAR_HD u32 r53_reconcile(const DevTables &T, const Work &W, u32 i, bool valid, OpSink &s) {
   const gar_objects &o = T.o;
   const gar_actual &A = T.a;
-  u32 dv = W.derived[i];
-  if (!(dv & GAR_DV_R53_ELIGIBLE)) return GAR_STATUS(GAR_ST_IGNORED, 0, 0);
-  u32 kind = o.obj_kind[i];
-  Str okey = object_key(T, i);
-  if (!(dv & GAR_DV_R53_ANNOTATED)) {
-    r53_cleanup(T, W, i, kind, okey, s);
-    return GAR_STATUS(GAR_ST_OK, 0, GAR_EV_DELETED);
+  u32 result = GAR_STATUS(GAR_ST_IGNORED, 0, 0);
+  u32 kind = 0, jb = 0, nj = 0;
+  Str okey{T.o.slab, 0}, hostnames{T.o.slab, 0};
+  u64 okh = 0;
+  bool ensure = false;
+  Owned ow;
+  ow.n = 0;
+  if (valid) {
+    u32 dv = W.derived[i];
+    if (dv & GAR_DV_R53_ELIGIBLE) {
+      kind = o.obj_kind[i];
+      okey = object_key(T, i);
+      okh = W.okey_hash[i];
+      if (!(dv & GAR_DV_R53_ANNOTATED)) {  // cleanup path: divergent, no votes inside
+        owned_collect(T, W, okh, kind, okey, ow);
+        r53_cleanup(T, W, i, kind, ow, s);
+        result = GAR_STATUS(GAR_ST_OK, 0, GAR_EV_DELETED);
+      } else {
+        ensure = true;
+        hostnames = mkstr(o.slab, W.ann_r53[i]);
+        jb = o.obj_lbi_begin[i];
+        nj = o.obj_lbi_begin[i + 1] - jb;
+      }
+    }
   }
-  Str hostnames = mkstr(o.slab, W.ann_r53[i]);
-  u32 jb = o.obj_lbi_begin[i], je = o.obj_lbi_begin[i + 1];
   u32 ev = 0;
-  for (u32 j = 0; j < je - jb; j++) {
-    u32 code = W.tok_code[jb + j];
-    if (code == GAR_TOK_PANIC) return GAR_STATUS(GAR_ST_PANIC, 0, ev);
-    if (code == GAR_TOK_NOT_AWS) continue;
-    if (code >= GAR_TOK_ERR_NOT_ELB) return GAR_STATUS(GAR_ST_ERR_RETRY, GAR_D_NOT_ELB + (code - GAR_TOK_ERR_NOT_ELB), ev);
-    Str lb_hostname = mkstr(o.slab, o.lbi_hostname[jb + j]);
-    u32 acc;
-    u32 nacc = find_by_hostname(T, W, lb_hostname, &acc);
-    if (nacc > 1) return GAR_STATUS(GAR_ST_REQUEUE_60S, GAR_D_ACCEL_MANY, ev);
-    if (nacc == 0) return GAR_STATUS(GAR_ST_REQUEUE_60S, GAR_D_ACCEL_NONE, ev);
-    Str acc_dns = mkstr(A.slab, A.acc_dns[acc]);
+  bool stop = false, collected = false;
+  for (u32 j = 0;; j++) {
+    bool act = ensure && !stop && j < nj;
+    if (!GAR_ANY(act)) break;
+    bool probe = false;
+    Str lbhost{o.slab, 0};
+    if (act) {
+      u32 code = W.tok_code[jb + j];
+      if (code == GAR_TOK_PANIC) {
+        result = GAR_STATUS(GAR_ST_PANIC, 0, ev);
+        stop = true;
+      } else if (code == GAR_TOK_NOT_AWS) {
+      } else if (code >= GAR_TOK_ERR_NOT_ELB) {
+        result = GAR_STATUS(GAR_ST_ERR_RETRY, GAR_D_NOT_ELB + (code - GAR_TOK_ERR_NOT_ELB), ev);
+        stop = true;
+      } else {
+        probe = true;
+        lbhost = mkstr(o.slab, o.lbi_hostname[jb + j]);
+      }
+    }
+    // ensureRoute53 (route53.go:56-130)
+    u32 acc = GAR_NONE;
+    gar_str acc_dns_ref = 0;
+    u32 nacc = u_find_by_hostname(T, W, probe, lbhost, &acc, &acc_dns_ref);
+    bool go = false;
+    if (probe) {
+      if (nacc > 1) {
+        result = GAR_STATUS(GAR_ST_REQUEUE_60S, GAR_D_ACCEL_MANY, ev);
+        stop = true;
+      } else if (nacc == 0) {
+        result = GAR_STATUS(GAR_ST_REQUEUE_60S, GAR_D_ACCEL_NONE, ev);
+        stop = true;
+      } else {
+        go = true;
+      }
+    }
+    Str acc_dns = go ? mkstr(A.slab, acc_dns_ref) : Str{A.slab, 0};
+    if (GAR_ANY(go && !collected)) {  // the object's owner-value rows, fetched once (all lanes walk their bucket together)
+      u_owned_collect(T, W, go && !collected, okh, kind, okey, ow);
+      if (go) collected = true;
+    }
     bool created = false;
     u32 pos = 0, k = 0;
-    Str hn;
-    while (next_piece(hostnames, &pos, &hn)) {
-      u32 zone = find_hosted_zone(T, W, hn);
-      if (zone == GAR_NONE) return GAR_STATUS(GAR_ST_ERR_RETRY, GAR_D_NO_HOSTED_ZONE, ev);
+    for (;;) {  // hostnames of the annotation, in order: strings.Split(annotation, ",")
+      bool more = go && !stop && pos <= hostnames.n;
+      if (!GAR_ANY(more)) break;
+      u32 comma = u_find_byte(more, hostnames, pos, ',');
+      Str hn = more ? substr(hostnames, pos, comma - pos) : Str{o.slab, 0};
+      pos = comma + 1;
+      u32 zone = u_find_hosted_zone(T, W, more, hn);
+      if (more && zone == GAR_NONE) {
+        result = GAR_STATUS(GAR_ST_ERR_RETRY, GAR_D_NO_HOSTED_ZONE, ev);
+        stop = true;
+        more = false;
+      }
       // findARecord over FindOwneredARecordSets: first (by record row) alias A record of the zone whose name is
       // owned by this object and unescapes to hostname + "."
       u32 rec = GAR_NONE;
-      ValIter it = val_open(W, kind, okey);
-      for (u32 v; (v = val_next(T, W, it)) != GAR_NONE;) {
-        u32 vr = W.val_rec[v];
-        u32 vz = W.rec_zone[vr];
-        if (vz < zone) continue;
-        if (vz > zone) break;
-        Str nm = mkstr(A.slab, A.rec_name[vr]);
-        if (!record_name_matches(nm, hn)) continue;
-        u32 r = first_alias_a(T, W, zone, nm);
-        if (r != GAR_NONE && (rec == GAR_NONE || r < rec)) rec = r;
+      gar_str rec_alias = 0;
+      for (u32 x = 0;; x++) {
+        bool has = more && x < ow.n;
+        if (!GAR_ANY(has)) break;
+        Str nm{A.slab, 0};
+        bool inzone = false;
+        if (has) {
+          OwnedHit h = owned_get(T, W, ow, x);
+          inzone = h.zone == zone;
+          if (inzone) nm = mkstr(A.slab, h.name);
+        }
+        bool cand = u_record_name_matches(inzone, nm, hn);
+        gar_str al = 0;
+        u32 r = u_first_alias_a(T, W, cand, zone, nm, &al);
+        if (cand && r != GAR_NONE && (rec == GAR_NONE || r < rec)) {
+          rec = r;
+          rec_alias = al;
+        }
       }
-      if (rec == GAR_NONE) {
-        s.put(GAR_OP_HEAD(GAR_OP_R53_CREATE, GAR_CTRL_R53, kind), i, GAR_R53_SUB(j, k), zone, acc, GAR_NONE);
-        created = true;
-      } else {
-        // needRecordsUpdate (route53.go:373-381); rec is an alias record by construction
-        Str al = mkstr(A.slab, A.rec_alias_dns[rec]);
-        bool same = al.n == acc_dns.n + 1 && al.p[al.n - 1] == '.' && streq(substr(al, 0, acc_dns.n), acc_dns);
-        if (!same) s.put(GAR_OP_HEAD(GAR_OP_R53_UPSERT_A, GAR_CTRL_R53, kind), i, GAR_R53_SUB(j, k), zone, acc, rec);
+      // needRecordsUpdate (route53.go:373-381): *AliasTarget.DNSName != *accelerator.DnsName + "."
+      bool have = more && rec != GAR_NONE;
+      Str al = have ? mkstr(A.slab, rec_alias) : Str{A.slab, 0};
+      bool shape = have && al.n == acc_dns.n + 1 && al.p[al.n - 1] == '.';
+      bool same = u_streq(shape, substr(al, 0, shape ? acc_dns.n : 0), acc_dns);
+      if (more) {
+        if (rec == GAR_NONE) {
+          s.put(GAR_OP_HEAD(GAR_OP_R53_CREATE, GAR_CTRL_R53, kind), i, GAR_R53_SUB(j, k), zone, acc, GAR_NONE);
+          created = true;
+        } else if (!same) {
+          s.put(GAR_OP_HEAD(GAR_OP_R53_UPSERT_A, GAR_CTRL_R53, kind), i, GAR_R53_SUB(j, k), zone, acc, rec);
+        }
+        k++;
       }
-      k++;
     }
-    if (created) ev |= GAR_EV_CREATED;
+    if (go && !stop && created) ev |= GAR_EV_CREATED;
   }
-  return GAR_STATUS(GAR_ST_OK, 0, ev);
+  if (ensure && !stop) result = GAR_STATUS(GAR_ST_OK, 0, ev);
+  return result;
 }
 
 // ------------------------------------------------------------------ orphans (delete events of keys that left the cache)
 
 GAR_HD bool object_in_cache(const DevTables &T, const Work &W, u32 kind, Str key) {
   Cursor c = idx_open(W.ix_obj, key_hash_kinded(kind, key));
-  for (u32 r; (r = idx_next(W.ix_obj, c)) != GAR_NONE;)
-    if (T.o.obj_kind[r] == kind && streq(object_key(T, r), key)) return true;
+  IdxEntry e;
+  while (idx_next(W.ix_obj, c, &e))
+    if (e.a0 == kind && streq(mkstr(T.o.slab, e.s0), key)) return true;
   return false;
 }
 
@@ -843,21 +1207,21 @@ GAR_HD void r53_orphan_alias(const DevTables &T, const Work &W, u32 r, OpSink &s
   Str name = mkstr(A.slab, A.rec_name[r]);
   u64 h = key_hash_zoned(zone, name);
   Cursor c = idx_open(W.ix_ovn, h);
-  for (u32 v; (v = idx_next(W.ix_ovn, c)) != GAR_NONE;) {
-    u32 vr = W.val_rec[v];
-    if (W.rec_zone[vr] != zone || !streq(mkstr(A.slab, A.rec_name[vr]), name)) continue;
+  IdxEntry e;
+  while (idx_next(W.ix_ovn, c, &e)) {
+    if (e.a1 != zone || !streq(mkstr(A.slab, e.s0), name)) continue;
     // skip if an earlier row of the bucket carries the same value under the same name
-    Str val = mkstr(A.slab, A.val_value[v]);
+    Str val = mkstr(A.slab, e.s1);
     bool dup = false;
     Cursor c2 = idx_open(W.ix_ovn, h);
-    for (u32 w; (w = idx_next(W.ix_ovn, c2)) != GAR_NONE && w < v;) {
-      u32 wr = W.val_rec[w];
-      if (W.rec_zone[wr] == zone && streq(mkstr(A.slab, A.rec_name[wr]), name) && streq(mkstr(A.slab, A.val_value[w]), val)) {
+    IdxEntry e2;
+    while (idx_next(W.ix_ovn, c2, &e2) && e2.row < e.row) {
+      if (e2.a1 == zone && streq(mkstr(A.slab, e2.s0), name) && streq(mkstr(A.slab, e2.s1), val)) {
         dup = true;
         break;
       }
     }
     if (dup) continue;
-    s.put(GAR_OP_HEAD(GAR_OP_R53_DELETE_RECORD, GAR_CTRL_R53, 0), GAR_NONE, 0, zone, r, v);
+    s.put(GAR_OP_HEAD(GAR_OP_R53_DELETE_RECORD, GAR_CTRL_R53, 0), GAR_NONE, 0, zone, r, e.row);
   }
 }

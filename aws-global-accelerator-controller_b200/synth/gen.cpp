@@ -291,7 +291,7 @@ void add_accel(Snapshot &S, const Gen &G, const std::string &arn_id, const std::
                const std::string &thost, const std::string &cluster, const std::vector<std::pair<std::string, std::string>> &user_tags, int n_lis,
                const std::vector<int32_t> &ports, bool udp, int n_eg, const std::string &endpoint) {
   std::string arn = "arn:aws:globalaccelerator::123456789012:accelerator/" + arn_id;
-  S.acc_arn.push_back(S.as.put(arn));
+  S.acc_arn.push_back(0);  // ARNs stay on the host side: the diff never reads them
   S.acc_name.push_back(S.as.put(name));
   S.acc_dns.push_back(S.as.put(dns));
   S.acc_enabled.push_back(enabled ? 1 : 0);
@@ -310,12 +310,12 @@ void add_accel(Snapshot &S, const Gen &G, const std::string &arn_id, const std::
   S.tag_b.push_back((uint32_t)S.tag_key.size());
   for (int l = 0; l < n_lis; l++) {
     std::string larn = arn + "/listener/" + hexs(mix(S.lis_arn.size(), 5), 8);
-    S.lis_arn.push_back(S.as.put(larn));
+    S.lis_arn.push_back(0);
     S.lis_proto.push_back(udp ? GAR_PROTO_UDP : GAR_PROTO_TCP);
     for (int32_t p : ports) S.pr_from.push_back(p);
     S.pr_b.push_back((uint32_t)S.pr_from.size());
     for (int e = 0; e < n_eg; e++) {
-      S.eg_arn.push_back(S.as.put(larn + "/endpoint-group/" + hexs(mix(S.eg_arn.size(), 9), 12)));
+      S.eg_arn.push_back(0);
       S.ep_id.push_back(S.as.put(endpoint));
       S.ep_b.push_back((uint32_t)S.ep_id.size());
     }
@@ -532,7 +532,7 @@ Snapshot *generate(const gsyn_config &cfg) {
     S.rec_b.push_back(0);
     S.val_b.push_back(0);
     for (uint32_t z = 0; z < nz; z++) {
-      S.zone_id.push_back(S.as.put("/hostedzone/Z" + hexs(mix(cfg.seed, 900 + z), 13)));
+      S.zone_id.push_back(0);
       S.zone_name.push_back(S.as.put(G.zone_name(z) + "."));
       for (auto &rc : zr[z]) {
         S.rec_name.push_back(S.as.put(rc.name));
@@ -579,7 +579,6 @@ Snapshot *generate(const gsyn_config &cfg) {
   a.lb_arn = S.lb_arn.data();
   a.lb_state = S.lb_state.data();
   a.n_accels = (uint32_t)S.acc_arn.size();
-  a.acc_arn = S.acc_arn.data();
   a.acc_name = S.acc_name.data();
   a.acc_dns = S.acc_dns.data();
   a.acc_enabled = S.acc_enabled.data();
@@ -589,19 +588,16 @@ Snapshot *generate(const gsyn_config &cfg) {
   a.tag_key = S.tag_key.data();
   a.tag_val = S.tag_val.data();
   a.n_listeners = (uint32_t)S.lis_arn.size();
-  a.lis_arn = S.lis_arn.data();
   a.lis_proto = S.lis_proto.data();
   a.lis_pr_begin = S.pr_b.data();
   a.lis_eg_begin = S.eg_b.data();
   a.n_port_ranges = (uint32_t)S.pr_from.size();
   a.pr_from = S.pr_from.data();
   a.n_egs = (uint32_t)S.eg_arn.size();
-  a.eg_arn = S.eg_arn.data();
   a.eg_ep_begin = S.ep_b.data();
   a.n_endpoints = (uint32_t)S.ep_id.size();
   a.ep_id = S.ep_id.data();
   a.n_zones = (uint32_t)S.zone_name.size();
-  a.zone_id = S.zone_id.data();
   a.zone_name = S.zone_name.data();
   a.zone_rec_begin = S.rec_b.data();
   a.n_records = (uint32_t)S.rec_name.size();

@@ -167,7 +167,7 @@ def pack(objects: list[dict], actual: dict | None = None) -> Snapshot:
     eg_arn, ep_b, ep_id = [], [0], []
     # strings are laid out accelerator-row-major: accelerator, its tags, its listeners, their egs
     for x in accs:
-        acc_arn.append(sl.put(x["arn"]))
+        acc_arn.append(0)
         acc_name.append(sl.put(x.get("name", "")))
         acc_dns.append(sl.put(x.get("dns", "")))
         acc_en.append(1 if x.get("enabled", True) else 0)
@@ -176,19 +176,18 @@ def pack(objects: list[dict], actual: dict | None = None) -> Snapshot:
             tag_v.append(sl.put(tv))
         tag_b.append(len(tag_k))
         for li in x.get("listeners", []):
-            lis_arn.append(sl.put(li["arn"]))
+            lis_arn.append(0)
             lis_proto.append(abi.PROTO_UDP if li.get("proto", "TCP") == "UDP" else abi.PROTO_TCP)
             pr_from.extend(int(p) for p in li.get("ports", []))
             pr_b.append(len(pr_from))
             for eg in li.get("egs", []):
-                eg_arn.append(sl.put(eg["arn"]))
+                eg_arn.append(0)
                 for e in eg.get("endpoints", []):
                     ep_id.append(sl.put(e))
                 ep_b.append(len(ep_id))
             eg_b.append(len(eg_arn))
         lis_b.append(len(lis_arn))
     a.n_accels = len(accs)
-    snap._set(a, "acc_arn", acc_arn, u64, C.c_uint64)
     snap._set(a, "acc_name", acc_name, u64, C.c_uint64)
     snap._set(a, "acc_dns", acc_dns, u64, C.c_uint64)
     snap._set(a, "acc_enabled", acc_en, u8, C.c_uint8)
@@ -198,14 +197,12 @@ def pack(objects: list[dict], actual: dict | None = None) -> Snapshot:
     snap._set(a, "tag_key", tag_k, u64, C.c_uint64)
     snap._set(a, "tag_val", tag_v, u64, C.c_uint64)
     a.n_listeners = len(lis_arn)
-    snap._set(a, "lis_arn", lis_arn, u64, C.c_uint64)
     snap._set(a, "lis_proto", lis_proto, u8, C.c_uint8)
     snap._set(a, "lis_pr_begin", pr_b, u32, C.c_uint32)
     snap._set(a, "lis_eg_begin", eg_b, u32, C.c_uint32)
     a.n_port_ranges = len(pr_from)
     snap._set(a, "pr_from", pr_from, i32, C.c_int32)
     a.n_egs = len(eg_arn)
-    snap._set(a, "eg_arn", eg_arn, u64, C.c_uint64)
     snap._set(a, "eg_ep_begin", ep_b, u32, C.c_uint32)
     a.n_endpoints = len(ep_id)
     snap._set(a, "ep_id", ep_id, u64, C.c_uint64)
@@ -214,7 +211,7 @@ def pack(objects: list[dict], actual: dict | None = None) -> Snapshot:
     z_id, z_name, rec_b = [], [], [0]
     r_name, r_type, r_has, r_alias, val_b, v_val = [], [], [], [], [0], []
     for z in zones:
-        z_id.append(sl.put(z.get("id", "")))
+        z_id.append(0)
         z_name.append(sl.put(z["name"]))
         for r in z.get("records", []):
             r_name.append(sl.put(r["name"]))
@@ -227,7 +224,6 @@ def pack(objects: list[dict], actual: dict | None = None) -> Snapshot:
             val_b.append(len(v_val))
         rec_b.append(len(r_name))
     a.n_zones = len(zones)
-    snap._set(a, "zone_id", z_id, u64, C.c_uint64)
     snap._set(a, "zone_name", z_name, u64, C.c_uint64)
     snap._set(a, "zone_rec_begin", rec_b, u32, C.c_uint32)
     a.n_records = len(r_name)

@@ -103,11 +103,11 @@ def _table_arrays(abi, o, a):
            (o.obj_ann_begin, n + 1, 4), (o.obj_lbi_begin, n + 1, 4), (o.obj_port_begin, n + 1, 4), (o.ann_key, o.n_ann, 8), (o.ann_val, o.n_ann, 8),
            (o.lbi_hostname, o.n_lbi, 8), (o.port_number, o.n_ports, 4), (o.port_proto, o.n_ports, 8), (o.slab, o.slab_len + 32, 1),
            (a.lb_region, a.n_lbs, 8), (a.lb_name, a.n_lbs, 8), (a.lb_dns, a.n_lbs, 8), (a.lb_arn, a.n_lbs, 8), (a.lb_state, a.n_lbs, 1),
-           (a.acc_arn, a.n_accels, 8), (a.acc_name, a.n_accels, 8), (a.acc_dns, a.n_accels, 8), (a.acc_enabled, a.n_accels, 1),
+           (a.acc_name, a.n_accels, 8), (a.acc_dns, a.n_accels, 8), (a.acc_enabled, a.n_accels, 1),
            (a.acc_tag_begin, a.n_accels + 1, 4), (a.acc_lis_begin, a.n_accels + 1, 4), (a.tag_key, a.n_tags, 8), (a.tag_val, a.n_tags, 8),
-           (a.lis_arn, a.n_listeners, 8), (a.lis_proto, a.n_listeners, 1), (a.lis_pr_begin, a.n_listeners + 1, 4), (a.lis_eg_begin, a.n_listeners + 1, 4),
-           (a.pr_from, a.n_port_ranges, 4), (a.eg_arn, a.n_egs, 8), (a.eg_ep_begin, a.n_egs + 1, 4), (a.ep_id, a.n_endpoints, 8),
-           (a.zone_id, a.n_zones, 8), (a.zone_name, a.n_zones, 8), (a.zone_rec_begin, a.n_zones + 1, 4), (a.rec_name, a.n_records, 8),
+           (a.lis_proto, a.n_listeners, 1), (a.lis_pr_begin, a.n_listeners + 1, 4), (a.lis_eg_begin, a.n_listeners + 1, 4),
+           (a.pr_from, a.n_port_ranges, 4), (a.eg_ep_begin, a.n_egs + 1, 4), (a.ep_id, a.n_endpoints, 8),
+           (a.zone_name, a.n_zones, 8), (a.zone_rec_begin, a.n_zones + 1, 4), (a.rec_name, a.n_records, 8),
            (a.rec_type, a.n_records, 1), (a.rec_has_alias, a.n_records, 1), (a.rec_alias_dns, a.n_records, 8), (a.rec_val_begin, a.n_records + 1, 4),
            (a.val_value, a.n_values, 8), (a.slab, a.slab_len + 32, 1)]
     return out

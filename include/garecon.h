@@ -105,6 +105,9 @@ enum { GAR_PROTO_TCP = 0, GAR_PROTO_UDP = 1 };
 /* rec_type — route53types.RRType; only A is distinguished by the path (route53.go:362) */
 enum { GAR_RR_OTHER = 0, GAR_RR_A = 1, GAR_RR_TXT = 2, GAR_RR_CNAME = 3, GAR_RR_AAAA = 4 };
 
+/* Only columns the decisions read are part of the ABI.  Identifiers the executor needs to CALL AWS with
+   (accelerator / listener / endpoint-group ARNs, hosted-zone ids) stay on the Go side, addressed by the row
+   indices the ops carry. */
 typedef struct gar_actual {
   /* ELBv2 DescribeLoadBalancers, every region listed (load_balancer.go:13-30).  A lookup is by
      (region, name); with duplicates the first row wins, as `range res.LoadBalancers` does. */
@@ -116,7 +119,6 @@ typedef struct gar_actual {
   const uint8_t *lb_state;
   /* Global Accelerator: ListAccelerators order (global_accelerator.go:624-641) */
   uint32_t n_accels;
-  const gar_str *acc_arn;
   const gar_str *acc_name;
   const gar_str *acc_dns;
   const uint8_t *acc_enabled;
@@ -126,21 +128,18 @@ typedef struct gar_actual {
   const gar_str *tag_key;
   const gar_str *tag_val;
   uint32_t n_listeners;
-  const gar_str *lis_arn;
   const uint8_t *lis_proto;
   const uint32_t *lis_pr_begin;    /* [n_listeners+1] -> pr_from: Listener.PortRanges[] */
   const uint32_t *lis_eg_begin;    /* [n_listeners+1] -> eg_*: ListEndpointGroups(listener) order (:885-898) */
   uint32_t n_port_ranges;
   const int32_t *pr_from;          /* PortRange.FromPort — the only field the comparison reads (:460-462) */
   uint32_t n_egs;
-  const gar_str *eg_arn;
   const uint32_t *eg_ep_begin;     /* [n_egs+1] -> ep_id: EndpointDescriptions[] */
   uint32_t n_endpoints;
   const gar_str *ep_id;            /* EndpointDescription.EndpointId (:496) */
   /* Route53: ListHostedZones order (route53.go:199-214); records in ListResourceRecordSets order (:317-333).
      A by-name zone lookup takes the first row whose name matches exactly (:349-353). */
   uint32_t n_zones;
-  const gar_str *zone_id;
   const gar_str *zone_name;        /* with trailing dot, as AWS returns it */
   const uint32_t *zone_rec_begin;  /* [n_zones+1] -> rec_* */
   uint32_t n_records;

@@ -9,7 +9,60 @@
 #include <string>
 #include <vector>
 
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+
 #include "../../aws-global-accelerator-controller_b200/csrc/gar_pipeline.h"
+
+// ---- warp emulation: for_each_warp runs every group of 32 lanes on 32 host threads; GAR_ANY is a barrier vote.
+// A vote that not all 32 lanes reach (a lane finished, or never arrives) would hang the real GPU: here it is
+// detected and reported, so vote-uniformity of the device code is checked on the CPU tier.
+struct WarpCtx {
+  std::mutex m;
+  std::condition_variable cv;
+  int arrived = 0, finished = 0;
+  unsigned generation = 0;
+  bool acc = false, result = false, error = false;
+  bool vote(bool p) {
+    std::unique_lock<std::mutex> lk(m);
+    if (error) return false;
+    if (finished > 0) {  // a lane already left the kernel: this vote can never complete on a GPU
+      error = true;
+      cv.notify_all();
+      return false;
+    }
+    acc = acc || p;
+    if (++arrived == 32) {
+      result = acc;
+      acc = false;
+      arrived = 0;
+      generation++;
+      cv.notify_all();
+      return result;
+    }
+    unsigned gen = generation;
+    cv.wait(lk, [&] { return generation != gen || error; });
+    return error ? false : result;
+  }
+  void finish() {
+    std::unique_lock<std::mutex> lk(m);
+    finished++;
+    if (arrived > 0) {  // others are waiting in a vote this lane will never join
+      error = true;
+      cv.notify_all();
+    }
+  }
+};
+static thread_local WarpCtx *tl_warp = nullptr;
+static bool g_vote_outside_warp = false, g_nonuniform_vote = false;
+bool gar_host_vote(bool p) {
+  if (!tl_warp) {
+    g_vote_outside_warp = true;  // GAR_ANY used in a kernel that is not warp-synchronous
+    return p;
+  }
+  return tl_warp->vote(p);
+}
 
 struct HBuf {
   std::vector<uint64_t> mem;
@@ -35,6 +88,23 @@ struct gar_engine {
   void for_each(const char *, u32 n, const F &f) {
     launches++;
     for (u32 i = 0; i < n; i++) f(i);
+  }
+  template <class F>
+  void for_each_warp(const char *, u32 n, const F &f) {
+    launches++;
+    for (u32 base = 0; base < n; base += 32) {
+      WarpCtx ctx;
+      std::thread lanes[32];
+      for (u32 l = 0; l < 32; l++)
+        lanes[l] = std::thread([&, l] {
+          tl_warp = &ctx;
+          f(base + l, base + l < n);
+          ctx.finish();
+          tl_warp = nullptr;
+        });
+      for (auto &t : lanes) t.join();
+      if (ctx.error) g_nonuniform_vote = true;
+    }
   }
   void fill32(u32 *p, u32 v, size_t n) { std::fill(p, p + n, v); }
   void copy32(u32 *d, const u32 *s, size_t n) { memcpy(d, s, n * 4); }
@@ -107,7 +177,13 @@ int gar_diff(gar_engine *e, gar_changeset *out) {
   e->launches = 0;
   Pipeline<gar_engine> P(*e, e->T);
   DiffCounts dc{};
+  g_vote_outside_warp = g_nonuniform_vote = false;
   int rc = P.run(&dc, [&](u64 nops) { return e->o_ops.ensure(sizeof(gar_op) * (size_t)(nops + 1)); });
+  if (g_nonuniform_vote || g_vote_outside_warp) {
+    e->err = g_nonuniform_vote ? "non-uniform warp vote: some lane did not reach a GAR_ANY that others executed (would hang on the GPU)"
+                               : "GAR_ANY executed outside a warp-synchronous kernel";
+    return GAR_E_STATE;
+  }
   if (rc != GAR_OK) {
     e->err = "objects layout rule violated";
     return rc;
