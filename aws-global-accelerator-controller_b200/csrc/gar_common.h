@@ -51,10 +51,8 @@ GAR_HD u64 ld64u(const u8 *p) {
   uintptr_t a = (uintptr_t)p;
   const u64 *q = (const u64 *)(a & ~(uintptr_t)7);
   unsigned sh = (unsigned)(a & 7) * 8;
-  u64 lo = q[0];
-  if (sh == 0) return lo;
-  u64 hi = q[1];
-  return (lo >> sh) | (hi << (64 - sh));
+  u64 lo = q[0], hi = q[1];
+  return (lo >> sh) | ((hi << 1) << (63 - sh));  // branch-free: for sh == 0 the second term shifts out entirely
 }
 GAR_HD u64 lowmask(u32 nbytes) { return nbytes >= 8 ? ~0ull : ((1ull << (nbytes * 8)) - 1); }
 

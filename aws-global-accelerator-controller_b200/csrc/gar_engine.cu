@@ -563,6 +563,10 @@ static void do_diff(gar_engine *e, gar_changeset *out, bool to_host) {
   DiffCounts dc{};
   CK(cudaEventRecord(e->ev[2], e->stream));
   int rc = P.run(&dc, [&](u64 nops) { return e->dev_ensure(e->d_ops, sizeof(gar_op) * (size_t)(nops + 1)); });
+  if (rc == GAR_RETRY_WITH_RADIX) {  // some hash bucket was too large for the per-bucket build: redo with the stable radix sort
+    P.force_radix = true;
+    rc = P.run(&dc, [&](u64 nops) { return e->dev_ensure(e->d_ops, sizeof(gar_op) * (size_t)(nops + 1)); });
+  }
   CK(cudaEventRecord(e->ev[3], e->stream));
   if (rc == GAR_E_INVALID) {
     CK(cudaStreamSynchronize(e->stream));

@@ -15,6 +15,9 @@
 //   void download(void *host_dst, const void *dev_src, size_t bytes);       // blocking
 #pragma once
 
+#include <stdio.h>
+#include <stdlib.h>
+
 #include "gar_rows.h"
 
 #if defined(__CUDA_ARCH__)
@@ -29,7 +32,8 @@ enum Slot {
   S_DERIVED, S_OFLAGS, S_OKEY_HASH, S_STAGE_GA, S_STAGE_R53, S_ANN_R53, S_ANN_NAME, S_ANN_TAGS, S_ANN_LISTEN, S_DPORT_BEGIN, S_DPORTS,
   S_TOK_CODE, S_TOK_NAME, S_TOK_REGION,
   S_ACC_FLAGS, S_ACC_OWNER_KEY, S_ACC_OWNER, S_ACC_THOST, S_ACC_MANAGED,
-  S_REC_ZONE, S_VAL_REC, S_VAL_CLS, S_VAL_KEY, S_VAL_ORPHAN,
+  S_REC_ZONE, S_VAL_REC, S_VAL_CLS, S_VAL_KEY, S_VAL_ORPHAN, S_VAL_ALIAS_ROW, S_VAL_ALIAS_DNS,
+  S_R53_MODE, S_R53_ACC, S_R53_ACC_DNS, S_PAIR_BEGIN, S_PAIR_OBJ, S_PAIR_HN, S_PAIR_CODE, S_PAIR_ZONE, S_PAIR_REC,
   S_IX_LB, S_IX_OWNER = S_IX_LB + 3, S_IX_THOST = S_IX_OWNER + 3, S_IX_ZONE = S_IX_THOST + 3, S_IX_VAL = S_IX_ZONE + 3,
   S_IX_ALIAS = S_IX_VAL + 3, S_IX_OBJ = S_IX_ALIAS + 3, S_IX_OVN = S_IX_OBJ + 3,
   S_SORT_KEYS = S_IX_OVN + 3, S_SORT_VALS, S_SORT_KEYS_ALT, S_SORT_VALS_ALT, S_SORT_TAGS,
@@ -188,6 +192,63 @@ struct FKeyOvn {
     o.put(v, valid, valid ? key_hash_zoned(W.rec_zone[r], mkstr(T.a.slab, T.a.rec_name[r])) : 0);
   }
 };
+// Index build, fast path: rows are dropped into their bucket with an atomic cursor (any order), then one thread per
+// bucket sorts its handful of rows by row id and writes the entries.  The result is identical to a stable sort.
+// Buckets larger than IDX_SMALL_BUCKET (a hot key / adversarial input) raise `overflow`; the pipeline then rebuilds
+// that index with the stable radix sort.
+constexpr u32 IDX_SMALL_BUCKET = 48;
+struct FBucketFill {
+  const u32 *keys;
+  const u32 *begin;  // scanned
+  u32 *cursor;       // [nb] zeroed
+  u32 *rows;         // [n_valid] out: unsorted row ids, grouped by bucket
+  u32 nb;
+  GAR_HD void operator()(u32 i) const {
+    u32 k = keys[i];
+    if (k == nb) return;
+#if defined(__CUDA_ARCH__)
+    u32 slot = atomicAdd(&cursor[k], 1u);
+#else
+    u32 slot = cursor[k]++;
+#endif
+    rows[begin[k] + slot] = i;
+  }
+};
+template <class EntF>
+struct FBucketFinalize {
+  const u32 *begin;
+  const u32 *rows;
+  EntF entf;
+  u32 *overflow;
+  GAR_HD void operator()(u32 b) const {
+    u32 lo = begin[b], m = begin[b + 1] - lo;
+    if (m == 0) return;
+    if (m > IDX_SMALL_BUCKET) {
+      GAR_ATOMIC_ADD(overflow, 1u);
+      return;
+    }
+    u32 r[IDX_SMALL_BUCKET];
+    for (u32 k = 0; k < m; k++) {  // insertion sort by row id
+      u32 x = rows[lo + k];
+      u32 j = k;
+      while (j > 0 && r[j - 1] > x) {
+        r[j] = r[j - 1];
+        j--;
+      }
+      r[j] = x;
+    }
+    for (u32 k = 0; k < m; k++) entf.fill(lo + k, r[k]);
+  }
+};
+template <class EntF>
+struct FSortedFinalize {  // radix fallback: position p of the sorted order holds row vals[p]
+  const u32 *vals;
+  const u32 *nvalid;
+  EntF entf;
+  GAR_HD void operator()(u32 p) const {
+    if (p < *nvalid) entf.fill(p, vals[p]);
+  }
+};
 struct FHistogram {
   const u32 *keys;
   u32 *counts;
@@ -199,10 +260,8 @@ struct FHistogram {
 };
 // --- entry fill: position p of the sorted order -> 32-byte entry (payload conventions: gar_rows.h "index probes")
 struct EntOut {
-  const u32 *vals, *tags;
+  const u32 *tags;
   IdxEntry *ent;
-  const u32 *nvalid;  // device: number of indexed rows (sorted positions beyond it hold rows that are not indexed)
-  GAR_HD bool live(u32 p) const { return p < *nvalid; }
   GAR_HD void put(u32 p, u32 row, u32 a0, u32 a1, u64 s0, u64 s1) const {
     IdxEntry e;
     e.tag = tags[row];
@@ -217,9 +276,7 @@ struct EntOut {
 struct FEntLb {
   DevTables T;
   EntOut o;
-  GAR_HD void operator()(u32 p) const {
-    if (!o.live(p)) return;
-    u32 r = o.vals[p];
+  GAR_HD void fill(u32 p, u32 r) const {
     o.put(p, r, T.a.lb_state[r], 0, T.a.lb_name[r], T.a.lb_region[r]);
   }
 };
@@ -227,9 +284,7 @@ struct FEntOwner {
   DevTables T;
   Work W;
   EntOut o;
-  GAR_HD void operator()(u32 p) const {
-    if (!o.live(p)) return;
-    u32 r = o.vals[p];
+  GAR_HD void fill(u32 p, u32 r) const {
     o.put(p, r, W.acc_flags[r], 0, W.acc_owner_key[r], 0);
   }
 };
@@ -237,18 +292,14 @@ struct FEntThost {
   DevTables T;
   Work W;
   EntOut o;
-  GAR_HD void operator()(u32 p) const {
-    if (!o.live(p)) return;
-    u32 r = o.vals[p];
+  GAR_HD void fill(u32 p, u32 r) const {
     o.put(p, r, 0, 0, W.acc_thost[r], T.a.acc_dns[r]);
   }
 };
 struct FEntZone {
   DevTables T;
   EntOut o;
-  GAR_HD void operator()(u32 p) const {
-    if (!o.live(p)) return;
-    u32 r = o.vals[p];
+  GAR_HD void fill(u32 p, u32 r) const {
     o.put(p, r, 0, 0, T.a.zone_name[r], 0);
   }
 };
@@ -256,30 +307,26 @@ struct FEntVal {
   DevTables T;
   Work W;
   EntOut o;
-  GAR_HD void operator()(u32 p) const {
-    if (!o.live(p)) return;
-    u32 v = o.vals[p];
+  GAR_HD void fill(u32 p, u32 v) const {
     u32 rec = W.val_rec[v];
     u32 kind = (W.val_cls[v] & VAL_OWNER_INGRESS) ? 1u : 0u;
-    o.put(p, v, rec, W.rec_zone[rec] | (kind << 31), W.val_key[v], T.a.rec_name[rec]);
+    Str nm = mkstr(T.a.slab, T.a.rec_name[rec]);
+    u32 bs = find_byte(nm, 0, '\\') < nm.n ? VALNAME_HAS_BACKSLASH : 0u;
+    o.put(p, v, rec, W.rec_zone[rec] | bs | (kind << 31), W.val_key[v], T.a.rec_name[rec]);
   }
 };
 struct FEntAlias {
   DevTables T;
   Work W;
   EntOut o;
-  GAR_HD void operator()(u32 p) const {
-    if (!o.live(p)) return;
-    u32 r = o.vals[p];
+  GAR_HD void fill(u32 p, u32 r) const {
     o.put(p, r, W.rec_zone[r], T.a.rec_type[r], T.a.rec_name[r], T.a.rec_alias_dns[r]);
   }
 };
 struct FEntObj {
   DevTables T;
   EntOut o;
-  GAR_HD void operator()(u32 p) const {
-    if (!o.live(p)) return;
-    u32 i = o.vals[p];
+  GAR_HD void fill(u32 p, u32 i) const {
     gar_str ns = T.o.obj_ns[i];
     o.put(p, i, T.o.obj_kind[i], 0, GAR_STR(GAR_STR_OFF(ns), GAR_STR_LEN(ns) + 1 + GAR_STR_LEN(T.o.obj_name[i])), 0);
   }
@@ -288,9 +335,7 @@ struct FEntOvn {
   DevTables T;
   Work W;
   EntOut o;
-  GAR_HD void operator()(u32 p) const {
-    if (!o.live(p)) return;
-    u32 v = o.vals[p];
+  GAR_HD void fill(u32 p, u32 v) const {
     u32 rec = W.val_rec[v];
     o.put(p, v, rec, W.rec_zone[rec], T.a.rec_name[rec], T.a.val_value[v]);
   }
@@ -298,9 +343,11 @@ struct FEntOvn {
 struct FGather5 {
   const u32 *src;
   u32 idx[5];
+  const u32 *extra;
   u32 *dst;
-  GAR_HD void operator()(u32 k) const { dst[k] = src[idx[k]]; }
+  GAR_HD void operator()(u32 k) const { dst[k] = k < 5 ? src[idx[k]] : *extra; }
 };
+#define GAR_RETRY_WITH_RADIX 1000  // Pipeline::run: rebuild with force_radix (not an error)
 struct FGatherHeader {
   const u32 *ndports, *errflag;
   u32 *dst;
@@ -354,12 +401,33 @@ struct FR53Obj {
   u32 *status;
   GAR_HD void operator()(u32 i, bool valid) const {
     OpSink s{stage + (size_t)i * OPS_STAGE_CAP, 0, OPS_STAGE_CAP};
-    u32 st = r53_reconcile(T, W, i, valid, s);
+    u32 st = r53_combine(T, W, i, valid, valid ? status[i] : 0, s);
     if (valid) {
       status[i] = st;
       counts[L.r53_obj(i)] = s.n;
     }
   }
+};
+struct FLinkValueAlias {
+  DevTables T;
+  Work W;
+  GAR_HD void operator()(u32 v) const { link_value_alias(T, W, v); }
+};
+struct FR53Prepare {
+  DevTables T;
+  Work W;
+  u32 *status;
+  GAR_HD void operator()(u32 i, bool valid) const { r53_prepare(T, W, i, valid, status); }
+};
+struct FR53FillPairs {
+  DevTables T;
+  Work W;
+  GAR_HD void operator()(u32 i) const { r53_fill_pairs(T, W, i); }
+};
+struct FR53Pair {
+  DevTables T;
+  Work W;
+  GAR_HD void operator()(u32 p, bool valid) const { r53_pair(T, W, p, valid); }
 };
 struct FCompactOps {
   DevTables T;
@@ -473,29 +541,43 @@ struct Pipeline {
   B &be;
   DevTables T;
   Work W{};
+  bool force_radix = false;  // set when a bucket exceeded IDX_SMALL_BUCKET in the previous attempt
   explicit Pipeline(B &b, const DevTables &t) : be(b), T(t) {}
 
+  // nb: buckets (power of two).  load: target rows per bucket used to size nb from the row count.
   template <class KeyF, class EntF>
-  HashIdx build_index(int slot, u32 nrows, KeyF keyf, EntF entf) {
-    u32 nb = next_pow2(nrows < 16 ? 16 : nrows);
+  HashIdx build_index(int slot, u32 nrows, u32 load, KeyF keyf, EntF entf, u32 *overflow, bool force_radix) {
+    u32 nb = next_pow2(nrows / load < 16 ? 16 : nrows / load);
     u32 *keys = (u32 *)be.ensure(S_SORT_KEYS, sizeof(u32) * (size_t)(nrows + 1));
     u32 *vals = (u32 *)be.ensure(S_SORT_VALS, sizeof(u32) * (size_t)(nrows + 1));
-    u32 *keys2 = (u32 *)be.ensure(S_SORT_KEYS_ALT, sizeof(u32) * (size_t)(nrows + 1));
-    u32 *vals2 = (u32 *)be.ensure(S_SORT_VALS_ALT, sizeof(u32) * (size_t)(nrows + 1));
     u32 *tags = (u32 *)be.ensure(S_SORT_TAGS, sizeof(u32) * (size_t)(nrows + 1));
     u32 *begin = (u32 *)be.ensure(slot + 0, sizeof(u32) * (size_t)(nb + 2));
     IdxEntry *ent = (IdxEntry *)be.ensure(slot + 1, sizeof(IdxEntry) * (size_t)(nrows + 1));
     keyf.o = IdxOut{keys, vals, tags, nb - 1, nb};
+    entf.o = EntOut{tags, ent};
     be.fill32(begin, 0, nb + 2);
     if (nrows) {
       be.for_each("idx_keys", nrows, keyf);
       be.for_each("idx_histogram", nrows, FHistogram{keys, begin, nb});
     }
     be.exclusive_scan(begin, nb + 2);  // begin[b] = #rows with key < b; begin[nb] = #indexed rows
-    if (nrows) {
+    if (nrows && !force_radix) {
+      u32 *cursor = (u32 *)be.ensure(S_SORT_KEYS_ALT, sizeof(u32) * (size_t)(nb + 1));
+      be.fill32(cursor, 0, nb);
+      be.for_each("idx_bucket_fill", nrows, FBucketFill{keys, begin, cursor, vals, nb});
+      be.for_each("idx_bucket_finalize", nb, FBucketFinalize<EntF>{begin, vals, entf, overflow});
+#if !defined(__CUDACC__)
+      if (getenv("GAR_DEBUG_INDEX")) {
+        u32 mx = 0;
+        for (u32 b = 0; b < nb; b++) mx = begin[b + 1] - begin[b] > mx ? begin[b + 1] - begin[b] : mx;
+        fprintf(stderr, "index slot %d: rows %u buckets %u indexed %u max bucket %u overflow %u\n", slot, nrows, nb, begin[nb], mx, *overflow);
+      }
+#endif
+    } else if (nrows) {
+      u32 *keys2 = (u32 *)be.ensure(S_SORT_KEYS_ALT, sizeof(u32) * (size_t)(nrows + 1));
+      u32 *vals2 = (u32 *)be.ensure(S_SORT_VALS_ALT, sizeof(u32) * (size_t)(nrows + 1));
       be.sort_pairs(keys, vals, keys2, vals2, nrows, ilog2(nb) + 1);
-      entf.o = EntOut{vals, tags, ent, begin + nb};
-      be.for_each("idx_entries", nrows, entf);
+      be.for_each("idx_entries", nrows, FSortedFinalize<EntF>{vals, begin + nb, entf});
     }
     return HashIdx{begin, ent, nb - 1};
   }
@@ -527,6 +609,12 @@ struct Pipeline {
     W.val_cls = (u8 *)be.ensure(S_VAL_CLS, nval + 1);
     W.val_key = (gar_str *)be.ensure(S_VAL_KEY, 8 * (size_t)(nval + 1));
     W.val_orphan = (u8 *)be.ensure(S_VAL_ORPHAN, nval + 1);
+    W.val_alias_row = (u32 *)be.ensure(S_VAL_ALIAS_ROW, 4 * (size_t)(nval + 1));
+    W.val_alias_dns = (gar_str *)be.ensure(S_VAL_ALIAS_DNS, 8 * (size_t)(nval + 1));
+    W.r53_mode = (u8 *)be.ensure(S_R53_MODE, (size_t)n + 1);
+    W.r53_acc = (u32 *)be.ensure(S_R53_ACC, 4 * (size_t)(n + 1));
+    W.r53_acc_dns = (gar_str *)be.ensure(S_R53_ACC_DNS, 8 * (size_t)(n + 1));
+    W.pair_begin = (u32 *)be.ensure(S_PAIR_BEGIN, 4 * (size_t)(n + 2));
     u32 *errflag = (u32 *)be.ensure(S_ERRFLAG, 64);
     be.fill32(errflag, 0, 4);
 
@@ -552,15 +640,17 @@ struct Pipeline {
     if (n && hdr[0]) be.for_each("listen_ports_write", n, FJsonWrite{T, W});
 
     // stage 3: hash indexes
-    W.ix_lb = build_index(S_IX_LB, T.a.n_lbs, FKeyLb{T, {}}, FEntLb{T, {}});
-    W.ix_owner = build_index(S_IX_OWNER, nacc, FKeyOwner{T, W, {}}, FEntOwner{T, W, {}});
-    W.ix_thost = build_index(S_IX_THOST, nacc, FKeyThost{T, W, {}}, FEntThost{T, W, {}});
-    W.ix_zone = build_index(S_IX_ZONE, nzone, FKeyZone{T, {}}, FEntZone{T, {}});
-    W.ix_val = build_index(S_IX_VAL, nval, FKeyVal{T, W, {}}, FEntVal{T, W, {}});
-    W.ix_alias = build_index(S_IX_ALIAS, nrec, FKeyAlias{T, W, {}}, FEntAlias{T, W, {}});
-    W.ix_obj = build_index(S_IX_OBJ, n, FKeyObj{T, W, {}}, FEntObj{T, {}});
+    u32 *overflow = errflag + 1;
+    W.ix_lb = build_index(S_IX_LB, T.a.n_lbs, 1, FKeyLb{T, {}}, FEntLb{T, {}}, overflow, force_radix);
+    W.ix_owner = build_index(S_IX_OWNER, nacc, 1, FKeyOwner{T, W, {}}, FEntOwner{T, W, {}}, overflow, force_radix);
+    W.ix_thost = build_index(S_IX_THOST, nacc, 1, FKeyThost{T, W, {}}, FEntThost{T, W, {}}, overflow, force_radix);
+    W.ix_zone = build_index(S_IX_ZONE, nzone, 1, FKeyZone{T, {}}, FEntZone{T, {}}, overflow, force_radix);
+    W.ix_val = build_index(S_IX_VAL, nval, 1, FKeyVal{T, W, {}}, FEntVal{T, W, {}}, overflow, force_radix);
+    W.ix_alias = build_index(S_IX_ALIAS, nrec, 2, FKeyAlias{T, W, {}}, FEntAlias{T, W, {}}, overflow, force_radix);
+    if (nval) be.for_each("link_value_alias", nval, FLinkValueAlias{T, W});
+    W.ix_obj = build_index(S_IX_OBJ, n, 1, FKeyObj{T, W, {}}, FEntObj{T, {}}, overflow, force_radix);
     if (nval) be.for_each("mark_orphan_values", nval, FMarkOrphanValue{T, W});
-    W.ix_ovn = build_index(S_IX_OVN, nval, FKeyOvn{T, W, {}}, FEntOvn{T, W, {}});
+    W.ix_ovn = build_index(S_IX_OVN, nval, 8, FKeyOvn{T, W, {}}, FEntOvn{T, W, {}}, overflow, force_radix);
 
     // stage 4: evaluate every object once (status + count + staged ops); count the orphan sections
     CountLayout L{n, nacc, nrec, nval};
@@ -572,14 +662,30 @@ struct Pipeline {
     u32 *st_r53 = (u32 *)be.out_status_r53(n);
     if (n) be.for_each_warp("ga_objects", n, FGaObj{T, W, L, counts, stage_ga, st_ga});
     if (nacc) be.for_each("ga_orphans_count", nacc, FGaOrphan{T, W, L, counts, nullptr});
+    // route53 ensure in relational form: per object -> (object, hostname) pairs -> per object
+    be.fill32(W.pair_begin, 0, (size_t)n + 1);
+    if (n) be.for_each_warp("r53_prepare", n, FR53Prepare{T, W, st_r53});
+    be.exclusive_scan(W.pair_begin, n + 1);
+    u32 npairs = 0;
+    be.download(&npairs, W.pair_begin + n, 4);
+    W.pair_obj = (u32 *)be.ensure(S_PAIR_OBJ, 4 * (size_t)(npairs + 1));
+    W.pair_hn = (gar_str *)be.ensure(S_PAIR_HN, 8 * (size_t)(npairs + 1));
+    W.pair_code = (u8 *)be.ensure(S_PAIR_CODE, (size_t)npairs + 1);
+    W.pair_zone = (u32 *)be.ensure(S_PAIR_ZONE, 4 * (size_t)(npairs + 1));
+    W.pair_rec = (u32 *)be.ensure(S_PAIR_REC, 4 * (size_t)(npairs + 1));
+    if (npairs) {
+      be.for_each("r53_fill_pairs", n, FR53FillPairs{T, W});
+      be.for_each_warp("r53_pairs", npairs, FR53Pair{T, W});
+    }
     if (n) be.for_each_warp("r53_objects", n, FR53Obj{T, W, L, counts, stage_r53, st_r53});
     if (nrec) be.for_each("r53_orphan_alias_count", nrec, FR53OrphanAlias{T, W, L, counts, nullptr});
     if (nval) be.for_each("r53_orphan_value_count", nval, FR53OrphanValue{T, W, L, counts, nullptr});
     be.exclusive_scan(counts, L.total() + 1);
-    u32 sec[5];
+    u32 sec[6];
     u32 *secdev = errflag + 8;  // same small scratch buffer
-    be.for_each("gather_section_begins", 5, FGather5{counts, {0, L.ga_orph(0), L.r53_obj(0), L.base0(), L.total()}, secdev});
+    be.for_each("gather_section_begins", 6, FGather5{counts, {0, L.ga_orph(0), L.r53_obj(0), L.base0(), L.total()}, overflow, secdev});
     be.download(sec, secdev, sizeof(sec));
+    if (sec[5] && !force_radix) return GAR_RETRY_WITH_RADIX;  // an index bucket was too large for the fast build
     for (int k = 0; k < 5; k++) dc->section_begin[k] = sec[k];
     dc->n_ops = sec[4];
 

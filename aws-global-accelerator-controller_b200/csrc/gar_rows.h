@@ -33,6 +33,15 @@ enum {
   ACC_HAS_MANAGED = 1u << 4, ACC_HAS_OWNER = 1u << 5, ACC_HAS_THOST = 1u << 6,
 };
 
+// r53_mode: how the route53 decisions of an object are evaluated
+enum {
+  R53_MODE_DONE = 0,   // status final after r53_prepare (ignored / early status), no ops
+  R53_MODE_PAIRS = 1,  // one lbIngress with a usable accelerator: hostnames are evaluated as (object, hostname) pairs
+  R53_MODE_OBJECT = 2, // everything else (cleanup, several lbIngress): the per-object routine r53_reconcile
+};
+enum { PAIR_IN_SYNC = 0, PAIR_CREATE = 1, PAIR_UPSERT = 2, PAIR_NO_ZONE = 3 };
+#define VALNAME_HAS_BACKSLASH (1u << 30)  // ix_val entry a1 bit: the record name contains a backslash (possible \052 escape)
+
 // per-value-row class: is this ResourceRecord value an owner value of this cluster?
 enum { VAL_NOT_OWNER = 0, VAL_OWNER_SERVICE = 1, VAL_OWNER_INGRESS = 2, VAL_OWNER_3PART = 4 };
 
@@ -61,6 +70,18 @@ struct Work {
   u8 *val_cls;    // [n_values] VAL_*
   gar_str *val_key;  // [n_values] "<ns>/<name>" part of an owner value
   u8 *val_orphan;    // [n_values] 1 = owner value of this cluster whose object is not in the cache
+  u32 *val_alias_row;     // [n_values] owner values: first alias record of type A under the same (zone, name), or GAR_NONE
+  gar_str *val_alias_dns; // [n_values] its AliasTarget.DNSName
+  // route53 ensure, relational form (objects with exactly one lbIngress)
+  u8 *r53_mode;        // [n] R53_MODE_*
+  u32 *r53_acc;        // [n] the accelerator found by target hostname
+  gar_str *r53_acc_dns;// [n] its DnsName
+  u32 *pair_begin;     // [n+1] (object, hostname) pairs, CSR
+  u32 *pair_obj;       // [n_pairs]
+  gar_str *pair_hn;    // [n_pairs] the k-th piece of strings.Split(annotation, ",")
+  u8 *pair_code;       // [n_pairs] PAIR_*
+  u32 *pair_zone;      // [n_pairs]
+  u32 *pair_rec;       // [n_pairs]
   // indexes
   HashIdx ix_lb;     // (region, name) -> LB rows
   HashIdx ix_owner;  // (kind, "ns/name") -> accelerators that are ACC_MINE and ACC_OWNER_KEYED
@@ -936,7 +957,7 @@ GAR_HD void owned_collect(const DevTables &T, const Work &W, u64 okh, u32 kind, 
   IdxEntry e;
   while (idx_next(W.ix_val, c, &e)) {
     if (!owned_match(T, e, kind, key)) continue;
-    if (o.n < OWNED_CACHE) o.hit[o.n] = OwnedHit{e.row, e.a0, e.a1 & 0x7FFFFFFFu, e.s1};
+    if (o.n < OWNED_CACHE) o.hit[o.n] = OwnedHit{e.row, e.a0, e.a1 & 0x3FFFFFFFu, e.s1};
     o.n++;
   }
 }
@@ -956,7 +977,7 @@ GAR_HD void u_owned_collect(const DevTables &T, const Work &W, bool active, u64 
       hit = e.tag == c.tag && (e.a1 >> 31) == kind;
     }
     if (u_streq(hit, hit ? mkstr(T.a.slab, e.s0) : Str{T.a.slab, 0}, key)) {
-      if (o.n < OWNED_CACHE) o.hit[o.n] = OwnedHit{e.row, e.a0, e.a1 & 0x7FFFFFFFu, e.s1};
+      if (o.n < OWNED_CACHE) o.hit[o.n] = OwnedHit{e.row, e.a0, e.a1 & 0x3FFFFFFFu, e.s1};
       o.n++;
     }
   }
@@ -970,7 +991,7 @@ GAR_HD OwnedHit owned_get(const DevTables &T, const Work &W, const Owned &o, u32
   while (idx_next(W.ix_val, c, &e)) {
     if (!owned_match(T, e, o.kind, o.key)) continue;
     if (seen++ == k) {
-      h = OwnedHit{e.row, e.a0, e.a1 & 0x7FFFFFFFu, e.s1};
+      h = OwnedHit{e.row, e.a0, e.a1 & 0x3FFFFFFFu, e.s1};
       break;
     }
   }
@@ -1164,6 +1185,183 @@ GAR_HD u32 r53_reconcile(const DevTables &T, const Work &W, u32 i, bool valid, O
   }
   if (ensure && !stop) result = GAR_STATUS(GAR_ST_OK, 0, ev);
   return result;
+}
+
+// ------------------------------------------------------------------ (a9) Route53 ensure, relational form
+//
+// The same decisions as r53_reconcile for the common shape (one lbIngress), split into uniform data-parallel steps:
+//   link_value_alias  per owner value row : first alias A record under the same (zone, name)       [build side, once]
+//   r53_prepare       per object          : filter, accelerator by target hostname, number of hostnames
+//   r53_fill_pairs    per object          : (object, k, hostname slice) rows
+//   r53_pair          per (object, k)     : GetHostedZone + findARecord over the object's owned names + needRecordsUpdate
+//   r53_combine       per object          : replay the pair results in order (first NO_ZONE ends the stream), emit ops
+// Objects of any other shape go through r53_reconcile inside r53_combine.
+
+GAR_HD void link_value_alias(const DevTables &T, const Work &W, u32 v) {
+  u32 row = GAR_NONE;
+  gar_str dns = 0;
+  if (W.val_cls[v] != VAL_NOT_OWNER) {
+    u32 rec = W.val_rec[v];
+    row = first_alias_a(T, W, W.rec_zone[rec], mkstr(T.a.slab, T.a.rec_name[rec]), &dns);
+  }
+  W.val_alias_row[v] = row;
+  W.val_alias_dns[v] = dns;
+}
+
+// warp-synchronous.  Writes r53_mode, r53_acc, r53_acc_dns, pair count (into pair_begin[i]) and, for objects that
+// are finished here, the status word.
+GAR_HD void r53_prepare(const DevTables &T, const Work &W, u32 i, bool valid, u32 *status) {
+  const gar_objects &o = T.o;
+  u32 mode = R53_MODE_DONE, st = GAR_STATUS(GAR_ST_IGNORED, 0, 0), npairs = 0;
+  bool probe = false;
+  Str lbhost{o.slab, 0}, hostnames{o.slab, 0};
+  if (valid) {
+    u32 dv = W.derived[i];
+    if (dv & GAR_DV_R53_ELIGIBLE) {
+      u32 jb = o.obj_lbi_begin[i], nj = o.obj_lbi_begin[i + 1] - jb;
+      if (!(dv & GAR_DV_R53_ANNOTATED) || nj > 1) {
+        mode = R53_MODE_OBJECT;
+      } else if (nj == 0) {
+        st = GAR_STATUS(GAR_ST_OK, 0, 0);  // annotated, no lbIngress: the loop body never runs (route53/service.go:73)
+      } else {
+        u32 code = W.tok_code[jb];
+        if (code == GAR_TOK_PANIC) st = GAR_STATUS(GAR_ST_PANIC, 0, 0);
+        else if (code == GAR_TOK_NOT_AWS) st = GAR_STATUS(GAR_ST_OK, 0, 0);
+        else if (code >= GAR_TOK_ERR_NOT_ELB) st = GAR_STATUS(GAR_ST_ERR_RETRY, GAR_D_NOT_ELB + (code - GAR_TOK_ERR_NOT_ELB), 0);
+        else {
+          probe = true;
+          lbhost = mkstr(o.slab, o.lbi_hostname[jb]);
+          hostnames = mkstr(o.slab, W.ann_r53[i]);
+        }
+      }
+    }
+  }
+  u32 acc = GAR_NONE;
+  gar_str acc_dns = 0;
+  u32 nacc = u_find_by_hostname(T, W, probe, lbhost, &acc, &acc_dns);
+  bool go = false;
+  if (probe) {
+    if (nacc > 1) st = GAR_STATUS(GAR_ST_REQUEUE_60S, GAR_D_ACCEL_MANY, 0);
+    else if (nacc == 0) st = GAR_STATUS(GAR_ST_REQUEUE_60S, GAR_D_ACCEL_NONE, 0);
+    else go = true;
+  }
+  // number of pieces of strings.Split(annotation, ",") = commas + 1
+  u32 pos = 0;
+  for (;;) {
+    bool more = go && pos <= hostnames.n;
+    if (!GAR_ANY(more)) break;
+    u32 comma = u_find_byte(more, hostnames, pos, ',');
+    if (more) {
+      npairs++;
+      pos = comma + 1;
+    }
+  }
+  if (go) mode = R53_MODE_PAIRS;
+  if (valid) {
+    W.r53_mode[i] = (u8)mode;
+    W.r53_acc[i] = acc;
+    W.r53_acc_dns[i] = acc_dns;
+    W.pair_begin[i] = npairs;
+    if (mode == R53_MODE_DONE) status[i] = st;
+  }
+}
+
+GAR_HD void r53_fill_pairs(const DevTables &T, const Work &W, u32 i) {
+  if (W.r53_mode[i] != R53_MODE_PAIRS) return;
+  gar_str ref = W.ann_r53[i];
+  Str hostnames = mkstr(T.o.slab, ref);
+  u32 p = W.pair_begin[i], pos = 0;
+  Str piece;
+  while (next_piece(hostnames, &pos, &piece)) {
+    W.pair_obj[p] = i;
+    W.pair_hn[p] = GAR_STR(GAR_STR_OFF(ref) + (u64)(piece.p - hostnames.p), piece.n);
+    p++;
+  }
+}
+
+// warp-synchronous; one lane per (object, hostname)
+GAR_HD void r53_pair(const DevTables &T, const Work &W, u32 p, bool valid) {
+  const gar_actual &A = T.a;
+  u32 i = 0, kind = 0;
+  Str hn{T.o.slab, 0}, okey{T.o.slab, 0};
+  u64 okh = 0;
+  if (valid) {
+    i = W.pair_obj[p];
+    hn = mkstr(T.o.slab, W.pair_hn[p]);
+    kind = T.o.obj_kind[i];
+    okey = object_key(T, i);
+    okh = W.okey_hash[i];
+  }
+  u32 zone = u_find_hosted_zone(T, W, valid, hn);
+  bool live = valid && zone != GAR_NONE;
+  // findARecord over FindOwneredARecordSets: among the owner-value rows of this object in `zone` whose record name
+  // unescapes to hostname + ".", the smallest first-alias-A row (route53.go:216-238,360-367)
+  u32 rec = GAR_NONE;
+  gar_str rec_alias = 0;
+  Cursor c = u_open(W.ix_val, live, okh);
+  for (; GAR_ANY(c.pos < c.end);) {
+    IdxEntry e;
+    bool hit = false;
+    if (c.pos < c.end) {
+      e = load_entry(W.ix_val.ent + c.pos++);
+      hit = e.tag == c.tag && (e.a1 >> 31) == kind && (e.a1 & 0x3FFFFFFFu) == zone;
+    }
+    bool mine = u_streq(hit, hit ? mkstr(A.slab, e.s0) : Str{A.slab, 0}, okey);
+    Str nm = mine ? mkstr(A.slab, e.s1) : Str{A.slab, 0};
+    bool plain = mine && !(e.a1 & VALNAME_HAS_BACKSLASH);
+    bool shape = plain && nm.n == hn.n + 1 && nm.p[nm.n - 1] == '.';
+    bool match = u_streq(shape, substr(nm, 0, shape ? hn.n : 0), hn);
+    if (mine && !plain) match = record_name_matches(nm, hn);  // possible \052 escape: scalar, rare
+    if (match) {
+      u32 r = W.val_alias_row[e.row];
+      if (r != GAR_NONE && (rec == GAR_NONE || r < rec)) {
+        rec = r;
+        rec_alias = W.val_alias_dns[e.row];
+      }
+    }
+  }
+  // needRecordsUpdate (route53.go:373-381)
+  bool have = live && rec != GAR_NONE;
+  Str acc_dns = have ? mkstr(A.slab, W.r53_acc_dns[i]) : Str{A.slab, 0};
+  Str al = have ? mkstr(A.slab, rec_alias) : Str{A.slab, 0};
+  bool shape = have && al.n == acc_dns.n + 1 && al.p[al.n - 1] == '.';
+  bool same = u_streq(shape, substr(al, 0, shape ? acc_dns.n : 0), acc_dns);
+  if (valid) {
+    u32 code = !live ? PAIR_NO_ZONE : rec == GAR_NONE ? PAIR_CREATE : same ? PAIR_IN_SYNC : PAIR_UPSERT;
+    W.pair_code[p] = (u8)code;
+    W.pair_zone[p] = zone;
+    W.pair_rec[p] = rec;
+  }
+}
+
+// warp-synchronous (objects in R53_MODE_OBJECT call the voted r53_reconcile)
+GAR_HD u32 r53_combine(const DevTables &T, const Work &W, u32 i, bool valid, u32 prev_status, OpSink &s) {
+  u32 mode = valid ? W.r53_mode[i] : R53_MODE_DONE;
+  u32 st = prev_status;
+  bool slow = mode == R53_MODE_OBJECT;
+  if (GAR_ANY(slow)) {
+    u32 r = r53_reconcile(T, W, i, slow, s);
+    if (slow) st = r;
+  }
+  if (mode == R53_MODE_PAIRS) {
+    u32 kind = T.o.obj_kind[i], acc = W.r53_acc[i];
+    bool created = false, stop = false;
+    u32 k = 0;
+    for (u32 p = W.pair_begin[i]; p < W.pair_begin[i + 1] && !stop; p++, k++) {
+      u32 code = W.pair_code[p];
+      if (code == PAIR_NO_ZONE) {
+        st = GAR_STATUS(GAR_ST_ERR_RETRY, GAR_D_NO_HOSTED_ZONE, 0);
+        stop = true;
+      } else if (code == PAIR_CREATE) {
+        s.put(GAR_OP_HEAD(GAR_OP_R53_CREATE, GAR_CTRL_R53, kind), i, GAR_R53_SUB(0, k), W.pair_zone[p], acc, GAR_NONE);
+        created = true;
+      } else if (code == PAIR_UPSERT) {
+        s.put(GAR_OP_HEAD(GAR_OP_R53_UPSERT_A, GAR_CTRL_R53, kind), i, GAR_R53_SUB(0, k), W.pair_zone[p], acc, W.pair_rec[p]);
+      }
+    }
+    if (!stop) st = GAR_STATUS(GAR_ST_OK, 0, created ? GAR_EV_CREATED : 0);
+  }
+  return st;
 }
 
 // ------------------------------------------------------------------ orphans (delete events of keys that left the cache)

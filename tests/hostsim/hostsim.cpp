@@ -179,6 +179,10 @@ int gar_diff(gar_engine *e, gar_changeset *out) {
   DiffCounts dc{};
   g_vote_outside_warp = g_nonuniform_vote = false;
   int rc = P.run(&dc, [&](u64 nops) { return e->o_ops.ensure(sizeof(gar_op) * (size_t)(nops + 1)); });
+  if (rc == GAR_RETRY_WITH_RADIX) {
+    P.force_radix = true;
+    rc = P.run(&dc, [&](u64 nops) { return e->o_ops.ensure(sizeof(gar_op) * (size_t)(nops + 1)); });
+  }
   if (g_nonuniform_vote || g_vote_outside_warp) {
     e->err = g_nonuniform_vote ? "non-uniform warp vote: some lane did not reach a GAR_ANY that others executed (would hang on the GPU)"
                                : "GAR_ANY executed outside a warp-synchronous kernel";

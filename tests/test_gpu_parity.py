@@ -83,3 +83,16 @@ def test_bad_string_reference_is_an_error(garecon, engine):
     snap.arrays["ann_val"][0] = (100 << garecon.abi.OFF_BITS) | 5
     with pytest.raises(garecon.GarError):
         engine.load(snap)
+
+
+def test_hot_keys_force_the_fallback_paths(garecon, oracle, engine):
+    """> 16 duplicates per hash bucket (radix-sort fallback of the index build), > 4 ops per object (re-evaluation
+    in the compaction pass), > 8 owned value rows (bucket re-walk): all must stay bit-exact."""
+    import hotkeys
+    objects, actual = hotkeys.make()
+    snap = garecon.pack(objects, actual)
+    engine.load(snap)
+    got = engine.diff()
+    want = oracle.diff(snap, "default", mode=1)
+    assert got.diff(want) == [], got.describe_first_mismatch(want)
+    assert len(got.ops) > 200

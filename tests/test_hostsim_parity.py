@@ -48,3 +48,42 @@ def test_hostsim_other_cluster_name(garecon, oracle):
     want = oracle.diff(snap, "prod-1", mode=1)
     assert got.diff(want) == [], got.describe_first_mismatch(want)
     assert len(got.ops) > 10
+
+
+def test_hostsim_hot_keys_force_the_fallback_paths(garecon, oracle, hostsim):
+    import hotkeys
+    objects, actual = hotkeys.make()
+    snap = garecon.pack(objects, actual)
+    hostsim.load(snap)
+    got = hostsim.diff()
+    want = oracle.diff(snap, "default", mode=1)
+    faithful = oracle.diff(snap, "default", mode=0)
+    assert want.diff(faithful) == []
+    assert got.diff(want) == [], got.describe_first_mismatch(want)
+    assert len(got.ops) > 200
+
+
+def test_warp_emulation_catches_a_non_uniform_vote(garecon):
+    """The hostsim warp emulator must flag a GAR_ANY that not every lane reaches (it would hang a real GPU)."""
+    import ctypes, subprocess, tempfile, textwrap
+    from pathlib import Path
+    repo = Path(__file__).resolve().parent.parent
+    src = textwrap.dedent(r'''
+        #define main hostsim_unused_main
+        #include "tests/hostsim/hostsim.cpp"
+        #undef main
+        struct Bad { GAR_HD void operator()(u32 i, bool valid) const { if (i % 2 == 0) (void)GAR_ANY(true); } };
+        struct Good { GAR_HD void operator()(u32 i, bool valid) const { for (u32 k = 0; GAR_ANY(k < i % 5); k++) {} } };
+        extern "C" int probe(int which) {
+          gar_engine e;
+          g_nonuniform_vote = false;
+          if (which) e.for_each_warp("bad", 64, Bad{}); else e.for_each_warp("good", 64, Good{});
+          return g_nonuniform_vote ? 1 : 0;
+        }
+    ''')
+    with tempfile.TemporaryDirectory() as d:
+        (Path(d) / "t.cpp").write_text(src)
+        subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-pthread", "-I", str(repo), "-o", f"{d}/t.so", f"{d}/t.cpp"], check=True)
+        lib = ctypes.CDLL(f"{d}/t.so")
+        assert lib.probe(0) == 0
+        assert lib.probe(1) == 1
