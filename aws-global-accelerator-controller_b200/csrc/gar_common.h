@@ -28,6 +28,7 @@ bool gar_host_vote(bool p);  // tests/hostsim: 32 host threads emulate a warp; a
 #endif
 
 typedef uint8_t u8;
+typedef uint16_t u16;
 typedef uint32_t u32;
 typedef uint64_t u64;
 typedef int32_t i32;
@@ -69,31 +70,30 @@ GAR_HD bool streq(Str a, Str b) {
   return true;
 }
 
-// equality with a short literal held in registers/constant space (byte loop; literals are <= 80 bytes)
-GAR_HD bool streq_lit(Str a, const char *lit, u32 n) {
-  if (a.n != n) return false;
-  for (u32 i = 0; i < n; i++)
-    if (a.p[i] != (u8)lit[i]) return false;
+// Comparisons with string literals: the literal is packed into 8-byte words at compile time (constant-folded), the
+// string side is read 8 bytes per step; no byte loops.
+GAR_HD constexpr u64 lit_word(const char *lit, u32 n, u32 i) {
+  u64 w = 0;
+  for (u32 k = 0; k < 8 && i + k < n; k++) w |= (u64)(u8)lit[i + k] << (8 * k);
+  return w;
+}
+// a[off .. off+n) == lit, given off + n <= a.n
+template <u32 N>
+GAR_HD bool lit_eq_at(Str a, u32 off, const char (&lit)[N]) {
+  constexpr u32 n = N - 1;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (u32 i = 0; i < n; i += 8) {
+    u64 w = ld64u(a.p + off + i);
+    if (n - i < 8) w &= lowmask(n - i);
+    if (w != lit_word(lit, n, i)) return false;
+  }
   return true;
 }
-#define STREQ_LIT(s, lit) streq_lit((s), (lit), (u32)(sizeof(lit) - 1))
-
-GAR_HD bool has_prefix_lit(Str a, const char *lit, u32 n) {
-  if (a.n < n) return false;
-  for (u32 i = 0; i < n; i++)
-    if (a.p[i] != (u8)lit[i]) return false;
-  return true;
-}
-#define HAS_PREFIX_LIT(s, lit) has_prefix_lit((s), (lit), (u32)(sizeof(lit) - 1))
-
-GAR_HD bool has_suffix_lit(Str a, const char *lit, u32 n) {
-  if (a.n < n) return false;
-  const u8 *p = a.p + (a.n - n);
-  for (u32 i = 0; i < n; i++)
-    if (p[i] != (u8)lit[i]) return false;
-  return true;
-}
-#define HAS_SUFFIX_LIT(s, lit) has_suffix_lit((s), (lit), (u32)(sizeof(lit) - 1))
+#define STREQ_LIT(s, lit) ((s).n == (u32)(sizeof(lit) - 1) && lit_eq_at((s), 0, lit))
+#define HAS_PREFIX_LIT(s, lit) ((s).n >= (u32)(sizeof(lit) - 1) && lit_eq_at((s), 0, lit))
+#define HAS_SUFFIX_LIT(s, lit) ((s).n >= (u32)(sizeof(lit) - 1) && lit_eq_at((s), (s).n - (u32)(sizeof(lit) - 1), lit))
 
 // ------------------------------------------------------------------ SWAR byte search (8 bytes per step)
 
@@ -116,6 +116,24 @@ GAR_HD u32 find_byte(Str s, u32 from, u8 c) {
     if (m) return i + (ctz64(m) >> 3);
   }
   return s.n;
+}
+// exact per-byte equality mask (0x80 in every byte of w equal to c; unlike swar_eq_mask, exact in every position)
+GAR_HD u64 swar_eq_exact(u64 w, u8 c) {
+  u64 x = w ^ (0x0101010101010101ull * c);
+  return ~(((x & 0x7F7F7F7F7F7F7F7Full) + 0x7F7F7F7F7F7F7F7Full) | x) & 0x8080808080808080ull;
+}
+// 0x80 in every byte b of w with lo <= b <= hi; all bytes of w must be < 0x80 (caller checks), 0 < lo <= hi < 0x80
+GAR_HD u64 swar_in_range(u64 w, u8 lo, u8 hi) {
+  u64 ge = w + 0x0101010101010101ull * (u8)(0x80 - lo);
+  u64 le = 0x0101010101010101ull * (u8)(0x80 | hi) - w;
+  return ge & le & 0x8080808080808080ull;
+}
+GAR_HD u32 clz64(u64 x) {
+#if defined(__CUDA_ARCH__)
+  return (u32)__clzll((long long)x);
+#else
+  return (u32)__builtin_clzll(x);
+#endif
 }
 GAR_HD u32 count_byte(Str s, u8 c) {  // byte-exact count (the SWAR mask can over-report bytes above the first hit, so count per byte)
   u32 n = 0;

@@ -31,8 +31,8 @@
 enum Slot {
   S_DERIVED, S_OFLAGS, S_OKEY_HASH, S_STAGE_GA, S_STAGE_R53, S_ANN_R53, S_ANN_NAME, S_ANN_TAGS, S_ANN_LISTEN, S_DPORT_BEGIN, S_DPORTS,
   S_TOK_CODE, S_TOK_NAME, S_TOK_REGION,
-  S_ACC_FLAGS, S_ACC_OWNER_KEY, S_ACC_OWNER, S_ACC_THOST, S_ACC_MANAGED,
-  S_REC_ZONE, S_VAL_REC, S_VAL_CLS, S_VAL_KEY, S_VAL_ORPHAN, S_VAL_ALIAS_ROW, S_VAL_ALIAS_DNS,
+  S_ACC_FLAGS, S_ACC_OWNER_KEY, S_ACC_OWNER, S_ACC_THOST, S_ACC_MANAGED, S_ACC_OWNER_HASH, S_ACC_THOST_HASH, S_REC_NAME_HASH, S_VAL_KEY_HASH,
+  S_REC_ZONE, S_VAL_REC, S_VAL_CLS, S_VAL_KEY, S_VAL_ORPHAN, S_VAL_LINK, S_ACC_DIGEST,
   S_R53_MODE, S_R53_ACC, S_R53_ACC_DNS, S_PAIR_BEGIN, S_PAIR_OBJ, S_PAIR_HN, S_PAIR_CODE, S_PAIR_ZONE, S_PAIR_REC,
   S_IX_LB, S_IX_OWNER = S_IX_LB + 3, S_IX_THOST = S_IX_OWNER + 3, S_IX_ZONE = S_IX_THOST + 3, S_IX_VAL = S_IX_ZONE + 3,
   S_IX_ALIAS = S_IX_VAL + 3, S_IX_OBJ = S_IX_ALIAS + 3, S_IX_OVN = S_IX_OBJ + 3,
@@ -79,6 +79,21 @@ struct FExpand {
       else hi = mid;
     }
     parent_of[c] = lo;
+  }
+};
+// record row -> zone row, and the hash of the record name (every (zone, name) key is derived from it)
+struct FPrepareRecord {
+  DevTables T;
+  Work W;
+  GAR_HD void operator()(u32 r) const {
+    u32 lo = 0, hi = T.a.n_zones;
+    while (hi - lo > 1) {
+      u32 mid = (lo + hi) >> 1;
+      if (T.a.zone_rec_begin[mid] <= r) lo = mid;
+      else hi = mid;
+    }
+    W.rec_zone[r] = lo;
+    W.rec_name_hash[r] = gar_hash(mkstr(T.a.slab, T.a.rec_name[r]));
   }
 };
 struct FClassifyValue {
@@ -132,8 +147,7 @@ struct FKeyOwner {
   GAR_HD void operator()(u32 i) const {
     u32 fl = W.acc_flags[i];
     bool valid = (fl & ACC_MINE) && (fl & ACC_OWNER_KEYED);
-    u64 h = valid ? key_hash_kinded((fl & ACC_OWNER_INGRESS) ? 1u : 0u, mkstr(T.a.slab, W.acc_owner_key[i])) : 0;
-    o.put(i, valid, h);
+    o.put(i, valid, W.acc_owner_hash[i]);
   }
 };
 struct FKeyThost {
@@ -142,7 +156,7 @@ struct FKeyThost {
   IdxOut o;
   GAR_HD void operator()(u32 i) const {
     bool valid = (W.acc_flags[i] & ACC_MINE) != 0;
-    o.put(i, valid, valid ? key_hash_str(mkstr(T.a.slab, W.acc_thost[i])) : 0);
+    o.put(i, valid, W.acc_thost_hash[i]);
   }
 };
 struct FKeyZone {
@@ -161,7 +175,7 @@ struct FKeyVal {
   GAR_HD void operator()(u32 v) const {
     u32 cls = W.val_cls[v];
     bool valid = cls != VAL_NOT_OWNER;
-    o.put(v, valid, valid ? key_hash_kinded((cls & VAL_OWNER_INGRESS) ? 1u : 0u, mkstr(T.a.slab, W.val_key[v])) : 0);
+    o.put(v, valid, W.val_key_hash[v]);
   }
 };
 struct FKeyAlias {
@@ -170,7 +184,7 @@ struct FKeyAlias {
   IdxOut o;
   GAR_HD void operator()(u32 r) const {
     bool valid = T.a.rec_has_alias[r] != 0;
-    o.put(r, valid, valid ? key_hash_zoned(W.rec_zone[r], mkstr(T.a.slab, T.a.rec_name[r])) : 0);
+    o.put(r, valid, key_hash_zoned_h(W.rec_zone[r], W.rec_name_hash[r]));
   }
 };
 struct FKeyObj {
@@ -189,7 +203,7 @@ struct FKeyOvn {
   GAR_HD void operator()(u32 v) const {
     bool valid = W.val_orphan[v] != 0;
     u32 r = W.val_rec[v];
-    o.put(v, valid, valid ? key_hash_zoned(W.rec_zone[r], mkstr(T.a.slab, T.a.rec_name[r])) : 0);
+    o.put(v, valid, key_hash_zoned_h(W.rec_zone[r], W.rec_name_hash[r]));
   }
 };
 // Index build, fast path: rows are dropped into their bucket with an atomic cursor (any order), then one thread per
@@ -604,13 +618,17 @@ struct Pipeline {
     W.acc_owner = (gar_str *)be.ensure(S_ACC_OWNER, 8 * (size_t)(nacc + 1));
     W.acc_thost = (gar_str *)be.ensure(S_ACC_THOST, 8 * (size_t)(nacc + 1));
     W.acc_managed = (gar_str *)be.ensure(S_ACC_MANAGED, 8 * (size_t)(nacc + 1));
+    W.acc_owner_hash = (u64 *)be.ensure(S_ACC_OWNER_HASH, 8 * (size_t)(nacc + 1));
+    W.acc_thost_hash = (u64 *)be.ensure(S_ACC_THOST_HASH, 8 * (size_t)(nacc + 1));
+    W.rec_name_hash = (u64 *)be.ensure(S_REC_NAME_HASH, 8 * (size_t)(nrec + 1));
+    W.val_key_hash = (u64 *)be.ensure(S_VAL_KEY_HASH, 8 * (size_t)(nval + 1));
     W.rec_zone = (u32 *)be.ensure(S_REC_ZONE, 4 * (size_t)(nrec + 1));
     W.val_rec = (u32 *)be.ensure(S_VAL_REC, 4 * (size_t)(nval + 1));
     W.val_cls = (u8 *)be.ensure(S_VAL_CLS, nval + 1);
     W.val_key = (gar_str *)be.ensure(S_VAL_KEY, 8 * (size_t)(nval + 1));
     W.val_orphan = (u8 *)be.ensure(S_VAL_ORPHAN, nval + 1);
-    W.val_alias_row = (u32 *)be.ensure(S_VAL_ALIAS_ROW, 4 * (size_t)(nval + 1));
-    W.val_alias_dns = (gar_str *)be.ensure(S_VAL_ALIAS_DNS, 8 * (size_t)(nval + 1));
+    W.val_link = (ValLink *)be.ensure(S_VAL_LINK, sizeof(ValLink) * (size_t)(nval + 1));
+    W.acc_digest = (AccDigest *)be.ensure(S_ACC_DIGEST, sizeof(AccDigest) * (size_t)(nacc + 1));
     W.r53_mode = (u8 *)be.ensure(S_R53_MODE, (size_t)n + 1);
     W.r53_acc = (u32 *)be.ensure(S_R53_ACC, 4 * (size_t)(n + 1));
     W.r53_acc_dns = (gar_str *)be.ensure(S_R53_ACC_DNS, 8 * (size_t)(n + 1));
@@ -622,7 +640,7 @@ struct Pipeline {
     if (n) be.for_each("classify_objects", n, FClassify{T, W, derived_public, oflags, errflag});
     if (nlbi) be.for_each("tokenise_hostnames", nlbi, FTokenise{T, W});
     if (nacc) be.for_each("digest_accelerators", nacc, FDigestAccel{T, W});
-    if (nrec) be.for_each("expand_rec_zone", nrec, FExpand{T.a.zone_rec_begin, nzone, W.rec_zone});
+    if (nrec) be.for_each("prepare_records", nrec, FPrepareRecord{T, W});
     if (nval) be.for_each("expand_val_rec", nval, FExpand{T.a.rec_val_begin, nrec, W.val_rec});
     if (nval) be.for_each("classify_values", nval, FClassifyValue{T, W});
 

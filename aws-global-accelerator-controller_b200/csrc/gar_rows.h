@@ -45,6 +45,34 @@ enum { PAIR_IN_SYNC = 0, PAIR_CREATE = 1, PAIR_UPSERT = 2, PAIR_NO_ZONE = 3 };
 // per-value-row class: is this ResourceRecord value an owner value of this cluster?
 enum { VAL_NOT_OWNER = 0, VAL_OWNER_SERVICE = 1, VAL_OWNER_INGRESS = 2, VAL_OWNER_3PART = 4 };
 
+// Everything the Global Accelerator decisions read about one accelerator besides its strings, gathered into ONE
+// 64-byte record by the streaming digest pass: the probe side then pays one DRAM burst instead of a dozen scattered
+// column reads (acc_enabled, acc_name, acc_lis_begin, lis_proto, lis_pr_begin, pr_from, lis_eg_begin, eg_ep_begin, ep_id ...).
+struct alignas(64) AccDigest {
+  u32 flags;     // ACC_* | ACCD_*
+  u32 lis;       // first listener row (valid if >= 1 listener)
+  u32 eg;        // first endpoint-group row of that listener (valid if >= 1)
+  u32 pr_begin;  // port ranges of that listener
+  u32 ep_begin;  // endpoint descriptions of that endpoint group
+  u16 n_ports, n_eps;
+  i32 port0, port1;  // the first two FromPorts inline
+  gar_str name;       // Accelerator.Name
+  gar_str thost;      // target-hostname tag value
+  gar_str owner_key;  // owner tag value minus "service/" | "ingress/"
+  gar_str ep0;        // first EndpointDescription.EndpointId
+};
+enum {
+  ACCD_ENABLED = 1u << 8,
+  ACCD_MANAGED_TRUE = 1u << 9,     // managed tag value == "true"
+  ACCD_LIS_NONE = 1u << 10, ACCD_LIS_MANY = 1u << 11,
+  ACCD_LIS_UDP = 1u << 12,
+  ACCD_EG_NONE = 1u << 13, ACCD_EG_MANY = 1u << 14,
+};
+struct alignas(16) ValLink {  // per owner value row: first alias A record under the same (zone, name)
+  u32 alias_row, pad;
+  gar_str alias_dns;
+};
+
 struct Work {
   // objects
   u32 *derived;        // [n] GAR_DV_* | OBJ_*
@@ -64,14 +92,18 @@ struct Work {
   gar_str *acc_owner;      // full owner tag value ("" if missing)
   gar_str *acc_thost;      // target-hostname tag value ("" if missing)
   gar_str *acc_managed;    // managed tag value
+  AccDigest *acc_digest;   // [n_accels]
+  u64 *acc_owner_hash;     // key_hash_kinded(kind, owner key) for ACC_OWNER_KEYED rows
+  u64 *acc_thost_hash;     // gar_hash(target hostname)
   // route53 expansion
   u32 *rec_zone;  // [n_records]
+  u64 *rec_name_hash;  // [n_records] gar_hash(record name): every (zone, name) key is derived from it
   u32 *val_rec;   // [n_values]
   u8 *val_cls;    // [n_values] VAL_*
   gar_str *val_key;  // [n_values] "<ns>/<name>" part of an owner value
+  u64 *val_key_hash; // [n_values] key_hash_kinded(kind, val_key) for owner values
   u8 *val_orphan;    // [n_values] 1 = owner value of this cluster whose object is not in the cache
-  u32 *val_alias_row;     // [n_values] owner values: first alias record of type A under the same (zone, name), or GAR_NONE
-  gar_str *val_alias_dns; // [n_values] its AliasTarget.DNSName
+  ValLink *val_link;      // [n_values] owner values: first alias record of type A under the same (zone, name) + its DNSName
   // route53 ensure, relational form (objects with exactly one lbIngress)
   u8 *r53_mode;        // [n] R53_MODE_*
   u32 *r53_acc;        // [n] the accelerator found by target hostname
@@ -97,7 +129,8 @@ struct Work {
 
 GAR_HD u64 key_hash_kinded(u32 kind, Str nsname) { return hmix(kind + 1, gar_hash(nsname)); }
 GAR_HD u64 key_hash_lb(Str region, Str name) { return hmix(gar_hash(region), gar_hash(name)); }
-GAR_HD u64 key_hash_zoned(u32 zone, Str name) { return hmix((u64)zone + 0x100, gar_hash(name)); }
+GAR_HD u64 key_hash_zoned_h(u32 zone, u64 name_hash) { return hmix((u64)zone + 0x100, name_hash); }
+GAR_HD u64 key_hash_zoned(u32 zone, Str name) { return key_hash_zoned_h(zone, gar_hash(name)); }
 GAR_HD u64 key_hash_str(Str s) { return gar_hash(s); }
 
 // the workqueue key "ns/name" of an object row (cache.MetaNamespaceKeyFunc; reconcile.go:47).  Layout rule of
@@ -196,16 +229,19 @@ GAR_HD void classify_object(const DevTables &T, const Work &W, u32 i) {
 // DetectCloudProvider (pkg/cloudprovider/provider.go:8-17) followed by GetLBNameFromHostname and its helpers
 // (pkg/cloudprovider/aws/load_balancer.go:32-93), as a byte scanner instead of six regexps.
 
-GAR_HD bool is_word(u8 c) { return (c >= '0' && c <= '9') || (c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z') || c == '_'; }
-
-// `^([\w\-]+)\-[\w]+$`: every byte is \w or '-', and the last '-' has >= 1 byte on both sides.
-// Returns the length of group 1, or 0 when the regexp does not match.
+// `^([\\w\\-]+)\\-[\\w]+$`: every byte is \\w or '-', and the last '-' has >= 1 byte on both sides.
+// Returns the length of group 1, or 0 when the regexp does not match.  8 bytes per step: byte classes by SWAR
+// range tests ([0-9], [A-Z], [a-z], '_', '-'); bytes >= 0x80 are never \\w in RE2.
 GAR_HD u32 name_dash_id(Str s) {
   u32 last = GAR_NONE;
-  for (u32 k = 0; k < s.n; k++) {
-    u8 c = s.p[k];
-    if (c == '-') last = k;
-    else if (!is_word(c)) return 0;
+  for (u32 i = 0; i < s.n; i += 8) {
+    u64 w = load_word(s, i);
+    u64 pad = s.n - i < 8 ? ~lowmask(s.n - i) & 0x8080808080808080ull : 0;  // bytes beyond the end count as valid
+    if (w & 0x8080808080808080ull) return 0;
+    u64 dash = swar_eq_exact(w, '-') & ~pad;
+    u64 ok = swar_in_range(w, '0', '9') | swar_in_range(w, 'A', 'Z') | swar_in_range(w, 'a', 'z') | swar_eq_exact(w, '_') | dash | pad;
+    if (ok != 0x8080808080808080ull) return 0;
+    if (dash) last = i + ((63 - clz64(dash)) >> 3);
   }
   if (last == GAR_NONE || last < 1 || last + 1 >= s.n) return 0;
   return last;
@@ -217,16 +253,11 @@ GAR_HD void tokenise_hostname(const DevTables &T, const Work &W, u32 row) {
   u64 base = GAR_STR_OFF(href);
   u8 code;
   gar_str name = 0, region = 0;
-  // label boundaries: first three dots, and whether any dot exists
-  u32 d1 = GAR_NONE, d2 = GAR_NONE, d3 = GAR_NONE, ndots = 0;
-  for (u32 k = 0; k < h.n; k++)
-    if (h.p[k] == '.') {
-      if (ndots == 0) d1 = k;
-      else if (ndots == 1) d2 = k;
-      else if (ndots == 2) d3 = k;
-      ndots++;
-    }
-  if (ndots == 0) {
+  // label boundaries: the first three dots
+  u32 d1 = find_byte(h, 0, '.');
+  u32 d2 = d1 < h.n ? find_byte(h, d1 + 1, '.') : h.n;
+  u32 d3 = d2 < h.n ? find_byte(h, d2 + 1, '.') : h.n;
+  if (d1 >= h.n) {
     code = GAR_TOK_PANIC;  // parts[len(parts)-2] with a single part
   } else if (!(STREQ_LIT(h, "amazonaws.com") || HAS_SUFFIX_LIT(h, ".amazonaws.com"))) {
     code = GAR_TOK_NOT_AWS;
@@ -257,10 +288,8 @@ GAR_HD void tokenise_hostname(const DevTables &T, const Work &W, u32 row) {
     bool nlb = false;
     if (h.n >= 20) {
       for (u32 i = h.n - 20 + 1; i-- > 0;) {
-        if (h.p[i] == '.' && h.p[i + 1] == 'e' && h.p[i + 2] == 'l' && h.p[i + 3] == 'b' && h.p[i + 4] == '.') {
-          nlb = true;
-          for (u32 k = i + 5; k < h.n - 14; k++)
-            if (h.p[k] == '\n') nlb = false;
+        if (h.p[i] == '.' && lit_eq_at(h, i, ".elb.")) {
+          nlb = find_byte(substr(h, 0, h.n - 14), i + 5, '\n') >= h.n - 14;
           break;
         }
       }
@@ -331,6 +360,40 @@ GAR_HD void digest_accelerator(const DevTables &T, const Work &W, u32 a) {
     key = GAR_STR(GAR_STR_OFF(owner) + 8, ow.n - 8);
   }
   if ((fl & ACC_OWNER_KEYED) && count_slashes(mkstr(A.slab, key)) == 1) fl |= ACC_OWNER_3PART;
+  AccDigest d;
+  d.flags = fl | (A.acc_enabled[a] ? ACCD_ENABLED : 0) | (STREQ_LIT(mkstr(A.slab, managed), "true") ? ACCD_MANAGED_TRUE : 0);
+  d.lis = d.eg = d.pr_begin = d.ep_begin = 0;
+  d.n_ports = d.n_eps = 0;
+  d.port0 = d.port1 = 0;
+  d.ep0 = 0;
+  u32 lb = A.acc_lis_begin[a], le = A.acc_lis_begin[a + 1];
+  if (le == lb) d.flags |= ACCD_LIS_NONE;
+  else if (le - lb > 1) d.flags |= ACCD_LIS_MANY;
+  else {
+    d.lis = lb;
+    if (A.lis_proto[lb] == GAR_PROTO_UDP) d.flags |= ACCD_LIS_UDP;
+    d.pr_begin = A.lis_pr_begin[lb];
+    u32 np = A.lis_pr_begin[lb + 1] - d.pr_begin;
+    d.n_ports = (u16)(np > 0xFFFF ? 0xFFFF : np);
+    if (np > 0) d.port0 = A.pr_from[d.pr_begin];
+    if (np > 1) d.port1 = A.pr_from[d.pr_begin + 1];
+    u32 eb = A.lis_eg_begin[lb], ee = A.lis_eg_begin[lb + 1];
+    if (ee == eb) d.flags |= ACCD_EG_NONE;
+    else if (ee - eb > 1) d.flags |= ACCD_EG_MANY;
+    else {
+      d.eg = eb;
+      d.ep_begin = A.eg_ep_begin[eb];
+      u32 ne = A.eg_ep_begin[eb + 1] - d.ep_begin;
+      d.n_eps = (u16)(ne > 0xFFFF ? 0xFFFF : ne);
+      if (ne > 0) d.ep0 = A.ep_id[d.ep_begin];
+    }
+  }
+  d.name = A.acc_name[a];
+  d.thost = thost;
+  d.owner_key = key;
+  W.acc_digest[a] = d;
+  W.acc_owner_hash[a] = (fl & ACC_OWNER_KEYED) ? key_hash_kinded((fl & ACC_OWNER_INGRESS) ? 1u : 0u, mkstr(A.slab, key)) : 0;
+  W.acc_thost_hash[a] = (fl & ACC_MINE) ? gar_hash(mkstr(A.slab, thost)) : 0;
   W.acc_flags[a] = fl;
   W.acc_owner_key[a] = key;
   W.acc_owner[a] = owner;
@@ -354,7 +417,7 @@ GAR_HD void classify_value(const DevTables &T, const Work &W, u32 v) {
   gar_str key = 0;
   const u32 hl = (u32)(sizeof(R53_HERITAGE) - 1);
   u32 fixed = hl + T.cluster_len + 1 + 8 + 1;  // heritage + cluster + ',' + "service/" + closing quote
-  if (s.n >= fixed && has_prefix_lit(s, R53_HERITAGE, hl) && streq(substr(s, hl, T.cluster_len), Str{T.cluster, T.cluster_len}) &&
+  if (s.n >= fixed && HAS_PREFIX_LIT(s, R53_HERITAGE) && streq(substr(s, hl, T.cluster_len), Str{T.cluster, T.cluster_len}) &&
       s.p[hl + T.cluster_len] == ',' && s.p[s.n - 1] == '"') {
     u32 ro = hl + T.cluster_len + 1;
     Str rest = substr(s, ro, s.n - 1 - ro);
@@ -367,6 +430,7 @@ GAR_HD void classify_value(const DevTables &T, const Work &W, u32 v) {
   }
   W.val_cls[v] = cls;
   W.val_key[v] = key;
+  W.val_key_hash[v] = cls ? key_hash_kinded((cls & VAL_OWNER_INGRESS) ? 1u : 0u, mkstr(A.slab, key)) : 0;
 }
 
 // ------------------------------------------------------------------ index probes
@@ -756,12 +820,12 @@ GAR_HD void put_delete_chain(const DevTables &T, OpSink &s, u32 obj, u32 kind, u
 
 // acceleratorChanged (global_accelerator.go:412-437), all lanes together.  The rare tags-annotation overlay keeps the
 // scalar routine (divergent, no votes inside).
-GAR_HD bool u_accelerator_changed(const DevTables &T, const Work &W, bool act, u32 i, u32 dv, u32 kind, u32 acc, Str okey, Str lb_dns) {
+GAR_HD bool u_accelerator_changed(const DevTables &T, const Work &W, bool act, u32 i, u32 dv, u32 kind, u32 acc, const AccDigest &d, Str okey, Str lb_dns) {
   const gar_actual &A = T.a;
-  bool ch = act && !A.acc_enabled[acc];
+  bool ch = act && !(d.flags & ACCD_ENABLED);
   // name: the annotation when non-empty, else resource-ns-name
   bool need = act && !ch;
-  Str an = need ? mkstr(A.slab, A.acc_name[acc]) : Str{A.slab, 0};
+  Str an = need ? mkstr(A.slab, d.name) : Str{A.slab, 0};
   Str ann = (need && (dv & OBJ_HAS_NAME_ANN)) ? mkstr(T.o.slab, W.ann_name[i]) : Str{T.o.slab, 0};
   bool by_ann = need && ann.n != 0;
   bool eq_ann = u_streq(by_ann, ann, an);
@@ -778,14 +842,11 @@ GAR_HD bool u_accelerator_changed(const DevTables &T, const Work &W, bool act, u
   bool overlay = tagcheck && (dv & OBJ_HAS_TAGS_ANN);
   if (overlay) ch = accelerator_tags_changed(T, W, i, kind, acc, lb_dns);
   bool sys = tagcheck && !overlay;
-  u32 fl = sys ? W.acc_flags[acc] : 0;
-  if (sys && !STREQ_LIT(mkstr(A.slab, W.acc_managed[acc]), "true")) ch = true;
-  bool own_shape = sys && !ch && (fl & ACC_OWNER_KEYED) && (((fl & ACC_OWNER_INGRESS) ? 1u : 0u) == kind);
-  if (sys && !ch && !own_shape) ch = true;
-  bool own_eq = u_streq(own_shape, own_shape ? mkstr(A.slab, W.acc_owner_key[acc]) : Str{A.slab, 0}, okey);
-  if (own_shape && !own_eq) ch = true;
+  u32 fl = d.flags;
+  if (sys && !(fl & ACCD_MANAGED_TRUE)) ch = true;
+  // the owner tag equals resource/ns/name: guaranteed by the index probe that produced `acc` (kind + key compared there)
   bool th = sys && !ch;
-  bool th_eq = u_streq(th, th ? mkstr(A.slab, W.acc_thost[acc]) : Str{A.slab, 0}, lb_dns);
+  bool th_eq = u_streq(th, th ? mkstr(A.slab, d.thost) : Str{A.slab, 0}, lb_dns);
   if (th && !th_eq) ch = true;
   return ch;
 }
@@ -874,46 +935,50 @@ GAR_HD u32 ga_reconcile(const DevTables &T, const Work &W, u32 i, bool valid, Op
       bool a = acc != GAR_NONE;
       if (!GAR_ANY(a)) break;
       if (a) nacc++;
+      AccDigest d;
+      d.flags = 0;
+      if (a) d = W.acc_digest[acc];
       // updateGlobalAcceleratorFor{Service,Ingress} (:290-410)
-      if (u_accelerator_changed(T, W, a, i, dv, kind, acc, okey, lb_dns)) s.put(GAR_OP_HEAD(GAR_OP_GA_UPDATE_ACCEL, GAR_CTRL_GA, kind), i, j, acc, lb, GAR_NONE);
+      if (u_accelerator_changed(T, W, a, i, dv, kind, acc, d, okey, lb_dns)) s.put(GAR_OP_HEAD(GAR_OP_GA_UPDATE_ACCEL, GAR_CTRL_GA, kind), i, j, acc, lb, GAR_NONE);
       u32 eg = GAR_NONE;
       if (a) {
-        u32 lbeg = A.acc_lis_begin[acc], lend = A.acc_lis_begin[acc + 1];
-        if (lend - lbeg > 1) {
+        if (d.flags & ACCD_LIS_MANY) {
           result = GAR_STATUS(GAR_ST_ERR_RETRY, GAR_D_TOO_MANY_LISTENERS, ev);
           stop = true;
-        } else if (lend == lbeg) {
+        } else if (d.flags & ACCD_LIS_NONE) {
           // the listener is created from the desired state, so neither change predicate fires on it; it has no
           // endpoint group yet, and the one created for it contains the LB (:298-345)
           s.put(GAR_OP_HEAD(GAR_OP_GA_CREATE_LISTENER, GAR_CTRL_GA, kind), i, j, acc, GAR_NONE, GAR_NONE);
           s.put(GAR_OP_HEAD(GAR_OP_GA_CREATE_EG, GAR_CTRL_GA, kind), i, j, acc, GAR_NONE, lb);
         } else {
-          u32 lis = lbeg;
-          u32 want_proto = kind == GAR_KIND_SERVICE ? ((dv & GAR_DV_PROTO_UDP) ? GAR_PROTO_UDP : GAR_PROTO_TCP) : GAR_PROTO_TCP;
-          bool changed = A.lis_proto[lis] != want_proto;  // :439-456
+          u32 lis = d.lis;
+          bool want_udp = kind == GAR_KIND_SERVICE && (dv & GAR_DV_PROTO_UDP);
+          bool changed = ((d.flags & ACCD_LIS_UDP) != 0) != want_udp;  // :439-456
           if (!changed) {
-            u32 pb = A.lis_pr_begin[lis];
-            changed = ports_changed(PortList{A.pr_from + pb, A.lis_pr_begin[lis + 1] - pb}, desired_ports(T, W, i));
+            PortList want = desired_ports(T, W, i);
+            // the common shapes compare against the inline ports; anything else reads the port-range rows
+            if (d.n_ports <= 2 && want.n == d.n_ports && (d.n_ports < 1 || want.p[0] == d.port0) && (d.n_ports < 2 || (want.p[1] == d.port1 && d.port0 != d.port1))) changed = false;
+            else changed = ports_changed(PortList{A.pr_from + d.pr_begin, d.n_ports == 0xFFFF ? A.lis_pr_begin[lis + 1] - d.pr_begin : d.n_ports}, want);
           }
           if (changed) s.put(GAR_OP_HEAD(GAR_OP_GA_UPDATE_LISTENER, GAR_CTRL_GA, kind), i, j, acc, lis, GAR_NONE);
-          u32 eb = A.lis_eg_begin[lis], ee = A.lis_eg_begin[lis + 1];
-          if (ee - eb > 1) {
+          if (d.flags & ACCD_EG_MANY) {
             result = GAR_STATUS(GAR_ST_ERR_RETRY, GAR_D_TOO_MANY_EGS, ev);
             stop = true;
-          } else if (ee == eb) {
+          } else if (d.flags & ACCD_EG_NONE) {
             s.put(GAR_OP_HEAD(GAR_OP_GA_CREATE_EG, GAR_CTRL_GA, kind), i, j, acc, lis, lb);
           } else {
-            eg = eb;
+            eg = d.eg;
           }
         }
       }
-      // endpointContainsLB (:494-501): one voted step per endpoint description
+      // endpointContainsLB (:494-501): one voted step per endpoint description (the first id comes from the digest)
       bool contains = false;
-      u32 d = eg != GAR_NONE ? A.eg_ep_begin[eg] : 0, dend = eg != GAR_NONE ? A.eg_ep_begin[eg + 1] : 0;
-      for (;; d++) {
-        bool more = !contains && d < dend;
+      u32 nep = eg != GAR_NONE ? (d.n_eps == 0xFFFF ? A.eg_ep_begin[eg + 1] - d.ep_begin : d.n_eps) : 0;
+      for (u32 x = 0;; x++) {
+        bool more = !contains && x < nep;
         if (!GAR_ANY(more)) break;
-        if (u_streq(more, more ? mkstr(A.slab, A.ep_id[d]) : Str{A.slab, 0}, lb_arn)) contains = true;
+        gar_str id = more ? (x == 0 ? d.ep0 : A.ep_id[d.ep_begin + x]) : 0;
+        if (u_streq(more, mkstr(A.slab, id), lb_arn)) contains = true;
       }
       if (eg != GAR_NONE && !contains) s.put(GAR_OP_HEAD(GAR_OP_GA_UPDATE_EG, GAR_CTRL_GA, kind), i, j, acc, eg, lb);
     }
@@ -999,8 +1064,8 @@ GAR_HD OwnedHit owned_get(const DevTables &T, const Work &W, const Owned &o, u32
 }
 
 // first alias record with type A under (zone, name): row and its alias DNSName ref  (rows of a bucket are ascending)
-GAR_HD u32 first_alias_a(const DevTables &T, const Work &W, u32 zone, Str name, gar_str *alias_dns) {
-  Cursor c = idx_open(W.ix_alias, key_hash_zoned(zone, name));
+GAR_HD u32 first_alias_a(const DevTables &T, const Work &W, u32 zone, Str name, u64 name_hash, gar_str *alias_dns) {
+  Cursor c = idx_open(W.ix_alias, key_hash_zoned_h(zone, name_hash));
   IdxEntry e;
   while (idx_next(W.ix_alias, c, &e)) {
     if (e.a0 != zone || e.a1 != GAR_RR_A) continue;
@@ -1202,10 +1267,13 @@ GAR_HD void link_value_alias(const DevTables &T, const Work &W, u32 v) {
   gar_str dns = 0;
   if (W.val_cls[v] != VAL_NOT_OWNER) {
     u32 rec = W.val_rec[v];
-    row = first_alias_a(T, W, W.rec_zone[rec], mkstr(T.a.slab, T.a.rec_name[rec]), &dns);
+    row = first_alias_a(T, W, W.rec_zone[rec], mkstr(T.a.slab, T.a.rec_name[rec]), W.rec_name_hash[rec], &dns);
   }
-  W.val_alias_row[v] = row;
-  W.val_alias_dns[v] = dns;
+  ValLink l;
+  l.alias_row = row;
+  l.pad = 0;
+  l.alias_dns = dns;
+  W.val_link[v] = l;
 }
 
 // warp-synchronous.  Writes r53_mode, r53_acc, r53_acc_dns, pair count (into pair_begin[i]) and, for objects that
@@ -1313,10 +1381,10 @@ GAR_HD void r53_pair(const DevTables &T, const Work &W, u32 p, bool valid) {
     bool match = u_streq(shape, substr(nm, 0, shape ? hn.n : 0), hn);
     if (mine && !plain) match = record_name_matches(nm, hn);  // possible \052 escape: scalar, rare
     if (match) {
-      u32 r = W.val_alias_row[e.row];
-      if (r != GAR_NONE && (rec == GAR_NONE || r < rec)) {
-        rec = r;
-        rec_alias = W.val_alias_dns[e.row];
+      ValLink l = W.val_link[e.row];
+      if (l.alias_row != GAR_NONE && (rec == GAR_NONE || l.alias_row < rec)) {
+        rec = l.alias_row;
+        rec_alias = l.alias_dns;
       }
     }
   }
@@ -1366,8 +1434,8 @@ GAR_HD u32 r53_combine(const DevTables &T, const Work &W, u32 i, bool valid, u32
 
 // ------------------------------------------------------------------ orphans (delete events of keys that left the cache)
 
-GAR_HD bool object_in_cache(const DevTables &T, const Work &W, u32 kind, Str key) {
-  Cursor c = idx_open(W.ix_obj, key_hash_kinded(kind, key));
+GAR_HD bool object_in_cache(const DevTables &T, const Work &W, u32 kind, Str key, u64 key_hash) {
+  Cursor c = idx_open(W.ix_obj, key_hash);
   IdxEntry e;
   while (idx_next(W.ix_obj, c, &e))
     if (e.a0 == kind && streq(mkstr(T.o.slab, e.s0), key)) return true;
@@ -1380,7 +1448,7 @@ GAR_HD u32 ga_orphan(const DevTables &T, const Work &W, u32 acc, OpSink &s) {
   u32 fl = W.acc_flags[acc];
   if (!(fl & ACC_MINE) || !(fl & ACC_OWNER_3PART)) return 0;
   u32 kind = (fl & ACC_OWNER_INGRESS) ? 1u : 0u;
-  if (object_in_cache(T, W, kind, mkstr(T.a.slab, W.acc_owner_key[acc]))) return 0;
+  if (object_in_cache(T, W, kind, mkstr(T.a.slab, W.acc_owner_key[acc]), W.acc_owner_hash[acc])) return 0;
   put_delete_chain(T, s, GAR_NONE, 0, acc);
   return 1;
 }
@@ -1391,7 +1459,7 @@ GAR_HD void mark_orphan_value(const DevTables &T, const Work &W, u32 v) {
   u8 orphan = 0;
   if (cls & VAL_OWNER_3PART) {
     u32 kind = (cls & VAL_OWNER_INGRESS) ? 1u : 0u;
-    orphan = object_in_cache(T, W, kind, mkstr(T.a.slab, W.val_key[v])) ? 0 : 1;
+    orphan = object_in_cache(T, W, kind, mkstr(T.a.slab, W.val_key[v]), W.val_key_hash[v]) ? 0 : 1;
   }
   W.val_orphan[v] = orphan;
 }
@@ -1403,7 +1471,7 @@ GAR_HD void r53_orphan_alias(const DevTables &T, const Work &W, u32 r, OpSink &s
   if (!A.rec_has_alias[r]) return;
   u32 zone = W.rec_zone[r];
   Str name = mkstr(A.slab, A.rec_name[r]);
-  u64 h = key_hash_zoned(zone, name);
+  u64 h = key_hash_zoned_h(zone, W.rec_name_hash[r]);
   Cursor c = idx_open(W.ix_ovn, h);
   IdxEntry e;
   while (idx_next(W.ix_ovn, c, &e)) {

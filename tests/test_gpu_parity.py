@@ -96,3 +96,21 @@ def test_hot_keys_force_the_fallback_paths(garecon, oracle, engine):
     want = oracle.diff(snap, "default", mode=1)
     assert got.diff(want) == [], got.describe_first_mismatch(want)
     assert len(got.ops) > 200
+
+
+def test_tokeniser_fuzz(garecon, oracle, engine):
+    import fuzzcases
+    snap = garecon.pack(fuzzcases.fuzz_hostnames(12, 5000), {})
+    engine.load(snap)
+    got = engine.diff()
+    want = oracle.diff(snap, "default", mode=1)
+    assert got.diff(want) == [], got.describe_first_mismatch(want)
+
+
+def test_listen_ports_fuzz(garecon, oracle, engine):
+    import fuzzcases
+    snap = garecon.pack(fuzzcases.listen_objects(), {})
+    engine.load(snap)
+    got = engine.diff()
+    want = oracle.diff(snap, "default", mode=1)
+    assert got.diff(want) == [], got.describe_first_mismatch(want)

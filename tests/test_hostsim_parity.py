@@ -87,3 +87,23 @@ def test_warp_emulation_catches_a_non_uniform_vote(garecon):
         lib = ctypes.CDLL(f"{d}/t.so")
         assert lib.probe(0) == 0
         assert lib.probe(1) == 1
+
+
+def test_hostsim_tokeniser_fuzz(garecon, oracle, hostsim):
+    import fuzzcases
+    snap = garecon.pack(fuzzcases.fuzz_hostnames(11, 1500), {})
+    hostsim.load(snap)
+    got = hostsim.diff()
+    want = oracle.diff(snap, "default", mode=1)
+    assert got.diff(want) == [], got.describe_first_mismatch(want)
+    assert len(set(got.tok_code.tolist())) >= 8
+
+
+def test_hostsim_listen_ports_fuzz(garecon, oracle, hostsim):
+    import fuzzcases
+    snap = garecon.pack(fuzzcases.listen_objects(), {})
+    hostsim.load(snap)
+    got = hostsim.diff()
+    want = oracle.diff(snap, "default", mode=1)
+    assert got.diff(want) == [], got.describe_first_mismatch(want)
+    assert len(got.dports) > 10
