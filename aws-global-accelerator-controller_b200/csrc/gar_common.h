@@ -181,8 +181,9 @@ GAR_HD u64 gar_hash(Str s) {
 // each loop iteration is one GAR_ANY vote, so the lanes' loads issue together.
 GAR_HD u64 u_hash(bool act, Str s) {
   u64 h = hash_init(s.n);
+  const u32 n = act ? s.n : 0;
   for (u32 i = 0;; i += 8) {
-    bool step = act && i < s.n;
+    bool step = i < n;
     if (!GAR_ANY(step)) break;
     if (step) h = hash_word(h, load_word(s, i));
   }
@@ -190,10 +191,15 @@ GAR_HD u64 u_hash(bool act, Str s) {
 }
 GAR_HD bool u_streq(bool act, Str a, Str b) {
   bool eq = act && a.n == b.n;
+  const u32 n = eq ? a.n : 0;
   for (u32 i = 0;; i += 8) {
-    bool step = eq && i < a.n;
+    bool step = eq && i < n;
     if (!GAR_ANY(step)) break;
-    if (step && load_word(a, i) != load_word(b, i)) eq = false;
+    if (step) {
+      u64 x = ld64u(a.p + i) ^ ld64u(b.p + i);  // one tail mask for both sides
+      if (n - i < 8) x &= lowmask(n - i);
+      if (x) eq = false;
+    }
   }
   return eq;
 }

@@ -29,11 +29,17 @@ __global__ void __launch_bounds__(256) k_for_each(const __grid_constant__ F f, u
 }
 
 // Warp-synchronous variant: every lane of every warp calls f (padding lanes with valid = false), so f may vote.
-template <class F>
-__global__ void __launch_bounds__(256) k_for_each_warp(const __grid_constant__ F f, u32 n) {
+template <class F, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_for_each_warp(const __grid_constant__ F f, u32 n) {
   u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   f(i, i < n);
 }
+// resident 256-thread blocks per SM each warp-synchronous stage is compiled for (register cap = 65536 / (256 * N)):
+// these stages wait on dependent DRAM loads, so occupancy matters more than registers
+template <class F> struct MinBlocks { static constexpr int value = 2; };
+template <> struct MinBlocks<FGaObj> { static constexpr int value = 3; };
+template <> struct MinBlocks<FR53Pair> { static constexpr int value = 5; };
+template <> struct MinBlocks<FR53Prepare> { static constexpr int value = 6; };
 
 __global__ void k_fill32(u32 *p, u32 v, size_t n) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -310,7 +316,7 @@ struct gar_engine {
   void for_each_warp(const char *name, u32 n, const F &f) {
     if (!n) return;
     stage_begin(name);
-    k_for_each_warp<F><<<(n + 255) / 256, 256, 0, stream>>>(f, n);
+    k_for_each_warp<F, MinBlocks<F>::value><<<(n + 255) / 256, 256, 0, stream>>>(f, n);
     launches++;
     stage_end();
   }

@@ -125,233 +125,185 @@ struct FJsonWrite {
   }
 };
 
-// --- index key functors: write bucket key (or the sentinel `nb` for rows that are not indexed) and the tag
-struct IdxOut {
-  u32 *keys, *vals, *tags;
-  u32 mask, nb;
-  GAR_HD void put(u32 i, bool valid, u64 h) const {
-    keys[i] = valid ? hash_bucket(h, mask) : nb;
-    vals[i] = i;
-    tags[i] = hash_tag(h);
+// --- index rows: one functor per index says whether a row is indexed, its key hash and its entry payload
+// (payload conventions: gar_rows.h "index probes").  The key pass streams the table once (coalesced) and leaves a
+// complete 32-byte entry per row; the build then only moves entries.
+struct FRowLb {
+  DevTables T;
+  GAR_HD bool make(u32 i, u64 *h, IdxEntry *e) const {
+    *h = key_hash_lb(mkstr(T.a.slab, T.a.lb_region[i]), mkstr(T.a.slab, T.a.lb_name[i]));
+    e->a0 = T.a.lb_state[i];
+    e->a1 = 0;
+    e->s0 = T.a.lb_name[i];
+    e->s1 = T.a.lb_region[i];
+    return true;
   }
 };
-struct FKeyLb {
-  DevTables T;
-  IdxOut o;
-  GAR_HD void operator()(u32 i) const { o.put(i, true, key_hash_lb(mkstr(T.a.slab, T.a.lb_region[i]), mkstr(T.a.slab, T.a.lb_name[i]))); }
-};
-struct FKeyOwner {
+struct FRowOwner {
   DevTables T;
   Work W;
-  IdxOut o;
-  GAR_HD void operator()(u32 i) const {
+  GAR_HD bool make(u32 i, u64 *h, IdxEntry *e) const {
     u32 fl = W.acc_flags[i];
-    bool valid = (fl & ACC_MINE) && (fl & ACC_OWNER_KEYED);
-    o.put(i, valid, W.acc_owner_hash[i]);
+    *h = W.acc_owner_hash[i];
+    e->a0 = fl;
+    e->a1 = 0;
+    e->s0 = W.acc_owner_key[i];
+    e->s1 = 0;
+    return (fl & ACC_MINE) && (fl & ACC_OWNER_KEYED);
   }
 };
-struct FKeyThost {
+struct FRowThost {
   DevTables T;
   Work W;
-  IdxOut o;
-  GAR_HD void operator()(u32 i) const {
-    bool valid = (W.acc_flags[i] & ACC_MINE) != 0;
-    o.put(i, valid, W.acc_thost_hash[i]);
+  GAR_HD bool make(u32 i, u64 *h, IdxEntry *e) const {
+    *h = W.acc_thost_hash[i];
+    e->a0 = e->a1 = 0;
+    e->s0 = W.acc_thost[i];
+    e->s1 = T.a.acc_dns[i];
+    return (W.acc_flags[i] & ACC_MINE) != 0;
   }
 };
-struct FKeyZone {
+struct FRowZone {
   DevTables T;
-  IdxOut o;
-  GAR_HD void operator()(u32 i) const {
+  GAR_HD bool make(u32 i, u64 *h, IdxEntry *e) const {
     Str zn = mkstr(T.a.slab, T.a.zone_name[i]);
     bool valid = zn.n >= 1 && zn.p[zn.n - 1] == '.';
-    o.put(i, valid, valid ? key_hash_str(substr(zn, 0, zn.n - 1)) : 0);
+    *h = valid ? key_hash_str(substr(zn, 0, zn.n - 1)) : 0;
+    e->a0 = e->a1 = 0;
+    e->s0 = T.a.zone_name[i];
+    e->s1 = 0;
+    return valid;
   }
 };
-struct FKeyVal {
+struct FRowVal {
   DevTables T;
   Work W;
-  IdxOut o;
-  GAR_HD void operator()(u32 v) const {
+  GAR_HD bool make(u32 v, u64 *h, IdxEntry *e) const {
     u32 cls = W.val_cls[v];
-    bool valid = cls != VAL_NOT_OWNER;
-    o.put(v, valid, W.val_key_hash[v]);
+    *h = W.val_key_hash[v];
+    if (cls == VAL_NOT_OWNER) return false;
+    u32 rec = W.val_rec[v];
+    u32 kind = (cls & VAL_OWNER_INGRESS) ? 1u : 0u;
+    Str nm = mkstr(T.a.slab, T.a.rec_name[rec]);
+    u32 bs = find_byte(nm, 0, '\\') < nm.n ? VALNAME_HAS_BACKSLASH : 0u;
+    e->a0 = rec;
+    e->a1 = W.rec_zone[rec] | bs | (kind << 31);
+    e->s0 = W.val_key[v];
+    e->s1 = T.a.rec_name[rec];
+    return true;
   }
 };
-struct FKeyAlias {
+struct FRowAlias {
   DevTables T;
   Work W;
-  IdxOut o;
-  GAR_HD void operator()(u32 r) const {
-    bool valid = T.a.rec_has_alias[r] != 0;
-    o.put(r, valid, key_hash_zoned_h(W.rec_zone[r], W.rec_name_hash[r]));
+  GAR_HD bool make(u32 r, u64 *h, IdxEntry *e) const {
+    *h = key_hash_zoned_h(W.rec_zone[r], W.rec_name_hash[r]);
+    e->a0 = W.rec_zone[r];
+    e->a1 = T.a.rec_type[r];
+    e->s0 = T.a.rec_name[r];
+    e->s1 = T.a.rec_alias_dns[r];
+    return T.a.rec_has_alias[r] != 0;
   }
 };
-struct FKeyObj {
+struct FRowObj {
   DevTables T;
   Work W;
-  IdxOut o;
-  GAR_HD void operator()(u32 i) const {
-    bool valid = !(W.derived[i] & OBJ_KEY_BAD);
-    o.put(i, valid, W.okey_hash[i]);
+  GAR_HD bool make(u32 i, u64 *h, IdxEntry *e) const {
+    gar_str ns = T.o.obj_ns[i];
+    *h = W.okey_hash[i];
+    e->a0 = T.o.obj_kind[i];
+    e->a1 = 0;
+    e->s0 = GAR_STR(GAR_STR_OFF(ns), GAR_STR_LEN(ns) + 1 + GAR_STR_LEN(T.o.obj_name[i]));
+    e->s1 = 0;
+    return !(W.derived[i] & OBJ_KEY_BAD);
   }
 };
-struct FKeyOvn {
+struct FRowOvn {
   DevTables T;
   Work W;
-  IdxOut o;
-  GAR_HD void operator()(u32 v) const {
-    bool valid = W.val_orphan[v] != 0;
-    u32 r = W.val_rec[v];
-    o.put(v, valid, key_hash_zoned_h(W.rec_zone[r], W.rec_name_hash[r]));
+  GAR_HD bool make(u32 v, u64 *h, IdxEntry *e) const {
+    u32 rec = W.val_rec[v];
+    *h = key_hash_zoned_h(W.rec_zone[rec], W.rec_name_hash[rec]);
+    e->a0 = rec;
+    e->a1 = W.rec_zone[rec];
+    e->s0 = T.a.rec_name[rec];
+    e->s1 = T.a.val_value[v];
+    return W.val_orphan[v] != 0;
   }
 };
-// Index build, fast path: rows are dropped into their bucket with an atomic cursor (any order), then one thread per
-// bucket sorts its handful of rows by row id and writes the entries.  The result is identical to a stable sort.
-// Buckets larger than IDX_SMALL_BUCKET (a hot key / adversarial input) raise `overflow`; the pipeline then rebuilds
-// that index with the stable radix sort.
+
+// Index build.  Fast path: (1) idx_rows: per row, entry + bucket key + bucket histogram; (2) scan; (3) idx_place: every
+// indexed row drops its entry into its bucket with an atomic cursor (any order); (4) idx_order: buckets with >= 2
+// entries are sorted by row id, which makes the result identical to a stable sort.  Buckets larger than
+// IDX_SMALL_BUCKET (a hot key / adversarial input) raise `overflow`; the pipeline then rebuilds with the stable
+// radix sort (idx_gather).
 constexpr u32 IDX_SMALL_BUCKET = 48;
-struct FBucketFill {
+template <class RowF>
+struct FIdxRows {
+  RowF rowf;
+  u32 *keys, *vals;
+  IdxEntry *tmp;
+  u32 *counts;
+  u32 mask, nb;
+  GAR_HD void operator()(u32 i) const {
+    u64 h = 0;
+    IdxEntry e;
+    bool valid = rowf.make(i, &h, &e);
+    e.tag = hash_tag(h);
+    e.row = i;
+    tmp[i] = e;
+    u32 k = valid ? hash_bucket(h, mask) : nb;  // rows that are not indexed carry the sentinel key nb
+    keys[i] = k;
+    vals[i] = i;
+    if (valid) GAR_ATOMIC_ADD(&counts[k], 1u);
+  }
+};
+struct FIdxPlace {
   const u32 *keys;
-  const u32 *begin;  // scanned
-  u32 *cursor;       // [nb] zeroed
-  u32 *rows;         // [n_valid] out: unsorted row ids, grouped by bucket
+  u32 *cursor;  // [nb] starts as a copy of begin[]
+  const IdxEntry *tmp;
+  IdxEntry *ent;
   u32 nb;
   GAR_HD void operator()(u32 i) const {
     u32 k = keys[i];
     if (k == nb) return;
 #if defined(__CUDA_ARCH__)
-    u32 slot = atomicAdd(&cursor[k], 1u);
+    u32 pos = atomicAdd(&cursor[k], 1u);
 #else
-    u32 slot = cursor[k]++;
+    u32 pos = cursor[k]++;
 #endif
-    rows[begin[k] + slot] = i;
+    ent[pos] = tmp[i];
   }
 };
-template <class EntF>
-struct FBucketFinalize {
+struct FIdxOrder {
   const u32 *begin;
-  const u32 *rows;
-  EntF entf;
+  IdxEntry *ent;
   u32 *overflow;
   GAR_HD void operator()(u32 b) const {
     u32 lo = begin[b], m = begin[b + 1] - lo;
-    if (m == 0) return;
+    if (m < 2) return;
     if (m > IDX_SMALL_BUCKET) {
       GAR_ATOMIC_ADD(overflow, 1u);
       return;
     }
-    u32 r[IDX_SMALL_BUCKET];
-    for (u32 k = 0; k < m; k++) {  // insertion sort by row id
-      u32 x = rows[lo + k];
+    for (u32 k = 1; k < m; k++) {  // insertion sort of 32-byte entries by row id, in place
+      IdxEntry x = ent[lo + k];
       u32 j = k;
-      while (j > 0 && r[j - 1] > x) {
-        r[j] = r[j - 1];
+      while (j > 0 && ent[lo + j - 1].row > x.row) {
+        ent[lo + j] = ent[lo + j - 1];
         j--;
       }
-      r[j] = x;
+      if (j != k) ent[lo + j] = x;
     }
-    for (u32 k = 0; k < m; k++) entf.fill(lo + k, r[k]);
   }
 };
-template <class EntF>
-struct FSortedFinalize {  // radix fallback: position p of the sorted order holds row vals[p]
+struct FIdxGather {  // radix fallback: position p of the stable sorted order holds row vals[p]
   const u32 *vals;
   const u32 *nvalid;
-  EntF entf;
-  GAR_HD void operator()(u32 p) const {
-    if (p < *nvalid) entf.fill(p, vals[p]);
-  }
-};
-struct FHistogram {
-  const u32 *keys;
-  u32 *counts;
-  u32 nb;  // rows that are not indexed carry the sentinel key nb: not counted (they would all hit one counter)
-  GAR_HD void operator()(u32 i) const {
-    u32 k = keys[i];
-    if (k != nb) GAR_ATOMIC_ADD(&counts[k], 1u);
-  }
-};
-// --- entry fill: position p of the sorted order -> 32-byte entry (payload conventions: gar_rows.h "index probes")
-struct EntOut {
-  const u32 *tags;
+  const IdxEntry *tmp;
   IdxEntry *ent;
-  GAR_HD void put(u32 p, u32 row, u32 a0, u32 a1, u64 s0, u64 s1) const {
-    IdxEntry e;
-    e.tag = tags[row];
-    e.row = row;
-    e.a0 = a0;
-    e.a1 = a1;
-    e.s0 = s0;
-    e.s1 = s1;
-    ent[p] = e;
-  }
-};
-struct FEntLb {
-  DevTables T;
-  EntOut o;
-  GAR_HD void fill(u32 p, u32 r) const {
-    o.put(p, r, T.a.lb_state[r], 0, T.a.lb_name[r], T.a.lb_region[r]);
-  }
-};
-struct FEntOwner {
-  DevTables T;
-  Work W;
-  EntOut o;
-  GAR_HD void fill(u32 p, u32 r) const {
-    o.put(p, r, W.acc_flags[r], 0, W.acc_owner_key[r], 0);
-  }
-};
-struct FEntThost {
-  DevTables T;
-  Work W;
-  EntOut o;
-  GAR_HD void fill(u32 p, u32 r) const {
-    o.put(p, r, 0, 0, W.acc_thost[r], T.a.acc_dns[r]);
-  }
-};
-struct FEntZone {
-  DevTables T;
-  EntOut o;
-  GAR_HD void fill(u32 p, u32 r) const {
-    o.put(p, r, 0, 0, T.a.zone_name[r], 0);
-  }
-};
-struct FEntVal {
-  DevTables T;
-  Work W;
-  EntOut o;
-  GAR_HD void fill(u32 p, u32 v) const {
-    u32 rec = W.val_rec[v];
-    u32 kind = (W.val_cls[v] & VAL_OWNER_INGRESS) ? 1u : 0u;
-    Str nm = mkstr(T.a.slab, T.a.rec_name[rec]);
-    u32 bs = find_byte(nm, 0, '\\') < nm.n ? VALNAME_HAS_BACKSLASH : 0u;
-    o.put(p, v, rec, W.rec_zone[rec] | bs | (kind << 31), W.val_key[v], T.a.rec_name[rec]);
-  }
-};
-struct FEntAlias {
-  DevTables T;
-  Work W;
-  EntOut o;
-  GAR_HD void fill(u32 p, u32 r) const {
-    o.put(p, r, W.rec_zone[r], T.a.rec_type[r], T.a.rec_name[r], T.a.rec_alias_dns[r]);
-  }
-};
-struct FEntObj {
-  DevTables T;
-  EntOut o;
-  GAR_HD void fill(u32 p, u32 i) const {
-    gar_str ns = T.o.obj_ns[i];
-    o.put(p, i, T.o.obj_kind[i], 0, GAR_STR(GAR_STR_OFF(ns), GAR_STR_LEN(ns) + 1 + GAR_STR_LEN(T.o.obj_name[i])), 0);
-  }
-};
-struct FEntOvn {
-  DevTables T;
-  Work W;
-  EntOut o;
-  GAR_HD void fill(u32 p, u32 v) const {
-    u32 rec = W.val_rec[v];
-    o.put(p, v, rec, W.rec_zone[rec], T.a.rec_name[rec], T.a.val_value[v]);
+  GAR_HD void operator()(u32 p) const {
+    if (p < *nvalid) ent[p] = tmp[vals[p]];
   }
 };
 struct FGather5 {
@@ -559,39 +511,27 @@ struct Pipeline {
   explicit Pipeline(B &b, const DevTables &t) : be(b), T(t) {}
 
   // nb: buckets (power of two).  load: target rows per bucket used to size nb from the row count.
-  template <class KeyF, class EntF>
-  HashIdx build_index(int slot, u32 nrows, u32 load, KeyF keyf, EntF entf, u32 *overflow, bool force_radix) {
+  template <class RowF>
+  HashIdx build_index(int slot, u32 nrows, u32 load, RowF rowf, u32 *overflow, bool force_radix) {
     u32 nb = next_pow2(nrows / load < 16 ? 16 : nrows / load);
     u32 *keys = (u32 *)be.ensure(S_SORT_KEYS, sizeof(u32) * (size_t)(nrows + 1));
     u32 *vals = (u32 *)be.ensure(S_SORT_VALS, sizeof(u32) * (size_t)(nrows + 1));
-    u32 *tags = (u32 *)be.ensure(S_SORT_TAGS, sizeof(u32) * (size_t)(nrows + 1));
+    IdxEntry *tmp = (IdxEntry *)be.ensure(S_SORT_TAGS, sizeof(IdxEntry) * (size_t)(nrows + 1));
     u32 *begin = (u32 *)be.ensure(slot + 0, sizeof(u32) * (size_t)(nb + 2));
     IdxEntry *ent = (IdxEntry *)be.ensure(slot + 1, sizeof(IdxEntry) * (size_t)(nrows + 1));
-    keyf.o = IdxOut{keys, vals, tags, nb - 1, nb};
-    entf.o = EntOut{tags, ent};
     be.fill32(begin, 0, nb + 2);
-    if (nrows) {
-      be.for_each("idx_keys", nrows, keyf);
-      be.for_each("idx_histogram", nrows, FHistogram{keys, begin, nb});
-    }
+    if (nrows) be.for_each("idx_rows", nrows, FIdxRows<RowF>{rowf, keys, vals, tmp, begin, nb - 1, nb});
     be.exclusive_scan(begin, nb + 2);  // begin[b] = #rows with key < b; begin[nb] = #indexed rows
     if (nrows && !force_radix) {
       u32 *cursor = (u32 *)be.ensure(S_SORT_KEYS_ALT, sizeof(u32) * (size_t)(nb + 1));
-      be.fill32(cursor, 0, nb);
-      be.for_each("idx_bucket_fill", nrows, FBucketFill{keys, begin, cursor, vals, nb});
-      be.for_each("idx_bucket_finalize", nb, FBucketFinalize<EntF>{begin, vals, entf, overflow});
-#if !defined(__CUDACC__)
-      if (getenv("GAR_DEBUG_INDEX")) {
-        u32 mx = 0;
-        for (u32 b = 0; b < nb; b++) mx = begin[b + 1] - begin[b] > mx ? begin[b + 1] - begin[b] : mx;
-        fprintf(stderr, "index slot %d: rows %u buckets %u indexed %u max bucket %u overflow %u\n", slot, nrows, nb, begin[nb], mx, *overflow);
-      }
-#endif
+      be.copy32(cursor, begin, nb);
+      be.for_each("idx_place", nrows, FIdxPlace{keys, cursor, tmp, ent, nb});
+      be.for_each("idx_order", nb, FIdxOrder{begin, ent, overflow});
     } else if (nrows) {
       u32 *keys2 = (u32 *)be.ensure(S_SORT_KEYS_ALT, sizeof(u32) * (size_t)(nrows + 1));
       u32 *vals2 = (u32 *)be.ensure(S_SORT_VALS_ALT, sizeof(u32) * (size_t)(nrows + 1));
       be.sort_pairs(keys, vals, keys2, vals2, nrows, ilog2(nb) + 1);
-      be.for_each("idx_entries", nrows, FSortedFinalize<EntF>{vals, begin + nb, entf});
+      be.for_each("idx_gather", nrows, FIdxGather{vals, begin + nb, tmp, ent});
     }
     return HashIdx{begin, ent, nb - 1};
   }
@@ -659,16 +599,16 @@ struct Pipeline {
 
     // stage 3: hash indexes
     u32 *overflow = errflag + 1;
-    W.ix_lb = build_index(S_IX_LB, T.a.n_lbs, 1, FKeyLb{T, {}}, FEntLb{T, {}}, overflow, force_radix);
-    W.ix_owner = build_index(S_IX_OWNER, nacc, 1, FKeyOwner{T, W, {}}, FEntOwner{T, W, {}}, overflow, force_radix);
-    W.ix_thost = build_index(S_IX_THOST, nacc, 1, FKeyThost{T, W, {}}, FEntThost{T, W, {}}, overflow, force_radix);
-    W.ix_zone = build_index(S_IX_ZONE, nzone, 1, FKeyZone{T, {}}, FEntZone{T, {}}, overflow, force_radix);
-    W.ix_val = build_index(S_IX_VAL, nval, 1, FKeyVal{T, W, {}}, FEntVal{T, W, {}}, overflow, force_radix);
-    W.ix_alias = build_index(S_IX_ALIAS, nrec, 2, FKeyAlias{T, W, {}}, FEntAlias{T, W, {}}, overflow, force_radix);
+    W.ix_lb = build_index(S_IX_LB, T.a.n_lbs, 1, FRowLb{T}, overflow, force_radix);
+    W.ix_owner = build_index(S_IX_OWNER, nacc, 1, FRowOwner{T, W}, overflow, force_radix);
+    W.ix_thost = build_index(S_IX_THOST, nacc, 1, FRowThost{T, W}, overflow, force_radix);
+    W.ix_zone = build_index(S_IX_ZONE, nzone, 1, FRowZone{T}, overflow, force_radix);
+    W.ix_val = build_index(S_IX_VAL, nval, 1, FRowVal{T, W}, overflow, force_radix);
+    W.ix_alias = build_index(S_IX_ALIAS, nrec, 2, FRowAlias{T, W}, overflow, force_radix);
     if (nval) be.for_each("link_value_alias", nval, FLinkValueAlias{T, W});
-    W.ix_obj = build_index(S_IX_OBJ, n, 1, FKeyObj{T, W, {}}, FEntObj{T, {}}, overflow, force_radix);
+    W.ix_obj = build_index(S_IX_OBJ, n, 1, FRowObj{T, W}, overflow, force_radix);
     if (nval) be.for_each("mark_orphan_values", nval, FMarkOrphanValue{T, W});
-    W.ix_ovn = build_index(S_IX_OVN, nval, 8, FKeyOvn{T, W, {}}, FEntOvn{T, W, {}}, overflow, force_radix);
+    W.ix_ovn = build_index(S_IX_OVN, nval, 8, FRowOvn{T, W}, overflow, force_radix);
 
     // stage 4: evaluate every object once (status + count + staged ops); count the orphan sections
     CountLayout L{n, nacc, nrec, nval};
