@@ -11,7 +11,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <exception>
+#include <functional>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 #include <utility>
@@ -402,57 +406,109 @@ static void check_ptr(const char *name, const void *p, size_t n) {
   if (n && !p) throw InvalidError{std::string(name) + " is NULL"};
 }
 
+// Host-side validation runs as a small task list over a few threads: at 10^6 objects there are ~4*10^7 references
+// to check, which single-threaded would cost more than the PCIe copy it overlaps with.
+struct Tasks {
+  std::vector<std::function<void()>> list;
+  void str_col(const char *name, const gar_str *col, size_t n, u64 slab_len) {
+    if (n && !col) throw InvalidError{std::string(name) + " is NULL"};
+    const size_t chunk = 1u << 19;
+    for (size_t b = 0; b < n; b += chunk) {
+      size_t e = b + chunk < n ? b + chunk : n;
+      list.push_back([=] { check_str_col(name, col + b, e - b, slab_len); });
+    }
+  }
+  void csr(const char *name, const u32 *b, size_t nparents, size_t nchildren) {
+    list.push_back([=] { check_csr(name, b, nparents, nchildren); });
+  }
+  void run() {
+    unsigned nt = std::thread::hardware_concurrency();
+    nt = nt < 1 ? 1 : (nt > 16 ? 16 : nt);
+    std::atomic<size_t> next{0};
+    std::exception_ptr err;
+    std::mutex em;
+    auto worker = [&] {
+      for (;;) {
+        size_t k = next.fetch_add(1);
+        if (k >= list.size()) return;
+        try {
+          list[k]();
+        } catch (...) {
+          std::lock_guard<std::mutex> lk(em);
+          if (!err) err = std::current_exception();
+        }
+      }
+    };
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < nt; t++) th.emplace_back(worker);
+    worker();
+    for (auto &t : th) t.join();
+    if (err) std::rethrow_exception(err);
+  }
+};
+
 static void validate(const gar_objects *o, const gar_actual *a) {
   if (!o || !a) throw InvalidError{"NULL table struct"};
+  Tasks T;
   size_t n = o->n_objects;
   check_ptr("obj_kind", o->obj_kind, n);
   check_ptr("obj_spec_type", o->obj_spec_type, n);
   check_ptr("obj_flags", o->obj_flags, n);
   check_ptr("objects.slab", o->slab, o->slab_len);
-  check_str_col("obj_ns", o->obj_ns, n, o->slab_len);
-  check_str_col("obj_name", o->obj_name, n, o->slab_len);
-  check_str_col("obj_ingress_class", o->obj_ingress_class, n, o->slab_len);
-  check_csr("obj_ann_begin", o->obj_ann_begin, n, o->n_ann);
-  check_csr("obj_lbi_begin", o->obj_lbi_begin, n, o->n_lbi);
-  check_csr("obj_port_begin", o->obj_port_begin, n, o->n_ports);
-  check_str_col("ann_key", o->ann_key, o->n_ann, o->slab_len);
-  check_str_col("ann_val", o->ann_val, o->n_ann, o->slab_len);
-  check_str_col("lbi_hostname", o->lbi_hostname, o->n_lbi, o->slab_len);
+  T.str_col("obj_ns", o->obj_ns, n, o->slab_len);
+  T.str_col("obj_name", o->obj_name, n, o->slab_len);
+  T.str_col("obj_ingress_class", o->obj_ingress_class, n, o->slab_len);
+  T.csr("obj_ann_begin", o->obj_ann_begin, n, o->n_ann);
+  T.csr("obj_lbi_begin", o->obj_lbi_begin, n, o->n_lbi);
+  T.csr("obj_port_begin", o->obj_port_begin, n, o->n_ports);
+  T.str_col("ann_key", o->ann_key, o->n_ann, o->slab_len);
+  T.str_col("ann_val", o->ann_val, o->n_ann, o->slab_len);
+  T.str_col("lbi_hostname", o->lbi_hostname, o->n_lbi, o->slab_len);
   check_ptr("port_number", o->port_number, o->n_ports);
-  check_str_col("port_proto", o->port_proto, o->n_ports, o->slab_len);
-  for (size_t i = 0; i < n; i++) {
-    if (o->obj_kind[i] > GAR_KIND_INGRESS) throw InvalidError{"obj_kind out of range"};
-    u64 sep = GAR_STR_OFF(o->obj_ns[i]) + GAR_STR_LEN(o->obj_ns[i]);
-    if (GAR_STR_OFF(o->obj_name[i]) != sep + 1 || sep >= o->slab_len || o->slab[sep] != '/')
-      throw InvalidError{"objects layout rule violated: obj_ns and obj_name must be slices of one \"ns/name\" key string"};
+  T.str_col("port_proto", o->port_proto, o->n_ports, o->slab_len);
+  if (n && (!o->obj_ns || !o->obj_name || !o->obj_kind)) throw InvalidError{"object columns are NULL"};
+  {
+    const size_t chunk = 1u << 19;
+    for (size_t b = 0; b < n; b += chunk) {
+      size_t e = b + chunk < n ? b + chunk : n;
+      T.list.push_back([=] {
+        for (size_t i = b; i < e; i++) {
+          if (o->obj_kind[i] > GAR_KIND_INGRESS) throw InvalidError{"obj_kind out of range"};
+          u64 sep = GAR_STR_OFF(o->obj_ns[i]) + GAR_STR_LEN(o->obj_ns[i]);
+          if (GAR_STR_OFF(o->obj_name[i]) != sep + 1 || sep >= o->slab_len || o->slab[sep] != '/')
+            throw InvalidError{"objects layout rule violated: obj_ns and obj_name must be slices of one \"ns/name\" key string"};
+        }
+      });
+    }
   }
   check_ptr("actual.slab", a->slab, a->slab_len);
-  check_str_col("lb_region", a->lb_region, a->n_lbs, a->slab_len);
-  check_str_col("lb_name", a->lb_name, a->n_lbs, a->slab_len);
-  check_str_col("lb_dns", a->lb_dns, a->n_lbs, a->slab_len);
-  check_str_col("lb_arn", a->lb_arn, a->n_lbs, a->slab_len);
+  T.str_col("lb_region", a->lb_region, a->n_lbs, a->slab_len);
+  T.str_col("lb_name", a->lb_name, a->n_lbs, a->slab_len);
+  T.str_col("lb_dns", a->lb_dns, a->n_lbs, a->slab_len);
+  T.str_col("lb_arn", a->lb_arn, a->n_lbs, a->slab_len);
   check_ptr("lb_state", a->lb_state, a->n_lbs);
-  check_str_col("acc_name", a->acc_name, a->n_accels, a->slab_len);
-  check_str_col("acc_dns", a->acc_dns, a->n_accels, a->slab_len);
+  T.str_col("acc_name", a->acc_name, a->n_accels, a->slab_len);
+  T.str_col("acc_dns", a->acc_dns, a->n_accels, a->slab_len);
   check_ptr("acc_enabled", a->acc_enabled, a->n_accels);
-  check_csr("acc_tag_begin", a->acc_tag_begin, a->n_accels, a->n_tags);
-  check_csr("acc_lis_begin", a->acc_lis_begin, a->n_accels, a->n_listeners);
-  check_str_col("tag_key", a->tag_key, a->n_tags, a->slab_len);
-  check_str_col("tag_val", a->tag_val, a->n_tags, a->slab_len);
+  T.csr("acc_tag_begin", a->acc_tag_begin, a->n_accels, a->n_tags);
+  T.csr("acc_lis_begin", a->acc_lis_begin, a->n_accels, a->n_listeners);
+  T.str_col("tag_key", a->tag_key, a->n_tags, a->slab_len);
+  T.str_col("tag_val", a->tag_val, a->n_tags, a->slab_len);
   check_ptr("lis_proto", a->lis_proto, a->n_listeners);
-  check_csr("lis_pr_begin", a->lis_pr_begin, a->n_listeners, a->n_port_ranges);
-  check_csr("lis_eg_begin", a->lis_eg_begin, a->n_listeners, a->n_egs);
+  T.csr("lis_pr_begin", a->lis_pr_begin, a->n_listeners, a->n_port_ranges);
+  T.csr("lis_eg_begin", a->lis_eg_begin, a->n_listeners, a->n_egs);
   check_ptr("pr_from", a->pr_from, a->n_port_ranges);
-  check_csr("eg_ep_begin", a->eg_ep_begin, a->n_egs, a->n_endpoints);
-  check_str_col("ep_id", a->ep_id, a->n_endpoints, a->slab_len);
-  check_str_col("zone_name", a->zone_name, a->n_zones, a->slab_len);
-  check_csr("zone_rec_begin", a->zone_rec_begin, a->n_zones, a->n_records);
-  check_str_col("rec_name", a->rec_name, a->n_records, a->slab_len);
+  T.csr("eg_ep_begin", a->eg_ep_begin, a->n_egs, a->n_endpoints);
+  T.str_col("ep_id", a->ep_id, a->n_endpoints, a->slab_len);
+  T.str_col("zone_name", a->zone_name, a->n_zones, a->slab_len);
+  T.csr("zone_rec_begin", a->zone_rec_begin, a->n_zones, a->n_records);
+  T.str_col("rec_name", a->rec_name, a->n_records, a->slab_len);
   check_ptr("rec_type", a->rec_type, a->n_records);
   check_ptr("rec_has_alias", a->rec_has_alias, a->n_records);
-  check_str_col("rec_alias_dns", a->rec_alias_dns, a->n_records, a->slab_len);
-  check_csr("rec_val_begin", a->rec_val_begin, a->n_records, a->n_values);
-  check_str_col("val_value", a->val_value, a->n_values, a->slab_len);
+  T.str_col("rec_alias_dns", a->rec_alias_dns, a->n_records, a->slab_len);
+  T.csr("rec_val_begin", a->rec_val_begin, a->n_records, a->n_values);
+  T.str_col("val_value", a->val_value, a->n_values, a->slab_len);
+  T.run();
 }
 
 // bytes of the input tables, each array counted once (roofline numerator)

@@ -215,7 +215,7 @@ def main():
     snap = synth.SynthSnapshot(cfg)
     o, a = snap.objects, snap.actual
     h2d_bytes = sum(int(c) * s for (_, c, s) in _table_arrays(abi, o, a))
-    _pin_host_tables(torch, abi, o, a)
+    pinned_bytes = _pin_host_tables(torch, abi, o, a)
 
     eng = pkg.Engine(cluster_name=snap.cluster, device=local_rank)
     sampler = ClockSampler(local_rank)
@@ -247,9 +247,13 @@ def main():
         full = eng.diff()
     barrier()
     t2 = time.perf_counter()
+    e2e_parts = {"ms_h2d": 0.0, "ms_kernels": 0.0, "ms_d2h": 0.0}
     for _ in range(args.steps):
         eng.load(snap)
         full = eng.diff()
+        e2e_parts["ms_h2d"] += full.ms_h2d / args.steps
+        e2e_parts["ms_kernels"] += full.ms_kernels / args.steps
+        e2e_parts["ms_d2h"] += full.ms_d2h / args.steps
     barrier()
     t3 = time.perf_counter()
     dt_e2e = max_over_ranks(t3 - t2)
@@ -292,7 +296,8 @@ def main():
                        "objects_per_gpu": args.objects, "parallelism": f"replicas x{world} (independent clusters, no collective)",
                        "cache": f"inputs ({h2d_bytes / 1e6:.0f} MB per GPU) larger than L2 (126 MB); no flush needed", "seed": int(cfg.seed),
                        "n_ops": n_ops, "algorithmic_bytes": b_alg, "bytes_per_object": b_alg / args.objects},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "ms_per_step": dt_e2e / args.steps * 1e3},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "ms_per_step": dt_e2e / args.steps * 1e3,
+                    "pinned_host_bytes": pinned_bytes, **{k: round(v, 3) for k, v in e2e_parts.items()}},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": top[0], "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,

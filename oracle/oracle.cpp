@@ -24,6 +24,7 @@
 #include "../include/garecon.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cstdint>
 #include <cstring>
 #include <map>
@@ -720,21 +721,30 @@ struct Snap {
 };
 
 // indexes for mode 1
-struct Index {
-  std::unordered_map<std::string, std::vector<uint32_t>> byOwner;     // owner tag value -> accelerators (managed, cluster)
-  std::unordered_map<std::string, std::vector<uint32_t>> byHostname;  // target hostname -> accelerators (managed, cluster)
-  std::unordered_map<std::string, uint32_t> lbByRegionName;           // region + '\0' + name -> first LB row
-  std::unordered_map<std::string, uint32_t> zoneByName;               // zone name -> first zone row
-  std::unordered_map<std::string, std::vector<uint32_t>> valByValue;  // value string -> value rows (ascending)
-  std::unordered_map<std::string, std::vector<uint32_t>> aliasByZoneName;  // zone(4 bytes) + name -> alias record rows
-  std::vector<uint32_t> recZone, valRec;
+// keys are views into the snapshot slabs (no copies); composite keys carry their parts
+struct K2 {
+  sv a, b;
+  bool operator==(const K2 &o) const { return a == o.a && b == o.b; }
 };
-
-std::string zkey(uint32_t z, sv name) {
-  std::string k((const char *)&z, 4);
-  k += std::string(name);
-  return k;
-}
+struct K2Hash {
+  size_t operator()(const K2 &k) const { return std::hash<sv>()(k.a) * 0x9E3779B97F4A7C15ull ^ std::hash<sv>()(k.b); }
+};
+struct ZK {
+  uint32_t z;
+  sv name;
+  bool operator==(const ZK &o) const { return z == o.z && name == o.name; }
+};
+struct ZKHash {
+  size_t operator()(const ZK &k) const { return std::hash<sv>()(k.name) ^ ((size_t)k.z * 0x9E3779B97F4A7C15ull); }
+};
+struct Index {
+  std::unordered_map<sv, std::vector<uint32_t>> byOwner;     // owner tag value -> accelerators (managed, cluster)
+  std::unordered_map<sv, std::vector<uint32_t>> byHostname;  // target hostname -> accelerators (managed, cluster)
+  std::unordered_map<K2, uint32_t, K2Hash> lbByRegionName;   // (region, name) -> first LB row
+  std::unordered_map<sv, uint32_t> zoneByName;               // zone name -> first zone row
+  std::unordered_map<sv, std::vector<uint32_t>> valByValue;  // value string -> value rows (ascending)
+  std::unordered_map<ZK, std::vector<uint32_t>, ZKHash> aliasByZoneName;  // (zone, name) -> alias record rows
+};
 
 struct Out {
   std::vector<gar_op> ops;
@@ -786,23 +796,36 @@ class Engine {
     return true;
   }
 
+  // the five indexes are independent: built concurrently (this is the "batch CPU version" a maintainer would write)
   void buildIndex() {
     const gar_actual *a = S.a;
-    for (uint32_t i = 0; i < a->n_accels; i++) {
-      auto m = tagMap(i);
-      if (mget(m, kTagManaged) != "true") continue;
-      if (mget(m, kTagCluster) != sv(S.cluster)) continue;
-      ix.byOwner[std::string(mget(m, kTagOwner))].push_back(i);
-      ix.byHostname[std::string(mget(m, kTagTargetHostname))].push_back(i);
-    }
-    for (uint32_t i = 0; i < a->n_lbs; i++) {
-      std::string k = std::string(S.as(a->lb_region[i])) + '\0' + std::string(S.as(a->lb_name[i]));
-      ix.lbByRegionName.emplace(k, i);  // first wins
-    }
-    for (uint32_t z = 0; z < a->n_zones; z++) ix.zoneByName.emplace(std::string(S.as(a->zone_name[z])), z);
-    for (uint32_t v = 0; v < a->n_values; v++) ix.valByValue[std::string(S.as(a->val_value[v]))].push_back(v);
-    for (uint32_t r = 0; r < a->n_records; r++)
-      if (a->rec_has_alias[r]) ix.aliasByZoneName[zkey(recZone[r], S.as(a->rec_name[r]))].push_back(r);
+    std::vector<std::thread> th;
+    th.emplace_back([&] {
+      ix.byOwner.reserve(a->n_accels);
+      ix.byHostname.reserve(a->n_accels);
+      for (uint32_t i = 0; i < a->n_accels; i++) {
+        auto m = tagMap(i);
+        if (mget(m, kTagManaged) != "true") continue;
+        if (mget(m, kTagCluster) != sv(S.cluster)) continue;
+        ix.byOwner[mget(m, kTagOwner)].push_back(i);
+        ix.byHostname[mget(m, kTagTargetHostname)].push_back(i);
+      }
+    });
+    th.emplace_back([&] {
+      ix.lbByRegionName.reserve(a->n_lbs);
+      for (uint32_t i = 0; i < a->n_lbs; i++) ix.lbByRegionName.emplace(K2{S.as(a->lb_region[i]), S.as(a->lb_name[i])}, i);  // first wins
+      for (uint32_t z = 0; z < a->n_zones; z++) ix.zoneByName.emplace(S.as(a->zone_name[z]), z);
+    });
+    th.emplace_back([&] {
+      ix.valByValue.reserve(a->n_values);
+      for (uint32_t v = 0; v < a->n_values; v++) ix.valByValue[S.as(a->val_value[v])].push_back(v);
+    });
+    th.emplace_back([&] {
+      ix.aliasByZoneName.reserve(a->n_records / 2);
+      for (uint32_t r = 0; r < a->n_records; r++)
+        if (a->rec_has_alias[r]) ix.aliasByZoneName[ZK{recZone[r], S.as(a->rec_name[r])}].push_back(r);
+    });
+    for (auto &t : th) t.join();
   }
 
   // ---- object view
@@ -878,7 +901,7 @@ class Engine {
   std::vector<uint32_t> listByResource(sv resource, sv ns, sv name) const {
     std::string owner = ownerTagValue(resource, ns, name);
     if (mode == 1) {
-      auto it = ix.byOwner.find(owner);
+      auto it = ix.byOwner.find(sv(owner));
       return it == ix.byOwner.end() ? std::vector<uint32_t>() : it->second;
     }
     std::vector<uint32_t> res;
@@ -890,7 +913,7 @@ class Engine {
   // ListGlobalAcceleratorByHostname (:62-85)
   std::vector<uint32_t> listByHostname(sv hostname) const {
     if (mode == 1) {
-      auto it = ix.byHostname.find(std::string(hostname));
+      auto it = ix.byHostname.find(hostname);
       return it == ix.byHostname.end() ? std::vector<uint32_t>() : it->second;
     }
     std::vector<uint32_t> res;
@@ -902,7 +925,7 @@ class Engine {
   // GetLoadBalancer (load_balancer.go:13-30), client bound to `region` (aws.go:23-25)
   int64_t getLoadBalancer(sv region, sv name) const {
     if (mode == 1) {
-      auto it = ix.lbByRegionName.find(std::string(region) + '\0' + std::string(name));
+      auto it = ix.lbByRegionName.find(K2{region, name});
       return it == ix.lbByRegionName.end() ? -1 : (int64_t)it->second;
     }
     for (uint32_t i = 0; i < S.a->n_lbs; i++)
@@ -1021,7 +1044,7 @@ class Engine {
       if (target.empty()) return -1;
       std::string want = target + ".";
       if (mode == 1) {
-        auto it = ix.zoneByName.find(want);
+        auto it = ix.zoneByName.find(sv(want));
         if (it != ix.zoneByName.end()) return it->second;
       } else {
         for (uint32_t z = 0; z < S.a->n_zones; z++)
@@ -1040,7 +1063,7 @@ class Engine {
     const gar_actual *a = S.a;
     std::vector<Owned> res;
     if (mode == 1) {
-      auto it = ix.valByValue.find(std::string(ownerValue));
+      auto it = ix.valByValue.find(ownerValue);
       if (it == ix.valByValue.end()) return res;
       std::vector<std::pair<sv, uint32_t>> names;  // distinct names in first-seen order, with first value row
       for (uint32_t v : it->second) {
@@ -1051,7 +1074,7 @@ class Engine {
         if (!seen) names.push_back({n, v});
       }
       for (auto &p : names) {
-        auto at = ix.aliasByZoneName.find(zkey(z, p.first));
+        auto at = ix.aliasByZoneName.find(ZK{z, p.first});
         if (at == ix.aliasByZoneName.end()) continue;
         for (uint32_t r : at->second) res.push_back({r, p.second});
       }
@@ -1077,7 +1100,7 @@ class Engine {
     const gar_actual *a = S.a;
     std::vector<Owned> res;
     if (mode == 1) {
-      auto it = ix.valByValue.find(std::string(ownerValue));
+      auto it = ix.valByValue.find(ownerValue);
       if (it == ix.valByValue.end()) return res;
       for (uint32_t v : it->second)
         if (recZone[valRec[v]] == z) res.push_back({valRec[v], v});
@@ -1103,7 +1126,20 @@ class Engine {
   // CleanupRecordSet (route53.go:132-165)
   void cleanupRecordSet(std::vector<gar_op> &ops, uint32_t objRow, int kind, sv ownerValue) const {
     uint32_t head = GAR_OP_HEAD(GAR_OP_R53_DELETE_RECORD, GAR_CTRL_R53, objRow == GAR_NONE ? 0 : kind);
-    if (mode == 1 && ix.valByValue.find(std::string(ownerValue)) == ix.valByValue.end()) return;
+    if (mode == 1) {
+      // indexed: only the zones that hold one of the owner's value rows can contribute (rows are zone-major)
+      auto it = ix.valByValue.find(ownerValue);
+      if (it == ix.valByValue.end()) return;
+      uint32_t last = GAR_NONE;
+      for (uint32_t v : it->second) {
+        uint32_t z = recZone[valRec[v]];
+        if (z == last) continue;
+        last = z;
+        for (auto &r : findOwneredARecordSets(z, ownerValue)) ops.push_back({head, objRow, 0, z, r.rec, r.val});
+        for (auto &r : findOwneredMetadataRecordSets(z, ownerValue)) ops.push_back({head, objRow, 1, z, r.rec, r.val});
+      }
+      return;
+    }
     for (uint32_t z = 0; z < S.a->n_zones; z++) {
       for (auto &r : findOwneredARecordSets(z, ownerValue)) ops.push_back({head, objRow, 0, z, r.rec, r.val});
       for (auto &r : findOwneredMetadataRecordSets(z, ownerValue)) ops.push_back({head, objRow, 1, z, r.rec, r.val});
@@ -1207,8 +1243,16 @@ int orc_diff(const gar_objects *o, const gar_actual *a, const char *cluster, int
   R->tokName.assign(o->n_lbi, 0);
   R->tokRegion.assign(o->n_lbi, 0);
 
+  if (threads < 1 || mode == 0) threads = 1;
+  // cache membership for orphan detection (built while the objects are being evaluated)
+  std::unordered_map<ObjKey, uint32_t, ObjKeyHash> cache;
+  std::thread cacheBuilder([&] {
+    cache.reserve(n);
+    for (uint32_t i = 0; i < n; i++) cache.emplace(ObjKey{o->obj_kind[i], E.S.os(o->obj_ns[i]), E.S.os(o->obj_name[i])}, i);
+  });
   // tokeniser results per lbIngress row
-  for (uint32_t i = 0; i < o->n_lbi; i++) {
+  auto tokRange = [&](uint32_t lo, uint32_t hi) {
+  for (uint32_t i = lo; i < hi; i++) {
     sv h = E.S.os(o->lbi_hostname[i]);
     Tok t = tokenise(h);
     R->tokCode[i] = (uint8_t)t.code;
@@ -1218,8 +1262,14 @@ int orc_diff(const gar_objects *o, const gar_actual *a, const char *cluster, int
       R->tokRegion[i] = GAR_STR(base + (uint64_t)(t.region.data() - h.data()), t.region.size());
     }
   }
+  };
+  {
+    std::vector<std::thread> th;
+    for (int t = 1; t < threads; t++) th.emplace_back(tokRange, (uint32_t)((uint64_t)o->n_lbi * t / threads), (uint32_t)((uint64_t)o->n_lbi * (t + 1) / threads));
+    tokRange(0, (uint32_t)((uint64_t)o->n_lbi / threads));
+    for (auto &x : th) x.join();
+  }
 
-  if (threads < 1 || mode == 0) threads = 1;
   std::vector<std::vector<gar_op>> gaOps(threads), r53Ops(threads);
   std::vector<std::vector<std::vector<int32_t>>> dps(threads);
   auto work = [&](int t) {
@@ -1264,9 +1314,7 @@ int orc_diff(const gar_objects *o, const gar_actual *a, const char *cluster, int
   for (auto &v : dps)
     for (auto &p : v) R->dports.insert(R->dports.end(), p.begin(), p.end());
 
-  // cache membership for orphan detection
-  std::unordered_map<ObjKey, uint32_t, ObjKeyHash> cache;
-  for (uint32_t i = 0; i < n; i++) cache.emplace(ObjKey{o->obj_kind[i], E.S.os(o->obj_ns[i]), E.S.os(o->obj_name[i])}, i);
+  cacheBuilder.join();
 
   // section 0: GA ops of cached objects
   R->cs.section_begin[0] = 0;
@@ -1298,30 +1346,49 @@ int orc_diff(const gar_objects *o, const gar_actual *a, const char *cluster, int
       return cache.count(*k) == 0;
     };
     uint32_t head = GAR_OP_HEAD(GAR_OP_R53_DELETE_RECORD, GAR_CTRL_R53, 0);
-    for (uint32_t z = 0; z < a->n_zones; z++) {
+    std::vector<std::vector<gar_op>> zoneOps(a->n_zones);
+    auto zoneWork = [&](uint32_t z) {
+      std::vector<gar_op> &out = zoneOps[z];
       uint32_t rb = a->zone_rec_begin[z], re = a->zone_rec_begin[z + 1];
-      // orphan value rows of this zone, ascending
+      // orphan value rows of this zone, ascending, grouped by record name
       std::vector<uint32_t> ov;
+      std::unordered_map<sv, std::vector<uint32_t>> byName;
       for (uint32_t r = rb; r < re; r++)
         for (uint32_t v = a->rec_val_begin[r]; v < a->rec_val_begin[r + 1]; v++) {
           ObjKey k;
-          if (orphanKey(E.S.as(a->val_value[v]), &k)) ov.push_back(v);
+          if (orphanKey(E.S.as(a->val_value[v]), &k)) {
+            ov.push_back(v);
+            byName[E.S.as(a->rec_name[r])].push_back(v);
+          }
         }
       // phase 0: alias set r x orphan owner value (represented by its first value row under that name)
-      for (uint32_t r = rb; r < re; r++) {
-        if (!a->rec_has_alias[r]) continue;
-        std::vector<sv> seen;
-        for (uint32_t v : ov) {
-          if (E.S.as(a->rec_name[E.valRec[v]]) != E.S.as(a->rec_name[r])) continue;
-          sv val = E.S.as(a->val_value[v]);
-          if (std::find(seen.begin(), seen.end(), val) != seen.end()) continue;
-          seen.push_back(val);
-          R->ops.push_back({head, GAR_NONE, 0, z, r, v});
+      if (!ov.empty())
+        for (uint32_t r = rb; r < re; r++) {
+          if (!a->rec_has_alias[r]) continue;
+          auto it = byName.find(E.S.as(a->rec_name[r]));
+          if (it == byName.end()) continue;
+          std::vector<sv> seen;
+          for (uint32_t v : it->second) {
+            sv val = E.S.as(a->val_value[v]);
+            if (std::find(seen.begin(), seen.end(), val) != seen.end()) continue;
+            seen.push_back(val);
+            out.push_back({head, GAR_NONE, 0, z, r, v});
+          }
         }
-      }
       // phase 1: owner metadata sets
-      for (uint32_t v : ov) R->ops.push_back({head, GAR_NONE, 1, z, E.valRec[v], v});
+      for (uint32_t v : ov) out.push_back({head, GAR_NONE, 1, z, E.valRec[v], v});
+    };
+    {
+      std::vector<std::thread> th;
+      std::atomic<uint32_t> next{0};
+      auto worker = [&] {
+        for (uint32_t z; (z = next.fetch_add(1)) < a->n_zones;) zoneWork(z);
+      };
+      for (int t = 1; t < threads; t++) th.emplace_back(worker);
+      worker();
+      for (auto &x : th) x.join();
     }
+    for (auto &v : zoneOps) R->ops.insert(R->ops.end(), v.begin(), v.end());
   }
   R->cs.section_begin[4] = R->ops.size();
 
