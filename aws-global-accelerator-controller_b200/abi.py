@@ -269,6 +269,16 @@ class Engine:
             self.lib.gar_changeset_free(self._h, C.byref(cs))
         return out
 
+    def diff_raw(self) -> dict:
+        """gar_diff + gar_changeset_free without copying the arrays into numpy: what a C / cgo caller pays.
+        Returns counts and timings only."""
+        cs = GarChangeset()
+        self._check(self.lib.gar_diff(self._h, C.byref(cs)))
+        out = {"n_ops": int(cs.n_ops), "n_dports": int(cs.n_dports), "ms_h2d": cs.ms_h2d, "ms_kernels": cs.ms_kernels, "ms_d2h": cs.ms_d2h,
+               "kernel_launches": int(cs.kernel_launches), "first_status": int(cs.status_ga[0]) if cs.n_objects else 0}
+        self.lib.gar_changeset_free(self._h, C.byref(cs))
+        return out
+
     def diff_device(self) -> GarChangeset:
         """Kernels only; result stays on the device.  Returns the raw struct (counts + timings valid)."""
         cs = GarChangeset()

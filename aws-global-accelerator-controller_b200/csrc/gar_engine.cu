@@ -86,42 +86,88 @@ __device__ __forceinline__ u32 block_excl_scan(u32 v, u32 *total) {
   return r;
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const u32 *in, u32 *tile_sums, u32 n) {
-  u32 base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
-  u32 s = 0;
-#pragma unroll
-  for (int k = 0; k < SCAN_ITEMS; k++)
-    if (base + k < n) s += in[base + k];
-  u32 tot;
-  block_excl_scan(s, &tot);
-  if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
-}
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(u32 *tile_sums, u32 ntiles) {
-  u32 carry = 0;
-  for (u32 b = 0; b < ntiles; b += SCAN_THREADS) {
-    u32 i = b + threadIdx.x;
-    u32 v = i < ntiles ? tile_sums[i] : 0;
-    u32 tot;
-    u32 ex = block_excl_scan(v, &tot);
-    if (i < ntiles) tile_sums[i] = carry + ex;
-    carry += tot;
-  }
-}
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(u32 *data, const u32 *tile_sums, u32 n) {
-  u32 base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+// Single-pass chained scan with decoupled look-back.  Tiles take a ticket (so a tile only ever waits on tiles that
+// already run or ran), publish their aggregate, then their inclusive prefix; a tile's exclusive prefix is the sum
+// of its predecessors' aggregates back to the first published inclusive prefix.
+// state word: bits 62..63 = 0 empty, 1 aggregate, 2 inclusive prefix; low 32 bits = value.
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_lookback(u32 *data, u32 n, unsigned long long *state, u32 *ticket) {
+  __shared__ u32 s_tile, s_excl;
+  if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const u32 tile = s_tile;
+  const u32 base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
   u32 v[SCAN_ITEMS];
+  if (base + SCAN_ITEMS <= n) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(data + base);
+    uint4 a = q[0], b = q[1];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) v[k] = base + k < n ? data[base + k] : 0;
+  }
   u32 s = 0;
 #pragma unroll
-  for (int k = 0; k < SCAN_ITEMS; k++) {
-    v[k] = base + k < n ? data[base + k] : 0;
-    s += v[k];
-  }
-  u32 tot;
-  u32 ex = block_excl_scan(s, &tot) + tile_sums[blockIdx.x];
+  for (int k = 0; k < SCAN_ITEMS; k++) s += v[k];
+  u32 total;
+  u32 ex = block_excl_scan(s, &total);
+  if (threadIdx.x < 32) {  // warp 0 looks back over 32 predecessors per step
+    volatile unsigned long long *st = state;
+    const unsigned lane = threadIdx.x;
+    if (tile == 0) {
+      if (lane == 0) {
+        st[0] = (2ull << 62) | total;
+        s_excl = 0;
+      }
+    } else {
+      if (lane == 0) {
+        st[tile] = (1ull << 62) | total;
+        __threadfence();
+      }
+      u32 excl = 0;
+      for (long long p = (long long)tile - 1;; p -= 32) {
+        long long idx = p - (long long)lane;
+        unsigned long long w = 2ull << 62;  // before tile 0: an inclusive prefix of 0
+        if (idx >= 0) {
+          do {
+            w = st[idx];
+          } while ((w >> 62) == 0);
+        }
+        unsigned pm = __ballot_sync(0xffffffffu, (w >> 62) == 2);
+        int first = __ffs(pm) - 1;  // nearest predecessor that already knows its inclusive prefix
+        u32 val = (first < 0 || (int)lane <= first) ? (u32)w : 0u;
 #pragma unroll
-  for (int k = 0; k < SCAN_ITEMS; k++) {
-    if (base + k < n) data[base + k] = ex;
-    ex += v[k];
+        for (int off = 16; off > 0; off >>= 1) val += __shfl_down_sync(0xffffffffu, val, off);
+        excl += val;  // meaningful in lane 0
+        if (first >= 0) break;
+      }
+      if (lane == 0) {
+        st[tile] = (2ull << 62) | (u32)(excl + total);
+        s_excl = excl;
+      }
+    }
+  }
+  __syncthreads();
+  ex += s_excl;
+  if (base + SCAN_ITEMS <= n) {
+    uint4 a, b;
+    a.x = ex; ex += v[0];
+    a.y = ex; ex += v[1];
+    a.z = ex; ex += v[2];
+    a.w = ex; ex += v[3];
+    b.x = ex; ex += v[4];
+    b.y = ex; ex += v[5];
+    b.z = ex; ex += v[6];
+    b.w = ex;
+    uint4 *q = reinterpret_cast<uint4 *>(data + base);
+    q[0] = a;
+    q[1] = b;
+  } else {
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+      if (base + k < n) data[base + k] = ex;
+      ex += v[k];
+    }
   }
 }
 
@@ -342,11 +388,11 @@ struct gar_engine {
     if (!n) return;
     stage_begin("exclusive_scan");
     u32 ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
-    u32 *tiles = (u32 *)dev_ensure(d_scan_tiles, 4 * (size_t)(ntiles + 1));
-    k_scan_reduce<<<ntiles, SCAN_THREADS, 0, stream>>>(data, tiles, n);
-    k_scan_tiles<<<1, SCAN_THREADS, 0, stream>>>(tiles, ntiles);
-    k_scan_apply<<<ntiles, SCAN_THREADS, 0, stream>>>(data, tiles, n);
-    launches += 3;
+    size_t sbytes = 8 * (size_t)(ntiles + 2);
+    unsigned long long *state = (unsigned long long *)dev_ensure(d_scan_tiles, sbytes);
+    CK(cudaMemsetAsync(state, 0, sbytes, stream));  // tile states + the ticket counter (last word)
+    k_scan_lookback<<<ntiles, SCAN_THREADS, 0, stream>>>(data, n, state, (u32 *)(state + ntiles + 1));
+    launches += 1;
     stage_end();
   }
   void sort_pairs(u32 *keys, u32 *vals, u32 *keys_alt, u32 *vals_alt, u32 n, int bits) {

@@ -689,20 +689,21 @@ GAR_HD PortList desired_ports(const DevTables &T, const Work &W, u32 i) {
 // listener FromPorts and desired ports; changed iff some port has count <= 1, i.e. occurs exactly once in
 // the concatenation of both lists.
 GAR_HD bool ports_changed(PortList l, PortList d) {
-  // fast paths for the common shapes (no duplicates inside a list): identical lists are unchanged
-  if (l.n == d.n) {
-    bool same = true;
-    for (u32 x = 0; x < l.n && same; x++) same = l.p[x] == d.p[x];
-    if (same) return false;  // every port occurs (at least) twice
-  }
-  u32 n = l.n + d.n;
-  for (u32 x = 0; x < n; x++) {
-    i32 px = x < l.n ? l.p[x] : d.p[x - l.n];
+  // A port that sits at the same position in both lists occurs at least twice in the concatenation, so it can never be
+  // the witness.  Strip the common prefix and the common suffix; only the ports of the two middle parts (usually 0-2
+  // of them: one drifted or extra port) have to be counted against the full lists.  Exact for every input; shuffled
+  // lists degrade to the quadratic count.
+  u32 nmin = l.n < d.n ? l.n : d.n;
+  u32 pre = 0;
+  while (pre < nmin && l.p[pre] == d.p[pre]) pre++;
+  u32 suf = 0;
+  while (suf < nmin - pre && l.p[l.n - 1 - suf] == d.p[d.n - 1 - suf]) suf++;
+  u32 ml = l.n - pre - suf, md = d.n - pre - suf;  // middle lengths
+  for (u32 x = 0; x < ml + md; x++) {
+    i32 px = x < ml ? l.p[pre + x] : d.p[pre + (x - ml)];
     u32 cnt = 0;
-    for (u32 y = 0; y < n && cnt < 2; y++) {
-      i32 py = y < l.n ? l.p[y] : d.p[y - l.n];
-      cnt += (py == px);
-    }
+    for (u32 y = 0; y < l.n && cnt < 2; y++) cnt += (l.p[y] == px);
+    for (u32 y = 0; y < d.n && cnt < 2; y++) cnt += (d.p[y] == px);
     if (cnt <= 1) return true;
   }
   return false;

@@ -107,3 +107,46 @@ def test_hostsim_listen_ports_fuzz(garecon, oracle, hostsim):
     want = oracle.diff(snap, "default", mode=1)
     assert got.diff(want) == [], got.describe_first_mismatch(want)
     assert len(got.dports) > 10
+
+
+def test_hostsim_port_multisets(garecon, oracle, hostsim):
+    """listenerPortChanged semantics (global_accelerator.go:458-492) on many list shapes: duplicates, permutations,
+    prefixes, long lists — the kernel strips common prefix/suffix, the oracle builds the reference's count map."""
+    import random
+    rng = random.Random(3)
+    ANN = "aws-global-accelerator-controller.h3poteto.dev/"
+    host = "{:032x}-{:016x}.elb.us-east-1.amazonaws.com"
+    objects, lbs, accs = [], [], []
+    for i in range(300):
+        n = rng.choice([0, 1, 2, 3, 5, 17, 64])
+        want = [rng.choice([80, 443, 8080, 8443, 9000 + rng.randrange(50)]) for _ in range(n)]
+        shape = rng.randrange(7)
+        have = list(want)
+        if shape == 1 and have:
+            have[rng.randrange(len(have))] = 7
+        elif shape == 2:
+            have = have + [rng.choice(have) if have and rng.random() < 0.5 else 7]
+        elif shape == 3 and have:
+            have = have[:-1]
+        elif shape == 4:
+            rng.shuffle(have)
+        elif shape == 5 and have:
+            have = have + have
+        elif shape == 6:
+            have = [p for p in have if rng.random() < 0.7]
+        h = host.format(i, i)
+        name = f"svc{i}"
+        objects.append(dict(kind="service", ns="d", name=name, annotations={ANN + "global-accelerator-managed": "true", "service.beta.kubernetes.io/aws-load-balancer-type": "nlb"},
+                            lb_ingress=[h], ports=[(p, "TCP") for p in want]))
+        arn = f"arn:lb:{i}"
+        lbs.append(dict(region="us-east-1", name=f"{i:032x}", dns=h, arn=arn, state="active"))
+        tags = [("aws-global-accelerator-controller-managed", "true"), ("aws-global-accelerator-owner", f"service/d/{name}"),
+                ("aws-global-accelerator-target-hostname", h), ("aws-global-accelerator-cluster", "default")]
+        accs.append(dict(arn=f"a{i}", name=f"service-d-{name}", dns="x", enabled=True, tags=tags,
+                         listeners=[dict(arn="l", proto="TCP", ports=have, egs=[dict(arn="e", endpoints=[arn])])]))
+    snap = garecon.pack(objects, dict(lbs=lbs, accelerators=accs))
+    hostsim.load(snap)
+    got = hostsim.diff()
+    want_cs = oracle.diff(snap, "default", mode=0)
+    assert got.diff(want_cs) == [], got.describe_first_mismatch(want_cs)
+    assert 30 < len(got.ops) < 300
