@@ -15,7 +15,7 @@
 #include <thread>
 #include <vector>
 
-#include "../../include/garecon.h"
+#include "gsyn.h"
 
 namespace {
 
@@ -68,27 +68,7 @@ const char *kRegions[8] = {"us-east-1", "us-west-2", "eu-west-1", "eu-central-1"
 
 extern "C" {
 
-typedef struct gsyn_config {
-  uint64_t seed;
-  uint32_t n_objects;
-  float frac_ingress;
-  uint32_t n_zones;
-  float frac_r53;          // objects carrying the route53-hostname annotation
-  uint32_t min_hostnames, max_hostnames;
-  float frac_wildcard;
-  uint32_t svc_ports;      // ports per Service
-  float frac_hot;          // hostnames drawn from a small shared pool (adversarial)
-  uint32_t hot_pool;
-  float frac_listen_ann;   // Ingresses carrying alb.ingress.kubernetes.io/listen-ports
-  float frac_unmanaged;    // eligible objects without the managed annotation (cleanup path)
-  float frac_ineligible;   // objects that fail the controller filter
-  // Global Accelerator mix over managed objects (rest: in sync)
-  float p_missing_acc, p_port_drift, p_proto_drift, p_tag_drift, p_missing_listener, p_missing_eg, p_lb_not_active, p_orphan_acc;
-  // Route53 mix over (object, hostname) (rest: in sync)
-  float p_rec_missing, p_alias_drift, p_orphan_rec;
-  float p_dup_ports;       // Services whose port list contains a duplicate (adversarial)
-  char cluster[64];
-} gsyn_config;
+/* struct gsyn_config: see gsyn.h */
 
 // presets follow BASELINE.json "configs"
 void gsyn_preset(int cfg, uint32_t n, gsyn_config *c) {
@@ -615,8 +595,6 @@ Snapshot *generate(const gsyn_config &cfg) {
 }  // namespace
 
 extern "C" {
-
-typedef struct gsyn_snapshot gsyn_snapshot;
 
 // Generate a snapshot; the returned handle owns every buffer the two table structs point to.
 gsyn_snapshot *gsyn_generate(const gsyn_config *cfg) { return (gsyn_snapshot *)generate(*cfg); }

@@ -1,0 +1,37 @@
+/* gsyn.h — C interface of libgarecon_synth.so (synthetic snapshots for tests and bench.py; see gen.cpp). */
+#ifndef GSYN_H
+#define GSYN_H
+#include <stdint.h>
+#include "../../include/garecon.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+typedef struct gsyn_config {
+  uint64_t seed;
+  uint32_t n_objects;
+  float frac_ingress;
+  uint32_t n_zones;
+  float frac_r53;
+  uint32_t min_hostnames, max_hostnames;
+  float frac_wildcard;
+  uint32_t svc_ports;
+  float frac_hot;
+  uint32_t hot_pool;
+  float frac_listen_ann;
+  float frac_unmanaged;
+  float frac_ineligible;
+  float p_missing_acc, p_port_drift, p_proto_drift, p_tag_drift, p_missing_listener, p_missing_eg, p_lb_not_active, p_orphan_acc;
+  float p_rec_missing, p_alias_drift, p_orphan_rec;
+  float p_dup_ports;
+  char cluster[64];
+} gsyn_config;
+typedef struct gsyn_snapshot gsyn_snapshot;
+void gsyn_preset(int cfg, uint32_t n, gsyn_config *c);
+gsyn_snapshot *gsyn_generate(const gsyn_config *cfg);
+const gar_objects *gsyn_objects(const gsyn_snapshot *s);
+const gar_actual *gsyn_actual(const gsyn_snapshot *s);
+void gsyn_free(gsyn_snapshot *s);
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -113,6 +113,47 @@ def _table_arrays(abi, o, a):
     return out
 
 
+def _np_col(ptr, n, dtype):
+    import numpy as np
+    n = int(n)
+    if n == 0:
+        return np.zeros(0, dtype=dtype)
+    addr = C.cast(ptr, C.c_void_p).value
+    return np.frombuffer((C.c_char * (n * np.dtype(dtype).itemsize)).from_address(addr), dtype=dtype, count=n)
+
+
+def kernel_byte_models(o, a, n_ops_ga_obj: int, n_pairs: int, frac_ga: float):
+    """Algorithmic bytes of the two decide kernels (DESIGN.md "Per-kernel byte model"): the unique input bytes each must
+    read at least once + what it must write.  Index/digest structures it reads are counted (they are its inputs);
+    re-reads, sector padding and scratch are not."""
+    import numpy as np
+    L = lambda ptr, n: int((_np_col(ptr, n, np.uint64) >> np.uint64(40)).sum())
+    n = o.n_objects
+    key_bytes = L(o.obj_ns, n) + L(o.obj_name, n) + n
+    host_bytes = L(o.lbi_hostname, o.n_lbi)
+    lb_strings = L(a.lb_region, a.n_lbs) + L(a.lb_name, a.n_lbs) + L(a.lb_dns, a.n_lbs) + L(a.lb_arn, a.n_lbs)
+    tk = _np_col(a.tag_key, a.n_tags, np.uint64) >> np.uint64(40)
+    tv = _np_col(a.tag_val, a.n_tags, np.uint64) >> np.uint64(40)
+    thost_bytes = int(tv[tk == 38].sum())   # aws-global-accelerator-target-hostname
+    owner_bytes = int(tv[tk == 28].sum())   # aws-global-accelerator-owner
+    acc_strings = L(a.acc_name, a.n_accels) + thost_bytes + owner_bytes + L(a.ep_id, a.n_endpoints)
+    ga = frac_ga * (host_bytes + 17 * o.n_lbi + lb_strings + (32 + 16) * a.n_lbs + acc_strings + (32 + 64) * a.n_accels) \
+        + n * (4 + 8 + 16 + 8 + 1) + key_bytes + 4 * o.n_ports * frac_ga + n * 8 + 24 * n_ops_ga_obj
+    nrec, nval = a.n_records, a.n_values
+    val_bytes = L(a.val_value, nval)
+    name_bytes_per_rec = L(a.rec_name, nrec) / max(nrec, 1)
+    alias_bytes_per_rec = L(a.rec_alias_dns, nrec) / max(int(_np_col(a.rec_has_alias, nrec, np.uint8).sum()), 1)
+    acc_dns_per = L(a.acc_dns, a.n_accels) / max(a.n_accels, 1)
+    zone_name_per = L(a.zone_name, a.n_zones) / max(a.n_zones, 1)
+    # per pair: hostname piece, pair row, zone entry + name, the object's value entries (32 B each, ~1 per pair) with the
+    # owner-key bytes of the in-zone one, its record name, the value->alias link, the alias DNS name, the accelerator DNS name
+    ak = _np_col(o.ann_key, o.n_ann, np.uint64) >> np.uint64(40)
+    av = _np_col(o.ann_val, o.n_ann, np.uint64) >> np.uint64(40)
+    ann_r53 = int(av[ak == 63].sum())  # aws-global-accelerator-controller.h3poteto.dev/route53-hostname (63 bytes)
+    r53 = ann_r53 + n_pairs * ((4 + 8) + (1 + 4 + 4) + 32 + zone_name_per + 32 + key_bytes / max(n, 1) + name_bytes_per_rec + 16 + alias_bytes_per_rec + acc_dns_per + 8 + 8 + 1 + 16)
+    return {"ga_objects": int(ga), "r53_pairs": int(r53)}
+
+
 def _pin_host_tables(torch, abi, o, a):
     """cudaHostRegister every generator-owned array so the e2e arm copies from pinned memory."""
     rt = torch.cuda.cudart()
@@ -181,37 +222,23 @@ def main():
         return
 
     import torch
-    import torch.distributed as dist
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
     torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     import __graft_entry__ as ge
-    if rank == 0:
-        ge.ensure_built()
-    if world > 1:
-        dist.barrier()
     pkg = importlib.import_module("aws-global-accelerator-controller_b200")
     synth = importlib.import_module("aws-global-accelerator-controller_b200.synth")
+    ranks_mod = importlib.import_module("aws-global-accelerator-controller_b200.ranks")
+    R = ranks_mod.Ranks(backend="nccl", device=torch.device("cuda", local_rank))
+    if rank == 0:
+        ge.ensure_built()
+    R.barrier()
     abi = pkg.abi
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    def max_over_ranks(x: float) -> float:
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+    barrier, max_over_ranks = R.barrier, R.max_over_ranks
 
     # ---- workload: one synthetic cluster per rank (different seed per rank)
     cfg = synth.preset(args.config, args.objects)
-    cfg.seed = cfg.seed + 1000 * rank
+    cfg.seed = ranks_mod.rank_seed(cfg.seed, rank)
     snap = synth.SynthSnapshot(cfg)
     o, a = snap.objects, snap.actual
     h2d_bytes = sum(int(c) * s for (_, c, s) in _table_arrays(abi, o, a))
@@ -306,9 +333,34 @@ def main():
                          "stages_ms": {s[0]: round(s[1], 4) for s in stages}},
             "kernel_ms_per_step_cuda_events": ms_kernels / args.steps,
         }
-        # the dominant kernel's own byte model (DESIGN.md "Per-kernel byte model"); the pipeline figure is the honest headline
-        line["roofline"]["achieved"] = pipe_achieved
-        line["roofline"]["frac"] = pipe_achieved / peak
+        # the dominant kernel's own byte model (DESIGN.md "Per-kernel byte model"); the pipeline figure is the headline
+        host = pkg.Engine(cluster_name=snap.cluster, device=local_rank)
+        host.load(snap)
+        hcs = host.diff()
+        host.close()
+        frac_ga = float(((hcs.status_ga & 0xFF) > 2).sum() + ((hcs.status_ga & 0xFF) == 1).sum()) / max(args.objects, 1)
+        sb = [int(x) for x in hcs.section_begin]
+        # pairs = hostnames of the objects that reach ensureRoute53's hostname loop = R53 ensure ops + in-sync pairs; the
+        # engine reports the exact count through the r53_pairs stage size: approximate it by (commas + 1) of annotated objects
+        import numpy as _np
+        ak = _np_col(o.ann_key, o.n_ann, _np.uint64) >> _np.uint64(40)
+        n_r53 = int((ak == 63).sum())
+        n_pairs_model = int(round(n_r53 * (cfg.min_hostnames + cfg.max_hostnames) / 2.0 * 0.985))
+        models = kernel_byte_models(o, a, sb[1] - sb[0], n_pairs_model, frac_ga)
+        traffic = {}
+        tp = REPO / "profiles" / "r01_ncu_traffic.json"
+        if tp.exists():
+            traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch", {})
+        kb = models.get(top[0])
+        if kb:
+            line["roofline"]["achieved"] = kb / (top[1] * 1e-3) / 1e9
+            line["roofline"]["frac"] = line["roofline"]["achieved"] / peak
+            line["roofline"]["kernel_bytes"] = kb
+            line["roofline"]["traffic"] = traffic.get(top[0])
+            line["roofline"]["traffic_source"] = "profiles/r01_ncu_traffic.json (ncu --set full, same workload)" if top[0] in traffic else None
+        else:
+            line["roofline"]["achieved"] = pipe_achieved
+            line["roofline"]["frac"] = pipe_achieved / peak
         if not args.no_cpu_baseline:
             ob = importlib.import_module("oracle.binding")
             cores = os.cpu_count() or 1
@@ -323,9 +375,7 @@ def main():
             line["cpu_baseline"] = {"value": cn / cdt, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"config {args.config} generator at {cn} objects, oracle indexed mode, {cores} threads, mean of {reps} runs; Go reference not timed (no toolchain)"}
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    R.close()
 
 
 if __name__ == "__main__":
