@@ -19,6 +19,7 @@ class SynthConfig(C.Structure):
         ("p_missing_acc", C.c_float), ("p_port_drift", C.c_float), ("p_proto_drift", C.c_float), ("p_tag_drift", C.c_float),
         ("p_missing_listener", C.c_float), ("p_missing_eg", C.c_float), ("p_lb_not_active", C.c_float), ("p_orphan_acc", C.c_float),
         ("p_rec_missing", C.c_float), ("p_alias_drift", C.c_float), ("p_orphan_rec", C.c_float), ("p_dup_ports", C.c_float),
+        ("intern_keys", C.c_uint32),
         ("cluster", C.c_char * 64),
     ]
 

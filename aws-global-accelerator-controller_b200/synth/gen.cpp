@@ -13,6 +13,7 @@
 #include <cstring>
 #include <string>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "gsyn.h"
@@ -38,6 +39,16 @@ uint64_t mix(uint64_t a, uint64_t b) {
 
 struct Slab {
   std::string b;
+  std::unordered_map<std::string, gar_str> interned;
+  // constant strings (annotation keys, tag keys): one copy in the slab, shared by every row that references it
+  gar_str intern(const char *p, size_t n, bool on) {
+    if (!on) return put(p, n);
+    auto it = interned.find(std::string(p, n));
+    if (it != interned.end()) return it->second;
+    gar_str r = put(p, n);
+    interned.emplace(std::string(p, n), r);
+    return r;
+  }
   gar_str put(const char *p, size_t n) {
     uint64_t off = b.size();
     b.append(p, n);
@@ -98,6 +109,7 @@ void gsyn_preset(int cfg, uint32_t n, gsyn_config *c) {
   c->p_rec_missing = 0.15f;
   c->p_alias_drift = 0.05f;
   c->p_orphan_rec = 0.05f;
+  c->intern_keys = 1;
   switch (cfg) {
     case 1:  // 100 Services type LoadBalancer, fixture shape (plumbing)
       c->frac_ingress = 0.0f;
@@ -276,7 +288,7 @@ void add_accel(Snapshot &S, const Gen &G, const std::string &arn_id, const std::
   S.acc_dns.push_back(S.as.put(dns));
   S.acc_enabled.push_back(enabled ? 1 : 0);
   auto tag = [&](const char *k, const std::string &v) {
-    S.tag_key.push_back(S.as.put(k, strlen(k)));
+    S.tag_key.push_back(S.as.intern(k, strlen(k), G.c.intern_keys != 0));
     S.tag_val.push_back(S.as.put(v));
   };
   tag("aws-global-accelerator-controller-managed", "true");
@@ -284,7 +296,7 @@ void add_accel(Snapshot &S, const Gen &G, const std::string &arn_id, const std::
   tag("aws-global-accelerator-target-hostname", thost);
   tag("aws-global-accelerator-cluster", cluster);
   for (auto &t : user_tags) {
-    S.tag_key.push_back(S.as.put(t.first));
+    S.tag_key.push_back(S.as.intern(t.first.data(), t.first.size(), G.c.intern_keys != 0));
     S.tag_val.push_back(S.as.put(t.second));
   }
   S.tag_b.push_back((uint32_t)S.tag_key.size());
@@ -317,7 +329,7 @@ Snapshot *generate(const gsyn_config &cfg) {
   S.lbi_b.push_back(0);
   S.port_b.push_back(0);
   auto ann = [&](const char *k, const std::string &v) {
-    S.ann_key.push_back(S.os.put(k, strlen(k)));
+    S.ann_key.push_back(S.os.intern(k, strlen(k), cfg.intern_keys != 0));
     S.ann_val.push_back(S.os.put(v));
   };
   gar_str tcp = 0, udp = 0;

@@ -23,6 +23,8 @@ typedef struct gsyn_config {
   float p_missing_acc, p_port_drift, p_proto_drift, p_tag_drift, p_missing_listener, p_missing_eg, p_lb_not_active, p_orphan_acc;
   float p_rec_missing, p_alias_drift, p_orphan_rec;
   float p_dup_ports;
+  uint32_t intern_keys; /* 1: annotation keys and tag keys are stored once in the slab and referenced by every row (what a
+                           packer with a small map[string]ref does); 0: every row carries its own copy */
   char cluster[64];
 } gsyn_config;
 typedef struct gsyn_snapshot gsyn_snapshot;
