@@ -95,6 +95,10 @@ class GarConfig(C.Structure):
     _fields_ = [("abi_version", C.c_uint32), ("device", C.c_int32), ("cluster_name", C.c_char_p), ("flags", C.c_uint32)]
 
 
+class GarKeyset(C.Structure):
+    _fields_ = [("n_rows", C.c_uint32), ("rows", _u32p), ("n_deleted", C.c_uint32), ("deleted_kind", _u8p), ("deleted_key", C.POINTER(C.c_char_p))]
+
+
 class GarStageTiming(C.Structure):
     _fields_ = [("name", C.c_char_p), ("ms", C.c_float), ("launches", C.c_uint32), ("bytes", C.c_uint64)]
 
@@ -135,7 +139,7 @@ def _np_from(ptr, n, dtype):
 class ChangeSet:
     """Host copy of a gar_changeset (plain numpy arrays; safe after the C-side object is freed)."""
 
-    def __init__(self, cs: GarChangeset):
+    def __init__(self, cs: GarChangeset, keyset: bool = False):
         n = cs.n_objects
         self.n_objects = n
         self.status_ga = _np_from(cs.status_ga, n, np.uint32)
@@ -146,7 +150,7 @@ class ChangeSet:
         self.tok_code = _np_from(cs.tok_code, cs.n_lbi, np.uint8)
         self.tok_name = _np_from(cs.tok_name, cs.n_lbi, np.uint64)
         self.tok_region = _np_from(cs.tok_region, cs.n_lbi, np.uint64)
-        self.dport_begin = _np_from(cs.dport_begin, n + 1, np.uint32)
+        self.dport_begin = _np_from(cs.dport_begin, 0 if keyset else n + 1, np.uint32)
         self.dports = _np_from(cs.dports, cs.n_dports, np.int32)
         self.ms_h2d, self.ms_kernels, self.ms_d2h = cs.ms_h2d, cs.ms_kernels, cs.ms_d2h
         self.kernel_launches = cs.kernel_launches
@@ -184,6 +188,22 @@ class ChangeSet:
         return h
 
 
+def make_keyset(rows, deleted=()):
+    """ctypes gar_keyset from a list of object rows and [(kind, "ns/name"), ...]; keeps its buffers alive on the struct."""
+    ks = GarKeyset()
+    r = np.ascontiguousarray(np.asarray(list(rows), dtype=np.uint32))
+    backing = r if r.size else np.zeros(1, dtype=np.uint32)
+    ks.n_rows = int(r.size)
+    ks.rows = backing.ctypes.data_as(_u32p)
+    kinds = np.ascontiguousarray(np.asarray([k for k, _ in deleted] or [0], dtype=np.uint8))
+    keys = (C.c_char_p * max(1, len(deleted)))(*[s.encode() for _, s in deleted])
+    ks.n_deleted = len(deleted)
+    ks.deleted_kind = kinds.ctypes.data_as(_u8p)
+    ks.deleted_key = C.cast(keys, C.POINTER(C.c_char_p))
+    ks._keep = (backing, kinds, keys)
+    return ks
+
+
 _lib = None
 
 
@@ -206,6 +226,8 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
     for fn in ("gar_diff", "gar_diff_device"):
         getattr(lib, fn).argtypes = [C.c_void_p, C.POINTER(GarChangeset)]
         getattr(lib, fn).restype = C.c_int
+    lib.gar_diff_keys.argtypes = [C.c_void_p, C.POINTER(GarKeyset), C.POINTER(GarChangeset)]
+    lib.gar_diff_keys.restype = C.c_int
     lib.gar_changeset_free.argtypes = [C.c_void_p, C.POINTER(GarChangeset)]
     lib.gar_changeset_free.restype = None
     lib.gar_last_error.argtypes = [C.c_void_p]
@@ -223,7 +245,7 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
 
 EXPORTED_SYMBOLS = (
     "gar_engine_create", "gar_engine_destroy", "gar_snapshot_load", "gar_snapshot_attach_device", "gar_diff",
-    "gar_diff_device", "gar_changeset_free", "gar_last_error", "gar_version", "gar_algorithmic_bytes",
+    "gar_diff_device", "gar_diff_keys", "gar_changeset_free", "gar_last_error", "gar_version", "gar_algorithmic_bytes",
     "gar_last_stage_timings",
 )
 
@@ -265,6 +287,18 @@ class Engine:
         try:
             out = ChangeSet(cs)
             out.algorithmic_bytes = int(self.lib.gar_algorithmic_bytes(self._h, C.byref(cs)))
+        finally:
+            self.lib.gar_changeset_free(self._h, C.byref(cs))
+        return out
+
+    def diff_keys(self, rows, deleted=()) -> ChangeSet:
+        """Incremental mode: decisions for the object rows `rows` and the deleted keys [(kind, "ns/name"), ...]."""
+        ks = make_keyset(rows, deleted)
+        cs = GarChangeset()
+        self._check(self.lib.gar_diff_keys(self._h, C.byref(ks), C.byref(cs)))
+        try:
+            cs.n_lbi = 0
+            out = ChangeSet(cs, keyset=True)
         finally:
             self.lib.gar_changeset_free(self._h, C.byref(cs))
         return out

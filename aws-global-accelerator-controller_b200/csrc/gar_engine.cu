@@ -289,6 +289,8 @@ struct gar_engine {
   DBuf cluster_dev;
   DBuf slot[S_NSLOTS];
   DBuf d_status_ga, d_status_r53, d_derived, d_ops, d_tok_code, d_tok_name, d_tok_region, d_dport_begin, d_dports, d_scan_tiles, d_hist;
+  DBuf d_derived_keys, d_key_rows, d_del_kind, d_del_key, d_del_slab;  // incremental mode
+  Pipeline<gar_engine> *pipe = nullptr;  // lives as long as the loaded snapshot: keeps digests + indexes resident
   std::vector<HostResult *> free_results;
   float ms_h2d = 0;
   u32 launches = 0;
@@ -423,6 +425,7 @@ struct gar_engine {
     CK(cudaStreamSynchronize(stream));
   }
   void *out_derived(u32 n) { return dev_ensure(d_derived, 4 * (size_t)(n + 1)); }
+  void *out_derived_keys(u32 n) { return dev_ensure(d_derived_keys, 4 * (size_t)(n + 1)); }
   void *out_dport_begin(u32 n) { return dev_ensure(d_dport_begin, 4 * (size_t)(n + 2)); }
   void *out_tok_code(u32 n) { return dev_ensure(d_tok_code, (size_t)n + 1); }
   void *out_tok_name(u32 n) { return dev_ensure(d_tok_name, 8 * (size_t)(n + 1)); }
@@ -592,6 +595,8 @@ static const Tp *upload(gar_engine *e, const Tp *host, size_t count, size_t pad_
 static void do_load(gar_engine *e, const gar_objects *o, const gar_actual *a) {
   if (!o || !a) throw InvalidError{"NULL table struct"};
   e->loaded = false;
+  delete e->pipe;  // the prepared state belongs to the previous snapshot
+  e->pipe = nullptr;
   CK(cudaSetDevice(e->device));
   e->in_used = 0;
   DevTables &T = e->T;
@@ -659,7 +664,7 @@ static void do_load(gar_engine *e, const gar_objects *o, const gar_actual *a) {
 
 // ------------------------------------------------------------------ diff
 
-static void do_diff(gar_engine *e, gar_changeset *out, bool to_host) {
+static void do_diff(gar_engine *e, gar_changeset *out, bool to_host, const gar_keyset *ks = nullptr) {
   if (!e->loaded) throw InvalidError{"no snapshot loaded"};
   CK(cudaSetDevice(e->device));
   memset(out, 0, sizeof(*out));
@@ -667,20 +672,56 @@ static void do_diff(gar_engine *e, gar_changeset *out, bool to_host) {
   e->marks.clear();
   e->events_used = 0;
   e->stage_depth = 0;
-  Pipeline<gar_engine> P(*e, e->T);
+  if (!e->pipe) {
+    e->pipe = new Pipeline<gar_engine>(*e, e->T);
+    e->T.cluster = (const u8 *)e->cluster_dev.p;
+  }
+  Pipeline<gar_engine> &P = *e->pipe;
   DiffCounts dc{};
+  auto ops_alloc = [&](u64 nops) { return e->dev_ensure(e->d_ops, sizeof(gar_op) * (size_t)(nops + 1)); };
   CK(cudaEventRecord(e->ev[2], e->stream));
-  int rc = P.run(&dc, [&](u64 nops) { return e->dev_ensure(e->d_ops, sizeof(gar_op) * (size_t)(nops + 1)); });
-  if (rc == GAR_RETRY_WITH_RADIX) {  // some hash bucket was too large for the per-bucket build: redo with the stable radix sort
-    P.force_radix = true;
-    rc = P.run(&dc, [&](u64 nops) { return e->dev_ensure(e->d_ops, sizeof(gar_op) * (size_t)(nops + 1)); });
+  int rc;
+  u32 n_out = e->T.o.n_objects;
+  if (!ks) {
+    rc = P.run(&dc, ops_alloc);
+  } else {
+    // incremental mode: upload the key batch (rows + deleted keys)
+    if ((ks->n_rows && !ks->rows) || (ks->n_deleted && (!ks->deleted_kind || !ks->deleted_key))) throw InvalidError{"NULL key set arrays"};
+    for (u32 k = 0; k < ks->n_rows; k++)
+      if (ks->rows[k] >= e->T.o.n_objects) throw InvalidError{"key set row out of range"};
+    n_out = ks->n_rows;
+    u32 *rows = (u32 *)e->dev_ensure(e->d_key_rows, 4 * (size_t)(ks->n_rows + 1));
+    if (ks->n_rows) CK(cudaMemcpyAsync(rows, ks->rows, 4 * (size_t)ks->n_rows, cudaMemcpyHostToDevice, e->stream));
+    std::vector<u8> slab;
+    std::vector<gar_str> refs(ks->n_deleted);
+    std::vector<u8> kinds(ks->n_deleted);
+    for (u32 k = 0; k < ks->n_deleted; k++) {
+      if (!ks->deleted_key[k] || ks->deleted_kind[k] > GAR_KIND_INGRESS) throw InvalidError{"bad deleted key"};
+      size_t len = strlen(ks->deleted_key[k]);
+      refs[k] = GAR_STR(slab.size(), len);
+      slab.insert(slab.end(), ks->deleted_key[k], ks->deleted_key[k] + len);
+      kinds[k] = ks->deleted_kind[k];
+    }
+    slab.resize(slab.size() + GAR_SLAB_PAD, 0);
+    u8 *dslab = (u8 *)e->dev_ensure(e->d_del_slab, slab.size());
+    u8 *dkind = (u8 *)e->dev_ensure(e->d_del_kind, ks->n_deleted + 1);
+    gar_str *dkey = (gar_str *)e->dev_ensure(e->d_del_key, 8 * (size_t)(ks->n_deleted + 1));
+    CK(cudaMemcpyAsync(dslab, slab.data(), slab.size(), cudaMemcpyHostToDevice, e->stream));
+    if (ks->n_deleted) {
+      CK(cudaMemcpyAsync(dkind, kinds.data(), ks->n_deleted, cudaMemcpyHostToDevice, e->stream));
+      CK(cudaMemcpyAsync(dkey, refs.data(), 8 * (size_t)ks->n_deleted, cudaMemcpyHostToDevice, e->stream));
+    }
+    CK(cudaStreamSynchronize(e->stream));  // the staging vectors go out of scope
+    rc = P.run_keys(rows, ks->n_rows, DelKeys{dkind, dkey, dslab}, ks->n_deleted, &dc, ops_alloc);
   }
   CK(cudaEventRecord(e->ev[3], e->stream));
   if (rc == GAR_E_INVALID) {
     CK(cudaStreamSynchronize(e->stream));
     throw InvalidError{"objects layout rule violated: obj_ns and obj_name must be slices of one \"ns/name\" key string"};
   }
-  const u32 n = e->T.o.n_objects, nlbi = e->T.o.n_lbi;
+  if (rc != GAR_OK) throw InvalidError{"index build did not converge"};
+  const u32 n = n_out, nlbi = ks ? 0 : e->T.o.n_lbi;
+  const DBuf &d_derived_src = ks ? e->d_derived_keys : e->d_derived;
   out->n_objects = n;
   out->n_ops = dc.n_ops;
   for (int k = 0; k <= GAR_N_SECTIONS; k++) out->section_begin[k] = dc.section_begin[k];
@@ -702,17 +743,17 @@ static void do_diff(gar_engine *e, gar_changeset *out, bool to_host) {
     };
     out->status_ga = (const u32 *)pull(h->status_ga, e->d_status_ga, 4 * (size_t)n);
     out->status_r53 = (const u32 *)pull(h->status_r53, e->d_status_r53, 4 * (size_t)n);
-    out->derived = (const u32 *)pull(h->derived, e->d_derived, 4 * (size_t)n);
+    out->derived = (const u32 *)pull(h->derived, d_derived_src, 4 * (size_t)n);
     out->ops = (const gar_op *)pull(h->ops, e->d_ops, sizeof(gar_op) * (size_t)dc.n_ops);
     out->tok_code = (const u8 *)pull(h->tok_code, e->d_tok_code, nlbi);
     out->tok_name = (const gar_str *)pull(h->tok_name, e->d_tok_name, 8 * (size_t)nlbi);
     out->tok_region = (const gar_str *)pull(h->tok_region, e->d_tok_region, 8 * (size_t)nlbi);
-    out->dport_begin = (const u32 *)pull(h->dport_begin, e->d_dport_begin, 4 * (size_t)(n + 1));
+    out->dport_begin = (const u32 *)pull(h->dport_begin, e->d_dport_begin, ks ? 0 : 4 * (size_t)(n + 1));
     out->dports = (const i32 *)pull(h->dports, e->d_dports, 4 * (size_t)dc.n_dports);
   } else {
     out->status_ga = (const u32 *)e->d_status_ga.p;
     out->status_r53 = (const u32 *)e->d_status_r53.p;
-    out->derived = (const u32 *)e->d_derived.p;
+    out->derived = (const u32 *)d_derived_src.p;
     out->ops = (const gar_op *)e->d_ops.p;
     out->tok_code = (const u8 *)e->d_tok_code.p;
     out->tok_name = (const gar_str *)e->d_tok_name.p;
@@ -813,6 +854,8 @@ void gar_engine_destroy(gar_engine *e) {
   if (e->stream) cudaStreamSynchronize(e->stream);
   for (auto &b : e->in) cudaFree(b.p);
   for (auto &b : e->slot) cudaFree(b.p);
+  delete e->pipe;
+  for (DBuf *b : {&e->d_derived_keys, &e->d_key_rows, &e->d_del_kind, &e->d_del_key, &e->d_del_slab}) cudaFree(b->p);
   for (DBuf *b : {&e->cluster_dev, &e->d_status_ga, &e->d_status_r53, &e->d_derived, &e->d_ops, &e->d_tok_code, &e->d_tok_name, &e->d_tok_region,
                   &e->d_dport_begin, &e->d_dports, &e->d_scan_tiles, &e->d_hist})
     cudaFree(b->p);
@@ -838,6 +881,8 @@ int gar_snapshot_load(gar_engine *e, const gar_objects *desired, const gar_actua
 int gar_snapshot_attach_device(gar_engine *e, const gar_objects *desired, const gar_actual *actual) {
   return guarded(e, [&] {
     if (!desired || !actual) throw InvalidError{"NULL table struct"};
+    delete e->pipe;
+    e->pipe = nullptr;
     e->T.o = *desired;
     e->T.a = *actual;
     e->T.cluster = (const u8 *)e->cluster_dev.p;
@@ -857,6 +902,11 @@ int gar_diff(gar_engine *e, gar_changeset *out) {
 int gar_diff_device(gar_engine *e, gar_changeset *out) {
   if (!out) return GAR_E_INVALID;
   return guarded(e, [&] { do_diff(e, out, false); });
+}
+
+int gar_diff_keys(gar_engine *e, const gar_keyset *keys, gar_changeset *out) {
+  if (!out || !keys) return GAR_E_INVALID;
+  return guarded(e, [&] { do_diff(e, out, true, keys); });
 }
 
 void gar_changeset_free(gar_engine *e, gar_changeset *cs) {

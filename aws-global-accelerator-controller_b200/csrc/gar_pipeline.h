@@ -342,35 +342,39 @@ struct CountLayout {
 // up to OPS_STAGE_CAP ops into the object's staging slot; after the scan FCompactOps moves staged ops to their
 // final position (objects with more ops than the slot holds are re-evaluated straight into the output).
 constexpr u32 OPS_STAGE_CAP = 4;
+// `rows` (nullable) selects a subset of object rows (incremental mode): slot t evaluates object rows[t]; status, counts
+// and staging are indexed by the slot, everything about the object by its row.
 struct FGaObj {
   DevTables T;
   Work W;
-  CountLayout L;
-  u32 *counts;
-  gar_op *stage;  // [n * OPS_STAGE_CAP]
+  u32 *counts;    // [slots] this section's counts
+  gar_op *stage;  // [slots * OPS_STAGE_CAP]
   u32 *status;
-  GAR_HD void operator()(u32 i, bool valid) const {
-    OpSink s{stage + (size_t)i * OPS_STAGE_CAP, 0, OPS_STAGE_CAP};
+  const u32 *rows;
+  GAR_HD void operator()(u32 t, bool valid) const {
+    u32 i = (rows && valid) ? rows[t] : t;
+    OpSink s{stage + (size_t)t * OPS_STAGE_CAP, 0, OPS_STAGE_CAP};
     u32 st = ga_reconcile(T, W, i, valid, s);
     if (valid) {
-      status[i] = st;
-      counts[L.ga_obj(i)] = s.n;
+      status[t] = st;
+      counts[t] = s.n;
     }
   }
 };
 struct FR53Obj {
   DevTables T;
   Work W;
-  CountLayout L;
   u32 *counts;
   gar_op *stage;
   u32 *status;
-  GAR_HD void operator()(u32 i, bool valid) const {
-    OpSink s{stage + (size_t)i * OPS_STAGE_CAP, 0, OPS_STAGE_CAP};
-    u32 st = r53_combine(T, W, i, valid, valid ? status[i] : 0, s);
+  const u32 *rows;
+  GAR_HD void operator()(u32 t, bool valid) const {
+    u32 i = (rows && valid) ? rows[t] : t;
+    OpSink s{stage + (size_t)t * OPS_STAGE_CAP, 0, OPS_STAGE_CAP};
+    u32 st = r53_combine(T, W, i, t, valid, valid ? status[t] : 0, s);
     if (valid) {
-      status[i] = st;
-      counts[L.r53_obj(i)] = s.n;
+      status[t] = st;
+      counts[t] = s.n;
     }
   }
 };
@@ -383,32 +387,79 @@ struct FR53Prepare {
   DevTables T;
   Work W;
   u32 *status;
-  GAR_HD void operator()(u32 i, bool valid) const { r53_prepare(T, W, i, valid, status); }
+  const u32 *rows;
+  GAR_HD void operator()(u32 t, bool valid) const { r53_prepare(T, W, (rows && valid) ? rows[t] : t, t, valid, status); }
 };
 struct FR53FillPairs {
   DevTables T;
   Work W;
-  GAR_HD void operator()(u32 i) const { r53_fill_pairs(T, W, i); }
+  const u32 *rows;
+  GAR_HD void operator()(u32 t) const { r53_fill_pairs(T, W, rows ? rows[t] : t, t); }
 };
 struct FR53Pair {
   DevTables T;
   Work W;
   GAR_HD void operator()(u32 p, bool valid) const { r53_pair(T, W, p, valid); }
 };
+// incremental mode: processDelete of one work-queue key that left the cache (globalaccelerator/service.go:28-52,
+// route53/service.go:29-46): cleanup of everything the key owns, in the reference's order
+struct DelKeys {
+  const u8 *kind;
+  const gar_str *key;  // refs into `slab`
+  const u8 *slab;
+};
+struct FDelKeyGa {
+  DevTables T;
+  Work W;
+  DelKeys D;
+  u32 *counts;   // count pass: written; emit pass: scanned
+  gar_op *ops;   // nullptr in the count pass
+  GAR_HD void operator()(u32 k) const {
+    u32 kind = D.kind[k];
+    Str key = mkstr(D.slab, D.key[k]);
+    OpSink s{ops ? ops + counts[k] : nullptr, 0, 0xFFFFFFFFu};
+    OwnerIter it = owner_open(W, key_hash_kinded(kind, key), key);
+    for (u32 acc; (acc = owner_next(T, W, kind, it)) != GAR_NONE;) put_delete_chain(T, s, GAR_NONE, 0, acc);
+    if (!ops) counts[k] = s.n;
+  }
+};
+struct FDelKeyR53 {
+  DevTables T;
+  Work W;
+  DelKeys D;
+  u32 *counts;
+  gar_op *ops;
+  GAR_HD void operator()(u32 k) const {
+    u32 kind = D.kind[k];
+    Str key = mkstr(D.slab, D.key[k]);
+    OpSink s{ops ? ops + counts[k] : nullptr, 0, 0xFFFFFFFFu};
+    Owned ow;
+    owned_collect(T, W, key_hash_kinded(kind, key), kind, key, ow);
+    r53_cleanup(T, W, GAR_NONE, 0, ow, s);
+    if (!ops) counts[k] = s.n;
+  }
+};
+struct FGatherDerived {
+  const u32 *derived, *rows;
+  u32 *out;
+  GAR_HD void operator()(u32 t) const { out[t] = derived[rows[t]] & 0xFFu; }
+};
 struct FCompactOps {
   DevTables T;
   Work W;
-  const u32 *scanned;  // exclusive-scanned counts of this section (entry i+1 exists: the layout is contiguous)
+  const u32 *scanned;  // exclusive-scanned counts of this section (entry t+1 exists: the layout is contiguous)
   const gar_op *stage;
   gar_op *ops;
   u32 ctrl;
-  GAR_HD void operator()(u32 i, bool valid) const {
+  const u32 *rows;
+  GAR_HD void operator()(u32 t, bool valid) const {
+    u32 i = (rows && valid) ? rows[t] : t;
     u32 off = 0, c = 0;
     if (valid) {
-      off = scanned[i];
-      c = scanned[i + 1] - off;
+      off = scanned[t];
+      c = scanned[t + 1] - off;
       if (c <= OPS_STAGE_CAP)
-        for (u32 k = 0; k < c; k++) ops[off + k] = stage[(size_t)i * OPS_STAGE_CAP + k];
+        for (u32 k = 0; k < c; k++) ops[off + k] = stage[(size_t)t * OPS_STAGE_CAP + k];
     }
     // objects with more ops than a staging slot holds are re-evaluated straight into the output (warp-uniform:
     // the decide functions vote, so the whole warp enters when any lane needs it)
@@ -416,7 +467,7 @@ struct FCompactOps {
     if (GAR_ANY(redo)) {
       OpSink s{ops + off, 0, redo ? 0xFFFFFFFFu : 0u};
       if (ctrl == GAR_CTRL_GA) ga_reconcile(T, W, i, redo, s);
-      else r53_reconcile(T, W, i, redo, s);
+      else r53_reconcile(T, W, i, redo, s);  // the per-object routine: same decisions as prepare/pairs/combine
     }
   }
 };
@@ -536,14 +587,16 @@ struct Pipeline {
     return HashIdx{begin, ent, nb - 1};
   }
 
-  // Runs every stage.  `ops_out` is called once the op count is known and must return the device buffer the
-  // ops are written to (capacity >= n_ops).
-  template <class OpsAlloc>
-  int run(DiffCounts *dc, OpsAlloc ops_alloc) {
+  // ---- prepare: everything that depends on the snapshot only (stages 1-3).  Runs once per loaded snapshot; the
+  // digests and indexes stay resident for every later diff (full or incremental).
+  bool prepared = false;
+  u64 n_dports = 0;
+  u32 *errflag = nullptr;
+
+  int prepare() {
     const u32 n = T.o.n_objects, nlbi = T.o.n_lbi, nacc = T.a.n_accels, nzone = T.a.n_zones, nrec = T.a.n_records, nval = T.a.n_values;
     W.derived = (u32 *)be.ensure(S_DERIVED, 4 * (size_t)(n + 1));
     u32 *derived_public = (u32 *)be.out_derived(n);
-    u8 *oflags = (u8 *)be.ensure(S_OFLAGS, n + 1);
     W.okey_hash = (u64 *)be.ensure(S_OKEY_HASH, 8 * (size_t)(n + 1));
     W.ann_r53 = (gar_str *)be.ensure(S_ANN_R53, 8 * (size_t)(n + 1));
     W.ann_name = (gar_str *)be.ensure(S_ANN_NAME, 8 * (size_t)(n + 1));
@@ -572,12 +625,11 @@ struct Pipeline {
     W.r53_mode = (u8 *)be.ensure(S_R53_MODE, (size_t)n + 1);
     W.r53_acc = (u32 *)be.ensure(S_R53_ACC, 4 * (size_t)(n + 1));
     W.r53_acc_dns = (gar_str *)be.ensure(S_R53_ACC_DNS, 8 * (size_t)(n + 1));
-    W.pair_begin = (u32 *)be.ensure(S_PAIR_BEGIN, 4 * (size_t)(n + 2));
-    u32 *errflag = (u32 *)be.ensure(S_ERRFLAG, 64);
+    errflag = (u32 *)be.ensure(S_ERRFLAG, 64);
     be.fill32(errflag, 0, 4);
 
     // stage 1: row-local preprocessing
-    if (n) be.for_each("classify_objects", n, FClassify{T, W, derived_public, oflags, errflag});
+    if (n) be.for_each("classify_objects", n, FClassify{T, W, derived_public, nullptr, errflag});
     if (nlbi) be.for_each("tokenise_hostnames", nlbi, FTokenise{T, W});
     if (nacc) be.for_each("digest_accelerators", nacc, FDigestAccel{T, W});
     if (nrec) be.for_each("prepare_records", nrec, FPrepareRecord{T, W});
@@ -591,8 +643,7 @@ struct Pipeline {
     u32 hdr[2] = {0, 0};
     be.for_each("gather_header", 1, FGatherHeader{W.dport_begin + n, errflag, errflag + 4});
     be.download(hdr, errflag + 4, sizeof(hdr));
-    dc->n_dports = hdr[0];
-    dc->bad_keys = hdr[1];
+    n_dports = hdr[0];
     if (hdr[1]) return GAR_E_INVALID;
     W.dports = (i32 *)be.out_dports(hdr[0]);
     if (n && hdr[0]) be.for_each("listen_ports_write", n, FJsonWrite{T, W});
@@ -609,7 +660,33 @@ struct Pipeline {
     W.ix_obj = build_index(S_IX_OBJ, n, 1, FRowObj{T, W}, overflow, force_radix);
     if (nval) be.for_each("mark_orphan_values", nval, FMarkOrphanValue{T, W});
     W.ix_ovn = build_index(S_IX_OVN, nval, 8, FRowOvn{T, W}, overflow, force_radix);
+    return GAR_OK;
+  }
 
+  // route53 ensure in relational form over `slots` object slots (rows == nullptr: slot = object row)
+  void r53_relational(u32 slots, const u32 *rows, u32 *st_r53) {
+    W.pair_begin = (u32 *)be.ensure(S_PAIR_BEGIN, 4 * (size_t)(slots + 2));
+    be.fill32(W.pair_begin, 0, (size_t)slots + 1);
+    if (slots) be.for_each_warp("r53_prepare", slots, FR53Prepare{T, W, st_r53, rows});
+    be.exclusive_scan(W.pair_begin, slots + 1);
+    u32 npairs = 0;
+    be.download(&npairs, W.pair_begin + slots, 4);
+    W.pair_obj = (u32 *)be.ensure(S_PAIR_OBJ, 4 * (size_t)(npairs + 1));
+    W.pair_hn = (gar_str *)be.ensure(S_PAIR_HN, 8 * (size_t)(npairs + 1));
+    W.pair_code = (u8 *)be.ensure(S_PAIR_CODE, (size_t)npairs + 1);
+    W.pair_zone = (u32 *)be.ensure(S_PAIR_ZONE, 4 * (size_t)(npairs + 1));
+    W.pair_rec = (u32 *)be.ensure(S_PAIR_REC, 4 * (size_t)(npairs + 1));
+    if (npairs) {
+      be.for_each("r53_fill_pairs", slots, FR53FillPairs{T, W, rows});
+      be.for_each_warp("r53_pairs", npairs, FR53Pair{T, W});
+    }
+  }
+
+  // ---- full diff: every object + the orphan sections
+  template <class OpsAlloc>
+  int decide_all(DiffCounts *dc, OpsAlloc ops_alloc) {
+    const u32 n = T.o.n_objects, nacc = T.a.n_accels, nrec = T.a.n_records, nval = T.a.n_values;
+    u32 *overflow = errflag + 1;
     // stage 4: evaluate every object once (status + count + staged ops); count the orphan sections
     CountLayout L{n, nacc, nrec, nval};
     u32 *counts = (u32 *)be.ensure(S_COUNTS, 4 * (size_t)(L.total() + 2));
@@ -618,24 +695,10 @@ struct Pipeline {
     gar_op *stage_r53 = (gar_op *)be.ensure(S_STAGE_R53, sizeof(gar_op) * ((size_t)n * OPS_STAGE_CAP + 1));
     u32 *st_ga = (u32 *)be.out_status_ga(n);
     u32 *st_r53 = (u32 *)be.out_status_r53(n);
-    if (n) be.for_each_warp("ga_objects", n, FGaObj{T, W, L, counts, stage_ga, st_ga});
+    if (n) be.for_each_warp("ga_objects", n, FGaObj{T, W, counts + L.ga_obj(0), stage_ga, st_ga, nullptr});
     if (nacc) be.for_each("ga_orphans_count", nacc, FGaOrphan{T, W, L, counts, nullptr});
-    // route53 ensure in relational form: per object -> (object, hostname) pairs -> per object
-    be.fill32(W.pair_begin, 0, (size_t)n + 1);
-    if (n) be.for_each_warp("r53_prepare", n, FR53Prepare{T, W, st_r53});
-    be.exclusive_scan(W.pair_begin, n + 1);
-    u32 npairs = 0;
-    be.download(&npairs, W.pair_begin + n, 4);
-    W.pair_obj = (u32 *)be.ensure(S_PAIR_OBJ, 4 * (size_t)(npairs + 1));
-    W.pair_hn = (gar_str *)be.ensure(S_PAIR_HN, 8 * (size_t)(npairs + 1));
-    W.pair_code = (u8 *)be.ensure(S_PAIR_CODE, (size_t)npairs + 1);
-    W.pair_zone = (u32 *)be.ensure(S_PAIR_ZONE, 4 * (size_t)(npairs + 1));
-    W.pair_rec = (u32 *)be.ensure(S_PAIR_REC, 4 * (size_t)(npairs + 1));
-    if (npairs) {
-      be.for_each("r53_fill_pairs", n, FR53FillPairs{T, W});
-      be.for_each_warp("r53_pairs", npairs, FR53Pair{T, W});
-    }
-    if (n) be.for_each_warp("r53_objects", n, FR53Obj{T, W, L, counts, stage_r53, st_r53});
+    r53_relational(n, nullptr, st_r53);
+    if (n) be.for_each_warp("r53_objects", n, FR53Obj{T, W, counts + L.r53_obj(0), stage_r53, st_r53, nullptr});
     if (nrec) be.for_each("r53_orphan_alias_count", nrec, FR53OrphanAlias{T, W, L, counts, nullptr});
     if (nval) be.for_each("r53_orphan_value_count", nval, FR53OrphanValue{T, W, L, counts, nullptr});
     be.exclusive_scan(counts, L.total() + 1);
@@ -646,14 +709,79 @@ struct Pipeline {
     if (sec[5] && !force_radix) return GAR_RETRY_WITH_RADIX;  // an index bucket was too large for the fast build
     for (int k = 0; k < 5; k++) dc->section_begin[k] = sec[k];
     dc->n_ops = sec[4];
+    dc->n_dports = n_dports;
 
     // stage 5: move ops to their final, canonical positions
     gar_op *ops = (gar_op *)ops_alloc(dc->n_ops);
-    if (n) be.for_each_warp("ga_objects_compact", n, FCompactOps{T, W, counts + L.ga_obj(0), stage_ga, ops, GAR_CTRL_GA});
+    if (n) be.for_each_warp("ga_objects_compact", n, FCompactOps{T, W, counts + L.ga_obj(0), stage_ga, ops, GAR_CTRL_GA, nullptr});
     if (nacc) be.for_each("ga_orphans_emit", nacc, FGaOrphan{T, W, L, counts, ops});
-    if (n) be.for_each_warp("r53_objects_compact", n, FCompactOps{T, W, counts + L.r53_obj(0), stage_r53, ops, GAR_CTRL_R53});
+    if (n) be.for_each_warp("r53_objects_compact", n, FCompactOps{T, W, counts + L.r53_obj(0), stage_r53, ops, GAR_CTRL_R53, nullptr});
     if (nrec) be.for_each("r53_orphan_alias_emit", nrec, FR53OrphanAlias{T, W, L, counts, ops});
     if (nval) be.for_each("r53_orphan_value_emit", nval, FR53OrphanValue{T, W, L, counts, ops});
     return GAR_OK;
+  }
+
+  // ---- incremental diff: `m` object rows + `nd` deleted keys (device arrays).  counts layout:
+  // [GA rows: m][GA deleted keys: nd][R53 rows: m][R53 deleted keys: nd][total]
+  template <class OpsAlloc>
+  int decide_keys(const u32 *rows, u32 m, DelKeys D, u32 nd, DiffCounts *dc, OpsAlloc ops_alloc) {
+    u32 *overflow = errflag + 1;
+    const u32 total = 2 * m + 2 * nd;
+    u32 *counts = (u32 *)be.ensure(S_COUNTS, 4 * (size_t)(total + 2));
+    be.fill32(counts, 0, (size_t)total + 1);
+    u32 *c_ga = counts, *c_gad = counts + m, *c_r53 = counts + m + nd, *c_r53d = counts + 2 * m + nd;
+    gar_op *stage_ga = (gar_op *)be.ensure(S_STAGE_GA, sizeof(gar_op) * ((size_t)m * OPS_STAGE_CAP + 1));
+    gar_op *stage_r53 = (gar_op *)be.ensure(S_STAGE_R53, sizeof(gar_op) * ((size_t)m * OPS_STAGE_CAP + 1));
+    u32 *st_ga = (u32 *)be.out_status_ga(m);
+    u32 *st_r53 = (u32 *)be.out_status_r53(m);
+    u32 *derived_out = (u32 *)be.out_derived_keys(m);
+    if (m) {
+      be.for_each("gather_derived", m, FGatherDerived{W.derived, rows, derived_out});
+      be.for_each_warp("ga_objects", m, FGaObj{T, W, c_ga, stage_ga, st_ga, rows});
+    }
+    if (nd) be.for_each("ga_deleted_keys_count", nd, FDelKeyGa{T, W, D, c_gad, nullptr});
+    r53_relational(m, rows, st_r53);
+    if (m) be.for_each_warp("r53_objects", m, FR53Obj{T, W, c_r53, stage_r53, st_r53, rows});
+    if (nd) be.for_each("r53_deleted_keys_count", nd, FDelKeyR53{T, W, D, c_r53d, nullptr});
+    be.exclusive_scan(counts, total + 1);
+    u32 sec[6];
+    u32 *secdev = errflag + 8;
+    be.for_each("gather_section_begins", 6, FGather5{counts, {0, m, m + nd, 2 * m + nd, total}, overflow, secdev});
+    be.download(sec, secdev, sizeof(sec));
+    if (sec[5] && !force_radix) return GAR_RETRY_WITH_RADIX;
+    for (int k = 0; k < 5; k++) dc->section_begin[k] = sec[k];
+    dc->n_ops = sec[4];
+    dc->n_dports = 0;
+    gar_op *ops = (gar_op *)ops_alloc(dc->n_ops);
+    if (m) be.for_each_warp("ga_objects_compact", m, FCompactOps{T, W, c_ga, stage_ga, ops, GAR_CTRL_GA, rows});
+    if (nd) be.for_each("ga_deleted_keys_emit", nd, FDelKeyGa{T, W, D, c_gad, ops});
+    if (m) be.for_each_warp("r53_objects_compact", m, FCompactOps{T, W, c_r53, stage_r53, ops, GAR_CTRL_R53, rows});
+    if (nd) be.for_each("r53_deleted_keys_emit", nd, FDelKeyR53{T, W, D, c_r53d, ops});
+    return GAR_OK;
+  }
+
+  // prepare (once per snapshot; redone with the radix build if a bucket overflowed) + one of the decide flavours
+  template <class DecideF>
+  int run_with(DecideF decide) {
+    for (int attempt = 0; attempt < 2; attempt++) {
+      if (!prepared) {
+        int rc = prepare();
+        if (rc != GAR_OK) return rc;
+        prepared = true;
+      }
+      int rc = decide();
+      if (rc != GAR_RETRY_WITH_RADIX) return rc;
+      force_radix = true;  // some hash bucket was too large for the per-bucket build: rebuild with the stable radix sort
+      prepared = false;
+    }
+    return GAR_E_STATE;
+  }
+  template <class OpsAlloc>
+  int run(DiffCounts *dc, OpsAlloc ops_alloc) {
+    return run_with([&] { return decide_all(dc, ops_alloc); });
+  }
+  template <class OpsAlloc>
+  int run_keys(const u32 *rows, u32 m, DelKeys D, u32 nd, DiffCounts *dc, OpsAlloc ops_alloc) {
+    return run_with([&] { return decide_keys(rows, m, D, nd, dc, ops_alloc); });
   }
 };

@@ -1279,7 +1279,7 @@ GAR_HD void link_value_alias(const DevTables &T, const Work &W, u32 v) {
 
 // warp-synchronous.  Writes r53_mode, r53_acc, r53_acc_dns, pair count (into pair_begin[i]) and, for objects that
 // are finished here, the status word.
-GAR_HD void r53_prepare(const DevTables &T, const Work &W, u32 i, bool valid, u32 *status) {
+GAR_HD void r53_prepare(const DevTables &T, const Work &W, u32 i, u32 t, bool valid, u32 *status) {
   const gar_objects &o = T.o;
   u32 mode = R53_MODE_DONE, st = GAR_STATUS(GAR_ST_IGNORED, 0, 0), npairs = 0;
   bool probe = false;
@@ -1330,16 +1330,16 @@ GAR_HD void r53_prepare(const DevTables &T, const Work &W, u32 i, bool valid, u3
     W.r53_mode[i] = (u8)mode;
     W.r53_acc[i] = acc;
     W.r53_acc_dns[i] = acc_dns;
-    W.pair_begin[i] = npairs;
-    if (mode == R53_MODE_DONE) status[i] = st;
+    W.pair_begin[t] = npairs;
+    if (mode == R53_MODE_DONE) status[t] = st;
   }
 }
 
-GAR_HD void r53_fill_pairs(const DevTables &T, const Work &W, u32 i) {
+GAR_HD void r53_fill_pairs(const DevTables &T, const Work &W, u32 i, u32 t) {
   if (W.r53_mode[i] != R53_MODE_PAIRS) return;
   gar_str ref = W.ann_r53[i];
   Str hostnames = mkstr(T.o.slab, ref);
-  u32 p = W.pair_begin[i], pos = 0;
+  u32 p = W.pair_begin[t], pos = 0;
   Str piece;
   while (next_piece(hostnames, &pos, &piece)) {
     W.pair_obj[p] = i;
@@ -1404,7 +1404,7 @@ GAR_HD void r53_pair(const DevTables &T, const Work &W, u32 p, bool valid) {
 }
 
 // warp-synchronous (objects in R53_MODE_OBJECT call the voted r53_reconcile)
-GAR_HD u32 r53_combine(const DevTables &T, const Work &W, u32 i, bool valid, u32 prev_status, OpSink &s) {
+GAR_HD u32 r53_combine(const DevTables &T, const Work &W, u32 i, u32 t, bool valid, u32 prev_status, OpSink &s) {
   u32 mode = valid ? W.r53_mode[i] : R53_MODE_DONE;
   u32 st = prev_status;
   bool slow = mode == R53_MODE_OBJECT;
@@ -1416,7 +1416,7 @@ GAR_HD u32 r53_combine(const DevTables &T, const Work &W, u32 i, bool valid, u32
     u32 kind = T.o.obj_kind[i], acc = W.r53_acc[i];
     bool created = false, stop = false;
     u32 k = 0;
-    for (u32 p = W.pair_begin[i]; p < W.pair_begin[i + 1] && !stop; p++, k++) {
+    for (u32 p = W.pair_begin[t]; p < W.pair_begin[t + 1] && !stop; p++, k++) {
       u32 code = W.pair_code[p];
       if (code == PAIR_NO_ZONE) {
         st = GAR_STATUS(GAR_ST_ERR_RETRY, GAR_D_NO_HOSTED_ZONE, 0);

@@ -349,7 +349,7 @@ def main():
         models = kernel_byte_models(o, a, sb[1] - sb[0], n_pairs_model, frac_ga)
         traffic = {}
         tp = REPO / "profiles" / "r01_ncu_traffic.json"
-        if tp.exists():
+        if tp.exists() and args.config == 3 and args.objects == 1_000_000:  # the capture is of this exact workload
             traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch", {})
         kb = models.get(top[0])
         if kb:

@@ -331,6 +331,26 @@ int gar_diff(gar_engine *e, gar_changeset *out);
    valid until the next diff/load on this engine. */
 int gar_diff_device(gar_engine *e, gar_changeset *out);
 
+/* Incremental mode: the decisions of a batch of work-queue keys against the loaded snapshot.
+   `rows` are the object rows whose keys fired (informer add/update events, globalaccelerator/controller.go:91-111);
+   `deleted_*` are keys that are no longer in the cache (delete events, :113-173): kind + "ns/name".
+   Stands for: ProcessNextWorkItem once per key (pkg/reconcile/reconcile.go:26-42) -> processCreateOrUpdate for the
+   rows, processDelete for the deleted keys.  The snapshot's digests and hash indexes are built on the first diff after
+   a load and reused by every later gar_diff / gar_diff_keys until the next load.
+   Result layout: n_objects = n_rows; status_ga[k], status_r53[k], derived[k] belong to rows[k]; object-section ops
+   follow the order of `rows` and carry the real object row in `obj`; the orphan sections hold the cleanup ops of the
+   deleted keys in the order given (per key: processDelete order, i.e. accelerators in list order / per zone alias
+   sets then owner metadata sets); they carry obj = GAR_NONE.  tok_* and dports are not produced (n_lbi = 0,
+   n_dports = 0). */
+typedef struct gar_keyset {
+  uint32_t n_rows;
+  const uint32_t *rows;            /* [n_rows] object rows, each < n_objects */
+  uint32_t n_deleted;
+  const uint8_t *deleted_kind;     /* [n_deleted] GAR_KIND_* */
+  const char *const *deleted_key;  /* [n_deleted] NUL-terminated "ns/name" */
+} gar_keyset;
+int gar_diff_keys(gar_engine *e, const gar_keyset *keys, gar_changeset *out);
+
 void gar_changeset_free(gar_engine *e, gar_changeset *cs);
 
 const char *gar_last_error(const gar_engine *e); /* never NULL; valid until the next call on e */

@@ -32,6 +32,9 @@ def lib() -> C.CDLL:
         L = C.CDLL(str(LIB))
         L.orc_diff.argtypes = [C.POINTER(abi.GarObjects), C.POINTER(abi.GarActual), C.c_char_p, C.c_int, C.c_int, C.POINTER(C.POINTER(abi.GarChangeset))]
         L.orc_diff.restype = C.c_int
+        L.orc_diff_keys.argtypes = [C.POINTER(abi.GarObjects), C.POINTER(abi.GarActual), C.c_char_p, C.c_int, C.POINTER(C.c_uint32), C.c_uint32,
+                                    C.POINTER(C.c_uint8), C.POINTER(C.c_char_p), C.c_uint32, C.POINTER(C.POINTER(abi.GarChangeset))]
+        L.orc_diff_keys.restype = C.c_int
         L.orc_free.argtypes = [C.POINTER(abi.GarChangeset)]
         L.orc_free.restype = None
         L.orc_detect_cloud_provider.argtypes = [C.c_char_p, C.c_uint32]
@@ -57,6 +60,20 @@ def diff(snap, cluster: str = "default", mode: int = 1, threads: int = 1):
         raise RuntimeError(f"orc_diff rc={rc}")
     try:
         return abi.ChangeSet(out.contents)
+    finally:
+        L.orc_free(out)
+
+
+def diff_keys(snap, rows, deleted=(), cluster: str = "default", mode: int = 1):
+    """Incremental-mode oracle: per-key reconcile of `rows` + processDelete of the deleted keys."""
+    L = lib()
+    ks = abi.make_keyset(rows, deleted)
+    out = C.POINTER(abi.GarChangeset)()
+    rc = L.orc_diff_keys(C.byref(snap.objects), C.byref(snap.actual), cluster.encode(), mode, ks.rows, ks.n_rows, ks.deleted_kind, ks.deleted_key, ks.n_deleted, C.byref(out))
+    if rc != 0:
+        raise RuntimeError(f"orc_diff_keys rc={rc}")
+    try:
+        return abi.ChangeSet(out.contents, keyset=True)
     finally:
         L.orc_free(out)
 

@@ -1411,6 +1411,68 @@ int orc_diff(const gar_objects *o, const gar_actual *a, const char *cluster, int
   return 0;
 }
 
+// Incremental mode (include/garecon.h gar_diff_keys): ProcessNextWorkItem once per key — processCreateOrUpdate for the
+// object rows, processDelete (globalaccelerator/service.go:28-52, ingress.go:29-54, route53/service.go:29-46,
+// ingress.go:20-38) for the keys that left the cache.
+int orc_diff_keys(const gar_objects *o, const gar_actual *a, const char *cluster, int mode, const uint32_t *rows, uint32_t n_rows,
+                  const uint8_t *del_kind, const char *const *del_key, uint32_t n_del, gar_changeset **out) {
+  Engine E(o, a, cluster, mode);
+  auto *R = new Result();
+  R->stGa.assign(n_rows, 0);
+  R->stR53.assign(n_rows, 0);
+  R->derived.assign(n_rows, 0);
+  std::vector<gar_op> gaOps, gaDel, r53Ops, r53Del;
+  for (uint32_t t = 0; t < n_rows; t++) {
+    Object ob = E.object(rows[t]);
+    uint32_t dv = 0;
+    std::vector<int32_t> ports;
+    int proto;
+    bool fromAnn;
+    E.desiredListener(ob, &ports, &proto, &fromAnn);
+    if (proto == GAR_PROTO_UDP) dv |= GAR_DV_PROTO_UDP;
+    if (ob.get(kAnnIPPreserve) == "true") dv |= GAR_DV_IP_PRESERVE;
+    sv ipt = ob.get(kAnnIPType);
+    if (ipt == "ipv4" || ipt == "IPV4") dv |= GAR_DV_IPV4;
+    if (fromAnn) dv |= GAR_DV_PORTS_FROM_ANN;
+    bool gaEl = ob.kind == GAR_KIND_SERVICE ? E.wasLoadBalancerService(ob) : E.wasALBIngress(ob);
+    bool r53El = ob.kind == GAR_KIND_SERVICE ? E.wasLoadBalancerService(ob) : true;
+    if (gaEl) dv |= GAR_DV_GA_ELIGIBLE;
+    if (ob.has(kAnnManaged)) dv |= GAR_DV_GA_MANAGED;
+    if (r53El) dv |= GAR_DV_R53_ELIGIBLE;
+    if (ob.has(kAnnR53Host)) dv |= GAR_DV_R53_ANNOTATED;
+    R->derived[t] = dv;
+    R->stGa[t] = E.gaReconcile(gaOps, ob);
+    R->stR53[t] = E.r53Reconcile(r53Ops, ob);
+  }
+  for (uint32_t k = 0; k < n_del; k++) {
+    sv key(del_key[k]);
+    size_t slash = key.find('/');  // cache.SplitMetaNamespaceKey
+    sv ns = slash == sv::npos ? sv() : key.substr(0, slash), name = slash == sv::npos ? key : key.substr(slash + 1);
+    const char *resource = Engine::resourceOf(del_kind[k]);
+    for (uint32_t acc : E.listByResource(resource, ns, name)) E.emitDeleteChain(gaDel, GAR_NONE, 0, acc);
+    E.cleanupRecordSet(r53Del, GAR_NONE, 0, route53OwnerValue(E.S.cluster, resource, ns, name));
+  }
+  R->cs.section_begin[0] = 0;
+  R->ops.insert(R->ops.end(), gaOps.begin(), gaOps.end());
+  R->cs.section_begin[1] = R->ops.size();
+  R->ops.insert(R->ops.end(), gaDel.begin(), gaDel.end());
+  R->cs.section_begin[2] = R->ops.size();
+  R->ops.insert(R->ops.end(), r53Ops.begin(), r53Ops.end());
+  R->cs.section_begin[3] = R->ops.size();
+  R->ops.insert(R->ops.end(), r53Del.begin(), r53Del.end());
+  R->cs.section_begin[4] = R->ops.size();
+  gar_changeset &cs = R->cs;
+  cs.n_objects = n_rows;
+  cs.status_ga = R->stGa.data();
+  cs.status_r53 = R->stR53.data();
+  cs.derived = R->derived.data();
+  cs.n_ops = R->ops.size();
+  cs.ops = R->ops.data();
+  cs.opaque = R;
+  *out = &R->cs;
+  return 0;
+}
+
 void orc_free(gar_changeset *cs) {
   if (cs) delete (Result *)cs->opaque;
 }

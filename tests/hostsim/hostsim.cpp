@@ -80,7 +80,11 @@ struct gar_engine {
   bool loaded = false;
   std::vector<std::vector<uint8_t>> slabs;
   HBuf slot[S_NSLOTS];
-  HBuf o_status_ga, o_status_r53, o_derived, o_ops, o_tok_code, o_tok_name, o_tok_region, o_dport_begin, o_dports;
+  HBuf o_status_ga, o_status_r53, o_derived, o_ops, o_tok_code, o_tok_name, o_tok_region, o_dport_begin, o_dports, o_derived_keys;
+  Pipeline<gar_engine> *pipe = nullptr;
+  std::vector<u8> del_slab, del_kind;
+  std::vector<gar_str> del_key;
+  std::vector<u32> key_rows;
   u64 input_bytes = 0;
   u32 launches = 0;
 
@@ -131,6 +135,7 @@ struct gar_engine {
   void *ensure(int s, size_t bytes) { return slot[s].ensure(bytes); }
   void download(void *dst, const void *src, size_t bytes) { memcpy(dst, src, bytes); }
   void *out_derived(u32 n) { return o_derived.ensure(4 * (size_t)(n + 1)); }
+  void *out_derived_keys(u32 n) { return o_derived_keys.ensure(4 * (size_t)(n + 1)); }
   void *out_dport_begin(u32 n) { return o_dport_begin.ensure(4 * (size_t)(n + 2)); }
   void *out_tok_code(u32 n) { return o_tok_code.ensure(n + 1); }
   void *out_tok_name(u32 n) { return o_tok_name.ensure(8 * (size_t)(n + 1)); }
@@ -168,20 +173,39 @@ int gar_snapshot_load(gar_engine *e, const gar_objects *o, const gar_actual *a) 
   e->T.cluster = e->cluster_pad.data();
   e->T.cluster_len = (u32)e->cluster.size();
   e->loaded = true;
+  delete e->pipe;
+  e->pipe = nullptr;
   return GAR_OK;
 }
 int gar_snapshot_attach_device(gar_engine *e, const gar_objects *o, const gar_actual *a) { return gar_snapshot_load(e, o, a); }
 
-int gar_diff(gar_engine *e, gar_changeset *out) {
+static int diff_impl(gar_engine *e, gar_changeset *out, const gar_keyset *ks) {
   memset(out, 0, sizeof(*out));
   e->launches = 0;
-  Pipeline<gar_engine> P(*e, e->T);
+  if (!e->pipe) e->pipe = new Pipeline<gar_engine>(*e, e->T);
+  Pipeline<gar_engine> &P = *e->pipe;
   DiffCounts dc{};
   g_vote_outside_warp = g_nonuniform_vote = false;
-  int rc = P.run(&dc, [&](u64 nops) { return e->o_ops.ensure(sizeof(gar_op) * (size_t)(nops + 1)); });
-  if (rc == GAR_RETRY_WITH_RADIX) {
-    P.force_radix = true;
-    rc = P.run(&dc, [&](u64 nops) { return e->o_ops.ensure(sizeof(gar_op) * (size_t)(nops + 1)); });
+  auto ops_alloc = [&](u64 nops) { return e->o_ops.ensure(sizeof(gar_op) * (size_t)(nops + 1)); };
+  int rc;
+  u32 n_out = e->T.o.n_objects;
+  if (!ks) {
+    rc = P.run(&dc, ops_alloc);
+  } else {
+    n_out = ks->n_rows;
+    e->key_rows.assign(ks->rows, ks->rows + ks->n_rows);
+    e->key_rows.push_back(0);
+    e->del_slab.clear();
+    e->del_key.assign(ks->n_deleted + 1, 0);
+    e->del_kind.assign(ks->n_deleted + 1, 0);
+    for (u32 k = 0; k < ks->n_deleted; k++) {
+      size_t len = strlen(ks->deleted_key[k]);
+      e->del_key[k] = GAR_STR(e->del_slab.size(), len);
+      e->del_slab.insert(e->del_slab.end(), ks->deleted_key[k], ks->deleted_key[k] + len);
+      e->del_kind[k] = ks->deleted_kind[k];
+    }
+    e->del_slab.resize(e->del_slab.size() + 64, 0);
+    rc = P.run_keys(e->key_rows.data(), ks->n_rows, DelKeys{e->del_kind.data(), e->del_key.data(), e->del_slab.data()}, ks->n_deleted, &dc, ops_alloc);
   }
   if (g_nonuniform_vote || g_vote_outside_warp) {
     e->err = g_nonuniform_vote ? "non-uniform warp vote: some lane did not reach a GAR_ANY that others executed (would hang on the GPU)"
@@ -192,14 +216,14 @@ int gar_diff(gar_engine *e, gar_changeset *out) {
     e->err = "objects layout rule violated";
     return rc;
   }
-  out->n_objects = e->T.o.n_objects;
+  out->n_objects = n_out;
   out->status_ga = (const u32 *)e->o_status_ga.mem.data();
   out->status_r53 = (const u32 *)e->o_status_r53.mem.data();
-  out->derived = (const u32 *)e->o_derived.mem.data();
+  out->derived = (const u32 *)(ks ? e->o_derived_keys.mem.data() : e->o_derived.mem.data());
   out->n_ops = dc.n_ops;
   out->ops = (const gar_op *)e->o_ops.mem.data();
   for (int k = 0; k <= GAR_N_SECTIONS; k++) out->section_begin[k] = dc.section_begin[k];
-  out->n_lbi = e->T.o.n_lbi;
+  out->n_lbi = ks ? 0 : e->T.o.n_lbi;
   out->tok_code = (const u8 *)e->o_tok_code.mem.data();
   out->tok_name = (const gar_str *)e->o_tok_name.mem.data();
   out->tok_region = (const gar_str *)e->o_tok_region.mem.data();
@@ -209,6 +233,8 @@ int gar_diff(gar_engine *e, gar_changeset *out) {
   out->kernel_launches = e->launches;
   return GAR_OK;
 }
+int gar_diff(gar_engine *e, gar_changeset *out) { return diff_impl(e, out, nullptr); }
+int gar_diff_keys(gar_engine *e, const gar_keyset *ks, gar_changeset *out) { return diff_impl(e, out, ks); }
 int gar_diff_device(gar_engine *e, gar_changeset *out) { return gar_diff(e, out); }
 void gar_changeset_free(gar_engine *, gar_changeset *cs) { memset(cs, 0, sizeof(*cs)); }
 const char *gar_last_error(const gar_engine *e) { return e ? e->err.c_str() : g_err.c_str(); }
