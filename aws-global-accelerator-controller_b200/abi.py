@@ -104,6 +104,7 @@ class GarStageTiming(C.Structure):
 
 
 FLAG_STAGE_TIMING = 1
+FLAG_REPREPARE = 2
 
 
 class GarOp(C.Structure):
@@ -259,11 +260,11 @@ class GarError(RuntimeError):
 class Engine:
     """Thin RAII wrapper over gar_engine_* (one engine per process per device)."""
 
-    def __init__(self, cluster_name: str = "default", device: int = 0, lib: C.CDLL | None = None, stage_timing: bool = False):
+    def __init__(self, cluster_name: str = "default", device: int = 0, lib: C.CDLL | None = None, stage_timing: bool = False, reprepare: bool = False):
         self.lib = lib or load_library()
         self._h = C.c_void_p()
         self._cluster = cluster_name.encode()
-        cfg = GarConfig(GAR_ABI_VERSION, device, self._cluster, FLAG_STAGE_TIMING if stage_timing else 0)
+        cfg = GarConfig(GAR_ABI_VERSION, device, self._cluster, (FLAG_STAGE_TIMING if stage_timing else 0) | (FLAG_REPREPARE if reprepare else 0))
         rc = self.lib.gar_engine_create(C.byref(cfg), C.byref(self._h))
         if rc != GAR_OK:
             msg = self.lib.gar_last_error(self._h).decode(errors="replace") if self._h else self.lib.gar_last_error(None).decode(errors="replace")

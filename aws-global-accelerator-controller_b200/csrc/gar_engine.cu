@@ -297,6 +297,7 @@ struct gar_engine {
   u64 input_bytes = 0;  // slabs + fixed-width columns, each once
   // stage timing (GAR_FLAG_STAGE_TIMING)
   bool timing = false;
+  bool reprepare = false;  // GAR_FLAG_REPREPARE
   struct Mark {
     const char *name;
     cudaEvent_t a, b;
@@ -677,6 +678,7 @@ static void do_diff(gar_engine *e, gar_changeset *out, bool to_host, const gar_k
     e->T.cluster = (const u8 *)e->cluster_dev.p;
   }
   Pipeline<gar_engine> &P = *e->pipe;
+  if (e->reprepare) P.prepared = false;
   DiffCounts dc{};
   auto ops_alloc = [&](u64 nops) { return e->dev_ensure(e->d_ops, sizeof(gar_op) * (size_t)(nops + 1)); };
   CK(cudaEventRecord(e->ev[2], e->stream));
@@ -831,6 +833,7 @@ int gar_engine_create(const gar_config *cfg, gar_engine **out) {
   e->device = cfg->device;
   e->cluster = cfg->cluster_name ? cfg->cluster_name : "";
   e->timing = (cfg->flags & GAR_FLAG_STAGE_TIMING) != 0;
+  e->reprepare = (cfg->flags & GAR_FLAG_REPREPARE) != 0;
   try {
     CK(cudaSetDevice(e->device));
     CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));

@@ -163,6 +163,8 @@ typedef struct gar_config {
   uint32_t flags;            /* GAR_FLAG_* */
 } gar_config;
 #define GAR_FLAG_STAGE_TIMING 1u /* bracket every stage with CUDA events; read them with gar_last_stage_timings */
+#define GAR_FLAG_REPREPARE 2u    /* rebuild the snapshot's digests and hash indexes on EVERY diff instead of once per load:
+                                    for measuring the complete pipeline (bench.py "value", ncu captures) */
 
 /* ---------------------------------------------------------------- output: the change set */
 

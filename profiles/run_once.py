@@ -12,7 +12,7 @@ reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 pkg = importlib.import_module("aws-global-accelerator-controller_b200")
 synth = importlib.import_module("aws-global-accelerator-controller_b200.synth")
 snap = synth.generate(cfg, n)
-with pkg.Engine(cluster_name=snap.cluster) as e:
+with pkg.Engine(cluster_name=snap.cluster, reprepare=True) as e:
     e.load(snap)
     for _ in range(reps):
         cs = e.diff_device()

@@ -79,4 +79,15 @@ def test_device_resident_path_matches_host_path(garecon, engine, synth):
     cs = engine.diff_device()
     assert int(cs.n_ops) == len(full.ops)
     assert list(cs.section_begin) == list(full.section_begin)
-    assert cs.kernel_launches == full.kernel_launches
+    # the second diff reuses the prepared snapshot (digests + indexes stay resident): fewer launches, same result
+    assert 0 < cs.kernel_launches < full.kernel_launches
+
+
+def test_reprepare_flag_runs_the_complete_pipeline_every_time(garecon, synth):
+    snap = synth.generate(2, 20_000)
+    with garecon.Engine(cluster_name="default", reprepare=True) as e:
+        e.load(snap)
+        a = e.diff()
+        b = e.diff()
+    assert a.diff(b) == []
+    assert a.kernel_launches == b.kernel_launches
