@@ -371,7 +371,9 @@ struct FR53Obj {
   GAR_HD void operator()(u32 t, bool valid) const {
     u32 i = (rows && valid) ? rows[t] : t;
     OpSink s{stage + (size_t)t * OPS_STAGE_CAP, 0, OPS_STAGE_CAP};
-    u32 st = r53_combine(T, W, i, t, valid, valid ? status[t] : 0, s);
+    // objects finished by r53_prepare keep the status it wrote; every other status is produced here
+    u32 prev = (valid && W.r53_mode[i] == R53_MODE_DONE) ? status[t] : 0;
+    u32 st = r53_combine(T, W, i, t, valid, prev, s);
     if (valid) {
       status[t] = st;
       counts[t] = s.n;
