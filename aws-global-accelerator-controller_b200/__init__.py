@@ -6,6 +6,6 @@ exposes it as `garecon`).
 """
 from . import abi, tables  # noqa: F401
 from .abi import Engine, GarError, ChangeSet  # noqa: F401
-from .tables import pack, Snapshot  # noqa: F401
+from .tables import pack, pack_bindings, Snapshot  # noqa: F401
 
 __version__ = "0.1.0"

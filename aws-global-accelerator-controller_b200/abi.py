@@ -99,6 +99,20 @@ class GarKeyset(C.Structure):
     _fields_ = [("n_rows", C.c_uint32), ("rows", _u32p), ("n_deleted", C.c_uint32), ("deleted_kind", _u8p), ("deleted_key", C.POINTER(C.c_char_p))]
 
 
+class GarBindings(C.Structure):
+    _fields_ = [
+        ("n_bindings", C.c_uint32), ("egb_flags", _u8p), ("egb_ref_kind", _u8p), ("egb_ref_key", _u64p), ("egb_eg_arn", _u64p),
+        ("egb_ep_begin", _u32p), ("n_endpoint_ids", C.c_uint32), ("ep_id", _u64p), ("n_known_egs", C.c_uint32), ("known_eg_arn", _u64p),
+        ("slab", _u8p), ("slab_len", C.c_uint64),
+    ]
+
+
+EGB_DELETING, EGB_HAS_FINALIZERS, EGB_OBSERVED = 1, 2, 4
+(OP_EGB_ADD_FINALIZER, OP_EGB_REMOVE_FINALIZER, OP_EGB_REMOVE_ENDPOINT, OP_EGB_ADD_ENDPOINT, OP_EGB_UPDATE_WEIGHT, OP_EGB_UPDATE_STATUS) = range(11, 17)
+ST_REQUEUE_1S = 8
+D_REF_NOT_FOUND, D_EG_NOT_FOUND = 12, 13
+
+
 class GarStageTiming(C.Structure):
     _fields_ = [("name", C.c_char_p), ("ms", C.c_float), ("launches", C.c_uint32), ("bytes", C.c_uint64)]
 
@@ -140,12 +154,12 @@ def _np_from(ptr, n, dtype):
 class ChangeSet:
     """Host copy of a gar_changeset (plain numpy arrays; safe after the C-side object is freed)."""
 
-    def __init__(self, cs: GarChangeset, keyset: bool = False):
+    def __init__(self, cs: GarChangeset, keyset: bool = False, bindings: bool = False):
         n = cs.n_objects
         self.n_objects = n
         self.status_ga = _np_from(cs.status_ga, n, np.uint32)
-        self.status_r53 = _np_from(cs.status_r53, n, np.uint32)
-        self.derived = _np_from(cs.derived, n, np.uint32)
+        self.status_r53 = _np_from(cs.status_r53, 0 if bindings else n, np.uint32)
+        self.derived = _np_from(cs.derived, 0 if bindings else n, np.uint32)
         self.ops = _np_from(cs.ops, cs.n_ops, OP_DTYPE)
         self.section_begin = np.array(list(cs.section_begin), dtype=np.uint64)
         self.tok_code = _np_from(cs.tok_code, cs.n_lbi, np.uint8)
@@ -229,6 +243,8 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
         getattr(lib, fn).restype = C.c_int
     lib.gar_diff_keys.argtypes = [C.c_void_p, C.POINTER(GarKeyset), C.POINTER(GarChangeset)]
     lib.gar_diff_keys.restype = C.c_int
+    lib.gar_bindings_diff.argtypes = [C.c_void_p, C.POINTER(GarBindings), C.POINTER(GarChangeset)]
+    lib.gar_bindings_diff.restype = C.c_int
     lib.gar_changeset_free.argtypes = [C.c_void_p, C.POINTER(GarChangeset)]
     lib.gar_changeset_free.restype = None
     lib.gar_last_error.argtypes = [C.c_void_p]
@@ -246,7 +262,7 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
 
 EXPORTED_SYMBOLS = (
     "gar_engine_create", "gar_engine_destroy", "gar_snapshot_load", "gar_snapshot_attach_device", "gar_diff",
-    "gar_diff_device", "gar_diff_keys", "gar_changeset_free", "gar_last_error", "gar_version", "gar_algorithmic_bytes",
+    "gar_diff_device", "gar_diff_keys", "gar_bindings_diff", "gar_changeset_free", "gar_last_error", "gar_version", "gar_algorithmic_bytes",
     "gar_last_stage_timings",
 )
 
@@ -300,6 +316,16 @@ class Engine:
         try:
             cs.n_lbi = 0
             out = ChangeSet(cs, keyset=True)
+        finally:
+            self.lib.gar_changeset_free(self._h, C.byref(cs))
+        return out
+
+    def bindings_diff(self, bindings) -> ChangeSet:
+        """EndpointGroupBinding set-diff against the loaded snapshot; `bindings` has a .struct (GarBindings)."""
+        cs = GarChangeset()
+        self._check(self.lib.gar_bindings_diff(self._h, C.byref(bindings.struct), C.byref(cs)))
+        try:
+            out = ChangeSet(cs, keyset=True, bindings=True)
         finally:
             self.lib.gar_changeset_free(self._h, C.byref(cs))
         return out

@@ -290,6 +290,7 @@ struct gar_engine {
   DBuf slot[S_NSLOTS];
   DBuf d_status_ga, d_status_r53, d_derived, d_ops, d_tok_code, d_tok_name, d_tok_region, d_dport_begin, d_dports, d_scan_tiles, d_hist;
   DBuf d_derived_keys, d_key_rows, d_del_kind, d_del_key, d_del_slab;  // incremental mode
+  DBuf d_egb[8];                                                      // EndpointGroupBinding tables
   Pipeline<gar_engine> *pipe = nullptr;  // lives as long as the loaded snapshot: keeps digests + indexes resident
   std::vector<HostResult *> free_results;
   float ms_h2d = 0;
@@ -665,7 +666,7 @@ static void do_load(gar_engine *e, const gar_objects *o, const gar_actual *a) {
 
 // ------------------------------------------------------------------ diff
 
-static void do_diff(gar_engine *e, gar_changeset *out, bool to_host, const gar_keyset *ks = nullptr) {
+static void do_diff(gar_engine *e, gar_changeset *out, bool to_host, const gar_keyset *ks = nullptr, const gar_bindings *bd = nullptr) {
   if (!e->loaded) throw InvalidError{"no snapshot loaded"};
   CK(cudaSetDevice(e->device));
   memset(out, 0, sizeof(*out));
@@ -684,7 +685,37 @@ static void do_diff(gar_engine *e, gar_changeset *out, bool to_host, const gar_k
   CK(cudaEventRecord(e->ev[2], e->stream));
   int rc;
   u32 n_out = e->T.o.n_objects;
-  if (!ks) {
+  if (bd) {
+    // EndpointGroupBinding set-diff: validate and upload the (small) binding tables
+    const gar_bindings &b = *bd;
+    size_t nb = b.n_bindings;
+    if (nb && (!b.egb_flags || !b.egb_ref_kind)) throw InvalidError{"NULL binding columns"};
+    check_str_col("egb_ref_key", b.egb_ref_key, nb, b.slab_len);
+    check_str_col("egb_eg_arn", b.egb_eg_arn, nb, b.slab_len);
+    check_csr("egb_ep_begin", b.egb_ep_begin, nb, b.n_endpoint_ids);
+    check_str_col("ep_id", b.ep_id, b.n_endpoint_ids, b.slab_len);
+    check_str_col("known_eg_arn", b.known_eg_arn, b.n_known_egs, b.slab_len);
+    for (size_t k = 0; k < nb; k++)
+      if (b.egb_ref_kind[k] > GAR_EGB_REF_INGRESS) throw InvalidError{"egb_ref_kind out of range"};
+    auto up = [&](DBuf &db, const void *src, size_t bytes, size_t pad) -> void * {
+      void *p = e->dev_ensure(db, bytes + pad + 16);
+      if (bytes) CK(cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, e->stream));
+      if (pad) CK(cudaMemsetAsync((char *)p + bytes, 0, pad, e->stream));
+      return p;
+    };
+    gar_bindings d = b;
+    d.egb_flags = (const u8 *)up(e->d_egb[0], b.egb_flags, nb, 0);
+    d.egb_ref_kind = (const u8 *)up(e->d_egb[1], b.egb_ref_kind, nb, 0);
+    d.egb_ref_key = (const gar_str *)up(e->d_egb[2], b.egb_ref_key, 8 * nb, 0);
+    d.egb_eg_arn = (const gar_str *)up(e->d_egb[3], b.egb_eg_arn, 8 * nb, 0);
+    d.egb_ep_begin = (const u32 *)up(e->d_egb[4], b.egb_ep_begin, 4 * (nb + 1), 0);
+    d.ep_id = (const gar_str *)up(e->d_egb[5], b.ep_id, 8 * (size_t)b.n_endpoint_ids, 0);
+    d.known_eg_arn = (const gar_str *)up(e->d_egb[6], b.known_eg_arn, 8 * (size_t)b.n_known_egs, 0);
+    d.slab = (const u8 *)up(e->d_egb[7], b.slab, b.slab_len, GAR_SLAB_PAD);
+    CK(cudaStreamSynchronize(e->stream));
+    n_out = b.n_bindings;
+    rc = P.run_bindings(d, &dc, ops_alloc);
+  } else if (!ks) {
     rc = P.run(&dc, ops_alloc);
   } else {
     // incremental mode: upload the key batch (rows + deleted keys)
@@ -722,7 +753,8 @@ static void do_diff(gar_engine *e, gar_changeset *out, bool to_host, const gar_k
     throw InvalidError{"objects layout rule violated: obj_ns and obj_name must be slices of one \"ns/name\" key string"};
   }
   if (rc != GAR_OK) throw InvalidError{"index build did not converge"};
-  const u32 n = n_out, nlbi = ks ? 0 : e->T.o.n_lbi;
+  const bool partial = ks || bd;
+  const u32 n = n_out, nlbi = partial ? 0 : e->T.o.n_lbi;
   const DBuf &d_derived_src = ks ? e->d_derived_keys : e->d_derived;
   out->n_objects = n;
   out->n_ops = dc.n_ops;
@@ -744,13 +776,13 @@ static void do_diff(gar_engine *e, gar_changeset *out, bool to_host, const gar_k
       return p;
     };
     out->status_ga = (const u32 *)pull(h->status_ga, e->d_status_ga, 4 * (size_t)n);
-    out->status_r53 = (const u32 *)pull(h->status_r53, e->d_status_r53, 4 * (size_t)n);
-    out->derived = (const u32 *)pull(h->derived, d_derived_src, 4 * (size_t)n);
+    out->status_r53 = (const u32 *)pull(h->status_r53, e->d_status_r53, bd ? 0 : 4 * (size_t)n);
+    out->derived = (const u32 *)pull(h->derived, d_derived_src, bd ? 0 : 4 * (size_t)n);
     out->ops = (const gar_op *)pull(h->ops, e->d_ops, sizeof(gar_op) * (size_t)dc.n_ops);
     out->tok_code = (const u8 *)pull(h->tok_code, e->d_tok_code, nlbi);
     out->tok_name = (const gar_str *)pull(h->tok_name, e->d_tok_name, 8 * (size_t)nlbi);
     out->tok_region = (const gar_str *)pull(h->tok_region, e->d_tok_region, 8 * (size_t)nlbi);
-    out->dport_begin = (const u32 *)pull(h->dport_begin, e->d_dport_begin, ks ? 0 : 4 * (size_t)(n + 1));
+    out->dport_begin = (const u32 *)pull(h->dport_begin, e->d_dport_begin, partial ? 0 : 4 * (size_t)(n + 1));
     out->dports = (const i32 *)pull(h->dports, e->d_dports, 4 * (size_t)dc.n_dports);
   } else {
     out->status_ga = (const u32 *)e->d_status_ga.p;
@@ -859,6 +891,7 @@ void gar_engine_destroy(gar_engine *e) {
   for (auto &b : e->slot) cudaFree(b.p);
   delete e->pipe;
   for (DBuf *b : {&e->d_derived_keys, &e->d_key_rows, &e->d_del_kind, &e->d_del_key, &e->d_del_slab}) cudaFree(b->p);
+  for (auto &b : e->d_egb) cudaFree(b.p);
   for (DBuf *b : {&e->cluster_dev, &e->d_status_ga, &e->d_status_r53, &e->d_derived, &e->d_ops, &e->d_tok_code, &e->d_tok_name, &e->d_tok_region,
                   &e->d_dport_begin, &e->d_dports, &e->d_scan_tiles, &e->d_hist})
     cudaFree(b->p);
@@ -910,6 +943,11 @@ int gar_diff_device(gar_engine *e, gar_changeset *out) {
 int gar_diff_keys(gar_engine *e, const gar_keyset *keys, gar_changeset *out) {
   if (!out || !keys) return GAR_E_INVALID;
   return guarded(e, [&] { do_diff(e, out, true, keys); });
+}
+
+int gar_bindings_diff(gar_engine *e, const gar_bindings *bindings, gar_changeset *out) {
+  if (!out || !bindings) return GAR_E_INVALID;
+  return guarded(e, [&] { do_diff(e, out, true, nullptr, bindings); });
 }
 
 void gar_changeset_free(gar_engine *e, gar_changeset *cs) {

@@ -37,7 +37,7 @@ enum Slot {
   S_IX_LB, S_IX_OWNER = S_IX_LB + 3, S_IX_THOST = S_IX_OWNER + 3, S_IX_ZONE = S_IX_THOST + 3, S_IX_VAL = S_IX_ZONE + 3,
   S_IX_ALIAS = S_IX_VAL + 3, S_IX_OBJ = S_IX_ALIAS + 3, S_IX_OVN = S_IX_OBJ + 3,
   S_SORT_KEYS = S_IX_OVN + 3, S_SORT_VALS, S_SORT_KEYS_ALT, S_SORT_VALS_ALT, S_SORT_TAGS,
-  S_COUNTS, S_STATUS_GA, S_STATUS_R53, S_OPS, S_ERRFLAG,
+  S_COUNTS, S_STATUS_GA, S_STATUS_R53, S_OPS, S_ERRFLAG, S_IX_EG, S_IX_EG_ENT, S_IX_EG_PAD,
   S_NSLOTS
 };
 
@@ -441,6 +441,30 @@ struct FDelKeyR53 {
     if (!ops) counts[k] = s.n;
   }
 };
+struct FRowKnownEg {
+  gar_bindings b;
+  GAR_HD bool make(u32 i, u64 *h, IdxEntry *e) const {
+    *h = gar_hash(mkstr(b.slab, b.known_eg_arn[i]));
+    e->a0 = e->a1 = 0;
+    e->s0 = b.known_eg_arn[i];
+    e->s1 = 0;
+    return true;
+  }
+};
+struct FEgb {
+  DevTables T;
+  Work W;
+  DevBindings B;
+  u32 *counts;   // count pass: written; emit pass: scanned
+  gar_op *ops;
+  u32 *status;
+  GAR_HD void operator()(u32 k) const {
+    OpSink s{ops ? ops + counts[k] : nullptr, 0, 0xFFFFFFFFu};
+    u32 st = egb_reconcile(T, W, B, k, s);
+    if (ops) status[k] = st;
+    else counts[k] = s.n;
+  }
+};
 struct FGatherDerived {
   const u32 *derived, *rows;
   u32 *out;
@@ -760,6 +784,34 @@ struct Pipeline {
     if (m) be.for_each_warp("r53_objects_compact", m, FCompactOps{T, W, c_r53, stage_r53, ops, GAR_CTRL_R53, rows});
     if (nd) be.for_each("r53_deleted_keys_emit", nd, FDelKeyR53{T, W, D, c_r53d, ops});
     return GAR_OK;
+  }
+
+  // ---- EndpointGroupBinding set-diff over `nb` bindings (device pointers in `b`)
+  template <class OpsAlloc>
+  int decide_bindings(const gar_bindings &b, DiffCounts *dc, OpsAlloc ops_alloc) {
+    u32 *overflow = errflag + 1;
+    const u32 nb = b.n_bindings;
+    DevBindings DB{b, build_index(S_IX_EG, b.n_known_egs, 1, FRowKnownEg{b}, overflow, force_radix)};
+    u32 *counts = (u32 *)be.ensure(S_COUNTS, 4 * (size_t)(nb + 2));
+    be.fill32(counts, 0, (size_t)nb + 1);
+    u32 *st = (u32 *)be.out_status_ga(nb);
+    if (nb) be.for_each("egb_count", nb, FEgb{T, W, DB, counts, nullptr, nullptr});
+    be.exclusive_scan(counts, nb + 1);
+    u32 sec[6];
+    u32 *secdev = errflag + 8;
+    be.for_each("gather_section_begins", 6, FGather5{counts, {0, nb, nb, nb, nb}, overflow, secdev});
+    be.download(sec, secdev, sizeof(sec));
+    if (sec[5] && !force_radix) return GAR_RETRY_WITH_RADIX;
+    for (int k = 0; k < 5; k++) dc->section_begin[k] = sec[k];
+    dc->n_ops = sec[4];
+    dc->n_dports = 0;
+    gar_op *ops = (gar_op *)ops_alloc(dc->n_ops);
+    if (nb) be.for_each("egb_emit", nb, FEgb{T, W, DB, counts, ops, st});
+    return GAR_OK;
+  }
+  template <class OpsAlloc>
+  int run_bindings(const gar_bindings &b, DiffCounts *dc, OpsAlloc ops_alloc) {
+    return run_with([&] { return decide_bindings(b, dc, ops_alloc); });
   }
 
   // prepare (once per snapshot; redone with the radix build if a bucket overflowed) + one of the decide flavours

@@ -1492,3 +1492,142 @@ GAR_HD void r53_orphan_alias(const DevTables &T, const Work &W, u32 r, OpSink &s
     s.put(GAR_OP_HEAD(GAR_OP_R53_DELETE_RECORD, GAR_CTRL_R53, 0), GAR_NONE, 0, zone, r, e.row);
   }
 }
+
+// ------------------------------------------------------------------ (f3) EndpointGroupBinding set-diff
+//
+// pkg/controller/endpointgroupbinding/reconcile.go:20-217.  One thread per binding (bindings are few); uses the
+// snapshot's object index, tokeniser output and LB index.
+
+struct DevBindings {
+  gar_bindings b;     // device pointers
+  HashIdx ix_eg;      // endpoint-group ARN -> known_eg row
+};
+
+GAR_HD bool egb_eg_exists(const DevBindings &B, Str arn) {
+  Cursor c = idx_open(B.ix_eg, gar_hash(arn));
+  IdxEntry e;
+  while (idx_next(B.ix_eg, c, &e))
+    if (streq(mkstr(B.b.slab, e.s0), arn)) return true;
+  return false;
+}
+
+// the LB row a lbIngress row resolves to: GetLBNameFromHostname + GetLoadBalancer (reconcile.go:125-138); *detail != 0 on error
+GAR_HD u32 egb_lb_of(const DevTables &T, const Work &W, u32 lbi_row, u32 *detail) {
+  u32 code = W.tok_code[lbi_row];
+  *detail = 0;
+  if (code == GAR_TOK_NOT_AWS || code == GAR_TOK_PANIC) {  // no DetectCloudProvider on this path: both regexps simply do not match
+    *detail = GAR_D_NOT_ELB;
+    return GAR_NONE;
+  }
+  if (code >= GAR_TOK_ERR_NOT_ELB) {
+    *detail = GAR_D_NOT_ELB + (code - GAR_TOK_ERR_NOT_ELB);
+    return GAR_NONE;
+  }
+  u32 st;
+  u32 lb = find_lb(T, W, mkstr(T.o.slab, W.tok_region[lbi_row]), mkstr(T.o.slab, W.tok_name[lbi_row]), &st);
+  if (lb == GAR_NONE) *detail = GAR_D_LB_NOT_FOUND;
+  return lb;
+}
+
+GAR_HD u32 egb_reconcile(const DevTables &T, const Work &W, const DevBindings &B, u32 k, OpSink &s) {
+  const gar_bindings &b = B.b;
+  const gar_actual &A = T.a;
+  u32 flags = b.egb_flags[k];
+  u32 eb = b.egb_ep_begin[k], n = b.egb_ep_begin[k + 1] - eb;
+  Str eg_arn = mkstr(b.slab, b.egb_eg_arn[k]);
+  auto H = [](u32 op) { return GAR_OP_HEAD(op, GAR_CTRL_EGB, 0); };
+  if (flags & GAR_EGB_DELETING) {  // reconcileDelete (:35-96)
+    if (n == 0 || !egb_eg_exists(B, eg_arn)) {
+      s.put(H(GAR_OP_EGB_REMOVE_FINALIZER), k, 0, GAR_NONE, GAR_NONE, GAR_NONE);
+      return GAR_STATUS(GAR_ST_OK, 0, 0);
+    }
+    // `endpointIds` aliases obj.Status.EndpointIds while the loop indexes the latter (:70-85): iteration i sees the element
+    // that started at index min(2i, n-1), and `endpointIds[i+1:]` panics as soon as i+1 exceeds the shrinking length
+    u32 len = n;
+    for (u32 i = 0; i < n; i++) {
+      u32 src = 2 * i < n - 1 ? 2 * i : n - 1;
+      s.put(H(GAR_OP_EGB_REMOVE_ENDPOINT), k, 0, eb + src, GAR_NONE, GAR_NONE);
+      if (i + 1 > len) return GAR_STATUS(GAR_ST_PANIC, 0, 0);
+      len--;
+    }
+    s.put(H(GAR_OP_EGB_UPDATE_STATUS), k, 0, GAR_NONE, GAR_NONE, GAR_NONE);
+    return GAR_STATUS(GAR_ST_REQUEUE_1S, 0, 0);
+  }
+  if (!(flags & GAR_EGB_HAS_FINALIZERS)) {  // reconcileCreate (:98-110)
+    s.put(H(GAR_OP_EGB_ADD_FINALIZER), k, 0, GAR_NONE, GAR_NONE, GAR_NONE);
+    return GAR_STATUS(GAR_ST_OK, 0, 0);
+  }
+  // reconcileUpdate (:112-217).  getLoadBalancerHostName (:219-252)
+  u32 jb = 0, nj = 0;
+  u32 refkind = b.egb_ref_kind[k];
+  if (refkind != GAR_EGB_REF_NONE) {
+    u32 kind = refkind == GAR_EGB_REF_SERVICE ? GAR_KIND_SERVICE : GAR_KIND_INGRESS;
+    Str key = mkstr(b.slab, b.egb_ref_key[k]);
+    Cursor c = idx_open(W.ix_obj, key_hash_kinded(kind, key));
+    IdxEntry e;
+    u32 obj = GAR_NONE;
+    while (idx_next(W.ix_obj, c, &e))
+      if (e.a0 == kind && streq(mkstr(T.o.slab, e.s0), key)) {
+        obj = e.row;
+        break;
+      }
+    if (obj == GAR_NONE) return GAR_STATUS(GAR_ST_ERR_RETRY, GAR_D_REF_NOT_FOUND, 0);
+    jb = T.o.obj_lbi_begin[obj];
+    nj = T.o.obj_lbi_begin[obj + 1] - jb;
+  }
+  for (u32 j = 0; j < nj; j++) {  // every hostname must resolve before anything is decided (:124-139)
+    u32 detail;
+    if (egb_lb_of(T, W, jb + j, &detail) == GAR_NONE) return GAR_STATUS(GAR_ST_ERR_RETRY, detail, 0);
+  }
+  // the `arns` map: ARN -> LB name.  first(j): hostname j is the first one with its ARN.
+  auto arn_of = [&](u32 j) {
+    u32 d;
+    return mkstr(A.slab, A.lb_arn[egb_lb_of(T, W, jb + j, &d)]);
+  };
+  auto is_first = [&](u32 j) {
+    Str a = arn_of(j);
+    for (u32 i = 0; i < j; i++)
+      if (streq(arn_of(i), a)) return false;
+    return true;
+  };
+  auto in_status = [&](Str a) {
+    for (u32 x = 0; x < n; x++)
+      if (streq(mkstr(b.slab, b.ep_id[eb + x]), a)) return true;
+    return false;
+  };
+  auto in_arns = [&](Str id) {
+    for (u32 j = 0; j < nj; j++)
+      if (streq(arn_of(j), id)) return true;
+    return false;
+  };
+  u32 nnew = 0, nrem = 0;
+  for (u32 j = 0; j < nj; j++)
+    if (is_first(j) && !in_status(arn_of(j))) nnew++;
+  for (u32 x = 0; x < n; x++)
+    if (!in_arns(mkstr(b.slab, b.ep_id[eb + x]))) nrem++;
+  if (nnew == 0 && nrem == 0 && (flags & GAR_EGB_OBSERVED)) return GAR_STATUS(GAR_ST_OK, 0, 0);
+  if (!egb_eg_exists(B, eg_arn)) return GAR_STATUS(GAR_ST_ERR_RETRY, GAR_D_EG_NOT_FOUND, 0);
+  if (nrem > 0 && nj == 0) return GAR_STATUS(GAR_ST_PANIC, 0, 0);  // regionalCloud is nil (:121,:160)
+  for (u32 x = 0; x < n; x++)
+    if (!in_arns(mkstr(b.slab, b.ep_id[eb + x]))) s.put(H(GAR_OP_EGB_REMOVE_ENDPOINT), k, 0, eb + x, GAR_NONE, GAR_NONE);
+  // AddLBToEndpointGroup looks the LB up again by NAME in the region of the LAST hostname (:122-131,:172; global_accelerator.go:572-591)
+  Str last_region = nj ? mkstr(T.o.slab, W.tok_region[jb + nj - 1]) : Str{T.o.slab, 0};
+  for (u32 j = 0; j < nj; j++) {
+    if (!is_first(j) || in_status(arn_of(j))) continue;
+    u32 jl = j;  // arns[arn] holds the name written by the LAST hostname with this ARN
+    for (u32 i = j + 1; i < nj; i++)
+      if (streq(arn_of(i), arn_of(j))) jl = i;
+    u32 st;
+    u32 lb2 = find_lb(T, W, last_region, mkstr(T.o.slab, W.tok_name[jb + jl]), &st);
+    if (lb2 == GAR_NONE) return GAR_STATUS(GAR_ST_ERR_RETRY, GAR_D_LB_NOT_FOUND, 0);
+    if (st != GAR_LB_ACTIVE) return GAR_STATUS(GAR_ST_REQUEUE_30S, 0, 0);
+    s.put(H(GAR_OP_EGB_ADD_ENDPOINT), k, 0, lb2, GAR_NONE, GAR_NONE);
+  }
+  for (u32 j = 0; j < nj; j++)
+    if (is_first(j)) {
+      u32 d;
+      s.put(H(GAR_OP_EGB_UPDATE_WEIGHT), k, 0, egb_lb_of(T, W, jb + j, &d), GAR_NONE, GAR_NONE);
+    }
+  s.put(H(GAR_OP_EGB_UPDATE_STATUS), k, 0, GAR_NONE, GAR_NONE, GAR_NONE);
+  return GAR_STATUS(GAR_ST_OK, 0, 0);
+}

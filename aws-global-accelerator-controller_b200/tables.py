@@ -240,3 +240,52 @@ def pack(objects: list[dict], actual: dict | None = None) -> Snapshot:
     a.slab_len = len(sl.buf)
     snap.model = (objects, actual)
     return snap
+
+
+class Bindings:
+    """Owns the buffers behind a GarBindings struct."""
+
+    def __init__(self):
+        self.struct = abi.GarBindings()
+        self.arrays = {}
+
+
+def pack_bindings(bindings: list[dict], known_egs: list[str]) -> Bindings:
+    """EndpointGroupBinding objects -> gar_bindings.  Each binding:
+       {ns, ref: None | ("service"|"ingress", name), eg_arn, deleting: bool, finalizers: bool, observed: bool, endpoint_ids: [arn...]}"""
+    out = Bindings()
+    b = out.struct
+    sl = _Slab()
+    flags, kinds, keys, arns, ep_b, eps = [], [], [], [], [0], []
+    for x in bindings:
+        f = (abi.EGB_DELETING if x.get("deleting") else 0) | (abi.EGB_HAS_FINALIZERS if x.get("finalizers", True) else 0) | (abi.EGB_OBSERVED if x.get("observed", True) else 0)
+        flags.append(f)
+        ref = x.get("ref")
+        kinds.append(0 if ref is None else (1 if ref[0] == "service" else 2))
+        keys.append(sl.put(f"{x.get('ns', 'default')}/{ref[1]}") if ref is not None else 0)
+        arns.append(sl.put(x.get("eg_arn", "")))
+        for e in x.get("endpoint_ids", []):
+            eps.append(sl.put(e))
+        ep_b.append(len(eps))
+    known = [sl.put(k) for k in known_egs]
+
+    def setcol(name, values, dtype, ctype):
+        arr = np.ascontiguousarray(np.asarray(values if len(values) else [0], dtype=dtype))
+        out.arrays[name] = arr
+        setattr(b, name, _ptr(arr, ctype))
+
+    b.n_bindings = len(bindings)
+    setcol("egb_flags", flags, np.uint8, C.c_uint8)
+    setcol("egb_ref_kind", kinds, np.uint8, C.c_uint8)
+    setcol("egb_ref_key", keys, np.uint64, C.c_uint64)
+    setcol("egb_eg_arn", arns, np.uint64, C.c_uint64)
+    setcol("egb_ep_begin", ep_b, np.uint32, C.c_uint32)
+    b.n_endpoint_ids = len(eps)
+    setcol("ep_id", eps, np.uint64, C.c_uint64)
+    b.n_known_egs = len(known)
+    setcol("known_eg_arn", known, np.uint64, C.c_uint64)
+    slab = np.frombuffer(bytes(sl.buf) + b"\0" * 16, dtype=np.uint8).copy()
+    out.arrays["slab"] = slab
+    b.slab = _ptr(slab, C.c_uint8)
+    b.slab_len = len(sl.buf)
+    return out

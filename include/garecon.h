@@ -353,6 +353,52 @@ typedef struct gar_keyset {
 } gar_keyset;
 int gar_diff_keys(gar_engine *e, const gar_keyset *keys, gar_changeset *out);
 
+/* ---------------------------------------------------------------- EndpointGroupBinding set-diff
+   The third controller's decisions (pkg/controller/endpointgroupbinding/reconcile.go:20-217): finalizer handling and the
+   set difference between the load balancers of the referenced Service/Ingress and status.endpointIds.  Evaluated against
+   the loaded snapshot (object cache, tokenised lbIngress hostnames, listed load balancers). */
+enum { GAR_EGB_REF_NONE = 0, GAR_EGB_REF_SERVICE = 1, GAR_EGB_REF_INGRESS = 2 };
+enum {
+  GAR_EGB_DELETING = 1u << 0,       /* metadata.deletionTimestamp != nil (reconcile.go:27) */
+  GAR_EGB_HAS_FINALIZERS = 1u << 1, /* len(metadata.finalizers) != 0 (:30) */
+  GAR_EGB_OBSERVED = 1u << 2        /* status.observedGeneration == metadata.generation (:148) */
+};
+typedef struct gar_bindings {
+  uint32_t n_bindings;
+  const uint8_t *egb_flags;        /* GAR_EGB_* */
+  const uint8_t *egb_ref_kind;     /* GAR_EGB_REF_*: spec.serviceRef / spec.ingressRef (:219-252) */
+  const gar_str *egb_ref_key;      /* "<binding namespace>/<ref name>": the lister key of the referenced object */
+  const gar_str *egb_eg_arn;       /* spec.endpointGroupArn */
+  const uint32_t *egb_ep_begin;    /* [n_bindings+1] -> ep_id: status.endpointIds[] in order */
+  uint32_t n_endpoint_ids;
+  const gar_str *ep_id;
+  uint32_t n_known_egs;            /* endpoint groups for which DescribeEndpointGroup succeeds (global_accelerator.go:867-876) */
+  const gar_str *known_eg_arn;
+  const uint8_t *slab;
+  uint64_t slab_len;
+} gar_bindings;
+
+/* EGB ops (ctrl = GAR_CTRL_EGB, obj = binding row):
+     EGB_ADD_FINALIZER      -            reconcileCreate  (:98-110)
+     EGB_REMOVE_FINALIZER   -            reconcileDelete  (:36-47, :53-66)
+     EGB_REMOVE_ENDPOINT    a0 = ep_id row                 RemoveLBFromEdnpointGroup (:80, :161)
+     EGB_ADD_ENDPOINT       a0 = lb row                    AddLBToEndpointGroup (:172)
+     EGB_UPDATE_WEIGHT      a0 = lb row                    UpdateEndpointWeight (:190)
+     EGB_UPDATE_STATUS      -                              UpdateStatus (:87-90, :197-200)
+   Go map iteration order (the `arns` map, :119,:139,:189) is unspecified; the canonical order here is first occurrence
+   among the referenced object's lbIngress hostnames.  Statuses: GAR_ST_OK, GAR_ST_ERR_RETRY (GAR_D_*),
+   GAR_ST_REQUEUE_30S (LB not active, global_accelerator.go:579-582), GAR_ST_REQUEUE_1S (:96), GAR_ST_PANIC (nil regional
+   client when endpoints must be removed but the reference has no hostnames, :160; slice bounds in the delete loop, :84). */
+enum { GAR_OP_EGB_ADD_FINALIZER = 11, GAR_OP_EGB_REMOVE_FINALIZER = 12, GAR_OP_EGB_REMOVE_ENDPOINT = 13, GAR_OP_EGB_ADD_ENDPOINT = 14,
+       GAR_OP_EGB_UPDATE_WEIGHT = 15, GAR_OP_EGB_UPDATE_STATUS = 16 };
+enum { GAR_CTRL_EGB = 2 };
+enum { GAR_ST_REQUEUE_1S = 8 };
+enum { GAR_D_REF_NOT_FOUND = 12, GAR_D_EG_NOT_FOUND = 13 };
+
+/* Result: n_objects = n_bindings, status_ga[] holds the binding statuses, ops the EGB ops in binding order (one section);
+   status_r53 / derived / tok_* / dports are not produced. */
+int gar_bindings_diff(gar_engine *e, const gar_bindings *bindings, gar_changeset *out);
+
 void gar_changeset_free(gar_engine *e, gar_changeset *cs);
 
 const char *gar_last_error(const gar_engine *e); /* never NULL; valid until the next call on e */

@@ -35,6 +35,8 @@ def lib() -> C.CDLL:
         L.orc_diff_keys.argtypes = [C.POINTER(abi.GarObjects), C.POINTER(abi.GarActual), C.c_char_p, C.c_int, C.POINTER(C.c_uint32), C.c_uint32,
                                     C.POINTER(C.c_uint8), C.POINTER(C.c_char_p), C.c_uint32, C.POINTER(C.POINTER(abi.GarChangeset))]
         L.orc_diff_keys.restype = C.c_int
+        L.orc_bindings_diff.argtypes = [C.POINTER(abi.GarObjects), C.POINTER(abi.GarActual), C.c_char_p, C.POINTER(abi.GarBindings), C.POINTER(C.POINTER(abi.GarChangeset))]
+        L.orc_bindings_diff.restype = C.c_int
         L.orc_free.argtypes = [C.POINTER(abi.GarChangeset)]
         L.orc_free.restype = None
         L.orc_detect_cloud_provider.argtypes = [C.c_char_p, C.c_uint32]
@@ -74,6 +76,18 @@ def diff_keys(snap, rows, deleted=(), cluster: str = "default", mode: int = 1):
         raise RuntimeError(f"orc_diff_keys rc={rc}")
     try:
         return abi.ChangeSet(out.contents, keyset=True)
+    finally:
+        L.orc_free(out)
+
+
+def bindings_diff(snap, bindings, cluster: str = "default"):
+    L = lib()
+    out = C.POINTER(abi.GarChangeset)()
+    rc = L.orc_bindings_diff(C.byref(snap.objects), C.byref(snap.actual), cluster.encode(), C.byref(bindings.struct), C.byref(out))
+    if rc != 0:
+        raise RuntimeError(f"orc_bindings_diff rc={rc}")
+    try:
+        return abi.ChangeSet(out.contents, keyset=True, bindings=True)
     finally:
         L.orc_free(out)
 

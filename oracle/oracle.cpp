@@ -1473,6 +1473,127 @@ int orc_diff_keys(const gar_objects *o, const gar_actual *a, const char *cluster
   return 0;
 }
 
+// EndpointGroupBinding controller (pkg/controller/endpointgroupbinding/reconcile.go:20-252), literal restatement.
+// Go map iteration order is unspecified: ops that the reference issues while ranging over the `arns` map are emitted
+// in first-occurrence order of the ARN among the hostnames (include/garecon.h).
+int orc_bindings_diff(const gar_objects *o, const gar_actual *a, const char *cluster, const gar_bindings *b, gar_changeset **out) {
+  Engine E(o, a, cluster, 1);
+  auto *R = new Result();
+  auto bs = [&](gar_str r) { return sv((const char *)b->slab + GAR_STR_OFF(r), GAR_STR_LEN(r)); };
+  std::unordered_map<ObjKey, uint32_t, ObjKeyHash> cache;
+  for (uint32_t i = 0; i < o->n_objects; i++) cache.emplace(ObjKey{o->obj_kind[i], E.S.os(o->obj_ns[i]), E.S.os(o->obj_name[i])}, i);
+  auto egExists = [&](sv arn) {  // DescribeEndpointGroup (global_accelerator.go:867-876)
+    for (uint32_t k = 0; k < b->n_known_egs; k++)
+      if (bs(b->known_eg_arn[k]) == arn) return true;
+    return false;
+  };
+  auto H = [](int op) { return GAR_OP_HEAD(op, GAR_CTRL_EGB, 0); };
+  R->stGa.assign(b->n_bindings, 0);
+  for (uint32_t k = 0; k < b->n_bindings; k++) {
+    auto put = [&](int op, uint32_t a0) { R->ops.push_back({H(op), k, 0, a0, GAR_NONE, GAR_NONE}); };
+    uint32_t flags = b->egb_flags[k];
+    uint32_t eb = b->egb_ep_begin[k], n = b->egb_ep_begin[k + 1] - eb;
+    sv egArn = bs(b->egb_eg_arn[k]);
+    auto reconcile = [&]() -> uint32_t {
+      if (flags & GAR_EGB_DELETING) {  // reconcileDelete (:35-96)
+        if (n == 0) {
+          put(GAR_OP_EGB_REMOVE_FINALIZER, GAR_NONE);
+          return GAR_STATUS(GAR_ST_OK, 0, 0);
+        }
+        if (!egExists(egArn)) {  // ErrEndpointGroupNotFoundException (:53-66)
+          put(GAR_OP_EGB_REMOVE_FINALIZER, GAR_NONE);
+          return GAR_STATUS(GAR_ST_OK, 0, 0);
+        }
+        // endpointIds := obj.Status.EndpointIds shares the backing array the loop indexes (:70-85)
+        std::vector<uint32_t> backing(n);  // endpoint-id rows
+        for (uint32_t x = 0; x < n; x++) backing[x] = eb + x;
+        size_t len = n;  // len(endpointIds); cap stays n
+        for (uint32_t i = 0; i < n; i++) {
+          uint32_t id = backing[i];  // obj.Status.EndpointIds[i]
+          put(GAR_OP_EGB_REMOVE_ENDPOINT, id);
+          // endpointIds = append(endpointIds[:i], endpointIds[i+1:]...): endpointIds[i+1:] needs i+1 <= len
+          if ((size_t)i + 1 > len) return GAR_STATUS(GAR_ST_PANIC, 0, 0);
+          for (size_t x = i + 1; x < len; x++) backing[x - 1] = backing[x];
+          len = len - 1;
+        }
+        put(GAR_OP_EGB_UPDATE_STATUS, GAR_NONE);
+        return GAR_STATUS(GAR_ST_REQUEUE_1S, 0, 0);
+      }
+      if (!(flags & GAR_EGB_HAS_FINALIZERS)) {  // reconcileCreate (:98-110)
+        put(GAR_OP_EGB_ADD_FINALIZER, GAR_NONE);
+        return GAR_STATUS(GAR_ST_OK, 0, 0);
+      }
+      // reconcileUpdate (:112-217); getLoadBalancerHostName (:219-252)
+      std::vector<sv> hostnames;
+      std::vector<uint32_t> hostRows;
+      if (b->egb_ref_kind[k] != GAR_EGB_REF_NONE) {
+        int kind = b->egb_ref_kind[k] == GAR_EGB_REF_SERVICE ? GAR_KIND_SERVICE : GAR_KIND_INGRESS;
+        sv key = bs(b->egb_ref_key[k]);
+        size_t slash = key.find('/');
+        auto it = cache.find(ObjKey{kind, key.substr(0, slash), key.substr(slash + 1)});
+        if (slash == sv::npos || it == cache.end()) return GAR_STATUS(GAR_ST_ERR_RETRY, GAR_D_REF_NOT_FOUND, 0);
+        for (uint32_t r = o->obj_lbi_begin[it->second]; r < o->obj_lbi_begin[it->second + 1]; r++) hostnames.push_back(E.S.os(o->lbi_hostname[r]));
+      }
+      std::vector<std::string> arnOrder;              // first-occurrence order of map keys
+      std::map<std::string, std::string> arns;        // arn -> LB name
+      std::map<std::string, uint32_t> arnRow;         // arn -> LB row of its first occurrence
+      sv lastRegion;
+      bool haveRegional = false;
+      for (sv hostname : hostnames) {
+        Tok t = getLBNameFromHostname(hostname);
+        if (t.code >= GAR_TOK_ERR_NOT_ELB) return GAR_STATUS(GAR_ST_ERR_RETRY, GAR_D_NOT_ELB + (t.code - GAR_TOK_ERR_NOT_ELB), 0);
+        lastRegion = t.region;
+        haveRegional = true;
+        int64_t lb = E.getLoadBalancer(t.region, t.name);
+        if (lb < 0) return GAR_STATUS(GAR_ST_ERR_RETRY, GAR_D_LB_NOT_FOUND, 0);
+        std::string arn(E.S.as(a->lb_arn[lb]));
+        if (!arns.count(arn)) {
+          arnOrder.push_back(arn);
+          arnRow[arn] = (uint32_t)lb;
+        }
+        arns[arn] = std::string(t.name);
+      }
+      std::vector<std::string> newIds;
+      std::vector<uint32_t> removedRows;
+      auto inStatus = [&](const std::string &arn) {
+        for (uint32_t x = 0; x < n; x++)
+          if (bs(b->ep_id[eb + x]) == sv(arn)) return true;
+        return false;
+      };
+      for (auto &arn : arnOrder)
+        if (!inStatus(arn)) newIds.push_back(arn);
+      for (uint32_t x = 0; x < n; x++)
+        if (!arns.count(std::string(bs(b->ep_id[eb + x])))) removedRows.push_back(eb + x);
+      if (newIds.empty() && removedRows.empty() && (flags & GAR_EGB_OBSERVED)) return GAR_STATUS(GAR_ST_OK, 0, 0);
+      if (!egExists(egArn)) return GAR_STATUS(GAR_ST_ERR_RETRY, GAR_D_EG_NOT_FOUND, 0);
+      for (uint32_t row : removedRows) {
+        if (!haveRegional) return GAR_STATUS(GAR_ST_PANIC, 0, 0);  // regionalCloud == nil (:121,:160)
+        put(GAR_OP_EGB_REMOVE_ENDPOINT, row);
+      }
+      for (auto &arn : newIds) {  // AddLBToEndpointGroup (global_accelerator.go:572-591) on the LAST hostname's regional client
+        int64_t lb = E.getLoadBalancer(lastRegion, arns[arn]);
+        if (lb < 0) return GAR_STATUS(GAR_ST_ERR_RETRY, GAR_D_LB_NOT_FOUND, 0);
+        if (a->lb_state[lb] != GAR_LB_ACTIVE) return GAR_STATUS(GAR_ST_REQUEUE_30S, 0, 0);
+        put(GAR_OP_EGB_ADD_ENDPOINT, (uint32_t)lb);
+      }
+      for (auto &arn : arnOrder) put(GAR_OP_EGB_UPDATE_WEIGHT, arnRow[arn]);
+      put(GAR_OP_EGB_UPDATE_STATUS, GAR_NONE);
+      return GAR_STATUS(GAR_ST_OK, 0, 0);
+    };
+    R->stGa[k] = reconcile();
+  }
+  gar_changeset &cs = R->cs;
+  cs.n_objects = b->n_bindings;
+  cs.status_ga = R->stGa.data();
+  cs.n_ops = R->ops.size();
+  cs.ops = R->ops.data();
+  cs.section_begin[0] = 0;
+  for (int k = 1; k <= GAR_N_SECTIONS; k++) cs.section_begin[k] = R->ops.size();
+  cs.opaque = R;
+  *out = &R->cs;
+  return 0;
+}
+
 void orc_free(gar_changeset *cs) {
   if (cs) delete (Result *)cs->opaque;
 }

@@ -179,7 +179,7 @@ int gar_snapshot_load(gar_engine *e, const gar_objects *o, const gar_actual *a) 
 }
 int gar_snapshot_attach_device(gar_engine *e, const gar_objects *o, const gar_actual *a) { return gar_snapshot_load(e, o, a); }
 
-static int diff_impl(gar_engine *e, gar_changeset *out, const gar_keyset *ks) {
+static int diff_impl(gar_engine *e, gar_changeset *out, const gar_keyset *ks, const gar_bindings *bd = nullptr) {
   memset(out, 0, sizeof(*out));
   e->launches = 0;
   if (!e->pipe) e->pipe = new Pipeline<gar_engine>(*e, e->T);
@@ -189,7 +189,15 @@ static int diff_impl(gar_engine *e, gar_changeset *out, const gar_keyset *ks) {
   auto ops_alloc = [&](u64 nops) { return e->o_ops.ensure(sizeof(gar_op) * (size_t)(nops + 1)); };
   int rc;
   u32 n_out = e->T.o.n_objects;
-  if (!ks) {
+  std::vector<uint8_t> bslab;
+  if (bd) {
+    gar_bindings d = *bd;
+    bslab.assign(bd->slab, bd->slab + bd->slab_len);
+    bslab.resize(bslab.size() + 64, 0);
+    d.slab = bslab.data();
+    n_out = bd->n_bindings;
+    rc = P.run_bindings(d, &dc, ops_alloc);
+  } else if (!ks) {
     rc = P.run(&dc, ops_alloc);
   } else {
     n_out = ks->n_rows;
@@ -223,7 +231,7 @@ static int diff_impl(gar_engine *e, gar_changeset *out, const gar_keyset *ks) {
   out->n_ops = dc.n_ops;
   out->ops = (const gar_op *)e->o_ops.mem.data();
   for (int k = 0; k <= GAR_N_SECTIONS; k++) out->section_begin[k] = dc.section_begin[k];
-  out->n_lbi = ks ? 0 : e->T.o.n_lbi;
+  out->n_lbi = (ks || bd) ? 0 : e->T.o.n_lbi;
   out->tok_code = (const u8 *)e->o_tok_code.mem.data();
   out->tok_name = (const gar_str *)e->o_tok_name.mem.data();
   out->tok_region = (const gar_str *)e->o_tok_region.mem.data();
@@ -235,6 +243,7 @@ static int diff_impl(gar_engine *e, gar_changeset *out, const gar_keyset *ks) {
 }
 int gar_diff(gar_engine *e, gar_changeset *out) { return diff_impl(e, out, nullptr); }
 int gar_diff_keys(gar_engine *e, const gar_keyset *ks, gar_changeset *out) { return diff_impl(e, out, ks); }
+int gar_bindings_diff(gar_engine *e, const gar_bindings *bd, gar_changeset *out) { return diff_impl(e, out, nullptr, bd); }
 int gar_diff_device(gar_engine *e, gar_changeset *out) { return gar_diff(e, out); }
 void gar_changeset_free(gar_engine *, gar_changeset *cs) { memset(cs, 0, sizeof(*cs)); }
 const char *gar_last_error(const gar_engine *e) { return e ? e->err.c_str() : g_err.c_str(); }
