@@ -113,6 +113,13 @@ ST_REQUEUE_1S = 8
 D_REF_NOT_FOUND, D_EG_NOT_FOUND = 12, 13
 
 
+SHARD_MAX_RANKS, SHARD_META_WORDS = 8, 40
+
+
+class GarShard(C.Structure):
+    _fields_ = [(k, C.c_uint32) for k in ("rank", "n_ranks", "obj_base", "lb_base", "acc_base", "lis_base", "eg_base", "rec_base", "val_base")]
+
+
 class GarStageTiming(C.Structure):
     _fields_ = [("name", C.c_char_p), ("ms", C.c_float), ("launches", C.c_uint32), ("bytes", C.c_uint64)]
 
@@ -135,7 +142,7 @@ class GarChangeset(C.Structure):
         ("n_ops", C.c_uint64), ("ops", C.POINTER(GarOp)),
         ("section_begin", C.c_uint64 * (N_SECTIONS + 1)),
         ("n_lbi", C.c_uint32), ("tok_code", _u8p), ("tok_name", _u64p), ("tok_region", _u64p),
-        ("dport_begin", _u32p), ("n_dports", C.c_uint64), ("dports", _i32p),
+        ("dport_begin", _u32p), ("n_dports", C.c_uint64), ("dports", _i32p), ("obj_gid", _u32p),
         ("ms_h2d", C.c_float), ("ms_kernels", C.c_float), ("ms_d2h", C.c_float), ("kernel_launches", C.c_uint32),
         ("opaque", C.c_void_p),
     ]
@@ -169,6 +176,7 @@ class ChangeSet:
         self.dports = _np_from(cs.dports, cs.n_dports, np.int32)
         self.ms_h2d, self.ms_kernels, self.ms_d2h = cs.ms_h2d, cs.ms_kernels, cs.ms_d2h
         self.kernel_launches = cs.kernel_launches
+        self.obj_gid = _np_from(cs.obj_gid, n, np.uint32) if cs.obj_gid else None  # sharded mode only
 
     ARRAYS = ("status_ga", "status_r53", "derived", "ops", "section_begin", "tok_code", "tok_name", "tok_region", "dport_begin", "dports")
 
@@ -245,6 +253,14 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
     lib.gar_diff_keys.restype = C.c_int
     lib.gar_bindings_diff.argtypes = [C.c_void_p, C.POINTER(GarBindings), C.POINTER(GarChangeset)]
     lib.gar_bindings_diff.restype = C.c_int
+    lib.gar_shard_route.argtypes = [C.c_void_p, C.POINTER(GarShard), C.c_int, _u64p, _u64p]
+    lib.gar_shard_route.restype = C.c_int
+    lib.gar_shard_pack.argtypes = [C.c_void_p, C.c_void_p]
+    lib.gar_shard_pack.restype = C.c_int
+    lib.gar_shard_unpack.argtypes = [C.c_void_p, C.c_int, C.c_void_p, _u64p]
+    lib.gar_shard_unpack.restype = C.c_int
+    lib.gar_shard_blob_bytes.argtypes = [_u64p]
+    lib.gar_shard_blob_bytes.restype = C.c_uint64
     lib.gar_changeset_free.argtypes = [C.c_void_p, C.POINTER(GarChangeset)]
     lib.gar_changeset_free.restype = None
     lib.gar_last_error.argtypes = [C.c_void_p]
@@ -262,7 +278,8 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
 
 EXPORTED_SYMBOLS = (
     "gar_engine_create", "gar_engine_destroy", "gar_snapshot_load", "gar_snapshot_attach_device", "gar_diff",
-    "gar_diff_device", "gar_diff_keys", "gar_bindings_diff", "gar_changeset_free", "gar_last_error", "gar_version", "gar_algorithmic_bytes",
+    "gar_diff_device", "gar_diff_keys", "gar_bindings_diff", "gar_shard_route", "gar_shard_pack", "gar_shard_unpack", "gar_shard_blob_bytes",
+    "gar_changeset_free", "gar_last_error", "gar_version", "gar_algorithmic_bytes",
     "gar_last_stage_timings",
 )
 
@@ -329,6 +346,26 @@ class Engine:
         finally:
             self.lib.gar_changeset_free(self._h, C.byref(cs))
         return out
+
+    # ---- sharded mode (include/garecon.h "sharded mode"): the caller moves the blobs between the calls
+    def shard_route(self, shard: GarShard, rnd: int):
+        """-> (meta [n_ranks, SHARD_META_WORDS] uint64, send_bytes [n_ranks] uint64) of this rank's outgoing blobs."""
+        g = int(shard.n_ranks)
+        meta = np.zeros((g, SHARD_META_WORDS), dtype=np.uint64)
+        nbytes = np.zeros(g, dtype=np.uint64)
+        self._check(self.lib.gar_shard_route(self._h, C.byref(shard), rnd, meta.ctypes.data_as(_u64p), nbytes.ctypes.data_as(_u64p)))
+        return meta, nbytes
+
+    def shard_pack(self, send_ptr: int) -> None:
+        self._check(self.lib.gar_shard_pack(self._h, C.c_void_p(send_ptr)))
+
+    def shard_unpack(self, rnd: int, recv_ptr: int, recv_meta: np.ndarray) -> None:
+        m = np.ascontiguousarray(recv_meta, dtype=np.uint64)
+        self._check(self.lib.gar_shard_unpack(self._h, rnd, C.c_void_p(recv_ptr), m.ctypes.data_as(_u64p)))
+
+    def blob_bytes(self, meta_row: np.ndarray) -> int:
+        m = np.ascontiguousarray(meta_row, dtype=np.uint64)
+        return int(self.lib.gar_shard_blob_bytes(m.ctypes.data_as(_u64p)))
 
     def diff_raw(self) -> dict:
         """gar_diff + gar_changeset_free without copying the arrays into numpy: what a C / cgo caller pays.

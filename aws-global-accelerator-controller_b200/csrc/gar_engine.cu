@@ -21,6 +21,7 @@
 #include <utility>
 
 #include "gar_pipeline.h"
+#include "gar_shard.h"
 
 #define GAR_VERSION_STRING "garecon 0.1.0 (sm_100a)"
 
@@ -253,7 +254,7 @@ struct DBuf {
 };
 
 struct HostResult {  // pinned host buffers of one change set
-  DBuf status_ga, status_r53, derived, ops, tok_code, tok_name, tok_region, dport_begin, dports;
+  DBuf status_ga, status_r53, derived, ops, tok_code, tok_name, tok_region, dport_begin, dports, obj_gid;
 };
 
 #define CK(call)                                                                                             \
@@ -292,6 +293,21 @@ struct gar_engine {
   DBuf d_derived_keys, d_key_rows, d_del_kind, d_del_key, d_del_slab;  // incremental mode
   DBuf d_egb[8];                                                      // EndpointGroupBinding tables
   Pipeline<gar_engine> *pipe = nullptr;  // lives as long as the loaded snapshot: keeps digests + indexes resident
+  // sharded mode (gar_shard.h)
+  Sharder<gar_engine> *sharder = nullptr;
+  DevTables slice{};          // the loaded slice (T switches to the home sub-snapshot after the second unpack)
+  bool shard_home = false;    // T is a home sub-snapshot: results are translated to global rows
+  int shard_round = 0;        // last completed step: 1 routed1, 2 unpacked1, 3 routed2, 4 unpacked2
+  std::vector<DBuf> arena[3];
+  size_t arena_used[3] = {0, 0, 0};
+  void *shard_alloc(int a, size_t bytes) {
+    if (arena_used[a] >= arena[a].size()) arena[a].emplace_back();
+    return dev_ensure(arena[a][arena_used[a]++], bytes + 32);
+  }
+  void shard_reset(int a) { arena_used[a] = 0; }
+  void copy_bytes(void *dst, const void *src, size_t n) {
+    if (n) CK(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToDevice, stream));
+  }
   std::vector<HostResult *> free_results;
   float ms_h2d = 0;
   u32 launches = 0;
@@ -662,6 +678,9 @@ static void do_load(gar_engine *e, const gar_objects *o, const gar_actual *a) {
   e->input_bytes = table_bytes(o, a);
   e->loaded = true;
   e->attached = false;
+  e->slice = e->T;
+  e->shard_home = false;
+  e->shard_round = 0;
 }
 
 // ------------------------------------------------------------------ diff
@@ -674,9 +693,13 @@ static void do_diff(gar_engine *e, gar_changeset *out, bool to_host, const gar_k
   e->marks.clear();
   e->events_used = 0;
   e->stage_depth = 0;
+  if (e->shard_home && (ks || bd)) throw InvalidError{"incremental / binding diffs are not available on a sharded sub-snapshot"};
   if (!e->pipe) {
     e->pipe = new Pipeline<gar_engine>(*e, e->T);
-    e->T.cluster = (const u8 *)e->cluster_dev.p;
+    if (e->shard_home) {
+      e->pipe->acc_guest_from = e->sharder->guest_from;
+      e->pipe->sharded = 1;
+    }
   }
   Pipeline<gar_engine> &P = *e->pipe;
   if (e->reprepare) P.prepared = false;
@@ -747,6 +770,7 @@ static void do_diff(gar_engine *e, gar_changeset *out, bool to_host, const gar_k
     CK(cudaStreamSynchronize(e->stream));  // the staging vectors go out of scope
     rc = P.run_keys(rows, ks->n_rows, DelKeys{dkind, dkey, dslab}, ks->n_deleted, &dc, ops_alloc);
   }
+  if (rc == GAR_OK && e->shard_home && dc.n_ops) e->for_each("shard_translate_ops", (u32)dc.n_ops, FShTranslateOps{(gar_op *)e->d_ops.p, e->sharder->gids});
   CK(cudaEventRecord(e->ev[3], e->stream));
   if (rc == GAR_E_INVALID) {
     CK(cudaStreamSynchronize(e->stream));
@@ -784,7 +808,13 @@ static void do_diff(gar_engine *e, gar_changeset *out, bool to_host, const gar_k
     out->tok_region = (const gar_str *)pull(h->tok_region, e->d_tok_region, 8 * (size_t)nlbi);
     out->dport_begin = (const u32 *)pull(h->dport_begin, e->d_dport_begin, partial ? 0 : 4 * (size_t)(n + 1));
     out->dports = (const i32 *)pull(h->dports, e->d_dports, 4 * (size_t)dc.n_dports);
+    if (e->shard_home) {
+      void *p = e->pin_ensure(h->obj_gid, 4 * (size_t)n);
+      if (n) CK(cudaMemcpyAsync(p, e->sharder->gids.obj, 4 * (size_t)n, cudaMemcpyDeviceToHost, e->stream));
+      out->obj_gid = (const u32 *)p;
+    }
   } else {
+    if (e->shard_home) out->obj_gid = e->sharder->gids.obj;
     out->status_ga = (const u32 *)e->d_status_ga.p;
     out->status_r53 = (const u32 *)e->d_status_r53.p;
     out->derived = (const u32 *)d_derived_src.p;
@@ -890,13 +920,16 @@ void gar_engine_destroy(gar_engine *e) {
   for (auto &b : e->in) cudaFree(b.p);
   for (auto &b : e->slot) cudaFree(b.p);
   delete e->pipe;
+  delete e->sharder;
+  for (auto &ar : e->arena)
+    for (auto &b : ar) cudaFree(b.p);
   for (DBuf *b : {&e->d_derived_keys, &e->d_key_rows, &e->d_del_kind, &e->d_del_key, &e->d_del_slab}) cudaFree(b->p);
   for (auto &b : e->d_egb) cudaFree(b.p);
   for (DBuf *b : {&e->cluster_dev, &e->d_status_ga, &e->d_status_r53, &e->d_derived, &e->d_ops, &e->d_tok_code, &e->d_tok_name, &e->d_tok_region,
                   &e->d_dport_begin, &e->d_dports, &e->d_scan_tiles, &e->d_hist})
     cudaFree(b->p);
   for (HostResult *h : e->free_results) {
-    for (DBuf *b : {&h->status_ga, &h->status_r53, &h->derived, &h->ops, &h->tok_code, &h->tok_name, &h->tok_region, &h->dport_begin, &h->dports}) cudaFreeHost(b->p);
+    for (DBuf *b : {&h->status_ga, &h->status_r53, &h->derived, &h->ops, &h->tok_code, &h->tok_name, &h->tok_region, &h->dport_begin, &h->dports, &h->obj_gid}) cudaFreeHost(b->p);
     delete h;
   }
   for (auto &ev : e->ev)
@@ -927,6 +960,9 @@ int gar_snapshot_attach_device(gar_engine *e, const gar_objects *desired, const 
     e->ms_h2d = 0;
     e->loaded = true;
     e->attached = true;
+    e->slice = e->T;
+    e->shard_home = false;
+    e->shard_round = 0;
   });
 }
 
@@ -949,6 +985,63 @@ int gar_bindings_diff(gar_engine *e, const gar_bindings *bindings, gar_changeset
   if (!out || !bindings) return GAR_E_INVALID;
   return guarded(e, [&] { do_diff(e, out, true, nullptr, bindings); });
 }
+
+int gar_shard_route(gar_engine *e, const gar_shard *shard, int round, uint64_t *meta, uint64_t *send_bytes) {
+  if (!shard || !meta || !send_bytes) return GAR_E_INVALID;
+  return guarded(e, [&] {
+    if (!e->loaded) throw InvalidError{"no slice loaded"};
+    if (shard->n_ranks < 1 || shard->n_ranks > GAR_SHARD_MAX_RANKS || shard->rank >= shard->n_ranks) throw InvalidError{"bad gar_shard"};
+    CK(cudaSetDevice(e->device));
+    if (!e->sharder) e->sharder = new Sharder<gar_engine>(*e);
+    if (round == 1) {
+      e->slice.cluster = (const u8 *)e->cluster_dev.p;
+      e->slice.cluster_len = (u32)e->cluster.size();
+      e->sharder->route1(e->slice, *shard, meta, send_bytes);
+      e->shard_round = 1;
+    } else if (round == 2) {
+      if (e->shard_round != 2) throw InvalidError{"gar_shard_route(2) needs the round-1 blobs unpacked first"};
+      e->sharder->route2(meta, send_bytes);
+      e->shard_round = 3;
+    } else {
+      throw InvalidError{"round must be 1 or 2"};
+    }
+    CK(cudaStreamSynchronize(e->stream));
+  });
+}
+
+int gar_shard_pack(gar_engine *e, void *send) {
+  return guarded(e, [&] {
+    if (e->shard_round != 1 && e->shard_round != 3) throw InvalidError{"gar_shard_pack without a routed plan"};
+    CK(cudaSetDevice(e->device));
+    e->sharder->pack((u8 *)send);
+    CK(cudaStreamSynchronize(e->stream));  // the host hands `send` to the exchange next
+    CK(cudaGetLastError());
+  });
+}
+
+int gar_shard_unpack(gar_engine *e, int round, const void *recv, const uint64_t *recv_meta) {
+  if (!recv_meta) return GAR_E_INVALID;
+  return guarded(e, [&] {
+    CK(cudaSetDevice(e->device));
+    if (round == 1 && e->shard_round == 1) {
+      e->sharder->unpack1((const u8 *)recv, recv_meta);
+      e->shard_round = 2;
+    } else if (round == 2 && e->shard_round == 3) {
+      e->sharder->unpack2((const u8 *)recv, recv_meta);
+      delete e->pipe;
+      e->pipe = nullptr;
+      e->T = e->sharder->H;
+      e->shard_home = true;
+      e->shard_round = 4;
+    } else {
+      throw InvalidError{"gar_shard_unpack out of sequence"};
+    }
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaGetLastError());
+  });
+}
+
+uint64_t gar_shard_blob_bytes(const uint64_t *meta_row) { return meta_row ? blob_bytes(meta_row) : 0; }
 
 void gar_changeset_free(gar_engine *e, gar_changeset *cs) {
   if (!e || !cs) return;

@@ -149,7 +149,7 @@ struct FRowOwner {
     e->a1 = 0;
     e->s0 = W.acc_owner_key[i];
     e->s1 = 0;
-    return (fl & ACC_MINE) && (fl & ACC_OWNER_KEYED);
+    return (fl & ACC_MINE) && (fl & ACC_OWNER_KEYED) && i < W.acc_guest_from;
   }
 };
 struct FRowThost {
@@ -160,7 +160,7 @@ struct FRowThost {
     e->a0 = e->a1 = 0;
     e->s0 = W.acc_thost[i];
     e->s1 = T.a.acc_dns[i];
-    return (W.acc_flags[i] & ACC_MINE) != 0;
+    return (W.acc_flags[i] & ACC_MINE) != 0 && (!W.sharded || i >= W.acc_guest_from);
   }
 };
 struct FRowZone {
@@ -619,10 +619,12 @@ struct Pipeline {
   u64 n_dports = 0;
   u32 *errflag = nullptr;
 
-  int prepare() {
-    const u32 n = T.o.n_objects, nlbi = T.o.n_lbi, nacc = T.a.n_accels, nzone = T.a.n_zones, nrec = T.a.n_records, nval = T.a.n_values;
+  u32 acc_guest_from = 0xFFFFFFFFu;  // sharded mode: set before prepare()
+  u32 sharded = 0;
+
+  void alloc_work() {
+    const u32 n = T.o.n_objects, nlbi = T.o.n_lbi, nacc = T.a.n_accels, nrec = T.a.n_records, nval = T.a.n_values;
     W.derived = (u32 *)be.ensure(S_DERIVED, 4 * (size_t)(n + 1));
-    u32 *derived_public = (u32 *)be.out_derived(n);
     W.okey_hash = (u64 *)be.ensure(S_OKEY_HASH, 8 * (size_t)(n + 1));
     W.ann_r53 = (gar_str *)be.ensure(S_ANN_R53, 8 * (size_t)(n + 1));
     W.ann_name = (gar_str *)be.ensure(S_ANN_NAME, 8 * (size_t)(n + 1));
@@ -653,7 +655,12 @@ struct Pipeline {
     W.r53_acc_dns = (gar_str *)be.ensure(S_R53_ACC_DNS, 8 * (size_t)(n + 1));
     errflag = (u32 *)be.ensure(S_ERRFLAG, 64);
     be.fill32(errflag, 0, 4);
-
+    W.acc_guest_from = acc_guest_from;
+    W.sharded = sharded;
+  }
+  void stage1() {
+    const u32 n = T.o.n_objects, nlbi = T.o.n_lbi, nacc = T.a.n_accels, nrec = T.a.n_records, nval = T.a.n_values;
+    u32 *derived_public = (u32 *)be.out_derived(n);
     // stage 1: row-local preprocessing
     if (n) be.for_each("classify_objects", n, FClassify{T, W, derived_public, nullptr, errflag});
     if (nlbi) be.for_each("tokenise_hostnames", nlbi, FTokenise{T, W});
@@ -661,7 +668,18 @@ struct Pipeline {
     if (nrec) be.for_each("prepare_records", nrec, FPrepareRecord{T, W});
     if (nval) be.for_each("expand_val_rec", nval, FExpand{T.a.rec_val_begin, nrec, W.val_rec});
     if (nval) be.for_each("classify_values", nval, FClassifyValue{T, W});
+  }
+  // what the sharded mode's routing needs of a rank's slice: the row-local pass + the (zone, name) -> alias record index
+  void prepare_route() {
+    alloc_work();
+    stage1();
+    W.ix_alias = build_index(S_IX_ALIAS, T.a.n_records, 2, FRowAlias{T, W}, errflag + 1, true);
+  }
 
+  int prepare() {
+    const u32 n = T.o.n_objects, nacc = T.a.n_accels, nzone = T.a.n_zones, nrec = T.a.n_records, nval = T.a.n_values;
+    alloc_work();
+    stage1();
     // stage 2: listen-ports annotation -> desired port lists (count, scan, write)
     be.fill32(W.dport_begin, 0, (size_t)n + 1);
     if (n) be.for_each("listen_ports_count", n, FJsonCount{T, W});

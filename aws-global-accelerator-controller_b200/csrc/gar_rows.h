@@ -104,6 +104,11 @@ struct Work {
   u64 *val_key_hash; // [n_values] key_hash_kinded(kind, val_key) for owner values
   u8 *val_orphan;    // [n_values] 1 = owner value of this cluster whose object is not in the cache
   ValLink *val_link;      // [n_values] owner values: first alias record of type A under the same (zone, name) + its DNSName
+  // sharded mode (gar_shard.h): rows >= acc_guest_from are guest copies that answer by-target-hostname lookups only;
+  // the rows below it are this shard's own accelerators (owner-keyed lookups, orphan detection).  Unsharded: 0xFFFFFFFF
+  // and every row serves both.
+  u32 acc_guest_from;
+  u32 sharded;
   // route53 ensure, relational form (objects with exactly one lbIngress)
   u8 *r53_mode;        // [n] R53_MODE_*
   u32 *r53_acc;        // [n] the accelerator found by target hostname
@@ -247,10 +252,8 @@ GAR_HD u32 name_dash_id(Str s) {
   return last;
 }
 
-GAR_HD void tokenise_hostname(const DevTables &T, const Work &W, u32 row) {
-  gar_str href = T.o.lbi_hostname[row];
-  Str h = mkstr(T.o.slab, href);
-  u64 base = GAR_STR_OFF(href);
+// the tokeniser proper: h = the hostname bytes, base = its offset in the slab the name/region refs point into
+GAR_HD u8 tokenise_str(Str h, u64 base, gar_str *name_out, gar_str *region_out) {
   u8 code;
   gar_str name = 0, region = 0;
   // label boundaries: the first three dots
@@ -312,6 +315,14 @@ GAR_HD void tokenise_hostname(const DevTables &T, const Work &W, u32 row) {
     name = 0;
     region = 0;
   }
+  *name_out = name;
+  *region_out = region;
+  return code;
+}
+GAR_HD void tokenise_hostname(const DevTables &T, const Work &W, u32 row) {
+  gar_str href = T.o.lbi_hostname[row];
+  gar_str name, region;
+  u8 code = tokenise_str(mkstr(T.o.slab, href), GAR_STR_OFF(href), &name, &region);
   W.tok_code[row] = code;
   W.tok_name[row] = name;
   W.tok_region[row] = region;
@@ -1446,6 +1457,7 @@ GAR_HD bool object_in_cache(const DevTables &T, const Work &W, u32 kind, Str key
 // process{Service,Ingress}Delete of the globalaccelerator controller (service.go:28-52, ingress.go:29-54) for an
 // accelerator whose owner key has no object: returns 1 and emits the delete op
 GAR_HD u32 ga_orphan(const DevTables &T, const Work &W, u32 acc, OpSink &s) {
+  if (acc >= W.acc_guest_from) return 0;
   u32 fl = W.acc_flags[acc];
   if (!(fl & ACC_MINE) || !(fl & ACC_OWNER_3PART)) return 0;
   u32 kind = (fl & ACC_OWNER_INGRESS) ? 1u : 0u;

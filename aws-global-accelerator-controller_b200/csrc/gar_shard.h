@@ -1,0 +1,981 @@
+// gar_shard.h — ONE cluster sharded by key hash across ranks (SURVEY.md §8 row e, BASELINE configs[3]:
+// "10^7 objects sharded by key-hash across 8xB200 with one NCCL all-to-all").
+//
+// Every rank starts with an arbitrary contiguous slice of each list (the packer just cuts the lister output and the
+// paginated AWS lists into n_ranks ranges; include/garecon.h "sharded mode").  The diff is a join DAG over several keys,
+// so rows are re-homed on the device:
+//
+//   round 1 (the all-to-all): every row travels to the shard its OWN key hashes to
+//        objects                               -> home(key_hash_kinded(kind, "ns/name"))
+//        accelerators of this cluster (+tags, listeners, port ranges, endpoint groups, endpoints)
+//                                              -> home(owner tag key)           ["own" rows: owner lookups, orphans]
+//        owner values (TXT) with their record  -> home(owner key inside the value)
+//        alias records                         -> every home an owner value under the same (zone, name) goes to
+//                                                 (the TXT-join-A on (zone, name) is local: whole zones stay together)
+//      and, for the two lookups keyed by something the OBJECT does not own (its load balancer's hostname):
+//        load balancers                        -> dir(key_hash_lb(region, name))
+//        accelerator stubs (row + tags)        -> dir(directory key of the target-hostname tag)
+//        one probe per lbIngress hostname      -> dir(directory key of the hostname), carrying home(object)
+//   round 2 (answers, small): each directory shard resolves its probes against the rows it received (first row wins,
+//      global order) and forwards the matching LB row / the first two by-hostname accelerators to the probe's home.
+//
+// After round 2 every rank holds a SELF-CONTAINED sub-snapshot (own objects + everything their decisions read) and runs
+// the ordinary single-GPU pipeline on it; ops and statuses come back with GLOBAL row ids.  Accelerators that arrived as
+// answers are "guest" rows: they serve by-target-hostname lookups only (Work::acc_guest_from).
+//
+// The exchange itself is the host's job (torch.distributed all_to_all_single over NCCL/NVLink in ranks.py): this file
+// plans, packs one contiguous blob per destination, and merges the received blobs.  Same text runs in tests/hostsim.
+//
+// Backend additions:  void *shard_alloc(int arena, size_t bytes);  void shard_reset(int arena);
+//                     void copy_bytes(void *dst, const void *src, size_t n);
+#pragma once
+
+#include "gar_pipeline.h"
+
+constexpr int SH_MAX_RANKS = GAR_SHARD_MAX_RANKS;
+constexpr int SH_MAX_SEGS = 2 * SH_MAX_RANKS;
+enum ShLevel { L_OBJ, L_ANN, L_LBI, L_PORT, L_ACC, L_TAG, L_LIS, L_PR, L_EG, L_EP, L_REC, L_VAL, L_ZONE, L_LB, L_STUB, L_STUBTAG, L_PROBE, L_NLEVELS };
+static_assert(2 * L_NLEVELS <= GAR_SHARD_META_WORDS, "meta row too small");
+constexpr int SH_MAX_STR = 4, SH_MAX_U8 = 3, SH_MAX_U32 = 1, SH_MAX_CHILD = 3;
+enum { SH_ARENA_PLAN = 0, SH_ARENA_DIR = 1, SH_ARENA_HOME = 2 };
+constexpr u32 SH_DROP = 255;  // destination of a row nobody needs
+
+struct LevelSchema {
+  int n_str, n_u8, n_u32, has_gid, n_child;
+  int child[SH_MAX_CHILD];
+};
+// columns per level (order = the order of the fields in include/garecon.h)
+static const LevelSchema SH_SCHEMA[L_NLEVELS] = {
+    /* OBJ     */ {2, 3, 1, 1, 3, {L_ANN, L_LBI, L_PORT}},  // "ns/name" key, ingress_class | kind, spec_type, flags | ns_len
+    /* ANN     */ {2, 0, 0, 0, 0, {0, 0, 0}},
+    /* LBI     */ {1, 0, 0, 0, 0, {0, 0, 0}},
+    /* PORT    */ {1, 0, 1, 0, 0, {0, 0, 0}},               // proto | number
+    /* ACC     */ {2, 1, 0, 1, 2, {L_TAG, L_LIS, 0}},       // name, dns | enabled
+    /* TAG     */ {2, 0, 0, 0, 0, {0, 0, 0}},
+    /* LIS     */ {0, 1, 0, 1, 2, {L_PR, L_EG, 0}},         // proto
+    /* PR      */ {0, 0, 1, 0, 0, {0, 0, 0}},
+    /* EG      */ {0, 0, 0, 1, 1, {L_EP, 0, 0}},
+    /* EP      */ {1, 0, 0, 0, 0, {0, 0, 0}},
+    /* REC     */ {2, 2, 1, 1, 1, {L_VAL, 0, 0}},           // name, alias_dns | type, has_alias | zone
+    /* VAL     */ {1, 0, 0, 1, 0, {0, 0, 0}},
+    /* ZONE    */ {1, 0, 0, 0, 0, {0, 0, 0}},
+    /* LB      */ {4, 1, 0, 1, 0, {0, 0, 0}},               // region, name, dns, arn | state
+    /* STUB    */ {2, 1, 0, 1, 1, {L_STUBTAG, 0, 0}},       // an accelerator row without its listeners
+    /* STUBTAG */ {2, 0, 0, 0, 0, {0, 0, 0}},
+    /* PROBE   */ {1, 0, 1, 0, 0, {0, 0, 0}},               // hostname | home shard
+};
+
+// byte offsets of one level's columns inside a blob (all 16-byte aligned)
+struct LevelLayout {
+  u64 str[SH_MAX_STR], u8c[SH_MAX_U8], u32c[SH_MAX_U32], gid, cnt[SH_MAX_CHILD], slab, end;
+};
+inline u64 sh_align(u64 x) { return (x + 15) & ~(u64)15; }
+inline LevelLayout level_layout(int lvl, u64 base, u64 n, u64 slab_bytes) {
+  const LevelSchema &S = SH_SCHEMA[lvl];
+  LevelLayout L{};
+  u64 p = base;
+  for (int c = 0; c < S.n_str; c++) { L.str[c] = p; p = sh_align(p + 8 * n); }
+  for (int c = 0; c < S.n_u8; c++) { L.u8c[c] = p; p = sh_align(p + n); }
+  for (int c = 0; c < S.n_u32; c++) { L.u32c[c] = p; p = sh_align(p + 4 * n); }
+  if (S.has_gid) { L.gid = p; p = sh_align(p + 4 * n); }
+  for (int c = 0; c < S.n_child; c++) { L.cnt[c] = p; p = sh_align(p + 4 * n); }
+  L.slab = p;
+  p = sh_align(p + slab_bytes);
+  L.end = p;
+  return L;
+}
+// meta row of one (source, destination) pair: rows per level, then slab bytes per level
+inline u64 blob_bytes(const u64 *meta) {
+  u64 p = 0;
+  for (int l = 0; l < L_NLEVELS; l++) p = level_layout(l, p, meta[l], meta[L_NLEVELS + l]).end;
+  return p;
+}
+
+// ------------------------------------------------------------------ device-side descriptors
+
+struct LevelSrc {  // where a level's rows come from (device pointers)
+  const gar_str *str[SH_MAX_STR];
+  const u8 *u8c[SH_MAX_U8];
+  const u32 *u32c[SH_MAX_U32];
+  const u32 *gid;  // explicit global ids (rows that already travelled once), else gid_base + row
+  u32 gid_base;
+  const u32 *child_begin[SH_MAX_CHILD];
+  const u8 *child_dest[SH_MAX_CHILD];  // nullable: child c follows its parent only to destination child_dest[c]
+  const u8 *slab;
+  u32 n;
+};
+struct LevelPlan {  // selection of one level: rows sel[0..*m) sorted by destination
+  u32 *sel;
+  u32 *m;         // device scalar
+  u32 cap;        // host upper bound of *m
+  u32 *row_off;   // device [n_ranks+1]
+  u32 *slab_scan; // [cap+1] exclusive scan of the rows' string bytes
+  u32 *slab_off;  // device [n_ranks+1]
+  u32 *cnt[SH_MAX_CHILD];  // [cap+1] exclusive scan of child counts per link
+  u32 multi;      // host-side note: a source row may be selected for several destinations (children can outnumber the source level)
+};
+
+GAR_HD u32 shard_of(u64 h, u32 n_ranks) { return (u32)(xx_avalanche(h + 0x9E3779B97F4A7C15ull) >> 33) % n_ranks; }
+// The key of the two by-hostname lookups (GetLoadBalancer by (region, name) of the tokenised hostname, global_accelerator.go:116-120;
+// ListGlobalAcceleratorByHostname by the hostname itself, :62-85): one function of the hostname string, so the probe, the
+// LB it resolves to and every accelerator tagged with that hostname meet on one shard.
+GAR_HD u64 directory_key(u8 code, Str host, Str region, Str name) { return code <= GAR_TOK_NLB ? key_hash_lb(region, name) : gar_hash(host); }
+GAR_HD u32 dest_of(u32 j, const u32 *row_off, u32 n_ranks) {
+  u32 d = 0;
+  while (d + 1 < n_ranks && j >= row_off[d + 1]) d++;
+  return d;
+}
+
+// ------------------------------------------------------------------ routing keys (round 1)
+
+struct FShKeyObj {
+  Work W;
+  u32 G;
+  u32 *keys, *vals;
+  GAR_HD void operator()(u32 i) const {
+    keys[i] = shard_of(W.okey_hash[i], G);
+    vals[i] = i;
+  }
+};
+struct FShObjKey {  // the "ns/name" key as one string + where it splits
+  DevTables T;
+  gar_str *key;
+  u32 *ns_len;
+  GAR_HD void operator()(u32 i) const {
+    gar_str ns = T.o.obj_ns[i];
+    key[i] = GAR_STR(GAR_STR_OFF(ns), GAR_STR_LEN(ns) + 1 + GAR_STR_LEN(T.o.obj_name[i]));
+    ns_len[i] = (u32)GAR_STR_LEN(ns);
+  }
+};
+struct FShKeyLb {
+  DevTables T;
+  u32 G;
+  u32 *keys, *vals;
+  GAR_HD void operator()(u32 i) const {
+    keys[i] = shard_of(key_hash_lb(mkstr(T.a.slab, T.a.lb_region[i]), mkstr(T.a.slab, T.a.lb_name[i])), G);
+    vals[i] = i;
+  }
+};
+struct FShKeyAcc {  // own rows: what ListGlobalAcceleratorByResource can return and what the orphan pass inspects
+  Work W;
+  u32 G;
+  u32 *keys, *vals;
+  GAR_HD void operator()(u32 a) const {
+    u32 fl = W.acc_flags[a];
+    keys[a] = ((fl & ACC_MINE) && (fl & ACC_OWNER_KEYED)) ? shard_of(W.acc_owner_hash[a], G) : SH_DROP;
+    vals[a] = a;
+  }
+};
+struct FShKeyStub {  // what ListGlobalAcceleratorByHostname can return
+  DevTables T;
+  Work W;
+  u32 G;
+  u32 *keys, *vals;
+  GAR_HD void operator()(u32 a) const {
+    u32 k = SH_DROP;
+    if (W.acc_flags[a] & ACC_MINE) {
+      gar_str th = W.acc_thost[a], name, region;
+      Str h = mkstr(T.a.slab, th);
+      u8 code = tokenise_str(h, GAR_STR_OFF(th), &name, &region);
+      k = shard_of(directory_key(code, h, mkstr(T.a.slab, region), mkstr(T.a.slab, name)), G);
+    }
+    keys[a] = k;
+    vals[a] = a;
+  }
+};
+struct FShKeyProbe {
+  DevTables T;
+  Work W;
+  const u32 *lbi_obj;
+  u32 G;
+  u32 *keys, *vals, *home;
+  GAR_HD void operator()(u32 l) const {
+    Str h = mkstr(T.o.slab, T.o.lbi_hostname[l]);
+    keys[l] = shard_of(directory_key(W.tok_code[l], h, mkstr(T.o.slab, W.tok_region[l]), mkstr(T.o.slab, W.tok_name[l])), G);
+    vals[l] = l;
+    home[l] = shard_of(W.okey_hash[lbi_obj[l]], G);
+  }
+};
+struct FShValDest {
+  Work W;
+  u32 G;
+  u8 *val_dest;
+  GAR_HD void operator()(u32 v) const { val_dest[v] = W.val_cls[v] == VAL_NOT_OWNER ? (u8)SH_DROP : (u8)shard_of(W.val_key_hash[v], G); }
+};
+// (destination, record) pairs: the record of every owner value, and every alias record under the same (zone, name)
+// (FindOwneredARecordSets, route53.go:216-238).  Count pass (pairs == nullptr) then fill pass.
+struct FShRecPairs {
+  DevTables T;
+  Work W;
+  const u8 *val_dest;
+  u32 *counts;  // count pass: written; fill pass: scanned
+  u32 *keys, *vals;
+  GAR_HD void operator()(u32 v) const {
+    u32 d = val_dest[v];
+    if (d == SH_DROP) {
+      if (!keys) counts[v] = 0;
+      return;
+    }
+    u32 rec = W.val_rec[v], zone = W.rec_zone[rec];
+    u32 n = 0, base = keys ? counts[v] : 0;
+    if (keys) {
+      keys[base] = d;
+      vals[base] = rec;
+    }
+    n++;
+    Str name = mkstr(T.a.slab, T.a.rec_name[rec]);
+    Cursor c = idx_open(W.ix_alias, key_hash_zoned_h(zone, W.rec_name_hash[rec]));
+    IdxEntry e;
+    while (idx_next(W.ix_alias, c, &e)) {
+      if (e.a0 != zone || e.row == rec || !streq(mkstr(T.a.slab, e.s0), name)) continue;
+      if (keys) {
+        keys[base + n] = d;
+        vals[base + n] = e.row;
+      }
+      n++;
+    }
+    if (!keys) counts[v] = n;
+  }
+};
+struct FShIota {
+  u32 *keys, *vals;
+  u32 key;
+  GAR_HD void operator()(u32 i) const {
+    keys[i] = key;
+    vals[i] = i;
+  }
+};
+
+// ------------------------------------------------------------------ selection lists
+
+// keys sorted ascending; row_off[d] = first position with key >= d (d = 0..G); *m = row_off[G]
+struct FShSelBounds {
+  const u32 *keys;
+  u32 n, G;
+  u32 *row_off, *m;
+  GAR_HD void operator()(u32 d) const {
+    u32 lo = 0, hi = n;
+    while (lo < hi) {
+      u32 mid = (lo + hi) >> 1;
+      if (keys[mid] < d) lo = mid + 1;
+      else hi = mid;
+    }
+    row_off[d] = lo;
+    if (d == G) *m = lo;
+  }
+};
+struct FShUniqueFlag {  // (keys, vals) sorted by (key, val): keep the first of each run, drop SH_DROP
+  const u32 *keys, *vals;
+  u32 n;
+  u32 *flag;  // [n+1]
+  GAR_HD void operator()(u32 j) const {
+    u32 f = 0;
+    if (j < n) f = keys[j] != SH_DROP && (j == 0 || keys[j] != keys[j - 1] || vals[j] != vals[j - 1]);
+    flag[j] = f;
+  }
+};
+struct FShCompact {
+  const u32 *keys, *vals, *scanned;
+  u32 *keys_out, *vals_out;
+  GAR_HD void operator()(u32 j) const {
+    if (scanned[j + 1] != scanned[j]) {
+      keys_out[scanned[j]] = keys[j];
+      vals_out[scanned[j]] = vals[j];
+    }
+  }
+};
+struct FShChildCount {
+  LevelSrc src;
+  int link;
+  LevelPlan P;
+  u32 G;
+  u32 *out;  // [cap+1]
+  GAR_HD void operator()(u32 j) const {
+    u32 c = 0;
+    if (j < *P.m) {
+      u32 p = P.sel[j], b0 = src.child_begin[link][p], b1 = src.child_begin[link][p + 1];
+      const u8 *cd = src.child_dest[link];
+      if (cd) {
+        u32 d = dest_of(j, P.row_off, G);
+        for (u32 ch = b0; ch < b1; ch++) c += cd[ch] == d;
+      } else {
+        c = b1 - b0;
+      }
+    }
+    out[j] = c;
+  }
+};
+struct FShChildFill {
+  LevelSrc src;
+  int link;
+  LevelPlan P;
+  u32 G;
+  u32 *child_sel;
+  GAR_HD void operator()(u32 j) const {
+    if (j >= *P.m) return;
+    u32 p = P.sel[j], b0 = src.child_begin[link][p], b1 = src.child_begin[link][p + 1];
+    u32 pos = P.cnt[link][j];
+    const u8 *cd = src.child_dest[link];
+    if (cd) {
+      u32 d = dest_of(j, P.row_off, G);
+      for (u32 ch = b0; ch < b1; ch++)
+        if (cd[ch] == d) child_sel[pos++] = ch;
+    } else {
+      for (u32 ch = b0; ch < b1; ch++) child_sel[pos++] = ch;
+    }
+  }
+};
+// boundaries of a derived list (children, string bytes): value of the parent's scan at the parent's boundaries
+struct FShDerivedBounds {
+  const u32 *parent_row_off, *scanned;
+  u32 G;
+  u32 *out_off, *out_m;
+  GAR_HD void operator()(u32 d) const {
+    u32 v = scanned[parent_row_off[d]];
+    out_off[d] = v;
+    if (d == G && out_m) *out_m = v;
+  }
+};
+struct FShStrLen {
+  LevelSrc src;
+  int n_str;
+  LevelPlan P;
+  u32 *out;  // [cap+1]
+  GAR_HD void operator()(u32 j) const {
+    u32 b = 0;
+    if (j < *P.m) {
+      u32 p = P.sel[j];
+      for (int c = 0; c < n_str; c++) b += (u32)GAR_STR_LEN(src.str[c][p]);
+    }
+    out[j] = b;
+  }
+};
+
+// ------------------------------------------------------------------ pack
+
+struct PackDst {
+  u8 *base[SH_MAX_RANKS];  // start of destination d's blob
+  LevelLayout lay[SH_MAX_RANKS];
+};
+struct FShPackCols {
+  LevelSrc src;
+  LevelSchema S;
+  LevelPlan P;
+  u32 G;
+  PackDst D;
+  GAR_HD void operator()(u32 j) const {
+    u32 d = dest_of(j, P.row_off, G), k = j - P.row_off[d], p = P.sel[j];
+    u8 *b = D.base[d];
+    const LevelLayout &L = D.lay[d];
+    u64 off = P.slab_scan[j] - P.slab_scan[P.row_off[d]];
+    for (int c = 0; c < S.n_str; c++) {
+      u64 len = GAR_STR_LEN(src.str[c][p]);
+      ((gar_str *)(b + L.str[c]))[k] = GAR_STR(off, len);
+      off += len;
+    }
+    for (int c = 0; c < S.n_u8; c++) (b + L.u8c[c])[k] = src.u8c[c][p];
+    for (int c = 0; c < S.n_u32; c++) ((u32 *)(b + L.u32c[c]))[k] = src.u32c[c][p];
+    if (S.has_gid) ((u32 *)(b + L.gid))[k] = src.gid ? src.gid[p] : src.gid_base + p;
+    for (int c = 0; c < S.n_child; c++) ((u32 *)(b + L.cnt[c]))[k] = P.cnt[c][j + 1] - P.cnt[c][j];
+  }
+};
+// one warp-width of threads per selected row: lane l copies bytes l, l+32, ... of each string (coalesced)
+struct FShPackBytes {
+  LevelSrc src;
+  int n_str;
+  LevelPlan P;
+  u32 G;
+  PackDst D;
+  GAR_HD void operator()(u32 t) const {
+    u32 j = t >> 5, lane = t & 31;
+    u32 d = dest_of(j, P.row_off, G), p = P.sel[j];
+    u8 *dst = D.base[d] + D.lay[d].slab + (P.slab_scan[j] - P.slab_scan[P.row_off[d]]);
+    for (int c = 0; c < n_str; c++) {
+      gar_str r = src.str[c][p];
+      const u8 *s = src.slab + GAR_STR_OFF(r);
+      u32 len = (u32)GAR_STR_LEN(r);
+      for (u32 x = lane; x < len; x += 32) dst[x] = s[x];
+      dst += len;
+    }
+  }
+};
+
+// ------------------------------------------------------------------ unpack (merge the received blobs of one level)
+
+struct SegSrc {
+  const u8 *base;
+  LevelLayout lay;
+};
+struct UnpackDst {
+  gar_str *str[SH_MAX_STR];
+  u8 *u8c[SH_MAX_U8];
+  u32 *u32c[SH_MAX_U32];
+  u32 *gid;
+  u32 *cnt[SH_MAX_CHILD];  // raw child counts (the caller scans them into CSR begins); nullable
+};
+struct FShUnpackCols {
+  int nseg;
+  SegSrc seg[SH_MAX_SEGS];
+  u8 has_cnt[SH_MAX_SEGS][SH_MAX_CHILD];  // a segment of a level without that child link (stubs have no listeners) reads as 0
+  u32 seg_row[SH_MAX_SEGS + 1];
+  u64 slab_base[SH_MAX_SEGS];  // where segment s's string bytes start in the merged slab
+  LevelSchema S;
+  UnpackDst D;
+  GAR_HD void operator()(u32 j) const {
+    int s = 0;
+    while (s + 1 < nseg && j >= seg_row[s + 1]) s++;
+    u32 k = j - seg_row[s];
+    const u8 *b = seg[s].base;
+    const LevelLayout &L = seg[s].lay;
+    for (int c = 0; c < S.n_str; c++) {
+      gar_str r = ((const gar_str *)(b + L.str[c]))[k];
+      D.str[c][j] = GAR_STR(GAR_STR_OFF(r) + slab_base[s], GAR_STR_LEN(r));
+    }
+    for (int c = 0; c < S.n_u8; c++) D.u8c[c][j] = (b + L.u8c[c])[k];
+    for (int c = 0; c < S.n_u32; c++) D.u32c[c][j] = ((const u32 *)(b + L.u32c[c]))[k];
+    if (S.has_gid) D.gid[j] = ((const u32 *)(b + L.gid))[k];
+    for (int c = 0; c < S.n_child; c++)
+      if (D.cnt[c]) D.cnt[c][j] = has_cnt[s][c] ? ((const u32 *)(b + L.cnt[c]))[k] : 0u;
+  }
+};
+struct FShObjNsName {
+  const gar_str *key;
+  const u32 *ns_len;
+  gar_str *ns, *name;
+  GAR_HD void operator()(u32 i) const {
+    u64 off = GAR_STR_OFF(key[i]), len = GAR_STR_LEN(key[i]), nl = ns_len[i];
+    ns[i] = GAR_STR(off, nl);
+    name[i] = GAR_STR(off + nl + 1, len - nl - 1);
+  }
+};
+struct FShZoneHist {
+  const u32 *rec_zone;
+  u32 *begin;
+  GAR_HD void operator()(u32 r) const { GAR_ATOMIC_ADD(&begin[rec_zone[r]], 1u); }
+};
+
+// ------------------------------------------------------------------ directory: answer the probes (round 2 selection)
+
+// One probe = one lbIngress hostname of some object.  The LB the reference would get (first row wins) and the first two
+// accelerators ListGlobalAcceleratorByHostname would return go to the probe's home shard.
+struct FShAnswer {
+  DevTables T;  // directory tables: lbi_* = probes, lb_* and acc_* = rows routed here
+  Work W;
+  const u32 *home;
+  u32 n;
+  u32 *lb_keys, *lb_vals;      // [n]
+  u32 *stub_keys, *stub_vals;  // [2n]
+  GAR_HD void operator()(u32 p) const {
+    u32 d = home[p];
+    u32 lk = SH_DROP, lv = 0;
+    if (W.tok_code[p] <= GAR_TOK_NLB) {
+      u32 st;
+      u32 lb = find_lb(T, W, mkstr(T.o.slab, W.tok_region[p]), mkstr(T.o.slab, W.tok_name[p]), &st);
+      if (lb != GAR_NONE) {
+        lk = d;
+        lv = lb;
+      }
+    }
+    lb_keys[p] = lk;
+    lb_vals[p] = lv;
+    Str host = mkstr(T.o.slab, T.o.lbi_hostname[p]);
+    Cursor c = idx_open(W.ix_thost, key_hash_str(host));
+    IdxEntry e;
+    u32 k = 0;
+    while (k < 2 && idx_next(W.ix_thost, c, &e)) {
+      if (!streq(mkstr(T.a.slab, e.s0), host)) continue;
+      stub_keys[2 * p + k] = d;
+      stub_vals[2 * p + k] = e.row;
+      k++;
+    }
+    for (; k < 2; k++) {
+      stub_keys[2 * p + k] = SH_DROP;
+      stub_vals[2 * p + k] = 0;
+    }
+  }
+};
+
+// ------------------------------------------------------------------ results: local rows -> global ids
+
+struct ShGids {
+  const u32 *obj, *lb, *acc, *lis, *eg, *rec, *val;
+};
+struct FShTranslateOps {
+  gar_op *ops;
+  ShGids g;
+  GAR_HD u32 m(const u32 *tab, u32 v) const { return v == GAR_NONE ? GAR_NONE : tab[v]; }
+  GAR_HD void operator()(u32 k) const {
+    gar_op o = ops[k];
+    o.obj = m(g.obj, o.obj);
+    switch (o.head & 0xFFu) {
+      case GAR_OP_GA_CREATE_CHAIN: o.a0 = m(g.lb, o.a0); break;
+      case GAR_OP_GA_UPDATE_ACCEL: o.a0 = m(g.acc, o.a0); o.a1 = m(g.lb, o.a1); break;
+      case GAR_OP_GA_CREATE_LISTENER: o.a0 = m(g.acc, o.a0); break;
+      case GAR_OP_GA_UPDATE_LISTENER: o.a0 = m(g.acc, o.a0); o.a1 = m(g.lis, o.a1); break;
+      case GAR_OP_GA_CREATE_EG: o.a0 = m(g.acc, o.a0); o.a1 = m(g.lis, o.a1); o.a2 = m(g.lb, o.a2); break;
+      case GAR_OP_GA_UPDATE_EG: o.a0 = m(g.acc, o.a0); o.a1 = m(g.eg, o.a1); o.a2 = m(g.lb, o.a2); break;
+      case GAR_OP_GA_DELETE_CHAIN: o.a0 = m(g.acc, o.a0); o.a1 = m(g.lis, o.a1); o.a2 = m(g.eg, o.a2); break;
+      case GAR_OP_R53_CREATE: o.a1 = m(g.acc, o.a1); break;  // a0 = zone: the zone table is the same on every rank
+      case GAR_OP_R53_UPSERT_A: o.a1 = m(g.acc, o.a1); o.a2 = m(g.rec, o.a2); break;
+      case GAR_OP_R53_DELETE_RECORD: o.a1 = m(g.rec, o.a1); o.a2 = m(g.val, o.a2); break;
+      default: break;
+    }
+    ops[k] = o;
+  }
+};
+
+// ------------------------------------------------------------------ host-side driver
+
+template <class B>
+struct Sharder {
+  B &be;
+  gar_shard cfg{};
+  u32 G = 1;
+  DevTables S{};                     // this rank's slice
+  Pipeline<B> *slice_pipe = nullptr; // row-local pass over the slice
+  Pipeline<B> *dir_pipe = nullptr;   // directory tables + their indexes
+  DevTables Dt{};                    // directory tables
+  const u32 *dir_home = nullptr, *dir_lb_gid = nullptr, *dir_stub_gid = nullptr;
+  DevTables H{};                     // home sub-snapshot (result)
+  ShGids gids{};
+  u32 guest_from = 0;
+
+  // current plan
+  LevelSrc src[L_NLEVELS]{};
+  LevelPlan plan[L_NLEVELS]{};
+  bool active[L_NLEVELS]{};
+  u32 *bounds_dev = nullptr;  // [L_NLEVELS][2][SH_MAX_RANKS+1]
+  u32 h_row_off[L_NLEVELS][SH_MAX_RANKS + 1]{}, h_slab_off[L_NLEVELS][SH_MAX_RANKS + 1]{};
+  // round 1 receive side, kept for the home merge after round 2
+  const u8 *recv1 = nullptr;
+  u64 meta1[SH_MAX_RANKS][GAR_SHARD_META_WORDS]{};
+
+  explicit Sharder(B &b) : be(b) {}
+  ~Sharder() {
+    delete slice_pipe;
+    delete dir_pipe;
+  }
+
+  template <class Tp>
+  Tp *alloc(int arena, size_t count) { return (Tp *)be.shard_alloc(arena, sizeof(Tp) * (count + 1)); }
+  u32 *row_off_dev(int l) { return bounds_dev + (size_t)l * 2 * (SH_MAX_RANKS + 1); }
+  u32 *slab_off_dev(int l) { return row_off_dev(l) + (SH_MAX_RANKS + 1); }
+
+  void plan_begin() {
+    be.shard_reset(SH_ARENA_PLAN);
+    bounds_dev = alloc<u32>(SH_ARENA_PLAN, (size_t)L_NLEVELS * 2 * (SH_MAX_RANKS + 1) + 2 * L_NLEVELS);
+    be.fill32(bounds_dev, 0, (size_t)L_NLEVELS * 2 * (SH_MAX_RANKS + 1) + 2 * L_NLEVELS);
+    for (int l = 0; l < L_NLEVELS; l++) {
+      active[l] = false;
+      src[l] = LevelSrc{};
+      plan[l] = LevelPlan{};
+    }
+  }
+  u32 *m_dev(int l) { return bounds_dev + (size_t)L_NLEVELS * 2 * (SH_MAX_RANKS + 1) + l; }
+
+  // top-level selection from (keys, vals) that are already in their final (key, val) order; keys >= G are dropped
+  void set_top(int l, u32 *keys, u32 *vals, u32 n, bool multi = false) {
+    active[l] = true;
+    plan[l].multi = multi;
+    plan[l].sel = vals;
+    plan[l].cap = n;
+    plan[l].m = m_dev(l);
+    plan[l].row_off = row_off_dev(l);
+    plan[l].slab_off = slab_off_dev(l);
+    be.for_each("shard_bounds", G + 1, FShSelBounds{keys, n, G, plan[l].row_off, plan[l].m});
+  }
+  // single-destination level: one key per source row, stable partition by destination
+  template <class KeyF>
+  void top_single(int l, u32 n, KeyF make) {
+    u32 *keys = alloc<u32>(SH_ARENA_PLAN, n), *vals = alloc<u32>(SH_ARENA_PLAN, n);
+    u32 *k2 = alloc<u32>(SH_ARENA_PLAN, n), *v2 = alloc<u32>(SH_ARENA_PLAN, n);
+    if (n) {
+      be.for_each("shard_keys", n, make(keys, vals));
+      be.sort_pairs(keys, vals, k2, v2, n, 8);
+    }
+    set_top(l, keys, vals, n);
+  }
+  // children of level l (whose plan is set), then its string bytes
+  void plan_children_and_strings(int l) {
+    const LevelSchema &Sc = SH_SCHEMA[l];
+    LevelPlan &P = plan[l];
+    for (int c = 0; c < Sc.n_child; c++) {
+      int ch = Sc.child[c];
+      P.cnt[c] = alloc<u32>(SH_ARENA_PLAN, (size_t)P.cap + 1);
+      be.for_each("shard_child_count", P.cap + 1, FShChildCount{src[l], c, P, G, P.cnt[c]});
+      be.exclusive_scan(P.cnt[c], P.cap + 1);
+      active[ch] = true;
+      plan[ch].cap = src[ch].n;
+      plan[ch].multi = P.multi;
+      if (P.multi && !src[l].child_dest[c]) be.download(&plan[ch].cap, P.cnt[c] + P.cap, 4);  // replicated parents: exact child count
+      plan[ch].sel = alloc<u32>(SH_ARENA_PLAN, plan[ch].cap);
+      plan[ch].m = m_dev(ch);
+      plan[ch].row_off = row_off_dev(ch);
+      plan[ch].slab_off = slab_off_dev(ch);
+      if (P.cap) be.for_each("shard_child_fill", P.cap, FShChildFill{src[l], c, P, G, plan[ch].sel});
+      be.for_each("shard_child_bounds", G + 1, FShDerivedBounds{P.row_off, P.cnt[c], G, plan[ch].row_off, plan[ch].m});
+    }
+    P.slab_scan = alloc<u32>(SH_ARENA_PLAN, (size_t)P.cap + 1);
+    if (Sc.n_str) {
+      be.for_each("shard_strlen", P.cap + 1, FShStrLen{src[l], Sc.n_str, P, P.slab_scan});
+      be.exclusive_scan(P.slab_scan, P.cap + 1);
+    } else {
+      be.fill32(P.slab_scan, 0, (size_t)P.cap + 1);
+    }
+    be.for_each("shard_slab_bounds", G + 1, FShDerivedBounds{P.row_off, P.slab_scan, G, P.slab_off, nullptr});
+  }
+  // after every level is planned: bring the boundaries to the host and fill the meta rows
+  void plan_finish(u64 *meta /* [G][GAR_SHARD_META_WORDS] */, u64 *send_bytes) {
+    for (int l = 0; l < L_NLEVELS; l++)
+      if (active[l]) plan_children_and_strings(l);  // parents precede their children in ShLevel order
+    std::vector<u32> h((size_t)L_NLEVELS * 2 * (SH_MAX_RANKS + 1));
+    be.download(h.data(), bounds_dev, 4 * h.size());
+    for (int l = 0; l < L_NLEVELS; l++)
+      for (u32 d = 0; d <= G; d++) {
+        h_row_off[l][d] = active[l] ? h[((size_t)l * 2) * (SH_MAX_RANKS + 1) + d] : 0;
+        h_slab_off[l][d] = active[l] ? h[((size_t)l * 2 + 1) * (SH_MAX_RANKS + 1) + d] : 0;
+      }
+    for (u32 d = 0; d < G; d++) {
+      u64 *row = meta + (size_t)d * GAR_SHARD_META_WORDS;
+      for (int w = 0; w < GAR_SHARD_META_WORDS; w++) row[w] = 0;
+      for (int l = 0; l < L_NLEVELS; l++) {
+        row[l] = h_row_off[l][d + 1] - h_row_off[l][d];
+        row[L_NLEVELS + l] = h_slab_off[l][d + 1] - h_slab_off[l][d];
+      }
+      send_bytes[d] = blob_bytes(row);
+    }
+  }
+
+  // ---- round 1: route the slice
+  void route1(const DevTables &slice, const gar_shard &c, u64 *meta, u64 *send_bytes) {
+    cfg = c;
+    G = c.n_ranks;
+    S = slice;
+    delete slice_pipe;
+    slice_pipe = new Pipeline<B>(be, S);
+    slice_pipe->prepare_route();
+    const Work &W = slice_pipe->W;
+    const gar_objects &O = S.o;
+    const gar_actual &A = S.a;
+    plan_begin();
+    // sources
+    gar_str *okey = alloc<gar_str>(SH_ARENA_PLAN, O.n_objects);
+    u32 *ns_len = alloc<u32>(SH_ARENA_PLAN, O.n_objects);
+    if (O.n_objects) be.for_each("shard_obj_key", O.n_objects, FShObjKey{S, okey, ns_len});
+    u32 *lbi_obj = alloc<u32>(SH_ARENA_PLAN, O.n_lbi);
+    if (O.n_lbi) be.for_each("expand_lbi_obj", O.n_lbi, FExpand{O.obj_lbi_begin, O.n_objects, lbi_obj});
+    u32 *probe_home = alloc<u32>(SH_ARENA_PLAN, O.n_lbi);
+    u8 *val_dest = alloc<u8>(SH_ARENA_PLAN, A.n_values);
+    if (A.n_values) be.for_each("shard_val_dest", A.n_values, FShValDest{W, G, val_dest});
+
+    LevelSrc x{};
+    x = LevelSrc{}; x.str[0] = okey; x.str[1] = O.obj_ingress_class; x.u8c[0] = O.obj_kind; x.u8c[1] = O.obj_spec_type; x.u8c[2] = O.obj_flags;
+    x.u32c[0] = ns_len; x.gid_base = c.obj_base; x.child_begin[0] = O.obj_ann_begin; x.child_begin[1] = O.obj_lbi_begin; x.child_begin[2] = O.obj_port_begin;
+    x.slab = O.slab; x.n = O.n_objects; src[L_OBJ] = x;
+    x = LevelSrc{}; x.str[0] = O.ann_key; x.str[1] = O.ann_val; x.slab = O.slab; x.n = O.n_ann; src[L_ANN] = x;
+    x = LevelSrc{}; x.str[0] = O.lbi_hostname; x.slab = O.slab; x.n = O.n_lbi; src[L_LBI] = x;
+    x = LevelSrc{}; x.str[0] = O.port_proto; x.u32c[0] = (const u32 *)O.port_number; x.slab = O.slab; x.n = O.n_ports; src[L_PORT] = x;
+    x = LevelSrc{}; x.str[0] = A.acc_name; x.str[1] = A.acc_dns; x.u8c[0] = A.acc_enabled; x.gid_base = c.acc_base;
+    x.child_begin[0] = A.acc_tag_begin; x.child_begin[1] = A.acc_lis_begin; x.slab = A.slab; x.n = A.n_accels; src[L_ACC] = x;
+    x.child_begin[1] = nullptr; src[L_STUB] = x;
+    x = LevelSrc{}; x.str[0] = A.tag_key; x.str[1] = A.tag_val; x.slab = A.slab; x.n = A.n_tags; src[L_TAG] = x; src[L_STUBTAG] = x;
+    x = LevelSrc{}; x.u8c[0] = A.lis_proto; x.gid_base = c.lis_base; x.child_begin[0] = A.lis_pr_begin; x.child_begin[1] = A.lis_eg_begin;
+    x.slab = A.slab; x.n = A.n_listeners; src[L_LIS] = x;
+    x = LevelSrc{}; x.u32c[0] = (const u32 *)A.pr_from; x.slab = A.slab; x.n = A.n_port_ranges; src[L_PR] = x;
+    x = LevelSrc{}; x.gid_base = c.eg_base; x.child_begin[0] = A.eg_ep_begin; x.slab = A.slab; x.n = A.n_egs; src[L_EG] = x;
+    x = LevelSrc{}; x.str[0] = A.ep_id; x.slab = A.slab; x.n = A.n_endpoints; src[L_EP] = x;
+    x = LevelSrc{}; x.str[0] = A.rec_name; x.str[1] = A.rec_alias_dns; x.u8c[0] = A.rec_type; x.u8c[1] = A.rec_has_alias; x.u32c[0] = W.rec_zone;
+    x.gid_base = c.rec_base; x.child_begin[0] = A.rec_val_begin; x.child_dest[0] = val_dest; x.slab = A.slab; x.n = A.n_records; src[L_REC] = x;
+    x = LevelSrc{}; x.str[0] = A.val_value; x.gid_base = c.val_base; x.slab = A.slab; x.n = A.n_values; src[L_VAL] = x;
+    x = LevelSrc{}; x.str[0] = A.zone_name; x.slab = A.slab; x.n = A.n_zones; src[L_ZONE] = x;
+    x = LevelSrc{}; x.str[0] = A.lb_region; x.str[1] = A.lb_name; x.str[2] = A.lb_dns; x.str[3] = A.lb_arn; x.u8c[0] = A.lb_state; x.gid_base = c.lb_base;
+    x.slab = A.slab; x.n = A.n_lbs; src[L_LB] = x;
+    x = LevelSrc{}; x.str[0] = O.lbi_hostname; x.u32c[0] = probe_home; x.slab = O.slab; x.n = O.n_lbi; src[L_PROBE] = x;
+
+    // top-level selections
+    const DevTables Sl = S;
+    const u32 Gn = G;
+    top_single(L_OBJ, O.n_objects, [&](u32 *k, u32 *v) { return FShKeyObj{W, Gn, k, v}; });
+    top_single(L_ACC, A.n_accels, [&](u32 *k, u32 *v) { return FShKeyAcc{W, Gn, k, v}; });
+    top_single(L_LB, A.n_lbs, [&](u32 *k, u32 *v) { return FShKeyLb{Sl, Gn, k, v}; });
+    top_single(L_STUB, A.n_accels, [&](u32 *k, u32 *v) { return FShKeyStub{Sl, W, Gn, k, v}; });
+    top_single(L_PROBE, O.n_lbi, [&](u32 *k, u32 *v) { return FShKeyProbe{Sl, W, lbi_obj, Gn, k, v, probe_home}; });
+    {  // the zone table stays where it is: every rank already holds all of it (sharded-mode contract)
+      u32 nz = A.n_zones;
+      u32 *keys = alloc<u32>(SH_ARENA_PLAN, nz), *vals = alloc<u32>(SH_ARENA_PLAN, nz);
+      if (nz) be.for_each("shard_keys", nz, FShIota{keys, vals, c.rank});
+      set_top(L_ZONE, keys, vals, nz);
+    }
+    {  // records: (destination, record) pairs, sorted and de-duplicated
+      u32 nv = A.n_values;
+      u32 *counts = alloc<u32>(SH_ARENA_PLAN, (size_t)nv + 1);
+      be.fill32(counts, 0, (size_t)nv + 1);
+      if (nv) be.for_each("shard_rec_pairs_count", nv, FShRecPairs{S, W, val_dest, counts, nullptr, nullptr});
+      be.exclusive_scan(counts, nv + 1);
+      u32 np = 0;
+      be.download(&np, counts + nv, 4);
+      u32 *keys = alloc<u32>(SH_ARENA_PLAN, np), *vals = alloc<u32>(SH_ARENA_PLAN, np);
+      u32 *k2 = alloc<u32>(SH_ARENA_PLAN, np), *v2 = alloc<u32>(SH_ARENA_PLAN, np);
+      if (np) be.for_each("shard_rec_pairs_fill", nv, FShRecPairs{S, W, val_dest, counts, keys, vals});
+      sorted_unique_top(L_REC, keys, vals, k2, v2, np, A.n_records);
+    }
+    plan_finish(meta, send_bytes);
+  }
+  // (keys, vals) in any order -> sorted by (key, val), duplicates and SH_DROP removed -> top-level selection of level l
+  void sorted_unique_top(int l, u32 *keys, u32 *vals, u32 *k2, u32 *v2, u32 np, u32 val_range) {
+    if (np) {
+      // LSD: by row, then (stable) by destination.  sort_pairs orders by its first array.
+      be.sort_pairs(vals, keys, v2, k2, np, ilog2(next_pow2(val_range + 1)) + 1);
+      be.sort_pairs(keys, vals, k2, v2, np, 8);
+    }
+    u32 *flag = alloc<u32>(SH_ARENA_PLAN, (size_t)np + 1);
+    be.for_each("shard_unique_flag", np + 1, FShUniqueFlag{keys, vals, np, flag});
+    be.exclusive_scan(flag, np + 1);
+    if (np) be.for_each("shard_compact", np, FShCompact{keys, vals, flag, k2, v2});
+    u32 nu = 0;
+    be.download(&nu, flag + np, 4);
+    set_top(l, k2, v2, nu, true);
+  }
+
+  // ---- pack the current plan into `send` (n_ranks blobs back to back, sizes as reported by the route call)
+  void pack(u8 *send) {
+    u64 blob_base[SH_MAX_RANKS + 1] = {0};
+    u64 lvl_off[SH_MAX_RANKS] = {0};
+    for (u32 d = 0; d < G; d++) {
+      u64 row[GAR_SHARD_META_WORDS] = {0};
+      for (int l = 0; l < L_NLEVELS; l++) {
+        row[l] = h_row_off[l][d + 1] - h_row_off[l][d];
+        row[L_NLEVELS + l] = h_slab_off[l][d + 1] - h_slab_off[l][d];
+      }
+      blob_base[d + 1] = blob_base[d] + blob_bytes(row);
+    }
+    for (int l = 0; l < L_NLEVELS; l++) {
+      PackDst D{};
+      for (u32 d = 0; d < G; d++) {
+        u64 n = h_row_off[l][d + 1] - h_row_off[l][d], sb = h_slab_off[l][d + 1] - h_slab_off[l][d];
+        D.base[d] = send + blob_base[d];
+        D.lay[d] = level_layout(l, lvl_off[d], n, sb);
+        lvl_off[d] = D.lay[d].end;
+      }
+      u32 m = h_row_off[l][G];
+      if (!active[l] || !m) continue;
+      be.for_each("shard_pack_columns", m, FShPackCols{src[l], SH_SCHEMA[l], plan[l], G, D});
+      if (SH_SCHEMA[l].n_str && h_slab_off[l][G]) be.for_each("shard_pack_strings", m * 32, FShPackBytes{src[l], SH_SCHEMA[l].n_str, plan[l], G, D});
+    }
+  }
+
+  // ---- merge one level out of received blobs.  `from[s]` = (blob start, its meta row, level inside that blob).
+  struct Seg {
+    const u8 *blob;
+    const u64 *meta;
+    int lvl;
+  };
+  struct Merged {
+    u32 n = 0;
+    gar_str *str[SH_MAX_STR] = {};
+    u8 *u8c[SH_MAX_U8] = {};
+    u32 *u32c[SH_MAX_U32] = {};
+    u32 *gid = nullptr;
+    u32 *begin[SH_MAX_CHILD] = {};  // CSR begins (scanned), [n+1]
+  };
+  static LevelLayout layout_in_blob(const u64 *meta, int lvl) {
+    u64 p = 0;
+    LevelLayout L{};
+    for (int l = 0; l <= lvl; l++) {
+      L = level_layout(l, p, meta[l], meta[L_NLEVELS + l]);
+      p = L.end;
+    }
+    return L;
+  }
+  // slab: merged slab of the side this level's strings live in; *slab_used advances
+  Merged merge_level(int arena, int schema_lvl, const std::vector<Seg> &from, u8 *slab, u64 *slab_used) {
+    const LevelSchema &Sc = SH_SCHEMA[schema_lvl];
+    Merged M;
+    FShUnpackCols f{};
+    f.nseg = (int)from.size();
+    f.S = Sc;
+    u32 n = 0;
+    for (int s = 0; s < f.nseg; s++) {
+      const Seg &g = from[s];
+      f.seg[s].base = g.blob;
+      f.seg[s].lay = layout_in_blob(g.meta, g.lvl);
+      for (int c = 0; c < SH_MAX_CHILD; c++) f.has_cnt[s][c] = c < SH_SCHEMA[g.lvl].n_child;
+      f.seg_row[s] = n;
+      f.slab_base[s] = *slab_used;
+      u64 sb = g.meta[L_NLEVELS + g.lvl];
+      if (sb) be.copy_bytes(slab + *slab_used, g.blob + f.seg[s].lay.slab, sb);
+      *slab_used += sb;
+      n += (u32)g.meta[g.lvl];
+    }
+    f.seg_row[f.nseg] = n;
+    M.n = n;
+    for (int c = 0; c < Sc.n_str; c++) f.D.str[c] = M.str[c] = alloc<gar_str>(arena, n);
+    for (int c = 0; c < Sc.n_u8; c++) f.D.u8c[c] = M.u8c[c] = alloc<u8>(arena, n);
+    for (int c = 0; c < Sc.n_u32; c++) f.D.u32c[c] = M.u32c[c] = alloc<u32>(arena, n);
+    if (Sc.has_gid) f.D.gid = M.gid = alloc<u32>(arena, n);
+    for (int c = 0; c < Sc.n_child; c++) {
+      f.D.cnt[c] = M.begin[c] = alloc<u32>(arena, (size_t)n + 1);
+      be.fill32(M.begin[c] + n, 0, 1);
+    }
+    if (n && f.nseg) be.for_each("shard_unpack_columns", n, f);
+    for (int c = 0; c < Sc.n_child; c++) be.exclusive_scan(M.begin[c], n + 1);
+    return M;
+  }
+  u64 slab_total(const std::vector<std::vector<Seg>> &groups) {
+    u64 t = 0;
+    for (auto &g : groups)
+      for (auto &s : g) t += s.meta[L_NLEVELS + s.lvl];
+    return t;
+  }
+  std::vector<Seg> segs(const u8 *recv, const u64 (*meta)[GAR_SHARD_META_WORDS], int lvl) {
+    std::vector<Seg> v;
+    u64 off = 0;
+    for (u32 s = 0; s < G; s++) {
+      v.push_back(Seg{recv + off, meta[s], lvl});
+      off += blob_bytes(meta[s]);
+    }
+    return v;
+  }
+
+  // ---- after the round-1 exchange: build the directory tables (LBs, stubs, probes routed here)
+  void unpack1(const u8 *recv, const u64 *meta_in) {
+    recv1 = recv;
+    for (u32 s = 0; s < G; s++)
+      for (int w = 0; w < GAR_SHARD_META_WORDS; w++) meta1[s][w] = meta_in[(size_t)s * GAR_SHARD_META_WORDS + w];
+    be.shard_reset(SH_ARENA_DIR);
+    auto lb = segs(recv, meta1, L_LB), st = segs(recv, meta1, L_STUB), stt = segs(recv, meta1, L_STUBTAG), pr = segs(recv, meta1, L_PROBE);
+    u64 a_bytes = slab_total({lb, st, stt}), o_bytes = slab_total({pr});
+    u8 *aslab = alloc<u8>(SH_ARENA_DIR, a_bytes + GAR_SLAB_PAD), *oslab = alloc<u8>(SH_ARENA_DIR, o_bytes + GAR_SLAB_PAD);
+    be.fill32((u32 *)(aslab + (a_bytes & ~(u64)3)), 0, GAR_SLAB_PAD / 4);
+    be.fill32((u32 *)(oslab + (o_bytes & ~(u64)3)), 0, GAR_SLAB_PAD / 4);
+    u64 au = 0, ou = 0;
+    Merged mlb = merge_level(SH_ARENA_DIR, L_LB, lb, aslab, &au);
+    Merged mst = merge_level(SH_ARENA_DIR, L_STUB, st, aslab, &au);
+    Merged mtt = merge_level(SH_ARENA_DIR, L_STUBTAG, stt, aslab, &au);
+    Merged mpr = merge_level(SH_ARENA_DIR, L_PROBE, pr, oslab, &ou);
+    Dt = DevTables{};
+    Dt.cluster = S.cluster;
+    Dt.cluster_len = S.cluster_len;
+    gar_objects &O = Dt.o;
+    O.n_objects = 0;
+    u32 *zero3 = alloc<u32>(SH_ARENA_DIR, 4);
+    be.fill32(zero3, 0, 4);
+    O.obj_ann_begin = O.obj_lbi_begin = O.obj_port_begin = zero3;
+    O.n_lbi = mpr.n;
+    O.lbi_hostname = mpr.str[0];
+    O.slab = oslab;
+    O.slab_len = o_bytes;
+    gar_actual &A = Dt.a;
+    A.n_lbs = mlb.n;
+    A.lb_region = mlb.str[0]; A.lb_name = mlb.str[1]; A.lb_dns = mlb.str[2]; A.lb_arn = mlb.str[3]; A.lb_state = mlb.u8c[0];
+    A.n_accels = mst.n;
+    A.acc_name = mst.str[0]; A.acc_dns = mst.str[1]; A.acc_enabled = mst.u8c[0];
+    A.acc_tag_begin = mst.begin[0];
+    u32 *nolis = alloc<u32>(SH_ARENA_DIR, (size_t)mst.n + 1);
+    be.fill32(nolis, 0, (size_t)mst.n + 1);
+    A.acc_lis_begin = nolis;
+    A.n_tags = mtt.n;
+    A.tag_key = mtt.str[0]; A.tag_val = mtt.str[1];
+    A.lis_pr_begin = A.lis_eg_begin = A.eg_ep_begin = A.zone_rec_begin = A.rec_val_begin = zero3;
+    A.slab = aslab;
+    A.slab_len = a_bytes;
+    dir_home = mpr.u32c[0];
+    dir_lb_gid = mlb.gid;
+    dir_stub_gid = mst.gid;
+  }
+
+  // ---- round 2: resolve the probes, route the answers to their homes
+  void route2(u64 *meta, u64 *send_bytes) {
+    delete dir_pipe;
+    dir_pipe = new Pipeline<B>(be, Dt);
+    dir_pipe->force_radix = true;  // directory tables see every duplicate of a hot hostname: no bucket-size assumption
+    dir_pipe->prepare();
+    const Work &W = dir_pipe->W;
+    const gar_actual &A = Dt.a;
+    plan_begin();
+    LevelSrc x{};
+    x.str[0] = A.lb_region; x.str[1] = A.lb_name; x.str[2] = A.lb_dns; x.str[3] = A.lb_arn; x.u8c[0] = A.lb_state; x.gid = dir_lb_gid;
+    x.slab = A.slab; x.n = A.n_lbs; src[L_LB] = x;
+    x = LevelSrc{}; x.str[0] = A.acc_name; x.str[1] = A.acc_dns; x.u8c[0] = A.acc_enabled; x.gid = dir_stub_gid; x.child_begin[0] = A.acc_tag_begin;
+    x.slab = A.slab; x.n = A.n_accels; src[L_STUB] = x;
+    x = LevelSrc{}; x.str[0] = A.tag_key; x.str[1] = A.tag_val; x.slab = A.slab; x.n = A.n_tags; src[L_STUBTAG] = x;
+    u32 np = Dt.o.n_lbi;
+    u32 *lk = alloc<u32>(SH_ARENA_PLAN, np), *lv = alloc<u32>(SH_ARENA_PLAN, np), *lk2 = alloc<u32>(SH_ARENA_PLAN, np), *lv2 = alloc<u32>(SH_ARENA_PLAN, np);
+    u32 *sk = alloc<u32>(SH_ARENA_PLAN, 2 * (size_t)np), *sv = alloc<u32>(SH_ARENA_PLAN, 2 * (size_t)np);
+    u32 *sk2 = alloc<u32>(SH_ARENA_PLAN, 2 * (size_t)np), *sv2 = alloc<u32>(SH_ARENA_PLAN, 2 * (size_t)np);
+    if (np) be.for_each("shard_answer_probes", np, FShAnswer{Dt, W, dir_home, np, lk, lv, sk, sv});
+    sorted_unique_top(L_LB, lk, lv, lk2, lv2, np, A.n_lbs);
+    sorted_unique_top(L_STUB, sk, sv, sk2, sv2, 2 * np, A.n_accels);
+    plan_finish(meta, send_bytes);
+  }
+
+  // ---- after the round-2 exchange: assemble the home sub-snapshot
+  void unpack2(const u8 *recv2, const u64 *meta_in2) {
+    u64 meta2[SH_MAX_RANKS][GAR_SHARD_META_WORDS];
+    for (u32 s = 0; s < G; s++)
+      for (int w = 0; w < GAR_SHARD_META_WORDS; w++) meta2[s][w] = meta_in2[(size_t)s * GAR_SHARD_META_WORDS + w];
+    be.shard_reset(SH_ARENA_HOME);
+    auto r1 = [&](int l) { return segs(recv1, meta1, l); };
+    auto r2 = [&](int l) { return segs(recv2, meta2, l); };
+    auto cat = [](std::vector<Seg> a, const std::vector<Seg> &b) {
+      a.insert(a.end(), b.begin(), b.end());
+      return a;
+    };
+    std::vector<Seg> s_obj = r1(L_OBJ), s_ann = r1(L_ANN), s_lbi = r1(L_LBI), s_port = r1(L_PORT);
+    std::vector<Seg> s_acc = cat(r1(L_ACC), r2(L_STUB)), s_tag = cat(r1(L_TAG), r2(L_STUBTAG));
+    std::vector<Seg> s_lis = r1(L_LIS), s_pr = r1(L_PR), s_eg = r1(L_EG), s_ep = r1(L_EP), s_rec = r1(L_REC), s_val = r1(L_VAL), s_zone = r1(L_ZONE);
+    std::vector<Seg> s_lb = r2(L_LB);
+    u64 o_bytes = slab_total({s_obj, s_ann, s_lbi, s_port});
+    u64 a_bytes = slab_total({s_acc, s_tag, s_lis, s_pr, s_eg, s_ep, s_rec, s_val, s_zone, s_lb});
+    u8 *oslab = alloc<u8>(SH_ARENA_HOME, o_bytes + GAR_SLAB_PAD), *aslab = alloc<u8>(SH_ARENA_HOME, a_bytes + GAR_SLAB_PAD);
+    be.fill32((u32 *)(oslab + (o_bytes & ~(u64)3)), 0, GAR_SLAB_PAD / 4);
+    be.fill32((u32 *)(aslab + (a_bytes & ~(u64)3)), 0, GAR_SLAB_PAD / 4);
+    u64 ou = 0, au = 0;
+    const int AR = SH_ARENA_HOME;
+    Merged obj = merge_level(AR, L_OBJ, s_obj, oslab, &ou), ann = merge_level(AR, L_ANN, s_ann, oslab, &ou);
+    Merged lbi = merge_level(AR, L_LBI, s_lbi, oslab, &ou), port = merge_level(AR, L_PORT, s_port, oslab, &ou);
+    u32 n_own = 0;
+    for (u32 s = 0; s < G; s++) n_own += (u32)meta1[s][L_ACC];
+    Merged acc = merge_level(AR, L_ACC, s_acc, aslab, &au), tag = merge_level(AR, L_TAG, s_tag, aslab, &au);
+    Merged lis = merge_level(AR, L_LIS, s_lis, aslab, &au), pr = merge_level(AR, L_PR, s_pr, aslab, &au);
+    Merged eg = merge_level(AR, L_EG, s_eg, aslab, &au), ep = merge_level(AR, L_EP, s_ep, aslab, &au);
+    Merged rec = merge_level(AR, L_REC, s_rec, aslab, &au), val = merge_level(AR, L_VAL, s_val, aslab, &au);
+    Merged zone = merge_level(AR, L_ZONE, s_zone, aslab, &au), lb = merge_level(AR, L_LB, s_lb, aslab, &au);
+
+    H = DevTables{};
+    H.cluster = S.cluster;
+    H.cluster_len = S.cluster_len;
+    gar_objects &O = H.o;
+    O.n_objects = obj.n;
+    O.obj_kind = obj.u8c[0]; O.obj_spec_type = obj.u8c[1]; O.obj_flags = obj.u8c[2];
+    gar_str *ns = alloc<gar_str>(AR, obj.n), *nm = alloc<gar_str>(AR, obj.n);
+    if (obj.n) be.for_each("shard_obj_ns_name", obj.n, FShObjNsName{obj.str[0], obj.u32c[0], ns, nm});
+    O.obj_ns = ns; O.obj_name = nm; O.obj_ingress_class = obj.str[1];
+    O.obj_ann_begin = obj.begin[0]; O.obj_lbi_begin = obj.begin[1]; O.obj_port_begin = obj.begin[2];
+    O.n_ann = ann.n; O.ann_key = ann.str[0]; O.ann_val = ann.str[1];
+    O.n_lbi = lbi.n; O.lbi_hostname = lbi.str[0];
+    O.n_ports = port.n; O.port_number = (const i32 *)port.u32c[0]; O.port_proto = port.str[0];
+    O.slab = oslab; O.slab_len = o_bytes;
+    gar_actual &A = H.a;
+    A.n_lbs = lb.n; A.lb_region = lb.str[0]; A.lb_name = lb.str[1]; A.lb_dns = lb.str[2]; A.lb_arn = lb.str[3]; A.lb_state = lb.u8c[0];
+    A.n_accels = acc.n; A.acc_name = acc.str[0]; A.acc_dns = acc.str[1]; A.acc_enabled = acc.u8c[0];
+    A.acc_tag_begin = acc.begin[0]; A.acc_lis_begin = acc.begin[1];
+    A.n_tags = tag.n; A.tag_key = tag.str[0]; A.tag_val = tag.str[1];
+    A.n_listeners = lis.n; A.lis_proto = lis.u8c[0]; A.lis_pr_begin = lis.begin[0]; A.lis_eg_begin = lis.begin[1];
+    A.n_port_ranges = pr.n; A.pr_from = (const i32 *)pr.u32c[0];
+    A.n_egs = eg.n; A.eg_ep_begin = eg.begin[0];
+    A.n_endpoints = ep.n; A.ep_id = ep.str[0];
+    A.n_zones = zone.n; A.zone_name = zone.str[0];
+    u32 *zb = alloc<u32>(AR, (size_t)zone.n + 1);
+    be.fill32(zb, 0, (size_t)zone.n + 1);
+    if (rec.n) be.for_each("shard_zone_hist", rec.n, FShZoneHist{rec.u32c[0], zb});
+    be.exclusive_scan(zb, zone.n + 1);
+    A.zone_rec_begin = zb;
+    A.n_records = rec.n; A.rec_name = rec.str[0]; A.rec_alias_dns = rec.str[1]; A.rec_type = rec.u8c[0]; A.rec_has_alias = rec.u8c[1];
+    A.rec_val_begin = rec.begin[0];
+    A.n_values = val.n; A.val_value = val.str[0];
+    A.slab = aslab; A.slab_len = a_bytes;
+    gids = ShGids{obj.gid, lb.gid, acc.gid, lis.gid, eg.gid, rec.gid, val.gid};
+    guest_from = n_own;
+  }
+};

@@ -1,0 +1,153 @@
+"""Sharded mode: ONE cluster spread over several engines (include/garecon.h "sharded mode", csrc/gar_shard.h).
+
+The engine plans, packs and merges; moving the blobs between ranks is the host's job and lives here:
+
+  exchange_dist   one process per GPU, torch.distributed all_to_all_single (NCCL over NVLink on the GPU box, gloo in the
+                  CPU tests): one all-to-all of the meta rows + one of the blobs per round
+  exchange_local  every rank's engine in this process, buffers in host memory (the hostsim test tier)
+
+`merge_changesets` puts per-shard results back into the cluster-wide canonical order so they can be compared with the
+unsharded diff bit for bit.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import abi
+
+NONE = 0xFFFFFFFF
+
+
+# ------------------------------------------------------------------ slicing a dict model (tests, small cases)
+
+def slice_model(objects: list[dict], actual: dict, n_ranks: int):
+    """Cut a tables.pack() model into n_ranks slices the way a packer would: contiguous ranges of every list, whole
+    zones per rank, the zone table replicated.  -> [(objects_r, actual_r, GarShard)], rank order."""
+    def cuts(n):
+        return [n * r // n_ranks for r in range(n_ranks + 1)]
+
+    accs, lbs, zones = actual.get("accelerators", []), actual.get("lbs", []), actual.get("zones", [])
+    co, ca, cl, cz = cuts(len(objects)), cuts(len(accs)), cuts(len(lbs)), cuts(len(zones))
+    out = []
+    base = dict(obj=0, lb=0, acc=0, lis=0, eg=0, rec=0, val=0)
+    for r in range(n_ranks):
+        objs_r = objects[co[r]:co[r + 1]]
+        accs_r = accs[ca[r]:ca[r + 1]]
+        lbs_r = lbs[cl[r]:cl[r + 1]]
+        zones_r = [dict(z, records=(z.get("records", []) if cz[r] <= i < cz[r + 1] else [])) for i, z in enumerate(zones)]
+        sh = abi.GarShard(r, n_ranks, base["obj"], base["lb"], base["acc"], base["lis"], base["eg"], base["rec"], base["val"])
+        out.append((objs_r, dict(accelerators=accs_r, lbs=lbs_r, zones=zones_r), sh))
+        base["obj"] += len(objs_r)
+        base["lb"] += len(lbs_r)
+        base["acc"] += len(accs_r)
+        for a in accs_r:
+            base["lis"] += len(a.get("listeners", []))
+            base["eg"] += sum(len(li.get("egs", [])) for li in a.get("listeners", []))
+        for z in zones_r:
+            base["rec"] += len(z["records"])
+            base["val"] += sum(len(rec.get("values", [])) for rec in z["records"])
+    return out
+
+
+# ------------------------------------------------------------------ exchanges
+
+def exchange_local(engines, shards, keep, device="cpu"):
+    """Both rounds for engines that all live in this process: host-memory backends (device="cpu", the hostsim test tier) or
+    several engines on one GPU (device="cuda:0").  `keep` collects the buffers that must outlive the call (the engines
+    read the round-1 blobs again in round 2)."""
+    import torch
+    g = len(engines)
+    for rnd in (1, 2):
+        metas, sends = [], []
+        for e, sh in zip(engines, shards):
+            meta, nbytes = e.shard_route(sh, rnd)
+            buf = torch.zeros(int(nbytes.sum()) + 64, dtype=torch.uint8, device=device)
+            e.shard_pack(buf.data_ptr())
+            metas.append(meta)
+            sends.append((buf, np.concatenate([[0], np.cumsum(nbytes)]).astype(np.int64)))
+        for d, e in enumerate(engines):
+            recv_meta = np.stack([metas[s][d] for s in range(g)])
+            parts = [sends[s][0][int(sends[s][1][d]):int(sends[s][1][d + 1])] for s in range(g)]
+            recv = torch.cat(parts + [torch.zeros(64, dtype=torch.uint8, device=device)])
+            if str(device) != "cpu":
+                torch.cuda.synchronize()
+            keep.append(recv)
+            e.shard_unpack(rnd, recv.data_ptr(), recv_meta)
+
+
+class DistExchange:
+    """torch.distributed data path of one rank.  Buffers are torch uint8 tensors on `device` (cuda:N or cpu)."""
+
+    def __init__(self, engine, shard, device):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.e, self.shard, self.device = engine, shard, device
+        self.g = int(shard.n_ranks)
+        self.keep = []
+        self.bytes_sent = 0
+
+    def round(self, rnd: int):
+        torch, dist = self.torch, self.dist
+        meta, nbytes = self.e.shard_route(self.shard, rnd)
+        # meta rows: a fixed-size all-to-all (int64 view of the uint64 words)
+        m_out = torch.from_numpy(meta.view(np.int64)).to(self.device)
+        m_in = torch.empty_like(m_out)
+        dist.all_to_all_single(m_in, m_out)
+        recv_meta = m_in.cpu().numpy().view(np.uint64)
+        in_sizes = [int(x) for x in nbytes]
+        out_sizes = [self.e.blob_bytes(recv_meta[s]) for s in range(self.g)]
+        send = torch.empty(sum(in_sizes) + 64, dtype=torch.uint8, device=self.device)
+        self.e.shard_pack(send.data_ptr())
+        recv = torch.empty(sum(out_sizes) + 64, dtype=torch.uint8, device=self.device)
+        dist.all_to_all_single(recv[:sum(out_sizes)], send[:sum(in_sizes)], output_split_sizes=out_sizes, input_split_sizes=in_sizes)
+        if str(self.device) != "cpu":
+            torch.cuda.current_stream().synchronize()  # the engine reads `recv` on its own stream
+        self.keep.append(recv)
+        self.bytes_sent += sum(in_sizes)
+        self.e.shard_unpack(rnd, recv.data_ptr(), recv_meta)
+
+    def run(self):
+        """Both rounds; afterwards the engine holds this rank's home sub-snapshot (diff() works)."""
+        self.keep.clear()
+        self.bytes_sent = 0
+        self.round(1)
+        self.round(2)
+
+
+# ------------------------------------------------------------------ putting shard results back together
+
+_SECTION_KEY = {
+    0: lambda ops: (ops["obj"],),
+    1: lambda ops: (ops["a0"],),
+    2: lambda ops: (ops["obj"],),
+    3: lambda ops: (ops["a2"], ops["a1"], ops["sub"], ops["a0"]),  # np.lexsort: last key is the primary one
+}
+
+
+def merge_changesets(parts, n_objects: int):
+    """Per-shard ChangeSets (global rows, shard-local canonical order) -> cluster-wide statuses and ops in the canonical
+    order of include/garecon.h.  Returns dict(status_ga, status_r53, derived, ops, section_begin)."""
+    st_ga = np.zeros(n_objects, dtype=np.uint32)
+    st_r53 = np.zeros(n_objects, dtype=np.uint32)
+    derived = np.zeros(n_objects, dtype=np.uint32)
+    seen = np.zeros(n_objects, dtype=np.uint32)
+    for cs in parts:
+        g = cs.obj_gid
+        st_ga[g] = cs.status_ga
+        st_r53[g] = cs.status_r53
+        derived[g] = cs.derived
+        seen[g] += 1
+    if not np.all(seen == 1):
+        raise AssertionError("every object must be homed on exactly one shard")
+    sections, begins = [], [0]
+    for sec in range(4):
+        chunks = [cs.ops[int(cs.section_begin[sec]):int(cs.section_begin[sec + 1])] for cs in parts]
+        ops = np.concatenate(chunks) if chunks else np.zeros(0, dtype=abi.OP_DTYPE)
+        if len(ops):
+            order = np.lexsort(_SECTION_KEY[sec](ops)) if sec == 3 else np.argsort(_SECTION_KEY[sec](ops)[0], kind="stable")
+            ops = ops[order]
+        sections.append(ops)
+        begins.append(begins[-1] + len(ops))
+    return dict(status_ga=st_ga, status_r53=st_r53, derived=derived, ops=np.concatenate(sections) if sections else np.zeros(0, dtype=abi.OP_DTYPE),
+                section_begin=np.array(begins, dtype=np.uint64))

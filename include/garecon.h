@@ -297,6 +297,8 @@ typedef struct gar_changeset {
   const uint32_t *dport_begin; /* [n_objects+1] */
   uint64_t n_dports;
   const int32_t *dports;       /* [n_dports] */
+  /* sharded mode only (NULL otherwise): global object row of each local object row; ops then carry global rows */
+  const uint32_t *obj_gid;     /* [n_objects] */
   /* timings of this diff, CUDA events on the engine's stream */
   float ms_h2d;                /* snapshot upload (measured at gar_snapshot_load) */
   float ms_kernels;            /* first kernel .. last kernel */
@@ -398,6 +400,42 @@ enum { GAR_D_REF_NOT_FOUND = 12, GAR_D_EG_NOT_FOUND = 13 };
 /* Result: n_objects = n_bindings, status_ga[] holds the binding statuses, ops the EGB ops in binding order (one section);
    status_r53 / derived / tok_* / dports are not produced. */
 int gar_bindings_diff(gar_engine *e, const gar_bindings *bindings, gar_changeset *out);
+
+/* ---------------------------------------------------------------- sharded mode (SURVEY.md §8 row e, BASELINE configs[3])
+
+   ONE cluster too large (or too slow) for one GPU, spread over n_ranks engines (one process per GPU).  Every rank loads
+   (gar_snapshot_load) a SLICE: contiguous ranges of the object list and of each AWS list, in rank order (rank r holds
+   global rows [base_r, base_r + n_r) of every table; nested rows travel with their parent), with these two rules:
+     - the zone table (zone_name, zone_rec_begin) is complete and identical on every rank; a rank holds the record sets of
+       whole zones only (other zones have empty record ranges), zone ranges ascending with the rank;
+     - *_base give the global row of the slice's first row of each table.
+   Rows are then re-homed by key hash on the device in two exchanges the HOST performs between the calls below (the data
+   path is torch.distributed all_to_all_single over NCCL in ranks.py, or any all-to-all):
+
+     for round in 1, 2:
+       gar_shard_route(e, &shard, round, meta, send_bytes)    meta[n_ranks][GAR_SHARD_META_WORDS]: row r describes the
+                                                              blob for rank r; send_bytes[r] its size (multiple of 16)
+       exchange the meta rows (all-to-all of GAR_SHARD_META_WORDS u64 per peer)
+       gar_shard_pack(e, send)                                send: device buffer of sum(send_bytes), blobs back to back
+       exchange the blobs (all-to-all, sizes from gar_shard_blob_bytes(received meta row))
+       gar_shard_unpack(e, round, recv, recv_meta)            recv: the received blobs back to back, in rank order;
+                                                              the round-1 buffer must stay alive until round 2 is unpacked
+   Round 1 moves every row to the shard its own key hashes to and one probe per lbIngress hostname to the "directory"
+   shard of that hostname; round 2 returns the load balancer / by-hostname accelerators each probe resolves to.  After the
+   second unpack the engine holds a self-contained sub-snapshot: gar_diff / gar_diff_device work as usual, n_objects is
+   the number of objects homed here, obj_gid[] gives their global rows, ops carry GLOBAL rows and keep the canonical order
+   within the shard (merge shards by (section, key row) for the cluster-wide order).  Stands for nothing in the reference
+   (it has one process and no batch); semantics = gar_diff over the concatenated slices, which the tests check bit for bit. */
+#define GAR_SHARD_MAX_RANKS 8
+#define GAR_SHARD_META_WORDS 40
+typedef struct gar_shard {
+  uint32_t rank, n_ranks;
+  uint32_t obj_base, lb_base, acc_base, lis_base, eg_base, rec_base, val_base;
+} gar_shard;
+int gar_shard_route(gar_engine *e, const gar_shard *shard, int round, uint64_t *meta, uint64_t *send_bytes);
+int gar_shard_pack(gar_engine *e, void *send);
+int gar_shard_unpack(gar_engine *e, int round, const void *recv, const uint64_t *recv_meta);
+uint64_t gar_shard_blob_bytes(const uint64_t *meta_row);
 
 void gar_changeset_free(gar_engine *e, gar_changeset *cs);
 

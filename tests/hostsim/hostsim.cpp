@@ -14,6 +14,7 @@
 #include <thread>
 
 #include "../../aws-global-accelerator-controller_b200/csrc/gar_pipeline.h"
+#include "../../aws-global-accelerator-controller_b200/csrc/gar_shard.h"
 
 // ---- warp emulation: for_each_warp runs every group of 32 lanes on 32 host threads; GAR_ANY is a barrier vote.
 // A vote that not all 32 lanes reach (a lane finished, or never arrives) would hang the real GPU: here it is
@@ -82,6 +83,18 @@ struct gar_engine {
   HBuf slot[S_NSLOTS];
   HBuf o_status_ga, o_status_r53, o_derived, o_ops, o_tok_code, o_tok_name, o_tok_region, o_dport_begin, o_dports, o_derived_keys;
   Pipeline<gar_engine> *pipe = nullptr;
+  Sharder<gar_engine> *sharder = nullptr;
+  DevTables slice{};
+  bool shard_home = false;
+  int shard_round = 0;
+  std::vector<HBuf> arena[3];
+  size_t arena_used[3] = {0, 0, 0};
+  void *shard_alloc(int a, size_t bytes) {
+    if (arena_used[a] >= arena[a].size()) arena[a].emplace_back();
+    return arena[a][arena_used[a]++].ensure(bytes + 32);
+  }
+  void shard_reset(int a) { arena_used[a] = 0; }
+  void copy_bytes(void *dst, const void *src, size_t n) { memcpy(dst, src, n); }
   std::vector<u8> del_slab, del_kind;
   std::vector<gar_str> del_key;
   std::vector<u32> key_rows;
@@ -175,6 +188,9 @@ int gar_snapshot_load(gar_engine *e, const gar_objects *o, const gar_actual *a) 
   e->loaded = true;
   delete e->pipe;
   e->pipe = nullptr;
+  e->slice = e->T;
+  e->shard_home = false;
+  e->shard_round = 0;
   return GAR_OK;
 }
 int gar_snapshot_attach_device(gar_engine *e, const gar_objects *o, const gar_actual *a) { return gar_snapshot_load(e, o, a); }
@@ -182,7 +198,13 @@ int gar_snapshot_attach_device(gar_engine *e, const gar_objects *o, const gar_ac
 static int diff_impl(gar_engine *e, gar_changeset *out, const gar_keyset *ks, const gar_bindings *bd = nullptr) {
   memset(out, 0, sizeof(*out));
   e->launches = 0;
-  if (!e->pipe) e->pipe = new Pipeline<gar_engine>(*e, e->T);
+  if (!e->pipe) {
+    e->pipe = new Pipeline<gar_engine>(*e, e->T);
+    if (e->shard_home) {
+      e->pipe->acc_guest_from = e->sharder->guest_from;
+      e->pipe->sharded = 1;
+    }
+  }
   Pipeline<gar_engine> &P = *e->pipe;
   DiffCounts dc{};
   g_vote_outside_warp = g_nonuniform_vote = false;
@@ -215,6 +237,7 @@ static int diff_impl(gar_engine *e, gar_changeset *out, const gar_keyset *ks, co
     e->del_slab.resize(e->del_slab.size() + 64, 0);
     rc = P.run_keys(e->key_rows.data(), ks->n_rows, DelKeys{e->del_kind.data(), e->del_key.data(), e->del_slab.data()}, ks->n_deleted, &dc, ops_alloc);
   }
+  if (rc == GAR_OK && e->shard_home && dc.n_ops) e->for_each("shard_translate_ops", (u32)dc.n_ops, FShTranslateOps{(gar_op *)e->o_ops.mem.data(), e->sharder->gids});
   if (g_nonuniform_vote || g_vote_outside_warp) {
     e->err = g_nonuniform_vote ? "non-uniform warp vote: some lane did not reach a GAR_ANY that others executed (would hang on the GPU)"
                                : "GAR_ANY executed outside a warp-synchronous kernel";
@@ -239,12 +262,46 @@ static int diff_impl(gar_engine *e, gar_changeset *out, const gar_keyset *ks, co
   out->n_dports = dc.n_dports;
   out->dports = (const i32 *)e->o_dports.mem.data();
   out->kernel_launches = e->launches;
+  out->obj_gid = e->shard_home ? e->sharder->gids.obj : nullptr;
   return GAR_OK;
 }
 int gar_diff(gar_engine *e, gar_changeset *out) { return diff_impl(e, out, nullptr); }
 int gar_diff_keys(gar_engine *e, const gar_keyset *ks, gar_changeset *out) { return diff_impl(e, out, ks); }
 int gar_bindings_diff(gar_engine *e, const gar_bindings *bd, gar_changeset *out) { return diff_impl(e, out, nullptr, bd); }
 int gar_diff_device(gar_engine *e, gar_changeset *out) { return gar_diff(e, out); }
+int gar_shard_route(gar_engine *e, const gar_shard *shard, int round, uint64_t *meta, uint64_t *send_bytes) {
+  if (!e->sharder) e->sharder = new Sharder<gar_engine>(*e);
+  if (round == 1) {
+    e->sharder->route1(e->slice, *shard, meta, send_bytes);
+    e->shard_round = 1;
+  } else {
+    if (e->shard_round != 2) return GAR_E_STATE;
+    e->sharder->route2(meta, send_bytes);
+    e->shard_round = 3;
+  }
+  return GAR_OK;
+}
+int gar_shard_pack(gar_engine *e, void *send) {
+  e->sharder->pack((u8 *)send);
+  return GAR_OK;
+}
+int gar_shard_unpack(gar_engine *e, int round, const void *recv, const uint64_t *recv_meta) {
+  if (round == 1 && e->shard_round == 1) {
+    e->sharder->unpack1((const u8 *)recv, recv_meta);
+    e->shard_round = 2;
+  } else if (round == 2 && e->shard_round == 3) {
+    e->sharder->unpack2((const u8 *)recv, recv_meta);
+    delete e->pipe;
+    e->pipe = nullptr;
+    e->T = e->sharder->H;
+    e->shard_home = true;
+    e->shard_round = 4;
+  } else {
+    return GAR_E_STATE;
+  }
+  return GAR_OK;
+}
+uint64_t gar_shard_blob_bytes(const uint64_t *meta_row) { return blob_bytes(meta_row); }
 void gar_changeset_free(gar_engine *, gar_changeset *cs) { memset(cs, 0, sizeof(*cs)); }
 const char *gar_last_error(const gar_engine *e) { return e ? e->err.c_str() : g_err.c_str(); }
 const char *gar_version(void) { return "garecon hostsim (test build)"; }
