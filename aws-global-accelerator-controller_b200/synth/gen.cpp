@@ -165,14 +165,15 @@ struct Gen {
 
   ObjSpec spec(uint32_t i) const {
     ObjSpec s;
-    s.i = i;
-    Rng r(mix(c.seed, i));
+    const uint32_t gi = c.index_base + i;  // cluster-wide index: names and random streams depend on it, not on the chunk
+    s.i = gi;
+    Rng r(mix(c.seed, gi));
     s.r = r.next();
     s.ingress = r.uni() < c.frac_ingress;
     s.eligible = r.uni() >= c.frac_ineligible;
     s.managed = r.uni() >= c.frac_unmanaged;
     s.ns = "team-" + num(r.below(50), 2);
-    s.name = (s.ingress ? "ing-" : "svc-") + num(i, 7);
+    s.name = (s.ingress ? "ing-" : "svc-") + num(gi, 7);
     s.region = kRegions[r.below(8)];
     s.internal_alb = s.ingress && r.uni() < 0.3;
     uint64_t h1 = r.next(), h2 = r.next();
@@ -229,7 +230,8 @@ struct Gen {
     bool hot;
     int fate;  // 0 in sync, 1 missing, 2 alias drift
   };
-  std::string zone_name(uint32_t z) const { return "z" + num(z, 4) + ".example" + num(z % 7) + ".com"; }
+  // z = zone row of THIS chunk; the name carries the cluster-wide zone row
+  std::string zone_name(uint32_t z) const { return "z" + num(c.zone_base + z, 4) + ".example" + num((c.zone_base + z) % 7) + ".com"; }
   Host host(const ObjSpec &s, uint32_t k) const {
     Rng r(mix(s.r, 1000 + k));
     Host h;
@@ -453,12 +455,12 @@ Snapshot *generate(const gsyn_config &cfg) {
             break;
           default: break;
         }
-        add_accel(S, G, uuid(mix(s.r, 41)), name, G.acc_dns(i), enabled, s.owner, thost, cfg.cluster, ut, n_lis, ports, lis_udp, n_eg, endpoint);
+        add_accel(S, G, uuid(mix(s.r, 41)), name, G.acc_dns(cfg.index_base + i), enabled, s.owner, thost, cfg.cluster, ut, n_lis, ports, lis_udp, n_eg, endpoint);
       }
       if (rr.uni() < cfg.p_orphan_acc) {  // accelerator whose owner left the cache
         std::string okind = rr.uni() < 0.5 ? "service" : "ingress";
-        std::string gone = okind + "/team-" + num(rr.below(50), 2) + "/gone-" + num(i, 7);
-        add_accel(S, G, uuid(mix(s.r, 43)), okind + "-gone-" + num(i, 7), "a" + hexs(mix(s.r, 44), 16) + ".awsglobalaccelerator.com", true, gone,
+        std::string gone = okind + "/team-" + num(rr.below(50), 2) + "/gone-" + num(cfg.index_base + i, 7);
+        add_accel(S, G, uuid(mix(s.r, 43)), okind + "-gone-" + num(cfg.index_base + i, 7), "a" + hexs(mix(s.r, 44), 16) + ".awsglobalaccelerator.com", true, gone,
                   "gone-" + hexs(s.r, 16) + ".elb.us-east-1.amazonaws.com", rr.uni() < 0.9 ? cfg.cluster : "other-cluster", {}, 1, {80, 443}, false, 1,
                   "arn:aws:elasticloadbalancing:us-east-1:123456789012:loadbalancer/net/gone/" + hexs(s.r, 16));
       }
@@ -489,7 +491,7 @@ Snapshot *generate(const gsyn_config &cfg) {
       const ObjSpec &s = specs[i];
       if (!s.eligible && !s.ingress) continue;
       std::string ov = G.owner_value(s);
-      std::string adns = G.acc_dns(i) + ".";
+      std::string adns = G.acc_dns(cfg.index_base + i) + ".";
       for (uint32_t k = 0; k < s.n_host; k++) {
         Gen::Host h = G.host(s, k);
         if (h.fate == 1) continue;
@@ -510,22 +512,31 @@ Snapshot *generate(const gsyn_config &cfg) {
       if (rr.uni() < cfg.p_orphan_rec) {  // records of an owner that left the cache
         uint32_t z = rr.below(nz);
         std::string okind = rr.uni() < 0.5 ? "service" : "ingress";
-        std::string nm = "gone" + num(i, 7) + "." + G.zone_name(z) + ".";
+        std::string nm = "gone" + num(cfg.index_base + i, 7) + "." + G.zone_name(z) + ".";
         std::string gv = "\"heritage=aws-global-accelerator-controller,cluster=" + std::string(rr.uni() < 0.9 ? cfg.cluster : "other") + "," + okind + "/team-" +
-                         num(rr.below(50), 2) + "/gone-" + num(i, 7) + "\"";
+                         num(rr.below(50), 2) + "/gone-" + num(cfg.index_base + i, 7) + "\"";
         zr[z].push_back({nm, GAR_RR_TXT, false, "", {gv}});
         zr[z].push_back({nm, GAR_RR_A, true, "a" + hexs(mix(s.r, 58), 16) + ".awsglobalaccelerator.com.", {}});
       }
       if (rr.uni() < 0.05) {  // unrelated records
         uint32_t z = rr.below(nz);
-        zr[z].push_back({"www" + num(i, 7) + "." + G.zone_name(z) + ".", GAR_RR_CNAME, false, "", {"target." + G.zone_name(z) + "."}});
+        zr[z].push_back({"www" + num(cfg.index_base + i, 7) + "." + G.zone_name(z) + ".", GAR_RR_CNAME, false, "", {"target." + G.zone_name(z) + "."}});
       }
     }
     S.rec_b.push_back(0);
     S.val_b.push_back(0);
-    for (uint32_t z = 0; z < nz; z++) {
+    // sharded clusters (zones_total > 0): the zone table is the cluster-wide one on every chunk, record sets only under
+    // this chunk's zones [zone_base, zone_base + n_zones)
+    const uint32_t zt = cfg.zones_total ? cfg.zones_total : nz, zb = cfg.zones_total ? cfg.zone_base : 0;
+    for (uint32_t gz = 0; gz < zt; gz++) {
+      const bool mine = gz >= zb && gz < zb + nz;
+      const uint32_t z = mine ? gz - zb : 0;
       S.zone_id.push_back(0);
-      S.zone_name.push_back(S.as.put(G.zone_name(z) + "."));
+      S.zone_name.push_back(S.as.put("z" + num(gz, 4) + ".example" + num(gz % 7) + ".com."));
+      if (!mine) {
+        S.rec_b.push_back((uint32_t)S.rec_name.size());
+        continue;
+      }
       for (auto &rc : zr[z]) {
         S.rec_name.push_back(S.as.put(rc.name));
         S.rec_type.push_back(rc.type);

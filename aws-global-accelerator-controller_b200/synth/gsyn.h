@@ -25,6 +25,10 @@ typedef struct gsyn_config {
   float p_dup_ports;
   uint32_t intern_keys; /* 1: annotation keys and tag keys are stored once in the slab and referenced by every row (what a
                            packer with a small map[string]ref does); 0: every row carries its own copy */
+  /* chunk of a larger cluster (sharded mode): names and random streams use the cluster-wide object index index_base + i and
+     zone row zone_base + z; with zones_total > 0 the zone table has zones_total rows (identical on every chunk) and record
+     sets only under this chunk's n_zones zones */
+  uint32_t index_base, zone_base, zones_total;
   char cluster[64];
 } gsyn_config;
 typedef struct gsyn_snapshot gsyn_snapshot;

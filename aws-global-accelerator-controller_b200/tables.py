@@ -289,3 +289,139 @@ def pack_bindings(bindings: list[dict], known_egs: list[str]) -> Bindings:
     b.slab = _ptr(slab, C.c_uint8)
     b.slab_len = len(sl.buf)
     return out
+
+
+# ------------------------------------------------------------------ numpy-level table tools (sharded mode: building slices
+# out of generator chunks, and the union of slices for parity checks)
+
+# table -> (row-count field, [(column, kind)]) with kind: "str" (gar_str, refs into the side's slab), "u8", "i32",
+# ("csr", child table) = begin array of n+1 entries into the child table
+OBJ_TABLES = {
+    "obj": ("n_objects", [("obj_kind", "u8"), ("obj_spec_type", "u8"), ("obj_flags", "u8"), ("obj_ns", "str"), ("obj_name", "str"), ("obj_ingress_class", "str"),
+                          ("obj_ann_begin", ("csr", "ann")), ("obj_lbi_begin", ("csr", "lbi")), ("obj_port_begin", ("csr", "port"))]),
+    "ann": ("n_ann", [("ann_key", "str"), ("ann_val", "str")]),
+    "lbi": ("n_lbi", [("lbi_hostname", "str")]),
+    "port": ("n_ports", [("port_number", "i32"), ("port_proto", "str")]),
+}
+ACT_TABLES = {
+    "lb": ("n_lbs", [("lb_region", "str"), ("lb_name", "str"), ("lb_dns", "str"), ("lb_arn", "str"), ("lb_state", "u8")]),
+    "acc": ("n_accels", [("acc_name", "str"), ("acc_dns", "str"), ("acc_enabled", "u8"), ("acc_tag_begin", ("csr", "tag")), ("acc_lis_begin", ("csr", "lis"))]),
+    "tag": ("n_tags", [("tag_key", "str"), ("tag_val", "str")]),
+    "lis": ("n_listeners", [("lis_proto", "u8"), ("lis_pr_begin", ("csr", "pr")), ("lis_eg_begin", ("csr", "eg"))]),
+    "pr": ("n_port_ranges", [("pr_from", "i32")]),
+    "eg": ("n_egs", [("eg_ep_begin", ("csr", "ep"))]),
+    "ep": ("n_endpoints", [("ep_id", "str")]),
+    "zone": ("n_zones", [("zone_name", "str"), ("zone_rec_begin", ("csr", "rec"))]),
+    "rec": ("n_records", [("rec_name", "str"), ("rec_type", "u8"), ("rec_has_alias", "u8"), ("rec_alias_dns", "str"), ("rec_val_begin", ("csr", "val"))]),
+    "val": ("n_values", [("val_value", "str")]),
+}
+_DT = {"u8": np.uint8, "i32": np.int32, "str": np.uint64}
+_CT = {"u8": C.c_uint8, "i32": C.c_int32, "str": C.c_uint64}
+ACC_FAMILY = ("acc", "tag", "lis", "pr", "eg", "ep")
+REC_FAMILY = ("zone", "rec", "val")
+
+
+def _view(ptr, n, dtype):
+    n = int(n)
+    if n == 0 or not ptr:
+        return np.zeros(0, dtype=dtype)
+    return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(n * np.dtype(dtype).itemsize,)).view(dtype)
+
+
+def columns(struct, tables) -> dict:
+    """Zero-copy numpy views of every column of a GarObjects / GarActual (plus "slab"); keep the owner alive."""
+    cols = {}
+    for t, (nf, cl) in tables.items():
+        n = getattr(struct, nf)
+        for name, kind in cl:
+            if isinstance(kind, tuple):
+                cols[name] = _view(getattr(struct, name), n + 1, np.uint32)
+            else:
+                cols[name] = _view(getattr(struct, name), n, _DT[kind])
+    cols["slab"] = _view(struct.slab, struct.slab_len, np.uint8)
+    return cols
+
+
+def _rebase(refs: np.ndarray, delta: int) -> np.ndarray:
+    return refs + np.uint64(delta)  # the offset lives in the low bits of a gar_str
+
+
+def from_columns(o_cols: dict, a_cols: dict) -> Snapshot:
+    """Snapshot (owning copies) from column dicts as returned by columns()."""
+    snap = Snapshot()
+    for struct, cols, tables, pre in ((snap.objects, o_cols, OBJ_TABLES, "o."), (snap.actual, a_cols, ACT_TABLES, "a.")):
+        for t, (nf, cl) in tables.items():
+            n = None
+            for name, kind in cl:
+                if isinstance(kind, tuple):
+                    arr = np.asarray(cols[name], dtype=np.uint32)
+                    n = len(arr) - 1
+                    snap._set(struct, name, arr, np.uint32, C.c_uint32)
+                else:
+                    arr = np.asarray(cols[name], dtype=_DT[kind])
+                    n = len(arr)
+                    snap._set(struct, name, arr, _DT[kind], _CT[kind])
+            setattr(struct, nf, int(n))
+        slab = np.concatenate([np.asarray(cols["slab"], dtype=np.uint8), np.zeros(64, dtype=np.uint8)])
+        snap.arrays[pre + "slab"] = slab
+        struct.slab = _ptr(slab, C.c_uint8)
+        struct.slab_len = len(slab) - 64
+    return snap
+
+
+def take_families(parts: dict) -> dict:
+    """Actual-side columns assembled from different sources: parts = {family tables tuple: a_cols of the source}.  Slabs are
+    concatenated and the string references of each family rebased."""
+    out, slabs, base = {}, [], 0
+    for fam, cols in parts.items():
+        for t in fam:
+            for name, kind in ACT_TABLES[t][1]:
+                out[name] = _rebase(cols[name], base) if kind == "str" else cols[name]
+        slabs.append(cols["slab"])
+        base += len(cols["slab"])
+    out["slab"] = np.concatenate(slabs) if slabs else np.zeros(0, dtype=np.uint8)
+    return out
+
+
+def concat_slices(slices) -> Snapshot:
+    """The cluster a list of sharded-mode slices [(o_cols, a_cols), ...] (rank order) stands for: every list concatenated in
+    rank order, the replicated zone table taken once."""
+    def cat(side, tables, skip_zone):
+        out, slab_base = {}, np.concatenate([[0], np.cumsum([len(s[side]["slab"]) for s in slices])]).astype(np.int64)
+        for t, (nf, cl) in tables.items():
+            for name, kind in cl:
+                if isinstance(kind, tuple):
+                    child_first = ACT_TABLES.get(kind[1], OBJ_TABLES.get(kind[1]))[1][0][0]
+                    if t == "zone":  # same zones on every slice, disjoint record ranges: begins add up
+                        out[name] = np.sum([s[side][name].astype(np.int64) for s in slices], axis=0).astype(np.uint32)
+                        continue
+                    begins, off = [np.zeros(1, dtype=np.int64)], 0
+                    for s in slices:
+                        b = s[side][name].astype(np.int64)
+                        begins.append(b[1:] + off)
+                        off += int(b[-1])
+                    out[name] = np.concatenate(begins).astype(np.uint32)
+                elif t == "zone":
+                    out[name] = _rebase(slices[0][side][name], 0)
+                else:
+                    arrs = [(_rebase(s[side][name], int(slab_base[k])) if kind == "str" else s[side][name]) for k, s in enumerate(slices)]
+                    out[name] = np.concatenate(arrs) if arrs else np.zeros(0, dtype=_DT[kind])
+        out["slab"] = np.concatenate([s[side]["slab"] for s in slices]) if slices else np.zeros(0, dtype=np.uint8)
+        return out
+    return from_columns(cat(0, OBJ_TABLES, False), cat(1, ACT_TABLES, True))
+
+
+def shard_bases(slices) -> list:
+    """GarShard (rank, n_ranks, global row of every table's first row) for each slice [(o_cols, a_cols), ...]."""
+    out, g = [], len(slices)
+    base = dict(obj=0, lb=0, acc=0, lis=0, eg=0, rec=0, val=0)
+    for r, (o, a) in enumerate(slices):
+        out.append(abi.GarShard(r, g, base["obj"], base["lb"], base["acc"], base["lis"], base["eg"], base["rec"], base["val"]))
+        base["obj"] += len(o["obj_kind"])
+        base["lb"] += len(a["lb_state"])
+        base["acc"] += len(a["acc_enabled"])
+        base["lis"] += len(a["lis_proto"])
+        base["eg"] += len(a["eg_ep_begin"]) - 1
+        base["rec"] += len(a["rec_type"])
+        base["val"] += len(a["val_value"])
+    return out

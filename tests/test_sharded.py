@@ -95,3 +95,158 @@ def test_shards_are_balanced_and_disjoint(garecon, oracle, hostlib):
     got, parts = check(garecon, oracle, hostlib, objects, actual, 4)
     sizes = [p.n_objects for p in parts]
     assert sum(sizes) == 400 and min(sizes) > 50
+
+
+# ------------------------------------------------------------------ generator slices (the bench workload of configs[3])
+
+def run_sharded_slices(garecon, lib, slices, device="cpu", **engine_kw):
+    tables = garecon.tables
+    bases = tables.shard_bases(slices)
+    engines, keep = [], []
+    for o, a in slices:
+        e = garecon.Engine(cluster_name="default", lib=lib, **engine_kw)
+        snap = tables.from_columns(o, a)
+        e.load(snap)
+        engines.append(e)
+        keep.append(snap)  # hostsim reads the columns in place
+    shard.exchange_local(engines, bases, keep, device=device)
+    parts = [e.diff() for e in engines]
+    for e in engines:
+        e.close()
+    return parts
+
+
+def check_slices(garecon, want, parts, n_total):
+    got = shard.merge_changesets(parts, n_total)
+    assert np.array_equal(got["status_ga"], want.status_ga)
+    assert np.array_equal(got["status_r53"], want.status_r53)
+    assert np.array_equal(got["derived"], want.derived)
+    assert got["section_begin"].tolist() == want.section_begin.tolist()
+    assert np.array_equal(got["ops"], want.ops), first_diff(got["ops"].tolist(), want.ops.tolist())
+
+
+@pytest.mark.parametrize("cfg,n_total,n_ranks", [(4, 1500, 3), (5, 1200, 4), (3, 1000, 2)])
+def test_generator_slices_on_hostsim(garecon, oracle, hostlib, cfg, n_total, n_ranks):
+    """Chunked generator output (objects / accelerators / LBs of different chunks on one rank) == the union, via the oracle."""
+    synth = importlib.import_module("aws-global-accelerator-controller_b200.synth")
+    slices = synth.cluster_slices(cfg, n_total, n_ranks)
+    union = garecon.tables.concat_slices(slices)
+    assert union.objects.n_objects == n_total
+    want = oracle.diff(union, "default", mode=1)
+    parts = run_sharded_slices(garecon, hostlib, slices)
+    check_slices(garecon, want, parts, n_total)
+    assert len(want.ops) > n_total // 4
+
+
+# ------------------------------------------------------------------ the torch.distributed data path, 2 processes on gloo
+
+GLOO_WORKER = r'''
+import importlib, json, sys
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import numpy as np, torch.distributed as dist
+import __graft_entry__ as ge
+import randmodel
+garecon = importlib.import_module("aws-global-accelerator-controller_b200")
+shard = importlib.import_module("aws-global-accelerator-controller_b200.shard")
+ob = importlib.import_module("oracle.binding")
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+lib = garecon.abi.load_library(ge.build_hostsim())
+objects, actual = randmodel.make(21, n_objects=120)
+objs_r, act_r, sh = shard.slice_model(objects, actual, world)[rank]
+e = garecon.Engine(cluster_name="default", lib=lib)
+snap = garecon.pack(objs_r, act_r)   # hostsim reads the columns in place: keep them alive
+e.load(snap)
+x = shard.DistExchange(e, sh, "cpu")
+x.run()
+part = e.diff()
+payload = dict(obj_gid=part.obj_gid, status_ga=part.status_ga, status_r53=part.status_r53, derived=part.derived, ops=part.ops,
+               section_begin=part.section_begin, sent=x.bytes_sent)
+gathered = [None] * world if rank == 0 else None
+dist.gather_object(payload, gathered, dst=0)
+if rank == 0:
+    class P: pass
+    parts = []
+    for g in gathered:
+        p = P(); p.__dict__.update(g); parts.append(p)
+    got = shard.merge_changesets(parts, len(objects))
+    want = ob.diff(garecon.pack(objects, actual), "default", mode=1)
+    ok = (np.array_equal(got["status_ga"], want.status_ga) and np.array_equal(got["status_r53"], want.status_r53)
+          and np.array_equal(got["ops"], want.ops) and got["section_begin"].tolist() == want.section_begin.tolist())
+    print(json.dumps({"ok": bool(ok), "world": world, "n_ops": int(len(want.ops)), "homed": [int(len(p.obj_gid)) for p in parts],
+                      "sent": [int(p.sent) for p in parts]}))
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+def test_two_ranks_gloo_all_to_all(tmp_path):
+    import json, os, subprocess, sys
+    from pathlib import Path
+    import __graft_entry__ as ge
+    ge.build_hostsim()
+    ge.build_oracle()
+    repo = Path(__file__).resolve().parent.parent
+    script = tmp_path / "worker.py"
+    script.write_text(GLOO_WORKER % (str(repo), str(repo / "tests")))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29541")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29541", str(script)], capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stderr[-3000:]
+    d = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert d["ok"] and d["world"] == 2 and d["n_ops"] > 50
+    assert sum(d["homed"]) == 120 and min(d["homed"]) > 20
+    assert min(d["sent"]) > 1000
+
+
+# ------------------------------------------------------------------ GPU tier: several engines on one B200, blobs in HBM
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed,n_ranks", [(0, 2), (1, 3), (2, 4), (3, 8), (4, 1)])
+def test_gpu_sharded_random_models(garecon, oracle, seed, n_ranks):
+    objects, actual = randmodel.make(seed, n_objects=80)
+    slices = shard.slice_model(objects, actual, n_ranks)
+    engines, keep = [], []
+    for objs_r, act_r, _ in slices:
+        e = garecon.Engine(cluster_name="default")
+        e.load(garecon.pack(objs_r, act_r))
+        engines.append(e)
+    shard.exchange_local(engines, [s[2] for s in slices], keep, device="cuda:0")
+    parts = [e.diff() for e in engines]
+    assert all(p.kernel_launches > 0 for p in parts)
+    for e in engines:
+        e.close()
+    want = oracle.diff(garecon.pack(objects, actual), "default", mode=1)
+    check_slices(garecon, want, parts, len(objects))
+
+
+@pytest.mark.gpu
+def test_gpu_sharded_hot_keys(garecon, oracle):
+    objects, actual = hotkeys.make()
+    slices = shard.slice_model(objects, actual, 4)
+    engines, keep = [], []
+    for objs_r, act_r, _ in slices:
+        e = garecon.Engine(cluster_name="default")
+        e.load(garecon.pack(objs_r, act_r))
+        engines.append(e)
+    shard.exchange_local(engines, [s[2] for s in slices], keep, device="cuda:0")
+    parts = [e.diff() for e in engines]
+    for e in engines:
+        e.close()
+    check_slices(garecon, oracle.diff(garecon.pack(objects, actual), "default", mode=1), parts, len(objects))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cfg,n_total,n_ranks", [(4, 400_000, 4), (5, 200_000, 8), (3, 200_000, 2)])
+def test_gpu_sharded_equals_unsharded_at_scale(garecon, cfg, n_total, n_ranks):
+    """The sharded result of a generator cluster equals the single-engine diff of the union, bit for bit (both on the GPU;
+    the unsharded GPU path is itself pinned against the oracle at this size in test_gpu_large.py)."""
+    synth = importlib.import_module("aws-global-accelerator-controller_b200.synth")
+    slices = synth.cluster_slices(cfg, n_total, n_ranks)
+    union = garecon.tables.concat_slices(slices)
+    with garecon.Engine(cluster_name="default") as e:
+        e.load(union)
+        want = e.diff()
+    parts = run_sharded_slices(garecon, None, slices, device="cuda:0")
+    check_slices(garecon, want, parts, n_total)
+    assert len(want.ops) > n_total // 4
