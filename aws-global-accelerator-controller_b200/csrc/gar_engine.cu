@@ -298,6 +298,8 @@ struct gar_engine {
   DevTables slice{};          // the loaded slice (T switches to the home sub-snapshot after the second unpack)
   bool shard_home = false;    // T is a home sub-snapshot: results are translated to global rows
   int shard_round = 0;        // last completed step: 1 routed1, 2 unpacked1, 3 routed2, 4 unpacked2
+  u32 shard_launches = 0;     // kernels of the exchange steps since the last diff
+  bool shard_reported = true; // stage marks of the exchange steps already folded into a diff's timings
   std::vector<DBuf> arena[3];
   size_t arena_used[3] = {0, 0, 0};
   void *shard_alloc(int a, size_t bytes) {
@@ -689,9 +691,13 @@ static void do_diff(gar_engine *e, gar_changeset *out, bool to_host, const gar_k
   if (!e->loaded) throw InvalidError{"no snapshot loaded"};
   CK(cudaSetDevice(e->device));
   memset(out, 0, sizeof(*out));
-  e->launches = 0;
-  e->marks.clear();
-  e->events_used = 0;
+  e->launches = e->shard_home ? e->shard_launches : 0;  // a sharded step counts its routing / packing / merging kernels too
+  e->shard_launches = 0;
+  if (!e->shard_home || e->shard_reported) {
+    e->marks.clear();
+    e->events_used = 0;
+  }
+  e->shard_reported = true;
   e->stage_depth = 0;
   if (e->shard_home && (ks || bd)) throw InvalidError{"incremental / binding diffs are not available on a sharded sub-snapshot"};
   if (!e->pipe) {
@@ -993,7 +999,13 @@ int gar_shard_route(gar_engine *e, const gar_shard *shard, int round, uint64_t *
     if (shard->n_ranks < 1 || shard->n_ranks > GAR_SHARD_MAX_RANKS || shard->rank >= shard->n_ranks) throw InvalidError{"bad gar_shard"};
     CK(cudaSetDevice(e->device));
     if (!e->sharder) e->sharder = new Sharder<gar_engine>(*e);
+    u32 l0 = e->launches;
     if (round == 1) {
+      e->marks.clear();
+      e->events_used = 0;
+      e->stage_depth = 0;
+      e->shard_reported = false;
+      e->shard_launches = 0;
       e->slice.cluster = (const u8 *)e->cluster_dev.p;
       e->slice.cluster_len = (u32)e->cluster.size();
       e->sharder->route1(e->slice, *shard, meta, send_bytes);
@@ -1005,6 +1017,7 @@ int gar_shard_route(gar_engine *e, const gar_shard *shard, int round, uint64_t *
     } else {
       throw InvalidError{"round must be 1 or 2"};
     }
+    e->shard_launches += e->launches - l0;
     CK(cudaStreamSynchronize(e->stream));
   });
 }
@@ -1013,7 +1026,9 @@ int gar_shard_pack(gar_engine *e, void *send) {
   return guarded(e, [&] {
     if (e->shard_round != 1 && e->shard_round != 3) throw InvalidError{"gar_shard_pack without a routed plan"};
     CK(cudaSetDevice(e->device));
+    u32 l0 = e->launches;
     e->sharder->pack((u8 *)send);
+    e->shard_launches += e->launches - l0;
     CK(cudaStreamSynchronize(e->stream));  // the host hands `send` to the exchange next
     CK(cudaGetLastError());
   });
@@ -1023,6 +1038,7 @@ int gar_shard_unpack(gar_engine *e, int round, const void *recv, const uint64_t 
   if (!recv_meta) return GAR_E_INVALID;
   return guarded(e, [&] {
     CK(cudaSetDevice(e->device));
+    u32 l0 = e->launches;
     if (round == 1 && e->shard_round == 1) {
       e->sharder->unpack1((const u8 *)recv, recv_meta);
       e->shard_round = 2;
@@ -1036,6 +1052,7 @@ int gar_shard_unpack(gar_engine *e, int round, const void *recv, const uint64_t 
     } else {
       throw InvalidError{"gar_shard_unpack out of sequence"};
     }
+    e->shard_launches += e->launches - l0;
     CK(cudaStreamSynchronize(e->stream));
     CK(cudaGetLastError());
   });

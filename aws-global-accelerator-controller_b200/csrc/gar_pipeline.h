@@ -669,11 +669,34 @@ struct Pipeline {
     if (nval) be.for_each("expand_val_rec", nval, FExpand{T.a.rec_val_begin, nrec, W.val_rec});
     if (nval) be.for_each("classify_values", nval, FClassifyValue{T, W});
   }
+  // index build that does not assume small buckets: fast per-bucket build first, stable radix rebuild if a bucket overflowed
+  template <class RowF>
+  HashIdx build_index_checked(int slot, u32 nrows, u32 load, RowF rowf) {
+    u32 *overflow = errflag + 1;
+    HashIdx ix = build_index(slot, nrows, load, rowf, overflow, force_radix);
+    if (!force_radix && nrows) {
+      u32 ov = 0;
+      be.download(&ov, overflow, 4);
+      if (ov) {
+        be.fill32(overflow, 0, 1);
+        ix = build_index(slot, nrows, load, rowf, overflow, true);
+      }
+    }
+    return ix;
+  }
   // what the sharded mode's routing needs of a rank's slice: the row-local pass + the (zone, name) -> alias record index
   void prepare_route() {
     alloc_work();
     stage1();
-    W.ix_alias = build_index(S_IX_ALIAS, T.a.n_records, 2, FRowAlias{T, W}, errflag + 1, true);
+    W.ix_alias = build_index_checked(S_IX_ALIAS, T.a.n_records, 2, FRowAlias{T, W});
+  }
+  // a directory shard's tables (gar_shard.h): probes in lbi_*, load balancers, accelerator stubs
+  void prepare_directory() {
+    alloc_work();
+    if (T.o.n_lbi) be.for_each("tokenise_hostnames", T.o.n_lbi, FTokenise{T, W});
+    if (T.a.n_accels) be.for_each("digest_accelerators", T.a.n_accels, FDigestAccel{T, W});
+    W.ix_lb = build_index_checked(S_IX_LB, T.a.n_lbs, 1, FRowLb{T});
+    W.ix_thost = build_index_checked(S_IX_THOST, T.a.n_accels, 1, FRowThost{T, W});
   }
 
   int prepare() {

@@ -115,6 +115,8 @@ struct LevelPlan {  // selection of one level: rows sel[0..*m) sorted by destina
   u32 multi;      // host-side note: a source row may be selected for several destinations (children can outnumber the source level)
 };
 
+// strings start 8-byte aligned inside a blob: the copy is whole words (unaligned 8-byte loads, aligned stores)
+GAR_HD u32 sh_pad8(u32 len) { return (len + 7u) & ~7u; }
 GAR_HD u32 shard_of(u64 h, u32 n_ranks) { return (u32)(xx_avalanche(h + 0x9E3779B97F4A7C15ull) >> 33) % n_ranks; }
 // The key of the two by-hostname lookups (GetLoadBalancer by (region, name) of the tokenised hostname, global_accelerator.go:116-120;
 // ListGlobalAcceleratorByHostname by the hostname itself, :62-85): one function of the hostname string, so the probe, the
@@ -345,7 +347,7 @@ struct FShStrLen {
     u32 b = 0;
     if (j < *P.m) {
       u32 p = P.sel[j];
-      for (int c = 0; c < n_str; c++) b += (u32)GAR_STR_LEN(src.str[c][p]);
+      for (int c = 0; c < n_str; c++) b += sh_pad8((u32)GAR_STR_LEN(src.str[c][p]));
     }
     out[j] = b;
   }
@@ -371,7 +373,7 @@ struct FShPackCols {
     for (int c = 0; c < S.n_str; c++) {
       u64 len = GAR_STR_LEN(src.str[c][p]);
       ((gar_str *)(b + L.str[c]))[k] = GAR_STR(off, len);
-      off += len;
+      off += sh_pad8((u32)len);
     }
     for (int c = 0; c < S.n_u8; c++) (b + L.u8c[c])[k] = src.u8c[c][p];
     for (int c = 0; c < S.n_u32; c++) ((u32 *)(b + L.u32c[c]))[k] = src.u32c[c][p];
@@ -379,7 +381,9 @@ struct FShPackCols {
     for (int c = 0; c < S.n_child; c++) ((u32 *)(b + L.cnt[c]))[k] = P.cnt[c][j + 1] - P.cnt[c][j];
   }
 };
-// one warp-width of threads per selected row: lane l copies bytes l, l+32, ... of each string (coalesced)
+// SH_COPY_LANES threads per selected row: lane l copies words l, l+LANES, ... of each string.  The source may sit at any byte
+// offset (ld64u), the destination word is aligned; the bytes behind a string's end up to the next word are don't-care.
+constexpr u32 SH_COPY_LANES = 8;
 struct FShPackBytes {
   LevelSrc src;
   int n_str;
@@ -387,15 +391,15 @@ struct FShPackBytes {
   u32 G;
   PackDst D;
   GAR_HD void operator()(u32 t) const {
-    u32 j = t >> 5, lane = t & 31;
+    u32 j = t / SH_COPY_LANES, lane = t % SH_COPY_LANES;
     u32 d = dest_of(j, P.row_off, G), p = P.sel[j];
-    u8 *dst = D.base[d] + D.lay[d].slab + (P.slab_scan[j] - P.slab_scan[P.row_off[d]]);
+    u64 *dst = (u64 *)(D.base[d] + D.lay[d].slab + (P.slab_scan[j] - P.slab_scan[P.row_off[d]]));
     for (int c = 0; c < n_str; c++) {
       gar_str r = src.str[c][p];
       const u8 *s = src.slab + GAR_STR_OFF(r);
-      u32 len = (u32)GAR_STR_LEN(r);
-      for (u32 x = lane; x < len; x += 32) dst[x] = s[x];
-      dst += len;
+      u32 words = sh_pad8((u32)GAR_STR_LEN(r)) >> 3;
+      for (u32 w = lane; w < words; w += SH_COPY_LANES) dst[w] = ld64u(s + 8 * (size_t)w);
+      dst += words;
     }
   }
 };
@@ -448,10 +452,21 @@ struct FShObjNsName {
     name[i] = GAR_STR(off + nl + 1, len - nl - 1);
   }
 };
-struct FShZoneHist {
+// records arrive zone-major (whole zones per source rank, zone ranges ascending with the rank): begin[z] = first record
+// whose zone is >= z
+struct FShZoneBegin {
   const u32 *rec_zone;
+  u32 n_rec;
   u32 *begin;
-  GAR_HD void operator()(u32 r) const { GAR_ATOMIC_ADD(&begin[rec_zone[r]], 1u); }
+  GAR_HD void operator()(u32 z) const {
+    u32 lo = 0, hi = n_rec;
+    while (lo < hi) {
+      u32 mid = (lo + hi) >> 1;
+      if (rec_zone[mid] < z) lo = mid + 1;
+      else hi = mid;
+    }
+    begin[z] = lo;
+  }
 };
 
 // ------------------------------------------------------------------ directory: answer the probes (round 2 selection)
@@ -760,7 +775,7 @@ struct Sharder {
       u32 m = h_row_off[l][G];
       if (!active[l] || !m) continue;
       be.for_each("shard_pack_columns", m, FShPackCols{src[l], SH_SCHEMA[l], plan[l], G, D});
-      if (SH_SCHEMA[l].n_str && h_slab_off[l][G]) be.for_each("shard_pack_strings", m * 32, FShPackBytes{src[l], SH_SCHEMA[l].n_str, plan[l], G, D});
+      if (SH_SCHEMA[l].n_str && h_slab_off[l][G]) be.for_each("shard_pack_strings", m * SH_COPY_LANES, FShPackBytes{src[l], SH_SCHEMA[l].n_str, plan[l], G, D});
     }
   }
 
@@ -888,8 +903,7 @@ struct Sharder {
   void route2(u64 *meta, u64 *send_bytes) {
     delete dir_pipe;
     dir_pipe = new Pipeline<B>(be, Dt);
-    dir_pipe->force_radix = true;  // directory tables see every duplicate of a hot hostname: no bucket-size assumption
-    dir_pipe->prepare();
+    dir_pipe->prepare_directory();
     const Work &W = dir_pipe->W;
     const gar_actual &A = Dt.a;
     plan_begin();
@@ -967,9 +981,7 @@ struct Sharder {
     A.n_endpoints = ep.n; A.ep_id = ep.str[0];
     A.n_zones = zone.n; A.zone_name = zone.str[0];
     u32 *zb = alloc<u32>(AR, (size_t)zone.n + 1);
-    be.fill32(zb, 0, (size_t)zone.n + 1);
-    if (rec.n) be.for_each("shard_zone_hist", rec.n, FShZoneHist{rec.u32c[0], zb});
-    be.exclusive_scan(zb, zone.n + 1);
+    be.for_each("shard_zone_begin", zone.n + 1, FShZoneBegin{rec.u32c[0], rec.n, zb});
     A.zone_rec_begin = zb;
     A.n_records = rec.n; A.rec_name = rec.str[0]; A.rec_alias_dns = rec.str[1]; A.rec_type = rec.u8c[0]; A.rec_has_alias = rec.u8c[1];
     A.rec_val_begin = rec.begin[0];

@@ -21,7 +21,7 @@ class SynthConfig(C.Structure):
         ("p_missing_acc", C.c_float), ("p_port_drift", C.c_float), ("p_proto_drift", C.c_float), ("p_tag_drift", C.c_float),
         ("p_missing_listener", C.c_float), ("p_missing_eg", C.c_float), ("p_lb_not_active", C.c_float), ("p_orphan_acc", C.c_float),
         ("p_rec_missing", C.c_float), ("p_alias_drift", C.c_float), ("p_orphan_rec", C.c_float), ("p_dup_ports", C.c_float),
-        ("intern_keys", C.c_uint32), ("index_base", C.c_uint32), ("zone_base", C.c_uint32), ("zones_total", C.c_uint32),
+        ("intern_keys", C.c_uint32), ("index_base", C.c_uint32), ("zone_base", C.c_uint32), ("zones_total", C.c_uint32), ("emit_mask", C.c_uint32),
         ("cluster", C.c_char * 64),
     ]
 
@@ -100,27 +100,21 @@ def cluster_slices(cfg_id: int, n_total: int, n_ranks: int, ranks=None, seed=Non
     n_chunk = n_total // n_ranks
     want = list(range(n_ranks)) if ranks is None else list(ranks)
 
-    def chunk(c):
+    def cols(c, mask):
+        c %= n_ranks
         cfg = preset(cfg_id, n_chunk, **overrides)
         if seed is not None:
             cfg.seed = seed
         cfg.index_base = c * n_chunk
         cfg.zone_base = c * cfg.n_zones
         cfg.zones_total = n_ranks * cfg.n_zones
-        return SynthSnapshot(cfg)
-
-    cache = {}
-
-    def cols(c):
-        c %= n_ranks
-        if c not in cache:
-            snap = chunk(c)
-            cache[c] = (snap, tables.columns(snap.objects, tables.OBJ_TABLES), tables.columns(snap.actual, tables.ACT_TABLES))
-        return cache[c]
+        cfg.emit_mask = mask
+        snap = SynthSnapshot(cfg)
+        return snap, tables.columns(snap.objects, tables.OBJ_TABLES), tables.columns(snap.actual, tables.ACT_TABLES)
 
     out = []
     for r in want:
-        own, acc_src, lb_src = cols(r), cols(r + 1), cols(r + 2)
+        own, acc_src, lb_src = cols(r, 1 | 8), cols(r + 1, 4), cols(r + 2, 2)
         a = tables.take_families({tables.REC_FAMILY: own[2], tables.ACC_FAMILY: acc_src[2], ("lb",): lb_src[2]})
         o = {k: np.array(v) for k, v in own[1].items()}
         out.append((o, {k: np.array(v) for k, v in a.items()}))

@@ -348,8 +348,11 @@ Snapshot *generate(const gsyn_config &cfg) {
       });
     for (auto &x : th) x.join();
   }
+  // emit_mask (0 = everything): chunks of a sharded cluster only need some table families of a chunk
+  const uint32_t mask = cfg.emit_mask ? cfg.emit_mask : 0xFu;
+  const uint32_t n_obj = (mask & 1u) ? n : 0, n_lb = (mask & 2u) ? n : 0, n_acc = (mask & 4u) ? n : 0, n_rec = (mask & 8u) ? n : 0;
   // ---------------- objects (informer cache order)
-  for (uint32_t i = 0; i < n; i++) {
+  for (uint32_t i = 0; i < n_obj; i++) {
     const ObjSpec &s = specs[i];
     S.obj_kind.push_back(s.ingress ? GAR_KIND_INGRESS : GAR_KIND_SERVICE);
     S.obj_spec.push_back(s.ingress ? 0 : (s.eligible ? GAR_SVC_LOADBALANCER : GAR_SVC_CLUSTERIP));
@@ -401,7 +404,7 @@ Snapshot *generate(const gsyn_config &cfg) {
   // ---------------- load balancers (DescribeLoadBalancers order: permuted)
   {
     Perm pi(n, cfg.seed ^ 0x1B);
-    for (uint32_t r = 0; r < n; r++) {
+    for (uint32_t r = 0; r < n_lb; r++) {
       const ObjSpec &s = specs[pi(r)];
       S.lb_region.push_back(S.as.put(s.region));
       S.lb_name.push_back(S.as.put(s.lb_name));
@@ -418,7 +421,7 @@ Snapshot *generate(const gsyn_config &cfg) {
   S.ep_b.push_back(0);
   {
     Perm pi(n, cfg.seed ^ 0xACC);
-    for (uint32_t r = 0; r < n; r++) {
+    for (uint32_t r = 0; r < n_acc; r++) {
       uint32_t i = pi(r);
       const ObjSpec &s = specs[i];
       Rng rr(mix(s.r, 31));
@@ -486,7 +489,7 @@ Snapshot *generate(const gsyn_config &cfg) {
       return o + ".";
     };
     Perm pi(n, cfg.seed ^ 0x53);
-    for (uint32_t r = 0; r < n; r++) {
+    for (uint32_t r = 0; r < n_rec; r++) {
       uint32_t i = pi(r);
       const ObjSpec &s = specs[i];
       if (!s.eligible && !s.ingress) continue;
@@ -555,7 +558,7 @@ Snapshot *generate(const gsyn_config &cfg) {
   S.os.b.append(64, '\0');
   S.as.b.append(64, '\0');
   gar_objects &o = S.o;
-  o.n_objects = n;
+  o.n_objects = n_obj;
   o.obj_kind = S.obj_kind.data();
   o.obj_spec_type = S.obj_spec.data();
   o.obj_flags = S.obj_flags.data();

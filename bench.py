@@ -201,6 +201,151 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_sharded(args, rank, world, local_rank):
+    """BASELINE configs[3]: one cluster of --objects objects, every GPU starts with an arbitrary slice of each list, rows are
+    re-homed by key hash with one all-to-all (+ a small answer exchange), every GPU diffs its self-contained shard."""
+    import torch
+    import __graft_entry__ as ge
+    pkg = importlib.import_module("aws-global-accelerator-controller_b200")
+    synth = importlib.import_module("aws-global-accelerator-controller_b200.synth")
+    ranks_mod = importlib.import_module("aws-global-accelerator-controller_b200.ranks")
+    shard = importlib.import_module("aws-global-accelerator-controller_b200.shard")
+    dev = torch.device("cuda", local_rank)
+    R = ranks_mod.Ranks(backend="nccl", device=dev)
+    if world > 1 and not R.dist.is_initialized():
+        raise SystemExit("sharded mode with WORLD_SIZE > 1 needs torch.distributed")
+    if world == 1 and not R.dist.is_initialized():  # single GPU: a 1-rank group keeps the code path identical
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29577")
+        R.dist.init_process_group("nccl", rank=0, world_size=1, device_id=dev)
+        R.owns_group = True
+    if rank == 0:
+        ge.ensure_built()
+    R.barrier()
+    cfg_id = 4 if args.config == 3 else args.config  # default workload of this mode: configs[3] = generator preset 4
+    n_total = args.objects - args.objects % world
+    o_cols, a_cols = synth.cluster_slices(cfg_id, n_total, world, ranks=[rank])[0]
+    snap = pkg.tables.from_columns(o_cols, a_cols)
+    counts = R.gather_counts([len(o_cols["obj_kind"]), len(a_cols["lb_state"]), len(a_cols["acc_enabled"]), len(a_cols["lis_proto"]),
+                              len(a_cols["eg_ep_begin"]) - 1, len(a_cols["rec_type"]), len(a_cols["val_value"]), snap.input_bytes()])
+    base = [sum(c[k] for c in counts[:rank]) for k in range(7)]
+    sh = pkg.abi.GarShard(rank, world, *base)
+    h2d_bytes = snap.input_bytes()
+    _pin_host_tables(torch, pkg.abi, snap.objects, snap.actual)
+    eng = pkg.Engine(cluster_name="default", device=local_rank)
+    ex = shard.DistExchange(eng, sh, dev)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    def step():
+        ex.run()
+        return eng.diff_device()
+
+    eng.load(snap)
+    launches = 0
+    for _ in range(args.warmup):
+        cs = step()
+    R.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cs = step()
+        launches += cs.kernel_launches
+    R.barrier()
+    t1 = time.perf_counter()
+    dt_dev = R.max_over_ranks(t1 - t0)
+    clocks = sampler.summary(t0, t1)
+    n_ops = int(cs.n_ops)
+    homed = int(cs.n_objects)
+    sent = ex.bytes_sent
+    # end to end: host slice in (H2D), host change set out (D2H), every step
+    for _ in range(2):
+        eng.load(snap)
+        ex.run()
+        full = eng.diff_raw()
+    R.barrier()
+    t2 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.load(snap)
+        ex.run()
+        full = eng.diff_raw()
+    R.barrier()
+    t3 = time.perf_counter()
+    dt_e2e = R.max_over_ranks(t3 - t2)
+    sampler.stop()
+    # phase breakdown (separate pass, synchronised between phases; not part of the timed numbers above)
+    phases = {}
+
+    def timed(name, fn):
+        torch.cuda.synchronize()
+        ta = time.perf_counter()
+        out = fn()
+        torch.cuda.synchronize()
+        phases[name] = phases.get(name, 0.0) + (time.perf_counter() - ta) * 1e3 / 3
+        return out
+    for _ in range(3):
+        ex.keep.clear()
+        for rnd in (1, 2):
+            meta, nbytes = timed(f"route{rnd}", lambda: eng.shard_route(sh, rnd))
+            m_out = torch.from_numpy(meta.view("int64")).to(dev)
+            m_in = torch.empty_like(m_out)
+            timed(f"meta_a2a{rnd}", lambda: R.dist.all_to_all_single(m_in, m_out))
+            recv_meta = m_in.cpu().numpy().view("uint64")
+            ins = [int(x) for x in nbytes]
+            outs = [eng.blob_bytes(recv_meta[s]) for s in range(world)]
+            send = torch.empty(sum(ins) + 64, dtype=torch.uint8, device=dev)
+            timed(f"pack{rnd}", lambda: eng.shard_pack(send.data_ptr()))
+            recv = torch.empty(sum(outs) + 64, dtype=torch.uint8, device=dev)
+            timed(f"blob_a2a{rnd}", lambda: R.dist.all_to_all_single(recv[:sum(outs)], send[:sum(ins)], output_split_sizes=outs, input_split_sizes=ins))
+            ex.keep.append(recv)
+            timed(f"unpack{rnd}", lambda: eng.shard_unpack(rnd, recv.data_ptr(), recv_meta))
+        timed("diff", lambda: eng.diff_device())
+    # per-kernel CUDA-event times of one whole sharded step (engine with GAR_FLAG_STAGE_TIMING; separate pass)
+    eng.close()
+    peng = pkg.Engine(cluster_name="default", device=local_rank, stage_timing=True)
+    peng.load(snap)
+    pex = shard.DistExchange(peng, sh, dev)
+    stage_acc = {}
+    for it in range(4):
+        pex.run()
+        peng.diff_device()
+        if it == 0:
+            continue
+        for name, ms, nl in peng.stage_timings():
+            e = stage_acc.setdefault(name, [0.0, 0])
+            e[0] += ms / 3
+            e[1] += nl
+    peng.close()
+    allc = R.gather_counts([homed, n_ops, sent, int(sum(phases.values()) * 1000)] + [int(phases[k] * 1000) for k in sorted(phases)])
+    if rank == 0:
+        peak, peak_src = _peaks()
+        in_bytes = sum(c[7] for c in counts)
+        b_alg = in_bytes + 8 * n_total + 24 * sum(c[1] for c in allc)
+        value = n_total * args.steps / dt_dev
+        achieved = b_alg / (dt_dev / args.steps) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "u8/u32 (bytes and indices)", "data": "synthetic",
+            "config": {"workload": f"BASELINE configs[3]: ONE cluster of {n_total} Service+Ingress (generator preset {cfg_id}) cut into {world} slices "
+                                   f"(objects / accelerators / load balancers of different chunks on each rank), re-homed by key hash",
+                       "objects_total": n_total, "parallelism": f"key-hash shards x{world}: all-to-all of rows + answer exchange (NCCL), then local diff",
+                       "cache": f"slice inputs ({h2d_bytes / 1e6:.0f} MB per GPU) larger than L2 (126 MB); no flush needed",
+                       "homed_objects_per_rank": [c[0] for c in allc], "ops_per_rank": [c[1] for c in allc],
+                       "all_to_all_bytes_sent_per_rank": [c[2] for c in allc], "algorithmic_bytes": b_alg},
+            "e2e": {"value": n_total * args.steps / dt_e2e, "unit": UNIT, "h2d_bytes_per_step": sum(c[7] for c in counts),
+                    "d2h_bytes_per_step": 12 * n_total + 24 * sum(c[1] for c in allc), "ms_per_step": dt_e2e / args.steps * 1e3},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "whole sharded step (route, pack, exchange, merge, diff)", "achieved": achieved, "peak": peak * world,
+                         "unit": "GB/s", "frac": achieved / (peak * world), "traffic": None, "peak_source": peak_src + f" x {world} GPUs"},
+            "phases_ms_rank0": {k: round(v, 3) for k, v in phases.items()},
+            "stages_ms_rank0": {k: round(v[0], 4) for k, v in sorted(stage_acc.items(), key=lambda kv: -kv[1][0])},
+            "phases_ms_max_over_ranks": {k: max(c[4 + i] for c in allc) / 1000 for i, k in enumerate(sorted(phases))},
+        }
+        print(json.dumps(line), flush=True)
+    R.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -211,6 +356,9 @@ def main():
     ap.add_argument("--objects", type=int, default=1_000_000)
     ap.add_argument("--cpu-sample", type=int, default=200_000, help="objects in the bounded sample the CPU baseline is timed on")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="replicas", choices=["replicas", "sharded"],
+                    help="replicas: one independent cluster per GPU (weak scaling, no collective; the default and the driver's scaling run); "
+                         "sharded: ONE cluster of --objects objects re-homed by key hash across the GPUs (BASELINE configs[3], strong scaling)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "garecon" else args.warmup
 
@@ -225,6 +373,9 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
     torch.cuda.set_device(local_rank)
+    if args.mode == "sharded":
+        run_sharded(args, rank, world, local_rank)
+        return
     import __graft_entry__ as ge
     pkg = importlib.import_module("aws-global-accelerator-controller_b200")
     synth = importlib.import_module("aws-global-accelerator-controller_b200.synth")
