@@ -140,63 +140,37 @@ def test_generator_slices_on_hostsim(garecon, oracle, hostlib, cfg, n_total, n_r
 
 # ------------------------------------------------------------------ the torch.distributed data path, 2 processes on gloo
 
-GLOO_WORKER = r'''
-import importlib, json, sys
-sys.path.insert(0, %r); sys.path.insert(0, %r)
-import numpy as np, torch.distributed as dist
-import __graft_entry__ as ge
-import randmodel
-garecon = importlib.import_module("aws-global-accelerator-controller_b200")
-shard = importlib.import_module("aws-global-accelerator-controller_b200.shard")
-ob = importlib.import_module("oracle.binding")
-dist.init_process_group("gloo")
-rank, world = dist.get_rank(), dist.get_world_size()
-lib = garecon.abi.load_library(ge.build_hostsim())
-objects, actual = randmodel.make(21, n_objects=120)
-objs_r, act_r, sh = shard.slice_model(objects, actual, world)[rank]
-e = garecon.Engine(cluster_name="default", lib=lib)
-snap = garecon.pack(objs_r, act_r)   # hostsim reads the columns in place: keep them alive
-e.load(snap)
-x = shard.DistExchange(e, sh, "cpu")
-x.run()
-part = e.diff()
-payload = dict(obj_gid=part.obj_gid, status_ga=part.status_ga, status_r53=part.status_r53, derived=part.derived, ops=part.ops,
-               section_begin=part.section_begin, sent=x.bytes_sent)
-gathered = [None] * world if rank == 0 else None
-dist.gather_object(payload, gathered, dst=0)
-if rank == 0:
-    class P: pass
-    parts = []
-    for g in gathered:
-        p = P(); p.__dict__.update(g); parts.append(p)
-    got = shard.merge_changesets(parts, len(objects))
-    want = ob.diff(garecon.pack(objects, actual), "default", mode=1)
-    ok = (np.array_equal(got["status_ga"], want.status_ga) and np.array_equal(got["status_r53"], want.status_r53)
-          and np.array_equal(got["ops"], want.ops) and got["section_begin"].tolist() == want.section_begin.tolist())
-    print(json.dumps({"ok": bool(ok), "world": world, "n_ops": int(len(want.ops)), "homed": [int(len(p.obj_gid)) for p in parts],
-                      "sent": [int(p.sent) for p in parts]}))
-dist.barrier()
-dist.destroy_process_group()
-'''
-
-
-def test_two_ranks_gloo_all_to_all(tmp_path):
+def _launch(nproc, port, *worker_args, timeout=900):
     import json, os, subprocess, sys
     from pathlib import Path
+    worker = Path(__file__).resolve().parent / "shard_worker.py"
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc), "--master-addr", "127.0.0.1",
+                          "--master-port", str(port), str(worker), *[str(a) for a in worker_args]], capture_output=True, text=True, env=env, timeout=timeout)
+    assert out.returncode == 0, out.stderr[-3000:]
+    return json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+
+
+def test_two_ranks_gloo_all_to_all():
     import __graft_entry__ as ge
     ge.build_hostsim()
     ge.build_oracle()
-    repo = Path(__file__).resolve().parent.parent
-    script = tmp_path / "worker.py"
-    script.write_text(GLOO_WORKER % (str(repo), str(repo / "tests")))
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29541")
-    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-                          "--master-port", "29541", str(script)], capture_output=True, text=True, env=env, timeout=600)
-    assert out.returncode == 0, out.stderr[-3000:]
-    d = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    d = _launch(2, 29541, "gloo", "randmodel", 21, 120)
     assert d["ok"] and d["world"] == 2 and d["n_ops"] > 50
     assert sum(d["homed"]) == 120 and min(d["homed"]) > 20
     assert min(d["sent"]) > 1000
+
+
+@pytest.mark.gpu
+def test_nccl_ranks_equal_unsharded():
+    """One process per GPU, blobs over NCCL: needs >= 2 GPUs (the single-GPU test box skips it; run with gpurun --gpus N)."""
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    d = _launch(min(n, 8), 29547, "nccl", "synth", 4, 400_000)
+    assert d["ok"] and d["n_ops"] > 100_000
+    assert sum(d["homed"]) == d["n_objects"] and min(d["launches"]) > 0
 
 
 # ------------------------------------------------------------------ GPU tier: several engines on one B200, blobs in HBM
