@@ -62,6 +62,8 @@ def exchange_local(engines, shards, keep, device="cpu"):
         for e, sh in zip(engines, shards):
             meta, nbytes = e.shard_route(sh, rnd)
             buf = torch.zeros(int(nbytes.sum()) + 64, dtype=torch.uint8, device=device)
+            if str(device) != "cpu":
+                torch.cuda.synchronize()  # the fill runs on torch's stream, the engine packs on its own: order them
             e.shard_pack(buf.data_ptr())
             metas.append(meta)
             sends.append((buf, np.concatenate([[0], np.cumsum(nbytes)]).astype(np.int64)))
