@@ -81,7 +81,9 @@ struct FExpand {
     parent_of[c] = lo;
   }
 };
-// record row -> zone row, and the hash of the record name (every (zone, name) key is derived from it)
+// record row -> zone row, the hash of the record name (every (zone, name) key is derived from it), and its values: value ->
+// record, owner-value classification.  One pass over the record table: a record's name and values are neighbours in the slab,
+// so they share DRAM sectors.
 struct FPrepareRecord {
   DevTables T;
   Work W;
@@ -94,12 +96,11 @@ struct FPrepareRecord {
     }
     W.rec_zone[r] = lo;
     W.rec_name_hash[r] = gar_hash(mkstr(T.a.slab, T.a.rec_name[r]));
+    for (u32 v = T.a.rec_val_begin[r]; v < T.a.rec_val_begin[r + 1]; v++) {
+      W.val_rec[v] = r;
+      classify_value(T, W, v);
+    }
   }
-};
-struct FClassifyValue {
-  DevTables T;
-  Work W;
-  GAR_HD void operator()(u32 v) const { classify_value(T, W, v); }
 };
 struct FJsonCount {
   DevTables T;
@@ -249,13 +250,15 @@ struct FIdxRows {
     u64 h = 0;
     IdxEntry e;
     bool valid = rowf.make(i, &h, &e);
-    e.tag = hash_tag(h);
-    e.row = i;
-    tmp[i] = e;
     u32 k = valid ? hash_bucket(h, mask) : nb;  // rows that are not indexed carry the sentinel key nb
     keys[i] = k;
-    vals[i] = i;
-    if (valid) GAR_ATOMIC_ADD(&counts[k], 1u);
+    if (vals) vals[i] = i;  // only the radix rebuild sorts (key, row) pairs
+    if (valid) {
+      e.tag = hash_tag(h);
+      e.row = i;
+      tmp[i] = e;
+      GAR_ATOMIC_ADD(&counts[k], 1u);
+    }
   }
 };
 struct FIdxPlace {
@@ -322,10 +325,15 @@ struct FGatherHeader {
     dst[1] = *errflag;
   }
 };
-struct FMarkOrphanValue {
+// the two per-value joins in one pass (independent probe chains overlap): first alias record under the value's (zone, name),
+// and whether the owner the value names is still in the object cache
+struct FValueJoins {
   DevTables T;
   Work W;
-  GAR_HD void operator()(u32 v) const { mark_orphan_value(T, W, v); }
+  GAR_HD void operator()(u32 v) const {
+    link_value_alias(T, W, v);
+    mark_orphan_value(T, W, v);
+  }
 };
 
 // --- count / emit.  counts layout: [GA obj: n][GA orphan: nacc][R53 obj: n][orphan alias: nrec][orphan value: nval][total]
@@ -379,11 +387,6 @@ struct FR53Obj {
       counts[t] = s.n;
     }
   }
-};
-struct FLinkValueAlias {
-  DevTables T;
-  Work W;
-  GAR_HD void operator()(u32 v) const { link_value_alias(T, W, v); }
 };
 struct FR53Prepare {
   DevTables T;
@@ -597,7 +600,7 @@ struct Pipeline {
     u32 *begin = (u32 *)be.ensure(slot + 0, sizeof(u32) * (size_t)(nb + 2));
     IdxEntry *ent = (IdxEntry *)be.ensure(slot + 1, sizeof(IdxEntry) * (size_t)(nrows + 1));
     be.fill32(begin, 0, nb + 2);
-    if (nrows) be.for_each("idx_rows", nrows, FIdxRows<RowF>{rowf, keys, vals, tmp, begin, nb - 1, nb});
+    if (nrows) be.for_each("idx_rows", nrows, FIdxRows<RowF>{rowf, keys, force_radix ? vals : nullptr, tmp, begin, nb - 1, nb});
     be.exclusive_scan(begin, nb + 2);  // begin[b] = #rows with key < b; begin[nb] = #indexed rows
     if (nrows && !force_radix) {
       u32 *cursor = (u32 *)be.ensure(S_SORT_KEYS_ALT, sizeof(u32) * (size_t)(nb + 1));
@@ -665,9 +668,7 @@ struct Pipeline {
     if (n) be.for_each("classify_objects", n, FClassify{T, W, derived_public, nullptr, errflag});
     if (nlbi) be.for_each("tokenise_hostnames", nlbi, FTokenise{T, W});
     if (nacc) be.for_each("digest_accelerators", nacc, FDigestAccel{T, W});
-    if (nrec) be.for_each("prepare_records", nrec, FPrepareRecord{T, W});
-    if (nval) be.for_each("expand_val_rec", nval, FExpand{T.a.rec_val_begin, nrec, W.val_rec});
-    if (nval) be.for_each("classify_values", nval, FClassifyValue{T, W});
+    if (nrec) be.for_each("prepare_records", nrec, FPrepareRecord{T, W});  // includes the records' values
   }
   // index build that does not assume small buckets: fast per-bucket build first, stable radix rebuild if a bucket overflowed
   template <class RowF>
@@ -723,9 +724,8 @@ struct Pipeline {
     W.ix_zone = build_index(S_IX_ZONE, nzone, 1, FRowZone{T}, overflow, force_radix);
     W.ix_val = build_index(S_IX_VAL, nval, 1, FRowVal{T, W}, overflow, force_radix);
     W.ix_alias = build_index(S_IX_ALIAS, nrec, 2, FRowAlias{T, W}, overflow, force_radix);
-    if (nval) be.for_each("link_value_alias", nval, FLinkValueAlias{T, W});
     W.ix_obj = build_index(S_IX_OBJ, n, 1, FRowObj{T, W}, overflow, force_radix);
-    if (nval) be.for_each("mark_orphan_values", nval, FMarkOrphanValue{T, W});
+    if (nval) be.for_each("value_joins", nval, FValueJoins{T, W});
     W.ix_ovn = build_index(S_IX_OVN, nval, 8, FRowOvn{T, W}, overflow, force_radix);
     return GAR_OK;
   }

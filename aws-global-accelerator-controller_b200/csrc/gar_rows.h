@@ -290,12 +290,11 @@ GAR_HD u8 tokenise_str(Str h, u64 base, gar_str *name_out, gar_str *region_out) 
     // ".amazonaws.com" (14 bytes), none of them '\n'.  The right-most candidate has the smallest middle.
     bool nlb = false;
     if (h.n >= 20) {
-      for (u32 i = h.n - 20 + 1; i-- > 0;) {
-        if (h.p[i] == '.' && lit_eq_at(h, i, ".elb.")) {
-          nlb = find_byte(substr(h, 0, h.n - 14), i + 5, '\n') >= h.n - 14;
-          break;
-        }
-      }
+      // walk the dots left to right (word-wise search) and keep the right-most ".elb." that starts at or before n - 20
+      u32 last = GAR_NONE;
+      for (u32 i = d1; i <= h.n - 20; i = find_byte(h, i + 1, '.'))
+        if (lit_eq_at(h, i, ".elb.")) last = i;
+      if (last != GAR_NONE) nlb = find_byte(substr(h, 0, h.n - 14), last + 5, '\n') >= h.n - 14;
     }
     if (!nlb) {
       code = GAR_TOK_ERR_NOT_ELB;
@@ -319,14 +318,15 @@ GAR_HD u8 tokenise_str(Str h, u64 base, gar_str *name_out, gar_str *region_out) 
   *region_out = region;
   return code;
 }
-GAR_HD void tokenise_hostname(const DevTables &T, const Work &W, u32 row) {
-  gar_str href = T.o.lbi_hostname[row];
+// h = the bytes of lbi_hostname[row] (in the slab, or staged in shared memory by the caller)
+GAR_HD void tokenise_hostname_at(const DevTables &T, const Work &W, u32 row, Str h) {
   gar_str name, region;
-  u8 code = tokenise_str(mkstr(T.o.slab, href), GAR_STR_OFF(href), &name, &region);
+  u8 code = tokenise_str(h, GAR_STR_OFF(T.o.lbi_hostname[row]), &name, &region);
   W.tok_code[row] = code;
   W.tok_name[row] = name;
   W.tok_region[row] = region;
 }
+GAR_HD void tokenise_hostname(const DevTables &T, const Work &W, u32 row) { tokenise_hostname_at(T, W, row, mkstr(T.o.slab, T.o.lbi_hostname[row])); }
 
 // ------------------------------------------------------------------ (a5) accelerator tag digest
 //
@@ -420,10 +420,10 @@ GAR_HD void digest_accelerator(const DevTables &T, const Work &W, u32 a) {
 
 #define R53_HERITAGE "\"heritage=aws-global-accelerator-controller,cluster="
 
-GAR_HD void classify_value(const DevTables &T, const Work &W, u32 v) {
+// s = the bytes of val_value[v] (in the slab, or staged in shared memory by the caller)
+GAR_HD void classify_value_at(const DevTables &T, const Work &W, u32 v, Str s) {
   const gar_actual &A = T.a;
   gar_str ref = A.val_value[v];
-  Str s = mkstr(A.slab, ref);
   u8 cls = VAL_NOT_OWNER;
   gar_str key = 0;
   const u32 hl = (u32)(sizeof(R53_HERITAGE) - 1);
@@ -436,13 +436,14 @@ GAR_HD void classify_value(const DevTables &T, const Work &W, u32 v) {
     else if (HAS_PREFIX_LIT(rest, "ingress/")) cls = VAL_OWNER_INGRESS;
     if (cls) {
       key = GAR_STR(GAR_STR_OFF(ref) + ro + 8, rest.n - 8);
-      if (count_slashes(mkstr(A.slab, key)) == 1) cls |= VAL_OWNER_3PART;
+      if (count_slashes(substr(rest, 8, rest.n - 8)) == 1) cls |= VAL_OWNER_3PART;
     }
   }
   W.val_cls[v] = cls;
   W.val_key[v] = key;
-  W.val_key_hash[v] = cls ? key_hash_kinded((cls & VAL_OWNER_INGRESS) ? 1u : 0u, mkstr(A.slab, key)) : 0;
+  W.val_key_hash[v] = cls ? key_hash_kinded((cls & VAL_OWNER_INGRESS) ? 1u : 0u, substr(s, (u32)(GAR_STR_OFF(key) - GAR_STR_OFF(ref)), (u32)GAR_STR_LEN(key))) : 0;
 }
+GAR_HD void classify_value(const DevTables &T, const Work &W, u32 v) { classify_value_at(T, W, v, mkstr(T.a.slab, T.a.val_value[v])); }
 
 // ------------------------------------------------------------------ index probes
 //
