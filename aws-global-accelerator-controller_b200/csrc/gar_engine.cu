@@ -1040,10 +1040,10 @@ int gar_shard_unpack(gar_engine *e, int round, const void *recv, const uint64_t 
     CK(cudaSetDevice(e->device));
     u32 l0 = e->launches;
     if (round == 1 && e->shard_round == 1) {
-      e->sharder->unpack1((const u8 *)recv, recv_meta);
+      if (e->sharder->unpack1((const u8 *)recv, recv_meta) != GAR_OK) throw InvalidError{e->sharder->contract_error};
       e->shard_round = 2;
     } else if (round == 2 && e->shard_round == 3) {
-      e->sharder->unpack2((const u8 *)recv, recv_meta);
+      if (e->sharder->unpack2((const u8 *)recv, recv_meta) != GAR_OK) throw InvalidError{e->sharder->contract_error};
       delete e->pipe;
       e->pipe = nullptr;
       e->T = e->sharder->H;

@@ -35,7 +35,7 @@
 constexpr int SH_MAX_RANKS = GAR_SHARD_MAX_RANKS;
 constexpr int SH_MAX_SEGS = 2 * SH_MAX_RANKS;
 enum ShLevel { L_OBJ, L_ANN, L_LBI, L_PORT, L_ACC, L_TAG, L_LIS, L_PR, L_EG, L_EP, L_REC, L_VAL, L_ZONE, L_LB, L_STUB, L_STUBTAG, L_PROBE, L_NLEVELS };
-static_assert(2 * L_NLEVELS <= GAR_SHARD_META_WORDS, "meta row too small");
+static_assert(2 * L_NLEVELS + 1 <= GAR_SHARD_META_WORDS, "meta row too small");
 constexpr int SH_MAX_STR = 4, SH_MAX_U8 = 3, SH_MAX_U32 = 1, SH_MAX_CHILD = 3;
 enum { SH_ARENA_PLAN = 0, SH_ARENA_DIR = 1, SH_ARENA_HOME = 2 };
 constexpr u32 SH_DROP = 255;  // destination of a row nobody needs
@@ -469,6 +469,31 @@ struct FShZoneBegin {
   }
 };
 
+// sharded-mode contract checks: the zone table must be the same on every rank (fingerprint travels in the meta row), and the
+// merged record sets must come out zone-major
+struct FShZoneFingerprint {
+  DevTables T;
+  unsigned long long *acc;
+  GAR_HD void operator()(u32 z) const {
+    u64 h = hmix((u64)z + 1, gar_hash(mkstr(T.a.slab, T.a.zone_name[z])));
+#if defined(__CUDA_ARCH__)
+    atomicAdd(acc, (unsigned long long)h);
+#else
+    *acc += h;
+#endif
+  }
+};
+struct FShCheckZoneOrder {
+  const u32 *rec_zone;
+  u32 n_zones;
+  u32 *bad;
+  GAR_HD void operator()(u32 r) const {
+    if (rec_zone[r] >= n_zones || (r > 0 && rec_zone[r - 1] > rec_zone[r])) GAR_ATOMIC_ADD(bad, 1u);
+  }
+};
+constexpr int SH_META_ZONE_FP = 2 * L_NLEVELS;  // meta word carrying the sender's zone-table fingerprint
+#define GAR_E_SHARD_CONTRACT 2000               // Sharder: the slices violate the sharded-mode contract (mapped to GAR_E_INVALID)
+
 // ------------------------------------------------------------------ directory: answer the probes (round 2 selection)
 
 // One probe = one lbIngress hostname of some object.  The LB the reference would get (first row wins) and the first two
@@ -564,6 +589,8 @@ struct Sharder {
   // round 1 receive side, kept for the home merge after round 2
   const u8 *recv1 = nullptr;
   u64 meta1[SH_MAX_RANKS][GAR_SHARD_META_WORDS]{};
+  u64 zone_fp = 0;           // fingerprint of this rank's zone table (round 1 meta)
+  const char *contract_error = nullptr;
 
   explicit Sharder(B &b) : be(b) {}
   ~Sharder() {
@@ -657,6 +684,7 @@ struct Sharder {
         row[l] = h_row_off[l][d + 1] - h_row_off[l][d];
         row[L_NLEVELS + l] = h_slab_off[l][d + 1] - h_slab_off[l][d];
       }
+      row[SH_META_ZONE_FP] = zone_fp;  // not part of the layout: blob_bytes ignores it
       send_bytes[d] = blob_bytes(row);
     }
   }
@@ -673,6 +701,13 @@ struct Sharder {
     const gar_objects &O = S.o;
     const gar_actual &A = S.a;
     plan_begin();
+    {
+      unsigned long long *fp = (unsigned long long *)alloc<u64>(SH_ARENA_PLAN, 2);
+      be.fill32((u32 *)fp, 0, 4);
+      if (A.n_zones) be.for_each("shard_zone_fingerprint", A.n_zones, FShZoneFingerprint{S, fp});
+      be.download(&zone_fp, fp, 8);
+      zone_fp ^= (u64)A.n_zones << 48;
+    }
     // sources
     gar_str *okey = alloc<gar_str>(SH_ARENA_PLAN, O.n_objects);
     u32 *ns_len = alloc<u32>(SH_ARENA_PLAN, O.n_objects);
@@ -853,10 +888,15 @@ struct Sharder {
   }
 
   // ---- after the round-1 exchange: build the directory tables (LBs, stubs, probes routed here)
-  void unpack1(const u8 *recv, const u64 *meta_in) {
+  int unpack1(const u8 *recv, const u64 *meta_in) {
     recv1 = recv;
     for (u32 s = 0; s < G; s++)
       for (int w = 0; w < GAR_SHARD_META_WORDS; w++) meta1[s][w] = meta_in[(size_t)s * GAR_SHARD_META_WORDS + w];
+    for (u32 s = 0; s < G; s++)
+      if (meta1[s][SH_META_ZONE_FP] != zone_fp) {
+        contract_error = "sharded mode: the zone table (zone_name, order, count) must be identical on every rank";
+        return GAR_E_SHARD_CONTRACT;
+      }
     be.shard_reset(SH_ARENA_DIR);
     auto lb = segs(recv, meta1, L_LB), st = segs(recv, meta1, L_STUB), stt = segs(recv, meta1, L_STUBTAG), pr = segs(recv, meta1, L_PROBE);
     u64 a_bytes = slab_total({lb, st, stt}), o_bytes = slab_total({pr});
@@ -897,6 +937,7 @@ struct Sharder {
     dir_home = mpr.u32c[0];
     dir_lb_gid = mlb.gid;
     dir_stub_gid = mst.gid;
+    return GAR_OK;
   }
 
   // ---- round 2: resolve the probes, route the answers to their homes
@@ -924,7 +965,7 @@ struct Sharder {
   }
 
   // ---- after the round-2 exchange: assemble the home sub-snapshot
-  void unpack2(const u8 *recv2, const u64 *meta_in2) {
+  int unpack2(const u8 *recv2, const u64 *meta_in2) {
     u64 meta2[SH_MAX_RANKS][GAR_SHARD_META_WORDS];
     for (u32 s = 0; s < G; s++)
       for (int w = 0; w < GAR_SHARD_META_WORDS; w++) meta2[s][w] = meta_in2[(size_t)s * GAR_SHARD_META_WORDS + w];
@@ -981,6 +1022,15 @@ struct Sharder {
     A.n_endpoints = ep.n; A.ep_id = ep.str[0];
     A.n_zones = zone.n; A.zone_name = zone.str[0];
     u32 *zb = alloc<u32>(AR, (size_t)zone.n + 1);
+    u32 *bad = alloc<u32>(AR, 2);
+    be.fill32(bad, 0, 2);
+    if (rec.n) be.for_each("shard_check_zone_order", rec.n, FShCheckZoneOrder{rec.u32c[0], zone.n, bad});
+    u32 nbad = 0;
+    be.download(&nbad, bad, 4);
+    if (nbad) {
+      contract_error = "sharded mode: a rank must hold the record sets of whole zones, zone ranges ascending with the rank";
+      return GAR_E_SHARD_CONTRACT;
+    }
     be.for_each("shard_zone_begin", zone.n + 1, FShZoneBegin{rec.u32c[0], rec.n, zb});
     A.zone_rec_begin = zb;
     A.n_records = rec.n; A.rec_name = rec.str[0]; A.rec_alias_dns = rec.str[1]; A.rec_type = rec.u8c[0]; A.rec_has_alias = rec.u8c[1];
@@ -989,5 +1039,6 @@ struct Sharder {
     A.slab = aslab; A.slab_len = a_bytes;
     gids = ShGids{obj.gid, lb.gid, acc.gid, lis.gid, eg.gid, rec.gid, val.gid};
     guest_from = n_own;
+    return GAR_OK;
   }
 };

@@ -287,10 +287,16 @@ int gar_shard_pack(gar_engine *e, void *send) {
 }
 int gar_shard_unpack(gar_engine *e, int round, const void *recv, const uint64_t *recv_meta) {
   if (round == 1 && e->shard_round == 1) {
-    e->sharder->unpack1((const u8 *)recv, recv_meta);
+    if (e->sharder->unpack1((const u8 *)recv, recv_meta) != GAR_OK) {
+      e->err = e->sharder->contract_error;
+      return GAR_E_INVALID;
+    }
     e->shard_round = 2;
   } else if (round == 2 && e->shard_round == 3) {
-    e->sharder->unpack2((const u8 *)recv, recv_meta);
+    if (e->sharder->unpack2((const u8 *)recv, recv_meta) != GAR_OK) {
+      e->err = e->sharder->contract_error;
+      return GAR_E_INVALID;
+    }
     delete e->pipe;
     e->pipe = nullptr;
     e->T = e->sharder->H;

@@ -90,6 +90,44 @@ def test_sharded_empty_and_lopsided(garecon, oracle, hostlib):
     check(garecon, oracle, hostlib, [], actual, 3)
 
 
+def test_contract_violations_are_errors(garecon, hostlib):
+    """The two layout rules of sharded mode are checked on the device: same zone table everywhere, whole zones per rank in
+    ascending ranges."""
+    objects, actual = randmodel.make(2, n_objects=40)
+    slices = shard.slice_model(objects, actual, 2)
+
+    def run(mutate):
+        engines, keep = [], []
+        for r, (objs_r, act_r, _) in enumerate(slices):
+            act_r = mutate(r, act_r)
+            e = garecon.Engine(cluster_name="default", lib=hostlib)
+            snap = garecon.pack(objs_r, act_r)
+            keep.append(snap)
+            e.load(snap)
+            engines.append(e)
+        try:
+            shard.exchange_local(engines, [s[2] for s in slices], keep)
+        finally:
+            for e in engines:
+                e.close()
+
+    def rename_zone(r, act):
+        if r == 1 and act["zones"]:
+            act = dict(act, zones=[dict(act["zones"][0], name="other.example.org.")] + act["zones"][1:])
+        return act
+
+    def swap_records(r, act):  # rank 0 holds the LAST zones' records, rank 1 the first ones': ranges descend with the rank
+        other = slices[1 - r][1]["zones"]
+        return dict(act, zones=[dict(z, records=other[i]["records"]) for i, z in enumerate(act["zones"])])
+
+    assert sum(len(z["records"]) for z in slices[0][1]["zones"]) > 0 and sum(len(z["records"]) for z in slices[1][1]["zones"]) > 0
+    with pytest.raises(garecon.abi.GarError, match="zone table"):
+        run(rename_zone)
+    with pytest.raises(garecon.abi.GarError, match="whole zones"):
+        run(swap_records)
+    run(lambda r, act: act)  # the unmodified slices are fine
+
+
 def test_shards_are_balanced_and_disjoint(garecon, oracle, hostlib):
     objects, actual = randmodel.make(5, n_objects=400)
     got, parts = check(garecon, oracle, hostlib, objects, actual, 4)
