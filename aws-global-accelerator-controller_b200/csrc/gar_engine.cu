@@ -246,6 +246,42 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const u32 *keys, c
   }
 }
 
+// ------------------------------------------------------------------ snapshot validation on the device
+//
+// Every string reference must stay inside its slab, every CSR must be monotone and closed, enums in range, and the object
+// key layout rule must hold.  The checks run as tiny streaming kernels over the freshly copied tables (no host pass that
+// would compete with the PCIe copy for memory bandwidth); the first failing check id lands in a flag the load reads back
+// BEFORE any pipeline kernel can see the tables.
+struct FValStr {
+  const gar_str *col;
+  u64 slab_len;
+  u32 id;
+  u32 *flag;
+  __device__ void operator()(u32 i) const {
+    gar_str r = col[i];
+    if (GAR_STR_OFF(r) + GAR_STR_LEN(r) > slab_len) atomicMin(flag, id);
+  }
+};
+struct FValCsr {
+  const u32 *b;
+  u32 nparents, nchildren, id;
+  u32 *flag;
+  __device__ void operator()(u32 i) const {  // i in [0, nparents]
+    bool bad = (i == 0 && b[0] != 0) || (i < nparents && b[i + 1] < b[i]) || (i == nparents && b[nparents] != nchildren);
+    if (bad) atomicMin(flag, id);
+  }
+};
+struct FValObj {
+  gar_objects o;
+  u32 id_kind, id_key;
+  u32 *flag;
+  __device__ void operator()(u32 i) const {
+    if (o.obj_kind[i] > GAR_KIND_INGRESS) atomicMin(flag, id_kind);
+    u64 sep = GAR_STR_OFF(o.obj_ns[i]) + GAR_STR_LEN(o.obj_ns[i]);
+    if (GAR_STR_OFF(o.obj_name[i]) != sep + 1 || sep >= o.slab_len || o.slab[sep] != '/') atomicMin(flag, id_key);
+  }
+};
+
 // ------------------------------------------------------------------ engine
 
 struct DBuf {
@@ -292,6 +328,7 @@ struct gar_engine {
   DBuf d_status_ga, d_status_r53, d_derived, d_ops, d_tok_code, d_tok_name, d_tok_region, d_dport_begin, d_dports, d_scan_tiles, d_hist;
   DBuf d_derived_keys, d_key_rows, d_del_kind, d_del_key, d_del_slab;  // incremental mode
   DBuf d_egb[8];                                                      // EndpointGroupBinding tables
+  DBuf d_valid;                                                       // validation flag
   Pipeline<gar_engine> *pipe = nullptr;  // lives as long as the loaded snapshot: keeps digests + indexes resident
   // sharded mode (gar_shard.h)
   Sharder<gar_engine> *sharder = nullptr;
@@ -455,7 +492,7 @@ struct gar_engine {
   void *out_status_r53(u32 n) { return dev_ensure(d_status_r53, 4 * (size_t)(n + 1)); }
 };
 
-// ------------------------------------------------------------------ snapshot validation (host, copy mode only)
+// ------------------------------------------------------------------ host-side checks of small tables (bindings) and of pointers
 
 static void check_str_col(const char *name, const gar_str *col, size_t n, u64 slab_len) {
   if (n && !col) throw InvalidError{std::string(name) + " is NULL"};
@@ -473,111 +510,6 @@ static void check_csr(const char *name, const u32 *b, size_t nparents, size_t nc
 }
 static void check_ptr(const char *name, const void *p, size_t n) {
   if (n && !p) throw InvalidError{std::string(name) + " is NULL"};
-}
-
-// Host-side validation runs as a small task list over a few threads: at 10^6 objects there are ~4*10^7 references
-// to check, which single-threaded would cost more than the PCIe copy it overlaps with.
-struct Tasks {
-  std::vector<std::function<void()>> list;
-  void str_col(const char *name, const gar_str *col, size_t n, u64 slab_len) {
-    if (n && !col) throw InvalidError{std::string(name) + " is NULL"};
-    const size_t chunk = 1u << 19;
-    for (size_t b = 0; b < n; b += chunk) {
-      size_t e = b + chunk < n ? b + chunk : n;
-      list.push_back([=] { check_str_col(name, col + b, e - b, slab_len); });
-    }
-  }
-  void csr(const char *name, const u32 *b, size_t nparents, size_t nchildren) {
-    list.push_back([=] { check_csr(name, b, nparents, nchildren); });
-  }
-  void run() {
-    unsigned nt = std::thread::hardware_concurrency();
-    nt = nt < 1 ? 1 : (nt > 16 ? 16 : nt);
-    std::atomic<size_t> next{0};
-    std::exception_ptr err;
-    std::mutex em;
-    auto worker = [&] {
-      for (;;) {
-        size_t k = next.fetch_add(1);
-        if (k >= list.size()) return;
-        try {
-          list[k]();
-        } catch (...) {
-          std::lock_guard<std::mutex> lk(em);
-          if (!err) err = std::current_exception();
-        }
-      }
-    };
-    std::vector<std::thread> th;
-    for (unsigned t = 1; t < nt; t++) th.emplace_back(worker);
-    worker();
-    for (auto &t : th) t.join();
-    if (err) std::rethrow_exception(err);
-  }
-};
-
-static void validate(const gar_objects *o, const gar_actual *a) {
-  if (!o || !a) throw InvalidError{"NULL table struct"};
-  Tasks T;
-  size_t n = o->n_objects;
-  check_ptr("obj_kind", o->obj_kind, n);
-  check_ptr("obj_spec_type", o->obj_spec_type, n);
-  check_ptr("obj_flags", o->obj_flags, n);
-  check_ptr("objects.slab", o->slab, o->slab_len);
-  T.str_col("obj_ns", o->obj_ns, n, o->slab_len);
-  T.str_col("obj_name", o->obj_name, n, o->slab_len);
-  T.str_col("obj_ingress_class", o->obj_ingress_class, n, o->slab_len);
-  T.csr("obj_ann_begin", o->obj_ann_begin, n, o->n_ann);
-  T.csr("obj_lbi_begin", o->obj_lbi_begin, n, o->n_lbi);
-  T.csr("obj_port_begin", o->obj_port_begin, n, o->n_ports);
-  T.str_col("ann_key", o->ann_key, o->n_ann, o->slab_len);
-  T.str_col("ann_val", o->ann_val, o->n_ann, o->slab_len);
-  T.str_col("lbi_hostname", o->lbi_hostname, o->n_lbi, o->slab_len);
-  check_ptr("port_number", o->port_number, o->n_ports);
-  T.str_col("port_proto", o->port_proto, o->n_ports, o->slab_len);
-  if (n && (!o->obj_ns || !o->obj_name || !o->obj_kind)) throw InvalidError{"object columns are NULL"};
-  {
-    const size_t chunk = 1u << 19;
-    for (size_t b = 0; b < n; b += chunk) {
-      size_t e = b + chunk < n ? b + chunk : n;
-      T.list.push_back([=] {
-        for (size_t i = b; i < e; i++) {
-          if (o->obj_kind[i] > GAR_KIND_INGRESS) throw InvalidError{"obj_kind out of range"};
-          u64 sep = GAR_STR_OFF(o->obj_ns[i]) + GAR_STR_LEN(o->obj_ns[i]);
-          if (GAR_STR_OFF(o->obj_name[i]) != sep + 1 || sep >= o->slab_len || o->slab[sep] != '/')
-            throw InvalidError{"objects layout rule violated: obj_ns and obj_name must be slices of one \"ns/name\" key string"};
-        }
-      });
-    }
-  }
-  check_ptr("actual.slab", a->slab, a->slab_len);
-  T.str_col("lb_region", a->lb_region, a->n_lbs, a->slab_len);
-  T.str_col("lb_name", a->lb_name, a->n_lbs, a->slab_len);
-  T.str_col("lb_dns", a->lb_dns, a->n_lbs, a->slab_len);
-  T.str_col("lb_arn", a->lb_arn, a->n_lbs, a->slab_len);
-  check_ptr("lb_state", a->lb_state, a->n_lbs);
-  T.str_col("acc_name", a->acc_name, a->n_accels, a->slab_len);
-  T.str_col("acc_dns", a->acc_dns, a->n_accels, a->slab_len);
-  check_ptr("acc_enabled", a->acc_enabled, a->n_accels);
-  T.csr("acc_tag_begin", a->acc_tag_begin, a->n_accels, a->n_tags);
-  T.csr("acc_lis_begin", a->acc_lis_begin, a->n_accels, a->n_listeners);
-  T.str_col("tag_key", a->tag_key, a->n_tags, a->slab_len);
-  T.str_col("tag_val", a->tag_val, a->n_tags, a->slab_len);
-  check_ptr("lis_proto", a->lis_proto, a->n_listeners);
-  T.csr("lis_pr_begin", a->lis_pr_begin, a->n_listeners, a->n_port_ranges);
-  T.csr("lis_eg_begin", a->lis_eg_begin, a->n_listeners, a->n_egs);
-  check_ptr("pr_from", a->pr_from, a->n_port_ranges);
-  T.csr("eg_ep_begin", a->eg_ep_begin, a->n_egs, a->n_endpoints);
-  T.str_col("ep_id", a->ep_id, a->n_endpoints, a->slab_len);
-  T.str_col("zone_name", a->zone_name, a->n_zones, a->slab_len);
-  T.csr("zone_rec_begin", a->zone_rec_begin, a->n_zones, a->n_records);
-  T.str_col("rec_name", a->rec_name, a->n_records, a->slab_len);
-  check_ptr("rec_type", a->rec_type, a->n_records);
-  check_ptr("rec_has_alias", a->rec_has_alias, a->n_records);
-  T.str_col("rec_alias_dns", a->rec_alias_dns, a->n_records, a->slab_len);
-  T.csr("rec_val_begin", a->rec_val_begin, a->n_records, a->n_values);
-  T.str_col("val_value", a->val_value, a->n_values, a->slab_len);
-  T.run();
 }
 
 // bytes of the input tables, each array counted once (roofline numerator)
@@ -600,6 +532,68 @@ static u64 table_bytes(const gar_objects *o, const gar_actual *a) {
 }
 
 // ------------------------------------------------------------------ load
+
+static void validate_pointers(const gar_objects *o, const gar_actual *a) {
+  size_t n = o->n_objects;
+  check_ptr("obj_kind", o->obj_kind, n); check_ptr("obj_spec_type", o->obj_spec_type, n); check_ptr("obj_flags", o->obj_flags, n);
+  check_ptr("obj_ns", o->obj_ns, n); check_ptr("obj_name", o->obj_name, n); check_ptr("obj_ingress_class", o->obj_ingress_class, n);
+  check_ptr("obj_ann_begin", o->obj_ann_begin, 1); check_ptr("obj_lbi_begin", o->obj_lbi_begin, 1); check_ptr("obj_port_begin", o->obj_port_begin, 1);
+  check_ptr("ann_key", o->ann_key, o->n_ann); check_ptr("ann_val", o->ann_val, o->n_ann); check_ptr("lbi_hostname", o->lbi_hostname, o->n_lbi);
+  check_ptr("port_number", o->port_number, o->n_ports); check_ptr("port_proto", o->port_proto, o->n_ports); check_ptr("objects.slab", o->slab, o->slab_len);
+  check_ptr("lb_region", a->lb_region, a->n_lbs); check_ptr("lb_name", a->lb_name, a->n_lbs); check_ptr("lb_dns", a->lb_dns, a->n_lbs);
+  check_ptr("lb_arn", a->lb_arn, a->n_lbs); check_ptr("lb_state", a->lb_state, a->n_lbs);
+  check_ptr("acc_name", a->acc_name, a->n_accels); check_ptr("acc_dns", a->acc_dns, a->n_accels); check_ptr("acc_enabled", a->acc_enabled, a->n_accels);
+  check_ptr("acc_tag_begin", a->acc_tag_begin, 1); check_ptr("acc_lis_begin", a->acc_lis_begin, 1);
+  check_ptr("tag_key", a->tag_key, a->n_tags); check_ptr("tag_val", a->tag_val, a->n_tags); check_ptr("lis_proto", a->lis_proto, a->n_listeners);
+  check_ptr("lis_pr_begin", a->lis_pr_begin, 1); check_ptr("lis_eg_begin", a->lis_eg_begin, 1); check_ptr("pr_from", a->pr_from, a->n_port_ranges);
+  check_ptr("eg_ep_begin", a->eg_ep_begin, 1); check_ptr("ep_id", a->ep_id, a->n_endpoints);
+  check_ptr("zone_name", a->zone_name, a->n_zones); check_ptr("zone_rec_begin", a->zone_rec_begin, 1);
+  check_ptr("rec_name", a->rec_name, a->n_records); check_ptr("rec_type", a->rec_type, a->n_records); check_ptr("rec_has_alias", a->rec_has_alias, a->n_records);
+  check_ptr("rec_alias_dns", a->rec_alias_dns, a->n_records); check_ptr("rec_val_begin", a->rec_val_begin, 1);
+  check_ptr("val_value", a->val_value, a->n_values); check_ptr("actual.slab", a->slab, a->slab_len);
+}
+
+// runs on e->stream after the copies; throws InvalidError naming the first failing check
+static void device_validate(gar_engine *e) {
+  const gar_objects &o = e->T.o;
+  const gar_actual &a = e->T.a;
+  u32 *flag = (u32 *)e->dev_ensure(e->d_valid, 64);
+  CK(cudaMemsetAsync(flag, 0xFF, 4, e->stream));
+  std::vector<const char *> names;
+  auto str = [&](const char *name, const gar_str *col, u32 n, u64 slab_len) {
+    names.push_back(name);
+    e->for_each("validate", n, FValStr{col, slab_len, (u32)names.size() - 1, flag});
+  };
+  auto csr = [&](const char *name, const u32 *b, u32 nparents, u32 nchildren) {
+    names.push_back(name);
+    e->for_each("validate", nparents + 1, FValCsr{b, nparents, nchildren, (u32)names.size() - 1, flag});
+  };
+  const u32 n = o.n_objects;
+  names.push_back("obj_kind out of range");
+  names.push_back("objects layout rule violated: obj_ns and obj_name must be slices of one \"ns/name\" key string");
+  str("obj_ns", o.obj_ns, n, o.slab_len); str("obj_name", o.obj_name, n, o.slab_len); str("obj_ingress_class", o.obj_ingress_class, n, o.slab_len);
+  e->for_each("validate", n, FValObj{o, 0, 1, flag});
+  csr("obj_ann_begin", o.obj_ann_begin, n, o.n_ann); csr("obj_lbi_begin", o.obj_lbi_begin, n, o.n_lbi); csr("obj_port_begin", o.obj_port_begin, n, o.n_ports);
+  str("ann_key", o.ann_key, o.n_ann, o.slab_len); str("ann_val", o.ann_val, o.n_ann, o.slab_len); str("lbi_hostname", o.lbi_hostname, o.n_lbi, o.slab_len);
+  str("port_proto", o.port_proto, o.n_ports, o.slab_len);
+  str("lb_region", a.lb_region, a.n_lbs, a.slab_len); str("lb_name", a.lb_name, a.n_lbs, a.slab_len); str("lb_dns", a.lb_dns, a.n_lbs, a.slab_len);
+  str("lb_arn", a.lb_arn, a.n_lbs, a.slab_len); str("acc_name", a.acc_name, a.n_accels, a.slab_len); str("acc_dns", a.acc_dns, a.n_accels, a.slab_len);
+  csr("acc_tag_begin", a.acc_tag_begin, a.n_accels, a.n_tags); csr("acc_lis_begin", a.acc_lis_begin, a.n_accels, a.n_listeners);
+  str("tag_key", a.tag_key, a.n_tags, a.slab_len); str("tag_val", a.tag_val, a.n_tags, a.slab_len);
+  csr("lis_pr_begin", a.lis_pr_begin, a.n_listeners, a.n_port_ranges); csr("lis_eg_begin", a.lis_eg_begin, a.n_listeners, a.n_egs);
+  csr("eg_ep_begin", a.eg_ep_begin, a.n_egs, a.n_endpoints); str("ep_id", a.ep_id, a.n_endpoints, a.slab_len);
+  str("zone_name", a.zone_name, a.n_zones, a.slab_len); csr("zone_rec_begin", a.zone_rec_begin, a.n_zones, a.n_records);
+  str("rec_name", a.rec_name, a.n_records, a.slab_len); str("rec_alias_dns", a.rec_alias_dns, a.n_records, a.slab_len);
+  csr("rec_val_begin", a.rec_val_begin, a.n_records, a.n_values); str("val_value", a.val_value, a.n_values, a.slab_len);
+  u32 bad = 0xFFFFFFFFu;
+  e->download(&bad, flag, 4);  // synchronises e->stream: copies and checks are complete
+  if (bad != 0xFFFFFFFFu) {
+    std::string nm = bad < names.size() ? names[bad] : "table";
+    if (bad >= 2) nm += bad < names.size() && strstr(names[bad], "_begin") ? ": CSR is not monotone, does not start at 0 or does not end at the child count"
+                                                                          : ": string reference outside the slab";
+    throw InvalidError{nm};
+  }
+}
 
 template <class Tp>
 static const Tp *upload(gar_engine *e, const Tp *host, size_t count, size_t pad_bytes = 0) {
@@ -667,16 +661,9 @@ static void do_load(gar_engine *e, const gar_objects *o, const gar_actual *a) {
   T.a.val_value = upload(e, a->val_value, a->n_values);
   T.a.slab = upload(e, a->slab, a->slab_len, GAR_SLAB_PAD);
   CK(cudaEventRecord(e->ev[1], e->stream));
-  // Host-side validation of every reference and CSR runs while the copies are in flight (they are asynchronous
-  // when the caller's buffers are pinned); a malformed snapshot is rejected before any kernel can see it.
-  try {
-    validate(o, a);
-  } catch (...) {
-    cudaStreamSynchronize(e->stream);
-    throw;
-  }
-  CK(cudaStreamSynchronize(e->stream));  // caller may free its buffers when we return
-  CK(cudaEventElapsedTime(&e->ms_h2d, e->ev[0], e->ev[1]));
+  validate_pointers(o, a);  // NULL checks only; the contents are checked on the device, below
+  device_validate(e);
+  CK(cudaEventElapsedTime(&e->ms_h2d, e->ev[0], e->ev[1]));  // device_validate synchronised: the caller may free its buffers
   e->input_bytes = table_bytes(o, a);
   e->loaded = true;
   e->attached = false;
@@ -931,6 +918,7 @@ void gar_engine_destroy(gar_engine *e) {
     for (auto &b : ar) cudaFree(b.p);
   for (DBuf *b : {&e->d_derived_keys, &e->d_key_rows, &e->d_del_kind, &e->d_del_key, &e->d_del_slab}) cudaFree(b->p);
   for (auto &b : e->d_egb) cudaFree(b.p);
+  cudaFree(e->d_valid.p);
   for (DBuf *b : {&e->cluster_dev, &e->d_status_ga, &e->d_status_r53, &e->d_derived, &e->d_ops, &e->d_tok_code, &e->d_tok_name, &e->d_tok_region,
                   &e->d_dport_begin, &e->d_dports, &e->d_scan_tiles, &e->d_hist})
     cudaFree(b->p);
