@@ -88,10 +88,34 @@ class DistExchange:
         self.g = int(shard.n_ranks)
         self.keep = []
         self.bytes_sent = 0
+        self.check_errors = True  # one tiny all-reduce after the calls that can fail on one rank only (route, unpack)
+
+    def _agree(self, err):
+        """All ranks learn whether any rank failed its last engine call (otherwise the healthy ones would wait forever in the
+        next collective).  Raises on every rank."""
+        torch, dist = self.torch, self.dist
+        flag = torch.tensor([1 if err is not None else 0], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        if int(flag.item()):
+            if err is not None:
+                raise err
+            raise RuntimeError("sharded exchange aborted: another rank reported an engine error")
+
+    def _guard(self, fn):
+        err, out = None, None
+        try:
+            out = fn()
+        except Exception as ex:  # noqa: BLE001 - reported to every rank, then re-raised
+            err = ex
+        if self.check_errors:
+            self._agree(err)
+        elif err is not None:
+            raise err
+        return out
 
     def round(self, rnd: int):
         torch, dist = self.torch, self.dist
-        meta, nbytes = self.e.shard_route(self.shard, rnd)
+        meta, nbytes = self._guard(lambda: self.e.shard_route(self.shard, rnd))
         # meta rows: a fixed-size all-to-all (int64 view of the uint64 words)
         m_out = torch.from_numpy(meta.view(np.int64)).to(self.device)
         m_in = torch.empty_like(m_out)
@@ -107,7 +131,7 @@ class DistExchange:
             torch.cuda.current_stream().synchronize()  # the engine reads `recv` on its own stream
         self.keep.append(recv)
         self.bytes_sent += sum(in_sizes)
-        self.e.shard_unpack(rnd, recv.data_ptr(), recv_meta)
+        self._guard(lambda: self.e.shard_unpack(rnd, recv.data_ptr(), recv_meta))
 
     def run(self):
         """Both rounds; afterwards the engine holds this rank's home sub-snapshot (diff() works)."""

@@ -46,6 +46,8 @@ def main():
         import randmodel
         objects, actual = randmodel.make(int(sys.argv[3]), n_objects=int(sys.argv[4]))
         objs_r, act_r, sh = shard.slice_model(objects, actual, world)[rank]
+        if len(sys.argv) > 5 and sys.argv[5] == "badzone" and rank == world - 1:  # contract violation on ONE rank only
+            act_r = dict(act_r, zones=[dict(act_r["zones"][0], name="other.example.org.")] + act_r["zones"][1:])
         snap = garecon.pack(objs_r, act_r)
         n_total = len(objects)
     else:
@@ -56,6 +58,20 @@ def main():
     e = garecon.Engine(cluster_name="default", lib=lib, device=device)
     e.load(snap)
     x = shard.DistExchange(e, sh, dev)
+    if len(sys.argv) > 5 and sys.argv[5] == "badzone":
+        # every rank must raise (the failing one its own error, the others the agreed abort): nobody may hang in a collective
+        try:
+            x.run()
+            raised = ""
+        except Exception as ex:  # noqa: BLE001
+            raised = type(ex).__name__ + ": " + str(ex)[:80]
+        allr = [None] * world
+        dist.all_gather_object(allr, raised)
+        if rank == 0:
+            print(json.dumps({"raised": allr}), flush=True)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     x.run()
     part = e.diff()
     payload = dict(obj_gid=part.obj_gid, status_ga=part.status_ga, status_r53=part.status_r53, derived=part.derived, ops=part.ops,

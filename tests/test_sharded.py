@@ -199,6 +199,15 @@ def test_two_ranks_gloo_all_to_all():
     assert min(d["sent"]) > 1000
 
 
+def test_an_engine_error_on_one_rank_aborts_every_rank():
+    """A contract violation only one rank can see must not leave the others waiting in the next collective."""
+    import __graft_entry__ as ge
+    ge.build_hostsim()
+    d = _launch(2, 29543, "gloo", "randmodel", 2, 40, "badzone", timeout=300)
+    assert len(d["raised"]) == 2 and all(d["raised"])
+    assert any("zone table" in r for r in d["raised"])
+
+
 @pytest.mark.gpu
 def test_nccl_ranks_equal_unsharded():
     """One process per GPU, blobs over NCCL: needs >= 2 GPUs (the single-GPU test box skips it; run with gpurun --gpus N)."""
