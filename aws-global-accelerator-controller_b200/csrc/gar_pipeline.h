@@ -83,10 +83,14 @@ struct FExpand {
 };
 // record row -> zone row, the hash of the record name (every (zone, name) key is derived from it), and its values: value ->
 // record, owner-value classification.  One pass over the record table: a record's name and values are neighbours in the slab,
-// so they share DRAM sectors.
+// so they share DRAM sectors.  A record set with MANY values (one hot TXT name claimed by thousands of owners) is not walked
+// by its one thread: it goes on a list that FClassifyBigRecords works through with whole blocks.
+constexpr u32 REC_INLINE_VALUES = 32;   // more values than this: a whole block works on the record
+constexpr u32 REC_HUGE_VALUES = 4096;   // more than this: the whole grid does
 struct FPrepareRecord {
   DevTables T;
   Work W;
+  u32 *big, *huge;  // [0] = count, then record rows
   GAR_HD void operator()(u32 r) const {
     u32 lo = 0, hi = T.a.n_zones;
     while (hi - lo > 1) {
@@ -96,9 +100,44 @@ struct FPrepareRecord {
     }
     W.rec_zone[r] = lo;
     W.rec_name_hash[r] = gar_hash(mkstr(T.a.slab, T.a.rec_name[r]));
-    for (u32 v = T.a.rec_val_begin[r]; v < T.a.rec_val_begin[r + 1]; v++) {
+    u32 v0 = T.a.rec_val_begin[r], v1 = T.a.rec_val_begin[r + 1];
+    if (v1 - v0 > REC_INLINE_VALUES) {
+      u32 *list = v1 - v0 > REC_HUGE_VALUES ? huge : big;
+#if defined(__CUDA_ARCH__)
+      list[1 + atomicAdd(list, 1u)] = r;
+#else
+      list[1 + list[0]++] = r;
+#endif
+      return;
+    }
+    for (u32 v = v0; v < v1; v++) {
       W.val_rec[v] = r;
       classify_value(T, W, v);
+    }
+  }
+};
+// fixed grid of BIG_BLOCKS x 256 threads: block b takes big records b, b + BIG_BLOCKS, ... and its threads stride over the
+// values; the (few) huge records are strided over by the whole grid
+constexpr u32 BIG_BLOCKS = 592;  // 4 x 148 SMs
+struct FClassifyBigRecords {
+  DevTables T;
+  Work W;
+  const u32 *big, *huge;
+  GAR_HD void operator()(u32 i) const {
+    const u32 blk = i >> 8, tid = i & 255u, nbig = big[0], nhuge = huge[0];
+    for (u32 k = blk; k < nbig; k += BIG_BLOCKS) {
+      u32 r = big[1 + k];
+      for (u32 v = T.a.rec_val_begin[r] + tid; v < T.a.rec_val_begin[r + 1]; v += 256) {
+        W.val_rec[v] = r;
+        classify_value(T, W, v);
+      }
+    }
+    for (u32 k = 0; k < nhuge; k++) {
+      u32 r = huge[1 + k];
+      for (u32 v = T.a.rec_val_begin[r] + i; v < T.a.rec_val_begin[r + 1]; v += BIG_BLOCKS * 256) {
+        W.val_rec[v] = r;
+        classify_value(T, W, v);
+      }
     }
   }
 };
@@ -668,7 +707,14 @@ struct Pipeline {
     if (n) be.for_each("classify_objects", n, FClassify{T, W, derived_public, nullptr, errflag});
     if (nlbi) be.for_each("tokenise_hostnames", nlbi, FTokenise{T, W});
     if (nacc) be.for_each("digest_accelerators", nacc, FDigestAccel{T, W});
-    if (nrec) be.for_each("prepare_records", nrec, FPrepareRecord{T, W});  // includes the records' values
+    if (nrec) {  // includes the records' values
+      u32 *big = (u32 *)be.ensure(S_SORT_KEYS, 4 * (size_t)(nval / REC_INLINE_VALUES + 2));
+      u32 *huge = (u32 *)be.ensure(S_SORT_VALS, 4 * (size_t)(nval / REC_HUGE_VALUES + 2));
+      be.fill32(big, 0, 1);
+      be.fill32(huge, 0, 1);
+      be.for_each("prepare_records", nrec, FPrepareRecord{T, W, big, huge});
+      if (nval > REC_INLINE_VALUES) be.for_each("prepare_records", BIG_BLOCKS * 256, FClassifyBigRecords{T, W, big, huge});
+    }
   }
   // index build that does not assume small buckets: fast per-bucket build first, stable radix rebuild if a bucket overflowed
   template <class RowF>

@@ -91,3 +91,15 @@ def test_reprepare_flag_runs_the_complete_pipeline_every_time(garecon, synth):
         b = e.diff()
     assert a.diff(b) == []
     assert a.kernel_launches == b.kernel_launches
+
+
+@pytest.mark.parametrize("cfg", [2, 3, 5])
+def test_no_performance_cliff(garecon, synth, cfg):
+    """Not a benchmark: a loose bound that catches algorithmic cliffs (a per-record loop over a 10^5-value hot TXT set once
+    cost 70x on config 5).  At 10^6 objects a complete diff takes 3-5 ms; allow 10x."""
+    snap = synth.generate(cfg, 1_000_000)
+    with garecon.Engine(cluster_name=snap.cluster, reprepare=True) as e:
+        e.load(snap)
+        e.diff_device()
+        ms = min(e.diff_device().ms_kernels for _ in range(3))
+    assert ms < 50.0, f"config {cfg}: {ms:.1f} ms for 10^6 objects"

@@ -114,3 +114,14 @@ def test_listen_ports_fuzz(garecon, oracle, engine):
     got = engine.diff()
     want = oracle.diff(snap, "default", mode=1)
     assert got.diff(want) == [], got.describe_first_mismatch(want)
+
+
+def test_huge_value_lists(garecon, oracle, engine):
+    """Record sets with > 32 and > 4096 values: the block-wide and grid-wide branches of the record pass."""
+    import hotkeys
+    objects, actual = hotkeys.make(ndup_acc=3, ndup_alias=2, ndup_val=2100)
+    snap = garecon.pack(objects, actual)
+    engine.load(snap)
+    got = engine.diff()
+    want = oracle.diff(snap, "default", mode=1)
+    assert got.diff(want) == [], got.describe_first_mismatch(want)

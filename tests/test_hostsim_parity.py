@@ -150,3 +150,16 @@ def test_hostsim_port_multisets(garecon, oracle, hostsim):
     want_cs = oracle.diff(snap, "default", mode=0)
     assert got.diff(want_cs) == [], got.describe_first_mismatch(want_cs)
     assert 30 < len(got.ops) < 300
+
+
+def test_hostsim_huge_value_lists(garecon, oracle, hostsim):
+    """A TXT record set with > 4096 values takes the grid-wide branch of the record pass (FClassifyBigRecords); one with > 32
+    values the block-wide one."""
+    import hotkeys
+    objects, actual = hotkeys.make(ndup_acc=3, ndup_alias=2, ndup_val=2100)
+    assert max(len(r.get("values", [])) for r in actual["zones"][0]["records"]) > 4096
+    snap = garecon.pack(objects, actual)
+    hostsim.load(snap)
+    got = hostsim.diff()
+    want = oracle.diff(snap, "default", mode=1)
+    assert got.diff(want) == [], got.describe_first_mismatch(want)
