@@ -38,7 +38,8 @@ enum ShLevel { L_OBJ, L_ANN, L_LBI, L_PORT, L_ACC, L_TAG, L_LIS, L_PR, L_EG, L_E
 static_assert(2 * L_NLEVELS + 1 <= GAR_SHARD_META_WORDS, "meta row too small");
 constexpr int SH_MAX_STR = 4, SH_MAX_U8 = 3, SH_MAX_U32 = 1, SH_MAX_CHILD = 3;
 enum { SH_ARENA_PLAN = 0, SH_ARENA_DIR = 1, SH_ARENA_HOME = 2 };
-constexpr u32 SH_DROP = 255;  // destination of a row nobody needs
+constexpr u32 SH_DROP = 255;    // destination of a row nobody needs
+constexpr u32 SH_FOLLOW = 254;  // child_dest value: the child goes wherever its parent goes
 
 struct LevelSchema {
   int n_str, n_u8, n_u32, has_gid, n_child;
@@ -198,6 +199,15 @@ struct FShKeyProbe {
     home[l] = shard_of(W.okey_hash[lbi_obj[l]], G);
   }
 };
+// a stub only answers ListGlobalAcceleratorByHostname: of its tags only the three that lookup reads travel with it
+struct FShStubTagKeep {
+  DevTables T;
+  u8 *keep;
+  GAR_HD void operator()(u32 t) const {
+    Str k = mkstr(T.a.slab, T.a.tag_key[t]);
+    keep[t] = (STREQ_LIT(k, TAG_MANAGED) || STREQ_LIT(k, TAG_THOST) || STREQ_LIT(k, TAG_CLUSTER)) ? (u8)SH_FOLLOW : (u8)SH_DROP;
+  }
+};
 struct FShValDest {
   Work W;
   u32 G;
@@ -299,7 +309,7 @@ struct FShChildCount {
       const u8 *cd = src.child_dest[link];
       if (cd) {
         u32 d = dest_of(j, P.row_off, G);
-        for (u32 ch = b0; ch < b1; ch++) c += cd[ch] == d;
+        for (u32 ch = b0; ch < b1; ch++) c += cd[ch] == d || cd[ch] == SH_FOLLOW;
       } else {
         c = b1 - b0;
       }
@@ -321,7 +331,7 @@ struct FShChildFill {
     if (cd) {
       u32 d = dest_of(j, P.row_off, G);
       for (u32 ch = b0; ch < b1; ch++)
-        if (cd[ch] == d) child_sel[pos++] = ch;
+        if (cd[ch] == d || cd[ch] == SH_FOLLOW) child_sel[pos++] = ch;
     } else {
       for (u32 ch = b0; ch < b1; ch++) child_sel[pos++] = ch;
     }
@@ -727,7 +737,11 @@ struct Sharder {
     x = LevelSrc{}; x.str[0] = O.port_proto; x.u32c[0] = (const u32 *)O.port_number; x.slab = O.slab; x.n = O.n_ports; src[L_PORT] = x;
     x = LevelSrc{}; x.str[0] = A.acc_name; x.str[1] = A.acc_dns; x.u8c[0] = A.acc_enabled; x.gid_base = c.acc_base;
     x.child_begin[0] = A.acc_tag_begin; x.child_begin[1] = A.acc_lis_begin; x.slab = A.slab; x.n = A.n_accels; src[L_ACC] = x;
-    x.child_begin[1] = nullptr; src[L_STUB] = x;
+    x.child_begin[1] = nullptr;
+    u8 *stub_tag_keep = alloc<u8>(SH_ARENA_PLAN, A.n_tags);
+    if (A.n_tags) be.for_each("shard_stub_tag_keep", A.n_tags, FShStubTagKeep{S, stub_tag_keep});
+    x.child_dest[0] = stub_tag_keep;
+    src[L_STUB] = x;
     x = LevelSrc{}; x.str[0] = A.tag_key; x.str[1] = A.tag_val; x.slab = A.slab; x.n = A.n_tags; src[L_TAG] = x; src[L_STUBTAG] = x;
     x = LevelSrc{}; x.u8c[0] = A.lis_proto; x.gid_base = c.lis_base; x.child_begin[0] = A.lis_pr_begin; x.child_begin[1] = A.lis_eg_begin;
     x.slab = A.slab; x.n = A.n_listeners; src[L_LIS] = x;

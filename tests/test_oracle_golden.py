@@ -1,17 +1,21 @@
 """Pins the CPU oracle against every known-answer vector the reference's own unit tests hold for the path
-(SURVEY.md §8c).  Each table below is the reference's table, cited file:line."""
+(SURVEY.md §8c).  The reference's tables live in tests/golden/reference_vectors.json (transcribed from the Go test files,
+file:line per table); the cases further down that are NOT from the reference say so."""
+import json
+from pathlib import Path
+
 import pytest
 
 TCP, UDP = 0, 1
+GOLDEN = json.loads((Path(__file__).resolve().parent / "golden" / "reference_vectors.json").read_text())
+
+
+def _cases(name):
+    return [tuple(c) for c in GOLDEN[name]["cases"]]
 
 
 # pkg/cloudprovider/aws/load_balancer_test.go:17-40  TestGetLBNameFromHostname
-LB_HOSTNAMES = [
-    ("aa5849cde256f49faa7487bb433155b7-3f43353a6cb6f633.elb.ap-northeast-1.amazonaws.com", "aa5849cde256f49faa7487bb433155b7", "ap-northeast-1", 2),
-    ("test-b6cdc5fbd1d6fa43.elb.ap-northeast-1.amazonaws.com", "test", "ap-northeast-1", 2),
-    ("k8s-default-h3poteto-f1f41628db-201899272.ap-northeast-1.elb.amazonaws.com", "k8s-default-h3poteto-f1f41628db", "ap-northeast-1", 1),
-    ("internal-k8s-default-h3poteto-35ca57562f-777774719.ap-northeast-1.elb.amazonaws.com", "k8s-default-h3poteto-35ca57562f", "ap-northeast-1", 0),
-]
+LB_HOSTNAMES = _cases("get_lb_name_from_hostname")
 
 
 @pytest.mark.parametrize("hostname,name,region,code", LB_HOSTNAMES)
@@ -20,8 +24,9 @@ def test_get_lb_name_from_hostname(oracle, hostname, name, region, code):
 
 
 # pkg/cloudprovider/provider_test.go:14-19  TestDetectCloudProvider
-def test_detect_cloud_provider(oracle):
-    assert oracle.detect_cloud_provider("aa5849cde256f49faa7487bb433155b7-3f43353a6cb6f633.elb.ap-northeast-1.amazonaws.com") == 0
+@pytest.mark.parametrize("hostname,code", _cases("detect_cloud_provider"))
+def test_detect_cloud_provider(oracle, hostname, code):
+    assert oracle.detect_cloud_provider(hostname) == code
 
 
 # hand-simulated vectors recorded in SURVEY.md §8.3 quirk 2 (derived from load_balancer.go:32-93)
@@ -44,14 +49,7 @@ def test_detect_cloud_provider_edges(oracle):
 
 
 # pkg/cloudprovider/aws/global_accelerator_test.go:22-146  TestListenerProtocolChange
-PROTOCOL_CASES = [
-    (UDP, ["UDP"], False),
-    (TCP, ["TCP", "TCP"], False),
-    (TCP, ["UDP", "TCP"], False),
-    (TCP, ["UDP"], True),
-    (TCP, ["UDP", "UDP"], True),
-    (TCP, ["TCP", "UDP"], True),
-]
+PROTOCOL_CASES = _cases("listener_protocol_change")
 
 
 @pytest.mark.parametrize("listener,protos,changed", PROTOCOL_CASES)
@@ -60,14 +58,7 @@ def test_listener_protocol_change(oracle, listener, protos, changed):
 
 
 # global_accelerator_test.go:164-335  TestListenerPortChanged
-PORT_CASES = [
-    ([80], [80], False),
-    ([80, 443, 8080], [443, 8080, 80], False),
-    ([80], [443], True),
-    ([80, 8080], [443, 8080], True),
-    ([80, 8080], [443, 8080, 8081], True),
-    ([80, 443, 8080], [443], True),
-]
+PORT_CASES = _cases("listener_port_changed")
 
 
 @pytest.mark.parametrize("listener,svc,changed", PORT_CASES)
@@ -105,19 +96,25 @@ def test_listener_for_ingress(garecon, oracle):
     assert oracle.parse_listen_ports('[{"HTTP": 80}, {"HTTPS": 443}]') == [80, 443]
 
 
-def test_e2e_listen_ports_fixture(oracle):
+@pytest.mark.parametrize("val,ports", _cases("e2e_listen_ports"))
+def test_e2e_listen_ports_fixture(oracle, val, ports):
     # local_e2e/pkg/fixtures/ingress.go:18 + local_e2e/e2e_test.go:192-205: exactly one port range 443-443
-    assert oracle.parse_listen_ports('[{"HTTPS":443}]') == [443]
+    assert oracle.parse_listen_ports(val) == ports
+
+
+@pytest.mark.parametrize("annotations,backend_ports,ports,proto", _cases("listener_for_ingress"))
+def test_listener_for_ingress_table(garecon, oracle, annotations, backend_ports, ports, proto):
+    """The reference's three TestListenerForIngress cases through the full oracle on a packed one-Ingress snapshot."""
+    s = _ingress(garecon, annotations, backend_ports)
+    cs = oracle.diff(s)
+    from_ann = bool(cs.derived[0] & garecon.abi.DV_PORTS_FROM_ANN)
+    got = list(cs.dports) if from_ann else list(s.arrays["port_number"])
+    assert got == ports and bool(cs.derived[0] & garecon.abi.DV_PROTO_UDP) == bool(proto)
 
 
 # pkg/cloudprovider/aws/route53_test.go:19-85  TestFindARecord
 A, CNAME = 1, 3
-FIND_A = [
-    (["foo.example.com.", "bar.example.com."], [CNAME, CNAME], "foo.example.com", -1),
-    (["foo.example.com.", "bar.example.com."], [A, A], "baz.example.com", -1),
-    (["foo.example.com.", "bar.example.com."], [A, A], "bar.example.com", 1),
-    (["\\052.example.com.", "bar.example.com."], [A, A], "*.example.com", 0),
-]
+FIND_A = _cases("find_a_record")
 
 
 @pytest.mark.parametrize("names,types,hostname,idx", FIND_A)
@@ -126,20 +123,13 @@ def test_find_a_record(oracle, names, types, hostname, idx):
 
 
 # route53_test.go:101-135  TestNeedRecordsUpdate
-def test_need_records_update(oracle):
-    assert oracle.need_records_update(False, "", "") is True
-    assert oracle.need_records_update(True, "foo.example.com.", "bar.example.com") is True
-    assert oracle.need_records_update(True, "foo.example.com.", "foo.example.com") is False
+@pytest.mark.parametrize("has_alias,alias_dns,accel_dns,expected", _cases("need_records_update"))
+def test_need_records_update(oracle, has_alias, alias_dns, accel_dns, expected):
+    assert oracle.need_records_update(has_alias, alias_dns, accel_dns) is expected
 
 
 # route53_test.go:150-175  TestParentDomain
-@pytest.mark.parametrize("hostname,parent", [
-    ("h3poteto-test.example.com", "example.com"),
-    ("h3poteto-test.foo.example.com", "foo.example.com"),
-    ("example.com", "com"),
-    ("com", ""),
-    (".", ""),
-])
+@pytest.mark.parametrize("hostname,parent", _cases("parent_domain"))
 def test_parent_domain(oracle, hostname, parent):
     assert oracle.parent_domain(hostname) == parent
 
