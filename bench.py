@@ -151,7 +151,30 @@ def kernel_byte_models(o, a, n_ops_ga_obj: int, n_pairs: int, frac_ga: float):
     av = _np_col(o.ann_val, o.n_ann, np.uint64) >> np.uint64(40)
     ann_r53 = int(av[ak == 63].sum())  # aws-global-accelerator-controller.h3poteto.dev/route53-hostname (63 bytes)
     r53 = ann_r53 + n_pairs * ((4 + 8) + (1 + 4 + 4) + 32 + zone_name_per + 32 + key_bytes / max(n, 1) + name_bytes_per_rec + 16 + alias_bytes_per_rec + acc_dns_per + 8 + 8 + 1 + 16)
-    return {"ga_objects": int(ga), "r53_pairs": int(r53)}
+    models = {"ga_objects": int(ga), "r53_pairs": int(r53)}
+    # ---- the other stages: input bytes each must read once + output bytes it writes (same rules: no re-reads, no scratch)
+    ann_key_refs = 8 * o.n_ann
+    known_key_bytes = 1024  # interned annotation keys: a handful of distinct strings
+    models["classify_objects"] = int(n * (3 + 3 * 8 + 3 * 4) + ann_key_refs + 8 * o.n_ann + known_key_bytes + key_bytes + n * (4 + 8 + 4 * 8 + 4))
+    models["tokenise_hostnames"] = int(host_bytes + 8 * o.n_lbi + 17 * o.n_lbi)
+    sys_tag_bytes = int(tv[(tk == 28) | (tk == 38) | (tk == 41) | (tk == 30)].sum())  # owner, target-hostname, managed, cluster
+    models["digest_accelerators"] = int(a.n_accels * (2 * 4 + 2 * 8 + 1) + 16 * a.n_tags + sys_tag_bytes + a.n_listeners * (1 + 8) + 4 * a.n_port_ranges
+                                        + 4 * a.n_egs + 8 * a.n_endpoints + a.n_accels * (64 + 5 * 8 + 2 * 8 + 4))
+    name_bytes = L(a.rec_name, nrec)
+    models["prepare_records"] = int(name_bytes + nrec * (8 + 4) + val_bytes + 8 * nval + nrec * (4 + 8) + nval * (4 + 1 + 8 + 8))
+    n_owner_vals = nval  # generator: every TXT value is an owner value (orphans and foreign clusters included)
+    models["value_joins"] = int(n_owner_vals * ((1 + 8 + 8 + 4) + (8 + 32 + 2 * name_bytes_per_rec) + (8 + 32 + 2 * key_bytes / max(n, 1)) + 16 + 1))
+    # index build: per indexed row one 32-byte entry written (+ 32-byte temporary written and read, counted as scratch: not here),
+    # the row's key hash / refs read (~24 B), 4 B per bucket
+    idx_rows_total = a.n_lbs + 2 * a.n_accels + a.n_zones + 2 * nval + nrec + n
+    models["idx_rows"] = int(idx_rows_total * (24 + 4))
+    models["idx_place"] = int(idx_rows_total * (4 + 32))
+    models["idx_order"] = int(idx_rows_total * 4)
+    n_annotated = int((ak == 63).sum())
+    models["r53_prepare"] = int(n * (4 + 8 + 1) + host_bytes + n_annotated * (32 + 8 + acc_dns_per) + ann_r53 + n * (1 + 4 + 8 + 4))
+    models["r53_objects"] = int(n * (1 + 4 + 4 + 4) + n_pairs * (1 + 4 + 4) + n * 8)
+    models["r53_fill_pairs"] = int(n * (4 + 8) + ann_r53 + n_pairs * (4 + 8))
+    return models
 
 
 def _pin_host_tables(torch, abi, o, a):
@@ -504,6 +527,10 @@ def main():
         tp = REPO / "profiles" / "r01_ncu_traffic.json"
         if tp.exists() and args.config == 3 and args.objects == 1_000_000:  # the capture is of this exact workload
             traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch", {})
+        # every stage with a byte model: its own achieved GB/s and fraction of the HBM roofline (CUDA-event stage times)
+        line["roofline"]["kernels"] = {name: {"ms": round(ms, 4), "bytes": models[name], "achieved_gbs": round(models[name] / (ms * 1e-3) / 1e9, 1),
+                                              "frac": round(models[name] / (ms * 1e-3) / 1e9 / peak, 4)}
+                                       for name, ms, _ in stages if name in models and ms > 0}
         kb = models.get(top[0])
         if kb:
             line["roofline"]["achieved"] = kb / (top[1] * 1e-3) / 1e9
