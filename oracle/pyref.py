@@ -496,3 +496,137 @@ def diff(objects, actual, cluster):
     ops = ga_ops + ga_orph + r53_ops + r53_orph
     sb = [0, len(ga_ops), len(ga_ops) + len(ga_orph), len(ga_ops) + len(ga_orph) + len(r53_ops), len(ops)]
     return dict(status_ga=st_ga, status_r53=st_r53, derived=derived, ops=ops, section_begin=sb, tok=tok, dports=dports)
+
+
+# ---------------------------------------------------------------- EndpointGroupBinding (pkg/controller/endpointgroupbinding/reconcile.go)
+#
+# Second, independently written restatement (the C++ one is oracle.cpp orc_bindings_diff).  Go slices are modelled as
+# (backing list, offset, length, capacity) so that `append(s[:i], s[i+1:]...)` aliases exactly as it does in Go.
+
+class _GoPanic(Exception):
+    pass
+
+
+class _Slice:
+    def __init__(self, backing, off, ln, cap):
+        self.b, self.off, self.len, self.cap = backing, off, ln, cap
+
+    def get(self, i):
+        if not 0 <= i < self.len:
+            raise _GoPanic("index out of range")
+        return self.b[self.off + i]
+
+    def sub(self, lo, hi=None):  # s[lo:hi]; hi defaults to len, may reach cap
+        hi = self.len if hi is None else hi
+        if not (0 <= lo <= hi <= self.cap):
+            raise _GoPanic("slice bounds out of range")
+        return _Slice(self.b, self.off + lo, hi - lo, self.cap - lo)
+
+    def append_all(self, other):  # append(self, other...) without reallocation when capacity suffices
+        vals = [other.get(i) for i in range(other.len)]
+        if self.len + len(vals) <= self.cap:
+            for k, v in enumerate(vals):
+                self.b[self.off + self.len + k] = v
+            return _Slice(self.b, self.off, self.len + len(vals), self.cap)
+        nb = [self.b[self.off + i] for i in range(self.len)] + vals
+        return _Slice(nb, 0, len(nb), len(nb))
+
+
+EGB_ADD_FINALIZER, EGB_REMOVE_FINALIZER, EGB_REMOVE_ENDPOINT, EGB_ADD_ENDPOINT, EGB_UPDATE_WEIGHT, EGB_UPDATE_STATUS = range(11, 17)
+ST_OK, ST_REQUEUE_30S, ST_ERR_RETRY, ST_PANIC, ST_REQUEUE_1S = 1, 3, 5, 7, 8
+D_LB_NOT_FOUND, D_REF_NOT_FOUND, D_EG_NOT_FOUND = 5, 12, 13
+
+
+def bindings_diff(objects, actual, bindings, known_egs):
+    """-> (status words, ops as (head, binding, 0, a0, NONE, NONE)); rows as tables.pack / pack_bindings number them."""
+    lbs = (actual or {}).get("lbs", [])
+    for i, lb in enumerate(lbs):
+        lb["_row"] = i
+    cache = {(ob.get("kind", "service"), ob.get("ns", "default"), ob["name"]): ob for ob in reversed(objects)}  # lister: first row wins
+
+    def get_lb(region, name):  # load_balancer.go:13-30 on the client of `region`
+        for lb in lbs:
+            if lb["region"] == region and lb["name"] == name:
+                return lb
+        return None
+
+    statuses, ops = [], []
+    ep_base = 0
+    for k, b in enumerate(bindings):
+        ids = list(b.get("endpoint_ids", []))
+        rows = list(range(ep_base, ep_base + len(ids)))  # global ep_id rows
+        ep_base += len(ids)
+
+        def put(code, a0=NONE):
+            ops.append((head(code, 2, 0), k, 0, a0, NONE, NONE))
+
+        def reconcile():
+            if b.get("deleting"):  # reconcileDelete :35-96
+                if len(ids) == 0 or b.get("eg_arn", "") not in known_egs:
+                    put(EGB_REMOVE_FINALIZER)
+                    return status(ST_OK)
+                status_ids = _Slice(list(rows), 0, len(rows), len(rows))  # obj.Status.EndpointIds
+                endpoint_ids = status_ids.sub(0)                           # endpointIds := obj.Status.EndpointIds
+                try:
+                    for i in range(status_ids.len):                        # len evaluated once by `range`
+                        put(EGB_REMOVE_ENDPOINT, status_ids.get(i))
+                        endpoint_ids = endpoint_ids.sub(0, i).append_all(endpoint_ids.sub(i + 1))
+                except _GoPanic:
+                    return status(ST_PANIC)
+                put(EGB_UPDATE_STATUS)
+                return status(ST_REQUEUE_1S)
+            if not b.get("finalizers", True):  # reconcileCreate :98-110
+                put(EGB_ADD_FINALIZER)
+                return status(ST_OK)
+            # reconcileUpdate :112-217
+            hostnames = []
+            ref = b.get("ref")
+            if ref is not None:
+                ob = cache.get((ref[0], b.get("ns", "default"), ref[1]))
+                if ob is None:
+                    return status(ST_ERR_RETRY, D_REF_NOT_FOUND)
+                hostnames = list(ob.get("lb_ingress", []))
+            arns, order, first_row, regional = {}, [], {}, None
+            for h in hostnames:
+                code, name, region = _get_lb_name(h)
+                if code >= 3:
+                    return status(ST_ERR_RETRY, code - 4)  # NOT_ELB 5 -> detail 1, ... NLB 8 -> detail 4
+                regional = region
+                lb = get_lb(region, name)
+                if lb is None:
+                    return status(ST_ERR_RETRY, D_LB_NOT_FOUND)
+                if lb["arn"] not in arns:
+                    order.append(lb["arn"])
+                    first_row[lb["arn"]] = lb["_row"]
+                arns[lb["arn"]] = name
+            new_ids = [a for a in order if a not in ids]
+            removed = [r for r, e in zip(rows, ids) if e not in arns]
+            if not new_ids and not removed and b.get("observed", True):
+                return status(ST_OK)
+            if b.get("eg_arn", "") not in known_egs:
+                return status(ST_ERR_RETRY, D_EG_NOT_FOUND)
+            for r in removed:
+                if regional is None:
+                    return status(ST_PANIC)  # nil *cloudaws.AWS
+                put(EGB_REMOVE_ENDPOINT, r)
+            for a in new_ids:
+                lb = get_lb(regional, arns[a])
+                if lb is None:
+                    return status(ST_ERR_RETRY, D_LB_NOT_FOUND)
+                if lb.get("state", "active") != "active":
+                    return status(ST_REQUEUE_30S)
+                put(EGB_ADD_ENDPOINT, lb["_row"])
+            for a in order:
+                put(EGB_UPDATE_WEIGHT, first_row[a])
+            put(EGB_UPDATE_STATUS)
+            return status(ST_OK)
+
+        statuses.append(reconcile())
+    return statuses, ops
+
+
+def _get_lb_name(hostname):
+    """GetLBNameFromHostname WITHOUT DetectCloudProvider in front (the binding controller calls it directly, reconcile.go:125)."""
+    if _ALB.search(hostname) or _NLB.search(hostname):
+        return tokenise(hostname)
+    return (5, None, None)

@@ -139,3 +139,17 @@ def test_gpu_bindings_then_diff_share_one_snapshot(garecon, oracle, engine):
     again = engine.diff()
     assert got.ops.tolist() == oracle.bindings_diff(snap, b).ops.tolist()
     assert again.diff(oracle.diff(snap, "default", mode=1)) == []
+
+
+# ------------------------------------------------------------------ second opinion: the Python restatement (explicit Go-slice model)
+
+@pytest.mark.parametrize("seed", range(30))
+def test_oracle_agrees_with_python_restatement(garecon, oracle, seed):
+    import importlib
+    pyref = importlib.import_module("oracle.pyref")
+    objects, actual, bindings, known = egbcases.random_bindings(seed) if seed else egbcases.hand_cases()
+    snap = garecon.pack(objects, actual)
+    want = oracle.bindings_diff(snap, garecon.pack_bindings(bindings, known))
+    st, ops = pyref.bindings_diff(objects, actual, bindings, set(known))
+    assert st == want.status_ga.tolist()
+    assert [tuple(int(x) for x in op) for op in want.ops.tolist()] == ops
