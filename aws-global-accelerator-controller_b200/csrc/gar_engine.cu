@@ -42,8 +42,8 @@ __global__ void __launch_bounds__(256, MINB) k_for_each_warp(const __grid_consta
 // resident 256-thread blocks per SM each warp-synchronous stage is compiled for (register cap = 65536 / (256 * N)):
 // these stages wait on dependent DRAM loads, so occupancy matters more than registers
 template <class F> struct MinBlocks { static constexpr int value = 2; };
-template <> struct MinBlocks<FGaObj> { static constexpr int value = 3; };
-template <> struct MinBlocks<FR53Pair> { static constexpr int value = 5; };
+template <> struct MinBlocks<FGaObj> { static constexpr int value = 4; };
+template <> struct MinBlocks<FR53Pair> { static constexpr int value = 6; };
 template <> struct MinBlocks<FR53Prepare> { static constexpr int value = 6; };
 
 __global__ void k_fill32(u32 *p, u32 v, size_t n) {
