@@ -409,6 +409,9 @@ int gar_bindings_diff(gar_engine *e, const gar_bindings *bindings, gar_changeset
      - the zone table (zone_name, zone_rec_begin) is complete and identical on every rank; a rank holds the record sets of
        whole zones only (other zones have empty record ranges), zone ranges ascending with the rank;
      - *_base give the global row of the slice's first row of each table.
+   Both rules are checked on the device (a fingerprint of the zone table travels in the meta rows); a violation makes
+   gar_shard_unpack return GAR_E_INVALID on the ranks that can see it — the host must propagate that to the other ranks
+   before their next collective (shard.py does it with one all-reduce).
    Rows are then re-homed by key hash on the device in two exchanges the HOST performs between the calls below (the data
    path is torch.distributed all_to_all_single over NCCL in ranks.py, or any all-to-all):
 
