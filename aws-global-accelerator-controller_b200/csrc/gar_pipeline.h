@@ -215,6 +215,20 @@ struct FRowZone {
     return valid;
   }
 };
+struct FZoneLenMask {
+  DevTables T;
+  unsigned long long *mask;  // [4]
+  GAR_HD void operator()(u32 z) const {
+    Str zn = mkstr(T.a.slab, T.a.zone_name[z]);
+    if (zn.n < 1 || zn.p[zn.n - 1] != '.') return;  // not indexed (FRowZone)
+    u32 b = zn.n - 1 < 255 ? zn.n - 1 : 255;
+#if defined(__CUDA_ARCH__)
+    atomicOr(&mask[b >> 6], 1ull << (b & 63));
+#else
+    mask[b >> 6] |= 1ull << (b & 63);
+#endif
+  }
+};
 struct FRowVal {
   DevTables T;
   Work W;
@@ -695,7 +709,7 @@ struct Pipeline {
     W.r53_mode = (u8 *)be.ensure(S_R53_MODE, (size_t)n + 1);
     W.r53_acc = (u32 *)be.ensure(S_R53_ACC, 4 * (size_t)(n + 1));
     W.r53_acc_dns = (gar_str *)be.ensure(S_R53_ACC_DNS, 8 * (size_t)(n + 1));
-    errflag = (u32 *)be.ensure(S_ERRFLAG, 64);
+    errflag = (u32 *)be.ensure(S_ERRFLAG, 256);
     be.fill32(errflag, 0, 4);
     W.acc_guest_from = acc_guest_from;
     W.sharded = sharded;
@@ -768,6 +782,12 @@ struct Pipeline {
     W.ix_owner = build_index(S_IX_OWNER, nacc, 1, FRowOwner{T, W}, overflow, force_radix);
     W.ix_thost = build_index(S_IX_THOST, nacc, 1, FRowThost{T, W}, overflow, force_radix);
     W.ix_zone = build_index(S_IX_ZONE, nzone, 1, FRowZone{T}, overflow, force_radix);
+    {
+      unsigned long long *zm = (unsigned long long *)(errflag + 16 + 8);  // 32 bytes inside the 128-byte flag block, 8-byte aligned
+      be.fill32((u32 *)zm, 0, 8);
+      if (nzone) be.for_each("zone_len_mask", nzone, FZoneLenMask{T, zm});
+      W.zone_len_mask = (const u64 *)zm;
+    }
     W.ix_val = build_index(S_IX_VAL, nval, 1, FRowVal{T, W}, overflow, force_radix);
     W.ix_alias = build_index(S_IX_ALIAS, nrec, 2, FRowAlias{T, W}, overflow, force_radix);
     W.ix_obj = build_index(S_IX_OBJ, n, 1, FRowObj{T, W}, overflow, force_radix);

@@ -124,6 +124,7 @@ struct Work {
   HashIdx ix_owner;  // (kind, "ns/name") -> accelerators that are ACC_MINE and ACC_OWNER_KEYED
   HashIdx ix_thost;  // target hostname -> accelerators that are ACC_MINE
   HashIdx ix_zone;   // zone name without the trailing dot -> zone rows
+  const u64 *zone_len_mask;  // [4] bit L set: some indexed zone name has L bytes (L >= 255 -> bit 255)
   HashIdx ix_val;    // (kind, "ns/name") -> owner value rows of this cluster
   HashIdx ix_alias;  // (zone, record name) -> alias record rows
   HashIdx ix_obj;    // (kind, "ns/name") -> object rows
@@ -503,15 +504,23 @@ GAR_HD u32 find_by_hostname(const DevTables &T, const Work &W, Str hostname, u32
 }
 
 // GetHostedZone (route53.go:335-358) + parentDomain (:383-386)
+// A candidate can only equal a zone name of its own length: zone_len_mask has one bit per length that occurs among the
+// indexed zone names (lengths >= 255 share bit 255), so most candidates of the parent walk are rejected without a probe.
+GAR_HD bool zone_len_possible(const Work &W, u32 n) {
+  u32 b = n < 255 ? n : 255;
+  return (W.zone_len_mask[b >> 6] >> (b & 63)) & 1ull;
+}
 GAR_HD u32 find_hosted_zone(const DevTables &T, const Work &W, Str hostname) {
   Str t = hostname;
   for (;;) {
     if (t.n == 0) return GAR_NONE;
-    Cursor c = idx_open(W.ix_zone, key_hash_str(t));
-    IdxEntry e;
-    while (idx_next(W.ix_zone, c, &e)) {
-      Str zn = mkstr(T.a.slab, e.s0);
-      if (zn.n == t.n + 1 && streq(substr(zn, 0, t.n), t)) return e.row;  // zone.Name == target + "." (index holds dotted names only)
+    if (zone_len_possible(W, t.n)) {
+      Cursor c = idx_open(W.ix_zone, key_hash_str(t));
+      IdxEntry e;
+      while (idx_next(W.ix_zone, c, &e)) {
+        Str zn = mkstr(T.a.slab, e.s0);
+        if (zn.n == t.n + 1 && streq(substr(zn, 0, t.n), t)) return e.row;  // zone.Name == target + "." (index holds dotted names only)
+      }
     }
     u32 k = find_byte(t, 0, '.');
     if (k >= t.n) return GAR_NONE;  // single label: parent is ""
@@ -619,7 +628,8 @@ GAR_HD u32 u_find_hosted_zone(const DevTables &T, const Work &W, bool active, St
   for (;;) {
     bool round = walking && t.n != 0;
     if (!GAR_ANY(round)) break;
-    Cursor c = u_open(W.ix_zone, round, u_hash(round, t));
+    bool probe = round && zone_len_possible(W, t.n);
+    Cursor c = u_open(W.ix_zone, probe, u_hash(probe, t));
     U_BUCKET_LOOP(zone == GAR_NONE, c) {
       IdxEntry e;
       bool hit = u_bucket_step(W.ix_zone, zone == GAR_NONE, c, &e);
