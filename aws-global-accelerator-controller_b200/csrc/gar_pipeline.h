@@ -37,7 +37,7 @@ enum Slot {
   S_IX_LB, S_IX_OWNER = S_IX_LB + 3, S_IX_THOST = S_IX_OWNER + 3, S_IX_ZONE = S_IX_THOST + 3, S_IX_VAL = S_IX_ZONE + 3,
   S_IX_ALIAS = S_IX_VAL + 3, S_IX_OBJ = S_IX_ALIAS + 3, S_IX_OVN = S_IX_OBJ + 3,
   S_SORT_KEYS = S_IX_OVN + 3, S_SORT_VALS, S_SORT_KEYS_ALT, S_SORT_VALS_ALT, S_SORT_TAGS,
-  S_COUNTS, S_STATUS_GA, S_STATUS_R53, S_OPS, S_ERRFLAG, S_IX_EG, S_IX_EG_ENT, S_IX_EG_PAD,
+  S_COUNTS, S_STATUS_GA, S_STATUS_R53, S_OPS, S_ERRFLAG, S_IX_EG, S_IX_EG_ENT, S_IX_EG_PAD, S_ACC_CLAIMED,
   S_NSLOTS
 };
 
@@ -713,6 +713,7 @@ struct Pipeline {
     be.fill32(errflag, 0, 4);
     W.acc_guest_from = acc_guest_from;
     W.sharded = sharded;
+    W.acc_claimed = nullptr;
   }
   void stage1() {
     const u32 n = T.o.n_objects, nlbi = T.o.n_lbi, nacc = T.a.n_accels, nrec = T.a.n_records, nval = T.a.n_values;
@@ -828,6 +829,8 @@ struct Pipeline {
     gar_op *stage_r53 = (gar_op *)be.ensure(S_STAGE_R53, sizeof(gar_op) * ((size_t)n * OPS_STAGE_CAP + 1));
     u32 *st_ga = (u32 *)be.out_status_ga(n);
     u32 *st_r53 = (u32 *)be.out_status_r53(n);
+    W.acc_claimed = (u8 *)be.ensure(S_ACC_CLAIMED, (size_t)nacc + 4);
+    be.fill32((u32 *)W.acc_claimed, 0, ((size_t)nacc + 3) / 4);
     if (n) be.for_each_warp("ga_objects", n, FGaObj{T, W, counts + L.ga_obj(0), stage_ga, st_ga, nullptr});
     if (nacc) be.for_each("ga_orphans_count", nacc, FGaOrphan{T, W, L, counts, nullptr});
     r53_relational(n, nullptr, st_r53);
@@ -848,6 +851,7 @@ struct Pipeline {
     gar_op *ops = (gar_op *)ops_alloc(dc->n_ops);
     if (n) be.for_each_warp("ga_objects_compact", n, FCompactOps{T, W, counts + L.ga_obj(0), stage_ga, ops, GAR_CTRL_GA, nullptr});
     if (nacc) be.for_each("ga_orphans_emit", nacc, FGaOrphan{T, W, L, counts, ops});
+    W.acc_claimed = nullptr;  // other decide flavours (incremental, bindings) do not maintain it
     if (n) be.for_each_warp("r53_objects_compact", n, FCompactOps{T, W, counts + L.r53_obj(0), stage_r53, ops, GAR_CTRL_R53, nullptr});
     if (nrec) be.for_each("r53_orphan_alias_emit", nrec, FR53OrphanAlias{T, W, L, counts, ops});
     if (nval) be.for_each("r53_orphan_value_emit", nval, FR53OrphanValue{T, W, L, counts, ops});

@@ -109,6 +109,7 @@ struct Work {
   // and every row serves both.
   u32 acc_guest_from;
   u32 sharded;
+  u8 *acc_claimed;  // [n_accels] written by ga_reconcile (full diff only; nullptr otherwise), read by ga_orphan
   // route53 ensure, relational form (objects with exactly one lbIngress)
   u8 *r53_mode;        // [n] R53_MODE_*
   u32 *r53_acc;        // [n] the accelerator found by target hostname
@@ -597,6 +598,8 @@ GAR_HD u32 u_owner_next(const DevTables &T, const Work &W, bool active, u32 kind
     hit = hit && (((e.a0 & ACC_OWNER_INGRESS) != 0) ? 1u : 0u) == kind;
     if (u_streq(hit, mkstr(T.a.slab, e.s0), key)) found = e.row;
   }
+  // an accelerator reached through its owner's object cannot be an orphan: the orphan pass skips its cache probe
+  if (found != GAR_NONE && W.acc_claimed) W.acc_claimed[found] = 1;
   return found;
 }
 
@@ -1469,6 +1472,7 @@ GAR_HD bool object_in_cache(const DevTables &T, const Work &W, u32 kind, Str key
 // accelerator whose owner key has no object: returns 1 and emits the delete op
 GAR_HD u32 ga_orphan(const DevTables &T, const Work &W, u32 acc, OpSink &s) {
   if (acc >= W.acc_guest_from) return 0;
+  if (W.acc_claimed && W.acc_claimed[acc]) return 0;  // its owner's object iterated it: the object is in the cache
   u32 fl = W.acc_flags[acc];
   if (!(fl & ACC_MINE) || !(fl & ACC_OWNER_3PART)) return 0;
   u32 kind = (fl & ACC_OWNER_INGRESS) ? 1u : 0u;
