@@ -481,6 +481,19 @@ struct gar_engine {
     CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
   }
+  // small read-backs that travel while later stages are queued (pinned staging + an event each)
+  DBuf dl_pin[2];
+  cudaEvent_t dl_ev[2] = {};
+  void download_start(int id, const void *src, size_t bytes) {
+    void *p = pin_ensure(dl_pin[id], 64);
+    if (!dl_ev[id]) CK(cudaEventCreateWithFlags(&dl_ev[id], cudaEventDisableTiming));
+    CK(cudaMemcpyAsync(p, src, bytes, cudaMemcpyDeviceToHost, stream));
+    CK(cudaEventRecord(dl_ev[id], stream));
+  }
+  void download_wait(int id, void *dst, size_t bytes) {
+    CK(cudaEventSynchronize(dl_ev[id]));
+    memcpy(dst, dl_pin[id].p, bytes);
+  }
   void *out_derived(u32 n) { return dev_ensure(d_derived, 4 * (size_t)(n + 1)); }
   void *out_derived_keys(u32 n) { return dev_ensure(d_derived_keys, 4 * (size_t)(n + 1)); }
   void *out_dport_begin(u32 n) { return dev_ensure(d_dport_begin, 4 * (size_t)(n + 2)); }
@@ -919,6 +932,10 @@ void gar_engine_destroy(gar_engine *e) {
   for (DBuf *b : {&e->d_derived_keys, &e->d_key_rows, &e->d_del_kind, &e->d_del_key, &e->d_del_slab}) cudaFree(b->p);
   for (auto &b : e->d_egb) cudaFree(b.p);
   cudaFree(e->d_valid.p);
+  for (int k = 0; k < 2; k++) {
+    if (e->dl_pin[k].p) cudaFreeHost(e->dl_pin[k].p);
+    if (e->dl_ev[k]) cudaEventDestroy(e->dl_ev[k]);
+  }
   for (DBuf *b : {&e->cluster_dev, &e->d_status_ga, &e->d_status_r53, &e->d_derived, &e->d_ops, &e->d_tok_code, &e->d_tok_name, &e->d_tok_region,
                   &e->d_dport_begin, &e->d_dports, &e->d_scan_tiles, &e->d_hist})
     cudaFree(b->p);

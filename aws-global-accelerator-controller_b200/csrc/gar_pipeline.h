@@ -13,6 +13,8 @@
 //   void fill32(u32 *p, u32 value, size_t n);
 //   void *ensure(int slot, size_t bytes);                                   // scratch buffer `slot`, at least `bytes`
 //   void download(void *host_dst, const void *dev_src, size_t bytes);       // blocking
+//   void download_start(int id, const void *dev_src, size_t bytes);         // id 0..1: small read-back in flight while later
+//   void download_wait(int id, void *host_dst, size_t bytes);               //   stages are queued; wait blocks only if needed
 #pragma once
 
 #include <stdio.h>
@@ -769,13 +771,8 @@ struct Pipeline {
     be.fill32(W.dport_begin, 0, (size_t)n + 1);
     if (n) be.for_each("listen_ports_count", n, FJsonCount{T, W});
     be.exclusive_scan(W.dport_begin, n + 1);
-    u32 hdr[2] = {0, 0};
     be.for_each("gather_header", 1, FGatherHeader{W.dport_begin + n, errflag, errflag + 4});
-    be.download(hdr, errflag + 4, sizeof(hdr));
-    n_dports = hdr[0];
-    if (hdr[1]) return GAR_E_INVALID;
-    W.dports = (i32 *)be.out_dports(hdr[0]);
-    if (n && hdr[0]) be.for_each("listen_ports_write", n, FJsonWrite{T, W});
+    be.download_start(0, errflag + 4, 8);  // port total + layout-rule flag: read back while the indexes are built
 
     // stage 3: hash indexes
     u32 *overflow = errflag + 1;
@@ -794,17 +791,29 @@ struct Pipeline {
     W.ix_obj = build_index(S_IX_OBJ, n, 1, FRowObj{T, W}, overflow, force_radix);
     if (nval) be.for_each("value_joins", nval, FValueJoins{T, W});
     W.ix_ovn = build_index(S_IX_OVN, nval, 8, FRowOvn{T, W}, overflow, force_radix);
+    // stage 2, second half: the port lists, now that their total is on the host
+    u32 hdr[2] = {0, 0};
+    be.download_wait(0, hdr, sizeof(hdr));
+    n_dports = hdr[0];
+    if (hdr[1]) return GAR_E_INVALID;
+    W.dports = (i32 *)be.out_dports(hdr[0]);
+    if (n && hdr[0]) be.for_each("listen_ports_write", n, FJsonWrite{T, W});
     return GAR_OK;
   }
 
   // route53 ensure in relational form over `slots` object slots (rows == nullptr: slot = object row)
-  void r53_relational(u32 slots, const u32 *rows, u32 *st_r53) {
+  // (begin: per-object filter + pair counts, the pair total starts travelling to the host; end: the pairs themselves.
+  //  Stages queued between the two overlap the read-back.)
+  void r53_relational_begin(u32 slots, const u32 *rows, u32 *st_r53) {
     W.pair_begin = (u32 *)be.ensure(S_PAIR_BEGIN, 4 * (size_t)(slots + 2));
     be.fill32(W.pair_begin, 0, (size_t)slots + 1);
     if (slots) be.for_each_warp("r53_prepare", slots, FR53Prepare{T, W, st_r53, rows});
     be.exclusive_scan(W.pair_begin, slots + 1);
+    be.download_start(1, W.pair_begin + slots, 4);
+  }
+  void r53_relational_end(u32 slots, const u32 *rows) {
     u32 npairs = 0;
-    be.download(&npairs, W.pair_begin + slots, 4);
+    be.download_wait(1, &npairs, 4);
     W.pair_obj = (u32 *)be.ensure(S_PAIR_OBJ, 4 * (size_t)(npairs + 1));
     W.pair_hn = (gar_str *)be.ensure(S_PAIR_HN, 8 * (size_t)(npairs + 1));
     W.pair_code = (u8 *)be.ensure(S_PAIR_CODE, (size_t)npairs + 1);
@@ -829,11 +838,12 @@ struct Pipeline {
     gar_op *stage_r53 = (gar_op *)be.ensure(S_STAGE_R53, sizeof(gar_op) * ((size_t)n * OPS_STAGE_CAP + 1));
     u32 *st_ga = (u32 *)be.out_status_ga(n);
     u32 *st_r53 = (u32 *)be.out_status_r53(n);
+    r53_relational_begin(n, nullptr, st_r53);
     W.acc_claimed = (u8 *)be.ensure(S_ACC_CLAIMED, (size_t)nacc + 4);
     be.fill32((u32 *)W.acc_claimed, 0, ((size_t)nacc + 3) / 4);
     if (n) be.for_each_warp("ga_objects", n, FGaObj{T, W, counts + L.ga_obj(0), stage_ga, st_ga, nullptr});
     if (nacc) be.for_each("ga_orphans_count", nacc, FGaOrphan{T, W, L, counts, nullptr});
-    r53_relational(n, nullptr, st_r53);
+    r53_relational_end(n, nullptr);
     if (n) be.for_each_warp("r53_objects", n, FR53Obj{T, W, counts + L.r53_obj(0), stage_r53, st_r53, nullptr});
     if (nrec) be.for_each("r53_orphan_alias_count", nrec, FR53OrphanAlias{T, W, L, counts, nullptr});
     if (nval) be.for_each("r53_orphan_value_count", nval, FR53OrphanValue{T, W, L, counts, nullptr});
@@ -877,7 +887,8 @@ struct Pipeline {
       be.for_each_warp("ga_objects", m, FGaObj{T, W, c_ga, stage_ga, st_ga, rows});
     }
     if (nd) be.for_each("ga_deleted_keys_count", nd, FDelKeyGa{T, W, D, c_gad, nullptr});
-    r53_relational(m, rows, st_r53);
+    r53_relational_begin(m, rows, st_r53);
+    r53_relational_end(m, rows);
     if (m) be.for_each_warp("r53_objects", m, FR53Obj{T, W, c_r53, stage_r53, st_r53, rows});
     if (nd) be.for_each("r53_deleted_keys_count", nd, FDelKeyR53{T, W, D, c_r53d, nullptr});
     be.exclusive_scan(counts, total + 1);

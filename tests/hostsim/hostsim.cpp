@@ -147,6 +147,9 @@ struct gar_engine {
   }
   void *ensure(int s, size_t bytes) { return slot[s].ensure(bytes); }
   void download(void *dst, const void *src, size_t bytes) { memcpy(dst, src, bytes); }
+  uint64_t dl_stage[2][4] = {};
+  void download_start(int id, const void *src, size_t bytes) { memcpy(dl_stage[id], src, bytes); }
+  void download_wait(int id, void *dst, size_t bytes) { memcpy(dst, dl_stage[id], bytes); }
   void *out_derived(u32 n) { return o_derived.ensure(4 * (size_t)(n + 1)); }
   void *out_derived_keys(u32 n) { return o_derived_keys.ensure(4 * (size_t)(n + 1)); }
   void *out_dport_begin(u32 n) { return o_dport_begin.ensure(4 * (size_t)(n + 2)); }
