@@ -34,14 +34,60 @@ _RR = {"A": abi.RR_A, "TXT": abi.RR_TXT, "CNAME": abi.RR_CNAME, "AAAA": abi.RR_A
 
 
 class _Slab:
-    def __init__(self):
+    """Byte slab under construction.  put() hands out a handle; finish() lays the bytes out in one of several orders (the
+    engine's results must not depend on where strings sit in the slab) and refs() turns handles into gar_str values:
+      "row"     insertion order = row-major by parent (an object's key, annotation values, hostname ... are neighbours)
+      "level"   column-major: all strings of one column together, columns in first-use order
+      "reverse" insertion order reversed
+      "shuffle" seeded random order
+    sub() is a handle for a slice of an earlier string (obj_ns / obj_name inside the "ns/name" key)."""
+
+    def __init__(self, layout: str = "row", seed: int = 0):
+        self.layout, self.seed = layout, seed
+        self.items: list[tuple[bytes, str]] = []
+        self.subs: list[tuple[int, int, int]] = []
+        self.off: list[int] = []
         self.buf = bytearray()
 
-    def put(self, s) -> int:
+    def put(self, s, col: str = "") -> int:
         b = s if isinstance(s, (bytes, bytearray)) else str(s).encode("utf-8", "surrogatepass")
-        off = len(self.buf)
-        self.buf += b
-        return (len(b) << abi.OFF_BITS) | off
+        self.items.append((bytes(b), col))
+        return len(self.items) - 1
+
+    def sub(self, handle: int, start: int, length: int) -> int:
+        self.subs.append((handle, start, length))
+        return -len(self.subs)
+
+    def finish(self):
+        n = len(self.items)
+        order = list(range(n))
+        if self.layout == "level":
+            first: dict[str, int] = {}
+            for _, col in self.items:
+                first.setdefault(col, len(first))
+            order.sort(key=lambda i: first[self.items[i][1]])
+        elif self.layout == "reverse":
+            order.reverse()
+        elif self.layout == "shuffle":
+            import random
+            random.Random(self.seed).shuffle(order)
+        elif self.layout != "row":
+            raise ValueError(f"unknown slab layout {self.layout!r}")
+        self.off = [0] * n
+        for i in order:
+            self.off[i] = len(self.buf)
+            self.buf += self.items[i][0]
+
+    def ref(self, handle) -> int:
+        if handle is None:
+            return 0
+        if handle < 0:
+            h, start, length = self.subs[-handle - 1]
+            return (length << abi.OFF_BITS) | (self.off[h] + start)
+        return (len(self.items[handle][0]) << abi.OFF_BITS) | self.off[handle]
+
+    def refs(self, handles) -> list[int]:
+        return [self.ref(h) for h in handles]
 
 
 def _ptr(arr: np.ndarray, ctype):
@@ -83,11 +129,12 @@ class Snapshot:
         return sum(a.nbytes for k, a in self.arrays.items() if not k.endswith("#backing"))
 
 
-def pack(objects: list[dict], actual: dict | None = None) -> Snapshot:
+def pack(objects: list[dict], actual: dict | None = None, layout: str = "row", seed: int = 0) -> Snapshot:
+    """layout: where the strings sit inside the two slabs (see _Slab); the tables are otherwise identical."""
     actual = actual or {}
     snap = Snapshot()
     o = snap.objects
-    sl = _Slab()
+    sl = _Slab(layout, seed)
     kind, spec, flags, ns, name, icls = [], [], [], [], [], []
     ann_b, lbi_b, port_b = [0], [0], [0]
     ann_k, ann_v, lbi_h, port_n, port_p = [], [], [], [], []
@@ -104,28 +151,29 @@ def pack(objects: list[dict], actual: dict | None = None) -> Snapshot:
         # layout rule: ns and name are slices of one "ns/name" string (the workqueue key, reconcile.go:47)
         nsb = str(ob.get("ns", "default")).encode("utf-8", "surrogatepass")
         nmb = str(ob["name"]).encode("utf-8", "surrogatepass")
-        kref = sl.put(nsb + b"/" + nmb)
-        koff = kref & abi.OFF_MASK
-        ns.append((len(nsb) << abi.OFF_BITS) | koff)
-        name.append((len(nmb) << abi.OFF_BITS) | (koff + len(nsb) + 1))
-        icls.append(sl.put(ob["ingress_class"]) if ob.get("ingress_class") is not None else 0)
+        kref = sl.put(nsb + b"/" + nmb, "obj_key")
+        ns.append(sl.sub(kref, 0, len(nsb)))
+        name.append(sl.sub(kref, len(nsb) + 1, len(nmb)))
+        icls.append(sl.put(ob["ingress_class"], "obj_ingress_class") if ob.get("ingress_class") is not None else None)
         anns = ob.get("annotations", {})
         items = list(anns.items()) if isinstance(anns, dict) else list(anns)
         for ak, av in items:
-            ann_k.append(sl.put(ak))
-            ann_v.append(sl.put(av))
+            ann_k.append(sl.put(ak, "ann_key"))
+            ann_v.append(sl.put(av, "ann_val"))
         ann_b.append(len(ann_k))
         for h in ob.get("lb_ingress", []):
-            lbi_h.append(sl.put(h))
+            lbi_h.append(sl.put(h, "lbi_hostname"))
         lbi_b.append(len(lbi_h))
         for p in ob.get("ports", []):
             if isinstance(p, (tuple, list)):
                 port_n.append(int(p[0]))
-                port_p.append(sl.put(p[1]) if k == abi.KIND_SERVICE else 0)
+                port_p.append(sl.put(p[1], "port_proto") if k == abi.KIND_SERVICE else None)
             else:
                 port_n.append(int(p))
-                port_p.append(sl.put("TCP") if k == abi.KIND_SERVICE else 0)
+                port_p.append(sl.put("TCP", "port_proto") if k == abi.KIND_SERVICE else None)
         port_b.append(len(port_n))
+    sl.finish()
+    ns, name, icls, ann_k, ann_v, lbi_h, port_p = (sl.refs(x) for x in (ns, name, icls, ann_k, ann_v, lbi_h, port_p))
     u8, u32, u64, i32 = np.uint8, np.uint32, np.uint64, np.int32
     o.n_objects = len(objects)
     snap._set(o, "obj_kind", kind, u8, C.c_uint8)
@@ -151,14 +199,12 @@ def pack(objects: list[dict], actual: dict | None = None) -> Snapshot:
     o.slab_len = len(sl.buf)
 
     a = snap.actual
-    sl = _Slab()
+    sl = _Slab(layout, seed + 1)
     lbs = actual.get("lbs", [])
-    a.n_lbs = len(lbs)
-    snap._set(a, "lb_region", [sl.put(x["region"]) for x in lbs], u64, C.c_uint64)
-    snap._set(a, "lb_name", [sl.put(x["name"]) for x in lbs], u64, C.c_uint64)
-    snap._set(a, "lb_dns", [sl.put(x["dns"]) for x in lbs], u64, C.c_uint64)
-    snap._set(a, "lb_arn", [sl.put(x["arn"]) for x in lbs], u64, C.c_uint64)
-    snap._set(a, "lb_state", [_LBSTATE[x.get("state", "active")] for x in lbs], u8, C.c_uint8)
+    lb_cols = {c: [] for c in ("lb_region", "lb_name", "lb_dns", "lb_arn")}
+    for x in lbs:  # row-major: the four strings of one load balancer are neighbours
+        for c, f in (("lb_region", "region"), ("lb_name", "name"), ("lb_dns", "dns"), ("lb_arn", "arn")):
+            lb_cols[c].append(sl.put(x[f], c))
 
     accs = actual.get("accelerators", [])
     acc_arn, acc_name, acc_dns, acc_en = [], [], [], []
@@ -168,12 +214,12 @@ def pack(objects: list[dict], actual: dict | None = None) -> Snapshot:
     # strings are laid out accelerator-row-major: accelerator, its tags, its listeners, their egs
     for x in accs:
         acc_arn.append(0)
-        acc_name.append(sl.put(x.get("name", "")))
-        acc_dns.append(sl.put(x.get("dns", "")))
+        acc_name.append(sl.put(x.get("name", ""), "acc_name"))
+        acc_dns.append(sl.put(x.get("dns", ""), "acc_dns"))
         acc_en.append(1 if x.get("enabled", True) else 0)
         for tk, tv in x.get("tags", []):
-            tag_k.append(sl.put(tk))
-            tag_v.append(sl.put(tv))
+            tag_k.append(sl.put(tk, "tag_key"))
+            tag_v.append(sl.put(tv, "tag_val"))
         tag_b.append(len(tag_k))
         for li in x.get("listeners", []):
             lis_arn.append(0)
@@ -183,10 +229,33 @@ def pack(objects: list[dict], actual: dict | None = None) -> Snapshot:
             for eg in li.get("egs", []):
                 eg_arn.append(0)
                 for e in eg.get("endpoints", []):
-                    ep_id.append(sl.put(e))
+                    ep_id.append(sl.put(e, "ep_id"))
                 ep_b.append(len(ep_id))
             eg_b.append(len(eg_arn))
         lis_b.append(len(lis_arn))
+    zones = actual.get("zones", [])
+    z_id, z_name, rec_b = [], [], [0]
+    r_name, r_type, r_has, r_alias, val_b, v_val = [], [], [], [], [0], []
+    for z in zones:
+        z_id.append(0)
+        z_name.append(sl.put(z["name"], "zone_name"))
+        for r in z.get("records", []):
+            r_name.append(sl.put(r["name"], "rec_name"))
+            r_type.append(_RR.get(r.get("type", "A"), abi.RR_OTHER))
+            alias = r.get("alias")
+            r_has.append(1 if alias is not None else 0)
+            r_alias.append(sl.put(alias, "rec_alias_dns") if alias is not None else None)
+            for v in r.get("values", []):
+                v_val.append(sl.put(v, "val_value"))
+            val_b.append(len(v_val))
+        rec_b.append(len(r_name))
+    sl.finish()
+    acc_name, acc_dns, tag_k, tag_v, ep_id, z_name, r_name, r_alias, v_val = (
+        sl.refs(x) for x in (acc_name, acc_dns, tag_k, tag_v, ep_id, z_name, r_name, r_alias, v_val))
+    a.n_lbs = len(lbs)
+    for c in lb_cols:
+        snap._set(a, c, sl.refs(lb_cols[c]), u64, C.c_uint64)
+    snap._set(a, "lb_state", [_LBSTATE[x.get("state", "active")] for x in lbs], u8, C.c_uint8)
     a.n_accels = len(accs)
     snap._set(a, "acc_name", acc_name, u64, C.c_uint64)
     snap._set(a, "acc_dns", acc_dns, u64, C.c_uint64)
@@ -207,22 +276,6 @@ def pack(objects: list[dict], actual: dict | None = None) -> Snapshot:
     a.n_endpoints = len(ep_id)
     snap._set(a, "ep_id", ep_id, u64, C.c_uint64)
 
-    zones = actual.get("zones", [])
-    z_id, z_name, rec_b = [], [], [0]
-    r_name, r_type, r_has, r_alias, val_b, v_val = [], [], [], [], [0], []
-    for z in zones:
-        z_id.append(0)
-        z_name.append(sl.put(z["name"]))
-        for r in z.get("records", []):
-            r_name.append(sl.put(r["name"]))
-            r_type.append(_RR.get(r.get("type", "A"), abi.RR_OTHER))
-            alias = r.get("alias")
-            r_has.append(1 if alias is not None else 0)
-            r_alias.append(sl.put(alias) if alias is not None else 0)
-            for v in r.get("values", []):
-                v_val.append(sl.put(v))
-            val_b.append(len(v_val))
-        rec_b.append(len(r_name))
     a.n_zones = len(zones)
     snap._set(a, "zone_name", z_name, u64, C.c_uint64)
     snap._set(a, "zone_rec_begin", rec_b, u32, C.c_uint32)
@@ -262,12 +315,14 @@ def pack_bindings(bindings: list[dict], known_egs: list[str]) -> Bindings:
         flags.append(f)
         ref = x.get("ref")
         kinds.append(0 if ref is None else (1 if ref[0] == "service" else 2))
-        keys.append(sl.put(f"{x.get('ns', 'default')}/{ref[1]}") if ref is not None else 0)
+        keys.append(sl.put(f"{x.get('ns', 'default')}/{ref[1]}") if ref is not None else None)
         arns.append(sl.put(x.get("eg_arn", "")))
         for e in x.get("endpoint_ids", []):
             eps.append(sl.put(e))
         ep_b.append(len(eps))
     known = [sl.put(k) for k in known_egs]
+    sl.finish()
+    keys, arns, eps, known = sl.refs(keys), sl.refs(arns), sl.refs(eps), sl.refs(known)
 
     def setcol(name, values, dtype, ctype):
         arr = np.ascontiguousarray(np.asarray(values if len(values) else [0], dtype=dtype))

@@ -125,3 +125,15 @@ def test_huge_value_lists(garecon, oracle, engine):
     got = engine.diff()
     want = oracle.diff(snap, "default", mode=1)
     assert got.diff(want) == [], got.describe_first_mismatch(want)
+
+
+@pytest.mark.parametrize("layout", ["level", "reverse", "shuffle"])
+def test_results_do_not_depend_on_the_slab_layout(garecon, oracle, engine, layout):
+    objects, actual = randmodel.make(17, n_objects=80)
+    base = oracle.diff(garecon.pack(objects, actual), "default", mode=1)
+    snap = garecon.pack(objects, actual, layout=layout, seed=3)
+    engine.load(snap)
+    got = engine.diff()
+    assert got.diff(oracle.diff(snap, "default", mode=1)) == []
+    for k in ("status_ga", "status_r53", "derived", "ops", "section_begin", "tok_code", "dport_begin", "dports"):
+        assert getattr(got, k).tolist() == getattr(base, k).tolist(), k
