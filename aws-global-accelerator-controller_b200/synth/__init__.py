@@ -21,7 +21,7 @@ class SynthConfig(C.Structure):
         ("p_missing_acc", C.c_float), ("p_port_drift", C.c_float), ("p_proto_drift", C.c_float), ("p_tag_drift", C.c_float),
         ("p_missing_listener", C.c_float), ("p_missing_eg", C.c_float), ("p_lb_not_active", C.c_float), ("p_orphan_acc", C.c_float),
         ("p_rec_missing", C.c_float), ("p_alias_drift", C.c_float), ("p_orphan_rec", C.c_float), ("p_dup_ports", C.c_float),
-        ("intern_keys", C.c_uint32), ("index_base", C.c_uint32), ("zone_base", C.c_uint32), ("zones_total", C.c_uint32), ("emit_mask", C.c_uint32),
+        ("intern_keys", C.c_uint32), ("index_base", C.c_uint32), ("zone_base", C.c_uint32), ("zones_total", C.c_uint32), ("layout", C.c_uint32), ("emit_mask", C.c_uint32),
         ("cluster", C.c_char * 64),
     ]
 

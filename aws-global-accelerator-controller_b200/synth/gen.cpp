@@ -552,6 +552,45 @@ Snapshot *generate(const gsyn_config &cfg) {
       std::vector<Rec>().swap(zr[z]);
     }
   }
+  // ---------------- optional re-layout: column-major slabs (every column's strings contiguous, in row order)
+  if (cfg.layout == 1) {
+    auto relayout = [](std::string &slab, std::vector<std::vector<gar_str> *> cols, std::vector<gar_str> *ns, std::vector<gar_str> *nm) {
+      std::string out;
+      out.reserve(slab.size());
+      if (ns) {  // "ns/name" is one string: obj_ns and obj_name stay slices of it
+        for (size_t i = 0; i < ns->size(); i++) {
+          uint64_t off = GAR_STR_OFF((*ns)[i]), nl = GAR_STR_LEN((*ns)[i]), ml = GAR_STR_LEN((*nm)[i]);
+          uint64_t no = out.size();
+          out.append(slab, off, nl + 1 + ml);
+          (*ns)[i] = GAR_STR(no, nl);
+          (*nm)[i] = GAR_STR(no + nl + 1, ml);
+        }
+      }
+      for (auto *col : cols) {
+        std::unordered_map<uint64_t, gar_str> seen;  // interned strings (one ref shared by many rows) are copied once
+        for (auto &r : *col) {
+          if (GAR_STR_LEN(r) == 0) {
+            r = 0;
+            continue;
+          }
+          auto it = seen.find(r);
+          if (it != seen.end()) {
+            r = it->second;
+            continue;
+          }
+          gar_str nr = GAR_STR(out.size(), GAR_STR_LEN(r));
+          out.append(slab, GAR_STR_OFF(r), GAR_STR_LEN(r));
+          if (seen.size() < 4096) seen.emplace(r, nr);
+          r = nr;
+        }
+      }
+      slab.swap(out);
+    };
+    relayout(S.os.b, {&S.obj_icls, &S.ann_key, &S.ann_val, &S.lbi_host, &S.port_proto}, &S.obj_ns, &S.obj_name);
+    relayout(S.as.b, {&S.lb_region, &S.lb_name, &S.lb_dns, &S.lb_arn, &S.acc_name, &S.acc_dns, &S.tag_key, &S.tag_val, &S.ep_id, &S.zone_name, &S.rec_name,
+                      &S.rec_alias, &S.val_value},
+             nullptr, nullptr);
+  }
   // ---------------- publish
   S.o.slab_len = S.os.b.size();
   S.a.slab_len = S.as.b.size();

@@ -29,6 +29,7 @@ typedef struct gsyn_config {
      zone row zone_base + z; with zones_total > 0 the zone table has zones_total rows (identical on every chunk) and record
      sets only under this chunk's n_zones zones */
   uint32_t index_base, zone_base, zones_total;
+  uint32_t layout;    /* 0 = strings row-major by parent (an object's strings are neighbours); 1 = column-major slabs */
   uint32_t emit_mask; /* 0 = all tables; else bit 0 objects, 1 load balancers, 2 accelerators (+ nested), 3 record sets */
   char cluster[64];
 } gsyn_config;

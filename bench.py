@@ -379,6 +379,9 @@ def main():
     ap.add_argument("--objects", type=int, default=1_000_000)
     ap.add_argument("--cpu-sample", type=int, default=200_000, help="objects in the bounded sample the CPU baseline is timed on")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layout", default="column", choices=["row", "column"],
+                    help="where the packer puts strings inside the slabs: column = every string column contiguous (what host/packer.hpp writes; "
+                         "default), row = row-major by parent object (9 %% slower: DESIGN.md §3).  Results do not depend on it.")
     ap.add_argument("--mode", default="replicas", choices=["replicas", "sharded"],
                     help="replicas: one independent cluster per GPU (weak scaling, no collective; the default and the driver's scaling run); "
                          "sharded: ONE cluster of --objects objects re-homed by key hash across the GPUs (BASELINE configs[3], strong scaling)")
@@ -413,6 +416,7 @@ def main():
     # ---- workload: one synthetic cluster per rank (different seed per rank)
     cfg = synth.preset(args.config, args.objects)
     cfg.seed = ranks_mod.rank_seed(cfg.seed, rank)
+    cfg.layout = 1 if args.layout == "column" else 0
     snap = synth.SynthSnapshot(cfg)
     o, a = snap.objects, snap.actual
     h2d_bytes = sum(int(c) * s for (_, c, s) in _table_arrays(abi, o, a))
@@ -496,7 +500,7 @@ def main():
             "dtype": "u8/u32 (bytes and indices)", "data": "synthetic",
             "config": {"workload": f"BASELINE configs[{args.config - 1}]: {args.objects} Service+Ingress per GPU, multi-hostname route53 annotation, "
                                    f"{a.n_accels} accelerators, {a.n_records} record sets, {a.n_lbs} load balancers",
-                       "objects_per_gpu": args.objects, "parallelism": f"replicas x{world} (independent clusters, no collective)",
+                       "slab_layout": args.layout, "objects_per_gpu": args.objects, "parallelism": f"replicas x{world} (independent clusters, no collective)",
                        "cache": f"inputs ({h2d_bytes / 1e6:.0f} MB per GPU) larger than L2 (126 MB); no flush needed", "seed": int(cfg.seed),
                        "n_ops": n_ops, "algorithmic_bytes": b_alg, "bytes_per_object": b_alg / args.objects},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "ms_per_step": dt_e2e / args.steps * 1e3,

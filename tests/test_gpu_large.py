@@ -49,6 +49,22 @@ def test_baseline_configs_1e5_bit_exact(garecon, oracle, engine, synth, cfg, n):
     _check_properties(got, snap)
 
 
+@pytest.mark.parametrize("cfg", [3, 5])
+def test_column_major_slabs_1e5_bit_exact(garecon, oracle, engine, synth, cfg):
+    """bench.py's default input layout (every string column contiguous, as host/packer.hpp writes it): same change set as the
+    row-major layout of the same cluster, and equal to the oracle on it."""
+    snap = synth.generate(cfg, 100_000, layout=1)
+    engine.load(snap)
+    got = engine.diff()
+    want = oracle.diff(snap, snap.cluster, mode=1)
+    assert got.diff(want) == [], got.describe_first_mismatch(want)
+    row = synth.generate(cfg, 100_000)
+    engine.load(row)
+    base = engine.diff()
+    for k in ("status_ga", "status_r53", "derived", "ops", "section_begin", "tok_code", "dports"):
+        assert np.array_equal(getattr(got, k), getattr(base, k)), k
+
+
 def test_config3_1e6_bit_exact_and_idempotent(garecon, oracle, engine, synth):
     """BASELINE configs[2] at full size (the bench workload)."""
     snap = synth.generate(3, 1_000_000)
