@@ -88,7 +88,7 @@ def generate(cfg: int, n: int, **overrides) -> SynthSnapshot:
     return SynthSnapshot(preset(cfg, n, **overrides))
 
 
-def cluster_slices(cfg_id: int, n_total: int, n_ranks: int, ranks=None, seed=None, **overrides):
+def cluster_slices(cfg_id: int, n_total: int, n_ranks: int, ranks=None, seed=None, layout: int = 0, **overrides):
     """Slices of ONE synthetic cluster of n_total objects for sharded mode (include/garecon.h "sharded mode").
 
     The cluster is generated as n_ranks chunks (same seed, cluster-wide object indexes, disjoint zone ranges of one zone
@@ -109,6 +109,7 @@ def cluster_slices(cfg_id: int, n_total: int, n_ranks: int, ranks=None, seed=Non
         cfg.zone_base = c * cfg.n_zones
         cfg.zones_total = n_ranks * cfg.n_zones
         cfg.emit_mask = mask
+        cfg.layout = layout  # 0 = strings row-major by parent, 1 = column-major slabs
         snap = SynthSnapshot(cfg)
         return snap, tables.columns(snap.objects, tables.OBJ_TABLES), tables.columns(snap.actual, tables.ACT_TABLES)
 

@@ -163,11 +163,12 @@ def check_slices(garecon, want, parts, n_total):
     assert np.array_equal(got["ops"], want.ops), first_diff(got["ops"].tolist(), want.ops.tolist())
 
 
-@pytest.mark.parametrize("cfg,n_total,n_ranks", [(4, 1500, 3), (5, 1200, 4), (3, 1000, 2)])
-def test_generator_slices_on_hostsim(garecon, oracle, hostlib, cfg, n_total, n_ranks):
-    """Chunked generator output (objects / accelerators / LBs of different chunks on one rank) == the union, via the oracle."""
+@pytest.mark.parametrize("cfg,n_total,n_ranks,layout", [(4, 1500, 3, 0), (5, 1200, 4, 0), (3, 1000, 2, 0), (4, 1200, 3, 1)])
+def test_generator_slices_on_hostsim(garecon, oracle, hostlib, cfg, n_total, n_ranks, layout):
+    """Chunked generator output (objects / accelerators / LBs of different chunks on one rank) == the union, via the oracle;
+    also with column-major string slabs in the slices."""
     synth = importlib.import_module("aws-global-accelerator-controller_b200.synth")
-    slices = synth.cluster_slices(cfg, n_total, n_ranks)
+    slices = synth.cluster_slices(cfg, n_total, n_ranks, layout=layout)
     union = garecon.tables.concat_slices(slices)
     assert union.objects.n_objects == n_total
     want = oracle.diff(union, "default", mode=1)
