@@ -126,6 +126,8 @@ class GarStageTiming(C.Structure):
 
 FLAG_STAGE_TIMING = 1
 FLAG_REPREPARE = 2
+FLAG_NO_ORPHANS = 4
+FLAG_ALLOW_EMPTY_CACHE = 8
 
 
 class GarOp(C.Structure):
@@ -271,6 +273,8 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
     lib.gar_algorithmic_bytes.restype = C.c_uint64
     lib.gar_last_stage_timings.argtypes = [C.c_void_p, C.POINTER(GarStageTiming), C.c_uint32]
     lib.gar_last_stage_timings.restype = C.c_uint32
+    lib.gar_last_counters.argtypes = [C.c_void_p, _u64p, C.c_uint32]
+    lib.gar_last_counters.restype = C.c_uint32
     if path is None:
         _lib = lib
     return lib
@@ -280,7 +284,7 @@ EXPORTED_SYMBOLS = (
     "gar_engine_create", "gar_engine_destroy", "gar_snapshot_load", "gar_snapshot_attach_device", "gar_diff",
     "gar_diff_device", "gar_diff_keys", "gar_bindings_diff", "gar_shard_route", "gar_shard_pack", "gar_shard_unpack", "gar_shard_blob_bytes",
     "gar_changeset_free", "gar_last_error", "gar_version", "gar_algorithmic_bytes",
-    "gar_last_stage_timings",
+    "gar_last_stage_timings", "gar_last_counters",
 )
 
 
@@ -293,11 +297,13 @@ class GarError(RuntimeError):
 class Engine:
     """Thin RAII wrapper over gar_engine_* (one engine per process per device)."""
 
-    def __init__(self, cluster_name: str = "default", device: int = 0, lib: C.CDLL | None = None, stage_timing: bool = False, reprepare: bool = False):
+    def __init__(self, cluster_name: str = "default", device: int = 0, lib: C.CDLL | None = None, stage_timing: bool = False, reprepare: bool = False,
+                 orphans: bool = True, allow_empty_cache: bool = False):
         self.lib = lib or load_library()
         self._h = C.c_void_p()
         self._cluster = cluster_name.encode()
-        cfg = GarConfig(GAR_ABI_VERSION, device, self._cluster, (FLAG_STAGE_TIMING if stage_timing else 0) | (FLAG_REPREPARE if reprepare else 0))
+        cfg = GarConfig(GAR_ABI_VERSION, device, self._cluster, (FLAG_STAGE_TIMING if stage_timing else 0) | (FLAG_REPREPARE if reprepare else 0)
+                        | (0 if orphans else FLAG_NO_ORPHANS) | (FLAG_ALLOW_EMPTY_CACHE if allow_empty_cache else 0))
         rc = self.lib.gar_engine_create(C.byref(cfg), C.byref(self._h))
         if rc != GAR_OK:
             msg = self.lib.gar_last_error(self._h).decode(errors="replace") if self._h else self.lib.gar_last_error(None).decode(errors="replace")
@@ -388,6 +394,13 @@ class Engine:
         arr = (GarStageTiming * 128)()
         n = self.lib.gar_last_stage_timings(self._h, arr, 128)
         return [(arr[i].name.decode(), float(arr[i].ms), int(arr[i].launches)) for i in range(min(n, 128))]
+
+    def counters(self) -> dict:
+        """Exact sizes of the intermediate relations of the last diff (include/garecon.h GAR_CTR_*)."""
+        arr = (C.c_uint64 * 8)()
+        n = self.lib.gar_last_counters(self._h, arr, 8)
+        names = ("r53_pairs", "dports")
+        return {names[i]: int(arr[i]) for i in range(min(n, len(names)))}
 
     def algorithmic_bytes(self, cs: GarChangeset) -> int:
         return int(self.lib.gar_algorithmic_bytes(self._h, C.byref(cs)))

@@ -273,12 +273,25 @@ struct FValCsr {
 };
 struct FValObj {
   gar_objects o;
-  u32 id_kind, id_key;
+  u32 id_kind, id_key, id_icls;
   u32 *flag;
   __device__ void operator()(u32 i) const {
-    if (o.obj_kind[i] > GAR_KIND_INGRESS) atomicMin(flag, id_kind);
+    if (o.obj_kind[i] > GAR_KIND_INGRESS || o.obj_spec_type[i] > GAR_SVC_EXTERNALNAME) atomicMin(flag, id_kind);
     u64 sep = GAR_STR_OFF(o.obj_ns[i]) + GAR_STR_LEN(o.obj_ns[i]);
     if (GAR_STR_OFF(o.obj_name[i]) != sep + 1 || sep >= o.slab_len || o.slab[sep] != '/') atomicMin(flag, id_key);
+    // obj_ingress_class is meaningful only where the flag says so (garecon.h): other rows may hold anything
+    if (o.obj_flags[i] & GAR_OBJ_HAS_INGRESS_CLASS) {
+      gar_str r = o.obj_ingress_class[i];
+      if (GAR_STR_OFF(r) + GAR_STR_LEN(r) > o.slab_len) atomicMin(flag, id_icls);
+    }
+  }
+};
+struct FValEnum {
+  const u8 *col;
+  u32 max_value, id;
+  u32 *flag;
+  __device__ void operator()(u32 i) const {
+    if (col[i] > max_value) atomicMin(flag, id);
   }
 };
 
@@ -307,6 +320,9 @@ struct CudaError {
   std::string msg;
 };
 struct InvalidError {
+  std::string msg;
+};
+struct StateError {
   std::string msg;
 };
 
@@ -354,6 +370,7 @@ struct gar_engine {
   // stage timing (GAR_FLAG_STAGE_TIMING)
   bool timing = false;
   bool reprepare = false;  // GAR_FLAG_REPREPARE
+  bool no_orphans = false, allow_empty_cache = false;  // GAR_FLAG_NO_ORPHANS, GAR_FLAG_ALLOW_EMPTY_CACHE
   struct Mark {
     const char *name;
     cudaEvent_t a, b;
@@ -365,6 +382,7 @@ struct gar_engine {
   int stage_depth = 0;
   u32 stage_launch0 = 0;
   std::vector<gar_stage_timing> last_timings;
+  u64 last_counters[GAR_CTR_N] = {};
   cudaEvent_t new_event() {
     if (events_used == event_pool.size()) {
       cudaEvent_t ev;
@@ -582,10 +600,17 @@ static void device_validate(gar_engine *e) {
     e->for_each("validate", nparents + 1, FValCsr{b, nparents, nchildren, (u32)names.size() - 1, flag});
   };
   const u32 n = o.n_objects;
-  names.push_back("obj_kind out of range");
+  names.push_back("obj_kind / obj_spec_type out of range");
   names.push_back("objects layout rule violated: obj_ns and obj_name must be slices of one \"ns/name\" key string");
-  str("obj_ns", o.obj_ns, n, o.slab_len); str("obj_name", o.obj_name, n, o.slab_len); str("obj_ingress_class", o.obj_ingress_class, n, o.slab_len);
-  e->for_each("validate", n, FValObj{o, 0, 1, flag});
+  auto en = [&](const char *name, const u8 *col, u32 cnt, u32 max_value) {
+    names.push_back(name);
+    e->for_each("validate", cnt, FValEnum{col, max_value, (u32)names.size() - 1, flag});
+  };
+  str("obj_ns", o.obj_ns, n, o.slab_len); str("obj_name", o.obj_name, n, o.slab_len);
+  names.push_back("obj_ingress_class");
+  e->for_each("validate", n, FValObj{o, 0, 1, (u32)names.size() - 1, flag});
+  en("lb_state out of range", a.lb_state, a.n_lbs, GAR_LB_FAILED); en("lis_proto out of range", a.lis_proto, a.n_listeners, GAR_PROTO_UDP);
+  en("rec_type out of range", a.rec_type, a.n_records, GAR_RR_AAAA);
   csr("obj_ann_begin", o.obj_ann_begin, n, o.n_ann); csr("obj_lbi_begin", o.obj_lbi_begin, n, o.n_lbi); csr("obj_port_begin", o.obj_port_begin, n, o.n_ports);
   str("ann_key", o.ann_key, o.n_ann, o.slab_len); str("ann_val", o.ann_val, o.n_ann, o.slab_len); str("lbi_hostname", o.lbi_hostname, o.n_lbi, o.slab_len);
   str("port_proto", o.port_proto, o.n_ports, o.slab_len);
@@ -602,8 +627,8 @@ static void device_validate(gar_engine *e) {
   e->download(&bad, flag, 4);  // synchronises e->stream: copies and checks are complete
   if (bad != 0xFFFFFFFFu) {
     std::string nm = bad < names.size() ? names[bad] : "table";
-    if (bad >= 2) nm += bad < names.size() && strstr(names[bad], "_begin") ? ": CSR is not monotone, does not start at 0 or does not end at the child count"
-                                                                          : ": string reference outside the slab";
+    if (bad >= 2 && !strstr(nm.c_str(), "out of range"))
+      nm += strstr(nm.c_str(), "_begin") ? ": CSR is not monotone, does not start at 0 or does not end at the child count" : ": string reference outside the slab";
     throw InvalidError{nm};
   }
 }
@@ -624,6 +649,7 @@ static void do_load(gar_engine *e, const gar_objects *o, const gar_actual *a) {
   e->loaded = false;
   delete e->pipe;  // the prepared state belongs to the previous snapshot
   e->pipe = nullptr;
+  validate_pointers(o, a);  // NULL checks before anything is copied; the contents are checked on the device, below
   CK(cudaSetDevice(e->device));
   e->in_used = 0;
   DevTables &T = e->T;
@@ -674,7 +700,6 @@ static void do_load(gar_engine *e, const gar_objects *o, const gar_actual *a) {
   T.a.val_value = upload(e, a->val_value, a->n_values);
   T.a.slab = upload(e, a->slab, a->slab_len, GAR_SLAB_PAD);
   CK(cudaEventRecord(e->ev[1], e->stream));
-  validate_pointers(o, a);  // NULL checks only; the contents are checked on the device, below
   device_validate(e);
   CK(cudaEventElapsedTime(&e->ms_h2d, e->ev[0], e->ev[1]));  // device_validate synchronised: the caller may free its buffers
   e->input_bytes = table_bytes(o, a);
@@ -708,6 +733,8 @@ static void do_diff(gar_engine *e, gar_changeset *out, bool to_host, const gar_k
     }
   }
   Pipeline<gar_engine> &P = *e->pipe;
+  P.orphan_sweep = !e->no_orphans;
+  P.allow_empty_cache = e->allow_empty_cache;
   if (e->reprepare) P.prepared = false;
   DiffCounts dc{};
   auto ops_alloc = [&](u64 nops) { return e->dev_ensure(e->d_ops, sizeof(gar_op) * (size_t)(nops + 1)); };
@@ -782,6 +809,11 @@ static void do_diff(gar_engine *e, gar_changeset *out, bool to_host, const gar_k
     CK(cudaStreamSynchronize(e->stream));
     throw InvalidError{"objects layout rule violated: obj_ns and obj_name must be slices of one \"ns/name\" key string"};
   }
+  if (rc == GAR_REFUSE_EMPTY_CACHE) {
+    CK(cudaStreamSynchronize(e->stream));
+    throw StateError{"the object table is empty but this cluster still owns AWS resources: refusing to emit delete-everything orphan sections "
+                     "(informer not synced?).  Set GAR_FLAG_ALLOW_EMPTY_CACHE if the cache really is empty, or GAR_FLAG_NO_ORPHANS"};
+  }
   if (rc != GAR_OK) throw InvalidError{"index build did not converge"};
   const bool partial = ks || bd;
   const u32 n = n_out, nlbi = partial ? 0 : e->T.o.n_lbi;
@@ -838,6 +870,8 @@ static void do_diff(gar_engine *e, gar_changeset *out, bool to_host, const gar_k
   CK(cudaEventElapsedTime(&out->ms_d2h, e->ev[3], e->ev[4]));
   out->ms_h2d = e->ms_h2d;
   out->kernel_launches = e->launches;
+  e->last_counters[GAR_CTR_R53_PAIRS] = P.n_pairs;
+  e->last_counters[GAR_CTR_DPORTS] = dc.n_dports;
   e->last_timings.clear();
   for (auto &m : e->marks) {
     float ms = 0;
@@ -870,6 +904,9 @@ static int guarded(gar_engine *e, Fn fn) {
   } catch (const InvalidError &ie) {
     e->err = ie.msg;
     return GAR_E_INVALID;
+  } catch (const StateError &se) {
+    e->err = se.msg;
+    return GAR_E_STATE;
   } catch (const std::bad_alloc &) {
     e->err = "out of host memory";
     return GAR_E_NOMEM;
@@ -902,6 +939,8 @@ int gar_engine_create(const gar_config *cfg, gar_engine **out) {
   e->cluster = cfg->cluster_name ? cfg->cluster_name : "";
   e->timing = (cfg->flags & GAR_FLAG_STAGE_TIMING) != 0;
   e->reprepare = (cfg->flags & GAR_FLAG_REPREPARE) != 0;
+  e->no_orphans = (cfg->flags & GAR_FLAG_NO_ORPHANS) != 0;
+  e->allow_empty_cache = (cfg->flags & GAR_FLAG_ALLOW_EMPTY_CACHE) != 0;
   try {
     CK(cudaSetDevice(e->device));
     CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
@@ -1086,6 +1125,14 @@ uint32_t gar_last_stage_timings(gar_engine *e, gar_stage_timing *out, uint32_t c
   std::lock_guard<std::mutex> lk(e->mu);
   uint32_t n = (uint32_t)e->last_timings.size();
   for (uint32_t i = 0; i < n && i < cap; i++) out[i] = e->last_timings[i];
+  return n;
+}
+
+uint32_t gar_last_counters(gar_engine *e, uint64_t *out, uint32_t cap) {
+  if (!e || !out) return 0;
+  std::lock_guard<std::mutex> lk(e->mu);
+  uint32_t n = cap < GAR_CTR_N ? cap : (uint32_t)GAR_CTR_N;
+  for (uint32_t i = 0; i < n; i++) out[i] = e->last_counters[i];
   return n;
 }
 

@@ -372,6 +372,7 @@ struct FGather5 {
   GAR_HD void operator()(u32 k) const { dst[k] = k < 5 ? src[idx[k]] : *extra; }
 };
 #define GAR_RETRY_WITH_RADIX 1000  // Pipeline::run: rebuild with force_radix (not an error)
+#define GAR_REFUSE_EMPTY_CACHE 1001  // orphan deletes against an empty object table (garecon.h "Orphan sweep precondition")
 struct FGatherHeader {
   const u32 *ndports, *errflag;
   u32 *dst;
@@ -679,6 +680,8 @@ struct Pipeline {
 
   u32 acc_guest_from = 0xFFFFFFFFu;  // sharded mode: set before prepare()
   u32 sharded = 0;
+  bool orphan_sweep = true;        // GAR_FLAG_NO_ORPHANS clears it
+  bool allow_empty_cache = false;  // GAR_FLAG_ALLOW_EMPTY_CACHE
 
   void alloc_work() {
     const u32 n = T.o.n_objects, nlbi = T.o.n_lbi, nacc = T.a.n_accels, nrec = T.a.n_records, nval = T.a.n_values;
@@ -811,9 +814,11 @@ struct Pipeline {
     be.exclusive_scan(W.pair_begin, slots + 1);
     be.download_start(1, W.pair_begin + slots, 4);
   }
+  u64 n_pairs = 0;  // size of the (object, hostname) relation of the last decide (gar_last_counters)
   void r53_relational_end(u32 slots, const u32 *rows) {
     u32 npairs = 0;
     be.download_wait(1, &npairs, 4);
+    n_pairs = npairs;
     W.pair_obj = (u32 *)be.ensure(S_PAIR_OBJ, 4 * (size_t)(npairs + 1));
     W.pair_hn = (gar_str *)be.ensure(S_PAIR_HN, 8 * (size_t)(npairs + 1));
     W.pair_code = (u8 *)be.ensure(S_PAIR_CODE, (size_t)npairs + 1);
@@ -842,17 +847,20 @@ struct Pipeline {
     W.acc_claimed = (u8 *)be.ensure(S_ACC_CLAIMED, (size_t)nacc + 4);
     be.fill32((u32 *)W.acc_claimed, 0, ((size_t)nacc + 3) / 4);
     if (n) be.for_each_warp("ga_objects", n, FGaObj{T, W, counts + L.ga_obj(0), stage_ga, st_ga, nullptr});
-    if (nacc) be.for_each("ga_orphans_count", nacc, FGaOrphan{T, W, L, counts, nullptr});
+    if (nacc && orphan_sweep) be.for_each("ga_orphans_count", nacc, FGaOrphan{T, W, L, counts, nullptr});
     r53_relational_end(n, nullptr);
     if (n) be.for_each_warp("r53_objects", n, FR53Obj{T, W, counts + L.r53_obj(0), stage_r53, st_r53, nullptr});
-    if (nrec) be.for_each("r53_orphan_alias_count", nrec, FR53OrphanAlias{T, W, L, counts, nullptr});
-    if (nval) be.for_each("r53_orphan_value_count", nval, FR53OrphanValue{T, W, L, counts, nullptr});
+    if (nrec && orphan_sweep) be.for_each("r53_orphan_alias_count", nrec, FR53OrphanAlias{T, W, L, counts, nullptr});
+    if (nval && orphan_sweep) be.for_each("r53_orphan_value_count", nval, FR53OrphanValue{T, W, L, counts, nullptr});
     be.exclusive_scan(counts, L.total() + 1);
     u32 sec[6];
     u32 *secdev = errflag + 8;  // same small scratch buffer
     be.for_each("gather_section_begins", 6, FGather5{counts, {0, L.ga_orph(0), L.r53_obj(0), L.base0(), L.total()}, overflow, secdev});
     be.download(sec, secdev, sizeof(sec));
     if (sec[5] && !force_radix) return GAR_RETRY_WITH_RADIX;  // an index bucket was too large for the fast build
+    // an EMPTY object table with owned resources left: an unsynced informer looks exactly like this, and the orphan sections
+    // would delete everything the cluster owns.  (A shard that happens to home no object is fine: the cluster is not empty.)
+    if (n == 0 && !sharded && !allow_empty_cache && sec[4] != 0) return GAR_REFUSE_EMPTY_CACHE;
     for (int k = 0; k < 5; k++) dc->section_begin[k] = sec[k];
     dc->n_ops = sec[4];
     dc->n_dports = n_dports;
@@ -860,11 +868,11 @@ struct Pipeline {
     // stage 5: move ops to their final, canonical positions
     gar_op *ops = (gar_op *)ops_alloc(dc->n_ops);
     if (n) be.for_each_warp("ga_objects_compact", n, FCompactOps{T, W, counts + L.ga_obj(0), stage_ga, ops, GAR_CTRL_GA, nullptr});
-    if (nacc) be.for_each("ga_orphans_emit", nacc, FGaOrphan{T, W, L, counts, ops});
+    if (nacc && orphan_sweep) be.for_each("ga_orphans_emit", nacc, FGaOrphan{T, W, L, counts, ops});
     W.acc_claimed = nullptr;  // other decide flavours (incremental, bindings) do not maintain it
     if (n) be.for_each_warp("r53_objects_compact", n, FCompactOps{T, W, counts + L.r53_obj(0), stage_r53, ops, GAR_CTRL_R53, nullptr});
-    if (nrec) be.for_each("r53_orphan_alias_emit", nrec, FR53OrphanAlias{T, W, L, counts, ops});
-    if (nval) be.for_each("r53_orphan_value_emit", nval, FR53OrphanValue{T, W, L, counts, ops});
+    if (nrec && orphan_sweep) be.for_each("r53_orphan_alias_emit", nrec, FR53OrphanAlias{T, W, L, counts, ops});
+    if (nval && orphan_sweep) be.for_each("r53_orphan_value_emit", nval, FR53OrphanValue{T, W, L, counts, ops});
     return GAR_OK;
   }
 

@@ -17,6 +17,55 @@ def rank_seed(base_seed: int, rank: int) -> int:
     return int(base_seed) + 1000 * int(rank)
 
 
+def _gpu_pci_path(local_rank: int):
+    import torch
+    pr = torch.cuda.get_device_properties(local_rank)
+    if all(hasattr(pr, k) for k in ("pci_bus_id", "pci_device_id", "pci_domain_id")):
+        return f"/sys/bus/pci/devices/{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+    import subprocess
+    out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local_rank)], capture_output=True, text=True, timeout=20).stdout.strip()
+    dom, rest = out.lower().split(":", 1)  # 00000000:1B:00.0
+    return f"/sys/bus/pci/devices/{dom[-4:]}:{rest}"
+
+
+class NumaBinding:
+    """Pin this process (and the threads it starts) to the CPUs of the NUMA node the GPU hangs off while host tables are
+    allocated and first-touched, so that the pages the engine later copies from are local to the GPU's PCIe root complex; with
+    8 ranks copying 1.7 GB each per step, remote-node reads held the end-to-end replicas efficiency at 0.65.  `release()`
+    restores the original affinity (CPU-side work such as the oracle then uses every core again).  `node` is None when the
+    topology cannot be read (containers without /sys topology): nothing is changed then."""
+
+    def __init__(self, local_rank: int):
+        self.node, self.saved = None, None
+        try:
+            path = _gpu_pci_path(local_rank)
+            node = int(open(path + "/numa_node").read().strip())
+            ids = set()
+            for part in open(path + "/local_cpulist").read().strip().split(","):
+                if "-" in part:
+                    lo, hi = part.split("-")
+                    ids.update(range(int(lo), int(hi) + 1))
+                elif part:
+                    ids.add(int(part))
+            allowed = os.sched_getaffinity(0)
+            ids &= allowed
+            if node >= 0:
+                self.node = node
+            if node >= 0 and ids and ids != allowed:
+                os.sched_setaffinity(0, ids)
+                self.saved = allowed
+        except Exception:  # noqa: BLE001 - leave the affinity alone
+            pass
+
+    def release(self):
+        if self.saved is not None:
+            try:
+                os.sched_setaffinity(0, self.saved)
+            except Exception:  # noqa: BLE001
+                pass
+            self.saved = None
+
+
 class Ranks:
     def __init__(self, backend: str | None = None, device=None):
         import torch

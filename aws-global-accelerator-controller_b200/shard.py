@@ -124,7 +124,9 @@ class DistExchange:
         in_sizes = [int(x) for x in nbytes]
         out_sizes = [self.e.blob_bytes(recv_meta[s]) for s in range(self.g)]
         send = torch.empty(sum(in_sizes) + 64, dtype=torch.uint8, device=self.device)
-        self.e.shard_pack(send.data_ptr())
+        if str(self.device) != "cpu":
+            torch.cuda.current_stream().synchronize()  # the allocation (and any fill) is on torch's stream, the engine packs on its own
+        self._guard(lambda: self.e.shard_pack(send.data_ptr()))  # a pack failure on one rank must not leave the others in the all-to-all
         recv = torch.empty(sum(out_sizes) + 64, dtype=torch.uint8, device=self.device)
         dist.all_to_all_single(recv[:sum(out_sizes)], send[:sum(in_sizes)], output_split_sizes=out_sizes, input_split_sizes=in_sizes)
         if str(self.device) != "cpu":
@@ -177,3 +179,64 @@ def merge_changesets(parts, n_objects: int):
         begins.append(begins[-1] + len(ops))
     return dict(status_ga=st_ga, status_r53=st_r53, derived=derived, ops=np.concatenate(sections) if sections else np.zeros(0, dtype=abi.OP_DTYPE),
                 section_begin=np.array(begins, dtype=np.uint64))
+
+
+# ------------------------------------------------------------------ merge-free parity: a checksum that adds over shards
+
+_M1, _M2, _M3 = np.uint64(0x9E3779B185EBCA87), np.uint64(0xC2B2AE3D27D4EB4F), np.uint64(0x165667B19E3779F9)
+
+
+def _mix(h, v):
+    h = (h ^ (v.astype(np.uint64) * _M2)) * _M1
+    return h ^ (h >> np.uint64(29))
+
+
+def _run_index(key_cols, n):
+    """position of every element inside its run of equal consecutive keys"""
+    if n == 0:
+        return np.zeros(0, dtype=np.uint64)
+    change = np.zeros(n, dtype=bool)
+    change[0] = True
+    for k in key_cols:
+        change[1:] |= k[1:] != k[:-1]
+    idx = np.arange(n, dtype=np.int64)
+    start = np.maximum.accumulate(np.where(change, idx, 0))
+    return (idx - start).astype(np.uint64)
+
+
+def canonical_checksum(cs) -> dict:
+    """Order-aware checksum of a change set that ADDS over shards: the sum (mod 2^64) of the per-shard values of one cluster
+    equals the value of the unsharded change set iff (up to hash collisions) the merged result is identical — every status
+    word is hashed with its GLOBAL object row, every op with its section, its canonical key (object row / accelerator row /
+    (zone, phase, record, value)) and its position among the ops of that key, which is exactly what `merge_changesets`
+    reconstructs.  Works on a ChangeSet of a whole cluster (rows = 0..n) and of a shard (rows = obj_gid, ops carry global rows).
+    Returns {"sum": int, "n_objects": int, "n_ops": int, "sections": [4 sizes]}; add the fields over the shards."""
+    with np.errstate(over="ignore"):
+        n = int(cs.n_objects)
+        rows = (cs.obj_gid if getattr(cs, "obj_gid", None) is not None else np.arange(n, dtype=np.uint32)).astype(np.uint64)
+        h = _mix(np.full(n, 0x51A7, dtype=np.uint64), rows)
+        for col in (cs.status_ga, cs.status_r53, cs.derived):
+            h = _mix(h, col)
+        total = int(h.sum(dtype=np.uint64)) if n else 0
+        sb = [int(x) for x in cs.section_begin]
+        for sec in range(4):
+            ops = cs.ops[sb[sec]:sb[sec + 1]]
+            m = len(ops)
+            if not m:
+                continue
+            keys = [ops["obj"]] if sec in (0, 2) else ([ops["a0"]] if sec == 1 else [ops["a0"], ops["sub"], ops["a1"], ops["a2"]])
+            h = _mix(np.full(m, 0xC0DE + sec, dtype=np.uint64), _run_index(keys, m))
+            for f in ("head", "obj", "sub", "a0", "a1", "a2"):
+                h = _mix(h, ops[f])
+            total = (total + int(h.sum(dtype=np.uint64))) & 0xFFFFFFFFFFFFFFFF
+        return {"sum": total, "n_objects": n, "n_ops": int(len(cs.ops)), "sections": [sb[k + 1] - sb[k] for k in range(4)]}
+
+
+def add_checksums(parts) -> dict:
+    out = {"sum": 0, "n_objects": 0, "n_ops": 0, "sections": [0, 0, 0, 0]}
+    for p in parts:
+        out["sum"] = (out["sum"] + p["sum"]) & 0xFFFFFFFFFFFFFFFF
+        out["n_objects"] += p["n_objects"]
+        out["n_ops"] += p["n_ops"]
+        out["sections"] = [a + b for a, b in zip(out["sections"], p["sections"])]
+    return out

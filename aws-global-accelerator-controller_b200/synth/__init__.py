@@ -88,35 +88,60 @@ def generate(cfg: int, n: int, **overrides) -> SynthSnapshot:
     return SynthSnapshot(preset(cfg, n, **overrides))
 
 
-def cluster_slices(cfg_id: int, n_total: int, n_ranks: int, ranks=None, seed=None, layout: int = 0, **overrides):
+def cluster_slices(cfg_id: int, n_total: int, n_ranks: int, ranks=None, seed=None, layout: int = 0, n_chunks: int | None = None, threads: int = 1, **overrides):
     """Slices of ONE synthetic cluster of n_total objects for sharded mode (include/garecon.h "sharded mode").
 
-    The cluster is generated as n_ranks chunks (same seed, cluster-wide object indexes, disjoint zone ranges of one zone
-    table).  Slice r holds chunk r's objects and record sets, but the accelerators of chunk r+1 and the load balancers of
-    chunk r+2: nothing an object needs is on its own rank, as after an arbitrary cut of the lists.  Returns
-    [(o_cols, a_cols)] for `ranks` (default: all) as numpy column dicts (tables.columns layout); row counts of every slice
-    are a pure function of (cfg, n_total, n_ranks), so ranks can generate only their own slice."""
+    The cluster is generated as n_chunks chunks (default: one per rank; same seed, cluster-wide object indexes, disjoint zone
+    ranges of one zone table), n_chunks a multiple of n_ranks.  Slice r holds the objects and record sets of its own group of
+    n_chunks / n_ranks consecutive chunks, but the accelerators of the next rank's group and the load balancers of the group
+    after that: nothing an object needs is on its own rank, as after an arbitrary cut of the lists.  Returns [(o_cols, a_cols)]
+    for `ranks` (default: all) as numpy column dicts (tables.columns layout); row counts of every slice are a pure function of
+    (cfg, n_total, n_ranks, n_chunks), so ranks can generate only their own slice.  `threads` > 1 generates chunks
+    concurrently (the generator runs outside the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
+
     from .. import tables
-    n_chunk = n_total // n_ranks
+    n_chunks = n_ranks if n_chunks is None else int(n_chunks)
+    if n_chunks % n_ranks or n_total % n_chunks:
+        raise ValueError("n_chunks must be a multiple of n_ranks and divide n_total")
+    cpr = n_chunks // n_ranks
+    n_chunk = n_total // n_chunks
     want = list(range(n_ranks)) if ranks is None else list(ranks)
 
-    def cols(c, mask):
-        c %= n_ranks
+    def cols(job):
+        c, mask = job
         cfg = preset(cfg_id, n_chunk, **overrides)
         if seed is not None:
             cfg.seed = seed
         cfg.index_base = c * n_chunk
         cfg.zone_base = c * cfg.n_zones
-        cfg.zones_total = n_ranks * cfg.n_zones
+        cfg.zones_total = n_chunks * cfg.n_zones
         cfg.emit_mask = mask
         cfg.layout = layout  # 0 = strings row-major by parent, 1 = column-major slabs
         snap = SynthSnapshot(cfg)
         return snap, tables.columns(snap.objects, tables.OBJ_TABLES), tables.columns(snap.actual, tables.ACT_TABLES)
 
+    def group(r, shift):
+        return [((r + shift) % n_ranks) * cpr + k for k in range(cpr)]
+
+    jobs = []
+    for r in want:
+        jobs += [(c, 1 | 8) for c in group(r, 0)] + [(c, 4) for c in group(r, 1)] + [(c, 2) for c in group(r, 2)]
+    jobs = list(dict.fromkeys(jobs))
+    if threads > 1 and len(jobs) > 1:
+        with ThreadPoolExecutor(max_workers=min(threads, len(jobs))) as pool:
+            done = dict(zip(jobs, pool.map(cols, jobs)))
+    else:
+        done = {j: cols(j) for j in jobs}
+
     out = []
     for r in want:
-        own, acc_src, lb_src = cols(r, 1 | 8), cols(r + 1, 4), cols(r + 2, 2)
-        a = tables.take_families({tables.REC_FAMILY: own[2], tables.ACC_FAMILY: acc_src[2], ("lb",): lb_src[2]})
-        o = {k: np.array(v) for k, v in own[1].items()}
-        out.append((o, {k: np.array(v) for k, v in a.items()}))
+        own = [done[(c, 1 | 8)] for c in group(r, 0)]
+        acc_src = [done[(c, 4)] for c in group(r, 1)]
+        lb_src = [done[(c, 2)] for c in group(r, 2)]
+        o = tables.concat_cols(tables.OBJ_TABLES, list(tables.OBJ_TABLES), [x[1] for x in own])
+        a = tables.take_families({tables.REC_FAMILY: tables.concat_cols(tables.ACT_TABLES, tables.REC_FAMILY, [x[2] for x in own]),
+                                  tables.ACC_FAMILY: tables.concat_cols(tables.ACT_TABLES, tables.ACC_FAMILY, [x[2] for x in acc_src]),
+                                  ("lb",): tables.concat_cols(tables.ACT_TABLES, ("lb",), [x[2] for x in lb_src])})
+        out.append(({k: np.array(v) for k, v in o.items()}, {k: np.array(v) for k, v in a.items()}))
     return out

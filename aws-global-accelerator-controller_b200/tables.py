@@ -438,32 +438,37 @@ def take_families(parts: dict) -> dict:
     return out
 
 
+def concat_cols(tables: dict, names, parts: list) -> dict:
+    """Column dicts of the tables `names` (one side: OBJ_TABLES or ACT_TABLES) concatenated in list order: rows appended, CSR
+    begins shifted, string references rebased into the concatenation of the parts' slabs.  The zone table is the same in every
+    part (disjoint record ranges): it is taken once and its begins add up."""
+    out = {}
+    slab_base = np.concatenate([[0], np.cumsum([len(p["slab"]) for p in parts])]).astype(np.int64)
+    for t in names:
+        for name, kind in tables[t][1]:
+            if isinstance(kind, tuple):
+                if t == "zone":
+                    out[name] = np.sum([p[name].astype(np.int64) for p in parts], axis=0).astype(np.uint32)
+                    continue
+                begins, off = [np.zeros(1, dtype=np.int64)], 0
+                for p in parts:
+                    b = p[name].astype(np.int64)
+                    begins.append(b[1:] + off)
+                    off += int(b[-1])
+                out[name] = np.concatenate(begins).astype(np.uint32)
+            elif t == "zone":
+                out[name] = _rebase(parts[0][name], 0)
+            else:
+                arrs = [(_rebase(p[name], int(slab_base[k])) if kind == "str" else p[name]) for k, p in enumerate(parts)]
+                out[name] = np.concatenate(arrs) if arrs else np.zeros(0, dtype=_DT[kind])
+    out["slab"] = np.concatenate([p["slab"] for p in parts]) if parts else np.zeros(0, dtype=np.uint8)
+    return out
+
+
 def concat_slices(slices) -> Snapshot:
     """The cluster a list of sharded-mode slices [(o_cols, a_cols), ...] (rank order) stands for: every list concatenated in
     rank order, the replicated zone table taken once."""
-    def cat(side, tables, skip_zone):
-        out, slab_base = {}, np.concatenate([[0], np.cumsum([len(s[side]["slab"]) for s in slices])]).astype(np.int64)
-        for t, (nf, cl) in tables.items():
-            for name, kind in cl:
-                if isinstance(kind, tuple):
-                    child_first = ACT_TABLES.get(kind[1], OBJ_TABLES.get(kind[1]))[1][0][0]
-                    if t == "zone":  # same zones on every slice, disjoint record ranges: begins add up
-                        out[name] = np.sum([s[side][name].astype(np.int64) for s in slices], axis=0).astype(np.uint32)
-                        continue
-                    begins, off = [np.zeros(1, dtype=np.int64)], 0
-                    for s in slices:
-                        b = s[side][name].astype(np.int64)
-                        begins.append(b[1:] + off)
-                        off += int(b[-1])
-                    out[name] = np.concatenate(begins).astype(np.uint32)
-                elif t == "zone":
-                    out[name] = _rebase(slices[0][side][name], 0)
-                else:
-                    arrs = [(_rebase(s[side][name], int(slab_base[k])) if kind == "str" else s[side][name]) for k, s in enumerate(slices)]
-                    out[name] = np.concatenate(arrs) if arrs else np.zeros(0, dtype=_DT[kind])
-        out["slab"] = np.concatenate([s[side]["slab"] for s in slices]) if slices else np.zeros(0, dtype=np.uint8)
-        return out
-    return from_columns(cat(0, OBJ_TABLES, False), cat(1, ACT_TABLES, True))
+    return from_columns(concat_cols(OBJ_TABLES, list(OBJ_TABLES), [s[0] for s in slices]), concat_cols(ACT_TABLES, list(ACT_TABLES), [s[1] for s in slices]))
 
 
 def shard_bases(slices) -> list:

@@ -178,9 +178,9 @@ def kernel_byte_models(o, a, n_ops_ga_obj: int, n_pairs: int, frac_ga: float):
 
 
 def _pin_host_tables(torch, abi, o, a):
-    """cudaHostRegister every generator-owned array so the e2e arm copies from pinned memory."""
+    """cudaHostRegister every generator-owned array so the e2e arm copies from pinned memory.  -> (bytes, [addresses])"""
     rt = torch.cuda.cudart()
-    pinned = 0
+    pinned, addrs = 0, []
     for ptr, cnt, sz in _table_arrays(abi, o, a):
         nbytes = int(cnt) * sz
         addr = C.cast(ptr, C.c_void_p).value
@@ -189,11 +189,38 @@ def _pin_host_tables(torch, abi, o, a):
         rc = rt.cudaHostRegister(addr, nbytes, 0)
         if int(rc) == 0:
             pinned += nbytes
-    return pinned
+            addrs.append(addr)
+    return pinned, addrs
+
+
+def _unpin(torch, addrs):
+    rt = torch.cuda.cudart()
+    for a in addrs:
+        rt.cudaHostUnregister(a)
+
+
+def _cpu_arm(ob, snap, threads_list, reps=1):
+    """objects/s of the CPU port (oracle indexed mode) on `snap` for each thread count: {threads: objects/s}"""
+    n = int(snap.objects.n_objects)
+    out = {}
+    for t in threads_list:
+        best = None
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            ob.diff_raw(snap.objects, snap.actual, snap.cluster.encode(), 1, t)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        out[int(t)] = n / best
+    return out
+
+
+def _thread_ladder(cores):
+    return sorted({t for t in (1, 8, 32, 128, cores) if t <= cores})
 
 
 def run_reference(args, rank, world):
-    """CPU arm: the oracle (port of the reference's decision functions; indexed mode, all host threads)."""
+    """CPU arm: the oracle (port of the reference's decision functions; indexed mode, all host threads) on the SAME workload
+    as the GPU arm: the full --objects cluster of --config, same generator seed and slab layout."""
     if rank != 0:
         return
     import __graft_entry__ as ge
@@ -202,8 +229,10 @@ def run_reference(args, rank, world):
     synth = importlib.import_module("aws-global-accelerator-controller_b200.synth")
     ob = importlib.import_module("oracle.binding")
     cores = os.cpu_count() or 1
-    n = args.cpu_sample
-    snap = synth.generate(args.config, n)
+    n = args.objects if args.cpu_sample <= 0 else min(args.cpu_sample, args.objects)
+    cfg = synth.preset(args.config, n)
+    cfg.layout = 1 if args.layout == "column" else 0
+    snap = synth.SynthSnapshot(cfg)
     cl = snap.cluster.encode()
     for _ in range(min(args.warmup, 1)):
         ob.diff_raw(snap.objects, snap.actual, cl, 1, cores)
@@ -212,49 +241,69 @@ def run_reference(args, rank, world):
         ob.diff_raw(snap.objects, snap.actual, cl, 1, cores)
     dt = time.perf_counter() - t0
     value = n * args.steps / dt
-    sample = f"config {args.config} generator at {n} objects (same distributions as the 10^6 workload), indexed oracle, {cores} threads"
+    scaling = _cpu_arm(ob, snap, [t for t in _thread_ladder(cores) if t != cores])
+    scaling[cores] = value
+    sample = f"the whole workload: config {args.config} generator at {n} objects (seed {int(cfg.seed)}, {args.layout}-major slabs), indexed oracle, {cores} threads"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32 (bytes and indices)",
-        "data": "synthetic", "config": {"workload": f"BASELINE configs[{args.config - 1}] shape, {args.objects} objects", "sample_objects": n},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "data": "synthetic", "config": {"workload": _workload_name(args.config, args.objects), "sample_objects": n, "same_config": n == args.objects,
+                                        "slab_layout": args.layout, "seed": int(cfg.seed)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "scaling": {str(k): round(v, 1) for k, v in sorted(scaling.items())}},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "Go reference not timed (no Go toolchain in this image); CPU baseline is a C++ restatement of the reference's decision functions",
+        "note": "Go reference not timed (no Go toolchain in this image); CPU baseline is a C++ restatement of the reference's decision functions; "
+                "with N > 1 GPUs the GPU arm diffs N clusters of this size, this arm one (rank 0 only, per the bench contract)",
     }
     print(json.dumps(line), flush=True)
 
 
-def run_sharded(args, rank, world, local_rank):
-    """BASELINE configs[3]: one cluster of --objects objects, every GPU starts with an arbitrary slice of each list, rows are
-    re-homed by key hash with one all-to-all (+ a small answer exchange), every GPU diffs its self-contained shard."""
+_WORKLOADS = {1: "100 Services type LoadBalancer (plumbing)", 2: "Service+Ingress vs mocked AWS lists (hash-join diff)",
+              3: "Service+Ingress with multi-hostname route53 annotation", 4: "cfg2 u cfg3 mix (the sharded 10^7 cluster)",
+              5: "adversarial: 90% colliding hostnames + 64-port listeners"}
+
+
+def _workload_name(config, objects):
+    return f"BASELINE configs[{config - 1}]: {objects} objects, {_WORKLOADS.get(config, '')}"
+
+
+def _cache_note(bytes_per_gpu):
+    """how the timed iterations avoid a warm L2 (126 MB): inputs larger than L2, or say that they are not"""
+    if bytes_per_gpu > 2 * 126e6:
+        return f"inputs ({bytes_per_gpu / 1e6:.0f} MB per GPU) larger than L2 (126 MB); no flush needed"
+    return f"inputs ({bytes_per_gpu / 1e6:.0f} MB per GPU) do NOT exceed L2 (126 MB): an L2-sized scratch buffer is rewritten between timed steps"
+
+
+SHARD_CHUNKS = 16  # the sharded cluster is always generated as 16 chunks, whatever the number of GPUs
+
+
+def sharded_measure(args, R, rank, world, local_rank, n_total, cfg_id, steps, warmup, with_single=True, detail=True):
+    """BASELINE configs[3]: ONE cluster of n_total objects; every GPU starts with an arbitrary slice of each list (objects /
+    accelerators / load balancers of different generator chunks on each rank), rows are re-homed by key hash (one all-to-all
+    of rows + a small answer exchange), every GPU diffs its self-contained shard.  Returns the record (rank 0) or None.
+
+    Parity inside the run (outside the timed regions): the additive canonical checksum (shard.canonical_checksum) of the
+    per-shard HOST change sets, summed over the ranks, must equal the checksum of the single-GPU diff of the same cluster."""
     import torch
-    import __graft_entry__ as ge
     pkg = importlib.import_module("aws-global-accelerator-controller_b200")
     synth = importlib.import_module("aws-global-accelerator-controller_b200.synth")
-    ranks_mod = importlib.import_module("aws-global-accelerator-controller_b200.ranks")
     shard = importlib.import_module("aws-global-accelerator-controller_b200.shard")
     dev = torch.device("cuda", local_rank)
-    R = ranks_mod.Ranks(backend="nccl", device=dev)
-    if world > 1 and not R.dist.is_initialized():
-        raise SystemExit("sharded mode with WORLD_SIZE > 1 needs torch.distributed")
-    if world == 1 and not R.dist.is_initialized():  # single GPU: a 1-rank group keeps the code path identical
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("MASTER_PORT", "29577")
-        R.dist.init_process_group("nccl", rank=0, world_size=1, device_id=dev)
-        R.owns_group = True
-    if rank == 0:
-        ge.ensure_built()
-    R.barrier()
-    cfg_id = 4 if args.config == 3 else args.config  # default workload of this mode: configs[3] = generator preset 4
-    n_total = args.objects - args.objects % world
-    o_cols, a_cols = synth.cluster_slices(cfg_id, n_total, world, ranks=[rank])[0]
+    cores = os.cpu_count() or 8
+    gen_threads = max(2, min(48, cores // max(world, 1)))
+    layout = 1 if args.layout == "column" else 0
+    n_chunks = SHARD_CHUNKS if (SHARD_CHUNKS % world == 0 and n_total % SHARD_CHUNKS == 0) else world
+    n_total -= n_total % n_chunks
+    tg = time.perf_counter()
+    o_cols, a_cols = synth.cluster_slices(cfg_id, n_total, world, ranks=[rank], layout=layout, n_chunks=n_chunks, threads=gen_threads)[0]
     snap = pkg.tables.from_columns(o_cols, a_cols)
+    gen_s = time.perf_counter() - tg
     counts = R.gather_counts([len(o_cols["obj_kind"]), len(a_cols["lb_state"]), len(a_cols["acc_enabled"]), len(a_cols["lis_proto"]),
                               len(a_cols["eg_ep_begin"]) - 1, len(a_cols["rec_type"]), len(a_cols["val_value"]), snap.input_bytes()])
     base = [sum(c[k] for c in counts[:rank]) for k in range(7)]
     sh = pkg.abi.GarShard(rank, world, *base)
     h2d_bytes = snap.input_bytes()
-    _pin_host_tables(torch, pkg.abi, snap.objects, snap.actual)
+    _, pinned_addrs = _pin_host_tables(torch, pkg.abi, snap.objects, snap.actual)
     eng = pkg.Engine(cluster_name="default", device=local_rank)
     ex = shard.DistExchange(eng, sh, dev)
     sampler = ClockSampler(local_rank)
@@ -266,35 +315,41 @@ def run_sharded(args, rank, world, local_rank):
 
     eng.load(snap)
     launches = 0
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         cs = step()
     R.barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         cs = step()
         launches += cs.kernel_launches
     R.barrier()
     t1 = time.perf_counter()
     dt_dev = R.max_over_ranks(t1 - t0)
     clocks = sampler.summary(t0, t1)
-    n_ops = int(cs.n_ops)
     homed = int(cs.n_objects)
     sent = ex.bytes_sent
     # end to end: host slice in (H2D), host change set out (D2H), every step
     for _ in range(2):
         eng.load(snap)
         ex.run()
-        full = eng.diff_raw()
+        eng.diff_raw()
     R.barrier()
     t2 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         eng.load(snap)
         ex.run()
-        full = eng.diff_raw()
+        eng.diff_raw()
     R.barrier()
     t3 = time.perf_counter()
     dt_e2e = R.max_over_ranks(t3 - t2)
     sampler.stop()
+    # parity: this shard's host change set -> additive checksum, summed over the ranks
+    part = eng.diff()
+    n_ops = len(part.ops)
+    ck = shard.canonical_checksum(part)
+    del part
+    lo, hi = ck["sum"] & 0xFFFFFFFF, ck["sum"] >> 32
+    allck = R.gather_counts([lo, hi, ck["n_objects"], ck["n_ops"]] + ck["sections"])
     # phase breakdown (separate pass, synchronised between phases; not part of the timed numbers above)
     phases = {}
 
@@ -322,49 +377,126 @@ def run_sharded(args, rank, world, local_rank):
             ex.keep.append(recv)
             timed(f"unpack{rnd}", lambda: eng.shard_unpack(rnd, recv.data_ptr(), recv_meta))
         timed("diff", lambda: eng.diff_device())
-    # per-kernel CUDA-event times of one whole sharded step (engine with GAR_FLAG_STAGE_TIMING; separate pass)
     eng.close()
-    peng = pkg.Engine(cluster_name="default", device=local_rank, stage_timing=True)
-    peng.load(snap)
-    pex = shard.DistExchange(peng, sh, dev)
     stage_acc = {}
-    for it in range(4):
-        pex.run()
-        peng.diff_device()
-        if it == 0:
-            continue
-        for name, ms, nl in peng.stage_timings():
-            e = stage_acc.setdefault(name, [0.0, 0])
-            e[0] += ms / 3
-            e[1] += nl
-    peng.close()
+    if detail:  # per-kernel CUDA-event times of one whole sharded step (engine with GAR_FLAG_STAGE_TIMING; separate pass)
+        peng = pkg.Engine(cluster_name="default", device=local_rank, stage_timing=True)
+        peng.load(snap)
+        pex = shard.DistExchange(peng, sh, dev)
+        for it in range(4):
+            pex.run()
+            peng.diff_device()
+            if it == 0:
+                continue
+            for name, ms, nl in peng.stage_timings():
+                e = stage_acc.setdefault(name, [0.0, 0])
+                e[0] += ms / 3
+                e[1] += nl
+        peng.close()
+    ex.keep.clear()
+    _unpin(torch, pinned_addrs)
+    del ex, snap, o_cols, a_cols
+    torch.cuda.empty_cache()
     allc = R.gather_counts([homed, n_ops, sent, int(sum(phases.values()) * 1000)] + [int(phases[k] * 1000) for k in sorted(phases)])
+    # ---- the same cluster on ONE GPU (rank 0): the strong-scaling denominator and the parity arbiter
+    single = None
+    if with_single and rank == 0:
+        tg = time.perf_counter()
+        slices = synth.cluster_slices(cfg_id, n_total, world, layout=layout, n_chunks=n_chunks, threads=min(48, cores))
+        union = pkg.tables.concat_slices(slices)
+        del slices
+        gen1_s = time.perf_counter() - tg
+        _, addrs1 = _pin_host_tables(torch, pkg.abi, union.objects, union.actual)
+        with pkg.Engine(cluster_name="default", device=local_rank, reprepare=True) as e1:
+            e1.load(union)
+            whole = e1.diff()
+            ck1 = shard.canonical_checksum(whole)
+            del whole
+            for _ in range(warmup):
+                e1.diff_device()
+            torch.cuda.synchronize()
+            ta = time.perf_counter()
+            for _ in range(steps):
+                e1.diff_device()
+            torch.cuda.synchronize()
+            dt1 = time.perf_counter() - ta
+            for _ in range(1):
+                e1.load(union)
+                e1.diff_raw()
+            tb = time.perf_counter()
+            for _ in range(max(1, steps // 2)):
+                e1.load(union)
+                e1.diff_raw()
+            dt1e = (time.perf_counter() - tb) / max(1, steps // 2)
+        single = {"value": n_total * steps / dt1, "ms_per_step": dt1 / steps * 1e3, "e2e_value": n_total / dt1e, "e2e_ms_per_step": dt1e * 1e3,
+                  "checksum": ck1, "input_bytes": union.input_bytes(), "generate_s": round(gen1_s, 1)}
+        _unpin(torch, addrs1)
+        del union
+    R.barrier()
+    if rank != 0:
+        return None
+    peak, peak_src = _peaks()
+    in_bytes = sum(c[7] for c in counts)
+    b_alg = in_bytes + 8 * n_total + 24 * sum(c[1] for c in allc)
+    value = n_total * steps / dt_dev
+    achieved = b_alg / (dt_dev / steps) / 1e9
+    merged = {"sum": sum((c[0] | (c[1] << 32)) for c in allck) & 0xFFFFFFFFFFFFFFFF, "n_objects": sum(c[2] for c in allck), "n_ops": sum(c[3] for c in allck),
+              "sections": [sum(c[4 + k] for c in allck) for k in range(4)]}
+    ph_max = {k: max(c[4 + i] for c in allc) / 1000 for i, k in enumerate(sorted(phases))}
+    exch_ms = sum(v for k, v in ph_max.items() if k != "diff")
+    sent_max = max(c[2] for c in allc)
+    rec = {
+        "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": dt_dev / steps * 1e3, "scaling": "strong",
+        "config": {"workload": f"BASELINE configs[3]: ONE cluster of {n_total} Service+Ingress (generator preset {cfg_id}, {n_chunks} chunks, {args.layout}-major slabs) "
+                               f"cut into {world} slices (objects / accelerators / load balancers of different chunk groups on each rank), re-homed by key hash",
+                   "objects_total": n_total, "parallelism": f"key-hash shards x{world}: all-to-all of rows + answer exchange (NCCL), then local diff",
+                   "cache": _cache_note(h2d_bytes), "homed_objects_per_rank": [c[0] for c in allc], "ops_per_rank": [c[1] for c in allc],
+                   "algorithmic_bytes": b_alg, "generate_s": round(gen_s, 1)},
+        "e2e": {"value": n_total * steps / dt_e2e, "unit": UNIT, "h2d_bytes_per_step": in_bytes,
+                "d2h_bytes_per_step": 12 * n_total + 24 * sum(c[1] for c in allc), "ms_per_step": dt_e2e / steps * 1e3},
+        "gpu_launches": launches, "clocks": clocks,
+        "bytes_sent": {"per_rank": [c[2] for c in allc], "max": sent_max,
+                       "nvlink_gbs_per_direction_in_blob_a2a": round(sent_max / max(ph_max.get("blob_a2a1", 0) + ph_max.get("blob_a2a2", 0), 1e-9) / 1e6, 1),
+                       "nvlink_peak_gbs_per_direction": 900.0},
+        "roofline": {"bound": "hbm", "kernel": "whole sharded step (route, pack, exchange, merge, diff)", "achieved": achieved, "peak": peak * world,
+                     "unit": "GB/s", "frac": achieved / (peak * world), "traffic": None, "peak_source": peak_src + f" x {world} GPUs"},
+        "phases_ms_rank0": {k: round(v, 3) for k, v in phases.items()},
+        "phases_ms_max_over_ranks": ph_max,
+        "exchange_ms_max_over_ranks": round(exch_ms, 3),
+        "stages_ms_rank0": {k: round(v[0], 4) for k, v in sorted(stage_acc.items(), key=lambda kv: -kv[1][0])},
+        "checksum": merged,
+    }
+    if single is not None:
+        rec["single_gpu_value"] = single["value"]
+        rec["single_gpu"] = single
+        rec["strong_scaling_speedup"] = value / single["value"]
+        rec["strong_scaling_efficiency"] = value / single["value"] / world
+        rec["e2e_speedup"] = rec["e2e"]["value"] / single["e2e_value"]
+        rec["checksum_equal"] = merged == single["checksum"]
+    return rec
+
+
+def run_sharded(args, rank, world, local_rank):
+    """`--mode sharded`: the sharded step as the bench line's own metric (the default invocation under torchrun reports it as
+    the `sharded` record of the replicas line instead)."""
+    import torch
+    import __graft_entry__ as ge
+    ranks_mod = importlib.import_module("aws-global-accelerator-controller_b200.ranks")
+    dev = torch.device("cuda", local_rank)
+    R = ranks_mod.Ranks(backend="nccl", device=dev)
+    if world == 1 and not R.dist.is_initialized():  # single GPU: a 1-rank group keeps the code path identical
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29577")
+        R.dist.init_process_group("nccl", rank=0, world_size=1, device_id=dev)
+        R.owns_group = True
     if rank == 0:
-        peak, peak_src = _peaks()
-        in_bytes = sum(c[7] for c in counts)
-        b_alg = in_bytes + 8 * n_total + 24 * sum(c[1] for c in allc)
-        value = n_total * args.steps / dt_dev
-        achieved = b_alg / (dt_dev / args.steps) / 1e9
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dt_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "u8/u32 (bytes and indices)", "data": "synthetic",
-            "config": {"workload": f"BASELINE configs[3]: ONE cluster of {n_total} Service+Ingress (generator preset {cfg_id}) cut into {world} slices "
-                                   f"(objects / accelerators / load balancers of different chunks on each rank), re-homed by key hash",
-                       "objects_total": n_total, "parallelism": f"key-hash shards x{world}: all-to-all of rows + answer exchange (NCCL), then local diff",
-                       "cache": f"slice inputs ({h2d_bytes / 1e6:.0f} MB per GPU) larger than L2 (126 MB); no flush needed",
-                       "homed_objects_per_rank": [c[0] for c in allc], "ops_per_rank": [c[1] for c in allc],
-                       "all_to_all_bytes_sent_per_rank": [c[2] for c in allc], "algorithmic_bytes": b_alg},
-            "e2e": {"value": n_total * args.steps / dt_e2e, "unit": UNIT, "h2d_bytes_per_step": sum(c[7] for c in counts),
-                    "d2h_bytes_per_step": 12 * n_total + 24 * sum(c[1] for c in allc), "ms_per_step": dt_e2e / args.steps * 1e3},
-            "gpu_launches": launches,
-            "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "whole sharded step (route, pack, exchange, merge, diff)", "achieved": achieved, "peak": peak * world,
-                         "unit": "GB/s", "frac": achieved / (peak * world), "traffic": None, "peak_source": peak_src + f" x {world} GPUs"},
-            "phases_ms_rank0": {k: round(v, 3) for k, v in phases.items()},
-            "stages_ms_rank0": {k: round(v[0], 4) for k, v in sorted(stage_acc.items(), key=lambda kv: -kv[1][0])},
-            "phases_ms_max_over_ranks": {k: max(c[4 + i] for c in allc) / 1000 for i, k in enumerate(sorted(phases))},
-        }
+        ge.ensure_built()
+    R.barrier()
+    cfg_id = 4 if args.config == 3 else args.config  # default workload of this mode: configs[3] = generator preset 4
+    rec = sharded_measure(args, R, rank, world, local_rank, args.objects, cfg_id, args.steps, args.warmup, with_single=not args.no_single)
+    if rank == 0:
+        line = {"metric": METRIC, "higher_is_better": True, "vs_baseline": None, "dtype": "u8/u32 (bytes and indices)", "data": "synthetic"}
+        line.update(rec)
         print(json.dumps(line), flush=True)
     R.close()
 
@@ -377,14 +509,20 @@ def main():
     ap.add_argument("--impl", default="garecon", choices=["garecon", "reference"])
     ap.add_argument("--config", type=int, default=3, help="BASELINE.json configs index (1-based): 3 = 10^6 multi-hostname route53")
     ap.add_argument("--objects", type=int, default=1_000_000)
-    ap.add_argument("--cpu-sample", type=int, default=200_000, help="objects in the bounded sample the CPU baseline is timed on")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="objects of the CPU baseline's workload; 0 = the whole workload (same config as the GPU arm)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the in-run oracle comparison of the timed workload's change set")
     ap.add_argument("--layout", default="column", choices=["row", "column"],
                     help="where the packer puts strings inside the slabs: column = every string column contiguous (what host/packer.hpp writes; "
                          "default), row = row-major by parent object (9 %% slower: DESIGN.md §3).  Results do not depend on it.")
     ap.add_argument("--mode", default="replicas", choices=["replicas", "sharded"],
-                    help="replicas: one independent cluster per GPU (weak scaling, no collective; the default and the driver's scaling run); "
-                         "sharded: ONE cluster of --objects objects re-homed by key hash across the GPUs (BASELINE configs[3], strong scaling)")
+                    help="replicas: one independent cluster per GPU (weak scaling, no collective); with N > 1 GPUs the line also carries a "
+                         "`sharded` record: ONE 10^7-object cluster re-homed by key hash across the GPUs (BASELINE configs[3], strong scaling, "
+                         "checksum-compared with the same cluster on one GPU).  sharded: only that, as the line's own metric")
+    ap.add_argument("--sharded-objects", type=int, default=10_000_000, help="size of the cluster of the `sharded` record")
+    ap.add_argument("--sharded-steps", type=int, default=5)
+    ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the sharded record")
+    ap.add_argument("--no-single", action="store_true", help="sharded: skip the single-GPU run of the same cluster (no checksum comparison)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "garecon" else args.warmup
 
@@ -406,6 +544,8 @@ def main():
     pkg = importlib.import_module("aws-global-accelerator-controller_b200")
     synth = importlib.import_module("aws-global-accelerator-controller_b200.synth")
     ranks_mod = importlib.import_module("aws-global-accelerator-controller_b200.ranks")
+    binding = ranks_mod.NumaBinding(local_rank)  # host tables are first-touched (and later pinned) on the GPU's own NUMA node
+    numa = binding.node
     R = ranks_mod.Ranks(backend="nccl", device=torch.device("cuda", local_rank))
     if rank == 0:
         ge.ensure_built()
@@ -420,7 +560,11 @@ def main():
     snap = synth.SynthSnapshot(cfg)
     o, a = snap.objects, snap.actual
     h2d_bytes = sum(int(c) * s for (_, c, s) in _table_arrays(abi, o, a))
-    pinned_bytes = _pin_host_tables(torch, abi, o, a)
+    pinned_bytes, pinned_addrs = _pin_host_tables(torch, abi, o, a)
+    binding.release()
+    # inputs that fit in L2 would make every timed step after the first an L2-warm re-read: rewrite an L2-sized buffer between steps
+    flush = h2d_bytes <= 2 * 126e6
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}") if flush else None
 
     # reprepare=True: every timed step runs the COMPLETE pipeline (digests, indexes, decide, placement); without it the
     # engine would reuse the prepared snapshot after the first diff, which is the incremental-mode optimisation, not the metric
@@ -436,15 +580,22 @@ def main():
     barrier()
     t0 = time.perf_counter()
     ms_kernels = 0.0
+    t_flush = 0.0
     for _ in range(args.steps):
+        if flush:
+            tf = time.perf_counter()
+            flush_buf.fill_(1)
+            torch.cuda.synchronize()
+            t_flush += time.perf_counter() - tf
         cs = eng.diff_device()
         ms_kernels += cs.ms_kernels
         launches += cs.kernel_launches
     barrier()
     t1 = time.perf_counter()
-    dt_dev = max_over_ranks(t1 - t0)
+    dt_dev = max_over_ranks(t1 - t0 - t_flush)
     b_alg = eng.algorithmic_bytes(cs)
     n_ops = int(cs.n_ops)
+    n_pairs = eng.counters().get("r53_pairs", 0)
     d2h_bytes = 4 * 3 * o.n_objects + 24 * n_ops + 17 * o.n_lbi + 4 * (o.n_objects + 1) + 4 * int(cs.n_dports)
     clocks = sampler.summary(t0, t1)
 
@@ -463,33 +614,56 @@ def main():
         e2e_parts["ms_d2h"] += full["ms_d2h"] / args.steps
     barrier()
     t3 = time.perf_counter()
-    dt_e2e = max_over_ranks(t3 - t2)
+    dt_e2e_local = t3 - t2
+    dt_e2e = max_over_ranks(dt_e2e_local)
+    e2e_per_rank = R.gather_counts([int(dt_e2e_local / args.steps * 1e6), int(e2e_parts["ms_h2d"] * 1e3), int(e2e_parts["ms_kernels"] * 1e3),
+                                    int(e2e_parts["ms_d2h"] * 1e3), -1 if numa is None else numa])
     sampler.stop()
+
+    # ---- parity gate (rank 0, outside the timed regions): the change set of the timed workload, bit for bit against the oracle
+    parity = {"checked": False}
+    hcs = None
+    if rank == 0:
+        eng.load(snap)
+        hcs = eng.diff()
+        if not args.no_parity:
+            ob = importlib.import_module("oracle.binding")
+            tp = time.perf_counter()
+            want = ob.diff(snap, snap.cluster, mode=1, threads=os.cpu_count() or 4)
+            bad = hcs.diff(want)
+            parity = {"checked": True, "equal": not bad, "oracle_objects": int(o.n_objects), "oracle": "oracle/oracle.cpp indexed mode (C++ port of the Go decision functions)",
+                      "arrays_compared": list(hcs.ARRAYS), "n_ops": int(len(want.ops)), "seconds": round(time.perf_counter() - tp, 2)}
+            if bad:
+                parity["mismatch"] = {"arrays": bad, "first": hcs.describe_first_mismatch(want)}
+            del want
+    eng.close()
 
     # ---- roofline pass (separate engine with per-stage CUDA events; not part of the timed numbers above)
     peak, peak_src = _peaks()
     stages = []
     if rank == 0:
-        eng.close()
         peng = pkg.Engine(cluster_name=snap.cluster, device=local_rank, stage_timing=True, reprepare=True)
         peng.load(snap)
         acc = {}
         reps = max(3, min(args.steps, 10))
         for it in range(reps + 2):
-            pcs = peng.diff_device()
+            if flush:
+                flush_buf.fill_(1)
+                torch.cuda.synchronize()
+            peng.diff_device()
             if it < 2:
                 continue
             for name, ms, nl in peng.stage_timings():
                 e = acc.setdefault(name, [0.0, 0])
                 e[0] += ms
                 e[1] += nl
-        tot = sum(v[0] for v in acc.values()) or 1.0
         stages = sorted(((name, v[0] / reps, v[1] // reps) for name, v in acc.items()), key=lambda x: -x[1])
         pipeline_ms = sum(s[1] for s in stages)
         top = stages[0]
         peng.close()
     total_objects = args.objects * world
 
+    line = None
     if rank == 0:
         value = total_objects * args.steps / dt_dev
         e2e_value = total_objects * args.steps / dt_e2e
@@ -498,13 +672,14 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8/u32 (bytes and indices)", "data": "synthetic",
-            "config": {"workload": f"BASELINE configs[{args.config - 1}]: {args.objects} Service+Ingress per GPU, multi-hostname route53 annotation, "
-                                   f"{a.n_accels} accelerators, {a.n_records} record sets, {a.n_lbs} load balancers",
+            "config": {"workload": _workload_name(args.config, args.objects) + f" per GPU; {a.n_accels} accelerators, {a.n_records} record sets, {a.n_lbs} load balancers",
                        "slab_layout": args.layout, "objects_per_gpu": args.objects, "parallelism": f"replicas x{world} (independent clusters, no collective)",
-                       "cache": f"inputs ({h2d_bytes / 1e6:.0f} MB per GPU) larger than L2 (126 MB); no flush needed", "seed": int(cfg.seed),
-                       "n_ops": n_ops, "algorithmic_bytes": b_alg, "bytes_per_object": b_alg / args.objects},
+                       "cache": _cache_note(h2d_bytes), "seed": int(cfg.seed),
+                       "n_ops": n_ops, "r53_pairs": n_pairs, "algorithmic_bytes": b_alg, "bytes_per_object": b_alg / args.objects},
+            "parity": parity,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "ms_per_step": dt_e2e / args.steps * 1e3,
-                    "pinned_host_bytes": pinned_bytes, **{k: round(v, 3) for k, v in e2e_parts.items()}},
+                    "pinned_host_bytes": pinned_bytes, **{k: round(v, 3) for k, v in e2e_parts.items()},
+                    "per_rank": [{"ms_per_step": c[0] / 1e3, "ms_h2d": c[1] / 1e3, "ms_kernels": c[2] / 1e3, "ms_d2h": c[3] / 1e3, "numa_node": c[4]} for c in e2e_per_rank]},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": top[0], "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
@@ -514,23 +689,15 @@ def main():
             "kernel_ms_per_step_cuda_events": ms_kernels / args.steps,
         }
         # the dominant kernel's own byte model (DESIGN.md "Per-kernel byte model"); the pipeline figure is the headline
-        host = pkg.Engine(cluster_name=snap.cluster, device=local_rank)
-        host.load(snap)
-        hcs = host.diff()
-        host.close()
         frac_ga = float(((hcs.status_ga & 0xFF) > 2).sum() + ((hcs.status_ga & 0xFF) == 1).sum()) / max(args.objects, 1)
         sb = [int(x) for x in hcs.section_begin]
-        # pairs = hostnames of the objects that reach ensureRoute53's hostname loop = R53 ensure ops + in-sync pairs; the
-        # engine reports the exact count through the r53_pairs stage size: approximate it by (commas + 1) of annotated objects
-        import numpy as _np
-        ak = _np_col(o.ann_key, o.n_ann, _np.uint64) >> _np.uint64(40)
-        n_r53 = int((ak == 63).sum())
-        n_pairs_model = int(round(n_r53 * (cfg.min_hostnames + cfg.max_hostnames) / 2.0 * 0.985))
-        models = kernel_byte_models(o, a, sb[1] - sb[0], n_pairs_model, frac_ga)
-        traffic = {}
-        tp = REPO / "profiles" / "r01_ncu_traffic.json"
-        if tp.exists() and args.config == 3 and args.objects == 1_000_000:  # the capture is of this exact workload
-            traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch", {})
+        models = kernel_byte_models(o, a, sb[1] - sb[0], n_pairs, frac_ga)
+        traffic, traffic_src = {}, None
+        for tp in (REPO / "profiles" / "r02_ncu_traffic.json", REPO / "profiles" / "r01_ncu_traffic.json"):
+            if tp.exists() and args.config == 3 and args.objects == 1_000_000:  # the capture is of this exact workload
+                traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch", {})
+                traffic_src = f"profiles/{tp.name} (ncu --set full, same workload)"
+                break
         # every stage with a byte model: its own achieved GB/s and fraction of the HBM roofline (CUDA-event stage times)
         line["roofline"]["kernels"] = {name: {"ms": round(ms, 4), "bytes": models[name], "achieved_gbs": round(models[name] / (ms * 1e-3) / 1e9, 1),
                                               "frac": round(models[name] / (ms * 1e-3) / 1e9 / peak, 4)}
@@ -541,7 +708,7 @@ def main():
             line["roofline"]["frac"] = line["roofline"]["achieved"] / peak
             line["roofline"]["kernel_bytes"] = kb
             line["roofline"]["traffic"] = traffic.get(top[0])
-            line["roofline"]["traffic_source"] = "profiles/r01_ncu_traffic.json (ncu --set full, same workload)" if top[0] in traffic else None
+            line["roofline"]["traffic_source"] = traffic_src if top[0] in traffic else None
         else:
             line["roofline"]["achieved"] = pipe_achieved
             line["roofline"]["frac"] = pipe_achieved / peak
@@ -572,14 +739,13 @@ def main():
         if not args.no_cpu_baseline:
             ob = importlib.import_module("oracle.binding")
             cores = os.cpu_count() or 1
-            cn = min(args.cpu_sample, args.objects)
-            csnap = synth.generate(args.config, cn)
-            ob.diff_raw(csnap.objects, csnap.actual, csnap.cluster.encode(), 1, cores)
-            tc = time.perf_counter()
-            reps = 3
-            for _ in range(reps):
-                ob.diff_raw(csnap.objects, csnap.actual, csnap.cluster.encode(), 1, cores)
-            cdt = (time.perf_counter() - tc) / reps
+            if args.cpu_sample and args.cpu_sample < args.objects:
+                csnap = synth.generate(args.config, args.cpu_sample)
+                same = False
+            else:
+                csnap, same = snap, True
+            cn = int(csnap.objects.n_objects)
+            scaling = _cpu_arm(ob, csnap, _thread_ladder(cores), reps=1)
             # the reference's own algorithm (per object: linear scan of all accelerators / all records, O(N*A)): timed at
             # two small sizes to show the quadratic growth; it is the bit-exactness arbiter, not a fair batch baseline
             faithful = []
@@ -591,8 +757,22 @@ def main():
                 faithful.append({"objects": fn, "seconds": round(fdt, 3), "objects_per_s": round(fn / fdt, 1)})
             line["cpu_faithful"] = {"kind": "port", "cores": 1, "runs": faithful,
                                     "note": "literal per-object linear scans as in the reference (quadratic); indexed multi-thread figure is cpu_baseline"}
-            line["cpu_baseline"] = {"value": cn / cdt, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"config {args.config} generator at {cn} objects, oracle indexed mode, {cores} threads, mean of {reps} runs; Go reference not timed (no toolchain)"}
+            line["cpu_baseline"] = {"value": scaling[cores], "unit": UNIT, "cores": cores, "kind": "port", "same_config": same,
+                                    "scaling": {str(k): round(v, 1) for k, v in sorted(scaling.items())},
+                                    "sample": f"{'the timed workload itself' if same else 'a sample'}: config {args.config} generator at {cn} objects, oracle indexed mode, "
+                                              f"{cores} threads (thread ladder in `scaling`); Go reference not timed (no toolchain)"}
+    _unpin(torch, pinned_addrs)
+    del snap, o, a, hcs, flush_buf
+    torch.cuda.empty_cache()
+    # ---- N > 1: BASELINE configs[3] — ONE 10^7-object cluster sharded by key hash across the GPUs (same JSON line)
+    if world > 1 and not args.no_sharded:
+        try:
+            rec = sharded_measure(args, R, rank, world, local_rank, args.sharded_objects, 4, args.sharded_steps, 3, with_single=not args.no_single, detail=False)
+        except Exception as ex:  # the replicas line must survive a failure here; every rank raises together (DistExchange agrees on errors)
+            rec = {"error": f"{type(ex).__name__}: {str(ex)[:300]}"}
+        if rank == 0:
+            line["sharded"] = rec
+    if rank == 0:
         print(json.dumps(line), flush=True)
     R.close()
 

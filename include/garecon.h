@@ -165,6 +165,17 @@ typedef struct gar_config {
 #define GAR_FLAG_STAGE_TIMING 1u /* bracket every stage with CUDA events; read them with gar_last_stage_timings */
 #define GAR_FLAG_REPREPARE 2u    /* rebuild the snapshot's digests and hash indexes on EVERY diff instead of once per load:
                                     for measuring the complete pipeline (bench.py "value", ncu captures) */
+#define GAR_FLAG_NO_ORPHANS 4u   /* gar_diff leaves the two orphan sections empty: nothing is ever deleted on the strength of a key being
+                                    ABSENT from the object table.  Deletes then come only from objects in the table (unmanaged / de-annotated)
+                                    and from keys passed explicitly to gar_diff_keys as deleted (the reference's own rule: cleanup runs on an
+                                    observed delete event, globalaccelerator/controller.go:113-173) */
+#define GAR_FLAG_ALLOW_EMPTY_CACHE 8u /* see "Orphan sweep precondition" below */
+/* Orphan sweep precondition.  The orphan sections of gar_diff stand for the delete events of every owner key that is tagged on an
+   AWS resource of this cluster but has no object in the table: they are only right when the table is the COMPLETE, SYNCED informer
+   cache of the whole cluster (HasSynced() true on both informers, no namespace-scoped cache, no failed or partial list, all slices
+   present in sharded mode).  A caller that cannot guarantee that must set GAR_FLAG_NO_ORPHANS.  As a last line of defence gar_diff
+   refuses (GAR_E_STATE) to emit orphan deletes when the object table is EMPTY while owned resources exist — the signature of an
+   informer that has not synced — unless GAR_FLAG_ALLOW_EMPTY_CACHE says the empty cache is real (the last object was deleted). */
 
 /* ---------------------------------------------------------------- output: the change set */
 
@@ -458,6 +469,15 @@ typedef struct gar_stage_timing {
   uint64_t bytes;   /* algorithmic bytes of the stage (DESIGN.md "Per-kernel byte model"), 0 if not modelled */
 } gar_stage_timing;
 uint32_t gar_last_stage_timings(gar_engine *e, gar_stage_timing *out, uint32_t cap);
+
+/* Work counters of the last gar_diff / gar_diff_device / gar_diff_keys: exact sizes of the intermediate relations, for the
+   per-kernel byte models of the roofline report (bench.py).  out[GAR_CTR_*]; returns the number of counters written. */
+enum {
+  GAR_CTR_R53_PAIRS = 0,   /* (object, route53 hostname) pairs evaluated by the r53_pairs stage (route53.go:84-124 loop bodies) */
+  GAR_CTR_DPORTS = 1,      /* ports parsed from listen-ports annotations */
+  GAR_CTR_N = 2
+};
+uint32_t gar_last_counters(gar_engine *e, uint64_t *out, uint32_t cap);
 
 #ifdef __cplusplus
 }

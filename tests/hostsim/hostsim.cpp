@@ -100,6 +100,7 @@ struct gar_engine {
   std::vector<u32> key_rows;
   u64 input_bytes = 0;
   u32 launches = 0;
+  u32 flags = 0;
 
   template <class F>
   void for_each(const char *, u32 n, const F &f) {
@@ -168,6 +169,7 @@ extern "C" {
 int gar_engine_create(const gar_config *cfg, gar_engine **out) {
   auto *e = new gar_engine();
   e->cluster = cfg->cluster_name ? cfg->cluster_name : "";
+  e->flags = cfg->flags;
   e->cluster_pad.assign(e->cluster.size() + 64, 0);
   memcpy(e->cluster_pad.data(), e->cluster.data(), e->cluster.size());
   *out = e;
@@ -209,6 +211,8 @@ static int diff_impl(gar_engine *e, gar_changeset *out, const gar_keyset *ks, co
     }
   }
   Pipeline<gar_engine> &P = *e->pipe;
+  P.orphan_sweep = !(e->flags & GAR_FLAG_NO_ORPHANS);
+  P.allow_empty_cache = (e->flags & GAR_FLAG_ALLOW_EMPTY_CACHE) != 0;
   DiffCounts dc{};
   g_vote_outside_warp = g_nonuniform_vote = false;
   auto ops_alloc = [&](u64 nops) { return e->o_ops.ensure(sizeof(gar_op) * (size_t)(nops + 1)); };
@@ -244,6 +248,10 @@ static int diff_impl(gar_engine *e, gar_changeset *out, const gar_keyset *ks, co
   if (g_nonuniform_vote || g_vote_outside_warp) {
     e->err = g_nonuniform_vote ? "non-uniform warp vote: some lane did not reach a GAR_ANY that others executed (would hang on the GPU)"
                                : "GAR_ANY executed outside a warp-synchronous kernel";
+    return GAR_E_STATE;
+  }
+  if (rc == GAR_REFUSE_EMPTY_CACHE) {
+    e->err = "the object table is empty but this cluster still owns AWS resources: refusing to emit delete-everything orphan sections";
     return GAR_E_STATE;
   }
   if (rc != GAR_OK) {
@@ -316,4 +324,10 @@ const char *gar_last_error(const gar_engine *e) { return e ? e->err.c_str() : g_
 const char *gar_version(void) { return "garecon hostsim (test build)"; }
 uint64_t gar_algorithmic_bytes(const gar_engine *, const gar_changeset *) { return 0; }
 uint32_t gar_last_stage_timings(gar_engine *, gar_stage_timing *, uint32_t) { return 0; }
+uint32_t gar_last_counters(gar_engine *e, uint64_t *out, uint32_t cap) {
+  if (!e || !out || cap < GAR_CTR_N) return 0;
+  out[GAR_CTR_R53_PAIRS] = e->pipe ? e->pipe->n_pairs : 0;
+  out[GAR_CTR_DPORTS] = e->pipe ? e->pipe->n_dports : 0;
+  return GAR_CTR_N;
+}
 }

@@ -78,6 +78,52 @@ def test_config3_1e6_bit_exact_and_idempotent(garecon, oracle, engine, synth):
     assert got.checksum() == want.checksum()
 
 
+def test_bench_workload_1e6_column_major_bit_exact(garecon, oracle, engine, synth):
+    """The exact workload bench.py times on rank 0 (configs[2], 10^6 objects, the preset's seed, COLUMN-major slabs) against the
+    oracle — bench.py repeats this comparison inside every run (`parity` in its JSON line)."""
+    cfg = synth.preset(3, 1_000_000)
+    cfg.layout = 1
+    snap = synth.SynthSnapshot(cfg)
+    engine.load(snap)
+    got = engine.diff()
+    _check_properties(got, snap)
+    want = oracle.diff(snap, snap.cluster, mode=1, threads=os.cpu_count() or 4)
+    assert got.diff(want) == [], got.describe_first_mismatch(want)
+    assert got.checksum() == want.checksum()
+
+
+def _mem_available_gb():
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                return int(line.split()[1]) / 1e6
+    except OSError:
+        pass
+    return 0.0
+
+
+def test_config4_1e7_single_gpu_bit_exact(garecon, oracle, synth):
+    """BASELINE configs[3] at its full size on ONE GPU: the 10^7-object cluster bench.py shards across GPUs (generator preset 4,
+    16 chunks, column-major slabs), diffed unsharded and compared bit for bit with the oracle on all host cores.  This pins the
+    single-GPU result that the sharded runs are checksum-compared with (bench.py `sharded.checksum_equal`)."""
+    if _mem_available_gb() < 120:
+        pytest.skip("needs ~100 GB of host memory for the 10^7-object tables, the oracle's indexes and two change sets")
+    shard = importlib.import_module("aws-global-accelerator-controller_b200.shard")
+    n = 10_000_000
+    slices = synth.cluster_slices(4, n, 1, layout=1, n_chunks=16, threads=min(32, os.cpu_count() or 4))
+    union = garecon.tables.concat_slices(slices)
+    del slices
+    assert union.objects.n_objects == n
+    with garecon.Engine(cluster_name="default", reprepare=True) as e:
+        e.load(union)
+        got = e.diff()
+    _check_properties(got, union)
+    want = oracle.diff(union, "default", mode=1, threads=os.cpu_count() or 4)
+    assert got.diff(want) == [], got.describe_first_mismatch(want)
+    assert shard.canonical_checksum(got) == shard.canonical_checksum(want)
+    assert len(got.ops) > n // 4
+
+
 def test_adversarial_1e6_properties_and_sampled_parity(garecon, oracle, engine, synth):
     """BASELINE configs[4]: 90% colliding hostnames + 64-port listeners at 10^6; full oracle comparison."""
     snap = synth.generate(5, 1_000_000)

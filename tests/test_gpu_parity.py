@@ -36,13 +36,36 @@ def test_objects_without_any_actual_state(garecon, oracle, engine):
 
 
 def test_orphans_only(garecon, oracle, engine):
+    """An EMPTY object table while the cluster still owns resources: refused by default (an unsynced informer looks like this,
+    include/garecon.h "Orphan sweep precondition"); with allow_empty_cache the orphan sections equal the oracle's."""
     _, actual = randmodel.make(9, n_objects=50)
     snap = garecon.pack([], actual)
     engine.load(snap)
-    got = engine.diff()
+    with pytest.raises(garecon.abi.GarError, match="object table is empty") as ei:
+        engine.diff()
+    assert ei.value.rc == garecon.abi.GAR_E_STATE
+    with garecon.Engine(cluster_name="default", allow_empty_cache=True) as e:
+        e.load(snap)
+        got = e.diff()
     want = oracle.diff(snap, "default", mode=1)
     assert got.diff(want) == [], got.describe_first_mismatch(want)
     assert len(got.ops) > 0
+
+
+def test_no_orphans_flag_leaves_the_orphan_sections_empty(garecon, oracle):
+    """GAR_FLAG_NO_ORPHANS: nothing is deleted on the strength of a key being absent; the object sections are unchanged."""
+    objects, actual = randmodel.make(12, n_objects=80)
+    snap = garecon.pack(objects[:40], actual)  # half of the objects are gone: their resources are orphans
+    want = oracle.diff(snap, "default", mode=1)
+    sb = [int(x) for x in want.section_begin]
+    assert sb[2] - sb[1] > 0 and sb[4] - sb[3] > 0
+    with garecon.Engine(cluster_name="default", orphans=False) as e:
+        e.load(snap)
+        got = e.diff()
+    gb = [int(x) for x in got.section_begin]
+    assert gb[2] == gb[1] and gb[4] == gb[3]
+    assert np.array_equal(got.ops[gb[0]:gb[1]], want.ops[sb[0]:sb[1]]) and np.array_equal(got.ops[gb[2]:gb[3]], want.ops[sb[2]:sb[3]])
+    assert np.array_equal(got.status_ga, want.status_ga) and np.array_equal(got.status_r53, want.status_r53)
 
 
 def test_golden_hostnames_through_the_abi(garecon, engine):

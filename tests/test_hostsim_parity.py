@@ -37,6 +37,31 @@ def test_hostsim_empty_snapshot(garecon, oracle, hostsim):
     assert len(got.ops) == 0
 
 
+def test_hostsim_empty_cache_guard_and_no_orphans_flag(garecon, oracle):
+    """include/garecon.h "Orphan sweep precondition" on the CPU tier (same pipeline text as the CUDA engine)."""
+    import numpy as np
+    import __graft_entry__ as ge
+    lib = garecon.abi.load_library(ge.build_hostsim())
+    objects, actual = randmodel.make(12, n_objects=80)
+    only_actual = garecon.pack([], actual)
+    with garecon.Engine(cluster_name="default", lib=lib) as e:
+        e.load(only_actual)
+        with pytest.raises(garecon.abi.GarError, match="object table is empty"):
+            e.diff()
+    with garecon.Engine(cluster_name="default", lib=lib, allow_empty_cache=True) as e:
+        e.load(only_actual)
+        assert e.diff().diff(oracle.diff(only_actual, "default", mode=1)) == []
+    snap = garecon.pack(objects[:40], actual)
+    want = oracle.diff(snap, "default", mode=1)
+    sb = [int(x) for x in want.section_begin]
+    with garecon.Engine(cluster_name="default", lib=lib, orphans=False) as e:
+        e.load(snap)
+        got = e.diff()
+    gb = [int(x) for x in got.section_begin]
+    assert gb[2] == gb[1] and gb[4] == gb[3] and sb[2] > sb[1] and sb[4] > sb[3]
+    assert np.array_equal(got.ops[gb[0]:gb[1]], want.ops[sb[0]:sb[1]]) and np.array_equal(got.ops[gb[2]:gb[3]], want.ops[sb[2]:sb[3]])
+
+
 def test_hostsim_other_cluster_name(garecon, oracle):
     import __graft_entry__ as ge
     lib = garecon.abi.load_library(ge.build_hostsim())

@@ -163,18 +163,48 @@ def check_slices(garecon, want, parts, n_total):
     assert np.array_equal(got["ops"], want.ops), first_diff(got["ops"].tolist(), want.ops.tolist())
 
 
-@pytest.mark.parametrize("cfg,n_total,n_ranks,layout", [(4, 1500, 3, 0), (5, 1200, 4, 0), (3, 1000, 2, 0), (4, 1200, 3, 1)])
-def test_generator_slices_on_hostsim(garecon, oracle, hostlib, cfg, n_total, n_ranks, layout):
+@pytest.mark.parametrize("cfg,n_total,n_ranks,layout,n_chunks", [(4, 1500, 3, 0, None), (5, 1200, 4, 0, None), (3, 1000, 2, 0, None), (4, 1200, 3, 1, None),
+                                                                 (4, 1600, 2, 1, 8), (4, 1600, 4, 1, 8)])
+def test_generator_slices_on_hostsim(garecon, oracle, hostlib, cfg, n_total, n_ranks, layout, n_chunks):
     """Chunked generator output (objects / accelerators / LBs of different chunks on one rank) == the union, via the oracle;
-    also with column-major string slabs in the slices."""
+    also with column-major string slabs in the slices, and with several generator chunks per rank (bench.py's 10^7 cluster is
+    16 chunks whatever the number of GPUs)."""
     synth = importlib.import_module("aws-global-accelerator-controller_b200.synth")
-    slices = synth.cluster_slices(cfg, n_total, n_ranks, layout=layout)
+    slices = synth.cluster_slices(cfg, n_total, n_ranks, layout=layout, n_chunks=n_chunks, threads=4)
     union = garecon.tables.concat_slices(slices)
     assert union.objects.n_objects == n_total
     want = oracle.diff(union, "default", mode=1)
     parts = run_sharded_slices(garecon, hostlib, slices)
     check_slices(garecon, want, parts, n_total)
     assert len(want.ops) > n_total // 4
+    # the merge-free checksum bench.py uses at 10^7 objects: adds over the shards to the unsharded value
+    assert shard.add_checksums([shard.canonical_checksum(p) for p in parts]) == shard.canonical_checksum(want)
+
+
+def test_canonical_checksum_is_sensitive(garecon, oracle):
+    """The additive checksum notices a changed status word, a changed op field, two ops of one object swapped, and an op moved
+    to another section boundary."""
+    import copy
+    objects, actual = randmodel.make(4, n_objects=120)
+    cs = oracle.diff(garecon.pack(objects, actual), "default", mode=1)
+    base = shard.canonical_checksum(cs)
+    assert base == shard.canonical_checksum(copy.deepcopy(cs))
+    x = copy.deepcopy(cs)
+    x.status_r53[7] ^= 0x100
+    assert shard.canonical_checksum(x) != base
+    x = copy.deepcopy(cs)
+    x.ops["a1"][3] ^= 1
+    assert shard.canonical_checksum(x) != base
+    sb = [int(v) for v in cs.section_begin]
+    objs = cs.ops["obj"][sb[0]:sb[1]]
+    same = [k for k in range(len(objs) - 1) if objs[k] == objs[k + 1] and cs.ops[k] != cs.ops[k + 1]]
+    assert same, "the model should contain an object with two different GA ops"
+    x = copy.deepcopy(cs)
+    x.ops[[same[0], same[0] + 1]] = x.ops[[same[0] + 1, same[0]]]
+    assert shard.canonical_checksum(x) != base
+    x = copy.deepcopy(cs)
+    x.section_begin[1] -= 1
+    assert shard.canonical_checksum(x) != base
 
 
 # ------------------------------------------------------------------ the torch.distributed data path, 2 processes on gloo
