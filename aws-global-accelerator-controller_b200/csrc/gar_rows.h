@@ -877,6 +877,47 @@ GAR_HD bool u_accelerator_changed(const DevTables &T, const Work &W, bool act, u
   return ch;
 }
 
+// ---- self-observation (include/garecon.h): what an object's own earlier ops mean for its later lbIngress iterations.
+// Everything here is scalar (no votes): objects with a second load balancer that reaches the update stage are rare.
+
+// What the object's user tags do, once written, to the tags ListGlobalAcceleratorByResource filters on (global_accelerator.go:99-103)
+// and to the target-hostname tag (createAccelerator :654-675 / updateAccelerator :720-735 append them after the system tags; a tag
+// list reads "later duplicate wins", :560-563).
+GAR_HD void user_tag_effects(const DevTables &T, const Work &W, u32 i, u32 kind, Str okey, bool *keep_visible, bool *user_thost) {
+  *keep_visible = true;
+  *user_thost = false;
+  if (!(W.derived[i] & OBJ_HAS_TAGS_ANN)) return;
+  Str tags = mkstr(T.o.slab, W.ann_tags[i]);
+  bool m_ok = true, o_ok = true, c_ok = true;  // verdict of the LAST ok piece of each key
+  u32 pos = 0;
+  Str piece;
+  while (next_piece(tags, &pos, &piece)) {
+    TagPiece tp = tag_piece(piece);
+    if (!tp.ok) continue;
+    if (STREQ_LIT(tp.key, TAG_MANAGED)) m_ok = STREQ_LIT(tp.val, "true");
+    else if (STREQ_LIT(tp.key, TAG_OWNER))
+      o_ok = tp.val.n == 8 + okey.n && (kind == GAR_KIND_SERVICE ? lit_eq_at(tp.val, 0, "service/") : lit_eq_at(tp.val, 0, "ingress/")) &&
+             streq(substr(tp.val, 8, okey.n), okey);
+    else if (STREQ_LIT(tp.key, TAG_CLUSTER)) c_ok = streq(tp.val, Str{T.cluster, T.cluster_len});
+    else if (STREQ_LIT(tp.key, TAG_THOST)) *user_thost = true;
+  }
+  *keep_visible = m_ok && o_ok && c_ok;
+}
+// endpointContainsLB (:494-501) on the snapshot's endpoint group of a digested accelerator
+GAR_HD bool eg_contains(const DevTables &T, const AccDigest &d, Str lb_arn) {
+  u32 nep = d.n_eps == 0xFFFF ? T.a.eg_ep_begin[d.eg + 1] - d.ep_begin : d.n_eps;
+  for (u32 x = 0; x < nep; x++)
+    if (streq(mkstr(T.a.slab, x == 0 ? d.ep0 : T.a.ep_id[d.ep_begin + x]), lb_arn)) return true;
+  return false;
+}
+// A later iteration (the object already went through the update/create stage with load balancer prev_lb):
+//   * its accelerators satisfy acceleratorChanged for prev_lb, have one desired listener and one endpoint group;
+//   * an endpoint group that was created or replaced holds exactly [prev_lb] (updateEndpointGroup replaces, :987-1002),
+//     an untouched one the snapshot's list;
+//   * the accelerator of an earlier GA_CREATE_CHAIN is listed as GAR_PENDING — unless the user tags overwrite a tag the
+//     list call filters on: then nothing the object wrote is listed and the reference creates again.
+GAR_HD void ga_later_step(const DevTables &T, const Work &W, u32 i, u32 kind, Str okey, u64 okh, u32 jb, u32 j, u32 lb, u32 prev_lb, bool pending, OpSink &s, u32 *ev);
+
 // Written warp-synchronously: every lane of the warp runs the same outer loops (lbIngress index, accelerator of the
 // owner) and the same probe / compare steps under GAR_ANY votes, carrying its own predicates; nothing returns from
 // inside a loop.  `valid` is false for padding lanes beyond the last object.
@@ -911,6 +952,8 @@ GAR_HD u32 ga_reconcile(const DevTables &T, const Work &W, u32 i, bool valid, Op
   }
   u32 ev = 0;
   bool stop = false;
+  u32 prev_lb = GAR_NONE;  // load balancer of the previous iteration that reached the update/create stage
+  bool pending = false;    // that stage emitted GA_CREATE_CHAIN: later iterations see a GAR_PENDING accelerator
   for (u32 j = 0;; j++) {
     bool act = ensure && !stop && j < nj;
     if (!GAR_ANY(act)) break;
@@ -953,6 +996,11 @@ GAR_HD u32 ga_reconcile(const DevTables &T, const Work &W, u32 i, bool valid, Op
         go = true;
       }
     }
+    // the first iteration that gets here evaluates the snapshot (all lanes together); later ones (rare) evaluate what the
+    // object's own earlier ops left behind, scalar
+    const bool later = go && prev_lb != GAR_NONE;
+    if (later) ga_later_step(T, W, i, kind, okey, okh, jb, j, lb, prev_lb, pending, s, &ev);
+    go = go && !later;
     Cursor oc = u_open(W.ix_owner, go, okh);
     Str lb_arn = go ? mkstr(A.slab, A.lb_arn[lb]) : Str{A.slab, 0};
     u32 nacc = 0;
@@ -1011,10 +1059,47 @@ GAR_HD u32 ga_reconcile(const DevTables &T, const Work &W, u32 i, bool valid, Op
     if (go && !stop && nacc == 0) {
       s.put(GAR_OP_HEAD(GAR_OP_GA_CREATE_CHAIN, GAR_CTRL_GA, kind), i, j, lb, GAR_NONE, GAR_NONE);
       ev |= GAR_EV_CREATED;
+      pending = true;
     }
+    if ((go || later) && !stop) prev_lb = lb;
   }
   if (ensure && !stop) result = GAR_STATUS(GAR_ST_OK, 0, ev);
   return result;
+}
+
+GAR_HD void ga_later_step(const DevTables &T, const Work &W, u32 i, u32 kind, Str okey, u64 okh, u32 jb, u32 j, u32 lb, u32 prev_lb, bool pending, OpSink &s, u32 *ev) {
+  const gar_actual &A = T.a;
+  bool keep_visible, user_thost;
+  user_tag_effects(T, W, i, kind, okey, &keep_visible, &user_thost);
+  if (!keep_visible) {  // nothing this object wrote is listed any more: the list is empty again
+    s.put(GAR_OP_HEAD(GAR_OP_GA_CREATE_CHAIN, GAR_CTRL_GA, kind), i, j, lb, GAR_NONE, GAR_NONE);
+    *ev |= GAR_EV_CREATED;
+    return;
+  }
+  Str lb_arn = mkstr(A.slab, A.lb_arn[lb]);
+  const bool dns_differs = !user_thost && !streq(mkstr(A.slab, A.lb_dns[lb]), mkstr(A.slab, A.lb_dns[prev_lb]));
+  const bool arn_differs = !streq(lb_arn, mkstr(A.slab, A.lb_arn[prev_lb]));
+  if (pending) {
+    if (dns_differs) s.put(GAR_OP_HEAD(GAR_OP_GA_UPDATE_ACCEL, GAR_CTRL_GA, kind), i, j, GAR_PENDING, lb, GAR_NONE);
+    if (arn_differs) s.put(GAR_OP_HEAD(GAR_OP_GA_UPDATE_EG, GAR_CTRL_GA, kind), i, j, GAR_PENDING, GAR_PENDING, lb);
+  }
+  OwnerIter it = owner_open(W, okh, okey);
+  for (u32 acc; (acc = owner_next(T, W, kind, it)) != GAR_NONE;) {
+    if (dns_differs) s.put(GAR_OP_HEAD(GAR_OP_GA_UPDATE_ACCEL, GAR_CTRL_GA, kind), i, j, acc, lb, GAR_NONE);
+    const AccDigest d = W.acc_digest[acc];
+    // (more than one listener / endpoint group ended the object at its first iteration)
+    const bool created = (d.flags & (ACCD_LIS_NONE | ACCD_EG_NONE)) != 0;
+    // replaced so far <=> created, or some earlier iteration's load balancer was not in the snapshot's endpoint list
+    bool replaced = created;
+    for (u32 jp = 0; jp < j && !replaced; jp++) {
+      if (W.tok_code[jb + jp] > GAR_TOK_NLB) continue;  // DetectCloudProvider error: that iteration was skipped
+      u32 st;
+      u32 lbp = find_lb(T, W, mkstr(T.o.slab, W.tok_region[jb + jp]), mkstr(T.o.slab, W.tok_name[jb + jp]), &st);
+      if (lbp != GAR_NONE && !eg_contains(T, d, mkstr(A.slab, A.lb_arn[lbp]))) replaced = true;
+    }
+    const bool contains = replaced ? !arn_differs : eg_contains(T, d, lb_arn);
+    if (!contains) s.put(GAR_OP_HEAD(GAR_OP_GA_UPDATE_EG, GAR_CTRL_GA, kind), i, j, acc, created ? GAR_PENDING : d.eg, lb);
+  }
 }
 
 // ------------------------------------------------------------------ (a9)(a10) Route53 decisions of one object
@@ -1149,6 +1234,17 @@ GAR_HD void r53_cleanup(const DevTables &T, const Work &W, u32 obj, u32 kind, co
   }
 }
 
+// does the piece `hn` of strings.Split(all, ",") (a slice of `all`) also occur, byte for byte, earlier in the list?  (scalar)
+GAR_HD bool piece_seen_before(Str all, Str hn) {
+  u32 pos = 0;
+  Str piece;
+  while (next_piece(all, &pos, &piece)) {
+    if (piece.p >= hn.p) return false;
+    if (streq(piece, hn)) return true;
+  }
+  return false;
+}
+
 // Warp-synchronous like ga_reconcile: uniform loops over lbIngress index, hostname index and owned value rows; every
 // probe and compare is a voted step.
 GAR_HD u32 r53_reconcile(const DevTables &T, const Work &W, u32 i, bool valid, OpSink &s) {
@@ -1181,6 +1277,10 @@ GAR_HD u32 r53_reconcile(const DevTables &T, const Work &W, u32 i, bool valid, O
   }
   u32 ev = 0;
   bool stop = false, collected = false;
+  // self-observation (include/garecon.h): a hostname this object visited before — earlier in the annotation or at an earlier
+  // lbIngress — has its alias record in place, pointing at the accelerator of that visit
+  bool have_prev = false;
+  Str prev_acc_dns{A.slab, 0};
   for (u32 j = 0;; j++) {
     bool act = ensure && !stop && j < nj;
     if (!GAR_ANY(act)) break;
@@ -1263,16 +1363,26 @@ GAR_HD u32 r53_reconcile(const DevTables &T, const Work &W, u32 i, bool valid, O
       bool shape = have && al.n == acc_dns.n + 1 && al.p[al.n - 1] == '.';
       bool same = u_streq(shape, substr(al, 0, shape ? acc_dns.n : 0), acc_dns);
       if (more) {
-        if (rec == GAR_NONE) {
-          s.put(GAR_OP_HEAD(GAR_OP_R53_CREATE, GAR_CTRL_R53, kind), i, GAR_R53_SUB(j, k), zone, acc, GAR_NONE);
-          created = true;
-        } else if (!same) {
-          s.put(GAR_OP_HEAD(GAR_OP_R53_UPSERT_A, GAR_CTRL_R53, kind), i, GAR_R53_SUB(j, k), zone, acc, rec);
+        if (!piece_seen_before(hostnames, hn)) {  // a repeated hostname was visited a moment ago with the same accelerator: in sync now
+          if (!have_prev) {
+            if (rec == GAR_NONE) {
+              s.put(GAR_OP_HEAD(GAR_OP_R53_CREATE, GAR_CTRL_R53, kind), i, GAR_R53_SUB(j, k), zone, acc, GAR_NONE);
+              created = true;
+            } else if (!same) {
+              s.put(GAR_OP_HEAD(GAR_OP_R53_UPSERT_A, GAR_CTRL_R53, kind), i, GAR_R53_SUB(j, k), zone, acc, rec);
+            }
+          } else if (!streq(acc_dns, prev_acc_dns)) {  // needRecordsUpdate only fires when the accelerator changed since the last visit
+            s.put(GAR_OP_HEAD(GAR_OP_R53_UPSERT_A, GAR_CTRL_R53, kind), i, GAR_R53_SUB(j, k), zone, acc, rec == GAR_NONE ? GAR_PENDING : rec);
+          }
         }
         k++;
       }
     }
     if (go && !stop && created) ev |= GAR_EV_CREATED;
+    if (go && !stop) {
+      have_prev = true;
+      prev_acc_dns = acc_dns;
+    }
   }
   if (ensure && !stop) result = GAR_STATUS(GAR_ST_OK, 0, ev);
   return result;
@@ -1441,8 +1551,18 @@ GAR_HD u32 r53_combine(const DevTables &T, const Work &W, u32 i, u32 t, bool val
     u32 kind = T.o.obj_kind[i], acc = W.r53_acc[i];
     bool created = false, stop = false;
     u32 k = 0;
-    for (u32 p = W.pair_begin[t]; p < W.pair_begin[t + 1] && !stop; p++, k++) {
+    const u32 p0 = W.pair_begin[t];
+    for (u32 p = p0; p < W.pair_begin[t + 1] && !stop; p++, k++) {
       u32 code = W.pair_code[p];
+      if (code == PAIR_CREATE || code == PAIR_UPSERT) {
+        // self-observation: the same hostname earlier in the annotation got this very op a moment ago -> in sync now
+        Str hn = mkstr(T.o.slab, W.pair_hn[p]);
+        for (u32 q = p0; q < p; q++)
+          if (streq(mkstr(T.o.slab, W.pair_hn[q]), hn)) {
+            code = PAIR_IN_SYNC;
+            break;
+          }
+      }
       if (code == PAIR_NO_ZONE) {
         st = GAR_STATUS(GAR_ST_ERR_RETRY, GAR_D_NO_HOSTED_ZONE, 0);
         stop = true;

@@ -142,16 +142,10 @@ class Packer {
     return (uint32_t)acc_enabled_.size() - 1;
   }
   uint32_t AddZone(const HostedZone &z) {
-    zone_name_.push_back(put(AZONE, z.name));
-    for (auto &r : z.records) {
-      rec_name_.push_back(put(ARECNAME, r.name));
-      rec_type_.push_back(r.type);
-      rec_has_alias_.push_back(r.has_alias ? 1 : 0);
-      rec_alias_.push_back(r.has_alias ? put(AALIAS, r.alias_dns) : 0);
-      for (auto &v : r.values) val_value_.push_back(put(AVAL, v));
-      val_b_.push_back((uint32_t)val_value_.size());
-    }
-    rec_b_.push_back((uint32_t)rec_name_.size());
+    close_zone();
+    open_zone(z);
+    for (auto &r : z.records) add_record(r);
+    close_zone();
     return (uint32_t)zone_name_.size() - 1;
   }
   void AddCloud(const CloudState &c) {
@@ -160,8 +154,46 @@ class Packer {
     for (auto &z : c.zones) AddZone(z);
   }
 
+  // ---- paginated ingestion: one call per page of the reference's pagers, in the order the pages arrive.  Row order IS list
+  // order (the change set's canonical order and "first row wins" lookups depend on it), so pages are append-only:
+  //   DescribeLoadBalancers pages, every region listed                  load_balancer.go:13-30
+  //   ListAccelerators pages (100 per page), each accelerator with its ListTagsForResource / ListListeners /
+  //   ListEndpointGroups results attached                               global_accelerator.go:624-652,789-813,885-907
+  //   ListHostedZones pages (100), then per zone its ListResourceRecordSets pages (300)   route53.go:199-214,317-333
+  // Returns the row of the page's first element.
+  uint32_t AddLoadBalancerPage(const std::vector<LoadBalancer> &page) {
+    uint32_t first = (uint32_t)lb_state_.size();
+    for (auto &lb : page) AddLoadBalancer(lb);
+    return first;
+  }
+  uint32_t AddAcceleratorPage(const std::vector<Accelerator> &page) {
+    uint32_t first = (uint32_t)acc_enabled_.size();
+    for (auto &a : page) AddAccelerator(a);
+    return first;
+  }
+  // zone rows are fixed by the ListHostedZones pages; record pages follow zone by zone (AddRecordSetPage)
+  uint32_t AddHostedZonePage(const std::vector<HostedZone> &page) {
+    uint32_t first = (uint32_t)pending_zones_.size();
+    for (auto &z : page) pending_zones_.push_back(HostedZone{z.id, z.name, {}});
+    return first;
+  }
+  // One ListResourceRecordSets page of zone row `zone`.  Zones must be visited in ascending row order (records are stored
+  // zone-major); a zone's pages are consecutive; zones that are skipped have no record sets.  false = out of order.
+  bool AddRecordSetPage(uint32_t zone, const std::vector<RecordSet> &page) {
+    if (zone >= pending_zones_.size() || zone < zone_name_.size() - (zone_open_ ? 1 : 0)) return false;
+    if (!(zone_open_ && zone == zone_name_.size() - 1)) {
+      close_zone();
+      while (zone_name_.size() < zone) open_zone(pending_zones_[zone_name_.size()]), close_zone();  // zones without records
+      open_zone(pending_zones_[zone]);
+    }
+    for (auto &r : page) add_record(r);
+    return true;
+  }
+
   // ---- publish: the two table structs point into this object's buffers (valid until the next Add* / Reset)
   void Finish() {
+    close_zone();
+    while (zone_name_.size() < pending_zones_.size()) open_zone(pending_zones_[zone_name_.size()]), close_zone();  // listed zones without record pages
     // concatenate the column buffers into the two slabs and rebase every reference (no padding needed on the host side:
     // gar_snapshot_load copies and pads on the device)
     uint64_t base[NCOLS];
@@ -231,6 +263,25 @@ class Packer {
     if (m.size() < 4096) m.emplace(s, r);
     return r;
   }
+  void open_zone(const HostedZone &z) {
+    zone_name_.push_back(put(AZONE, z.name));
+    zone_open_ = true;
+  }
+  void close_zone() {
+    if (!zone_open_) return;
+    rec_b_.push_back((uint32_t)rec_name_.size());
+    zone_open_ = false;
+  }
+  void add_record(const RecordSet &r) {
+    rec_name_.push_back(put(ARECNAME, r.name));
+    rec_type_.push_back(r.type);
+    rec_has_alias_.push_back(r.has_alias ? 1 : 0);
+    rec_alias_.push_back(r.has_alias ? put(AALIAS, r.alias_dns) : 0);
+    for (auto &v : r.values) val_value_.push_back(put(AVAL, v));
+    val_b_.push_back((uint32_t)val_value_.size());
+  }
+  bool zone_open_ = false;
+  std::vector<HostedZone> pending_zones_;  // zones listed by AddHostedZonePage (metadata only)
   std::string col_[NCOLS];
   std::string os_, as_;
   uint64_t os_len_ = 0, as_len_ = 0;

@@ -99,13 +99,22 @@ struct BatchStats {
 
 // KeyToRow: "ns/name" -> object row of the packed snapshot, or -1 when the key is no longer in the cache
 // (the reference's kerrors.IsNotFound branch, reconcile.go:61-62: processDelete; in the batch design the delete
-// decisions arrive as the orphan sections of the change set, so such a key is simply forgotten).
+// decisions arrive as the orphan sections of the change set, so such a key is forgotten unless its cleanup failed).
 using KeyToRowFunc = std::function<int64_t(const std::string &)>;
-using ExecuteOpsFunc = std::function<void(const gar_changeset &)>;
+// What went wrong while the ops were executed (host/executor.hpp ExecReport carries the same two maps): the reference returns
+// the AWS error from process{Create,Update,Delete} and reconcileHandler requeues the key rate-limited (reconcile.go:75-77).
+struct OpFailures {
+  std::map<std::pair<uint8_t, uint32_t>, std::string> objects;  // (controller, object row) -> first error
+  std::map<std::string, std::string> owners;                    // "service/ns/name" of a key that left the cache -> error of its cleanup
+};
+using ExecuteOpsFunc = std::function<OpFailures(const gar_changeset &)>;
 
 // Batch counterpart of `for ProcessNextWorkItem(...) {}` (globalaccelerator/controller.go:222-230): one diff,
-// then reconcileHandler's switch for every drained key.  `kind` selects the Service or the Ingress queue.
-inline int ProcessBatch(gar_engine *engine, RateLimitingQueue &queue, Controller ctrl, KeyToRowFunc keyToRow, ExecuteOpsFunc executeOps,
+// then reconcileHandler's switch for every drained key.  `ctrl` + `kind` name the queue (the reference has a Service and an
+// Ingress queue per controller); `executeOps` must execute the ops of THIS controller only (ExecuteChangeSet's filter) — the
+// other controller's worker executes the other half — and report what failed: a key whose ops hit an AWS error is requeued
+// rate-limited whatever its status word said.
+inline int ProcessBatch(gar_engine *engine, RateLimitingQueue &queue, Controller ctrl, uint8_t kind, KeyToRowFunc keyToRow, ExecuteOpsFunc executeOps,
                         BatchStats *stats = nullptr, std::string *error = nullptr) {
   std::vector<std::string> keys;
   for (;;) {
@@ -129,14 +138,24 @@ inline int ProcessBatch(gar_engine *engine, RateLimitingQueue &queue, Controller
     if (stats) *stats = st;
     return rc;
   }
-  if (executeOps) executeOps(cs);
+  OpFailures failures;
+  if (executeOps) failures = executeOps(cs);
   const uint32_t *status = ctrl == Controller::GlobalAccelerator ? cs.status_ga : cs.status_r53;
+  const std::string resource = kind == GAR_KIND_SERVICE ? "service/" : "ingress/";
   for (auto &k : keys) {
     int64_t row = keyToRow(k);
     if (row < 0 || row >= (int64_t)cs.n_objects) {
-      queue.Forget(k);  // processDelete returned (Result{}, nil): the orphan ops carry the cleanup
       st.deleted_keys++;
-      st.forgotten++;
+      if (failures.owners.count(resource + k)) {  // processDelete returned the AWS error (service.go:41-44)
+        queue.AddRateLimited(k);
+        st.requeued++;
+      } else {
+        queue.Forget(k);  // processDelete returned (Result{}, nil): the orphan ops carried the cleanup
+        st.forgotten++;
+      }
+    } else if (failures.objects.count({(uint8_t)ctrl, (uint32_t)row})) {
+      ApplyResult(queue, k, Result{}, Error::Retry(failures.objects[{(uint8_t)ctrl, (uint32_t)row}]));
+      st.requeued++;
     } else {
       auto re = ResultFromStatus(status[row]);
       ApplyResult(queue, k, re.first, re.second);

@@ -46,6 +46,7 @@ typedef uint64_t gar_str; /* bits 0..39 byte offset into the slab, bits 40..63 l
 #define GAR_STR_OFF(s) ((uint64_t)(s) & ((1ull << GAR_STR_OFF_BITS) - 1))
 #define GAR_STR_LEN(s) ((uint32_t)((uint64_t)(s) >> GAR_STR_OFF_BITS))
 #define GAR_NONE 0xFFFFFFFFu /* "no row" in op arguments */
+#define GAR_PENDING 0xFFFFFFFEu /* op argument: the resource an EARLIER op of the same object creates (see "Self-observation") */
 
 /* ---------------------------------------------------------------- return codes */
 
@@ -229,6 +230,19 @@ enum {
      R53_UPSERT_A          (j<<20)|k      zone    accel            record   route53.go:115-124
      R53_DELETE_RECORD     phase          zone    record           value    route53.go:132-165
    j = lbIngress index within the object, k = hostname index within the split route53-hostname annotation.
+   Self-observation.  The reference mutates AWS between the iterations of its lbIngress / hostname loops and re-lists, so a later
+   iteration of the SAME object sees what an earlier one did (ListGlobalAcceleratorByResource finds the accelerator created for
+   lbIngress 0 and takes the update path for lbIngress 1, global_accelerator.go:133-157; updateEndpointGroup REPLACES the
+   endpoint list, :987-1002; a hostname repeated in the route53 annotation finds the record just created, route53.go:92-124).
+   The change set reproduces that against the frozen snapshot: from the second lbIngress that reaches the update/create stage
+   on, an object's ops are what the reference would decide AFTER its own earlier ops — never a second GA_CREATE_CHAIN or a
+   second R53_CREATE for the same name.  Such ops name resources that do not exist yet with GAR_PENDING:
+     GA_UPDATE_ACCEL  a0 = PENDING          the accelerator of this object's earlier GA_CREATE_CHAIN
+     GA_UPDATE_EG     a0 = PENDING | accel, a1 = PENDING   the endpoint group made by this object's earlier GA_CREATE_CHAIN /
+                                                           GA_CREATE_LISTENER+GA_CREATE_EG / GA_CREATE_EG for that accelerator
+     R53_UPSERT_A     a2 = PENDING          the A record of this object's earlier R53_CREATE for the same hostname string
+   (User tags that overwrite the managed / owner / cluster tag with another value make an accelerator invisible to the list
+   call once written: every later lbIngress then creates again, as the reference would.)
    R53_DELETE_RECORD: phase 0 = owned alias set (FindOwneredARecordSets), a2 = first value row of that zone
    whose value is the owner value and whose record has the alias set's name; phase 1 = owner metadata set
    (findOwneredMetadataRecordSets), a2 = the matching value row (one op per matching value, as the reference

@@ -956,7 +956,12 @@ class Engine {
   }
 
   // updateGlobalAcceleratorFor{Service,Ingress} (:290-410).  Returns 0 or a gar_detail error.
-  int updateAccelerator(std::vector<gar_op> &ops, const Object &ob, uint32_t j, uint32_t acc, uint32_t lb) const {
+  // *egState (for the self-observation of later lbIngress iterations): bit 0 = the endpoint group now holds exactly [lb]
+  // (created or replaced by this call), bit 1 = it was created by this call (later ops name it GAR_PENDING).
+  int updateAccelerator(std::vector<gar_op> &ops, const Object &ob, uint32_t j, uint32_t acc, uint32_t lb, int *egState = nullptr) const {
+    int dummy = 0;
+    if (!egState) egState = &dummy;
+    *egState = 0;
     const gar_actual *a = S.a;
     sv resource = resourceOf(ob.kind);
     uint32_t head = 0;
@@ -974,6 +979,7 @@ class Engine {
       // endpoint group, and the endpoint group created for it contains the LB (:298-345)
       ops.push_back({H(GAR_OP_GA_CREATE_LISTENER), ob.row, j, acc, GAR_NONE, GAR_NONE});
       ops.push_back({H(GAR_OP_GA_CREATE_EG), ob.row, j, acc, GAR_NONE, lb});
+      *egState = 3;
       return 0;
     }
     uint32_t lis = lbeg;
@@ -986,14 +992,38 @@ class Engine {
     if (ee - eb > 1) return GAR_D_TOO_MANY_EGS;
     if (ee == eb) {
       ops.push_back({H(GAR_OP_GA_CREATE_EG), ob.row, j, acc, lis, lb});
+      *egState = 3;
       return 0;
     }
     uint32_t eg = eb;
-    bool contains = false;  // endpointContainsLB (:494-501)
-    for (uint32_t d = a->eg_ep_begin[eg]; d < a->eg_ep_begin[eg + 1]; d++)
-      if (S.as(a->ep_id[d]) == S.as(a->lb_arn[lb])) contains = true;
-    if (!contains) ops.push_back({H(GAR_OP_GA_UPDATE_EG), ob.row, j, acc, eg, lb});
+    if (!endpointContainsLB(eg, lb)) {
+      ops.push_back({H(GAR_OP_GA_UPDATE_EG), ob.row, j, acc, eg, lb});
+      *egState = 1;
+    }
     return 0;
+  }
+  // endpointContainsLB (:494-501) on the snapshot's endpoint group
+  bool endpointContainsLB(uint32_t eg, uint32_t lb) const {
+    const gar_actual *a = S.a;
+    for (uint32_t d = a->eg_ep_begin[eg]; d < a->eg_ep_begin[eg + 1]; d++)
+      if (S.as(a->ep_id[d]) == S.as(a->lb_arn[lb])) return true;
+    return false;
+  }
+  // What this object's user tags do to the three tags ListGlobalAcceleratorByResource filters on (:99-103) and to the
+  // target-hostname tag once they are written (createAccelerator :654-675 / updateAccelerator :720-735 append them after the
+  // system tags; a tag list reads "later duplicate wins", :560-563).
+  void userTagEffects(const Object &ob, sv resource, bool *keepVisible, bool *userThost) const {
+    *keepVisible = true;
+    *userThost = false;
+    std::map<sv, sv> last;
+    for (auto &t : acceleratorTags(ob)) last[t.first] = t.second;
+    auto it = last.find(sv(kTagManaged));
+    if (it != last.end() && it->second != "true") *keepVisible = false;
+    it = last.find(sv(kTagOwner));
+    if (it != last.end() && it->second != sv(ownerTagValue(resource, ob.ns, ob.name))) *keepVisible = false;
+    it = last.find(sv(kTagCluster));
+    if (it != last.end() && it->second != sv(S.cluster)) *keepVisible = false;
+    *userThost = last.count(sv(kTagTargetHostname)) != 0;
   }
 
   // process{Service,Ingress}CreateOrUpdate of the globalaccelerator controller (service.go:54-126, ingress.go:56-130)
@@ -1009,6 +1039,18 @@ class Engine {
       return GAR_STATUS(GAR_ST_OK, 0, GAR_EV_DELETED);
     }
     uint32_t ev = 0;
+    // Self-observation (include/garecon.h): the reference re-lists after its own mutations, so from the second lbIngress that
+    // reaches this stage on, the decisions are taken against what the object's earlier ops left behind:
+    //   * every accelerator it listed now satisfies acceleratorChanged for the PREVIOUS load balancer, has exactly one
+    //     listener in the desired state and exactly one endpoint group;
+    //   * an endpoint group that was created or replaced holds exactly [previous load balancer] (updateEndpointGroup
+    //     replaces the list, :987-1002), an untouched one still holds the snapshot's list;
+    //   * the accelerator of an earlier GA_CREATE_CHAIN is listed (rows = GAR_PENDING) — unless the user tags overwrite one of
+    //     the tags the list call filters on, in which case everything written so far has dropped out of the list.
+    auto accs = listByResource(resource, ob.ns, ob.name);  // the snapshot's list: the same at every iteration
+    std::vector<int> egState(accs.size(), 0);
+    int64_t prevLb = -1;
+    bool pending = false, keepVisible = true, userThost = false;
     for (uint32_t j = 0; j < je - jb; j++) {
       sv hostname = S.os(o->lbi_hostname[jb + j]);
       int prov = detectCloudProvider(hostname);
@@ -1021,16 +1063,42 @@ class Engine {
       if (lb < 0) return GAR_STATUS(GAR_ST_ERR_RETRY, GAR_D_LB_NOT_FOUND, ev);
       if (S.as(S.a->lb_dns[lb]) != hostname) return GAR_STATUS(GAR_ST_ERR_RETRY, GAR_D_LB_DNS_MISMATCH, ev);
       if (S.a->lb_state[lb] != GAR_LB_ACTIVE) return GAR_STATUS(GAR_ST_REQUEUE_30S, 0, ev);
-      auto accs = listByResource(resource, ob.ns, ob.name);
-      if (accs.empty()) {
-        ops.push_back({GAR_OP_HEAD(GAR_OP_GA_CREATE_CHAIN, GAR_CTRL_GA, ob.kind), ob.row, j, (uint32_t)lb, GAR_NONE, GAR_NONE});
+      auto H = [&](int op) { return GAR_OP_HEAD(op, GAR_CTRL_GA, ob.kind); };
+      if (prevLb < 0) {  // first iteration that gets here: the snapshot is the truth
+        userTagEffects(ob, resource, &keepVisible, &userThost);
+        if (accs.empty()) {
+          ops.push_back({H(GAR_OP_GA_CREATE_CHAIN), ob.row, j, (uint32_t)lb, GAR_NONE, GAR_NONE});
+          ev |= GAR_EV_CREATED;
+          pending = true;
+        } else {
+          for (size_t x = 0; x < accs.size(); x++) {
+            int err = updateAccelerator(ops, ob, j, accs[x], (uint32_t)lb, &egState[x]);
+            if (err) return GAR_STATUS(GAR_ST_ERR_RETRY, err, ev);
+          }
+        }
+      } else if (!keepVisible) {  // nothing this object wrote is listed any more: the list is empty again
+        ops.push_back({H(GAR_OP_GA_CREATE_CHAIN), ob.row, j, (uint32_t)lb, GAR_NONE, GAR_NONE});
         ev |= GAR_EV_CREATED;
-        continue;
+      } else {
+        bool dnsDiffers = !userThost && S.as(S.a->lb_dns[lb]) != S.as(S.a->lb_dns[prevLb]);
+        bool arnDiffers = S.as(S.a->lb_arn[lb]) != S.as(S.a->lb_arn[prevLb]);
+        if (pending) {
+          if (dnsDiffers) ops.push_back({H(GAR_OP_GA_UPDATE_ACCEL), ob.row, j, GAR_PENDING, (uint32_t)lb, GAR_NONE});
+          if (arnDiffers) ops.push_back({H(GAR_OP_GA_UPDATE_EG), ob.row, j, GAR_PENDING, GAR_PENDING, (uint32_t)lb});
+        }
+        for (size_t x = 0; x < accs.size(); x++) {
+          uint32_t acc = accs[x];
+          if (dnsDiffers) ops.push_back({H(GAR_OP_GA_UPDATE_ACCEL), ob.row, j, acc, (uint32_t)lb, GAR_NONE});
+          uint32_t eg = GAR_PENDING;
+          if (!(egState[x] & 2)) eg = S.a->lis_eg_begin[S.a->acc_lis_begin[acc]];
+          bool contains = (egState[x] & 1) ? !arnDiffers : endpointContainsLB(eg, (uint32_t)lb);
+          if (!contains) {
+            ops.push_back({H(GAR_OP_GA_UPDATE_EG), ob.row, j, acc, eg, (uint32_t)lb});
+            egState[x] |= 1;
+          }
+        }
       }
-      for (uint32_t acc : accs) {
-        int err = updateAccelerator(ops, ob, j, acc, (uint32_t)lb);
-        if (err) return GAR_STATUS(GAR_ST_ERR_RETRY, err, ev);
-      }
+      prevLb = lb;
     }
     return GAR_STATUS(GAR_ST_OK, 0, ev);
   }
@@ -1160,6 +1228,12 @@ class Engine {
     auto hostnames = goSplit(ob.get(kAnnR53Host), ',');  // route53/service.go:71
     uint32_t jb = o->obj_lbi_begin[ob.row], je = o->obj_lbi_begin[ob.row + 1];
     uint32_t ev = 0;
+    // Self-observation (include/garecon.h): a hostname visited before by this object — earlier in the annotation, or at an
+    // earlier lbIngress — has its alias record in place, pointing at the accelerator of that visit (created then: GAR_PENDING;
+    // found then: the snapshot row, re-pointed if it had drifted).  needRecordsUpdate (:373-381) therefore only fires when
+    // the accelerator's DNS name changed since the previous visit.
+    bool havePrev = false;
+    sv prevAccDns;
     for (uint32_t j = 0; j < je - jb; j++) {
       sv lbHostname = S.os(o->lbi_hostname[jb + j]);
       int prov = detectCloudProvider(lbHostname);
@@ -1172,21 +1246,31 @@ class Engine {
       if (accs.size() > 1) return GAR_STATUS(GAR_ST_REQUEUE_60S, GAR_D_ACCEL_MANY, ev);
       if (accs.empty()) return GAR_STATUS(GAR_ST_REQUEUE_60S, GAR_D_ACCEL_NONE, ev);
       uint32_t acc = accs[0];
+      sv accDns = S.as(S.a->acc_dns[acc]);
       bool created = false;
       for (uint32_t k = 0; k < hostnames.size(); k++) {
         sv hostname = hostnames[k];
         int64_t z = getHostedZone(hostname);
         if (z < 0) return GAR_STATUS(GAR_ST_ERR_RETRY, GAR_D_NO_HOSTED_ZONE, ev);
+        bool seen = false;  // same string earlier in the list: visited a moment ago with the same accelerator -> in sync now
+        for (uint32_t k2 = 0; k2 < k; k2++) seen |= hostnames[k2] == hostname;
+        if (seen) continue;
         auto records = findOwneredARecordSets((uint32_t)z, ownerValue);
         int64_t rec = findARecord(records, hostname);
-        if (rec < 0) {
-          ops.push_back({GAR_OP_HEAD(GAR_OP_R53_CREATE, GAR_CTRL_R53, ob.kind), ob.row, GAR_R53_SUB(j, k), (uint32_t)z, acc, GAR_NONE});
-          created = true;
-        } else if (needRecordsUpdate((uint32_t)rec, acc)) {
-          ops.push_back({GAR_OP_HEAD(GAR_OP_R53_UPSERT_A, GAR_CTRL_R53, ob.kind), ob.row, GAR_R53_SUB(j, k), (uint32_t)z, acc, (uint32_t)rec});
+        if (!havePrev) {
+          if (rec < 0) {
+            ops.push_back({GAR_OP_HEAD(GAR_OP_R53_CREATE, GAR_CTRL_R53, ob.kind), ob.row, GAR_R53_SUB(j, k), (uint32_t)z, acc, GAR_NONE});
+            created = true;
+          } else if (needRecordsUpdate((uint32_t)rec, acc)) {
+            ops.push_back({GAR_OP_HEAD(GAR_OP_R53_UPSERT_A, GAR_CTRL_R53, ob.kind), ob.row, GAR_R53_SUB(j, k), (uint32_t)z, acc, (uint32_t)rec});
+          }
+        } else if (accDns != prevAccDns) {
+          ops.push_back({GAR_OP_HEAD(GAR_OP_R53_UPSERT_A, GAR_CTRL_R53, ob.kind), ob.row, GAR_R53_SUB(j, k), (uint32_t)z, acc, rec < 0 ? GAR_PENDING : (uint32_t)rec});
         }
       }
       if (created) ev |= GAR_EV_CREATED;
+      havePrev = true;
+      prevAccDns = accDns;
     }
     return GAR_STATUS(GAR_ST_OK, 0, ev);
   }

@@ -14,6 +14,7 @@ import json
 import re
 
 NONE = 0xFFFFFFFF
+PENDING = 0xFFFFFFFE  # GAR_PENDING: a resource an earlier op of the same object creates (include/garecon.h)
 
 ANN_MANAGED = "aws-global-accelerator-controller.h3poteto.dev/global-accelerator-managed"
 ANN_R53 = "aws-global-accelerator-controller.h3poteto.dev/route53-hostname"
@@ -350,7 +351,32 @@ def diff(objects, actual, cluster):
                 for acc in list_by_resource(resource, ns, name):
                     delete_chain(ga_ops, row, kind, acc)
                 return status(ST_OK, 0, EV_DELETED)
+            # The reference mutates AWS between the lbIngress iterations and re-lists (ListGlobalAcceleratorByResource sees
+            # the accelerator it created one iteration earlier; updateEndpointGroup REPLACES the endpoint list).  A batch
+            # evaluates a frozen snapshot, so the object carries an overlay of what its own earlier ops changed: deep copies
+            # of the accelerators it touched plus the accelerator it created (rows = PENDING).
+            import copy
             ev = 0
+            over = {}     # accelerator row -> object-local copy
+            created = []  # accelerators created by this object's own ops
+
+            def view():
+                return [over.get(a["_row"], a) for a in accs] + created
+
+            def own(acc):
+                if acc["_row"] == PENDING or acc["_row"] in over:
+                    return acc
+                c = copy.deepcopy(acc)
+                c["_lis"] = [dict(li, _egs=[dict(eg) for eg in li["_egs"]]) for li in acc["_lis"]]
+                over[acc["_row"]] = c
+                return c
+
+            def desired_tags(lbdns, with_cluster):  # createAccelerator (:654-675) / updateAccelerator (:720-735)
+                t = [(TAG_MANAGED, "true"), (TAG_OWNER, f"{resource}/{ns}/{name}"), (TAG_HOST, lbdns)]
+                if with_cluster:
+                    t.append((TAG_CLUSTER, cluster))
+                return t + accelerator_tags(ob)
+
             for j, h in enumerate(hosts):
                 code, lbname, region = tokenise(h)
                 if code == 4:
@@ -366,10 +392,14 @@ def diff(objects, actual, cluster):
                     return status(ST_ERR_RETRY, 6, ev)
                 if lb.get("state", "active") != "active":
                     return status(ST_REQUEUE_30S, 0, ev)
-                found = list_by_resource(resource, ns, name)
+                t = {TAG_MANAGED: "true", TAG_OWNER: f"{resource}/{ns}/{name}", TAG_CLUSTER: cluster}
+                found = [a for a in view() if tags_contain(a.get("tags", []), t)]  # ListGlobalAcceleratorByResource on the overlaid state
                 if not found:
                     ga_ops.append((head(1, 0, kind), row, j, lb["_row"], NONE, NONE))
                     ev |= EV_CREATED
+                    created.append({"_row": PENDING, "name": accelerator_name(ob), "enabled": True, "tags": desired_tags(lb["dns"], True),
+                                    "_lis": [{"_row": PENDING, "proto": "UDP" if proto == 1 else "TCP", "ports": list(ports),
+                                              "_egs": [{"_row": PENDING, "endpoints": [lb["arn"]]}]}]})
                     continue
                 for acc in found:  # updateGlobalAcceleratorFor* (:290-410)
                     changed = (not acc.get("enabled", True)) or acc.get("name", "") != accelerator_name(ob)
@@ -380,26 +410,39 @@ def diff(objects, actual, cluster):
                         changed = not tags_contain(acc.get("tags", []), target)
                     if changed:
                         ga_ops.append((head(2, 0, kind), row, j, acc["_row"], lb["_row"], NONE))
+                        acc = own(acc)
+                        acc["enabled"], acc["name"] = True, accelerator_name(ob)
+                        acc["tags"] = list(acc.get("tags", [])) + desired_tags(lb["dns"], False)  # TagResource: later entries win
                     ls = acc["_lis"]
                     if len(ls) > 1:
                         return status(ST_ERR_RETRY, 7, ev)
                     if len(ls) == 0:
                         ga_ops.append((head(3, 0, kind), row, j, acc["_row"], NONE, NONE))
                         ga_ops.append((head(5, 0, kind), row, j, acc["_row"], NONE, lb["_row"]))
+                        acc = own(acc)
+                        acc["_lis"] = [{"_row": PENDING, "proto": "UDP" if proto == 1 else "TCP", "ports": list(ports),
+                                        "_egs": [{"_row": PENDING, "endpoints": [lb["arn"]]}]}]
                         continue
                     li = ls[0]
                     lproto = 1 if li.get("proto", "TCP") == "UDP" else 0
                     proto_changed = (lproto != proto) if kind == 0 else (lproto != 0)
                     if proto_changed or port_changed(li.get("ports", []), ports):
                         ga_ops.append((head(4, 0, kind), row, j, acc["_row"], li["_row"], NONE))
+                        acc = own(acc)
+                        li = acc["_lis"][0]
+                        li["proto"], li["ports"] = ("UDP" if proto == 1 else "TCP") if kind == 0 else "TCP", list(ports)
                     egs = li["_egs"]
                     if len(egs) > 1:
                         return status(ST_ERR_RETRY, 8, ev)
                     if len(egs) == 0:
                         ga_ops.append((head(5, 0, kind), row, j, acc["_row"], li["_row"], lb["_row"]))
+                        acc = own(acc)
+                        acc["_lis"][0]["_egs"] = [{"_row": PENDING, "endpoints": [lb["arn"]]}]
                         continue
                     if lb["arn"] not in egs[0].get("endpoints", []):
                         ga_ops.append((head(6, 0, kind), row, j, acc["_row"], egs[0]["_row"], lb["_row"]))
+                        acc = own(acc)
+                        acc["_lis"][0]["_egs"][0]["endpoints"] = [lb["arn"]]  # updateEndpointGroup replaces the list (:987-1002)
             return status(ST_OK, 0, ev)
 
         st_ga.append(ga())
@@ -414,6 +457,27 @@ def diff(objects, actual, cluster):
                 return status(ST_OK, 0, EV_DELETED)
             hostnames = ann[ANN_R53].split(",")
             ev = 0
+            # object-local overlay of Route53: record sets this object's own earlier ops created (rows = PENDING) or re-pointed
+            new_recs = {}   # zone row -> [record dicts]
+            new_alias = {}  # record row -> alias DNS name written by an UPSERT of this object
+
+            def alias_sets(z):
+                names = []
+                allrecs = z["_recs"] + new_recs.get(z["_row"], [])
+                for r in allrecs:
+                    for vi, v in r["_vals"]:
+                        if v == ov:
+                            names.append((r["name"], vi))
+                out = []
+                for r in allrecs:
+                    if r.get("alias") is None:
+                        continue
+                    for n, vi in names:
+                        if n == r["name"]:
+                            out.append((r, vi))
+                            break
+                return out
+
             for j, h in enumerate(hosts):
                 code, _, _ = tokenise(h)
                 if code == 4:
@@ -434,15 +498,26 @@ def diff(objects, actual, cluster):
                     if z is None:
                         return status(ST_ERR_RETRY, 9, ev)
                     rec = None
-                    for r, _vi in owned_alias_sets(z, ov):  # findARecord (:360-367)
+                    for r, _vi in alias_sets(z):  # findARecord (:360-367) over FindOwneredARecordSets on the overlaid state
                         if r.get("type", "A") == "A" and r["name"].replace("\\052", "*", 1) == hn + ".":
                             rec = r
                             break
+                    want = acc.get("dns", "") + "."
                     if rec is None:
                         r53_ops.append((head(8, 1, kind), row, (j << 20) | k, z["_row"], acc["_row"], NONE))
                         created = True
-                    elif rec.get("alias") is None or rec["alias"] != acc.get("dns", "") + ".":  # needRecordsUpdate (:373-381)
-                        r53_ops.append((head(9, 1, kind), row, (j << 20) | k, z["_row"], acc["_row"], rec["_row"]))
+                        rn = (hn + ".").replace("*", "\\052")  # Route53 stores '*' escaped
+                        new_recs.setdefault(z["_row"], []).extend([
+                            {"_row": PENDING, "name": rn, "type": "TXT", "_vals": [(PENDING, ov)]},
+                            {"_row": PENDING, "name": rn, "type": "A", "alias": want, "_vals": []}])
+                    else:
+                        cur = new_alias.get(rec["_row"], rec.get("alias")) if rec["_row"] != PENDING else rec["alias"]
+                        if cur is None or cur != want:  # needRecordsUpdate (:373-381)
+                            r53_ops.append((head(9, 1, kind), row, (j << 20) | k, z["_row"], acc["_row"], rec["_row"]))
+                            if rec["_row"] == PENDING:
+                                rec["alias"] = want
+                            else:
+                                new_alias[rec["_row"]] = want
                 if created:
                     ev |= EV_CREATED
             return status(ST_OK, 0, ev)

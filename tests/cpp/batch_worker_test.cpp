@@ -61,12 +61,16 @@ int main(int argc, char **argv) {
   BatchStats st;
   std::string err;
   int rc = ProcessBatch(
-      e, q, Controller::GlobalAccelerator,
+      e, q, Controller::GlobalAccelerator, GAR_KIND_SERVICE,
       [&](const std::string &k) -> int64_t {
         auto it = rowOf.find(k);
         return it == rowOf.end() ? -1 : it->second;
       },
-      [&](const gar_changeset &cs) { n_ops = cs.n_ops; }, &st, &err);
+      [&](const gar_changeset &cs) {
+        n_ops = cs.n_ops;
+        return OpFailures{};
+      },
+      &st, &err);
   printf("{\"rc\": %d, \"keys\": %zu, \"forgotten\": %zu, \"requeued\": %zu, \"delayed\": %zu, \"dropped\": %zu, \"deleted_keys\": %zu, \"n_ops\": %llu, "
          "\"q_done\": %d, \"q_forget\": %d, \"q_ratelimited\": %d, \"q_after30\": %d, \"q_after60\": %d}\n",
          rc, st.keys, st.forgotten, st.requeued, st.delayed, st.dropped, st.deleted_keys, (unsigned long long)n_ops, q.done, q.forget, q.ratelimited, q.after30, q.after60);

@@ -39,6 +39,7 @@ struct Round {
   size_t not_ok_ga = 0, not_ok_r53 = 0;
   bool oracle_equal = false;
   double pack_ms = 0, diff_ms = 0;
+  size_t executed = 0, events = 0;
 };
 
 static Round run_round(gar_engine *e, const std::vector<KObject> &objects, CloudState &state, const char *cluster) {
@@ -73,7 +74,15 @@ static Round run_round(gar_engine *e, const std::vector<KObject> &objects, Cloud
     r.not_ok_r53 += !(d == GAR_ST_OK || d == GAR_ST_IGNORED || d == GAR_ST_SKIP_NO_LB);
   }
   MockCloud cloud(&state);
-  ExecuteChangeSet(cs, objects, state, cluster, cloud);
+  // the two controllers' workers each execute their own half of the change set
+  ExecReport ga = ExecuteChangeSet(cs, objects, state, cluster, cloud, kExecGA);
+  ExecReport r53 = ExecuteChangeSet(cs, objects, state, cluster, cloud, kExecR53);
+  r.executed = ga.executed + r53.executed;
+  r.events = ga.events.size() + r53.events.size();
+  if (!ga.failed.empty() || !r53.failed.empty() || ga.executed + r53.executed != cs.n_ops) {
+    fprintf(stderr, "executor: %zu + %zu of %llu ops executed without fault injection\n", ga.executed, r53.executed, (unsigned long long)cs.n_ops);
+    exit(5);
+  }
   cloud.Commit();
   gar_changeset_free(e, &cs);
   return r;

@@ -12,6 +12,7 @@ import importlib
 pyref = importlib.import_module("oracle.pyref")
 
 NONE = 0xFFFFFFFF
+PENDING = 0xFFFFFFFE  # GAR_PENDING: the resource an earlier op of the same object created
 ANN_IPPRESERVE = pyref.ANN_IPPRESERVE
 
 
@@ -43,6 +44,7 @@ def apply(objects, actual, cs, cluster="default"):
     dead_accs, dead_recs = set(), set()
     serial = [len(accs)]
     last_created_listener = {}
+    created_acc, pending_eg, created_rec = {}, {}, {}  # per object: what its own earlier ops created (GAR_PENDING arguments)
 
     def desired(ob):
         ports, proto, _ = pyref.desired_listener(ob)
@@ -63,12 +65,16 @@ def apply(objects, actual, cs, cluster="default"):
             lb = lbs[a0]
             serial[0] += 1
             ports, proto = desired(ob)
-            actual["accelerators"].append({
+            eg = {"arn": f"e-new-{serial[0]}", "endpoints": [lb["arn"]]}
+            new_acc = {
                 "arn": f"arn:aws:globalaccelerator::1:accelerator/new-{serial[0]}", "name": pyref.accelerator_name(ob),
                 "dns": f"new{serial[0]:06d}.awsglobalaccelerator.com", "enabled": True, "tags": sys_tags(ob, lb, True),
-                "listeners": [{"arn": f"l-new-{serial[0]}", "proto": proto, "ports": ports, "egs": [{"arn": f"e-new-{serial[0]}", "endpoints": [lb["arn"]]}]}]})
+                "listeners": [{"arn": f"l-new-{serial[0]}", "proto": proto, "ports": ports, "egs": [eg]}]}
+            actual["accelerators"].append(new_acc)
+            created_acc[obj] = new_acc
+            pending_eg[(obj, PENDING)] = eg
         elif code == 2:  # GA_UPDATE_ACCEL: UpdateAccelerator(Enabled, Name) + TagResource (:703-741)
-            acc, lb = accs[a0], lbs[a1]
+            acc, lb = (created_acc[obj] if a0 == PENDING else accs[a0]), lbs[a1]
             acc["enabled"] = True
             acc["name"] = pyref.accelerator_name(ob)
             new = sys_tags(ob, lb, False)
@@ -88,9 +94,11 @@ def apply(objects, actual, cs, cluster="default"):
             li["ports"], li["proto"] = desired(ob)
         elif code == 5:  # GA_CREATE_EG (:971-990)
             li = last_created_listener[a0] if a1 == NONE else lis[a1][1]
-            li.setdefault("egs", []).append({"arn": f"e-new-{a0}-{len(li.get('egs', []))}", "endpoints": [lbs[a2]["arn"]]})
+            eg = {"arn": f"e-new-{a0}-{len(li.get('egs', []))}", "endpoints": [lbs[a2]["arn"]]}
+            li.setdefault("egs", []).append(eg)
+            pending_eg[(obj, a0)] = eg
         elif code == 6:  # GA_UPDATE_EG: EndpointConfigurations = [lb] (:992-1010)
-            _, eg = egs[a1]
+            eg = pending_eg[(obj, a0)] if a1 == PENDING else egs[a1][1]
             eg["endpoints"] = [lbs[a2]["arn"]]
         elif code == 7:  # GA_DELETE_CHAIN (:254-272)
             dead_accs.add(a0)
@@ -102,8 +110,13 @@ def apply(objects, actual, cs, cluster="default"):
             name = hn.replace("*", "\\052", 1) + "."
             z.setdefault("records", []).append({"name": name, "type": "TXT", "values": [pyref.owner_value(cluster, res, ob.get("ns", "default"), ob["name"])]})
             z["records"].append({"name": name, "type": "A", "alias": acc.get("dns", "") + "."})
+            created_rec[(obj, hn)] = z["records"][-1]
         elif code == 9:  # R53_UPSERT_A (:291-315)
-            _, rec = recs[a2]
+            if a2 == PENDING:
+                hn = dict(ob.get("annotations", {}))[pyref.ANN_R53].split(",")[sub & 0xFFFFF]
+                rec = created_rec[(obj, hn)]
+            else:
+                _, rec = recs[a2]
             rec["alias"] = accs[a1].get("dns", "") + "."
             rec["type"] = "A"
         elif code == 10:  # R53_DELETE_RECORD (:183-197)

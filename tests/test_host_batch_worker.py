@@ -9,11 +9,11 @@ import pytest
 REPO = Path(__file__).resolve().parent.parent
 
 
-def _run(tmp_path, lib: Path, n: int):
+def _run(tmp_path, lib: Path, n: int, prog: str = "converge_test"):
     import __graft_entry__ as ge
     oracle = ge.build_oracle()
-    exe = tmp_path / "converge_test"
-    subprocess.run(["g++", "-std=c++17", "-O1", "-I", str(REPO), "-o", str(exe), str(REPO / "tests" / "cpp" / "converge_test.cpp"),
+    exe = tmp_path / prog
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I", str(REPO), "-o", str(exe), str(REPO / "tests" / "cpp" / f"{prog}.cpp"),
                     str(lib), str(oracle), f"-Wl,-rpath,{lib.parent}", f"-Wl,-rpath,{Path(oracle).parent}", "-pthread"], check=True)
     out = subprocess.run([str(exe), str(n)], capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stderr[-2000:]
@@ -49,3 +49,18 @@ def test_batch_worker_converges_on_hostsim(tmp_path):
 def test_batch_worker_converges_on_gpu(tmp_path):
     rows = _run(tmp_path, REPO / "aws-global-accelerator-controller_b200" / "libgarecon.so", 5000)
     _check(rows, 5000)
+
+
+def test_executor_failure_semantics_on_hostsim(tmp_path):
+    """Injected AWS errors: rollback of a partial create, the Ingress path's swallowed listener error, first error ends the
+    object, events, rate-limited requeue of failed keys, per-controller execution, GAR_PENDING arguments, paginated packing,
+    convergence through failures (tests/cpp/executor_faults_test.cpp holds the hand-derived expectations)."""
+    import __graft_entry__ as ge
+    rows = _run(tmp_path, Path(ge.build_hostsim()), 0, prog="executor_faults_test")
+    assert rows[-1] == {"failed_checks": 0}
+
+
+@pytest.mark.gpu
+def test_executor_failure_semantics_on_gpu(tmp_path):
+    rows = _run(tmp_path, REPO / "aws-global-accelerator-controller_b200" / "libgarecon.so", 0, prog="executor_faults_test")
+    assert rows[-1] == {"failed_checks": 0}
