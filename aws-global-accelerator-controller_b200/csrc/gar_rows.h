@@ -39,7 +39,8 @@ enum {
   R53_MODE_PAIRS = 1,  // one lbIngress with a usable accelerator: hostnames are evaluated as (object, hostname) pairs
   R53_MODE_OBJECT = 2, // everything else (cleanup, several lbIngress): the per-object routine r53_reconcile
 };
-enum { PAIR_IN_SYNC = 0, PAIR_CREATE = 1, PAIR_UPSERT = 2, PAIR_NO_ZONE = 3 };
+enum { PAIR_IN_SYNC = 0, PAIR_CREATE = 1, PAIR_UPSERT = 2, PAIR_NO_ZONE = 3,
+       PAIR_REPEAT = 4 };  // the same hostname string earlier in the annotation: visited a moment ago with the same accelerator -> nothing to do
 #define VALNAME_HAS_BACKSLASH (1u << 30)  // ix_val entry a1 bit: the record name contains a backslash (possible \052 escape)
 
 // per-value-row class: is this ResourceRecord value an owner value of this cluster?
@@ -1479,6 +1480,8 @@ GAR_HD void r53_fill_pairs(const DevTables &T, const Work &W, u32 i, u32 t) {
   while (next_piece(hostnames, &pos, &piece)) {
     W.pair_obj[p] = i;
     W.pair_hn[p] = GAR_STR(GAR_STR_OFF(ref) + (u64)(piece.p - hostnames.p), piece.n);
+    // self-observation (include/garecon.h): a repeated hostname needs no evaluation — the annotation bytes are in hand here
+    W.pair_code[p] = piece_seen_before(hostnames, piece) ? (u8)PAIR_REPEAT : (u8)PAIR_IN_SYNC;
     p++;
   }
 }
@@ -1489,6 +1492,7 @@ GAR_HD void r53_pair(const DevTables &T, const Work &W, u32 p, bool valid) {
   u32 i = 0, kind = 0;
   Str hn{T.o.slab, 0}, okey{T.o.slab, 0};
   u64 okh = 0;
+  valid = valid && W.pair_code[p] != PAIR_REPEAT;
   if (valid) {
     i = W.pair_obj[p];
     hn = mkstr(T.o.slab, W.pair_hn[p]);
@@ -1551,18 +1555,8 @@ GAR_HD u32 r53_combine(const DevTables &T, const Work &W, u32 i, u32 t, bool val
     u32 kind = T.o.obj_kind[i], acc = W.r53_acc[i];
     bool created = false, stop = false;
     u32 k = 0;
-    const u32 p0 = W.pair_begin[t];
-    for (u32 p = p0; p < W.pair_begin[t + 1] && !stop; p++, k++) {
+    for (u32 p = W.pair_begin[t]; p < W.pair_begin[t + 1] && !stop; p++, k++) {
       u32 code = W.pair_code[p];
-      if (code == PAIR_CREATE || code == PAIR_UPSERT) {
-        // self-observation: the same hostname earlier in the annotation got this very op a moment ago -> in sync now
-        Str hn = mkstr(T.o.slab, W.pair_hn[p]);
-        for (u32 q = p0; q < p; q++)
-          if (streq(mkstr(T.o.slab, W.pair_hn[q]), hn)) {
-            code = PAIR_IN_SYNC;
-            break;
-          }
-      }
       if (code == PAIR_NO_ZONE) {
         st = GAR_STATUS(GAR_ST_ERR_RETRY, GAR_D_NO_HOSTED_ZONE, 0);
         stop = true;

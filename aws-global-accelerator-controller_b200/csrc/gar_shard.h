@@ -553,7 +553,7 @@ struct ShGids {
 struct FShTranslateOps {
   gar_op *ops;
   ShGids g;
-  GAR_HD u32 m(const u32 *tab, u32 v) const { return v == GAR_NONE ? GAR_NONE : tab[v]; }
+  GAR_HD u32 m(const u32 *tab, u32 v) const { return v >= GAR_PENDING ? v : tab[v]; }  // GAR_NONE / GAR_PENDING name no row
   GAR_HD void operator()(u32 k) const {
     gar_op o = ops[k];
     o.obj = m(g.obj, o.obj);

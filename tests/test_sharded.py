@@ -68,6 +68,15 @@ def test_sharded_more_seeds(garecon, oracle, hostlib, seed):
     check(garecon, oracle, hostlib, objects, actual, 2 + seed % 3)
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_sharded_multi_lbingress_models(garecon, oracle, hostlib, seed):
+    """Self-observation ops carry GAR_PENDING arguments: they must survive the local -> global row translation of a shard."""
+    import multilbi
+    objects, actual = multilbi.make(seed, n_objects=40)
+    got, _ = check(garecon, oracle, hostlib, objects, actual, 2 + seed % 3)
+    assert any(0xFFFFFFFE in (int(o["a0"]), int(o["a1"]), int(o["a2"])) for o in got["ops"])
+
+
 def test_sharded_hot_keys(garecon, oracle, hostlib):
     """Many owners claim the same record names / hostnames: alias records replicate to several homes, directory shards see
     long duplicate chains."""
