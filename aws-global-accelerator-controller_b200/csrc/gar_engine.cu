@@ -39,6 +39,53 @@ __global__ void __launch_bounds__(256, MINB) k_for_each_warp(const __grid_consta
   u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   f(i, i < n);
 }
+// Count on the device (an intermediate relation whose size the host never learns mid-diff): one element per thread over the
+// buffer's CAPACITY; blocks beyond the real count leave at once.
+template <class F>
+__global__ void __launch_bounds__(256) k_for_each_dyn(const __grid_constant__ F f, const u32 *n_dev, u32 cap) {
+  u32 n = *n_dev;
+  if (n > cap) n = cap;
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) f(i);
+}
+template <class F, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_for_each_warp_dyn(const __grid_constant__ F f, const u32 *n_dev, u32 cap) {
+  u32 n = *n_dev;
+  if (n > cap) n = cap;
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < ((n + 31u) & ~31u)) f(i, i < n);  // whole warps enter or leave together
+}
+// Several row functors over their own tables in ONE launch (the index placement pass; the orphan count / emit passes):
+// consecutive block ranges belong to consecutive functors.
+template <class... Fs>
+struct FPack;
+template <>
+struct FPack<> {
+  __device__ __forceinline__ void call(int, u32) const {}
+};
+template <class F, class... R>
+struct FPack<F, R...> {
+  F f;
+  FPack<R...> rest;
+  FPack(const F &f_, const R &...r) : f(f_), rest(r...) {}
+  __device__ __forceinline__ void call(int k, u32 i) const {
+    if (k == 0) f(i);
+    else rest.call(k - 1, i);
+  }
+};
+constexpr int MULTI_MAX = 8;
+struct MultiRanges {
+  u32 blk_end[MULTI_MAX], n[MULTI_MAX];
+  int count;
+};
+template <class P>
+__global__ void __launch_bounds__(256) k_for_each_multi(const __grid_constant__ P pack, const __grid_constant__ MultiRanges r) {
+  int k = 0;
+  while (k + 1 < r.count && blockIdx.x >= r.blk_end[k]) k++;
+  u32 i = (blockIdx.x - (k ? r.blk_end[k - 1] : 0u)) * blockDim.x + threadIdx.x;
+  if (i < r.n[k]) pack.call(k, i);
+}
+
 // resident 256-thread blocks per SM each warp-synchronous stage is compiled for (register cap = 65536 / (256 * N)):
 // these stages wait on dependent DRAM loads, so occupancy matters more than registers
 template <class F> struct MinBlocks { static constexpr int value = 2; };
@@ -447,6 +494,39 @@ struct gar_engine {
     launches++;
     stage_end();
   }
+  template <class F>
+  void for_each_dyn(const char *name, const u32 *n_dev, u32 cap, const F &f) {
+    if (!cap) return;
+    stage_begin(name);
+    k_for_each_dyn<F><<<(cap + 255) / 256, 256, 0, stream>>>(f, n_dev, cap);
+    launches++;
+    stage_end();
+  }
+  template <class F>
+  void for_each_warp_dyn(const char *name, const u32 *n_dev, u32 cap, const F &f) {
+    if (!cap) return;
+    stage_begin(name);
+    k_for_each_warp_dyn<F, MinBlocks<F>::value><<<(cap + 255) / 256, 256, 0, stream>>>(f, n_dev, cap);
+    launches++;
+    stage_end();
+  }
+  template <class... Fs>
+  void for_each_multi(const char *name, std::initializer_list<u32> ns, const Fs &...fs) {
+    static_assert(sizeof...(Fs) <= MULTI_MAX, "too many functors for one fused launch");
+    MultiRanges r{};
+    u32 blocks = 0;
+    for (u32 n : ns) {
+      blocks += (n + 255) / 256;
+      r.blk_end[r.count] = blocks;
+      r.n[r.count] = n;
+      r.count++;
+    }
+    if (!blocks) return;
+    stage_begin(name);
+    k_for_each_multi<FPack<Fs...>><<<blocks, 256, 0, stream>>>(FPack<Fs...>(fs...), r);
+    launches++;
+    stage_end();
+  }
   void fill32(u32 *p, u32 v, size_t n) {
     if (!n) return;
     if (v == 0) {
@@ -727,6 +807,7 @@ static void do_diff(gar_engine *e, gar_changeset *out, bool to_host, const gar_k
   if (e->shard_home && (ks || bd)) throw InvalidError{"incremental / binding diffs are not available on a sharded sub-snapshot"};
   if (!e->pipe) {
     e->pipe = new Pipeline<gar_engine>(*e, e->T);
+    if (const char *tc = getenv("GAR_TINY_CAPS")) e->pipe->tiny_caps = tc[0] == '1';
     if (e->shard_home) {
       e->pipe->acc_guest_from = e->sharder->guest_from;
       e->pipe->sharded = 1;
@@ -806,15 +887,13 @@ static void do_diff(gar_engine *e, gar_changeset *out, bool to_host, const gar_k
   if (rc == GAR_OK && e->shard_home && dc.n_ops) e->for_each("shard_translate_ops", (u32)dc.n_ops, FShTranslateOps{(gar_op *)e->d_ops.p, e->sharder->gids});
   CK(cudaEventRecord(e->ev[3], e->stream));
   if (rc == GAR_E_INVALID) {
-    CK(cudaStreamSynchronize(e->stream));
     throw InvalidError{"objects layout rule violated: obj_ns and obj_name must be slices of one \"ns/name\" key string"};
   }
   if (rc == GAR_REFUSE_EMPTY_CACHE) {
-    CK(cudaStreamSynchronize(e->stream));
     throw StateError{"the object table is empty but this cluster still owns AWS resources: refusing to emit delete-everything orphan sections "
                      "(informer not synced?).  Set GAR_FLAG_ALLOW_EMPTY_CACHE if the cache really is empty, or GAR_FLAG_NO_ORPHANS"};
   }
-  if (rc != GAR_OK) throw InvalidError{"index build did not converge"};
+  if (rc != GAR_OK) throw InvalidError{"the diff did not settle: an intermediate relation kept outgrowing its buffer"};
   const bool partial = ks || bd;
   const u32 n = n_out, nlbi = partial ? 0 : e->T.o.n_lbi;
   const DBuf &d_derived_src = ks ? e->d_derived_keys : e->d_derived;

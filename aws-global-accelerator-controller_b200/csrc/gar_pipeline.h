@@ -12,6 +12,9 @@
 //   void sort_pairs(u32 *keys, u32 *vals, u32 *keys_alt, u32 *vals_alt, u32 n, int bits);  // stable, result in keys/vals
 //   void fill32(u32 *p, u32 value, size_t n);
 //   void *ensure(int slot, size_t bytes);                                   // scratch buffer `slot`, at least `bytes`
+//   template <class... Fs> void for_each_multi(const char *name, std::initializer_list<u32> ns, const Fs &...fs);  // ONE launch: fs[k](i), i < ns[k]
+//   template <class F> void for_each_dyn(const char *name, const u32 *n_dev, u32 cap, const F &f);       // f(i) for i < min(*n_dev, cap); the count
+//   template <class F> void for_each_warp_dyn(const char *name, const u32 *n_dev, u32 cap, const F &f);  //   lives on the device: no read-back
 //   void download(void *host_dst, const void *dev_src, size_t bytes);       // blocking
 //   void download_start(int id, const void *dev_src, size_t bytes);         // id 0..1: small read-back in flight while later
 //   void download_wait(int id, void *host_dst, size_t bytes);               //   stages are queued; wait blocks only if needed
@@ -19,6 +22,8 @@
 
 #include <stdio.h>
 #include <stdlib.h>
+
+#include <initializer_list>
 
 #include "gar_rows.h"
 
@@ -40,6 +45,7 @@ enum Slot {
   S_IX_ALIAS = S_IX_VAL + 3, S_IX_OBJ = S_IX_ALIAS + 3, S_IX_OVN = S_IX_OBJ + 3,
   S_SORT_KEYS = S_IX_OVN + 3, S_SORT_VALS, S_SORT_KEYS_ALT, S_SORT_VALS_ALT, S_SORT_TAGS,
   S_COUNTS, S_STATUS_GA, S_STATUS_R53, S_OPS, S_ERRFLAG, S_IX_EG, S_IX_EG_ENT, S_IX_EG_PAD, S_ACC_CLAIMED,
+  S_IXA_BEGIN, S_IXA_FILL, S_IXA_ENT, S_IXA_MULTI, S_OVN_FILL, S_OVN_MULTI, S_LB_HASH, S_REC_FLAGS,
   S_NSLOTS
 };
 
@@ -101,7 +107,11 @@ struct FPrepareRecord {
       else hi = mid;
     }
     W.rec_zone[r] = lo;
-    W.rec_name_hash[r] = gar_hash(mkstr(T.a.slab, T.a.rec_name[r]));
+    const Str nm = mkstr(T.a.slab, T.a.rec_name[r]);
+    const u64 nh = gar_hash(nm);
+    W.rec_name_hash[r] = nh;
+    W.rec_flags[r] = find_byte(nm, 0, '\\') < nm.n ? 1 : 0;
+    if (T.a.rec_has_alias[r]) ix_count(W.hist[IX_ALIAS], key_hash_zoned_h(lo, nh));
     u32 v0 = T.a.rec_val_begin[r], v1 = T.a.rec_val_begin[r + 1];
     if (v1 - v0 > REC_INLINE_VALUES) {
       u32 *list = v1 - v0 > REC_HUGE_VALUES ? huge : big;
@@ -161,7 +171,7 @@ struct FJsonWrite {
   Work W;
   GAR_HD void operator()(u32 i) const {
     if (!(W.derived[i] & GAR_DV_PORTS_FROM_ANN)) return;
-    if (W.dport_begin[i + 1] == W.dport_begin[i]) return;
+    if (W.dport_begin[i + 1] == W.dport_begin[i] || W.dport_begin[i + 1] > W.dport_cap) return;
     u32 stk[GAR_JSON_STACK_WORDS];
     json_listen_ports(mkstr(T.o.slab, W.ann_listen[i]), W.dports + W.dport_begin[i], stk);
   }
@@ -170,10 +180,21 @@ struct FJsonWrite {
 // --- index rows: one functor per index says whether a row is indexed, its key hash and its entry payload
 // (payload conventions: gar_rows.h "index probes").  The key pass streams the table once (coalesced) and leaves a
 // complete 32-byte entry per row; the build then only moves entries.
+// (region, name) hash of every load balancer: the only index key that is not produced by a row-local pass anyway
+struct FLbHash {
+  DevTables T;
+  Work W;
+  GAR_HD void operator()(u32 i) const {
+    u64 h = key_hash_lb(mkstr(T.a.slab, T.a.lb_region[i]), mkstr(T.a.slab, T.a.lb_name[i]));
+    W.lb_hash[i] = h;
+    ix_count(W.hist[IX_LB], h);
+  }
+};
 struct FRowLb {
   DevTables T;
+  Work W;
   GAR_HD bool make(u32 i, u64 *h, IdxEntry *e) const {
-    *h = key_hash_lb(mkstr(T.a.slab, T.a.lb_region[i]), mkstr(T.a.slab, T.a.lb_name[i]));
+    *h = W.lb_hash[i];
     e->a0 = T.a.lb_state[i];
     e->a1 = 0;
     e->s0 = T.a.lb_name[i];
@@ -219,10 +240,12 @@ struct FRowZone {
 };
 struct FZoneLenMask {
   DevTables T;
+  Work W;
   unsigned long long *mask;  // [4]
   GAR_HD void operator()(u32 z) const {
     Str zn = mkstr(T.a.slab, T.a.zone_name[z]);
     if (zn.n < 1 || zn.p[zn.n - 1] != '.') return;  // not indexed (FRowZone)
+    ix_count(W.hist[IX_ZONE], key_hash_str(substr(zn, 0, zn.n - 1)));
     u32 b = zn.n - 1 < 255 ? zn.n - 1 : 255;
 #if defined(__CUDA_ARCH__)
     atomicOr(&mask[b >> 6], 1ull << (b & 63));
@@ -240,8 +263,7 @@ struct FRowVal {
     if (cls == VAL_NOT_OWNER) return false;
     u32 rec = W.val_rec[v];
     u32 kind = (cls & VAL_OWNER_INGRESS) ? 1u : 0u;
-    Str nm = mkstr(T.a.slab, T.a.rec_name[rec]);
-    u32 bs = find_byte(nm, 0, '\\') < nm.n ? VALNAME_HAS_BACKSLASH : 0u;
+    u32 bs = (W.rec_flags[rec] & 1) ? VALNAME_HAS_BACKSLASH : 0u;
     e->a0 = rec;
     e->a1 = W.rec_zone[rec] | bs | (kind << 31);
     e->s0 = W.val_key[v];
@@ -364,6 +386,75 @@ struct FIdxGather {  // radix fallback: position p of the stable sorted order ho
     if (p < *nvalid) ent[p] = tmp[vals[p]];
   }
 };
+// One-pass build (the default): the row-local passes have already counted every bucket (Work::hist); after ONE scan over the
+// concatenated bucket arrays of all indexes this pass builds each row's entry from columns and hashes that already exist and
+// drops it straight into its bucket — no temporary entry, no key array.  A bucket's second entry puts the bucket on the
+// `multi` list: only those buckets are ordered afterwards (by row id == stable).
+template <class RowF>
+struct FIdxPlaceDirect {
+  RowF rowf;
+  const u32 *begin;  // this index's slice of the scanned bucket array (values are positions in the shared entry array)
+  u32 *fill;         // this index's slice of the zeroed fill counters
+  IdxEntry *ent;     // shared entry array of the group
+  u32 mask, bucket_base;
+  u32 *multi;        // [0] = count, then global bucket ids
+  GAR_HD void operator()(u32 i) const {
+    u64 h = 0;
+    IdxEntry e;
+    if (!rowf.make(i, &h, &e)) return;
+    const u32 k = hash_bucket(h, mask);
+#if defined(__CUDA_ARCH__)
+    const u32 old = atomicAdd(&fill[k], 1u);
+#else
+    const u32 old = fill[k]++;
+#endif
+    e.tag = hash_tag(h);
+    e.row = i;
+    ent[begin[k] + old] = e;
+    if (old == 1) {
+#if defined(__CUDA_ARCH__)
+      multi[1 + atomicAdd(multi, 1u)] = bucket_base + k;
+#else
+      multi[1 + multi[0]++] = bucket_base + k;
+#endif
+    }
+  }
+};
+struct FIdxOrderMulti {
+  const u32 *begin;  // the group's whole bucket array
+  IdxEntry *ent;
+  const u32 *multi;
+  u32 *overflow;
+  GAR_HD void operator()(u32 t) const {
+    const u32 b = multi[1 + t];
+    const u32 lo = begin[b], m = begin[b + 1] - lo;
+    if (m > IDX_SMALL_BUCKET) {
+      GAR_ATOMIC_ADD(overflow, 1u);
+      return;
+    }
+    for (u32 k = 1; k < m; k++) {  // insertion sort of 32-byte entries by row id, in place
+      IdxEntry x = ent[lo + k];
+      u32 j = k;
+      while (j > 0 && ent[lo + j - 1].row > x.row) {
+        ent[lo + j] = ent[lo + j - 1];
+        j--;
+      }
+      if (j != k) ent[lo + j] = x;
+    }
+  }
+};
+// everything the host reads back at the END of a diff, gathered into one small block (no read-back in the middle)
+enum FlagWord { FW_BAD_KEYS = 0, FW_IDX_OVERFLOW = 1, FW_NDPORTS = 2, FW_NPAIRS = 3, FW_SEC0 = 4 /* 5 section words */, FW_WORDS = 16 };
+struct FGatherFinal {
+  const u32 *src;
+  u32 idx[5];
+  const u32 *npairs;  // nullable
+  u32 *flags;
+  GAR_HD void operator()(u32 k) const {
+    if (k < 5) flags[FW_SEC0 + k] = src[idx[k]];
+    else if (npairs) flags[FW_NPAIRS] = *npairs;
+  }
+};
 struct FGather5 {
   const u32 *src;
   u32 idx[5];
@@ -374,12 +465,9 @@ struct FGather5 {
 #define GAR_RETRY_WITH_RADIX 1000  // Pipeline::run: rebuild with force_radix (not an error)
 #define GAR_REFUSE_EMPTY_CACHE 1001  // orphan deletes against an empty object table (garecon.h "Orphan sweep precondition")
 struct FGatherHeader {
-  const u32 *ndports, *errflag;
-  u32 *dst;
-  GAR_HD void operator()(u32) const {
-    dst[0] = *ndports;
-    dst[1] = *errflag;
-  }
+  const u32 *ndports;
+  u32 *flags;
+  GAR_HD void operator()(u32) const { flags[FW_NDPORTS] = *ndports; }
 };
 // the two per-value joins in one pass (independent probe chains overlap): first alias record under the value's (zone, name),
 // and whether the owner the value names is still in the object cache
@@ -475,9 +563,11 @@ struct FDelKeyGa {
   DelKeys D;
   u32 *counts;   // count pass: written; emit pass: scanned
   gar_op *ops;   // nullptr in the count pass
+  u32 cap;
   GAR_HD void operator()(u32 k) const {
     u32 kind = D.kind[k];
     Str key = mkstr(D.slab, D.key[k]);
+    if (ops && counts[k + 1] > cap) return;  // beyond the buffer: dropped, the diff is re-run
     OpSink s{ops ? ops + counts[k] : nullptr, 0, 0xFFFFFFFFu};
     OwnerIter it = owner_open(W, key_hash_kinded(kind, key), key);
     for (u32 acc; (acc = owner_next(T, W, kind, it)) != GAR_NONE;) put_delete_chain(T, s, GAR_NONE, 0, acc);
@@ -490,9 +580,11 @@ struct FDelKeyR53 {
   DelKeys D;
   u32 *counts;
   gar_op *ops;
+  u32 cap;
   GAR_HD void operator()(u32 k) const {
     u32 kind = D.kind[k];
     Str key = mkstr(D.slab, D.key[k]);
+    if (ops && counts[k + 1] > cap) return;
     OpSink s{ops ? ops + counts[k] : nullptr, 0, 0xFFFFFFFFu};
     Owned ow;
     owned_collect(T, W, key_hash_kinded(kind, key), kind, key, ow);
@@ -517,7 +609,9 @@ struct FEgb {
   u32 *counts;   // count pass: written; emit pass: scanned
   gar_op *ops;
   u32 *status;
+  u32 cap;
   GAR_HD void operator()(u32 k) const {
+    if (ops && counts[k + 1] > cap) return;
     OpSink s{ops ? ops + counts[k] : nullptr, 0, 0xFFFFFFFFu};
     u32 st = egb_reconcile(T, W, B, k, s);
     if (ops) status[k] = st;
@@ -537,12 +631,14 @@ struct FCompactOps {
   gar_op *ops;
   u32 ctrl;
   const u32 *rows;
+  u32 cap;  // capacity of `ops`: nothing is written at or beyond it
   GAR_HD void operator()(u32 t, bool valid) const {
     u32 i = (rows && valid) ? rows[t] : t;
     u32 off = 0, c = 0;
     if (valid) {
       off = scanned[t];
       c = scanned[t + 1] - off;
+      if (off > cap || c > cap - off) c = 0;  // does not fit: dropped (the total in the flag block tells the host)
       if (c <= OPS_STAGE_CAP)
         for (u32 k = 0; k < c; k++) ops[off + k] = stage[(size_t)t * OPS_STAGE_CAP + k];
     }
@@ -550,7 +646,7 @@ struct FCompactOps {
     // the decide functions vote, so the whole warp enters when any lane needs it)
     bool redo = valid && c > OPS_STAGE_CAP;
     if (GAR_ANY(redo)) {
-      OpSink s{ops + off, 0, redo ? 0xFFFFFFFFu : 0u};
+      OpSink s{ops + off, 0, redo ? c : 0u};
       if (ctrl == GAR_CTRL_GA) ga_reconcile(T, W, i, redo, s);
       else r53_reconcile(T, W, i, redo, s);  // the per-object routine: same decisions as prepare/pairs/combine
     }
@@ -562,8 +658,10 @@ struct FGaOrphan {
   CountLayout L;
   u32 *counts;
   gar_op *ops;
+  u32 cap;
   GAR_HD void operator()(u32 a) const {
     if (ops && counts[L.ga_orph(a) + 1] == counts[L.ga_orph(a)]) return;  // emit pass: nothing to write
+    if (ops && counts[L.ga_orph(a) + 1] > cap) return;                    // beyond the buffer: dropped, the diff is re-run
     OpSink s{ops ? ops + counts[L.ga_orph(a)] : nullptr, 0, 0xFFFFFFFFu};
     ga_orphan(T, W, a, s);
     if (!ops) counts[L.ga_orph(a)] = s.n;
@@ -576,6 +674,7 @@ struct FR53OrphanAlias {
   CountLayout L;
   u32 *counts;
   gar_op *ops;
+  u32 cap;
   GAR_HD void operator()(u32 r) const {
     if (!ops) {
       OpSink s{nullptr, 0, 0};
@@ -584,6 +683,7 @@ struct FR53OrphanAlias {
       return;
     }
     if (counts[L.base0() + r + 1] == counts[L.base0() + r]) return;
+    if (counts[L.total()] > cap) return;  // the R53 orphan section interleaves two count ranges: all or nothing
     u32 z = W.rec_zone[r];
     u32 zv = T.a.rec_val_begin[T.a.zone_rec_begin[z]];  // first value row of the zone
     u32 off = counts[L.base0()] + (counts[L.base1() + zv] - counts[L.base1()]) + (counts[L.base0() + r] - counts[L.base0()]);
@@ -597,12 +697,13 @@ struct FR53OrphanValue {
   CountLayout L;
   u32 *counts;
   gar_op *ops;
+  u32 cap;
   GAR_HD void operator()(u32 v) const {
     if (!ops) {
       counts[L.base1() + v] = W.val_orphan[v];
       return;
     }
-    if (!W.val_orphan[v]) return;
+    if (!W.val_orphan[v] || counts[L.total()] > cap) return;
     u32 r = W.val_rec[v];
     u32 z = W.rec_zone[r];
     u32 rend = T.a.zone_rec_begin[z + 1];  // alias-phase ops of zones 0..z precede
@@ -675,7 +776,7 @@ struct Pipeline {
   // ---- prepare: everything that depends on the snapshot only (stages 1-3).  Runs once per loaded snapshot; the
   // digests and indexes stay resident for every later diff (full or incremental).
   bool prepared = false;
-  u64 n_dports = 0;
+  u64 n_dports = 0;  // from the final read-back of the last diff
   u32 *errflag = nullptr;
 
   u32 acc_guest_from = 0xFFFFFFFFu;  // sharded mode: set before prepare()
@@ -714,8 +815,13 @@ struct Pipeline {
     W.r53_mode = (u8 *)be.ensure(S_R53_MODE, (size_t)n + 1);
     W.r53_acc = (u32 *)be.ensure(S_R53_ACC, 4 * (size_t)(n + 1));
     W.r53_acc_dns = (gar_str *)be.ensure(S_R53_ACC_DNS, 8 * (size_t)(n + 1));
+    W.lb_hash = (u64 *)be.ensure(S_LB_HASH, 8 * (size_t)(T.a.n_lbs + 1));
+    W.rec_flags = (u8 *)be.ensure(S_REC_FLAGS, (size_t)nrec + 1);
+    for (int k = 0; k < IX_N; k++) W.hist[k] = IxHist{nullptr, 0};
+    W.pair_cap = 0;
+    W.dport_cap = 0;
     errflag = (u32 *)be.ensure(S_ERRFLAG, 256);
-    be.fill32(errflag, 0, 4);
+    be.fill32(errflag, 0, FW_WORDS);
     W.acc_guest_from = acc_guest_from;
     W.sharded = sharded;
     W.acc_claimed = nullptr;
@@ -727,6 +833,13 @@ struct Pipeline {
     if (n) be.for_each("classify_objects", n, FClassify{T, W, derived_public, nullptr, errflag});
     if (nlbi) be.for_each("tokenise_hostnames", nlbi, FTokenise{T, W});
     if (nacc) be.for_each("digest_accelerators", nacc, FDigestAccel{T, W});
+    if (T.a.n_lbs) be.for_each("hash_load_balancers", T.a.n_lbs, FLbHash{T, W});
+    {
+      unsigned long long *zm = (unsigned long long *)(errflag + 16 + 8);  // 32 bytes inside the 256-byte flag block, 8-byte aligned
+      be.fill32((u32 *)zm, 0, 8);
+      if (T.a.n_zones) be.for_each("zone_len_mask", T.a.n_zones, FZoneLenMask{T, W, zm});
+      W.zone_len_mask = (const u64 *)zm;
+    }
     if (nrec) {  // includes the records' values
       u32 *big = (u32 *)be.ensure(S_SORT_KEYS, 4 * (size_t)(nval / REC_INLINE_VALUES + 2));
       u32 *huge = (u32 *)be.ensure(S_SORT_VALS, 4 * (size_t)(nval / REC_HUGE_VALUES + 2));
@@ -736,105 +849,171 @@ struct Pipeline {
       if (nval > REC_INLINE_VALUES) be.for_each("prepare_records", BIG_BLOCKS * 256, FClassifyBigRecords{T, W, big, huge});
     }
   }
-  // index build that does not assume small buckets: fast per-bucket build first, stable radix rebuild if a bucket overflowed
-  template <class RowF>
-  HashIdx build_index_checked(int slot, u32 nrows, u32 load, RowF rowf) {
-    u32 *overflow = errflag + 1;
-    HashIdx ix = build_index(slot, nrows, load, rowf, overflow, force_radix);
-    if (!force_radix && nrows) {
-      u32 ov = 0;
-      be.download(&ov, overflow, 4);
-      if (ov) {
-        be.fill32(overflow, 0, 1);
-        ix = build_index(slot, nrows, load, rowf, overflow, true);
-      }
+  // ---- one-pass index build (the default).  plan: which indexes, their bucket counts and where each one's slice of the
+  // shared bucket / entry arrays starts.  The histogram hooks (Work::hist) must be armed BEFORE the row-local passes run.
+  struct IxPlan {
+    u32 off[IX_N] = {}, nb[IX_N] = {}, rows[IX_N] = {};
+    bool want[IX_N] = {};
+    u32 total_nb = 0;
+    u64 total_rows = 0;
+  };
+  IxPlan planA;
+  u32 *ixa_begin = nullptr, *ixa_fill = nullptr, *ixa_multi = nullptr;
+  IdxEntry *ixa_ent = nullptr;
+  u32 ovn_nb = 0;
+  void arm_group_a(u32 want_mask) {
+    const u32 rows[IX_N] = {T.a.n_lbs, T.a.n_accels, T.a.n_accels, T.a.n_zones, T.a.n_values, T.a.n_records, T.o.n_objects, 0};
+    const u32 load[IX_N] = {1, 1, 1, 1, 1, 2, 1, 8};
+    planA = IxPlan{};
+    for (int k = 0; k < IX_OVN; k++) {
+      planA.want[k] = (want_mask >> k) & 1u;
+      if (!planA.want[k]) continue;
+      planA.rows[k] = rows[k];
+      planA.nb[k] = next_pow2(rows[k] / load[k] < 16 ? 16 : rows[k] / load[k]);
+      planA.off[k] = planA.total_nb;
+      planA.total_nb += planA.nb[k];
+      planA.total_rows += rows[k];
     }
-    return ix;
+    ixa_begin = (u32 *)be.ensure(S_IXA_BEGIN, 4 * (size_t)(planA.total_nb + 2));
+    be.fill32(ixa_begin, 0, (size_t)planA.total_nb + 2);
+    for (int k = 0; k < IX_OVN; k++)
+      if (planA.want[k]) W.hist[k] = IxHist{ixa_begin + planA.off[k], planA.nb[k] - 1};
   }
+  HashIdx group_a_index(int k) const { return HashIdx{ixa_begin + planA.off[k], ixa_ent, planA.nb[k] - 1}; }
+  template <class RowF>
+  FIdxPlaceDirect<RowF> placer(int k, RowF rowf) const {
+    return FIdxPlaceDirect<RowF>{rowf, ixa_begin + planA.off[k], ixa_fill + planA.off[k], ixa_ent, planA.nb[k] - 1, planA.off[k], ixa_multi};
+  }
+  // scan + place + order of group A (after every armed row pass has run)
+  void finish_group_a() {
+    u32 *overflow = errflag + FW_IDX_OVERFLOW;
+    be.exclusive_scan(ixa_begin, planA.total_nb + 1);  // positions in the shared entry array; [total_nb] = number of entries
+    ixa_fill = (u32 *)be.ensure(S_IXA_FILL, 4 * (size_t)(planA.total_nb + 1));
+    ixa_ent = (IdxEntry *)be.ensure(S_IXA_ENT, sizeof(IdxEntry) * (size_t)(planA.total_rows + 1));
+    const u32 multi_cap = (u32)(planA.total_rows / 2 + 1);
+    ixa_multi = (u32 *)be.ensure(S_IXA_MULTI, 4 * (size_t)(multi_cap + 2));
+    be.fill32(ixa_fill, 0, (size_t)planA.total_nb + 1);
+    be.fill32(ixa_multi, 0, 1);
+    const IxPlan &P = planA;
+    auto n = [&](int k) { return P.want[k] ? P.rows[k] : 0u; };
+    be.for_each_multi("idx_place", {n(IX_LB), n(IX_OWNER), n(IX_THOST), n(IX_ZONE), n(IX_VAL), n(IX_ALIAS), n(IX_OBJ)}, placer(IX_LB, FRowLb{T, W}),
+                      placer(IX_OWNER, FRowOwner{T, W}), placer(IX_THOST, FRowThost{T, W}), placer(IX_ZONE, FRowZone{T}), placer(IX_VAL, FRowVal{T, W}),
+                      placer(IX_ALIAS, FRowAlias{T, W}), placer(IX_OBJ, FRowObj{T, W}));
+    be.for_each_dyn("idx_order", ixa_multi, multi_cap, FIdxOrderMulti{ixa_begin, ixa_ent, ixa_multi, overflow});
+    if (P.want[IX_LB]) W.ix_lb = group_a_index(IX_LB);
+    if (P.want[IX_OWNER]) W.ix_owner = group_a_index(IX_OWNER);
+    if (P.want[IX_THOST]) W.ix_thost = group_a_index(IX_THOST);
+    if (P.want[IX_ZONE]) W.ix_zone = group_a_index(IX_ZONE);
+    if (P.want[IX_VAL]) W.ix_val = group_a_index(IX_VAL);
+    if (P.want[IX_ALIAS]) W.ix_alias = group_a_index(IX_ALIAS);
+    if (P.want[IX_OBJ]) W.ix_obj = group_a_index(IX_OBJ);
+  }
+  // the orphan-value index: its keys exist only after the per-value joins (which count its buckets: mark_orphan_value)
+  void arm_ovn() {
+    ovn_nb = next_pow2(T.a.n_values / 8 < 16 ? 16 : T.a.n_values / 8);
+    u32 *cnt = (u32 *)be.ensure(S_IX_OVN + 0, 4 * (size_t)(ovn_nb + 2));
+    be.fill32(cnt, 0, (size_t)ovn_nb + 2);
+    W.hist[IX_OVN] = IxHist{cnt, ovn_nb - 1};
+  }
+  void finish_ovn() {
+    const u32 nval = T.a.n_values;
+    u32 *begin = W.hist[IX_OVN].cnt;
+    be.exclusive_scan(begin, ovn_nb + 1);
+    u32 *fill = (u32 *)be.ensure(S_OVN_FILL, 4 * (size_t)(ovn_nb + 1));
+    IdxEntry *ent = (IdxEntry *)be.ensure(S_IX_OVN + 1, sizeof(IdxEntry) * (size_t)(nval + 1));
+    u32 *multi = (u32 *)be.ensure(S_OVN_MULTI, 4 * (size_t)(nval / 2 + 3));
+    be.fill32(fill, 0, (size_t)ovn_nb + 1);
+    be.fill32(multi, 0, 1);
+    if (nval) be.for_each("idx_place", nval, FIdxPlaceDirect<FRowOvn>{FRowOvn{T, W}, begin, fill, ent, ovn_nb - 1, 0, multi});
+    be.for_each_dyn("idx_order", multi, nval / 2 + 1, FIdxOrderMulti{begin, ent, multi, errflag + FW_IDX_OVERFLOW});
+    W.ix_ovn = HashIdx{begin, ent, ovn_nb - 1};
+  }
+
   // what the sharded mode's routing needs of a rank's slice: the row-local pass + the (zone, name) -> alias record index
   void prepare_route() {
     alloc_work();
+    arm_group_a(1u << IX_ALIAS);
     stage1();
-    W.ix_alias = build_index_checked(S_IX_ALIAS, T.a.n_records, 2, FRowAlias{T, W});
+    finish_group_a();
   }
   // a directory shard's tables (gar_shard.h): probes in lbi_*, load balancers, accelerator stubs
   void prepare_directory() {
     alloc_work();
+    arm_group_a((1u << IX_LB) | (1u << IX_THOST));
     if (T.o.n_lbi) be.for_each("tokenise_hostnames", T.o.n_lbi, FTokenise{T, W});
     if (T.a.n_accels) be.for_each("digest_accelerators", T.a.n_accels, FDigestAccel{T, W});
-    W.ix_lb = build_index_checked(S_IX_LB, T.a.n_lbs, 1, FRowLb{T});
-    W.ix_thost = build_index_checked(S_IX_THOST, T.a.n_accels, 1, FRowThost{T, W});
+    if (T.a.n_lbs) be.for_each("hash_load_balancers", T.a.n_lbs, FLbHash{T, W});
+    finish_group_a();
   }
 
+  u32 dport_cap = 0, pair_cap = 0;  // capacities of the two intermediate relations whose size only the device knows
+  u64 ops_cap = 0;
+  bool tiny_caps = false;  // test hook (environment GAR_TINY_CAPS=1): start every capacity at 1 so that the grow-and-rerun paths run
   int prepare() {
     const u32 n = T.o.n_objects, nacc = T.a.n_accels, nzone = T.a.n_zones, nrec = T.a.n_records, nval = T.a.n_values;
     alloc_work();
+    if (!force_radix) {
+      arm_group_a((1u << IX_OVN) - 1);
+      arm_ovn();
+    }
     stage1();
-    // stage 2: listen-ports annotation -> desired port lists (count, scan, write)
+    // stage 2: listen-ports annotation -> desired port lists (count, scan, write).  The total stays on the device: the list
+    // buffer has a capacity, a diff that needs more is re-run (run_with)
     be.fill32(W.dport_begin, 0, (size_t)n + 1);
     if (n) be.for_each("listen_ports_count", n, FJsonCount{T, W});
     be.exclusive_scan(W.dport_begin, n + 1);
-    be.for_each("gather_header", 1, FGatherHeader{W.dport_begin + n, errflag, errflag + 4});
-    be.download_start(0, errflag + 4, 8);  // port total + layout-rule flag: read back while the indexes are built
+    be.for_each("gather_header", 1, FGatherHeader{W.dport_begin + n, errflag});
+    if (dport_cap < n / 2 + 1024 && !(tiny_caps && dport_cap)) dport_cap = tiny_caps ? 1 : n / 2 + 1024;
+    W.dport_cap = dport_cap;
+    W.dports = (i32 *)be.out_dports(dport_cap);
+    if (n) be.for_each("listen_ports_write", n, FJsonWrite{T, W});
 
     // stage 3: hash indexes
-    u32 *overflow = errflag + 1;
-    W.ix_lb = build_index(S_IX_LB, T.a.n_lbs, 1, FRowLb{T}, overflow, force_radix);
-    W.ix_owner = build_index(S_IX_OWNER, nacc, 1, FRowOwner{T, W}, overflow, force_radix);
-    W.ix_thost = build_index(S_IX_THOST, nacc, 1, FRowThost{T, W}, overflow, force_radix);
-    W.ix_zone = build_index(S_IX_ZONE, nzone, 1, FRowZone{T}, overflow, force_radix);
-    {
-      unsigned long long *zm = (unsigned long long *)(errflag + 16 + 8);  // 32 bytes inside the 128-byte flag block, 8-byte aligned
-      be.fill32((u32 *)zm, 0, 8);
-      if (nzone) be.for_each("zone_len_mask", nzone, FZoneLenMask{T, zm});
-      W.zone_len_mask = (const u64 *)zm;
+    u32 *overflow = errflag + FW_IDX_OVERFLOW;
+    if (!force_radix) {
+      finish_group_a();
+      if (nval) be.for_each("value_joins", nval, FValueJoins{T, W});
+      finish_ovn();
+    } else {  // some bucket was too large for the per-bucket ordering: every index through the stable radix sort
+      W.ix_lb = build_index(S_IX_LB, T.a.n_lbs, 1, FRowLb{T, W}, overflow, true);
+      W.ix_owner = build_index(S_IX_OWNER, nacc, 1, FRowOwner{T, W}, overflow, true);
+      W.ix_thost = build_index(S_IX_THOST, nacc, 1, FRowThost{T, W}, overflow, true);
+      W.ix_zone = build_index(S_IX_ZONE, nzone, 1, FRowZone{T}, overflow, true);
+      W.ix_val = build_index(S_IX_VAL, nval, 1, FRowVal{T, W}, overflow, true);
+      W.ix_alias = build_index(S_IX_ALIAS, nrec, 2, FRowAlias{T, W}, overflow, true);
+      W.ix_obj = build_index(S_IX_OBJ, n, 1, FRowObj{T, W}, overflow, true);
+      if (nval) be.for_each("value_joins", nval, FValueJoins{T, W});
+      W.ix_ovn = build_index(S_IX_OVN, nval, 8, FRowOvn{T, W}, overflow, true);
     }
-    W.ix_val = build_index(S_IX_VAL, nval, 1, FRowVal{T, W}, overflow, force_radix);
-    W.ix_alias = build_index(S_IX_ALIAS, nrec, 2, FRowAlias{T, W}, overflow, force_radix);
-    W.ix_obj = build_index(S_IX_OBJ, n, 1, FRowObj{T, W}, overflow, force_radix);
-    if (nval) be.for_each("value_joins", nval, FValueJoins{T, W});
-    W.ix_ovn = build_index(S_IX_OVN, nval, 8, FRowOvn{T, W}, overflow, force_radix);
-    // stage 2, second half: the port lists, now that their total is on the host
-    u32 hdr[2] = {0, 0};
-    be.download_wait(0, hdr, sizeof(hdr));
-    n_dports = hdr[0];
-    if (hdr[1]) return GAR_E_INVALID;
-    W.dports = (i32 *)be.out_dports(hdr[0]);
-    if (n && hdr[0]) be.for_each("listen_ports_write", n, FJsonWrite{T, W});
     return GAR_OK;
   }
 
-  // route53 ensure in relational form over `slots` object slots (rows == nullptr: slot = object row)
-  // (begin: per-object filter + pair counts, the pair total starts travelling to the host; end: the pairs themselves.
-  //  Stages queued between the two overlap the read-back.)
-  void r53_relational_begin(u32 slots, const u32 *rows, u32 *st_r53) {
+  // route53 ensure in relational form over `slots` object slots (rows == nullptr: slot = object row).  The number of
+  // (object, hostname) pairs stays on the device: the pair arrays have a capacity (re-run with larger ones if exceeded) and the
+  // pair kernel reads its extent from pair_begin[slots].
+  u64 n_pairs = 0;  // size of the relation in the last decide (filled from the final read-back; gar_last_counters)
+  void r53_relational(u32 slots, const u32 *rows, u32 *st_r53) {
     W.pair_begin = (u32 *)be.ensure(S_PAIR_BEGIN, 4 * (size_t)(slots + 2));
     be.fill32(W.pair_begin, 0, (size_t)slots + 1);
     if (slots) be.for_each_warp("r53_prepare", slots, FR53Prepare{T, W, st_r53, rows});
     be.exclusive_scan(W.pair_begin, slots + 1);
-    be.download_start(1, W.pair_begin + slots, 4);
-  }
-  u64 n_pairs = 0;  // size of the (object, hostname) relation of the last decide (gar_last_counters)
-  void r53_relational_end(u32 slots, const u32 *rows) {
-    u32 npairs = 0;
-    be.download_wait(1, &npairs, 4);
-    n_pairs = npairs;
-    W.pair_obj = (u32 *)be.ensure(S_PAIR_OBJ, 4 * (size_t)(npairs + 1));
-    W.pair_hn = (gar_str *)be.ensure(S_PAIR_HN, 8 * (size_t)(npairs + 1));
-    W.pair_code = (u8 *)be.ensure(S_PAIR_CODE, (size_t)npairs + 1);
-    W.pair_zone = (u32 *)be.ensure(S_PAIR_ZONE, 4 * (size_t)(npairs + 1));
-    W.pair_rec = (u32 *)be.ensure(S_PAIR_REC, 4 * (size_t)(npairs + 1));
-    if (npairs) {
+    if (pair_cap < slots + slots / 2 + 1024 && !(tiny_caps && pair_cap)) pair_cap = tiny_caps ? 1 : slots + slots / 2 + 1024;
+    W.pair_cap = pair_cap;
+    W.pair_obj = (u32 *)be.ensure(S_PAIR_OBJ, 4 * (size_t)(pair_cap + 1));
+    W.pair_hn = (gar_str *)be.ensure(S_PAIR_HN, 8 * (size_t)(pair_cap + 1));
+    W.pair_code = (u8 *)be.ensure(S_PAIR_CODE, (size_t)pair_cap + 1);
+    W.pair_zone = (u32 *)be.ensure(S_PAIR_ZONE, 4 * (size_t)(pair_cap + 1));
+    W.pair_rec = (u32 *)be.ensure(S_PAIR_REC, 4 * (size_t)(pair_cap + 1));
+    if (slots) {
       be.for_each("r53_fill_pairs", slots, FR53FillPairs{T, W, rows});
-      be.for_each_warp("r53_pairs", npairs, FR53Pair{T, W});
+      be.for_each_warp_dyn("r53_pairs", W.pair_begin + slots, pair_cap, FR53Pair{T, W});
     }
   }
 
-  // ---- full diff: every object + the orphan sections
+  // ---- full diff: every object + the orphan sections.  No read-back inside: sizes travel in the flag block (run_with).
   template <class OpsAlloc>
-  int decide_all(DiffCounts *dc, OpsAlloc ops_alloc) {
+  int decide_all(OpsAlloc ops_alloc) {
     const u32 n = T.o.n_objects, nacc = T.a.n_accels, nrec = T.a.n_records, nval = T.a.n_values;
-    u32 *overflow = errflag + 1;
     // stage 4: evaluate every object once (status + count + staged ops); count the orphan sections
     CountLayout L{n, nacc, nrec, nval};
     u32 *counts = (u32 *)be.ensure(S_COUNTS, 4 * (size_t)(L.total() + 2));
@@ -843,44 +1022,36 @@ struct Pipeline {
     gar_op *stage_r53 = (gar_op *)be.ensure(S_STAGE_R53, sizeof(gar_op) * ((size_t)n * OPS_STAGE_CAP + 1));
     u32 *st_ga = (u32 *)be.out_status_ga(n);
     u32 *st_r53 = (u32 *)be.out_status_r53(n);
-    r53_relational_begin(n, nullptr, st_r53);
     W.acc_claimed = (u8 *)be.ensure(S_ACC_CLAIMED, (size_t)nacc + 4);
     be.fill32((u32 *)W.acc_claimed, 0, ((size_t)nacc + 3) / 4);
     if (n) be.for_each_warp("ga_objects", n, FGaObj{T, W, counts + L.ga_obj(0), stage_ga, st_ga, nullptr});
-    if (nacc && orphan_sweep) be.for_each("ga_orphans_count", nacc, FGaOrphan{T, W, L, counts, nullptr});
-    r53_relational_end(n, nullptr);
+    r53_relational(n, nullptr, st_r53);
     if (n) be.for_each_warp("r53_objects", n, FR53Obj{T, W, counts + L.r53_obj(0), stage_r53, st_r53, nullptr});
-    if (nrec && orphan_sweep) be.for_each("r53_orphan_alias_count", nrec, FR53OrphanAlias{T, W, L, counts, nullptr});
-    if (nval && orphan_sweep) be.for_each("r53_orphan_value_count", nval, FR53OrphanValue{T, W, L, counts, nullptr});
+    if (orphan_sweep)
+      be.for_each_multi("orphans_count", {nacc, nrec, nval}, FGaOrphan{T, W, L, counts, nullptr, 0}, FR53OrphanAlias{T, W, L, counts, nullptr, 0},
+                        FR53OrphanValue{T, W, L, counts, nullptr, 0});
     be.exclusive_scan(counts, L.total() + 1);
-    u32 sec[6];
-    u32 *secdev = errflag + 8;  // same small scratch buffer
-    be.for_each("gather_section_begins", 6, FGather5{counts, {0, L.ga_orph(0), L.r53_obj(0), L.base0(), L.total()}, overflow, secdev});
-    be.download(sec, secdev, sizeof(sec));
-    if (sec[5] && !force_radix) return GAR_RETRY_WITH_RADIX;  // an index bucket was too large for the fast build
-    // an EMPTY object table with owned resources left: an unsynced informer looks exactly like this, and the orphan sections
-    // would delete everything the cluster owns.  (A shard that happens to home no object is fine: the cluster is not empty.)
-    if (n == 0 && !sharded && !allow_empty_cache && sec[4] != 0) return GAR_REFUSE_EMPTY_CACHE;
-    for (int k = 0; k < 5; k++) dc->section_begin[k] = sec[k];
-    dc->n_ops = sec[4];
-    dc->n_dports = n_dports;
+    be.for_each("gather_section_begins", 6, FGatherFinal{counts, {0, L.ga_orph(0), L.r53_obj(0), L.base0(), L.total()}, W.pair_begin + n, errflag});
 
-    // stage 5: move ops to their final, canonical positions
-    gar_op *ops = (gar_op *)ops_alloc(dc->n_ops);
-    if (n) be.for_each_warp("ga_objects_compact", n, FCompactOps{T, W, counts + L.ga_obj(0), stage_ga, ops, GAR_CTRL_GA, nullptr});
-    if (nacc && orphan_sweep) be.for_each("ga_orphans_emit", nacc, FGaOrphan{T, W, L, counts, ops});
+    // stage 5: move ops to their final, canonical positions (writes beyond the buffer's capacity are dropped: the diff is
+    // re-run with a larger buffer)
+    const u64 est = tiny_caps ? 1 : (u64)n + nacc / 8 + 1024;
+    if (ops_cap < est) ops_cap = est;
+    gar_op *ops = (gar_op *)ops_alloc(ops_cap);
+    const u32 cap = ops_cap > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (u32)ops_cap;
+    if (n) be.for_each_warp("ga_objects_compact", n, FCompactOps{T, W, counts + L.ga_obj(0), stage_ga, ops, GAR_CTRL_GA, nullptr, cap});
+    if (n) be.for_each_warp("r53_objects_compact", n, FCompactOps{T, W, counts + L.r53_obj(0), stage_r53, ops, GAR_CTRL_R53, nullptr, cap});
+    if (orphan_sweep)
+      be.for_each_multi("orphans_emit", {nacc, nrec, nval}, FGaOrphan{T, W, L, counts, ops, cap}, FR53OrphanAlias{T, W, L, counts, ops, cap},
+                        FR53OrphanValue{T, W, L, counts, ops, cap});
     W.acc_claimed = nullptr;  // other decide flavours (incremental, bindings) do not maintain it
-    if (n) be.for_each_warp("r53_objects_compact", n, FCompactOps{T, W, counts + L.r53_obj(0), stage_r53, ops, GAR_CTRL_R53, nullptr});
-    if (nrec && orphan_sweep) be.for_each("r53_orphan_alias_emit", nrec, FR53OrphanAlias{T, W, L, counts, ops});
-    if (nval && orphan_sweep) be.for_each("r53_orphan_value_emit", nval, FR53OrphanValue{T, W, L, counts, ops});
     return GAR_OK;
   }
 
   // ---- incremental diff: `m` object rows + `nd` deleted keys (device arrays).  counts layout:
   // [GA rows: m][GA deleted keys: nd][R53 rows: m][R53 deleted keys: nd][total]
   template <class OpsAlloc>
-  int decide_keys(const u32 *rows, u32 m, DelKeys D, u32 nd, DiffCounts *dc, OpsAlloc ops_alloc) {
-    u32 *overflow = errflag + 1;
+  int decide_keys(const u32 *rows, u32 m, DelKeys D, u32 nd, OpsAlloc ops_alloc) {
     const u32 total = 2 * m + 2 * nd;
     u32 *counts = (u32 *)be.ensure(S_COUNTS, 4 * (size_t)(total + 2));
     be.fill32(counts, 0, (size_t)total + 1);
@@ -894,78 +1065,101 @@ struct Pipeline {
       be.for_each("gather_derived", m, FGatherDerived{W.derived, rows, derived_out});
       be.for_each_warp("ga_objects", m, FGaObj{T, W, c_ga, stage_ga, st_ga, rows});
     }
-    if (nd) be.for_each("ga_deleted_keys_count", nd, FDelKeyGa{T, W, D, c_gad, nullptr});
-    r53_relational_begin(m, rows, st_r53);
-    r53_relational_end(m, rows);
+    if (nd) be.for_each("ga_deleted_keys_count", nd, FDelKeyGa{T, W, D, c_gad, nullptr, 0});
+    r53_relational(m, rows, st_r53);
     if (m) be.for_each_warp("r53_objects", m, FR53Obj{T, W, c_r53, stage_r53, st_r53, rows});
-    if (nd) be.for_each("r53_deleted_keys_count", nd, FDelKeyR53{T, W, D, c_r53d, nullptr});
+    if (nd) be.for_each("r53_deleted_keys_count", nd, FDelKeyR53{T, W, D, c_r53d, nullptr, 0});
     be.exclusive_scan(counts, total + 1);
-    u32 sec[6];
-    u32 *secdev = errflag + 8;
-    be.for_each("gather_section_begins", 6, FGather5{counts, {0, m, m + nd, 2 * m + nd, total}, overflow, secdev});
-    be.download(sec, secdev, sizeof(sec));
-    if (sec[5] && !force_radix) return GAR_RETRY_WITH_RADIX;
-    for (int k = 0; k < 5; k++) dc->section_begin[k] = sec[k];
-    dc->n_ops = sec[4];
-    dc->n_dports = 0;
-    gar_op *ops = (gar_op *)ops_alloc(dc->n_ops);
-    if (m) be.for_each_warp("ga_objects_compact", m, FCompactOps{T, W, c_ga, stage_ga, ops, GAR_CTRL_GA, rows});
-    if (nd) be.for_each("ga_deleted_keys_emit", nd, FDelKeyGa{T, W, D, c_gad, ops});
-    if (m) be.for_each_warp("r53_objects_compact", m, FCompactOps{T, W, c_r53, stage_r53, ops, GAR_CTRL_R53, rows});
-    if (nd) be.for_each("r53_deleted_keys_emit", nd, FDelKeyR53{T, W, D, c_r53d, ops});
+    be.for_each("gather_section_begins", 6, FGatherFinal{counts, {0, m, m + nd, 2 * m + nd, total}, W.pair_begin + m, errflag});
+    const u64 est = tiny_caps ? 1 : 2 * (u64)m + 4 * (u64)nd + 256;
+    if (ops_cap < est) ops_cap = est;
+    gar_op *ops = (gar_op *)ops_alloc(ops_cap);
+    const u32 cap = ops_cap > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (u32)ops_cap;
+    if (m) be.for_each_warp("ga_objects_compact", m, FCompactOps{T, W, c_ga, stage_ga, ops, GAR_CTRL_GA, rows, cap});
+    if (nd) be.for_each("ga_deleted_keys_emit", nd, FDelKeyGa{T, W, D, c_gad, ops, cap});
+    if (m) be.for_each_warp("r53_objects_compact", m, FCompactOps{T, W, c_r53, stage_r53, ops, GAR_CTRL_R53, rows, cap});
+    if (nd) be.for_each("r53_deleted_keys_emit", nd, FDelKeyR53{T, W, D, c_r53d, ops, cap});
     return GAR_OK;
   }
 
   // ---- EndpointGroupBinding set-diff over `nb` bindings (device pointers in `b`)
   template <class OpsAlloc>
-  int decide_bindings(const gar_bindings &b, DiffCounts *dc, OpsAlloc ops_alloc) {
-    u32 *overflow = errflag + 1;
+  int decide_bindings(const gar_bindings &b, OpsAlloc ops_alloc) {
+    u32 *overflow = errflag + FW_IDX_OVERFLOW;
     const u32 nb = b.n_bindings;
     DevBindings DB{b, build_index(S_IX_EG, b.n_known_egs, 1, FRowKnownEg{b}, overflow, force_radix)};
     u32 *counts = (u32 *)be.ensure(S_COUNTS, 4 * (size_t)(nb + 2));
     be.fill32(counts, 0, (size_t)nb + 1);
     u32 *st = (u32 *)be.out_status_ga(nb);
-    if (nb) be.for_each("egb_count", nb, FEgb{T, W, DB, counts, nullptr, nullptr});
+    if (nb) be.for_each("egb_count", nb, FEgb{T, W, DB, counts, nullptr, nullptr, 0});
     be.exclusive_scan(counts, nb + 1);
-    u32 sec[6];
-    u32 *secdev = errflag + 8;
-    be.for_each("gather_section_begins", 6, FGather5{counts, {0, nb, nb, nb, nb}, overflow, secdev});
-    be.download(sec, secdev, sizeof(sec));
-    if (sec[5] && !force_radix) return GAR_RETRY_WITH_RADIX;
-    for (int k = 0; k < 5; k++) dc->section_begin[k] = sec[k];
-    dc->n_ops = sec[4];
-    dc->n_dports = 0;
-    gar_op *ops = (gar_op *)ops_alloc(dc->n_ops);
-    if (nb) be.for_each("egb_emit", nb, FEgb{T, W, DB, counts, ops, st});
+    be.for_each("gather_section_begins", 6, FGatherFinal{counts, {0, nb, nb, nb, nb}, nullptr, errflag});
+    const u64 est = tiny_caps ? 1 : 4 * (u64)nb + 256;
+    if (ops_cap < est) ops_cap = est;
+    gar_op *ops = (gar_op *)ops_alloc(ops_cap);
+    const u32 cap = ops_cap > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (u32)ops_cap;
+    if (nb) be.for_each("egb_emit", nb, FEgb{T, W, DB, counts, ops, st, cap});
     return GAR_OK;
   }
-  template <class OpsAlloc>
-  int run_bindings(const gar_bindings &b, DiffCounts *dc, OpsAlloc ops_alloc) {
-    return run_with([&] { return decide_bindings(b, dc, ops_alloc); });
-  }
 
-  // prepare (once per snapshot; redone with the radix build if a bucket overflowed) + one of the decide flavours
+  // prepare (once per snapshot) + one of the decide flavours, then the ONE read-back of the diff: the flag block with the
+  // section sizes and everything that may force another attempt — a hash bucket too large for the per-bucket ordering
+  // (-> stable radix build), or an intermediate relation larger than its buffer (-> larger buffer).  Retries are rare:
+  // capacities only grow, so a snapshot shape settles after its first diff.
   template <class DecideF>
-  int run_with(DecideF decide) {
-    for (int attempt = 0; attempt < 2; attempt++) {
+  int run_with(DiffCounts *dc, bool full, DecideF decide) {
+    for (int attempt = 0; attempt < 8; attempt++) {
       if (!prepared) {
         int rc = prepare();
         if (rc != GAR_OK) return rc;
         prepared = true;
       }
       int rc = decide();
-      if (rc != GAR_RETRY_WITH_RADIX) return rc;
-      force_radix = true;  // some hash bucket was too large for the per-bucket build: rebuild with the stable radix sort
-      prepared = false;
+      if (rc != GAR_OK) return rc;
+      u32 fl[FW_WORDS];
+      be.download(fl, errflag, sizeof(fl));
+      if (fl[FW_BAD_KEYS]) return GAR_E_INVALID;
+      if (fl[FW_IDX_OVERFLOW] && !force_radix) {
+        force_radix = true;
+        prepared = false;
+        continue;
+      }
+      if (fl[FW_NDPORTS] > dport_cap) {
+        dport_cap = fl[FW_NDPORTS] + fl[FW_NDPORTS] / 8 + 16;
+        prepared = false;
+        continue;
+      }
+      if (fl[FW_NPAIRS] > pair_cap) {
+        pair_cap = fl[FW_NPAIRS] + fl[FW_NPAIRS] / 8 + 16;
+        continue;
+      }
+      const u64 nops = fl[FW_SEC0 + 4];
+      if (nops > ops_cap) {
+        ops_cap = nops + nops / 8 + 16;
+        continue;
+      }
+      n_dports = fl[FW_NDPORTS];
+      n_pairs = fl[FW_NPAIRS];
+      for (int k = 0; k < 5; k++) dc->section_begin[k] = fl[FW_SEC0 + k];
+      dc->n_ops = nops;
+      dc->n_dports = full ? n_dports : 0;
+      // an EMPTY object table with owned resources left: an unsynced informer looks exactly like this, and the orphan sections
+      // would delete everything the cluster owns.  (A shard that happens to home no object is fine: the cluster is not empty.)
+      if (full && T.o.n_objects == 0 && !sharded && !allow_empty_cache && nops != 0) return GAR_REFUSE_EMPTY_CACHE;
+      return GAR_OK;
     }
     return GAR_E_STATE;
   }
   template <class OpsAlloc>
   int run(DiffCounts *dc, OpsAlloc ops_alloc) {
-    return run_with([&] { return decide_all(dc, ops_alloc); });
+    return run_with(dc, true, [&] { return decide_all(ops_alloc); });
   }
   template <class OpsAlloc>
   int run_keys(const u32 *rows, u32 m, DelKeys D, u32 nd, DiffCounts *dc, OpsAlloc ops_alloc) {
-    return run_with([&] { return decide_keys(rows, m, D, nd, dc, ops_alloc); });
+    return run_with(dc, false, [&] { return decide_keys(rows, m, D, nd, ops_alloc); });
+  }
+  template <class OpsAlloc>
+  int run_bindings(const gar_bindings &b, DiffCounts *dc, OpsAlloc ops_alloc) {
+    return run_with(dc, false, [&] { return decide_bindings(b, ops_alloc); });
   }
 };

@@ -74,7 +74,29 @@ struct alignas(16) ValLink {  // per owner value row: first alias A record under
   gar_str alias_dns;
 };
 
+// the hash indexes, in build order (group A is built together in one pass, IX_OVN after the per-value joins)
+enum IxId { IX_LB, IX_OWNER, IX_THOST, IX_ZONE, IX_VAL, IX_ALIAS, IX_OBJ, IX_OVN, IX_N };
+// Bucket histogram hook of the one-pass index build: the row-local passes that PRODUCE a key hash also count its bucket
+// (cnt == nullptr: that index is not being built by the fast path).
+struct IxHist {
+  u32 *cnt;  // [nbuckets] zeroed before the row passes
+  u32 mask;
+};
+#if defined(__CUDA_ARCH__)
+#define GAR_HIST_ADD(p) atomicAdd((p), 1u)
+#else
+#define GAR_HIST_ADD(p) (++*(p))
+#endif
+GAR_HD void ix_count(const IxHist &h, u64 key_hash) {
+  if (h.cnt) GAR_HIST_ADD(&h.cnt[(u32)key_hash & h.mask]);
+}
+
 struct Work {
+  IxHist hist[IX_N];
+  u64 *lb_hash;    // [n_lbs] key_hash_lb(region, name), stored by the LB histogram pass for the placement pass
+  u8 *rec_flags;   // [n_records] bit 0: the record name contains a backslash (possible \\052 escape)
+  u32 pair_cap;    // capacity of the pair_* arrays (a diff whose pair count exceeds it is re-run with larger arrays)
+  u32 dport_cap;   // capacity of dports
   // objects
   u32 *derived;        // [n] GAR_DV_* | OBJ_*
   u64 *okey_hash;      // [n] key_hash_kinded(kind, "ns/name"): probes ix_owner / ix_val, builds ix_obj
@@ -132,6 +154,10 @@ struct Work {
   HashIdx ix_obj;    // (kind, "ns/name") -> object rows
   HashIdx ix_ovn;    // (zone, record name) -> orphan owner value rows
 };
+
+// which accelerators enter the owner / target-hostname indexes (sharded mode: guest rows answer by-hostname lookups only)
+GAR_HD bool acc_in_owner_index(const Work &W, u32 a, u32 fl) { return (fl & ACC_MINE) && (fl & ACC_OWNER_KEYED) && a < W.acc_guest_from; }
+GAR_HD bool acc_in_thost_index(const Work &W, u32 a, u32 fl) { return (fl & ACC_MINE) != 0 && (!W.sharded || a >= W.acc_guest_from); }
 
 // ------------------------------------------------------------------ key hashes (build and probe sides must agree)
 
@@ -224,7 +250,9 @@ GAR_HD void classify_object(const DevTables &T, const Work &W, u32 i) {
     if (has_listen) dv |= GAR_DV_PORTS_FROM_ANN;
   }
   if (!object_key_ok(T, i)) dv |= OBJ_KEY_BAD;
-  W.okey_hash[i] = (dv & OBJ_KEY_BAD) ? 0 : key_hash_kinded(kind, object_key(T, i));
+  const u64 okh = (dv & OBJ_KEY_BAD) ? 0 : key_hash_kinded(kind, object_key(T, i));
+  W.okey_hash[i] = okh;
+  if (!(dv & OBJ_KEY_BAD)) ix_count(W.hist[IX_OBJ], okh);
   W.derived[i] = dv;
   W.ann_r53[i] = r53;
   W.ann_name[i] = name;
@@ -406,8 +434,12 @@ GAR_HD void digest_accelerator(const DevTables &T, const Work &W, u32 a) {
   d.thost = thost;
   d.owner_key = key;
   W.acc_digest[a] = d;
-  W.acc_owner_hash[a] = (fl & ACC_OWNER_KEYED) ? key_hash_kinded((fl & ACC_OWNER_INGRESS) ? 1u : 0u, mkstr(A.slab, key)) : 0;
-  W.acc_thost_hash[a] = (fl & ACC_MINE) ? gar_hash(mkstr(A.slab, thost)) : 0;
+  const u64 owner_hash = (fl & ACC_OWNER_KEYED) ? key_hash_kinded((fl & ACC_OWNER_INGRESS) ? 1u : 0u, mkstr(A.slab, key)) : 0;
+  const u64 thost_hash = (fl & ACC_MINE) ? gar_hash(mkstr(A.slab, thost)) : 0;
+  W.acc_owner_hash[a] = owner_hash;
+  W.acc_thost_hash[a] = thost_hash;
+  if (acc_in_owner_index(W, a, fl)) ix_count(W.hist[IX_OWNER], owner_hash);
+  if (acc_in_thost_index(W, a, fl)) ix_count(W.hist[IX_THOST], thost_hash);
   W.acc_flags[a] = fl;
   W.acc_owner_key[a] = key;
   W.acc_owner[a] = owner;
@@ -444,7 +476,9 @@ GAR_HD void classify_value_at(const DevTables &T, const Work &W, u32 v, Str s) {
   }
   W.val_cls[v] = cls;
   W.val_key[v] = key;
-  W.val_key_hash[v] = cls ? key_hash_kinded((cls & VAL_OWNER_INGRESS) ? 1u : 0u, substr(s, (u32)(GAR_STR_OFF(key) - GAR_STR_OFF(ref)), (u32)GAR_STR_LEN(key))) : 0;
+  const u64 vkh = cls ? key_hash_kinded((cls & VAL_OWNER_INGRESS) ? 1u : 0u, substr(s, (u32)(GAR_STR_OFF(key) - GAR_STR_OFF(ref)), (u32)GAR_STR_LEN(key))) : 0;
+  W.val_key_hash[v] = vkh;
+  if (cls) ix_count(W.hist[IX_VAL], vkh);
 }
 GAR_HD void classify_value(const DevTables &T, const Work &W, u32 v) { classify_value_at(T, W, v, mkstr(T.a.slab, T.a.val_value[v])); }
 
@@ -706,7 +740,11 @@ struct PortList {
   u32 n;
 };
 GAR_HD PortList desired_ports(const DevTables &T, const Work &W, u32 i) {
-  if (W.derived[i] & GAR_DV_PORTS_FROM_ANN) return PortList{W.dports + W.dport_begin[i], W.dport_begin[i + 1] - W.dport_begin[i]};
+  if (W.derived[i] & GAR_DV_PORTS_FROM_ANN) {
+    u32 b = W.dport_begin[i], e = W.dport_begin[i + 1];
+    if (e > W.dport_cap) b = e = 0;  // more parsed ports than the buffer holds: the diff is re-run with a larger one
+    return PortList{W.dports + b, e - b};
+  }
   u32 b = T.o.obj_port_begin[i];
   return PortList{T.o.port_number + b, T.o.obj_port_begin[i + 1] - b};
 }
@@ -1478,6 +1516,7 @@ GAR_HD void r53_fill_pairs(const DevTables &T, const Work &W, u32 i, u32 t) {
   u32 p = W.pair_begin[t], pos = 0;
   Str piece;
   while (next_piece(hostnames, &pos, &piece)) {
+    if (p >= W.pair_cap) break;  // more pairs than the arrays hold: the diff is re-run with larger ones
     W.pair_obj[p] = i;
     W.pair_hn[p] = GAR_STR(GAR_STR_OFF(ref) + (u64)(piece.p - hostnames.p), piece.n);
     // self-observation (include/garecon.h): a repeated hostname needs no evaluation — the annotation bytes are in hand here
@@ -1555,7 +1594,7 @@ GAR_HD u32 r53_combine(const DevTables &T, const Work &W, u32 i, u32 t, bool val
     u32 kind = T.o.obj_kind[i], acc = W.r53_acc[i];
     bool created = false, stop = false;
     u32 k = 0;
-    for (u32 p = W.pair_begin[t]; p < W.pair_begin[t + 1] && !stop; p++, k++) {
+    for (u32 p = W.pair_begin[t]; p < W.pair_begin[t + 1] && p < W.pair_cap && !stop; p++, k++) {
       u32 code = W.pair_code[p];
       if (code == PAIR_NO_ZONE) {
         st = GAR_STATUS(GAR_ST_ERR_RETRY, GAR_D_NO_HOSTED_ZONE, 0);
@@ -1602,6 +1641,10 @@ GAR_HD void mark_orphan_value(const DevTables &T, const Work &W, u32 v) {
   if (cls & VAL_OWNER_3PART) {
     u32 kind = (cls & VAL_OWNER_INGRESS) ? 1u : 0u;
     orphan = object_in_cache(T, W, kind, mkstr(T.a.slab, W.val_key[v]), W.val_key_hash[v]) ? 0 : 1;
+  }
+  if (orphan) {
+    u32 rec = W.val_rec[v];
+    ix_count(W.hist[IX_OVN], key_hash_zoned_h(W.rec_zone[rec], W.rec_name_hash[rec]));
   }
   W.val_orphan[v] = orphan;
 }

@@ -124,6 +124,23 @@ struct gar_engine {
       if (ctx.error) g_nonuniform_vote = true;
     }
   }
+  template <class F>
+  void for_each_dyn(const char *name, const u32 *n_dev, u32 cap, const F &f) {
+    for_each(name, *n_dev < cap ? *n_dev : cap, f);
+  }
+  template <class F>
+  void for_each_warp_dyn(const char *name, const u32 *n_dev, u32 cap, const F &f) {
+    for_each_warp(name, *n_dev < cap ? *n_dev : cap, f);
+  }
+  template <class... Fs>
+  void for_each_multi(const char *, std::initializer_list<u32> ns, const Fs &...fs) {
+    launches++;
+    auto it = ns.begin();
+    auto one = [](u32 n, const auto &f) {
+      for (u32 i = 0; i < n; i++) f(i);
+    };
+    (one(*it++, fs), ...);
+  }
   void fill32(u32 *p, u32 v, size_t n) { std::fill(p, p + n, v); }
   void copy32(u32 *d, const u32 *s, size_t n) { memcpy(d, s, n * 4); }
   void exclusive_scan(u32 *d, u32 n) {
@@ -205,6 +222,7 @@ static int diff_impl(gar_engine *e, gar_changeset *out, const gar_keyset *ks, co
   e->launches = 0;
   if (!e->pipe) {
     e->pipe = new Pipeline<gar_engine>(*e, e->T);
+    if (const char *tc = getenv("GAR_TINY_CAPS")) e->pipe->tiny_caps = tc[0] == '1';
     if (e->shard_home) {
       e->pipe->acc_guest_from = e->sharder->guest_from;
       e->pipe->sharded = 1;

@@ -160,3 +160,18 @@ def test_results_do_not_depend_on_the_slab_layout(garecon, oracle, engine, layou
     assert got.diff(oracle.diff(snap, "default", mode=1)) == []
     for k in ("status_ga", "status_r53", "derived", "ops", "section_begin", "tok_code", "dport_begin", "dports"):
         assert getattr(got, k).tolist() == getattr(base, k).tolist(), k
+
+
+def test_capacity_overflow_paths(garecon, oracle, monkeypatch):
+    """GAR_TINY_CAPS=1: every capacity starts at 1, so the grow-and-rerun paths of the sync-free pipeline run on the GPU."""
+    monkeypatch.setenv("GAR_TINY_CAPS", "1")
+    for seed in (3, 4):
+        objects, actual = randmodel.make(seed, n_objects=200)
+        snap = garecon.pack(objects, actual)
+        with garecon.Engine(cluster_name="default") as e:
+            e.load(snap)
+            got = e.diff()
+            again = e.diff()
+        want = oracle.diff(snap, "default", mode=1)
+        assert got.diff(want) == [], got.describe_first_mismatch(want)
+        assert again.diff(want) == []

@@ -204,3 +204,25 @@ def test_results_do_not_depend_on_the_slab_layout(garecon, oracle, hostsim, seed
     assert got.diff(want) == [], got.describe_first_mismatch(want)
     for k in ("status_ga", "status_r53", "derived", "ops", "section_begin", "tok_code", "dport_begin", "dports"):
         assert getattr(got, k).tolist() == getattr(base, k).tolist(), k
+
+
+def test_hostsim_capacity_overflow_paths(garecon, oracle, monkeypatch):
+    """Intermediate relations whose size only the device knows (parsed ports, (object, hostname) pairs, ops) live in buffers
+    with a capacity; a diff that outgrows one is re-run with a larger buffer.  GAR_TINY_CAPS=1 starts every capacity at 1, so
+    every model takes those paths; the result must not change."""
+    import __graft_entry__ as ge
+    monkeypatch.setenv("GAR_TINY_CAPS", "1")
+    lib = garecon.abi.load_library(ge.build_hostsim())
+    for seed in range(8):
+        objects, actual = randmodel.make(seed, n_objects=40)
+        snap = garecon.pack(objects, actual)
+        with garecon.Engine(cluster_name="default", lib=lib) as e:
+            e.load(snap)
+            got = e.diff()
+            again = e.diff()
+            keys = e.diff_keys(list(range(0, len(objects), 3)), [(0, "default/gone")])
+        want = oracle.diff(snap, "default", mode=1)
+        assert got.diff(want) == [], got.describe_first_mismatch(want)
+        assert again.diff(want) == []
+        wk = oracle.diff_keys(snap, list(range(0, len(objects), 3)), [(0, "default/gone")], cluster="default", mode=1)
+        assert keys.diff(wk) == [], keys.describe_first_mismatch(wk)
