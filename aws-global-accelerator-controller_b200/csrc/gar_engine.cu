@@ -39,6 +39,81 @@ __global__ void __launch_bounds__(256, MINB) k_for_each_warp(const __grid_consta
   u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   f(i, i < n);
 }
+// ---- TMA-staged row passes (gar_pipeline.h "Staged"): one bulk copy (cp.async.bulk, completion on an mbarrier) brings the
+// block's string window(s) into shared memory; the row logic then reads shared memory instead of issuing its own global loads.
+__device__ __forceinline__ u32 smem_addr(const void *p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64 *bar, u32 count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u64 *bar, u32 bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, u32 bytes, u64 *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)), "l"(src), "r"(bytes),
+               "r"(smem_addr(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, u32 parity) {
+  u32 done;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+  } while (!done);
+}
+struct StagedView {
+  const u8 *smem[2];
+  const u8 *slab[2];
+  u64 lo[2], hi[2];  // staged slab byte range per window (hi includes 16 readable bytes of slack for the 8-byte unaligned loads)
+  __device__ __forceinline__ Str operator()(int c, gar_str r) const {
+    const u64 o = GAR_STR_OFF(r), n = GAR_STR_LEN(r);
+    if (o >= lo[c] && o + n + 16 <= hi[c]) return Str{smem[c] + (o - lo[c]), (u32)n};
+    return Str{slab[c] + o, (u32)n};
+  }
+};
+template <class F>
+__global__ void __launch_bounds__(256) k_for_each_staged(const __grid_constant__ F f, u32 n) {
+  constexpr u32 STAGE_BYTES = F::kStageBytes;  // per window
+  __shared__ alignas(128) u8 buf[F::kStageCols][STAGE_BYTES];
+  __shared__ alignas(8) u64 bar;
+  __shared__ u32 s_bytes[2];
+  __shared__ u64 s_lo[2];
+  const u32 r0 = blockIdx.x * blockDim.x, r1 = min(r0 + blockDim.x, n);
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    u32 total = 0;
+    for (int c = 0; c < F::kStageCols; c++) {
+      u64 lo = 0, hi = 0;
+      u32 bytes = 0;
+      const u8 *slab = f.stage_slab(c);
+      if (f.stage_window(c, r0, r1, &lo, &hi) && hi > lo && (((uintptr_t)slab) & 15) == 0) {
+        lo &= ~(u64)15;
+        u64 span = ((hi - lo + 15) & ~(u64)15) + 16;  // + slack for over-reads; slabs carry GAR_SLAB_PAD readable bytes behind their end
+        if (span > STAGE_BYTES) span = STAGE_BYTES;   // a wider window (other layouts): the strings beyond it fall back to the slab
+        bytes = (u32)span;
+      }
+      s_lo[c] = lo;
+      s_bytes[c] = bytes;
+      total += bytes;
+    }
+    mbar_expect_tx(&bar, total);
+    for (int c = 0; c < F::kStageCols; c++)
+      if (s_bytes[c]) tma_bulk_g2s(buf[c], f.stage_slab(c) + s_lo[c], s_bytes[c], &bar);
+  }
+  __syncthreads();
+  StagedView view;
+#pragma unroll
+  for (int c = 0; c < 2; c++) {
+    const bool on = c < F::kStageCols;
+    view.smem[c] = on ? buf[c < F::kStageCols ? c : 0] : nullptr;
+    view.slab[c] = on ? f.stage_slab(c) : nullptr;
+    view.lo[c] = on ? s_lo[c] : 1;
+    view.hi[c] = on ? s_lo[c] + s_bytes[c] : 0;
+  }
+  mbar_wait(&bar, 0);
+  const u32 i = r0 + threadIdx.x;
+  if (i < n) f.run(i, view);
+}
+
 // Count on the device (an intermediate relation whose size the host never learns mid-diff): one element per thread over the
 // buffer's CAPACITY; blocks beyond the real count leave at once.
 template <class F>
@@ -491,6 +566,16 @@ struct gar_engine {
     if (!n) return;
     stage_begin(name);
     k_for_each_warp<F, MinBlocks<F>::value><<<(n + 255) / 256, 256, 0, stream>>>(f, n);
+    launches++;
+    stage_end();
+  }
+  bool staged_passes = true;  // environment GAR_NO_TMA=1: the direct-load form of the staged row passes (A/B measurements)
+  template <class F>
+  void for_each_staged(const char *name, u32 n, const F &f) {
+    if (!n) return;
+    if (!staged_passes) return for_each(name, n, f);
+    stage_begin(name);
+    k_for_each_staged<F><<<(n + 255) / 256, 256, 0, stream>>>(f, n);
     launches++;
     stage_end();
   }
@@ -1018,6 +1103,7 @@ int gar_engine_create(const gar_config *cfg, gar_engine **out) {
   e->cluster = cfg->cluster_name ? cfg->cluster_name : "";
   e->timing = (cfg->flags & GAR_FLAG_STAGE_TIMING) != 0;
   e->reprepare = (cfg->flags & GAR_FLAG_REPREPARE) != 0;
+  if (const char *nt = getenv("GAR_NO_TMA")) e->staged_passes = nt[0] != '1';
   e->no_orphans = (cfg->flags & GAR_FLAG_NO_ORPHANS) != 0;
   e->allow_empty_cache = (cfg->flags & GAR_FLAG_ALLOW_EMPTY_CACHE) != 0;
   try {

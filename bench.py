@@ -199,15 +199,18 @@ def _unpin(torch, addrs):
         rt.cudaHostUnregister(a)
 
 
-def _cpu_arm(ob, snap, threads_list, reps=1):
-    """objects/s of the CPU port (oracle indexed mode) on `snap` for each thread count: {threads: objects/s}"""
+CPU_TUNED, CPU_LITERAL = 2, 1  # oracle modes: the tuned host-core baseline (flat indexes, tag digests, thread pool) / the literal indexed port
+
+
+def _cpu_arm(ob, snap, threads_list, reps=1, mode=CPU_TUNED):
+    """objects/s of a CPU mode of the oracle on `snap` for each thread count: {threads: objects/s}"""
     n = int(snap.objects.n_objects)
     out = {}
     for t in threads_list:
         best = None
         for _ in range(reps):
             t0 = time.perf_counter()
-            ob.diff_raw(snap.objects, snap.actual, snap.cluster.encode(), 1, t)
+            ob.diff_raw(snap.objects, snap.actual, snap.cluster.encode(), mode, t)
             dt = time.perf_counter() - t0
             best = dt if best is None else min(best, dt)
         out[int(t)] = n / best
@@ -235,22 +238,25 @@ def run_reference(args, rank, world):
     snap = synth.SynthSnapshot(cfg)
     cl = snap.cluster.encode()
     for _ in range(min(args.warmup, 1)):
-        ob.diff_raw(snap.objects, snap.actual, cl, 1, cores)
+        ob.diff_raw(snap.objects, snap.actual, cl, CPU_TUNED, cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        ob.diff_raw(snap.objects, snap.actual, cl, 1, cores)
+        ob.diff_raw(snap.objects, snap.actual, cl, CPU_TUNED, cores)
     dt = time.perf_counter() - t0
     value = n * args.steps / dt
     scaling = _cpu_arm(ob, snap, [t for t in _thread_ladder(cores) if t != cores])
     scaling[cores] = value
-    sample = f"the whole workload: config {args.config} generator at {n} objects (seed {int(cfg.seed)}, {args.layout}-major slabs), indexed oracle, {cores} threads"
+    literal = _cpu_arm(ob, snap, [cores], mode=CPU_LITERAL)[cores]
+    sample = (f"the whole workload: config {args.config} generator at {n} objects (seed {int(cfg.seed)}, {args.layout}-major slabs); oracle mode 2 "
+              f"(tuned: flat hash indexes, tag digests, thread pool; bit-identical to the literal port, tests/test_synth_configs.py), {cores} threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32 (bytes and indices)",
         "data": "synthetic", "config": {"workload": _workload_name(args.config, args.objects), "sample_objects": n, "same_config": n == args.objects,
                                         "slab_layout": args.layout, "seed": int(cfg.seed)},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-                         "scaling": {str(k): round(v, 1) for k, v in sorted(scaling.items())}},
+                         "scaling": {str(k): round(v, 1) for k, v in sorted(scaling.items())},
+                         "literal_port": {"value": literal, "cores": cores, "what": "oracle mode 1: the function-by-function restatement over unordered_map indexes"}},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "Go reference not timed (no Go toolchain in this image); CPU baseline is a C++ restatement of the reference's decision functions; "
                 "with N > 1 GPUs the GPU arm diffs N clusters of this size, this arm one (rank 0 only, per the bench contract)",
@@ -746,6 +752,7 @@ def main():
                 csnap, same = snap, True
             cn = int(csnap.objects.n_objects)
             scaling = _cpu_arm(ob, csnap, _thread_ladder(cores), reps=1)
+            literal = _cpu_arm(ob, csnap, sorted({1, cores}), mode=CPU_LITERAL)
             # the reference's own algorithm (per object: linear scan of all accelerators / all records, O(N*A)): timed at
             # two small sizes to show the quadratic growth; it is the bit-exactness arbiter, not a fair batch baseline
             faithful = []
@@ -759,8 +766,11 @@ def main():
                                     "note": "literal per-object linear scans as in the reference (quadratic); indexed multi-thread figure is cpu_baseline"}
             line["cpu_baseline"] = {"value": scaling[cores], "unit": UNIT, "cores": cores, "kind": "port", "same_config": same,
                                     "scaling": {str(k): round(v, 1) for k, v in sorted(scaling.items())},
-                                    "sample": f"{'the timed workload itself' if same else 'a sample'}: config {args.config} generator at {cn} objects, oracle indexed mode, "
-                                              f"{cores} threads (thread ladder in `scaling`); Go reference not timed (no toolchain)"}
+                                    "literal_port": {"scaling": {str(k): round(v, 1) for k, v in sorted(literal.items())},
+                                                     "what": "oracle mode 1: the function-by-function restatement over unordered_map indexes (the parity arbiter)"},
+                                    "sample": f"{'the timed workload itself' if same else 'a sample'}: config {args.config} generator at {cn} objects, oracle mode 2 (tuned: flat "
+                                              f"hash indexes, tag digests, thread pool; bit-identical to the literal port), {cores} threads (thread ladder in `scaling`); "
+                                              f"Go reference not timed (no toolchain)"}
     _unpin(torch, pinned_addrs)
     del snap, o, a, hcs, flush_buf
     torch.cuda.empty_cache()

@@ -16,16 +16,21 @@
 //     update sequencing and cardinality rules, cleanup, FindOwneredARecordSets, GetHostedZone,
 //     Route53OwnerValue, and the batch/ordering semantics (which the reference does not have).
 //
-// Two evaluation modes produce the same change set:
+// Three evaluation modes produce the same change set (tests/test_synth_configs.py, test_oracle_crosscheck.py):
 //   mode 0 "faithful": per object, the reference's own linear scans (O(N*A), O(N*H*R)).
 //   mode 1 "indexed" : same decision functions over unordered_map indexes built once; optionally
-//                      multi-threaded over object ranges.  This is the fair CPU batch baseline.
+//                      multi-threaded over object ranges.  The literal checker at sizes mode 0 cannot reach.
+//   mode 2 "tuned"   : the decisions restated over flat hash indexes on precomputed hashes, tag digests and a thread pool —
+//                      the fair host-core baseline of bench.py (BASELINE.md §3 cpu_indexed_mt); never the arbiter.
 
 #include "../include/garecon.h"
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
 #include <cstdint>
+#include <functional>
+#include <mutex>
 #include <cstring>
 #include <map>
 #include <string>
@@ -1308,6 +1313,860 @@ bool parseOwner(sv owner, ObjKey *k) {
   return true;
 }
 
+// ==================================================================== mode 2 "tuned": cpu_indexed_mt of BASELINE.md §3
+//
+// The SAME decisions as modes 0 / 1 (tests prove the three bit-identical), written the way a maintainer would write a fast
+// batch CPU version: flat bucketed hash indexes over precomputed 64-bit hashes of slab views, no std::map / std::string per
+// row, per-accelerator tag digests, index build and every pass range-partitioned over one persistent thread pool.  It exists
+// so that the GPU engine is compared with a FAIR host-core baseline (bench.py cpu_baseline "tuned"); it decides nothing the
+// other two modes do not.
+
+namespace tuned {
+
+// ---- a persistent pool: run(fn) calls fn(t) on every thread t in [0, T)
+class Pool {
+ public:
+  explicit Pool(int threads) : T(threads < 1 ? 1 : threads) {
+    for (int t = 1; t < T; t++) th.emplace_back([this, t] { loop(t); });
+  }
+  ~Pool() {
+    {
+      std::unique_lock<std::mutex> lk(m);
+      stop = true;
+      gen++;
+    }
+    cv.notify_all();
+    for (auto &x : th) x.join();
+  }
+  template <class F>
+  void run(const F &f) {
+    std::function<void(int)> g = f;
+    {
+      std::unique_lock<std::mutex> lk(m);
+      job = &g;
+      pending = T - 1;
+      gen++;
+    }
+    cv.notify_all();
+    g(0);
+    std::unique_lock<std::mutex> lk(m);
+    done.wait(lk, [&] { return pending == 0; });
+    job = nullptr;
+  }
+  // f(lo, hi) over [0, n) cut into T contiguous ranges
+  template <class F>
+  void ranges(uint64_t n, const F &f) {
+    run([&](int t) {
+      uint64_t lo = n * (uint64_t)t / T, hi = n * (uint64_t)(t + 1) / T;
+      if (hi > lo) f(lo, hi, t);
+    });
+  }
+  const int T;
+
+ private:
+  void loop(int t) {
+    uint64_t seen = 0;
+    for (;;) {
+      std::function<void(int)> *j;
+      {
+        std::unique_lock<std::mutex> lk(m);
+        cv.wait(lk, [&] { return gen != seen; });
+        seen = gen;
+        if (stop) return;
+        j = job;
+      }
+      (*j)(t);
+      std::unique_lock<std::mutex> lk(m);
+      if (--pending == 0) done.notify_one();
+    }
+  }
+  std::vector<std::thread> th;
+  std::mutex m;
+  std::condition_variable cv, done;
+  std::function<void(int)> *job = nullptr;
+  uint64_t gen = 0;
+  int pending = 0;
+  bool stop = false;
+};
+
+inline uint64_t mix(uint64_t h) {
+  h ^= h >> 32;
+  h *= 0xD6E8FEB86659FD93ull;
+  h ^= h >> 32;
+  h *= 0xD6E8FEB86659FD93ull;
+  return h ^ (h >> 32);
+}
+inline uint64_t h64(const char *p, size_t n) {  // 8 bytes per step
+  uint64_t h = 0x9E3779B97F4A7C15ull ^ (n * 0xC2B2AE3D27D4EB4Full);
+  size_t i = 0;
+  for (; i + 8 <= n; i += 8) {
+    uint64_t w;
+    memcpy(&w, p + i, 8);
+    h = (h ^ w) * 0x9E3779B185EBCA87ull;
+    h ^= h >> 29;
+  }
+  if (i < n) {
+    uint64_t w = 0;
+    memcpy(&w, p + i, n - i);
+    h = (h ^ w) * 0x9E3779B185EBCA87ull;
+    h ^= h >> 29;
+  }
+  return mix(h);
+}
+inline uint64_t h64(sv s) { return h64(s.data(), s.size()); }
+
+// a key assembled from parts on the stack (owner tag value, owner value, "zone name + dot" ...): no heap in the hot loop
+struct KeyBuf {
+  char small[512];
+  std::string big;
+  size_t n = 0;
+  bool heap = false;
+  void add(sv s) {
+    if (!heap && n + s.size() <= sizeof(small)) {
+      memcpy(small + n, s.data(), s.size());
+    } else {
+      if (!heap) {
+        big.assign(small, n);
+        heap = true;
+      }
+      big.append(s);
+    }
+    n += s.size();
+  }
+  void add(char c) { add(sv(&c, 1)); }
+  sv view() const { return heap ? sv(big) : sv(small, n); }
+};
+
+// bucketed multi-map hash -> rows, rows of equal hash ascending (the callers verify the key bytes)
+struct FlatIndex {
+  std::vector<uint32_t> begin, rows;
+  std::vector<uint64_t> hs;
+  uint32_t mask = 0;
+  // key(i, &h) -> indexed?
+  template <class KeyF>
+  void build(Pool &pool, uint32_t n, const KeyF &key) {
+    uint32_t nb = 16;
+    while (nb < n) nb <<= 1;
+    mask = nb - 1;
+    std::vector<uint64_t> th(n);
+    std::vector<uint8_t> ok(n);
+    std::vector<uint32_t> cnt((size_t)nb + 1, 0);
+    pool.ranges(n, [&](uint64_t lo, uint64_t hi, int) {
+      for (uint64_t i = lo; i < hi; i++) {
+        uint64_t h = 0;
+        ok[i] = key((uint32_t)i, &h) ? 1 : 0;
+        th[i] = h;
+        if (ok[i]) __atomic_fetch_add(&cnt[(uint32_t)h & mask], 1u, __ATOMIC_RELAXED);
+      }
+    });
+    // exclusive scan, blocked over the pool
+    begin.assign((size_t)nb + 1, 0);
+    std::vector<uint64_t> part((size_t)pool.T + 1, 0);
+    pool.ranges(nb, [&](uint64_t lo, uint64_t hi, int t) {
+      uint64_t s = 0;
+      for (uint64_t b = lo; b < hi; b++) s += cnt[b];
+      part[(size_t)t + 1] = s;
+    });
+    for (int t = 0; t < pool.T; t++) part[(size_t)t + 1] += part[(size_t)t];
+    pool.ranges(nb, [&](uint64_t lo, uint64_t hi, int t) {
+      uint64_t s = part[(size_t)t];
+      for (uint64_t b = lo; b < hi; b++) {
+        begin[b] = (uint32_t)s;
+        s += cnt[b];
+      }
+    });
+    const uint32_t total = (uint32_t)part[(size_t)pool.T];
+    begin[nb] = total;
+    rows.assign(total, 0);
+    hs.assign(total, 0);
+    std::vector<uint32_t> cur(begin.begin(), begin.end() - 1);
+    pool.ranges(n, [&](uint64_t lo, uint64_t hi, int) {
+      for (uint64_t i = lo; i < hi; i++)
+        if (ok[i]) {
+          uint32_t p = __atomic_fetch_add(&cur[(uint32_t)th[i] & mask], 1u, __ATOMIC_RELAXED);
+          rows[p] = (uint32_t)i;
+          hs[p] = th[i];
+        }
+    });
+    pool.ranges(nb, [&](uint64_t lo, uint64_t hi, int) {  // rows of a bucket ascending
+      for (uint64_t b = lo; b < hi; b++) {
+        uint32_t s = begin[b], e = begin[b + 1];
+        for (uint32_t k = s + 1; k < e; k++) {
+          uint32_t r = rows[k];
+          uint64_t h = hs[k];
+          uint32_t j = k;
+          while (j > s && rows[j - 1] > r) {
+            rows[j] = rows[j - 1];
+            hs[j] = hs[j - 1];
+            j--;
+          }
+          rows[j] = r;
+          hs[j] = h;
+        }
+      }
+    });
+  }
+  template <class F>
+  void each(uint64_t h, const F &f) const {  // f(row) -> keep going?
+    if (rows.empty()) return;
+    uint32_t b = (uint32_t)h & mask;
+    for (uint32_t p = begin[b]; p < begin[b + 1]; p++)
+      if (hs[p] == h && !f(rows[p])) return;
+  }
+};
+
+struct ObjV {  // one object: views only
+  const Snap *S;
+  uint32_t row;
+  int kind;
+  sv ns, name;
+  uint32_t a0, a1;
+  bool find(const char *k, sv *val) const {  // annotation keys are unique per object (garecon.h); a later duplicate would win, as in a map
+    size_t kl = strlen(k);
+    for (uint32_t x = a1; x > a0; x--) {
+      gar_str r = S->o->ann_key[x - 1];
+      if (GAR_STR_LEN(r) == kl && !memcmp(S->o->slab + GAR_STR_OFF(r), k, kl)) {
+        if (val) *val = S->os(S->o->ann_val[x - 1]);
+        return true;
+      }
+    }
+    return false;
+  }
+  bool has(const char *k) const { return find(k, nullptr); }
+  sv get(const char *k) const {
+    sv v;
+    find(k, &v);
+    return v;
+  }
+};
+
+struct AccDig {
+  sv managed, owner, thost, cluster;  // later duplicate wins, missing reads as ""
+  bool mine;                          // managed == "true" && cluster == --cluster-name
+};
+
+inline bool eqParts3(sv whole, sv a, char s1, sv b, char s2, sv c) {  // whole == a + s1 + b + s2 + c
+  if (whole.size() != a.size() + b.size() + c.size() + 2) return false;
+  const char *p = whole.data();
+  return !memcmp(p, a.data(), a.size()) && p[a.size()] == s1 && !memcmp(p + a.size() + 1, b.data(), b.size()) && p[a.size() + 1 + b.size()] == s2 &&
+         !memcmp(p + a.size() + 2 + b.size(), c.data(), c.size());
+}
+inline bool eqPlusDot(sv whole, sv a) { return whole.size() == a.size() + 1 && whole.back() == '.' && !memcmp(whole.data(), a.data(), a.size()); }
+// replaceWildcards(name) == hostname + "."  (route53.go:360-371)
+inline bool nameMatches(sv name, sv hostname) {
+  size_t p = name.find("\\052");
+  if (p == sv::npos) return eqPlusDot(name, hostname);
+  if (name.size() - 3 != hostname.size() + 1 || name.back() != '.') return false;
+  if (p >= hostname.size() || hostname[p] != '*') return false;
+  return !memcmp(name.data(), hostname.data(), p) && !memcmp(name.data() + p + 4, hostname.data() + p + 1, hostname.size() - p - 1);
+}
+inline bool lowerIs(sv p, const char *abc) {  // strings.ToLower(p) == abc for an ASCII-letter abc (asciiLower above)
+  auto lc = [](char c) { return (c >= 'A' && c <= 'Z') ? char(c - 'A' + 'a') : c; };
+  return p.size() == 3 && lc(p[0]) == abc[0] && lc(p[1]) == abc[1] && lc(p[2]) == abc[2];
+}
+
+struct Scratch {  // per thread, reused across objects
+  std::vector<uint32_t> accs, vals;
+  std::vector<int> egState;
+  std::vector<int32_t> ports;
+  std::vector<std::pair<sv, uint32_t>> names;
+  std::vector<std::pair<uint32_t, uint32_t>> recs;  // (alias record row, first value row)
+  std::vector<std::pair<sv, sv>> utags, target;
+  std::vector<sv> hostnames;
+};
+
+class Fast {
+ public:
+  Snap S;
+  Pool &pool;
+  std::vector<uint32_t> recZone, valRec;
+  std::vector<AccDig> ad;
+  FlatIndex ixOwner, ixThost, ixLb, ixZone, ixVal, ixAlias, ixObj;
+
+  Fast(const gar_objects *o, const gar_actual *a, const char *cluster, Pool &p) : S{o, a, cluster}, pool(p) {
+    recZone.resize(a->n_records);
+    valRec.resize(a->n_values);
+    pool.ranges(a->n_zones, [&](uint64_t lo, uint64_t hi, int) {
+      for (uint64_t z = lo; z < hi; z++)
+        for (uint32_t r = a->zone_rec_begin[z]; r < a->zone_rec_begin[z + 1]; r++) recZone[r] = (uint32_t)z;
+    });
+    pool.ranges(a->n_records, [&](uint64_t lo, uint64_t hi, int) {
+      for (uint64_t r = lo; r < hi; r++)
+        for (uint32_t v = a->rec_val_begin[r]; v < a->rec_val_begin[r + 1]; v++) valRec[v] = (uint32_t)r;
+    });
+    ad.resize(a->n_accels);
+    pool.ranges(a->n_accels, [&](uint64_t lo, uint64_t hi, int) {
+      for (uint64_t i = lo; i < hi; i++) {
+        AccDig d{};
+        for (uint32_t t = a->acc_tag_begin[i]; t < a->acc_tag_begin[i + 1]; t++) {
+          sv k = S.as(a->tag_key[t]), v = S.as(a->tag_val[t]);
+          if (k == kTagManaged) d.managed = v;
+          else if (k == kTagOwner) d.owner = v;
+          else if (k == kTagTargetHostname) d.thost = v;
+          else if (k == kTagCluster) d.cluster = v;
+        }
+        d.mine = d.managed == "true" && d.cluster == sv(S.cluster);
+        ad[i] = d;
+      }
+    });
+    ixOwner.build(pool, a->n_accels, [&](uint32_t i, uint64_t *h) {
+      *h = h64(ad[i].owner);
+      return ad[i].mine;
+    });
+    ixThost.build(pool, a->n_accels, [&](uint32_t i, uint64_t *h) {
+      *h = h64(ad[i].thost);
+      return ad[i].mine;
+    });
+    ixLb.build(pool, a->n_lbs, [&](uint32_t i, uint64_t *h) {
+      *h = mix(h64(S.as(a->lb_region[i])) + 0x51ull * h64(S.as(a->lb_name[i])));
+      return true;
+    });
+    ixZone.build(pool, a->n_zones, [&](uint32_t i, uint64_t *h) {
+      *h = h64(S.as(a->zone_name[i]));
+      return true;
+    });
+    ixVal.build(pool, a->n_values, [&](uint32_t v, uint64_t *h) {
+      *h = h64(S.as(a->val_value[v]));
+      return true;
+    });
+    ixAlias.build(pool, a->n_records, [&](uint32_t r, uint64_t *h) {
+      *h = mix(h64(S.as(a->rec_name[r])) + recZone[r]);
+      return a->rec_has_alias[r] != 0;
+    });
+    ixObj.build(pool, o->n_objects, [&](uint32_t i, uint64_t *h) {
+      *h = objHash(o->obj_kind[i], S.os(o->obj_ns[i]), S.os(o->obj_name[i]));
+      return true;
+    });
+  }
+  static uint64_t objHash(int kind, sv ns, sv name) { return mix(h64(ns) * 3 + h64(name) + (uint64_t)kind); }
+  bool inCache(int kind, sv ns, sv name) const {
+    bool found = false;
+    ixObj.each(objHash(kind, ns, name), [&](uint32_t i) {
+      found = S.o->obj_kind[i] == kind && S.os(S.o->obj_ns[i]) == ns && S.os(S.o->obj_name[i]) == name;
+      return !found;
+    });
+    return found;
+  }
+  ObjV object(uint32_t i) const {
+    return ObjV{&S, i, S.o->obj_kind[i], S.os(S.o->obj_ns[i]), S.os(S.o->obj_name[i]), S.o->obj_ann_begin[i], S.o->obj_ann_begin[i + 1]};
+  }
+  static sv resourceOf(int kind) { return kind == GAR_KIND_SERVICE ? sv("service") : sv("ingress"); }
+  bool wasLoadBalancerService(const ObjV &ob) const {
+    return S.o->obj_spec_type[ob.row] == GAR_SVC_LOADBALANCER && (ob.has(kAnnLBType) || (S.o->obj_flags[ob.row] & GAR_OBJ_HAS_LB_CLASS));
+  }
+  bool wasALBIngress(const ObjV &ob) const {
+    if ((S.o->obj_flags[ob.row] & GAR_OBJ_HAS_INGRESS_CLASS) && S.os(S.o->obj_ingress_class[ob.row]) == "alb") return true;
+    return ob.has(kAnnIngressClass);
+  }
+  // acceleratorTags (:35-51)
+  static void userTags(const ObjV &ob, std::vector<std::pair<sv, sv>> *out) {
+    out->clear();
+    sv all;
+    if (!ob.find(kAnnTags, &all)) all = sv();
+    size_t start = 0;
+    for (size_t i = 0; i <= all.size(); i++)
+      if (i == all.size() || all[i] == ',') {
+        sv piece = all.substr(start, i - start);
+        size_t e1 = piece.find('=');
+        if (e1 != sv::npos && piece.find('=', e1 + 1) == sv::npos) out->push_back({piece.substr(0, e1), piece.substr(e1 + 1)});
+        start = i + 1;
+      }
+  }
+  // listenerForService (:503-515) / listenerForIngress (:522-557)
+  void desiredListener(const ObjV &ob, std::vector<int32_t> *ports, int *proto, bool *fromAnn) const {
+    ports->clear();
+    *proto = GAR_PROTO_TCP;
+    *fromAnn = false;
+    uint32_t b = S.o->obj_port_begin[ob.row], e = S.o->obj_port_begin[ob.row + 1];
+    if (ob.kind == GAR_KIND_SERVICE) {
+      for (uint32_t p = b; p < e; p++) {
+        ports->push_back(S.o->port_number[p]);
+        sv pr = S.os(S.o->port_proto[p]);
+        if (lowerIs(pr, "udp")) *proto = GAR_PROTO_UDP;
+        else if (lowerIs(pr, "tcp")) *proto = GAR_PROTO_TCP;
+      }
+      return;
+    }
+    sv lp;
+    if (ob.find(kAnnListenPorts, &lp)) {
+      *fromAnn = true;
+      std::vector<int32_t> parsed;
+      if (parseListenPorts(lp, &parsed)) *ports = parsed;
+      return;
+    }
+    for (uint32_t p = b; p < e; p++) ports->push_back(S.o->port_number[p]);
+  }
+  // ListGlobalAcceleratorByResource (:87-110)
+  void listByResource(sv resource, sv ns, sv name, std::vector<uint32_t> *out) const {
+    out->clear();
+    KeyBuf k;
+    k.add(resource);
+    k.add('/');
+    k.add(ns);
+    k.add('/');
+    k.add(name);
+    sv key = k.view();
+    ixOwner.each(h64(key), [&](uint32_t i) {
+      if (ad[i].owner == key) out->push_back(i);
+      return true;
+    });
+  }
+  int64_t getLoadBalancer(sv region, sv name) const {
+    int64_t found = -1;
+    ixLb.each(mix(h64(region) + 0x51ull * h64(name)), [&](uint32_t i) {
+      if (S.as(S.a->lb_region[i]) == region && S.as(S.a->lb_name[i]) == name) found = i;
+      return found < 0;
+    });
+    return found;
+  }
+  sv actualTag(uint32_t acc, sv key) const {  // tagsContainsAllValues' `actual` map: later duplicate wins, missing reads as ""
+    if (key == kTagManaged) return ad[acc].managed;
+    if (key == kTagOwner) return ad[acc].owner;
+    if (key == kTagTargetHostname) return ad[acc].thost;
+    if (key == kTagCluster) return ad[acc].cluster;
+    sv v;
+    for (uint32_t t = S.a->acc_tag_begin[acc]; t < S.a->acc_tag_begin[acc + 1]; t++)
+      if (S.as(S.a->tag_key[t]) == key) v = S.as(S.a->tag_val[t]);
+    return v;
+  }
+  // acceleratorChanged (:412-437)
+  bool acceleratorChanged(uint32_t acc, sv lbDns, sv resource, const ObjV &ob, Scratch &sc) const {
+    if (!S.a->acc_enabled[acc]) return true;
+    sv an = S.as(S.a->acc_name[acc]), want = ob.get(kAnnName);
+    if (!want.empty()) {
+      if (an != want) return true;
+    } else if (!eqParts3(an, resource, '-', ob.ns, '-', ob.name)) {
+      return true;
+    }
+    // targetTags: the three system tags, overlaid by the user tags (a map: a later assignment to a key replaces the value)
+    userTags(ob, &sc.utags);
+    bool uManaged = false, uOwner = false, uThost = false;
+    for (size_t x = 0; x < sc.utags.size(); x++) {
+      sv k = sc.utags[x].first;
+      bool overridden = false;
+      for (size_t y = x + 1; y < sc.utags.size(); y++) overridden |= sc.utags[y].first == k;
+      uManaged |= k == kTagManaged;
+      uOwner |= k == kTagOwner;
+      uThost |= k == kTagTargetHostname;
+      if (!overridden && actualTag(acc, k) != sc.utags[x].second) return true;
+    }
+    if (!uManaged && ad[acc].managed != "true") return true;
+    if (!uOwner && !eqParts3(ad[acc].owner, resource, '/', ob.ns, '/', ob.name)) return true;
+    if (!uThost && ad[acc].thost != lbDns) return true;
+    return false;
+  }
+  bool endpointContainsLB(uint32_t eg, uint32_t lb) const {
+    sv arn = S.as(S.a->lb_arn[lb]);
+    for (uint32_t d = S.a->eg_ep_begin[eg]; d < S.a->eg_ep_begin[eg + 1]; d++)
+      if (S.as(S.a->ep_id[d]) == arn) return true;
+    return false;
+  }
+  // updateGlobalAcceleratorFor{Service,Ingress} (:290-410); egState as in Engine::updateAccelerator
+  int updateAccelerator(std::vector<gar_op> &ops, const ObjV &ob, uint32_t j, uint32_t acc, uint32_t lb, const std::vector<int32_t> &dports, int dproto, int *egState,
+                        Scratch &sc) const {
+    const gar_actual *a = S.a;
+    sv resource = resourceOf(ob.kind);
+    *egState = 0;
+    auto H = [&](int op) { return GAR_OP_HEAD(op, GAR_CTRL_GA, ob.kind); };
+    if (acceleratorChanged(acc, S.as(a->lb_dns[lb]), resource, ob, sc)) ops.push_back({H(GAR_OP_GA_UPDATE_ACCEL), ob.row, j, acc, lb, GAR_NONE});
+    uint32_t lbeg = a->acc_lis_begin[acc], lend = a->acc_lis_begin[acc + 1];
+    if (lend - lbeg > 1) return GAR_D_TOO_MANY_LISTENERS;
+    if (lend == lbeg) {
+      ops.push_back({H(GAR_OP_GA_CREATE_LISTENER), ob.row, j, acc, GAR_NONE, GAR_NONE});
+      ops.push_back({H(GAR_OP_GA_CREATE_EG), ob.row, j, acc, GAR_NONE, lb});
+      *egState = 3;
+      return 0;
+    }
+    uint32_t lis = lbeg;
+    bool protoChanged = ob.kind == GAR_KIND_SERVICE ? (a->lis_proto[lis] != dproto) : (a->lis_proto[lis] != GAR_PROTO_TCP);
+    uint32_t pb = a->lis_pr_begin[lis], pe = a->lis_pr_begin[lis + 1];
+    bool portChanged = listenerPortChanged(a->pr_from + pb, pe - pb, dports.data(), dports.size());
+    if (protoChanged || portChanged) ops.push_back({H(GAR_OP_GA_UPDATE_LISTENER), ob.row, j, acc, lis, GAR_NONE});
+    uint32_t eb = a->lis_eg_begin[lis], ee = a->lis_eg_begin[lis + 1];
+    if (ee - eb > 1) return GAR_D_TOO_MANY_EGS;
+    if (ee == eb) {
+      ops.push_back({H(GAR_OP_GA_CREATE_EG), ob.row, j, acc, lis, lb});
+      *egState = 3;
+      return 0;
+    }
+    if (!endpointContainsLB(eb, lb)) {
+      ops.push_back({H(GAR_OP_GA_UPDATE_EG), ob.row, j, acc, eb, lb});
+      *egState = 1;
+    }
+    return 0;
+  }
+  void emitDeleteChain(std::vector<gar_op> &ops, uint32_t objRow, int kind, uint32_t acc) const {
+    uint32_t lb = S.a->acc_lis_begin[acc], le = S.a->acc_lis_begin[acc + 1];
+    uint32_t lis = GAR_NONE, eg = GAR_NONE;
+    if (le - lb == 1) {
+      lis = lb;
+      uint32_t eb = S.a->lis_eg_begin[lis], ee = S.a->lis_eg_begin[lis + 1];
+      if (ee - eb == 1) eg = eb;
+    }
+    ops.push_back({GAR_OP_HEAD(GAR_OP_GA_DELETE_CHAIN, GAR_CTRL_GA, objRow == GAR_NONE ? 0 : kind), objRow, 0, acc, lis, eg});
+  }
+  // process{Service,Ingress}CreateOrUpdate of the globalaccelerator controller, with the self-observation rules of Engine::gaReconcile
+  uint32_t gaReconcile(std::vector<gar_op> &ops, const ObjV &ob, bool eligible, const std::vector<int32_t> &dports, int dproto, Scratch &sc) const {
+    const gar_objects *o = S.o;
+    if (!eligible) return GAR_STATUS(GAR_ST_IGNORED, 0, 0);
+    uint32_t jb = o->obj_lbi_begin[ob.row], je = o->obj_lbi_begin[ob.row + 1];
+    if (je - jb < 1) return GAR_STATUS(GAR_ST_SKIP_NO_LB, 0, 0);
+    sv resource = resourceOf(ob.kind);
+    listByResource(resource, ob.ns, ob.name, &sc.accs);
+    if (!ob.has(kAnnManaged)) {
+      for (uint32_t acc : sc.accs) emitDeleteChain(ops, ob.row, ob.kind, acc);
+      return GAR_STATUS(GAR_ST_OK, 0, GAR_EV_DELETED);
+    }
+    uint32_t ev = 0;
+    const std::vector<uint32_t> &accs = sc.accs;
+    sc.egState.assign(accs.size(), 0);
+    int64_t prevLb = -1;
+    bool pending = false, keepVisible = true, userThost = false;
+    auto H = [&](int op) { return GAR_OP_HEAD(op, GAR_CTRL_GA, ob.kind); };
+    for (uint32_t j = 0; j < je - jb; j++) {
+      sv hostname = S.os(o->lbi_hostname[jb + j]);
+      int prov = detectCloudProvider(hostname);
+      if (prov == DCP_PANIC) return GAR_STATUS(GAR_ST_PANIC, 0, ev);
+      if (prov == DCP_ERR) continue;
+      Tok t = getLBNameFromHostname(hostname);
+      if (t.code >= GAR_TOK_ERR_NOT_ELB) return GAR_STATUS(GAR_ST_ERR_RETRY, GAR_D_NOT_ELB + (t.code - GAR_TOK_ERR_NOT_ELB), ev);
+      int64_t lb = getLoadBalancer(t.region, t.name);
+      if (lb < 0) return GAR_STATUS(GAR_ST_ERR_RETRY, GAR_D_LB_NOT_FOUND, ev);
+      if (S.as(S.a->lb_dns[lb]) != hostname) return GAR_STATUS(GAR_ST_ERR_RETRY, GAR_D_LB_DNS_MISMATCH, ev);
+      if (S.a->lb_state[lb] != GAR_LB_ACTIVE) return GAR_STATUS(GAR_ST_REQUEUE_30S, 0, ev);
+      if (prevLb < 0) {
+        if (je - jb > 1) {  // only later iterations read these
+          userTags(ob, &sc.utags);
+          sv lm, lo_, lc;
+          bool hm = false, ho = false, hc = false;
+          for (auto &u : sc.utags) {
+            if (u.first == kTagManaged) lm = u.second, hm = true;
+            else if (u.first == kTagOwner) lo_ = u.second, ho = true;
+            else if (u.first == kTagCluster) lc = u.second, hc = true;
+            else if (u.first == kTagTargetHostname) userThost = true;
+          }
+          keepVisible = !(hm && lm != "true") && !(ho && !eqParts3(lo_, resource, '/', ob.ns, '/', ob.name)) && !(hc && lc != sv(S.cluster));
+        }
+        if (accs.empty()) {
+          ops.push_back({H(GAR_OP_GA_CREATE_CHAIN), ob.row, j, (uint32_t)lb, GAR_NONE, GAR_NONE});
+          ev |= GAR_EV_CREATED;
+          pending = true;
+        } else {
+          for (size_t x = 0; x < accs.size(); x++) {
+            int err = updateAccelerator(ops, ob, j, accs[x], (uint32_t)lb, dports, dproto, &sc.egState[x], sc);
+            if (err) return GAR_STATUS(GAR_ST_ERR_RETRY, err, ev);
+          }
+        }
+      } else if (!keepVisible) {
+        ops.push_back({H(GAR_OP_GA_CREATE_CHAIN), ob.row, j, (uint32_t)lb, GAR_NONE, GAR_NONE});
+        ev |= GAR_EV_CREATED;
+      } else {
+        bool dnsDiffers = !userThost && S.as(S.a->lb_dns[lb]) != S.as(S.a->lb_dns[prevLb]);
+        bool arnDiffers = S.as(S.a->lb_arn[lb]) != S.as(S.a->lb_arn[prevLb]);
+        if (pending) {
+          if (dnsDiffers) ops.push_back({H(GAR_OP_GA_UPDATE_ACCEL), ob.row, j, GAR_PENDING, (uint32_t)lb, GAR_NONE});
+          if (arnDiffers) ops.push_back({H(GAR_OP_GA_UPDATE_EG), ob.row, j, GAR_PENDING, GAR_PENDING, (uint32_t)lb});
+        }
+        for (size_t x = 0; x < accs.size(); x++) {
+          uint32_t acc = accs[x];
+          if (dnsDiffers) ops.push_back({H(GAR_OP_GA_UPDATE_ACCEL), ob.row, j, acc, (uint32_t)lb, GAR_NONE});
+          uint32_t eg = GAR_PENDING;
+          if (!(sc.egState[x] & 2)) eg = S.a->lis_eg_begin[S.a->acc_lis_begin[acc]];
+          bool contains = (sc.egState[x] & 1) ? !arnDiffers : endpointContainsLB(eg, (uint32_t)lb);
+          if (!contains) {
+            ops.push_back({H(GAR_OP_GA_UPDATE_EG), ob.row, j, acc, eg, (uint32_t)lb});
+            sc.egState[x] |= 1;
+          }
+        }
+      }
+      prevLb = lb;
+    }
+    return GAR_STATUS(GAR_ST_OK, 0, ev);
+  }
+
+  // ---- route53
+  int64_t getHostedZone(sv original) const {  // GetHostedZone (route53.go:335-358)
+    sv target = original;
+    for (;;) {
+      if (target.empty()) return -1;
+      KeyBuf k;
+      k.add(target);
+      k.add('.');
+      sv want = k.view();
+      int64_t found = -1;
+      ixZone.each(h64(want), [&](uint32_t z) {
+        if (S.as(S.a->zone_name[z]) == want) found = z;
+        return found < 0;
+      });
+      if (found >= 0) return found;
+      size_t dot = target.find('.');  // parentDomain (:383-386)
+      target = dot == sv::npos ? sv() : target.substr(dot + 1);
+    }
+  }
+  // the owner's value rows (ascending), fetched once per object
+  void ownerValues(sv ownerValue, std::vector<uint32_t> *out) const {
+    out->clear();
+    ixVal.each(h64(ownerValue), [&](uint32_t v) {
+      if (S.as(S.a->val_value[v]) == ownerValue) out->push_back(v);
+      return true;
+    });
+  }
+  // FindOwneredARecordSets (route53.go:216-238) for one zone
+  void findOwneredARecordSets(uint32_t z, const std::vector<uint32_t> &vals, Scratch &sc) const {
+    const gar_actual *a = S.a;
+    sc.names.clear();
+    sc.recs.clear();
+    for (uint32_t v : vals) {
+      if (recZone[valRec[v]] != z) continue;
+      sv n = S.as(a->rec_name[valRec[v]]);
+      bool seen = false;
+      for (auto &p : sc.names) seen |= (p.first == n);
+      if (!seen) sc.names.push_back({n, v});
+    }
+    for (auto &p : sc.names)
+      ixAlias.each(mix(h64(p.first) + z), [&](uint32_t r) {
+        if (recZone[r] == z && S.as(a->rec_name[r]) == p.first) sc.recs.push_back({r, p.second});
+        return true;
+      });
+    std::sort(sc.recs.begin(), sc.recs.end());
+  }
+  void cleanupRecordSet(std::vector<gar_op> &ops, uint32_t objRow, int kind, const std::vector<uint32_t> &vals, Scratch &sc) const {
+    uint32_t head = GAR_OP_HEAD(GAR_OP_R53_DELETE_RECORD, GAR_CTRL_R53, objRow == GAR_NONE ? 0 : kind);
+    uint32_t last = GAR_NONE;
+    for (uint32_t v : vals) {  // value rows are zone-major
+      uint32_t z = recZone[valRec[v]];
+      if (z == last) continue;
+      last = z;
+      findOwneredARecordSets(z, vals, sc);
+      for (auto &r : sc.recs) ops.push_back({head, objRow, 0, z, r.first, r.second});
+      for (uint32_t w : vals)
+        if (recZone[valRec[w]] == z) ops.push_back({head, objRow, 1, z, valRec[w], w});
+    }
+  }
+  uint32_t r53Reconcile(std::vector<gar_op> &ops, const ObjV &ob, bool eligible, Scratch &sc) const {
+    const gar_objects *o = S.o;
+    if (!eligible) return GAR_STATUS(GAR_ST_IGNORED, 0, 0);
+    sv resource = resourceOf(ob.kind);
+    KeyBuf ovb;
+    ovb.add("\"heritage=aws-global-accelerator-controller,cluster=");
+    ovb.add(S.cluster);
+    ovb.add(',');
+    ovb.add(resource);
+    ovb.add('/');
+    ovb.add(ob.ns);
+    ovb.add('/');
+    ovb.add(ob.name);
+    ovb.add('"');
+    ownerValues(ovb.view(), &sc.vals);
+    sv ann;
+    if (!ob.find(kAnnR53Host, &ann)) {
+      cleanupRecordSet(ops, ob.row, ob.kind, sc.vals, sc);
+      return GAR_STATUS(GAR_ST_OK, 0, GAR_EV_DELETED);
+    }
+    sc.hostnames.clear();
+    {
+      size_t start = 0;
+      for (size_t i = 0; i <= ann.size(); i++)
+        if (i == ann.size() || ann[i] == ',') {
+          sc.hostnames.push_back(ann.substr(start, i - start));
+          start = i + 1;
+        }
+    }
+    uint32_t jb = o->obj_lbi_begin[ob.row], je = o->obj_lbi_begin[ob.row + 1];
+    uint32_t ev = 0;
+    bool havePrev = false;
+    sv prevAccDns;
+    for (uint32_t j = 0; j < je - jb; j++) {
+      sv lbHostname = S.os(o->lbi_hostname[jb + j]);
+      int prov = detectCloudProvider(lbHostname);
+      if (prov == DCP_PANIC) return GAR_STATUS(GAR_ST_PANIC, 0, ev);
+      if (prov == DCP_ERR) continue;
+      Tok t = getLBNameFromHostname(lbHostname);
+      if (t.code >= GAR_TOK_ERR_NOT_ELB) return GAR_STATUS(GAR_ST_ERR_RETRY, GAR_D_NOT_ELB + (t.code - GAR_TOK_ERR_NOT_ELB), ev);
+      uint32_t nacc = 0, acc = 0;  // ListGlobalAcceleratorByHostname (:62-85)
+      ixThost.each(h64(lbHostname), [&](uint32_t i) {
+        if (ad[i].thost == lbHostname && nacc++ == 0) acc = i;
+        return nacc < 2;
+      });
+      if (nacc > 1) return GAR_STATUS(GAR_ST_REQUEUE_60S, GAR_D_ACCEL_MANY, ev);
+      if (nacc == 0) return GAR_STATUS(GAR_ST_REQUEUE_60S, GAR_D_ACCEL_NONE, ev);
+      sv accDns = S.as(S.a->acc_dns[acc]);
+      bool created = false;
+      for (uint32_t k = 0; k < sc.hostnames.size(); k++) {
+        sv hostname = sc.hostnames[k];
+        int64_t z = getHostedZone(hostname);
+        if (z < 0) return GAR_STATUS(GAR_ST_ERR_RETRY, GAR_D_NO_HOSTED_ZONE, ev);
+        bool seen = false;
+        for (uint32_t k2 = 0; k2 < k; k2++) seen |= sc.hostnames[k2] == hostname;
+        if (seen) continue;
+        findOwneredARecordSets((uint32_t)z, sc.vals, sc);
+        int64_t rec = -1;  // findARecord (:360-367)
+        for (auto &r : sc.recs)
+          if (S.a->rec_type[r.first] == GAR_RR_A && nameMatches(S.as(S.a->rec_name[r.first]), hostname)) {
+            rec = r.first;
+            break;
+          }
+        if (!havePrev) {
+          if (rec < 0) {
+            ops.push_back({GAR_OP_HEAD(GAR_OP_R53_CREATE, GAR_CTRL_R53, ob.kind), ob.row, GAR_R53_SUB(j, k), (uint32_t)z, acc, GAR_NONE});
+            created = true;
+          } else if (!S.a->rec_has_alias[rec] || !eqPlusDot(S.as(S.a->rec_alias_dns[rec]), accDns)) {  // needRecordsUpdate (:373-381)
+            ops.push_back({GAR_OP_HEAD(GAR_OP_R53_UPSERT_A, GAR_CTRL_R53, ob.kind), ob.row, GAR_R53_SUB(j, k), (uint32_t)z, acc, (uint32_t)rec});
+          }
+        } else if (accDns != prevAccDns) {
+          ops.push_back({GAR_OP_HEAD(GAR_OP_R53_UPSERT_A, GAR_CTRL_R53, ob.kind), ob.row, GAR_R53_SUB(j, k), (uint32_t)z, acc, rec < 0 ? GAR_PENDING : (uint32_t)rec});
+        }
+      }
+      if (created) ev |= GAR_EV_CREATED;
+      havePrev = true;
+      prevAccDns = accDns;
+    }
+    return GAR_STATUS(GAR_ST_OK, 0, ev);
+  }
+};
+
+}  // namespace tuned
+
+// R53 orphan section of ONE zone (shared by every mode): phase 0 alias sets x orphan owner values, phase 1 owner metadata sets
+template <class IsOrphan>
+void orphanZoneOps(const Snap &S, const std::vector<uint32_t> &valRec, uint32_t z, const IsOrphan &isOrphan, std::vector<gar_op> &out) {
+  const gar_actual *a = S.a;
+  const uint32_t head = GAR_OP_HEAD(GAR_OP_R53_DELETE_RECORD, GAR_CTRL_R53, 0);
+  uint32_t rb = a->zone_rec_begin[z], re = a->zone_rec_begin[z + 1];
+  // orphan value rows of this zone, ascending, grouped by record name
+  std::vector<uint32_t> ov;
+  std::unordered_map<sv, std::vector<uint32_t>> byName;
+  for (uint32_t r = rb; r < re; r++)
+    for (uint32_t v = a->rec_val_begin[r]; v < a->rec_val_begin[r + 1]; v++)
+      if (isOrphan(S.as(a->val_value[v]))) {
+        ov.push_back(v);
+        byName[S.as(a->rec_name[r])].push_back(v);
+      }
+  // phase 0: alias set r x orphan owner value (represented by its first value row under that name)
+  if (!ov.empty())
+    for (uint32_t r = rb; r < re; r++) {
+      if (!a->rec_has_alias[r]) continue;
+      auto it = byName.find(S.as(a->rec_name[r]));
+      if (it == byName.end()) continue;
+      std::vector<sv> seen;
+      for (uint32_t v : it->second) {
+        sv val = S.as(a->val_value[v]);
+        if (std::find(seen.begin(), seen.end(), val) != seen.end()) continue;
+        seen.push_back(val);
+        out.push_back({head, GAR_NONE, 0, z, r, v});
+      }
+    }
+  // phase 1: owner metadata sets
+  for (uint32_t v : ov) out.push_back({head, GAR_NONE, 1, z, valRec[v], v});
+}
+
+namespace tuned {
+
+int diff(const gar_objects *o, const gar_actual *a, const char *cluster, int threads, Result *R) {
+  Pool pool(threads);
+  Fast E(o, a, cluster, pool);
+  const uint32_t n = o->n_objects;
+  const int T = pool.T;
+  // tokeniser results per lbIngress row
+  pool.ranges(o->n_lbi, [&](uint64_t lo, uint64_t hi, int) {
+    for (uint64_t i = lo; i < hi; i++) {
+      sv h = E.S.os(o->lbi_hostname[i]);
+      Tok t = tokenise(h);
+      R->tokCode[i] = (uint8_t)t.code;
+      if (t.code <= GAR_TOK_NLB) {
+        uint64_t base = GAR_STR_OFF(o->lbi_hostname[i]);
+        R->tokName[i] = GAR_STR(base + (uint64_t)(t.name.data() - h.data()), t.name.size());
+        R->tokRegion[i] = GAR_STR(base + (uint64_t)(t.region.data() - h.data()), t.region.size());
+      }
+    }
+  });
+  std::vector<std::vector<gar_op>> gaOps(T), r53Ops(T), gaOrph(T);
+  std::vector<std::vector<int32_t>> dps(T);
+  pool.ranges(n, [&](uint64_t lo, uint64_t hi, int t) {
+    Scratch sc;
+    std::vector<int32_t> ports;
+    gaOps[t].reserve((hi - lo) / 2 + 16);
+    r53Ops[t].reserve((hi - lo) / 2 + 16);
+    for (uint64_t i = lo; i < hi; i++) {
+      ObjV ob = E.object((uint32_t)i);
+      uint32_t dv = 0;
+      int proto;
+      bool fromAnn;
+      E.desiredListener(ob, &ports, &proto, &fromAnn);
+      if (proto == GAR_PROTO_UDP) dv |= GAR_DV_PROTO_UDP;
+      if (ob.get(kAnnIPPreserve) == "true") dv |= GAR_DV_IP_PRESERVE;
+      sv ipt = ob.get(kAnnIPType);
+      if (ipt == "ipv4" || ipt == "IPV4") dv |= GAR_DV_IPV4;
+      if (fromAnn) {
+        dv |= GAR_DV_PORTS_FROM_ANN;
+        R->dportBegin[i + 1] = (uint32_t)ports.size();
+        dps[t].insert(dps[t].end(), ports.begin(), ports.end());
+      }
+      bool lbsvc = ob.kind == GAR_KIND_SERVICE && E.wasLoadBalancerService(ob);
+      bool gaEl = ob.kind == GAR_KIND_SERVICE ? lbsvc : E.wasALBIngress(ob);
+      bool r53El = ob.kind == GAR_KIND_SERVICE ? lbsvc : true;
+      if (gaEl) dv |= GAR_DV_GA_ELIGIBLE;
+      if (ob.has(kAnnManaged)) dv |= GAR_DV_GA_MANAGED;
+      if (r53El) dv |= GAR_DV_R53_ELIGIBLE;
+      if (ob.has(kAnnR53Host)) dv |= GAR_DV_R53_ANNOTATED;
+      R->derived[i] = dv;
+      R->stGa[i] = E.gaReconcile(gaOps[t], ob, gaEl, ports, proto, sc);
+      R->stR53[i] = E.r53Reconcile(r53Ops[t], ob, r53El, sc);
+    }
+  });
+  for (uint32_t i = 0; i < n; i++) R->dportBegin[i + 1] += R->dportBegin[i];
+  for (auto &v : dps) R->dports.insert(R->dports.end(), v.begin(), v.end());
+  // section 1: GA orphans
+  pool.ranges(a->n_accels, [&](uint64_t lo, uint64_t hi, int t) {
+    for (uint64_t acc = lo; acc < hi; acc++) {
+      if (!E.ad[acc].mine) continue;
+      ObjKey k;
+      if (!parseOwner(E.ad[acc].owner, &k)) continue;
+      if (E.inCache(k.kind, k.ns, k.name)) continue;
+      E.emitDeleteChain(gaOrph[t], GAR_NONE, 0, (uint32_t)acc);
+    }
+  });
+  // section 3: R53 orphans, zone by zone
+  std::vector<std::vector<gar_op>> zoneOps(a->n_zones);
+  {
+    std::string prefix = "\"heritage=aws-global-accelerator-controller,cluster=" + E.S.cluster + ",";
+    auto isOrphan = [&](sv value) {
+      if (!hasPrefix(value, prefix) || value.size() < prefix.size() + 1 || value.back() != '"') return false;
+      ObjKey k;
+      if (!parseOwner(value.substr(prefix.size(), value.size() - prefix.size() - 1), &k)) return false;
+      return !E.inCache(k.kind, k.ns, k.name);
+    };
+    std::atomic<uint32_t> next{0};
+    pool.run([&](int) {
+      for (uint32_t z; (z = next.fetch_add(1)) < a->n_zones;) orphanZoneOps(E.S, E.valRec, z, isOrphan, zoneOps[z]);
+    });
+  }
+  // assemble: [GA objects | GA orphans | R53 objects | R53 orphans], every part copied in parallel
+  std::vector<const std::vector<gar_op> *> parts;
+  for (auto &v : gaOps) parts.push_back(&v);
+  size_t sec1 = parts.size();
+  for (auto &v : gaOrph) parts.push_back(&v);
+  size_t sec2 = parts.size();
+  for (auto &v : r53Ops) parts.push_back(&v);
+  size_t sec3 = parts.size();
+  for (auto &v : zoneOps) parts.push_back(&v);
+  std::vector<uint64_t> off(parts.size() + 1, 0);
+  for (size_t p = 0; p < parts.size(); p++) off[p + 1] = off[p] + parts[p]->size();
+  R->ops.resize(off.back());
+  pool.ranges(parts.size(), [&](uint64_t lo, uint64_t hi, int) {
+    for (uint64_t p = lo; p < hi; p++)
+      if (!parts[p]->empty()) memcpy(R->ops.data() + off[p], parts[p]->data(), sizeof(gar_op) * parts[p]->size());
+  });
+  R->cs.section_begin[0] = 0;
+  R->cs.section_begin[1] = off[sec1];
+  R->cs.section_begin[2] = off[sec2];
+  R->cs.section_begin[3] = off[sec3];
+  R->cs.section_begin[4] = off.back();
+  return 0;
+}
+
+}  // namespace tuned
+
 }  // namespace
 
 // ==================================================================== exported C interface
@@ -1315,8 +2174,26 @@ bool parseOwner(sv owner, ObjKey *k) {
 extern "C" {
 
 // Full batch diff.  mode: 0 faithful, 1 indexed.  threads only used in mode 1.
+static void publish(Result *R, const gar_objects *o, gar_changeset **out) {
+  gar_changeset &cs = R->cs;
+  cs.n_objects = o->n_objects;
+  cs.status_ga = R->stGa.data();
+  cs.status_r53 = R->stR53.data();
+  cs.derived = R->derived.data();
+  cs.n_ops = R->ops.size();
+  cs.ops = R->ops.data();
+  cs.n_lbi = o->n_lbi;
+  cs.tok_code = R->tokCode.data();
+  cs.tok_name = R->tokName.data();
+  cs.tok_region = R->tokRegion.data();
+  cs.dport_begin = R->dportBegin.data();
+  cs.n_dports = R->dports.size();
+  cs.dports = R->dports.data();
+  cs.opaque = R;
+  *out = &R->cs;
+}
+
 int orc_diff(const gar_objects *o, const gar_actual *a, const char *cluster, int mode, int threads, gar_changeset **out) {
-  Engine E(o, a, cluster, mode);
   auto *R = new Result();
   uint32_t n = o->n_objects;
   R->stGa.assign(n, 0);
@@ -1326,6 +2203,12 @@ int orc_diff(const gar_objects *o, const gar_actual *a, const char *cluster, int
   R->tokCode.resize(o->n_lbi);
   R->tokName.assign(o->n_lbi, 0);
   R->tokRegion.assign(o->n_lbi, 0);
+  if (mode == 2) {
+    tuned::diff(o, a, cluster, threads, R);
+    publish(R, o, out);
+    return 0;
+  }
+  Engine E(o, a, cluster, mode);
 
   if (threads < 1 || mode == 0) threads = 1;
   // cache membership for orphan detection (built while the objects are being evaluated)

@@ -11,7 +11,9 @@ n = int(sys.argv[2]) if len(sys.argv) > 2 else 1_000_000
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 pkg = importlib.import_module("aws-global-accelerator-controller_b200")
 synth = importlib.import_module("aws-global-accelerator-controller_b200.synth")
-snap = synth.generate(cfg, n)
+c = synth.preset(cfg, n)
+c.layout = 1  # column-major slabs: the bench default
+snap = synth.SynthSnapshot(c)
 with pkg.Engine(cluster_name=snap.cluster, reprepare=True) as e:
     e.load(snap)
     for _ in range(reps):

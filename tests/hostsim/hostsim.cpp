@@ -125,6 +125,10 @@ struct gar_engine {
     }
   }
   template <class F>
+  void for_each_staged(const char *name, u32 n, const F &f) {
+    for_each(name, n, f);  // no shared memory on the host: the functor's direct form
+  }
+  template <class F>
   void for_each_dyn(const char *name, const u32 *n_dev, u32 cap, const F &f) {
     for_each(name, *n_dev < cap ? *n_dev : cap, f);
   }

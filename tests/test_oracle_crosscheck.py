@@ -26,6 +26,9 @@ def test_oracle_modes_and_pyref_agree(garecon, oracle, seed):
     mt = oracle.diff(snap, "default", mode=1, threads=3)
     assert faithful.diff(indexed) == [], faithful.describe_first_mismatch(indexed)
     assert faithful.diff(mt) == [], faithful.describe_first_mismatch(mt)
+    for threads in (1, 5):  # mode 2: the tuned host-core baseline of bench.py decides exactly what the literal modes decide
+        tuned = oracle.diff(snap, "default", mode=2, threads=threads)
+        assert faithful.diff(tuned) == [], faithful.describe_first_mismatch(tuned)
 
     import copy
     res = pyref.diff(copy.deepcopy(objects), copy.deepcopy(actual), "default")
@@ -60,3 +63,25 @@ def test_random_models_cover_the_op_space(garecon, oracle):
     assert ops == set(range(1, 11))
     assert sts >= {0, 1, 2, 3, 4, 5, 7}
     assert dets >= set(range(0, 12)) - {2}  # every detail code except the rare internal-ALB parse error is hit
+
+
+@pytest.mark.parametrize("seed", range(30))
+def test_tuned_baseline_equals_the_literal_port_on_multi_lbingress_models(garecon, oracle, seed):
+    import multilbi
+    snap = garecon.pack(*multilbi.make(seed))
+    want = oracle.diff(snap, "default", mode=0)
+    got = oracle.diff(snap, "default", mode=2, threads=1 + seed % 4)
+    assert got.diff(want) == [], got.describe_first_mismatch(want)
+
+
+def test_tuned_baseline_on_hot_keys_and_odd_clusters(garecon, oracle):
+    import hotkeys
+    snap = garecon.pack(*hotkeys.make())
+    assert oracle.diff(snap, "default", mode=2, threads=4).diff(oracle.diff(snap, "default", mode=1)) == []
+    objects, actual = randmodel.make(3, n_objects=40, cluster="prod-1")
+    snap = garecon.pack(objects, actual)
+    assert oracle.diff(snap, "prod-1", mode=2, threads=2).diff(oracle.diff(snap, "prod-1", mode=0)) == []
+    empty = garecon.pack([], {})
+    assert oracle.diff(empty, "default", mode=2, threads=3).diff(oracle.diff(empty, "default", mode=0)) == []
+    only_actual = garecon.pack([], actual)
+    assert oracle.diff(only_actual, "prod-1", mode=2, threads=3).diff(oracle.diff(only_actual, "prod-1", mode=0)) == []

@@ -24,6 +24,21 @@ def test_faithful_equals_indexed_on_baseline_configs(oracle, cfg, n):
     mt = oracle.diff(s, "default", mode=1, threads=4)
     assert faithful.diff(indexed) == [], faithful.describe_first_mismatch(indexed)
     assert faithful.diff(mt) == []
+    tuned = oracle.diff(s, "default", mode=2, threads=4)
+    assert faithful.diff(tuned) == [], faithful.describe_first_mismatch(tuned)
+
+
+@pytest.mark.parametrize("cfg,n,layout", [(2, 60000, 0), (3, 60000, 1), (4, 60000, 1), (5, 60000, 0)])
+def test_tuned_baseline_equals_indexed_at_size(oracle, cfg, n, layout):
+    """The tuned CPU baseline (bench.py cpu_baseline, --impl reference) against the literal indexed port on every BASELINE
+    distribution, both slab layouts, several thread counts."""
+    c = synth.preset(cfg, n)
+    c.layout = layout
+    s = synth.SynthSnapshot(c)
+    want = oracle.diff(s, "default", mode=1, threads=4)
+    for threads in (1, 7):
+        got = oracle.diff(s, "default", mode=2, threads=threads)
+        assert got.diff(want) == [], got.describe_first_mismatch(want)
 
 
 def test_cfg1_is_the_reference_fixture_shape(oracle):
