@@ -530,6 +530,8 @@ struct gar_engine {
   void *dev_ensure(DBuf &b, size_t bytes) {
     bytes = (bytes + 255) & ~(size_t)255;
     if (b.cap < bytes) {
+      if (capturing) throw CudaError{"internal: a buffer grew while a launch sequence was being recorded"};
+      graph_drop();  // recorded launches hold the old pointer
       if (b.p) CK(cudaFree(b.p));
       b.p = nullptr;
       b.cap = 0;
@@ -568,6 +570,54 @@ struct gar_engine {
     k_for_each_warp<F, MinBlocks<F>::value><<<(n + 255) / 256, 256, 0, stream>>>(f, n);
     launches++;
     stage_end();
+  }
+  // ---- launch-sequence caching.  A full diff of an unchanged snapshot issues exactly the same launches with the same arguments
+  // every time (all sizes that only the device knows live in capacity-sized buffers): the second such diff is recorded into
+  // a CUDA graph, later ones replay it — one graph launch instead of ~35 kernel launches and memsets (what a 10^5-object diff
+  // is bound by).  Anything that changes the sequence (new snapshot, a capacity that grew, stage timing) drops the graph.
+  bool use_graphs = true;  // environment GAR_NO_GRAPH=1 turns it off
+  cudaGraphExec_t graph_exec = nullptr;
+  u64 graph_sig = 0, seen_sig = 0;
+  u32 graph_launches = 0, capture_launch0 = 0;
+  bool capturing = false;
+  void graph_drop() {
+    if (graph_exec) cudaGraphExecDestroy(graph_exec);
+    graph_exec = nullptr;
+    graph_sig = seen_sig = 0;
+  }
+  int graph_begin(u64 sig) {
+    if (!use_graphs || timing) return 0;
+    if (graph_exec && graph_sig == sig) {
+      CK(cudaGraphLaunch(graph_exec, stream));
+      launches += graph_launches;
+      return 2;
+    }
+    if (seen_sig != sig) {  // first diff with this shape: run it eagerly (buffers get their sizes), remember the shape
+      graph_drop();
+      seen_sig = sig;
+      return 0;
+    }
+    graph_drop();
+    seen_sig = sig;
+    CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+    capturing = true;
+    capture_launch0 = launches;
+    return 1;
+  }
+  void graph_end() {
+    if (!capturing) return;
+    capturing = false;
+    cudaGraph_t g = nullptr;
+    CK(cudaStreamEndCapture(stream, &g));
+    cudaError_t ie = cudaGraphInstantiate(&graph_exec, g, 0);
+    cudaGraphDestroy(g);
+    if (ie != cudaSuccess) {
+      graph_exec = nullptr;
+      throw CudaError{std::string("cudaGraphInstantiate failed: ") + cudaGetErrorString(ie)};
+    }
+    graph_sig = seen_sig;
+    graph_launches = launches - capture_launch0;
+    CK(cudaGraphLaunch(graph_exec, stream));
   }
   bool staged_passes = true;  // environment GAR_NO_TMA=1: the direct-load form of the staged row passes (A/B measurements)
   template <class F>
@@ -812,6 +862,7 @@ static const Tp *upload(gar_engine *e, const Tp *host, size_t count, size_t pad_
 static void do_load(gar_engine *e, const gar_objects *o, const gar_actual *a) {
   if (!o || !a) throw InvalidError{"NULL table struct"};
   e->loaded = false;
+  e->graph_drop();
   delete e->pipe;  // the prepared state belongs to the previous snapshot
   e->pipe = nullptr;
   validate_pointers(o, a);  // NULL checks before anything is copied; the contents are checked on the device, below
@@ -891,6 +942,7 @@ static void do_diff(gar_engine *e, gar_changeset *out, bool to_host, const gar_k
   e->stage_depth = 0;
   if (e->shard_home && (ks || bd)) throw InvalidError{"incremental / binding diffs are not available on a sharded sub-snapshot"};
   if (!e->pipe) {
+    e->graph_drop();  // recorded launches belong to the previous pipeline's buffers and tables
     e->pipe = new Pipeline<gar_engine>(*e, e->T);
     if (const char *tc = getenv("GAR_TINY_CAPS")) e->pipe->tiny_caps = tc[0] == '1';
     if (e->shard_home) {
@@ -1063,6 +1115,13 @@ static int guarded(gar_engine *e, Fn fn) {
     return GAR_OK;
   } catch (const CudaError &ce) {
     e->err = ce.msg;
+    if (e->capturing) {  // abandon a half-recorded launch sequence
+      cudaGraph_t g = nullptr;
+      cudaStreamEndCapture(e->stream, &g);
+      if (g) cudaGraphDestroy(g);
+      e->capturing = false;
+    }
+    e->graph_drop();
     cudaGetLastError();
     return GAR_E_CUDA;
   } catch (const InvalidError &ie) {
@@ -1104,6 +1163,7 @@ int gar_engine_create(const gar_config *cfg, gar_engine **out) {
   e->timing = (cfg->flags & GAR_FLAG_STAGE_TIMING) != 0;
   e->reprepare = (cfg->flags & GAR_FLAG_REPREPARE) != 0;
   if (const char *nt = getenv("GAR_NO_TMA")) e->staged_passes = nt[0] != '1';
+  if (const char *ng = getenv("GAR_NO_GRAPH")) e->use_graphs = ng[0] != '1';
   e->no_orphans = (cfg->flags & GAR_FLAG_NO_ORPHANS) != 0;
   e->allow_empty_cache = (cfg->flags & GAR_FLAG_ALLOW_EMPTY_CACHE) != 0;
   try {
@@ -1127,6 +1187,7 @@ void gar_engine_destroy(gar_engine *e) {
   if (!e) return;
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
+  e->graph_drop();
   for (auto &b : e->in) cudaFree(b.p);
   for (auto &b : e->slot) cudaFree(b.p);
   delete e->pipe;
@@ -1165,6 +1226,7 @@ int gar_snapshot_load(gar_engine *e, const gar_objects *desired, const gar_actua
 int gar_snapshot_attach_device(gar_engine *e, const gar_objects *desired, const gar_actual *actual) {
   return guarded(e, [&] {
     if (!desired || !actual) throw InvalidError{"NULL table struct"};
+    e->graph_drop();
     delete e->pipe;
     e->pipe = nullptr;
     e->T.o = *desired;

@@ -17,6 +17,8 @@
 //   template <class F> void for_each_dyn(const char *name, const u32 *n_dev, u32 cap, const F &f);       // f(i) for i < min(*n_dev, cap); the count
 //   template <class F> void for_each_warp_dyn(const char *name, const u32 *n_dev, u32 cap, const F &f);  //   lives on the device: no read-back
 //   void download(void *host_dst, const void *dev_src, size_t bytes);       // blocking
+//   int graph_begin(u64 signature);  void graph_end();                      // launch-sequence caching (CUDA graphs): 0 = run the
+//                                                                           // launches, 1 = run them while they are recorded, 2 = replayed
 //   void download_start(int id, const void *dev_src, size_t bytes);         // id 0..1: small read-back in flight while later
 //   void download_wait(int id, void *host_dst, size_t bytes);               //   stages are queued; wait blocks only if needed
 #pragma once
@@ -435,31 +437,44 @@ struct FIdxGather {  // radix fallback: position p of the stable sorted order ho
 template <class RowF>
 struct FIdxPlaceDirect {
   RowF rowf;
-  const u32 *begin;  // this index's slice of the scanned bucket array (values are positions in the shared entry array)
-  u32 *fill;         // this index's slice of the zeroed fill counters
-  IdxEntry *ent;     // shared entry array of the group
-  u32 mask, bucket_base;
-  u32 *multi;        // [0] = count, then global bucket ids
+  u32 *cursor;    // this index's slice of the cursor array (a copy of the scanned bucket array): one atomic yields the position
+  IdxEntry *ent;  // shared entry array of the group
+  u32 mask;
   GAR_HD void operator()(u32 i) const {
     u64 h = 0;
     IdxEntry e;
     if (!rowf.make(i, &h, &e)) return;
     const u32 k = hash_bucket(h, mask);
 #if defined(__CUDA_ARCH__)
-    const u32 old = atomicAdd(&fill[k], 1u);
+    const u32 pos = atomicAdd(&cursor[k], 1u);
 #else
-    const u32 old = fill[k]++;
+    const u32 pos = cursor[k]++;
 #endif
     e.tag = hash_tag(h);
     e.row = i;
-    ent[begin[k] + old] = e;
-    if (old == 1) {
+    ent[pos] = e;
+  }
+};
+// buckets with two or more entries, compacted into a list (one pass over the scanned bucket array; the appends are aggregated
+// per warp, so the shared counter sees one atomic per warp, not one per bucket)
+struct FIdxMultiList {
+  const u32 *begin;
+  u32 *multi;  // [0] = count, then bucket ids
+  GAR_HD void operator()(u32 b) const {
+    const bool m = begin[b + 1] - begin[b] >= 2;
 #if defined(__CUDA_ARCH__)
-      multi[1 + atomicAdd(multi, 1u)] = bucket_base + k;
+    const unsigned active = __activemask();
+    const unsigned votes = __ballot_sync(active, m);
+    if (!m) return;
+    const unsigned lane = threadIdx.x & 31u;
+    const int leader = __ffs(votes) - 1;
+    u32 base = 0;
+    if ((int)lane == leader) base = atomicAdd(multi, (u32)__popc(votes));
+    base = __shfl_sync(votes, base, leader);
+    multi[1 + base + __popc(votes & ((1u << lane) - 1u))] = b;
 #else
-      multi[1 + multi[0]++] = bucket_base + k;
+    if (m) multi[1 + multi[0]++] = b;
 #endif
-    }
   }
 };
 struct FIdxOrderMulti {
@@ -924,23 +939,23 @@ struct Pipeline {
   HashIdx group_a_index(int k) const { return HashIdx{ixa_begin + planA.off[k], ixa_ent, planA.nb[k] - 1}; }
   template <class RowF>
   FIdxPlaceDirect<RowF> placer(int k, RowF rowf) const {
-    return FIdxPlaceDirect<RowF>{rowf, ixa_begin + planA.off[k], ixa_fill + planA.off[k], ixa_ent, planA.nb[k] - 1, planA.off[k], ixa_multi};
+    return FIdxPlaceDirect<RowF>{rowf, ixa_fill + planA.off[k], ixa_ent, planA.nb[k] - 1};
   }
   // scan + place + order of group A (after every armed row pass has run)
   void finish_group_a() {
     u32 *overflow = errflag + FW_IDX_OVERFLOW;
     be.exclusive_scan(ixa_begin, planA.total_nb + 1);  // positions in the shared entry array; [total_nb] = number of entries
-    ixa_fill = (u32 *)be.ensure(S_IXA_FILL, 4 * (size_t)(planA.total_nb + 1));
+    ixa_fill = (u32 *)be.ensure(S_IXA_FILL, 4 * (size_t)(planA.total_nb + 1));  // the placement cursors
     ixa_ent = (IdxEntry *)be.ensure(S_IXA_ENT, sizeof(IdxEntry) * (size_t)(planA.total_rows + 1));
     const u32 multi_cap = (u32)(planA.total_rows / 2 + 1);
     ixa_multi = (u32 *)be.ensure(S_IXA_MULTI, 4 * (size_t)(multi_cap + 2));
-    be.fill32(ixa_fill, 0, (size_t)planA.total_nb + 1);
+    be.copy32(ixa_fill, ixa_begin, (size_t)planA.total_nb + 1);
     be.fill32(ixa_multi, 0, 1);
     const IxPlan &P = planA;
     auto n = [&](int k) { return P.want[k] ? P.rows[k] : 0u; };
-    be.for_each_multi("idx_place", {n(IX_LB), n(IX_OWNER), n(IX_THOST), n(IX_ZONE), n(IX_VAL), n(IX_ALIAS), n(IX_OBJ)}, placer(IX_LB, FRowLb{T, W}),
-                      placer(IX_OWNER, FRowOwner{T, W}), placer(IX_THOST, FRowThost{T, W}), placer(IX_ZONE, FRowZone{T}), placer(IX_VAL, FRowVal{T, W}),
-                      placer(IX_ALIAS, FRowAlias{T, W}), placer(IX_OBJ, FRowObj{T, W}));
+    be.for_each_multi("idx_place", {n(IX_LB), n(IX_OWNER), n(IX_THOST), n(IX_ZONE), n(IX_VAL), n(IX_ALIAS), n(IX_OBJ), P.total_nb},
+                      placer(IX_LB, FRowLb{T, W}), placer(IX_OWNER, FRowOwner{T, W}), placer(IX_THOST, FRowThost{T, W}), placer(IX_ZONE, FRowZone{T}),
+                      placer(IX_VAL, FRowVal{T, W}), placer(IX_ALIAS, FRowAlias{T, W}), placer(IX_OBJ, FRowObj{T, W}), FIdxMultiList{ixa_begin, ixa_multi});
     be.for_each_dyn("idx_order", ixa_multi, multi_cap, FIdxOrderMulti{ixa_begin, ixa_ent, ixa_multi, overflow});
     if (P.want[IX_LB]) W.ix_lb = group_a_index(IX_LB);
     if (P.want[IX_OWNER]) W.ix_owner = group_a_index(IX_OWNER);
@@ -961,12 +976,12 @@ struct Pipeline {
     const u32 nval = T.a.n_values;
     u32 *begin = W.hist[IX_OVN].cnt;
     be.exclusive_scan(begin, ovn_nb + 1);
-    u32 *fill = (u32 *)be.ensure(S_OVN_FILL, 4 * (size_t)(ovn_nb + 1));
+    u32 *cursor = (u32 *)be.ensure(S_OVN_FILL, 4 * (size_t)(ovn_nb + 1));
     IdxEntry *ent = (IdxEntry *)be.ensure(S_IX_OVN + 1, sizeof(IdxEntry) * (size_t)(nval + 1));
     u32 *multi = (u32 *)be.ensure(S_OVN_MULTI, 4 * (size_t)(nval / 2 + 3));
-    be.fill32(fill, 0, (size_t)ovn_nb + 1);
+    be.copy32(cursor, begin, (size_t)ovn_nb + 1);
     be.fill32(multi, 0, 1);
-    if (nval) be.for_each("idx_place", nval, FIdxPlaceDirect<FRowOvn>{FRowOvn{T, W}, begin, fill, ent, ovn_nb - 1, 0, multi});
+    be.for_each_multi("idx_place", {nval, ovn_nb}, FIdxPlaceDirect<FRowOvn>{FRowOvn{T, W}, cursor, ent, ovn_nb - 1}, FIdxMultiList{begin, multi});
     be.for_each_dyn("idx_order", multi, nval / 2 + 1, FIdxOrderMulti{begin, ent, multi, errflag + FW_IDX_OVERFLOW});
     W.ix_ovn = HashIdx{begin, ent, ovn_nb - 1};
   }
@@ -1148,15 +1163,24 @@ struct Pipeline {
   // section sizes and everything that may force another attempt — a hash bucket too large for the per-bucket ordering
   // (-> stable radix build), or an intermediate relation larger than its buffer (-> larger buffer).  Retries are rare:
   // capacities only grow, so a snapshot shape settles after its first diff.
+  // `replayable`: the launch sequence of this flavour depends only on the snapshot and the capacities, so the backend may record
+  // it once and replay it (a CUDA graph): the full diff.  Incremental / binding diffs take new host inputs every time.
   template <class DecideF>
   int run_with(DiffCounts *dc, bool full, DecideF decide) {
     for (int attempt = 0; attempt < 8; attempt++) {
-      if (!prepared) {
-        int rc = prepare();
-        if (rc != GAR_OK) return rc;
-        prepared = true;
+      u64 sig = 0;
+      if (full) {
+        sig = hmix(hmix(prepared ? 1 : 2, force_radix ? 3 : 4), hmix(hmix(dport_cap, pair_cap), ops_cap));
+        sig = hmix(sig, hmix(orphan_sweep ? 5 : 6, tiny_caps ? 7 : 8)) | 1;
       }
-      int rc = decide();
+      const int g = full ? be.graph_begin(sig) : 0;
+      int rc = GAR_OK;
+      if (g != 2) {
+        if (!prepared) rc = prepare();
+        if (rc == GAR_OK) rc = decide();
+      }
+      prepared = true;
+      if (full) be.graph_end();
       if (rc != GAR_OK) return rc;
       u32 fl[FW_WORDS];
       be.download(fl, errflag, sizeof(fl));

@@ -1513,14 +1513,23 @@ GAR_HD void r53_fill_pairs(const DevTables &T, const Work &W, u32 i, u32 t) {
   if (W.r53_mode[i] != R53_MODE_PAIRS) return;
   gar_str ref = W.ann_r53[i];
   Str hostnames = mkstr(T.o.slab, ref);
-  u32 p = W.pair_begin[t], pos = 0;
+  u32 p = W.pair_begin[t], pos = 0, np = 0;
+  u32 st[8], ln[8];  // the first pieces, for the repeat check (annotations with more hostnames fall back to a re-scan)
   Str piece;
   while (next_piece(hostnames, &pos, &piece)) {
     if (p >= W.pair_cap) break;  // more pairs than the arrays hold: the diff is re-run with larger ones
     W.pair_obj[p] = i;
     W.pair_hn[p] = GAR_STR(GAR_STR_OFF(ref) + (u64)(piece.p - hostnames.p), piece.n);
     // self-observation (include/garecon.h): a repeated hostname needs no evaluation — the annotation bytes are in hand here
-    W.pair_code[p] = piece_seen_before(hostnames, piece) ? (u8)PAIR_REPEAT : (u8)PAIR_IN_SYNC;
+    bool repeat = false;
+    for (u32 q = 0; q < np && q < 8 && !repeat; q++) repeat = ln[q] == piece.n && streq(substr(hostnames, st[q], ln[q]), piece);
+    if (!repeat && np > 8) repeat = piece_seen_before(hostnames, piece);
+    W.pair_code[p] = repeat ? (u8)PAIR_REPEAT : (u8)PAIR_IN_SYNC;
+    if (np < 8) {
+      st[np] = (u32)(piece.p - hostnames.p);
+      ln[np] = piece.n;
+    }
+    np++;
     p++;
   }
 }

@@ -145,6 +145,8 @@ struct gar_engine {
     };
     (one(*it++, fs), ...);
   }
+  int graph_begin(u64) { return 0; }
+  void graph_end() {}
   void fill32(u32 *p, u32 v, size_t n) { std::fill(p, p + n, v); }
   void copy32(u32 *d, const u32 *s, size_t n) { memcpy(d, s, n * 4); }
   void exclusive_scan(u32 *d, u32 n) {

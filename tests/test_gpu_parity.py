@@ -175,3 +175,20 @@ def test_capacity_overflow_paths(garecon, oracle, monkeypatch):
         want = oracle.diff(snap, "default", mode=1)
         assert got.diff(want) == [], got.describe_first_mismatch(want)
         assert again.diff(want) == []
+
+
+def test_recorded_launch_sequences_replay_the_same_diff(garecon, oracle):
+    """The full diff of an unchanged snapshot is recorded into a CUDA graph on its second run and replayed afterwards (engine:
+    graph_begin / graph_end).  Replays must reproduce the result; a new snapshot, and the first diff after it, must not see a
+    stale recording — with and without GAR_FLAG_REPREPARE."""
+    for reprepare in (False, True):
+        with garecon.Engine(cluster_name="default", reprepare=reprepare) as e:
+            for seed in (31, 32, 31):
+                objects, actual = randmodel.make(seed, n_objects=150)
+                snap = garecon.pack(objects, actual)
+                want = oracle.diff(snap, "default", mode=1)
+                e.load(snap)
+                for k in range(6):  # eager, eager (prepared), recorded, replayed ...
+                    got = e.diff()
+                    assert got.diff(want) == [], (reprepare, seed, k, got.describe_first_mismatch(want))
+                    assert got.kernel_launches > 0
