@@ -619,11 +619,13 @@ struct gar_engine {
     graph_launches = launches - capture_launch0;
     CK(cudaGraphLaunch(graph_exec, stream));
   }
-  bool staged_passes = true;  // environment GAR_NO_TMA=1: the direct-load form of the staged row passes (A/B measurements)
+  // environment GAR_NO_TMA=1: every staged row pass in its direct-load form; GAR_TMA_ALL=1: every one staged (A/B measurements).
+  // Default: each pass in the form that measured faster on the B200 (F::kStageByDefault).
+  bool staged_passes = true, staged_all = false;
   template <class F>
   void for_each_staged(const char *name, u32 n, const F &f) {
     if (!n) return;
-    if (!staged_passes) return for_each(name, n, f);
+    if (!staged_passes || !(F::kStageByDefault || staged_all)) return for_each(name, n, f);
     stage_begin(name);
     k_for_each_staged<F><<<(n + 255) / 256, 256, 0, stream>>>(f, n);
     launches++;
@@ -1163,6 +1165,7 @@ int gar_engine_create(const gar_config *cfg, gar_engine **out) {
   e->timing = (cfg->flags & GAR_FLAG_STAGE_TIMING) != 0;
   e->reprepare = (cfg->flags & GAR_FLAG_REPREPARE) != 0;
   if (const char *nt = getenv("GAR_NO_TMA")) e->staged_passes = nt[0] != '1';
+  if (const char *ta = getenv("GAR_TMA_ALL")) e->staged_all = ta[0] == '1';
   if (const char *ng = getenv("GAR_NO_GRAPH")) e->use_graphs = ng[0] != '1';
   e->no_orphans = (cfg->flags & GAR_FLAG_NO_ORPHANS) != 0;
   e->allow_empty_cache = (cfg->flags & GAR_FLAG_ALLOW_EMPTY_CACHE) != 0;

@@ -79,6 +79,7 @@ struct FTokenise {
   Work W;
   static constexpr int kStageCols = 1;
   static constexpr u32 kStageBytes = 24 * 1024;  // 256 lbIngress hostnames of ~70 bytes
+  static constexpr bool kStageByDefault = true;
   GAR_HD void operator()(u32 i) const { tokenise_hostname(T, W, i); }
   GAR_HD const u8 *stage_slab(int) const { return T.o.slab; }
   GAR_HD bool stage_window(int, u32 r0, u32 r1, u64 *lo, u64 *hi) const {
@@ -126,6 +127,7 @@ struct FPrepareRecord {
   u32 *big, *huge;  // [0] = count, then record rows
   static constexpr int kStageCols = 2;  // window 0: record names, window 1: the records' values
   static constexpr u32 kStageBytes = 16 * 1024;  // 256 names of ~28 bytes; ~130 values of ~95 bytes
+  static constexpr bool kStageByDefault = false;  // measured on the B200 (profiles/r02_tma_ab.json): 0.297 ms staged vs 0.265 ms direct
   GAR_HD const u8 *stage_slab(int) const { return T.a.slab; }
   GAR_HD bool stage_window(int c, u32 r0, u32 r1, u64 *lo, u64 *hi) const {
     if (c == 0) {
