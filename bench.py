@@ -164,12 +164,12 @@ def kernel_byte_models(o, a, n_ops_ga_obj: int, n_pairs: int, frac_ga: float):
     models["prepare_records"] = int(name_bytes + nrec * (8 + 4) + val_bytes + 8 * nval + nrec * (4 + 8) + nval * (4 + 1 + 8 + 8))
     n_owner_vals = nval  # generator: every TXT value is an owner value (orphans and foreign clusters included)
     models["value_joins"] = int(n_owner_vals * ((1 + 8 + 8 + 4) + (8 + 32 + 2 * name_bytes_per_rec) + (8 + 32 + 2 * key_bytes / max(n, 1)) + 16 + 1))
-    # index build: per indexed row one 32-byte entry written (+ 32-byte temporary written and read, counted as scratch: not here),
-    # the row's key hash / refs read (~24 B), 4 B per bucket
-    idx_rows_total = a.n_lbs + 2 * a.n_accels + a.n_zones + 2 * nval + nrec + n
-    models["idx_rows"] = int(idx_rows_total * (24 + 4))
-    models["idx_place"] = int(idx_rows_total * (4 + 32))
-    models["idx_order"] = int(idx_rows_total * 4)
+    # index build (one pass over every index): per row its key hash and payload columns read once (~28 B), one 32-byte entry written,
+    # one 4-byte cursor touched, + the scanned bucket array read once for the multi-entry list
+    idx_rows_total = a.n_lbs + 2 * a.n_accels + a.n_zones + nval + nrec + n
+    models["idx_place"] = int(idx_rows_total * (28 + 32 + 4) + 4 * idx_rows_total)
+    models["idx_order"] = int(idx_rows_total * 0.25 * (4 + 2.5 * 32 * 2))  # ~a quarter of the buckets hold 2-3 entries: read + written back
+    models["hash_load_balancers"] = int(L(a.lb_region, a.n_lbs) + L(a.lb_name, a.n_lbs) + a.n_lbs * (16 + 8 + 4))
     n_annotated = int((ak == 63).sum())
     models["r53_prepare"] = int(n * (4 + 8 + 1) + host_bytes + n_annotated * (32 + 8 + acc_dns_per) + ann_r53 + n * (1 + 4 + 8 + 4))
     models["r53_objects"] = int(n * (1 + 4 + 4 + 4) + n_pairs * (1 + 4 + 4) + n * 8)
