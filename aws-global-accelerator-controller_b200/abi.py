@@ -113,7 +113,7 @@ ST_REQUEUE_1S = 8
 D_REF_NOT_FOUND, D_EG_NOT_FOUND = 12, 13
 
 
-SHARD_MAX_RANKS, SHARD_META_WORDS = 8, 40
+SHARD_MAX_RANKS, SHARD_META_WORDS, SHARD_HANDLE_BYTES = 8, 40, 96
 
 
 class GarShard(C.Structure):
@@ -263,6 +263,12 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
     lib.gar_shard_unpack.restype = C.c_int
     lib.gar_shard_blob_bytes.argtypes = [_u64p]
     lib.gar_shard_blob_bytes.restype = C.c_uint64
+    lib.gar_shard_arena.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.POINTER(C.c_void_p), _u8p, _u64p]
+    lib.gar_shard_arena.restype = C.c_int
+    lib.gar_shard_open_peers.argtypes = [C.c_void_p, C.c_int, _u8p]
+    lib.gar_shard_open_peers.restype = C.c_int
+    lib.gar_shard_pack_peers.argtypes = [C.c_void_p, C.c_int, _u64p]
+    lib.gar_shard_pack_peers.restype = C.c_int
     lib.gar_changeset_free.argtypes = [C.c_void_p, C.POINTER(GarChangeset)]
     lib.gar_changeset_free.restype = None
     lib.gar_last_error.argtypes = [C.c_void_p]
@@ -283,6 +289,7 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
 EXPORTED_SYMBOLS = (
     "gar_engine_create", "gar_engine_destroy", "gar_snapshot_load", "gar_snapshot_attach_device", "gar_diff",
     "gar_diff_device", "gar_diff_keys", "gar_bindings_diff", "gar_shard_route", "gar_shard_pack", "gar_shard_unpack", "gar_shard_blob_bytes",
+    "gar_shard_arena", "gar_shard_open_peers", "gar_shard_pack_peers",
     "gar_changeset_free", "gar_last_error", "gar_version", "gar_algorithmic_bytes",
     "gar_last_stage_timings", "gar_last_counters",
 )
@@ -368,6 +375,23 @@ class Engine:
     def shard_unpack(self, rnd: int, recv_ptr: int, recv_meta: np.ndarray) -> None:
         m = np.ascontiguousarray(recv_meta, dtype=np.uint64)
         self._check(self.lib.gar_shard_unpack(self._h, rnd, C.c_void_p(recv_ptr), m.ctypes.data_as(_u64p)))
+
+    # peer-memory exchange (include/garecon.h): pack kernels store straight into the other ranks' receive arenas
+    def shard_arena(self, rnd: int, need_bytes: int):
+        """-> (arena device pointer, handle bytes [SHARD_HANDLE_BYTES] uint8) of this rank's receive arena of round `rnd`."""
+        ptr = C.c_void_p()
+        cap = C.c_uint64()
+        handle = np.zeros(SHARD_HANDLE_BYTES, dtype=np.uint8)
+        self._check(self.lib.gar_shard_arena(self._h, rnd, int(need_bytes), C.byref(ptr), handle.ctypes.data_as(_u8p), C.byref(cap)))
+        return int(ptr.value), handle
+
+    def shard_open_peers(self, rnd: int, handles: np.ndarray) -> None:
+        h = np.ascontiguousarray(handles, dtype=np.uint8)
+        self._check(self.lib.gar_shard_open_peers(self._h, rnd, h.ctypes.data_as(_u8p)))
+
+    def shard_pack_peers(self, rnd: int, all_meta: np.ndarray) -> None:
+        m = np.ascontiguousarray(all_meta, dtype=np.uint64)
+        self._check(self.lib.gar_shard_pack_peers(self._h, rnd, m.ctypes.data_as(_u64p)))
 
     def blob_bytes(self, meta_row: np.ndarray) -> int:
         m = np.ascontiguousarray(meta_row, dtype=np.uint64)

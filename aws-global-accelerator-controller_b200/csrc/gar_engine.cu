@@ -7,6 +7,7 @@
 // There is deliberately no CPU path in this library: every entry point needs a live sm_100 device.
 
 #include <cuda_runtime.h>
+#include <unistd.h>
 
 #include <cstdio>
 #include <cstdlib>
@@ -484,6 +485,25 @@ struct gar_engine {
   void shard_reset(int a) { arena_used[a] = 0; }
   void copy_bytes(void *dst, const void *src, size_t n) {
     if (n) CK(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToDevice, stream));
+  }
+  // peer-memory exchange: this rank's receive arenas (one per round) and the mapped arenas of the other ranks
+  struct PeerHandle {  // what travels in GAR_SHARD_HANDLE_BYTES
+    u64 magic, pid, ptr, cap;
+    cudaIpcMemHandle_t ipc;
+  };
+  static_assert(sizeof(PeerHandle) <= GAR_SHARD_HANDLE_BYTES, "handle does not fit");
+  DBuf peer_arena[2];
+  u8 *peer_ptr[2][GAR_SHARD_MAX_RANKS] = {};
+  PeerHandle peer_seen[2][GAR_SHARD_MAX_RANKS] = {};
+  bool peer_mapped[2][GAR_SHARD_MAX_RANKS] = {};
+  void peers_close() {
+    for (int r = 0; r < 2; r++)
+      for (int k = 0; k < GAR_SHARD_MAX_RANKS; k++) {
+        if (peer_mapped[r][k]) cudaIpcCloseMemHandle(peer_ptr[r][k]);
+        peer_mapped[r][k] = false;
+        peer_ptr[r][k] = nullptr;
+        peer_seen[r][k] = PeerHandle{};
+      }
   }
   std::vector<HostResult *> free_results;
   float ms_h2d = 0;
@@ -1195,6 +1215,8 @@ void gar_engine_destroy(gar_engine *e) {
   for (auto &b : e->slot) cudaFree(b.p);
   delete e->pipe;
   delete e->sharder;
+  e->peers_close();
+  for (auto &b : e->peer_arena) cudaFree(b.p);
   for (auto &ar : e->arena)
     for (auto &b : ar) cudaFree(b.p);
   for (DBuf *b : {&e->d_derived_keys, &e->d_key_rows, &e->d_del_kind, &e->d_del_key, &e->d_del_slab}) cudaFree(b->p);
@@ -1333,6 +1355,84 @@ int gar_shard_unpack(gar_engine *e, int round, const void *recv, const uint64_t 
 }
 
 uint64_t gar_shard_blob_bytes(const uint64_t *meta_row) { return meta_row ? blob_bytes(meta_row) : 0; }
+
+int gar_shard_arena(gar_engine *e, int round, uint64_t need_bytes, void **arena, uint8_t *handle, uint64_t *capacity) {
+  if (!arena || !handle || (round != 1 && round != 2)) return GAR_E_INVALID;
+  return guarded(e, [&] {
+    CK(cudaSetDevice(e->device));
+    DBuf &b = e->peer_arena[round - 1];
+    if (b.cap < need_bytes + 64) {
+      CK(cudaStreamSynchronize(e->stream));  // nobody may still be reading the old arena (the caller's barrier covers the peers)
+      if (b.p) CK(cudaFree(b.p));
+      b.p = nullptr;
+      b.cap = 0;
+      size_t want = (size_t)(need_bytes + need_bytes / 4 + 4096);
+      CK(cudaMalloc(&b.p, want));  // plain cudaMalloc: the only kind of allocation CUDA IPC can export
+      b.cap = want;
+    }
+    gar_engine::PeerHandle h{};
+    h.magic = 0x6761725F70656572ull;  // "gar_peer"
+    h.pid = (u64)getpid();
+    h.ptr = (u64)(uintptr_t)b.p;
+    h.cap = b.cap;
+    CK(cudaIpcGetMemHandle(&h.ipc, b.p));
+    memset(handle, 0, GAR_SHARD_HANDLE_BYTES);
+    memcpy(handle, &h, sizeof(h));
+    *arena = b.p;
+    if (capacity) *capacity = b.cap;
+  });
+}
+
+int gar_shard_open_peers(gar_engine *e, int round, const uint8_t *handles) {
+  if (!handles || (round != 1 && round != 2)) return GAR_E_INVALID;
+  return guarded(e, [&] {
+    if (!e->sharder || e->shard_round == 0) throw InvalidError{"gar_shard_open_peers before gar_shard_route"};
+    CK(cudaSetDevice(e->device));
+    const u32 G = e->sharder->G, me = e->sharder->cfg.rank;
+    const int r = round - 1;
+    for (u32 k = 0; k < G; k++) {
+      gar_engine::PeerHandle h;
+      memcpy(&h, handles + (size_t)k * GAR_SHARD_HANDLE_BYTES, sizeof(h));
+      if (h.magic != 0x6761725F70656572ull) throw InvalidError{"bad peer handle"};
+      if (k == me || h.pid == (u64)getpid()) {  // this process's own memory (several engines in one process: tests): no IPC needed
+        e->peer_ptr[r][k] = (u8 *)(uintptr_t)h.ptr;
+        continue;
+      }
+      if (e->peer_mapped[r][k] && !memcmp(&e->peer_seen[r][k], &h, sizeof(h))) continue;  // still the mapping we have
+      if (e->peer_mapped[r][k]) {
+        CK(cudaIpcCloseMemHandle(e->peer_ptr[r][k]));
+        e->peer_mapped[r][k] = false;
+      }
+      void *p = nullptr;
+      CK(cudaIpcOpenMemHandle(&p, h.ipc, cudaIpcMemLazyEnablePeerAccess));
+      e->peer_ptr[r][k] = (u8 *)p;
+      e->peer_mapped[r][k] = true;
+      e->peer_seen[r][k] = h;
+    }
+  });
+}
+
+int gar_shard_pack_peers(gar_engine *e, int round, const uint64_t *all_meta) {
+  if (!all_meta || (round != 1 && round != 2)) return GAR_E_INVALID;
+  return guarded(e, [&] {
+    if (e->shard_round != 1 && e->shard_round != 3) throw InvalidError{"gar_shard_pack_peers without a routed plan"};
+    CK(cudaSetDevice(e->device));
+    const u32 G = e->sharder->G, me = e->sharder->cfg.rank;
+    const int r = round - 1;
+    u8 *bases[GAR_SHARD_MAX_RANKS] = {};
+    for (u32 d = 0; d < G; d++) {
+      if (!e->peer_ptr[r][d]) throw InvalidError{"gar_shard_pack_peers: a peer arena is not mapped (gar_shard_open_peers)"};
+      u64 off = 0;
+      for (u32 s = 0; s < me; s++) off += blob_bytes(all_meta + ((size_t)s * G + d) * GAR_SHARD_META_WORDS);
+      bases[d] = e->peer_ptr[r][d] + off;
+    }
+    u32 l0 = e->launches;
+    e->sharder->pack_to(bases);
+    e->shard_launches += e->launches - l0;
+    CK(cudaStreamSynchronize(e->stream));  // the stores are performed: after the ranks' barrier every arena is complete
+    CK(cudaGetLastError());
+  });
+}
 
 void gar_changeset_free(gar_engine *e, gar_changeset *cs) {
   if (!e || !cs) return;

@@ -804,7 +804,7 @@ struct Sharder {
   // ---- pack the current plan into `send` (n_ranks blobs back to back, sizes as reported by the route call)
   void pack(u8 *send) {
     u64 blob_base[SH_MAX_RANKS + 1] = {0};
-    u64 lvl_off[SH_MAX_RANKS] = {0};
+    u8 *bases[SH_MAX_RANKS] = {};
     for (u32 d = 0; d < G; d++) {
       u64 row[GAR_SHARD_META_WORDS] = {0};
       for (int l = 0; l < L_NLEVELS; l++) {
@@ -812,12 +812,20 @@ struct Sharder {
         row[L_NLEVELS + l] = h_slab_off[l][d + 1] - h_slab_off[l][d];
       }
       blob_base[d + 1] = blob_base[d] + blob_bytes(row);
+      bases[d] = send + blob_base[d];
     }
+    pack_to(bases);
+  }
+  // The pack kernels with one destination address per rank: bases[d] = where this rank's blob for rank d starts.  With peer
+  // memory mapped (gar_shard_pack_peers) these are addresses inside the OTHER GPUs' receive arenas: the rows travel over NVLink
+  // as the pack kernels store them — partitioning and transfer are one step, no staging buffer, no separate collective.
+  void pack_to(u8 *const bases[SH_MAX_RANKS]) {
+    u64 lvl_off[SH_MAX_RANKS] = {0};
     for (int l = 0; l < L_NLEVELS; l++) {
       PackDst D{};
       for (u32 d = 0; d < G; d++) {
         u64 n = h_row_off[l][d + 1] - h_row_off[l][d], sb = h_slab_off[l][d + 1] - h_slab_off[l][d];
-        D.base[d] = send + blob_base[d];
+        D.base[d] = bases[d];
         D.lay[d] = level_layout(l, lvl_off[d], n, sb);
         lvl_off[d] = D.lay[d].end;
       }

@@ -77,6 +77,28 @@ def exchange_local(engines, shards, keep, device="cpu"):
             e.shard_unpack(rnd, recv.data_ptr(), recv_meta)
 
 
+def exchange_local_peers(engines, shards):
+    """Both rounds over peer memory for engines that all live in this process (hostsim: host arenas; several engines on one
+    GPU: device arenas, no IPC needed): every engine's pack stores straight into the other engines' receive arenas."""
+    g = len(engines)
+    for rnd in (1, 2):
+        metas = [e.shard_route(sh, rnd)[0] for e, sh in zip(engines, shards)]
+        all_meta = np.stack(metas)  # [source][destination][words]
+        arenas, handles = [], []
+        for d, e in enumerate(engines):
+            need = sum(e.blob_bytes(all_meta[s][d]) for s in range(g))
+            ptr, h = e.shard_arena(rnd, need)
+            arenas.append(ptr)
+            handles.append(h)
+        handles = np.stack(handles)
+        for e in engines:
+            e.shard_open_peers(rnd, handles)
+        for e in engines:
+            e.shard_pack_peers(rnd, all_meta)
+        for d, e in enumerate(engines):
+            e.shard_unpack(rnd, arenas[d], np.ascontiguousarray(all_meta[:, d]))
+
+
 class DistExchange:
     """torch.distributed data path of one rank.  Buffers are torch uint8 tensors on `device` (cuda:N or cpu)."""
 
@@ -89,6 +111,20 @@ class DistExchange:
         self.keep = []
         self.bytes_sent = 0
         self.check_errors = True  # one tiny all-reduce after the calls that can fail on one rank only (route, unpack)
+        self.timing = False       # True: every phase is bracketed by device synchronisations and accumulated in phase_ms
+        self.phase_ms = {}
+
+    def _timed(self, name, fn):
+        if not self.timing:
+            return fn()
+        import time
+        sync = self.torch.cuda.synchronize if str(self.device) != "cpu" else (lambda: None)
+        sync()
+        t0 = time.perf_counter()
+        out = fn()
+        sync()
+        self.phase_ms[name] = self.phase_ms.get(name, 0.0) + (time.perf_counter() - t0) * 1e3
+        return out
 
     def _agree(self, err):
         """All ranks learn whether any rank failed its last engine call (otherwise the healthy ones would wait forever in the
@@ -115,25 +151,26 @@ class DistExchange:
 
     def round(self, rnd: int):
         torch, dist = self.torch, self.dist
-        meta, nbytes = self._guard(lambda: self.e.shard_route(self.shard, rnd))
+        meta, nbytes = self._timed(f"route{rnd}", lambda: self._guard(lambda: self.e.shard_route(self.shard, rnd)))
         # meta rows: a fixed-size all-to-all (int64 view of the uint64 words)
         m_out = torch.from_numpy(meta.view(np.int64)).to(self.device)
         m_in = torch.empty_like(m_out)
-        dist.all_to_all_single(m_in, m_out)
+        self._timed(f"meta{rnd}", lambda: dist.all_to_all_single(m_in, m_out))
         recv_meta = m_in.cpu().numpy().view(np.uint64)
         in_sizes = [int(x) for x in nbytes]
         out_sizes = [self.e.blob_bytes(recv_meta[s]) for s in range(self.g)]
         send = torch.empty(sum(in_sizes) + 64, dtype=torch.uint8, device=self.device)
         if str(self.device) != "cpu":
             torch.cuda.current_stream().synchronize()  # the allocation (and any fill) is on torch's stream, the engine packs on its own
-        self._guard(lambda: self.e.shard_pack(send.data_ptr()))  # a pack failure on one rank must not leave the others in the all-to-all
+        # a pack failure on one rank must not leave the others in the all-to-all
+        self._timed(f"pack{rnd}", lambda: self._guard(lambda: self.e.shard_pack(send.data_ptr())))
         recv = torch.empty(sum(out_sizes) + 64, dtype=torch.uint8, device=self.device)
-        dist.all_to_all_single(recv[:sum(out_sizes)], send[:sum(in_sizes)], output_split_sizes=out_sizes, input_split_sizes=in_sizes)
+        self._timed(f"transfer{rnd}", lambda: dist.all_to_all_single(recv[:sum(out_sizes)], send[:sum(in_sizes)], output_split_sizes=out_sizes, input_split_sizes=in_sizes))
         if str(self.device) != "cpu":
             torch.cuda.current_stream().synchronize()  # the engine reads `recv` on its own stream
         self.keep.append(recv)
         self.bytes_sent += sum(in_sizes)
-        self._guard(lambda: self.e.shard_unpack(rnd, recv.data_ptr(), recv_meta))
+        self._timed(f"unpack{rnd}", lambda: self._guard(lambda: self.e.shard_unpack(rnd, recv.data_ptr(), recv_meta)))
 
     def run(self):
         """Both rounds; afterwards the engine holds this rank's home sub-snapshot (diff() works)."""
@@ -240,3 +277,38 @@ def add_checksums(parts) -> dict:
         out["n_ops"] += p["n_ops"]
         out["sections"] = [a + b for a, b in zip(out["sections"], p["sections"])]
     return out
+
+
+class PeerExchange(DistExchange):
+    """One process per GPU on one NVLink node: the rows travel as the pack kernels store them into the other GPUs' receive
+    arenas (CUDA IPC mappings, include/garecon.h "Peer-memory exchange").  torch.distributed only moves the meta rows and the
+    arena handles (two tiny all-gathers per round) and provides the barrier after the packs."""
+
+    def round(self, rnd: int):
+        torch, dist = self.torch, self.dist
+        g = self.g
+        meta, nbytes = self._timed(f"route{rnd}", lambda: self._guard(lambda: self.e.shard_route(self.shard, rnd)))
+        m_out = torch.from_numpy(meta.view(np.int64)).to(self.device)
+        m_all = torch.empty((g,) + tuple(m_out.shape), dtype=m_out.dtype, device=self.device)
+        self._timed(f"meta{rnd}", lambda: dist.all_gather_into_tensor(m_all, m_out))
+        all_meta = m_all.cpu().numpy().view(np.uint64)  # [source][destination][words]
+        me = int(self.shard.rank)
+        need = sum(self.e.blob_bytes(all_meta[s][me]) for s in range(g))
+
+        def arenas():
+            arena, handle = self._guard(lambda: self.e.shard_arena(rnd, need))
+            h_out = torch.from_numpy(handle).to(self.device)
+            h_all = torch.empty((g, abi.SHARD_HANDLE_BYTES), dtype=torch.uint8, device=self.device)
+            dist.all_gather_into_tensor(h_all, h_out)  # also orders "arena (re)allocated" before anybody's stores
+            self._guard(lambda: self.e.shard_open_peers(rnd, h_all.cpu().numpy()))
+            return arena
+        arena = self._timed(f"meta{rnd}", arenas)
+        # pack == transfer: the stores land in the peers' arenas.  gar_shard_pack_peers returns after its stream has drained;
+        # _guard's all-reduce (or the barrier) then makes "every rank has packed" known to every rank
+        def pack():
+            self._guard(lambda: self.e.shard_pack_peers(rnd, all_meta))
+            if not self.check_errors:
+                dist.barrier()
+        self._timed(f"pack{rnd}", pack)
+        self.bytes_sent += int(sum(int(x) for k, x in enumerate(nbytes) if k != me))
+        self._timed(f"unpack{rnd}", lambda: self._guard(lambda: self.e.shard_unpack(rnd, arena, np.ascontiguousarray(all_meta[:, me]))))

@@ -311,7 +311,8 @@ def sharded_measure(args, R, rank, world, local_rank, n_total, cfg_id, steps, wa
     h2d_bytes = snap.input_bytes()
     _, pinned_addrs = _pin_host_tables(torch, pkg.abi, snap.objects, snap.actual)
     eng = pkg.Engine(cluster_name="default", device=local_rank)
-    ex = shard.DistExchange(eng, sh, dev)
+    Exchange = shard.PeerExchange if args.exchange == "p2p" else shard.DistExchange
+    ex = Exchange(eng, sh, dev)
     sampler = ClockSampler(local_rank)
     sampler.start()
 
@@ -357,38 +358,24 @@ def sharded_measure(args, R, rank, world, local_rank, n_total, cfg_id, steps, wa
     lo, hi = ck["sum"] & 0xFFFFFFFF, ck["sum"] >> 32
     allck = R.gather_counts([lo, hi, ck["n_objects"], ck["n_ops"]] + ck["sections"])
     # phase breakdown (separate pass, synchronised between phases; not part of the timed numbers above)
+    ex.timing, ex.phase_ms = True, {}
     phases = {}
-
-    def timed(name, fn):
+    for _ in range(3):
+        ex.run()
         torch.cuda.synchronize()
         ta = time.perf_counter()
-        out = fn()
+        eng.diff_device()
         torch.cuda.synchronize()
-        phases[name] = phases.get(name, 0.0) + (time.perf_counter() - ta) * 1e3 / 3
-        return out
-    for _ in range(3):
-        ex.keep.clear()
-        for rnd in (1, 2):
-            meta, nbytes = timed(f"route{rnd}", lambda: eng.shard_route(sh, rnd))
-            m_out = torch.from_numpy(meta.view("int64")).to(dev)
-            m_in = torch.empty_like(m_out)
-            timed(f"meta_a2a{rnd}", lambda: R.dist.all_to_all_single(m_in, m_out))
-            recv_meta = m_in.cpu().numpy().view("uint64")
-            ins = [int(x) for x in nbytes]
-            outs = [eng.blob_bytes(recv_meta[s]) for s in range(world)]
-            send = torch.empty(sum(ins) + 64, dtype=torch.uint8, device=dev)
-            timed(f"pack{rnd}", lambda: eng.shard_pack(send.data_ptr()))
-            recv = torch.empty(sum(outs) + 64, dtype=torch.uint8, device=dev)
-            timed(f"blob_a2a{rnd}", lambda: R.dist.all_to_all_single(recv[:sum(outs)], send[:sum(ins)], output_split_sizes=outs, input_split_sizes=ins))
-            ex.keep.append(recv)
-            timed(f"unpack{rnd}", lambda: eng.shard_unpack(rnd, recv.data_ptr(), recv_meta))
-        timed("diff", lambda: eng.diff_device())
+        phases["diff"] = phases.get("diff", 0.0) + (time.perf_counter() - ta) * 1e3 / 3
+    for k, v in ex.phase_ms.items():
+        phases[k] = v / 3
+    ex.timing = False
     eng.close()
     stage_acc = {}
     if detail:  # per-kernel CUDA-event times of one whole sharded step (engine with GAR_FLAG_STAGE_TIMING; separate pass)
         peng = pkg.Engine(cluster_name="default", device=local_rank, stage_timing=True)
         peng.load(snap)
-        pex = shard.DistExchange(peng, sh, dev)
+        pex = Exchange(peng, sh, dev)
         for it in range(4):
             pex.run()
             peng.diff_device()
@@ -451,19 +438,24 @@ def sharded_measure(args, R, rank, world, local_rank, n_total, cfg_id, steps, wa
     ph_max = {k: max(c[4 + i] for c in allc) / 1000 for i, k in enumerate(sorted(phases))}
     exch_ms = sum(v for k, v in ph_max.items() if k != "diff")
     sent_max = max(c[2] for c in allc)
+    # where the bytes cross NVLink: the all-to-all of the send-buffer path, the pack kernels themselves with peer memory
+    xfer = ["pack1", "pack2"] if args.exchange == "p2p" else ["transfer1", "transfer2"]
     rec = {
         "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": dt_dev / steps * 1e3, "scaling": "strong",
         "config": {"workload": f"BASELINE configs[3]: ONE cluster of {n_total} Service+Ingress (generator preset {cfg_id}, {n_chunks} chunks, {args.layout}-major slabs) "
                                f"cut into {world} slices (objects / accelerators / load balancers of different chunk groups on each rank), re-homed by key hash",
-                   "objects_total": n_total, "parallelism": f"key-hash shards x{world}: all-to-all of rows + answer exchange (NCCL), then local diff",
+                   "objects_total": n_total,
+                   "parallelism": f"key-hash shards x{world}: " + ("pack kernels store the rows straight into the peers' receive arenas over NVLink (CUDA IPC), " if args.exchange == "p2p"
+                                                                   else "pack -> NCCL all_to_all_single -> unpack, ") + "rows + answer round, then local diff",
+                   "exchange": args.exchange,
                    "cache": _cache_note(h2d_bytes), "homed_objects_per_rank": [c[0] for c in allc], "ops_per_rank": [c[1] for c in allc],
                    "algorithmic_bytes": b_alg, "generate_s": round(gen_s, 1)},
         "e2e": {"value": n_total * steps / dt_e2e, "unit": UNIT, "h2d_bytes_per_step": in_bytes,
                 "d2h_bytes_per_step": 12 * n_total + 24 * sum(c[1] for c in allc), "ms_per_step": dt_e2e / steps * 1e3},
         "gpu_launches": launches, "clocks": clocks,
         "bytes_sent": {"per_rank": [c[2] for c in allc], "max": sent_max,
-                       "nvlink_gbs_per_direction_in_blob_a2a": round(sent_max / max(ph_max.get("blob_a2a1", 0) + ph_max.get("blob_a2a2", 0), 1e-9) / 1e6, 1),
-                       "nvlink_peak_gbs_per_direction": 900.0},
+                       "nvlink_gbs_per_direction_in_transfer": round(sent_max / max(sum(ph_max.get(k, 0) for k in xfer), 1e-9) / 1e6, 1),
+                       "transfer_phases": xfer, "nvlink_peak_gbs_per_direction": 900.0, "nvlink_measured_peer_copy_gbs": 770.0},
         "roofline": {"bound": "hbm", "kernel": "whole sharded step (route, pack, exchange, merge, diff)", "achieved": achieved, "peak": peak * world,
                      "unit": "GB/s", "frac": achieved / (peak * world), "traffic": None, "peak_source": peak_src + f" x {world} GPUs"},
         "phases_ms_rank0": {k: round(v, 3) for k, v in phases.items()},
@@ -528,6 +520,9 @@ def main():
     ap.add_argument("--sharded-objects", type=int, default=10_000_000, help="size of the cluster of the `sharded` record")
     ap.add_argument("--sharded-steps", type=int, default=5)
     ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the sharded record")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="sharded mode data path: p2p = pack kernels store straight into the other GPUs' receive arenas (CUDA IPC peer memory); "
+                         "nccl = pack into a send buffer, torch.distributed all_to_all_single, unpack")
     ap.add_argument("--no-single", action="store_true", help="sharded: skip the single-GPU run of the same cluster (no checksum comparison)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "garecon" else args.warmup

@@ -465,6 +465,26 @@ int gar_shard_pack(gar_engine *e, void *send);
 int gar_shard_unpack(gar_engine *e, int round, const void *recv, const uint64_t *recv_meta);
 uint64_t gar_shard_blob_bytes(const uint64_t *meta_row);
 
+/* Peer-memory exchange (one process per GPU on one NVLink / NVSwitch node): instead of packing into a local send buffer that a
+   collective then copies, every rank's pack kernels store their rows straight into the RECEIVE arenas of the other GPUs, mapped
+   through CUDA IPC — partitioning by key hash and the transfer over NVLink are one step.  Per round:
+
+     gar_shard_route(e, &shard, round, meta, send_bytes)
+     all-gather the meta rows                                  -> all_meta[s][d] = row of source s for destination d
+     gar_shard_arena(e, round, need, &ptr, handle, &cap)       need = sum over s of gar_shard_blob_bytes(all_meta[s][rank]);
+                                                               (re)allocates this rank's arena of the round and exports it
+     all-gather the handles; gar_shard_open_peers(e, round, handles)     (mappings are cached: re-opened only when a handle changed)
+     gar_shard_pack_peers(e, round, all_meta)                  source s writes its blob for d at offset sum_{s' < s} blob bytes(s', d)
+     barrier over the ranks (every pack has completed)         gar_shard_pack_peers has synchronised its own stream before returning
+     gar_shard_unpack(e, round, ptr, column `rank` of all_meta)
+
+   Same result as the send-buffer + all-to-all path above (tests compare both with the unsharded diff).  The host still moves
+   the few hundred bytes of meta rows and handles (any all-gather); the bulk data never touches a collective library. */
+#define GAR_SHARD_HANDLE_BYTES 96
+int gar_shard_arena(gar_engine *e, int round, uint64_t need_bytes, void **arena, uint8_t *handle /* [GAR_SHARD_HANDLE_BYTES] */, uint64_t *capacity);
+int gar_shard_open_peers(gar_engine *e, int round, const uint8_t *handles /* [n_ranks][GAR_SHARD_HANDLE_BYTES], rank order */);
+int gar_shard_pack_peers(gar_engine *e, int round, const uint64_t *all_meta /* [n_ranks][n_ranks][GAR_SHARD_META_WORDS] */);
+
 void gar_changeset_free(gar_engine *e, gar_changeset *cs);
 
 const char *gar_last_error(const gar_engine *e); /* never NULL; valid until the next call on e */

@@ -87,6 +87,8 @@ struct gar_engine {
   DevTables slice{};
   bool shard_home = false;
   int shard_round = 0;
+  std::vector<uint64_t> peer_arena[2];
+  u8 *peer_ptr[2][GAR_SHARD_MAX_RANKS] = {};
   std::vector<HBuf> arena[3];
   size_t arena_used[3] = {0, 0, 0};
   void *shard_alloc(int a, size_t bytes) {
@@ -343,6 +345,36 @@ int gar_shard_unpack(gar_engine *e, int round, const void *recv, const uint64_t 
   return GAR_OK;
 }
 uint64_t gar_shard_blob_bytes(const uint64_t *meta_row) { return blob_bytes(meta_row); }
+// peer-memory exchange on the host build: every "rank" lives in this process, a handle is just the arena's address
+int gar_shard_arena(gar_engine *e, int round, uint64_t need_bytes, void **arena, uint8_t *handle, uint64_t *capacity) {
+  std::vector<uint64_t> &b = e->peer_arena[round - 1];
+  if (b.size() * 8 < need_bytes + 64) b.assign((need_bytes + need_bytes / 4 + 4096) / 8, 0);
+  uint64_t p = (uint64_t)(uintptr_t)b.data();
+  memset(handle, 0, GAR_SHARD_HANDLE_BYTES);
+  memcpy(handle, &p, 8);
+  *arena = b.data();
+  if (capacity) *capacity = b.size() * 8;
+  return GAR_OK;
+}
+int gar_shard_open_peers(gar_engine *e, int round, const uint8_t *handles) {
+  for (u32 k = 0; k < e->sharder->G; k++) {
+    uint64_t p;
+    memcpy(&p, handles + (size_t)k * GAR_SHARD_HANDLE_BYTES, 8);
+    e->peer_ptr[round - 1][k] = (u8 *)(uintptr_t)p;
+  }
+  return GAR_OK;
+}
+int gar_shard_pack_peers(gar_engine *e, int round, const uint64_t *all_meta) {
+  const u32 G = e->sharder->G, me = e->sharder->cfg.rank;
+  u8 *bases[GAR_SHARD_MAX_RANKS] = {};
+  for (u32 d = 0; d < G; d++) {
+    u64 off = 0;
+    for (u32 s = 0; s < me; s++) off += blob_bytes(all_meta + ((size_t)s * G + d) * GAR_SHARD_META_WORDS);
+    bases[d] = e->peer_ptr[round - 1][d] + off;
+  }
+  e->sharder->pack_to(bases);
+  return GAR_OK;
+}
 void gar_changeset_free(gar_engine *, gar_changeset *cs) { memset(cs, 0, sizeof(*cs)); }
 const char *gar_last_error(const gar_engine *e) { return e ? e->err.c_str() : g_err.c_str(); }
 const char *gar_version(void) { return "garecon hostsim (test build)"; }

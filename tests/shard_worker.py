@@ -57,7 +57,7 @@ def main():
         snap = garecon.tables.from_columns(*slices[rank])
     e = garecon.Engine(cluster_name="default", lib=lib, device=device)
     e.load(snap)
-    x = shard.DistExchange(e, sh, dev)
+    x = (shard.PeerExchange if len(sys.argv) > 5 and sys.argv[5] == "peers" else shard.DistExchange)(e, sh, dev)
     if len(sys.argv) > 5 and sys.argv[5] == "badzone":
         # every rank must raise (the failing one its own error, the others the agreed abort): nobody may hang in a collective
         try:

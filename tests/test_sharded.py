@@ -77,6 +77,29 @@ def test_sharded_multi_lbingress_models(garecon, oracle, hostlib, seed):
     assert any(0xFFFFFFFE in (int(o["a0"]), int(o["a1"]), int(o["a2"])) for o in got["ops"])
 
 
+@pytest.mark.parametrize("seed,n_ranks", [(0, 2), (1, 3), (2, 4), (3, 8), (4, 1)])
+def test_peer_memory_exchange_matches_unsharded(garecon, oracle, hostlib, seed, n_ranks):
+    """include/garecon.h "Peer-memory exchange": every rank's pack stores straight into the other ranks' receive arenas at the
+    offsets all ranks derive from the gathered meta rows — same sub-snapshots, same merged result as the all-to-all path."""
+    objects, actual = randmodel.make(seed, n_objects=60)
+    slices = shard.slice_model(objects, actual, n_ranks)
+    engines, snaps = [], []
+    for objs_r, act_r, _ in slices:
+        e = garecon.Engine(cluster_name="default", lib=hostlib)
+        snap = garecon.pack(objs_r, act_r)
+        e.load(snap)
+        engines.append(e)
+        snaps.append(snap)
+    shard.exchange_local_peers(engines, [s[2] for s in slices])
+    parts = [e.diff() for e in engines]
+    for e in engines:
+        e.close()
+    got = shard.merge_changesets(parts, len(objects))
+    want = oracle.diff(garecon.pack(objects, actual), "default", mode=1)
+    assert np.array_equal(got["status_ga"], want.status_ga) and np.array_equal(got["status_r53"], want.status_r53)
+    assert got["ops"].tolist() == want.ops.tolist(), first_diff(got["ops"].tolist(), want.ops.tolist())
+
+
 def test_sharded_hot_keys(garecon, oracle, hostlib):
     """Many owners claim the same record names / hostnames: alias records replicate to several homes, directory shards see
     long duplicate chains."""
@@ -146,7 +169,7 @@ def test_shards_are_balanced_and_disjoint(garecon, oracle, hostlib):
 
 # ------------------------------------------------------------------ generator slices (the bench workload of configs[3])
 
-def run_sharded_slices(garecon, lib, slices, device="cpu", **engine_kw):
+def run_sharded_slices(garecon, lib, slices, device="cpu", peers=False, **engine_kw):
     tables = garecon.tables
     bases = tables.shard_bases(slices)
     engines, keep = [], []
@@ -156,7 +179,10 @@ def run_sharded_slices(garecon, lib, slices, device="cpu", **engine_kw):
         e.load(snap)
         engines.append(e)
         keep.append(snap)  # hostsim reads the columns in place
-    shard.exchange_local(engines, bases, keep, device=device)
+    if peers:
+        shard.exchange_local_peers(engines, bases)
+    else:
+        shard.exchange_local(engines, bases, keep, device=device)
     parts = [e.diff() for e in engines]
     for e in engines:
         e.close()
@@ -258,6 +284,8 @@ def test_nccl_ranks_equal_unsharded():
     d = _launch(min(n, 8), 29547, "nccl", "synth", 4, 400_000)
     assert d["ok"] and d["n_ops"] > 100_000
     assert sum(d["homed"]) == d["n_objects"] and min(d["launches"]) > 0
+    d = _launch(min(n, 8), 29549, "nccl", "synth", 4, 400_000, "peers")  # rows stored straight into the other GPUs' arenas (CUDA IPC)
+    assert d["ok"] and d["n_ops"] > 100_000 and min(d["sent"]) > 0
 
 
 # ------------------------------------------------------------------ GPU tier: several engines on one B200, blobs in HBM
@@ -311,3 +339,5 @@ def test_gpu_sharded_equals_unsharded_at_scale(garecon, cfg, n_total, n_ranks):
     parts = run_sharded_slices(garecon, None, slices, device="cuda:0")
     check_slices(garecon, want, parts, n_total)
     assert len(want.ops) > n_total // 4
+    parts = run_sharded_slices(garecon, None, slices, device="cuda:0", peers=True)  # the peer-memory exchange (same process: plain pointers)
+    check_slices(garecon, want, parts, n_total)
