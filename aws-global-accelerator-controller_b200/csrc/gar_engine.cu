@@ -595,6 +595,10 @@ struct gar_engine {
   // every time (all sizes that only the device knows live in capacity-sized buffers): the second such diff is recorded into
   // a CUDA graph, later ones replay it — one graph launch instead of ~35 kernel launches and memsets (what a 10^5-object diff
   // is bound by).  Anything that changes the sequence (new snapshot, a capacity that grew, stage timing) drops the graph.
+  // capacities a previous snapshot's diffs settled on: the next snapshot of the same controller is almost always the same shape,
+  // so its first diff starts with buffers that fit (no grow-and-rerun on every load)
+  u32 hint_dport_cap = 0, hint_pair_cap = 0;
+  u64 hint_ops_cap = 0;
   bool use_graphs = true;  // environment GAR_NO_GRAPH=1 turns it off
   cudaGraphExec_t graph_exec = nullptr;
   u64 graph_sig = 0, seen_sig = 0;
@@ -967,6 +971,11 @@ static void do_diff(gar_engine *e, gar_changeset *out, bool to_host, const gar_k
     e->graph_drop();  // recorded launches belong to the previous pipeline's buffers and tables
     e->pipe = new Pipeline<gar_engine>(*e, e->T);
     if (const char *tc = getenv("GAR_TINY_CAPS")) e->pipe->tiny_caps = tc[0] == '1';
+    if (!e->pipe->tiny_caps) {
+      e->pipe->dport_cap = e->hint_dport_cap;
+      e->pipe->pair_cap = e->hint_pair_cap;
+      e->pipe->ops_cap = e->hint_ops_cap;
+    }
     if (e->shard_home) {
       e->pipe->acc_guest_from = e->sharder->guest_from;
       e->pipe->sharded = 1;
@@ -1108,6 +1117,11 @@ static void do_diff(gar_engine *e, gar_changeset *out, bool to_host, const gar_k
   CK(cudaEventElapsedTime(&out->ms_d2h, e->ev[3], e->ev[4]));
   out->ms_h2d = e->ms_h2d;
   out->kernel_launches = e->launches;
+  if (!ks && !bd) {  // remember what a full diff of this shape needs
+    e->hint_dport_cap = P.dport_cap;
+    e->hint_pair_cap = P.pair_cap;
+    e->hint_ops_cap = P.ops_cap;
+  }
   e->last_counters[GAR_CTR_R53_PAIRS] = P.n_pairs;
   e->last_counters[GAR_CTR_DPORTS] = dc.n_dports;
   e->last_timings.clear();

@@ -33,6 +33,7 @@
 #include <mutex>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <string>
 #include <string_view>
 #include <thread>
@@ -1437,10 +1438,23 @@ struct KeyBuf {
   sv view() const { return heap ? sv(big) : sv(small, n); }
 };
 
-// bucketed multi-map hash -> rows, rows of equal hash ascending (the callers verify the key bytes)
+// bucketed multi-map hash -> rows, rows of equal hash ascending (the callers verify the key bytes).  Large arrays are allocated
+// uninitialised and first touched by the pool's threads (a serial zero-fill of ~100 MB per index was the Amdahl term).
+template <class T>
+struct Raw {
+  std::unique_ptr<T[]> p;
+  size_t n = 0;
+  void alloc(size_t count) {
+    p.reset(new T[count]);
+    n = count;
+  }
+  T &operator[](size_t i) { return p[i]; }
+  const T &operator[](size_t i) const { return p[i]; }
+  bool empty() const { return n == 0; }
+};
 struct FlatIndex {
-  std::vector<uint32_t> begin, rows;
-  std::vector<uint64_t> hs;
+  Raw<uint32_t> begin, rows;
+  Raw<uint64_t> hs;
   uint32_t mask = 0;
   // key(i, &h) -> indexed?
   template <class KeyF>
@@ -1448,9 +1462,15 @@ struct FlatIndex {
     uint32_t nb = 16;
     while (nb < n) nb <<= 1;
     mask = nb - 1;
-    std::vector<uint64_t> th(n);
-    std::vector<uint8_t> ok(n);
-    std::vector<uint32_t> cnt((size_t)nb + 1, 0);
+    Raw<uint64_t> th;
+    Raw<uint8_t> ok;
+    Raw<uint32_t> cnt, cur;
+    th.alloc((size_t)n + 1);
+    ok.alloc((size_t)n + 1);
+    cnt.alloc((size_t)nb + 1);
+    cur.alloc((size_t)nb + 1);
+    begin.alloc((size_t)nb + 1);
+    pool.ranges(nb, [&](uint64_t lo, uint64_t hi, int) { memset(&cnt[lo], 0, 4 * (hi - lo)); });
     pool.ranges(n, [&](uint64_t lo, uint64_t hi, int) {
       for (uint64_t i = lo; i < hi; i++) {
         uint64_t h = 0;
@@ -1460,7 +1480,6 @@ struct FlatIndex {
       }
     });
     // exclusive scan, blocked over the pool
-    begin.assign((size_t)nb + 1, 0);
     std::vector<uint64_t> part((size_t)pool.T + 1, 0);
     pool.ranges(nb, [&](uint64_t lo, uint64_t hi, int t) {
       uint64_t s = 0;
@@ -1472,14 +1491,14 @@ struct FlatIndex {
       uint64_t s = part[(size_t)t];
       for (uint64_t b = lo; b < hi; b++) {
         begin[b] = (uint32_t)s;
+        cur[b] = (uint32_t)s;
         s += cnt[b];
       }
     });
     const uint32_t total = (uint32_t)part[(size_t)pool.T];
     begin[nb] = total;
-    rows.assign(total, 0);
-    hs.assign(total, 0);
-    std::vector<uint32_t> cur(begin.begin(), begin.end() - 1);
+    rows.alloc((size_t)total + 1);
+    hs.alloc((size_t)total + 1);
     pool.ranges(n, [&](uint64_t lo, uint64_t hi, int) {
       for (uint64_t i = lo; i < hi; i++)
         if (ok[i]) {
@@ -1505,10 +1524,12 @@ struct FlatIndex {
         }
       }
     });
+    n_entries = total;
   }
+  uint32_t n_entries = 0;
   template <class F>
   void each(uint64_t h, const F &f) const {  // f(row) -> keep going?
-    if (rows.empty()) return;
+    if (!n_entries) return;
     uint32_t b = (uint32_t)h & mask;
     for (uint32_t p = begin[b]; p < begin[b + 1]; p++)
       if (hs[p] == h && !f(rows[p])) return;
@@ -1579,13 +1600,13 @@ class Fast {
  public:
   Snap S;
   Pool &pool;
-  std::vector<uint32_t> recZone, valRec;
-  std::vector<AccDig> ad;
+  Raw<uint32_t> recZone, valRec;
+  Raw<AccDig> ad;
   FlatIndex ixOwner, ixThost, ixLb, ixZone, ixVal, ixAlias, ixObj;
 
   Fast(const gar_objects *o, const gar_actual *a, const char *cluster, Pool &p) : S{o, a, cluster}, pool(p) {
-    recZone.resize(a->n_records);
-    valRec.resize(a->n_values);
+    recZone.alloc((size_t)a->n_records + 1);
+    valRec.alloc((size_t)a->n_values + 1);
     pool.ranges(a->n_zones, [&](uint64_t lo, uint64_t hi, int) {
       for (uint64_t z = lo; z < hi; z++)
         for (uint32_t r = a->zone_rec_begin[z]; r < a->zone_rec_begin[z + 1]; r++) recZone[r] = (uint32_t)z;
@@ -1594,7 +1615,7 @@ class Fast {
       for (uint64_t r = lo; r < hi; r++)
         for (uint32_t v = a->rec_val_begin[r]; v < a->rec_val_begin[r + 1]; v++) valRec[v] = (uint32_t)r;
     });
-    ad.resize(a->n_accels);
+    ad.alloc((size_t)a->n_accels + 1);
     pool.ranges(a->n_accels, [&](uint64_t lo, uint64_t hi, int) {
       for (uint64_t i = lo; i < hi; i++) {
         AccDig d{};
@@ -2029,7 +2050,7 @@ class Fast {
 
 // R53 orphan section of ONE zone (shared by every mode): phase 0 alias sets x orphan owner values, phase 1 owner metadata sets
 template <class IsOrphan>
-void orphanZoneOps(const Snap &S, const std::vector<uint32_t> &valRec, uint32_t z, const IsOrphan &isOrphan, std::vector<gar_op> &out) {
+void orphanZoneOps(const Snap &S, const uint32_t *valRec, uint32_t z, const IsOrphan &isOrphan, std::vector<gar_op> &out) {
   const gar_actual *a = S.a;
   const uint32_t head = GAR_OP_HEAD(GAR_OP_R53_DELETE_RECORD, GAR_CTRL_R53, 0);
   uint32_t rb = a->zone_rec_begin[z], re = a->zone_rec_begin[z + 1];
@@ -2138,7 +2159,7 @@ int diff(const gar_objects *o, const gar_actual *a, const char *cluster, int thr
     };
     std::atomic<uint32_t> next{0};
     pool.run([&](int) {
-      for (uint32_t z; (z = next.fetch_add(1)) < a->n_zones;) orphanZoneOps(E.S, E.valRec, z, isOrphan, zoneOps[z]);
+      for (uint32_t z; (z = next.fetch_add(1)) < a->n_zones;) orphanZoneOps(E.S, &E.valRec[0], z, isOrphan, zoneOps[z]);
     });
   }
   // assemble: [GA objects | GA orphans | R53 objects | R53 orphans], every part copied in parallel
