@@ -378,12 +378,13 @@ class Engine:
 
     # peer-memory exchange (include/garecon.h): pack kernels store straight into the other ranks' receive arenas
     def shard_arena(self, rnd: int, need_bytes: int):
-        """-> (arena device pointer, handle bytes [SHARD_HANDLE_BYTES] uint8) of this rank's receive arena of round `rnd`."""
+        """-> (arena device pointer, handle bytes [SHARD_HANDLE_BYTES] uint8, capacity in bytes) of this rank's receive arena of
+        round `rnd`; need_bytes = 0 asks for the arena as it stands."""
         ptr = C.c_void_p()
         cap = C.c_uint64()
         handle = np.zeros(SHARD_HANDLE_BYTES, dtype=np.uint8)
         self._check(self.lib.gar_shard_arena(self._h, rnd, int(need_bytes), C.byref(ptr), handle.ctypes.data_as(_u8p), C.byref(cap)))
-        return int(ptr.value), handle
+        return int(ptr.value), handle, int(cap.value)
 
     def shard_open_peers(self, rnd: int, handles: np.ndarray) -> None:
         h = np.ascontiguousarray(handles, dtype=np.uint8)

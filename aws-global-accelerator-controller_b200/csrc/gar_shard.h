@@ -602,7 +602,12 @@ struct Sharder {
   u64 zone_fp = 0;           // fingerprint of this rank's zone table (round 1 meta)
   const char *contract_error = nullptr;
 
-  explicit Sharder(B &b) : be(b) {}
+  bool copy_merge = false;   // GAR_SHARD_COPY_MERGE=1: always copy the received string bytes into merged slabs (A/B, tests)
+
+  explicit Sharder(B &b) : be(b) {
+    const char *cm = getenv("GAR_SHARD_COPY_MERGE");
+    copy_merge = cm && cm[0] == '1';
+  }
   ~Sharder() {
     delete slice_pipe;
     delete dir_pipe;
@@ -819,7 +824,10 @@ struct Sharder {
   // The pack kernels with one destination address per rank: bases[d] = where this rank's blob for rank d starts.  With peer
   // memory mapped (gar_shard_pack_peers) these are addresses inside the OTHER GPUs' receive arenas: the rows travel over NVLink
   // as the pack kernels store them — partitioning and transfer are one step, no staging buffer, no separate collective.
-  void pack_to(u8 *const bases[SH_MAX_RANKS]) {
+  // `level_done(l, end)` (optional) runs on the host after level l's kernels are queued; end[d] = bytes of destination d's blob
+  // that are complete once those kernels have run — the engine uses it to start moving finished levels while later ones pack.
+  template <class Done>
+  void pack_to(u8 *const bases[SH_MAX_RANKS], Done level_done) {
     u64 lvl_off[SH_MAX_RANKS] = {0};
     for (int l = 0; l < L_NLEVELS; l++) {
       PackDst D{};
@@ -833,7 +841,12 @@ struct Sharder {
       if (!active[l] || !m) continue;
       be.for_each("shard_pack_columns", m, FShPackCols{src[l], SH_SCHEMA[l], plan[l], G, D});
       if (SH_SCHEMA[l].n_str && h_slab_off[l][G]) be.for_each("shard_pack_strings", m * SH_COPY_LANES, FShPackBytes{src[l], SH_SCHEMA[l].n_str, plan[l], G, D});
+      level_done(l, (const u64 *)lvl_off);
     }
+    level_done((int)L_NLEVELS, (const u64 *)lvl_off);
+  }
+  void pack_to(u8 *const bases[SH_MAX_RANKS]) {
+    pack_to(bases, [](int, const u64 *) {});
   }
 
   // ---- merge one level out of received blobs.  `from[s]` = (blob start, its meta row, level inside that blob).
@@ -859,8 +872,11 @@ struct Sharder {
     }
     return L;
   }
-  // slab: merged slab of the side this level's strings live in; *slab_used advances
-  Merged merge_level(int arena, int schema_lvl, const std::vector<Seg> &from, u8 *slab, u64 *slab_used) {
+  // String bytes are NOT moved when `origin` is set: a merged string reference is the byte's distance from `origin`, one
+  // address below every received blob, i.e. the receive buffers themselves serve as the slab of the merged tables (they must
+  // stay untouched until the last diff of this exchange).  Copy mode (origin == nullptr; buffers further apart than a 40-bit
+  // offset reaches, or GAR_SHARD_COPY_MERGE=1): the segments' bytes are appended to `slab`, *slab_used advances.
+  Merged merge_level(int arena, int schema_lvl, const std::vector<Seg> &from, u8 *slab, u64 *slab_used, const u8 *origin = nullptr) {
     const LevelSchema &Sc = SH_SCHEMA[schema_lvl];
     Merged M;
     FShUnpackCols f{};
@@ -873,10 +889,14 @@ struct Sharder {
       f.seg[s].lay = layout_in_blob(g.meta, g.lvl);
       for (int c = 0; c < SH_MAX_CHILD; c++) f.has_cnt[s][c] = c < SH_SCHEMA[g.lvl].n_child;
       f.seg_row[s] = n;
-      f.slab_base[s] = *slab_used;
       u64 sb = g.meta[L_NLEVELS + g.lvl];
-      if (sb) be.copy_bytes(slab + *slab_used, g.blob + f.seg[s].lay.slab, sb);
-      *slab_used += sb;
+      if (origin) {
+        f.slab_base[s] = (u64)((g.blob + f.seg[s].lay.slab) - origin);
+      } else {
+        f.slab_base[s] = *slab_used;
+        if (sb) be.copy_bytes(slab + *slab_used, g.blob + f.seg[s].lay.slab, sb);
+        *slab_used += sb;
+      }
       n += (u32)g.meta[g.lvl];
     }
     f.seg_row[f.nseg] = n;
@@ -897,6 +917,11 @@ struct Sharder {
     u64 t = 0;
     for (auto &g : groups)
       for (auto &s : g) t += s.meta[L_NLEVELS + s.lvl];
+    return t;
+  }
+  u64 recv_bytes(const u64 (*meta)[GAR_SHARD_META_WORDS]) {
+    u64 t = 0;
+    for (u32 s = 0; s < G; s++) t += blob_bytes(meta[s]);
     return t;
   }
   std::vector<Seg> segs(const u8 *recv, const u64 (*meta)[GAR_SHARD_META_WORDS], int lvl) {
@@ -922,14 +947,22 @@ struct Sharder {
     be.shard_reset(SH_ARENA_DIR);
     auto lb = segs(recv, meta1, L_LB), st = segs(recv, meta1, L_STUB), stt = segs(recv, meta1, L_STUBTAG), pr = segs(recv, meta1, L_PROBE);
     u64 a_bytes = slab_total({lb, st, stt}), o_bytes = slab_total({pr});
-    u8 *aslab = alloc<u8>(SH_ARENA_DIR, a_bytes + GAR_SLAB_PAD), *oslab = alloc<u8>(SH_ARENA_DIR, o_bytes + GAR_SLAB_PAD);
-    be.fill32((u32 *)(aslab + (a_bytes & ~(u64)3)), 0, GAR_SLAB_PAD / 4);
-    be.fill32((u32 *)(oslab + (o_bytes & ~(u64)3)), 0, GAR_SLAB_PAD / 4);
+    const u8 *origin = copy_merge ? nullptr : recv;
+    u8 *aslab = nullptr, *oslab = nullptr;
+    if (origin) {  // the received blobs are the slab (the caller keeps GAR_SLAB_PAD readable bytes behind them)
+      aslab = oslab = (u8 *)origin;
+      a_bytes = o_bytes = recv_bytes(meta1);
+    } else {
+      aslab = alloc<u8>(SH_ARENA_DIR, a_bytes + GAR_SLAB_PAD);
+      oslab = alloc<u8>(SH_ARENA_DIR, o_bytes + GAR_SLAB_PAD);
+      be.fill32((u32 *)(aslab + (a_bytes & ~(u64)3)), 0, GAR_SLAB_PAD / 4);
+      be.fill32((u32 *)(oslab + (o_bytes & ~(u64)3)), 0, GAR_SLAB_PAD / 4);
+    }
     u64 au = 0, ou = 0;
-    Merged mlb = merge_level(SH_ARENA_DIR, L_LB, lb, aslab, &au);
-    Merged mst = merge_level(SH_ARENA_DIR, L_STUB, st, aslab, &au);
-    Merged mtt = merge_level(SH_ARENA_DIR, L_STUBTAG, stt, aslab, &au);
-    Merged mpr = merge_level(SH_ARENA_DIR, L_PROBE, pr, oslab, &ou);
+    Merged mlb = merge_level(SH_ARENA_DIR, L_LB, lb, aslab, &au, origin);
+    Merged mst = merge_level(SH_ARENA_DIR, L_STUB, st, aslab, &au, origin);
+    Merged mtt = merge_level(SH_ARENA_DIR, L_STUBTAG, stt, aslab, &au, origin);
+    Merged mpr = merge_level(SH_ARENA_DIR, L_PROBE, pr, oslab, &ou, origin);
     Dt = DevTables{};
     Dt.cluster = S.cluster;
     Dt.cluster_len = S.cluster_len;
@@ -1004,20 +1037,33 @@ struct Sharder {
     std::vector<Seg> s_lb = r2(L_LB);
     u64 o_bytes = slab_total({s_obj, s_ann, s_lbi, s_port});
     u64 a_bytes = slab_total({s_acc, s_tag, s_lis, s_pr, s_eg, s_ep, s_rec, s_val, s_zone, s_lb});
-    u8 *oslab = alloc<u8>(SH_ARENA_HOME, o_bytes + GAR_SLAB_PAD), *aslab = alloc<u8>(SH_ARENA_HOME, a_bytes + GAR_SLAB_PAD);
-    be.fill32((u32 *)(oslab + (o_bytes & ~(u64)3)), 0, GAR_SLAB_PAD / 4);
-    be.fill32((u32 *)(aslab + (a_bytes & ~(u64)3)), 0, GAR_SLAB_PAD / 4);
+    // both receive buffers under one 40-bit string offset: no string byte moves
+    const u8 *origin = recv1 < recv2 ? recv1 : recv2;
+    const u8 *e1 = recv1 + recv_bytes(meta1), *e2 = recv2 + recv_bytes(meta2);
+    const u64 span = (u64)((e1 > e2 ? e1 : e2) - origin);
+    if (copy_merge || span + GAR_SLAB_PAD >= (1ull << 40)) origin = nullptr;
+    u8 *oslab = nullptr, *aslab = nullptr;
+    if (origin) {
+      oslab = aslab = (u8 *)origin;
+      o_bytes = a_bytes = span;
+    } else {
+      oslab = alloc<u8>(SH_ARENA_HOME, o_bytes + GAR_SLAB_PAD);
+      aslab = alloc<u8>(SH_ARENA_HOME, a_bytes + GAR_SLAB_PAD);
+      be.fill32((u32 *)(oslab + (o_bytes & ~(u64)3)), 0, GAR_SLAB_PAD / 4);
+      be.fill32((u32 *)(aslab + (a_bytes & ~(u64)3)), 0, GAR_SLAB_PAD / 4);
+    }
     u64 ou = 0, au = 0;
     const int AR = SH_ARENA_HOME;
-    Merged obj = merge_level(AR, L_OBJ, s_obj, oslab, &ou), ann = merge_level(AR, L_ANN, s_ann, oslab, &ou);
-    Merged lbi = merge_level(AR, L_LBI, s_lbi, oslab, &ou), port = merge_level(AR, L_PORT, s_port, oslab, &ou);
+    auto ml = [&](int lvl, const std::vector<Seg> &from, bool obj_side) { return merge_level(AR, lvl, from, obj_side ? oslab : aslab, obj_side ? &ou : &au, origin); };
+    Merged obj = ml(L_OBJ, s_obj, true), ann = ml(L_ANN, s_ann, true);
+    Merged lbi = ml(L_LBI, s_lbi, true), port = ml(L_PORT, s_port, true);
     u32 n_own = 0;
     for (u32 s = 0; s < G; s++) n_own += (u32)meta1[s][L_ACC];
-    Merged acc = merge_level(AR, L_ACC, s_acc, aslab, &au), tag = merge_level(AR, L_TAG, s_tag, aslab, &au);
-    Merged lis = merge_level(AR, L_LIS, s_lis, aslab, &au), pr = merge_level(AR, L_PR, s_pr, aslab, &au);
-    Merged eg = merge_level(AR, L_EG, s_eg, aslab, &au), ep = merge_level(AR, L_EP, s_ep, aslab, &au);
-    Merged rec = merge_level(AR, L_REC, s_rec, aslab, &au), val = merge_level(AR, L_VAL, s_val, aslab, &au);
-    Merged zone = merge_level(AR, L_ZONE, s_zone, aslab, &au), lb = merge_level(AR, L_LB, s_lb, aslab, &au);
+    Merged acc = ml(L_ACC, s_acc, false), tag = ml(L_TAG, s_tag, false);
+    Merged lis = ml(L_LIS, s_lis, false), pr = ml(L_PR, s_pr, false);
+    Merged eg = ml(L_EG, s_eg, false), ep = ml(L_EP, s_ep, false);
+    Merged rec = ml(L_REC, s_rec, false), val = ml(L_VAL, s_val, false);
+    Merged zone = ml(L_ZONE, s_zone, false), lb = ml(L_LB, s_lb, false);
 
     H = DevTables{};
     H.cluster = S.cluster;

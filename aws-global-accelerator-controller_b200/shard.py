@@ -87,7 +87,7 @@ def exchange_local_peers(engines, shards):
         arenas, handles = [], []
         for d, e in enumerate(engines):
             need = sum(e.blob_bytes(all_meta[s][d]) for s in range(g))
-            ptr, h = e.shard_arena(rnd, need)
+            ptr, h, _ = e.shard_arena(rnd, need)
             arenas.append(ptr)
             handles.append(h)
         handles = np.stack(handles)
@@ -280,31 +280,40 @@ def add_checksums(parts) -> dict:
 
 
 class PeerExchange(DistExchange):
-    """One process per GPU on one NVLink node: the rows travel as the pack kernels store them into the other GPUs' receive
-    arenas (CUDA IPC mappings, include/garecon.h "Peer-memory exchange").  torch.distributed only moves the meta rows and the
-    arena handles (two tiny all-gathers per round) and provides the barrier after the packs."""
+    """One process per GPU on one NVLink node: no collective on the data path.  Every rank maps the other GPUs' receive arenas
+    (CUDA IPC, include/garecon.h "Peer-memory exchange"); gar_shard_pack_peers packs and lets the copy engines push the blobs
+    into the peers' arenas while later levels still pack.  torch.distributed moves one small all-gather per round (meta rows +
+    arena handle, 0.4 KB per rank) and provides the barrier after the packs."""
 
     def round(self, rnd: int):
         torch, dist = self.torch, self.dist
         g = self.g
-        meta, nbytes = self._timed(f"route{rnd}", lambda: self._guard(lambda: self.e.shard_route(self.shard, rnd)))
-        m_out = torch.from_numpy(meta.view(np.int64)).to(self.device)
-        m_all = torch.empty((g,) + tuple(m_out.shape), dtype=m_out.dtype, device=self.device)
-        self._timed(f"meta{rnd}", lambda: dist.all_gather_into_tensor(m_all, m_out))
-        all_meta = m_all.cpu().numpy().view(np.uint64)  # [source][destination][words]
         me = int(self.shard.rank)
-        need = sum(self.e.blob_bytes(all_meta[s][me]) for s in range(g))
+        meta, nbytes = self._timed(f"route{rnd}", lambda: self._guard(lambda: self.e.shard_route(self.shard, rnd)))
 
-        def arenas():
-            arena, handle = self._guard(lambda: self.e.shard_arena(rnd, need))
-            h_out = torch.from_numpy(handle).to(self.device)
-            h_all = torch.empty((g, abi.SHARD_HANDLE_BYTES), dtype=torch.uint8, device=self.device)
-            dist.all_gather_into_tensor(h_all, h_out)  # also orders "arena (re)allocated" before anybody's stores
-            self._guard(lambda: self.e.shard_open_peers(rnd, h_all.cpu().numpy()))
-            return arena
-        arena = self._timed(f"meta{rnd}", arenas)
-        # pack == transfer: the stores land in the peers' arenas.  gar_shard_pack_peers returns after its stream has drained;
-        # _guard's all-reduce (or the barrier) then makes "every rank has packed" known to every rank
+        def gather():
+            # the arena as it stands (capacities only grow, so after the first step it fits) rides along with the meta rows
+            arena, handle, cap = self._guard(lambda: self.e.shard_arena(rnd, 0))
+            row = np.concatenate([meta.view(np.uint8).reshape(-1), handle, np.array([cap], dtype=np.uint64).view(np.uint8)])
+            out = torch.from_numpy(row).to(self.device)
+            gathered = torch.empty(g * row.size, dtype=torch.uint8, device=self.device)
+            dist.all_gather_into_tensor(gathered, out)
+            gathered = gathered.cpu().numpy().reshape(g, row.size)
+            all_meta = np.ascontiguousarray(gathered[:, :meta.nbytes]).view(np.uint64).reshape((g,) + meta.shape)  # [source][destination][words]
+            handles = np.ascontiguousarray(gathered[:, meta.nbytes:meta.nbytes + abi.SHARD_HANDLE_BYTES])
+            caps = [int(np.ascontiguousarray(gathered[d, meta.nbytes + abi.SHARD_HANDLE_BYTES:]).view(np.uint64)[0]) for d in range(g)]
+            need = [sum(self.e.blob_bytes(all_meta[s][d]) for s in range(g)) for d in range(g)]
+            if any(caps[d] < need[d] + 64 for d in range(g)):  # every rank sees the same numbers: all of them take this branch or none
+                arena, handle, _ = self._guard(lambda: self.e.shard_arena(rnd, need[me]))
+                h_out = torch.from_numpy(handle).to(self.device)
+                h_all = torch.empty(g * abi.SHARD_HANDLE_BYTES, dtype=torch.uint8, device=self.device)
+                dist.all_gather_into_tensor(h_all, h_out)  # also orders "arena (re)allocated" before anybody's stores
+                handles = h_all.cpu().numpy().reshape(g, abi.SHARD_HANDLE_BYTES)
+            self._guard(lambda: self.e.shard_open_peers(rnd, handles))
+            return all_meta, arena
+        all_meta, arena = self._timed(f"meta{rnd}", gather)
+        # gar_shard_pack_peers returns after its streams have drained: this rank's blobs are in the peers' arenas.  _guard's
+        # all-reduce (or the barrier) then makes "every rank has packed" known to every rank
         def pack():
             self._guard(lambda: self.e.shard_pack_peers(rnd, all_meta))
             if not self.check_errors:

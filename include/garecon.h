@@ -446,8 +446,12 @@ int gar_bindings_diff(gar_engine *e, const gar_bindings *bindings, gar_changeset
        exchange the meta rows (all-to-all of GAR_SHARD_META_WORDS u64 per peer)
        gar_shard_pack(e, send)                                send: device buffer of sum(send_bytes), blobs back to back
        exchange the blobs (all-to-all, sizes from gar_shard_blob_bytes(received meta row))
-       gar_shard_unpack(e, round, recv, recv_meta)            recv: the received blobs back to back, in rank order;
-                                                              the round-1 buffer must stay alive until round 2 is unpacked
+       gar_shard_unpack(e, round, recv, recv_meta)            recv: the received blobs back to back, in rank order, with
+                                                              32 readable bytes behind them.  The string bytes are NOT
+                                                              copied: the sub-snapshot's strings live in BOTH rounds' receive
+                                                              buffers, which must stay alive and unchanged until the last
+                                                              diff of this exchange (the next gar_shard_route(.., 1) or
+                                                              gar_snapshot_load ends their use)
    Round 1 moves every row to the shard its own key hashes to and one probe per lbIngress hostname to the "directory"
    shard of that hostname; round 2 returns the load balancer / by-hostname accelerators each probe resolves to.  After the
    second unpack the engine holds a self-contained sub-snapshot: gar_diff / gar_diff_device work as usual, n_objects is
@@ -465,9 +469,12 @@ int gar_shard_pack(gar_engine *e, void *send);
 int gar_shard_unpack(gar_engine *e, int round, const void *recv, const uint64_t *recv_meta);
 uint64_t gar_shard_blob_bytes(const uint64_t *meta_row);
 
-/* Peer-memory exchange (one process per GPU on one NVLink / NVSwitch node): instead of packing into a local send buffer that a
-   collective then copies, every rank's pack kernels store their rows straight into the RECEIVE arenas of the other GPUs, mapped
-   through CUDA IPC — partitioning by key hash and the transfer over NVLink are one step.  Per round:
+/* Peer-memory exchange (one process per GPU on one NVLink / NVSwitch node): no collective on the data path.  Every rank maps the
+   RECEIVE arenas of the other GPUs through CUDA IPC; gar_shard_pack_peers packs the rank's own blob in place and the others into a
+   local stage from which the copy engines push them into the peers' arenas over NVLink, one stream per destination, level group by
+   level group while the later levels are still being packed (transfer and partitioning overlap).  GAR_PEER_DIRECT=1 makes the pack
+   kernels store straight into the mapped arenas instead (one step, but 8-byte scattered stores over NVLink: 2.4x slower on 8
+   GPUs).  Per round:
 
      gar_shard_route(e, &shard, round, meta, send_bytes)
      all-gather the meta rows                                  -> all_meta[s][d] = row of source s for destination d

@@ -62,6 +62,15 @@ def test_sharded_matches_unsharded(garecon, oracle, hostlib, seed, n_ranks):
     check(garecon, oracle, hostlib, objects, actual, n_ranks)
 
 
+@pytest.mark.parametrize("seed,n_ranks", [(40, 2), (41, 3), (42, 8)])
+def test_sharded_copy_merge_fallback(garecon, oracle, hostlib, seed, n_ranks, monkeypatch):
+    """By default the merged sub-snapshot's strings stay in the receive buffers (no byte is copied); when the two rounds' buffers
+    lie further apart than a string offset reaches the engine copies them into merged slabs instead.  Same results."""
+    monkeypatch.setenv("GAR_SHARD_COPY_MERGE", "1")
+    objects, actual = randmodel.make(seed, n_objects=60)
+    check(garecon, oracle, hostlib, objects, actual, n_ranks)
+
+
 @pytest.mark.parametrize("seed", range(6, 30))
 def test_sharded_more_seeds(garecon, oracle, hostlib, seed):
     objects, actual = randmodel.make(seed, n_objects=40)
@@ -263,6 +272,16 @@ def test_two_ranks_gloo_all_to_all():
     assert d["ok"] and d["world"] == 2 and d["n_ops"] > 50
     assert sum(d["homed"]) == 120 and min(d["homed"]) > 20
     assert min(d["sent"]) > 1000
+
+
+def test_peer_exchange_host_logic_single_rank_gloo():
+    """PeerExchange's host side (meta rows + arena handle + capacity in one all-gather, regrow agreement, barrier) with the
+    hostsim engine: host arenas cannot be mapped across processes, so one rank — the multi-rank data path is the GPU tier's."""
+    import __graft_entry__ as ge
+    ge.build_hostsim()
+    ge.build_oracle()
+    d = _launch(1, 29545, "gloo", "randmodel", 22, 90, "peers")
+    assert d["ok"] and d["world"] == 1 and d["n_ops"] > 30 and d["homed"] == [90]
 
 
 def test_an_engine_error_on_one_rank_aborts_every_rank():
