@@ -32,6 +32,12 @@
 
 #include "gar_pipeline.h"
 
+#if defined(__CUDA_ARCH__)
+#define GAR_ATOMIC_OR(p, v) atomicOr((p), (v))
+#else
+#define GAR_ATOMIC_OR(p, v) (*(p) |= (v))
+#endif
+
 constexpr int SH_MAX_RANKS = GAR_SHARD_MAX_RANKS;
 constexpr int SH_MAX_SEGS = 2 * SH_MAX_RANKS;
 enum ShLevel { L_OBJ, L_ANN, L_LBI, L_PORT, L_ACC, L_TAG, L_LIS, L_PR, L_EG, L_EP, L_REC, L_VAL, L_ZONE, L_LB, L_STUB, L_STUBTAG, L_PROBE, L_NLEVELS };
@@ -214,39 +220,26 @@ struct FShValDest {
   u8 *val_dest;
   GAR_HD void operator()(u32 v) const { val_dest[v] = W.val_cls[v] == VAL_NOT_OWNER ? (u8)SH_DROP : (u8)shard_of(W.val_key_hash[v], G); }
 };
-// (destination, record) pairs: the record of every owner value, and every alias record under the same (zone, name)
-// (FindOwneredARecordSets, route53.go:216-238).  Count pass (pairs == nullptr) then fill pass.
-struct FShRecPairs {
+// Which shards need a record: bit d of mask[rec] for the record of every owner value homed on d, and for every alias record
+// under the same (zone, name) (FindOwneredARecordSets, route53.go:216-238).
+struct FShRecMask {
   DevTables T;
   Work W;
   const u8 *val_dest;
-  u32 *counts;  // count pass: written; fill pass: scanned
-  u32 *keys, *vals;
+  u32 *mask;  // [n_records]
   GAR_HD void operator()(u32 v) const {
     u32 d = val_dest[v];
-    if (d == SH_DROP) {
-      if (!keys) counts[v] = 0;
-      return;
-    }
+    if (d == SH_DROP) return;
     u32 rec = W.val_rec[v], zone = W.rec_zone[rec];
-    u32 n = 0, base = keys ? counts[v] : 0;
-    if (keys) {
-      keys[base] = d;
-      vals[base] = rec;
-    }
-    n++;
+    const u32 bit = 1u << d;
+    if (!(mask[rec] & bit)) GAR_ATOMIC_OR(&mask[rec], bit);
     Str name = mkstr(T.a.slab, T.a.rec_name[rec]);
     Cursor c = idx_open(W.ix_alias, key_hash_zoned_h(zone, W.rec_name_hash[rec]));
     IdxEntry e;
     while (idx_next(W.ix_alias, c, &e)) {
       if (e.a0 != zone || e.row == rec || !streq(mkstr(T.a.slab, e.s0), name)) continue;
-      if (keys) {
-        keys[base + n] = d;
-        vals[base + n] = e.row;
-      }
-      n++;
+      if (!(mask[e.row] & bit)) GAR_ATOMIC_OR(&mask[e.row], bit);
     }
-    if (!keys) counts[v] = n;
   }
 };
 struct FShIota {
@@ -276,45 +269,49 @@ struct FShSelBounds {
     if (d == G) *m = lo;
   }
 };
-struct FShUniqueFlag {  // (keys, vals) sorted by (key, val): keep the first of each run, drop SH_DROP
-  const u32 *keys, *vals;
-  u32 n;
-  u32 *flag;  // [n+1]
-  GAR_HD void operator()(u32 j) const {
-    u32 f = 0;
-    if (j < n) f = keys[j] != SH_DROP && (j == 0 || keys[j] != keys[j - 1] || vals[j] != vals[j - 1]);
-    flag[j] = f;
+// Destination masks -> the selection list sorted by (destination, row), duplicates impossible.  One thread per tile of 32 rows:
+// count per destination, one scan over the [destination][tile] counts, then the same threads write their rows.
+constexpr u32 SH_MASK_TILE = 32;
+struct FShMaskCount {
+  const u32 *mask;
+  u32 n, G, T;
+  u32 *counts;  // [G * T + 1], destination-major
+  GAR_HD void operator()(u32 t) const {
+    u32 c[SH_MAX_RANKS];
+    for (int d = 0; d < SH_MAX_RANKS; d++) c[d] = 0;
+    u32 r1 = (t + 1) * SH_MASK_TILE < n ? (t + 1) * SH_MASK_TILE : n;
+    for (u32 r = t * SH_MASK_TILE; r < r1; r++) {
+      u32 m = mask[r];
+      for (int d = 0; d < SH_MAX_RANKS; d++) c[d] += (m >> d) & 1u;
+    }
+    for (int d = 0; d < SH_MAX_RANKS; d++)
+      if ((u32)d < G) counts[(size_t)d * T + t] = c[d];
   }
 };
-struct FShCompact {
-  const u32 *keys, *vals, *scanned;
-  u32 *keys_out, *vals_out;
-  GAR_HD void operator()(u32 j) const {
-    if (scanned[j + 1] != scanned[j]) {
-      keys_out[scanned[j]] = keys[j];
-      vals_out[scanned[j]] = vals[j];
+struct FShMaskFill {
+  const u32 *mask;
+  u32 n, G, T;
+  const u32 *scanned;
+  u32 *sel;
+  GAR_HD void operator()(u32 t) const {
+    u32 pos[SH_MAX_RANKS];
+    for (int d = 0; d < SH_MAX_RANKS; d++) pos[d] = (u32)d < G ? scanned[(size_t)d * T + t] : 0;
+    u32 r1 = (t + 1) * SH_MASK_TILE < n ? (t + 1) * SH_MASK_TILE : n;
+    for (u32 r = t * SH_MASK_TILE; r < r1; r++) {
+      u32 m = mask[r];
+      for (int d = 0; d < SH_MAX_RANKS; d++)
+        if ((m >> d) & 1u) sel[pos[d]++] = r;
     }
   }
 };
-struct FShChildCount {
-  LevelSrc src;
-  int link;
-  LevelPlan P;
-  u32 G;
-  u32 *out;  // [cap+1]
-  GAR_HD void operator()(u32 j) const {
-    u32 c = 0;
-    if (j < *P.m) {
-      u32 p = P.sel[j], b0 = src.child_begin[link][p], b1 = src.child_begin[link][p + 1];
-      const u8 *cd = src.child_dest[link];
-      if (cd) {
-        u32 d = dest_of(j, P.row_off, G);
-        for (u32 ch = b0; ch < b1; ch++) c += cd[ch] == d || cd[ch] == SH_FOLLOW;
-      } else {
-        c = b1 - b0;
-      }
-    }
-    out[j] = c;
+struct FShMaskBounds {
+  const u32 *scanned;
+  u32 G, T;
+  u32 *row_off, *m;
+  GAR_HD void operator()(u32 d) const {
+    u32 v = scanned[(size_t)d * T];
+    row_off[d] = v;
+    if (d == G) *m = v;
   }
 };
 struct FShChildFill {
@@ -348,18 +345,35 @@ struct FShDerivedBounds {
     if (d == G && out_m) *out_m = v;
   }
 };
-struct FShStrLen {
+// child counts of every link and the string bytes of a selected row, one pass over the selection
+struct FShRowSizes {
   LevelSrc src;
-  int n_str;
+  LevelSchema S;
   LevelPlan P;
-  u32 *out;  // [cap+1]
+  u32 G;
   GAR_HD void operator()(u32 j) const {
-    u32 b = 0;
+    u32 cnt[SH_MAX_CHILD] = {0, 0, 0}, bytes = 0;
     if (j < *P.m) {
-      u32 p = P.sel[j];
-      for (int c = 0; c < n_str; c++) b += sh_pad8((u32)GAR_STR_LEN(src.str[c][p]));
+      u32 p = P.sel[j], d = 0;
+      bool need_d = false;
+      for (int c = 0; c < SH_MAX_CHILD; c++) need_d |= c < S.n_child && src.child_dest[c] != nullptr;
+      if (need_d) d = dest_of(j, P.row_off, G);
+      for (int c = 0; c < SH_MAX_CHILD; c++) {
+        if (c >= S.n_child) break;
+        u32 b0 = src.child_begin[c][p], b1 = src.child_begin[c][p + 1];
+        const u8 *cd = src.child_dest[c];
+        if (cd) {
+          for (u32 ch = b0; ch < b1; ch++) cnt[c] += cd[ch] == d || cd[ch] == SH_FOLLOW;
+        } else {
+          cnt[c] = b1 - b0;
+        }
+      }
+      for (int c = 0; c < SH_MAX_STR; c++)
+        if (c < S.n_str) bytes += sh_pad8((u32)GAR_STR_LEN(src.str[c][p]));
     }
-    out[j] = b;
+    for (int c = 0; c < SH_MAX_CHILD; c++)
+      if (c < S.n_child) P.cnt[c][j] = cnt[c];
+    P.slab_scan[j] = bytes;
   }
 };
 
@@ -369,47 +383,80 @@ struct PackDst {
   u8 *base[SH_MAX_RANKS];  // start of destination d's blob
   LevelLayout lay[SH_MAX_RANKS];
 };
-struct FShPackCols {
+// One thread per selected row: its fixed-width columns, then its strings, each copied as whole 8-byte words (the source may sit
+// at any byte offset: aligned loads + funnel shift, one load per word; the destination word is aligned; the bytes behind a
+// string's end up to the next word are don't-care).  A row's strings are ~30-250 bytes, so a thread keeps that many bytes in
+// flight behind ONE dependent chain (selection -> string refs -> bytes) — the 8-lanes-per-row version of round 1 moved 8 bytes
+// per chain and ran at 1.4 TB/s.  Strings longer than SH_LONG_WORDS words are cut here and finished by FShPackLong.
+constexpr u32 SH_LONG_WORDS = 256;  // 2 KB
+GAR_HD void sh_copy_words(u64 *dst, const u8 *s, u32 words) {
+  if (!words) return;
+  uintptr_t a = (uintptr_t)s;
+  const u64 *q = (const u64 *)(a & ~(uintptr_t)7);
+  const unsigned sh = (unsigned)(a & 7) * 8;
+  u64 lo = q[0];
+#pragma unroll 4
+  for (u32 w = 0; w < words; w++) {
+    u64 hi = q[w + 1];
+    dst[w] = (lo >> sh) | ((hi << 1) << (63 - sh));
+    lo = hi;
+  }
+}
+struct FShPackRows {
   LevelSrc src;
   LevelSchema S;
   LevelPlan P;
   u32 G;
   PackDst D;
+  u32 *any_long;  // device flag: some string was cut
   GAR_HD void operator()(u32 j) const {
     u32 d = dest_of(j, P.row_off, G), k = j - P.row_off[d], p = P.sel[j];
     u8 *b = D.base[d];
     const LevelLayout &L = D.lay[d];
     u64 off = P.slab_scan[j] - P.slab_scan[P.row_off[d]];
-    for (int c = 0; c < S.n_str; c++) {
-      u64 len = GAR_STR_LEN(src.str[c][p]);
-      ((gar_str *)(b + L.str[c]))[k] = GAR_STR(off, len);
-      off += sh_pad8((u32)len);
-    }
+    gar_str ref[SH_MAX_STR];
+    for (int c = 0; c < SH_MAX_STR; c++)
+      if (c < S.n_str) ref[c] = src.str[c][p];
     for (int c = 0; c < S.n_u8; c++) (b + L.u8c[c])[k] = src.u8c[c][p];
     for (int c = 0; c < S.n_u32; c++) ((u32 *)(b + L.u32c[c]))[k] = src.u32c[c][p];
     if (S.has_gid) ((u32 *)(b + L.gid))[k] = src.gid ? src.gid[p] : src.gid_base + p;
     for (int c = 0; c < S.n_child; c++) ((u32 *)(b + L.cnt[c]))[k] = P.cnt[c][j + 1] - P.cnt[c][j];
+    bool cut = false;
+    for (int c = 0; c < SH_MAX_STR; c++) {
+      if (c >= S.n_str) break;
+      u64 len = GAR_STR_LEN(ref[c]);
+      ((gar_str *)(b + L.str[c]))[k] = GAR_STR(off, len);
+      u32 words = sh_pad8((u32)len) >> 3;
+      cut |= words > SH_LONG_WORDS;
+      sh_copy_words((u64 *)(b + L.slab + off), src.slab + GAR_STR_OFF(ref[c]), words > SH_LONG_WORDS ? SH_LONG_WORDS : words);
+      off += (u64)words << 3;
+    }
+    if (cut) *any_long = 1;
   }
 };
-// SH_COPY_LANES threads per selected row: lane l copies words l, l+LANES, ... of each string.  The source may sit at any byte
-// offset (ld64u), the destination word is aligned; the bytes behind a string's end up to the next word are don't-care.
-constexpr u32 SH_COPY_LANES = 8;
-struct FShPackBytes {
+// The rest of the cut strings: a fixed number of workers stride over the rows, SH_COPY_LANES lanes per row.  Leaves at once when
+// no string was cut (the flag stays on the device: no host round-trip decides about this launch).
+constexpr u32 SH_COPY_LANES = 8, SH_LONG_WORKERS = 148 * 8 * 256;
+struct FShPackLong {
   LevelSrc src;
   int n_str;
   LevelPlan P;
-  u32 G;
+  u32 G, m;
   PackDst D;
+  const u32 *any_long;
   GAR_HD void operator()(u32 t) const {
-    u32 j = t / SH_COPY_LANES, lane = t % SH_COPY_LANES;
-    u32 d = dest_of(j, P.row_off, G), p = P.sel[j];
-    u64 *dst = (u64 *)(D.base[d] + D.lay[d].slab + (P.slab_scan[j] - P.slab_scan[P.row_off[d]]));
-    for (int c = 0; c < n_str; c++) {
-      gar_str r = src.str[c][p];
-      const u8 *s = src.slab + GAR_STR_OFF(r);
-      u32 words = sh_pad8((u32)GAR_STR_LEN(r)) >> 3;
-      for (u32 w = lane; w < words; w += SH_COPY_LANES) dst[w] = ld64u(s + 8 * (size_t)w);
-      dst += words;
+    if (!*any_long) return;
+    const u32 lane = t % SH_COPY_LANES;
+    for (u32 j = t / SH_COPY_LANES; j < m; j += SH_LONG_WORKERS / SH_COPY_LANES) {
+      u32 d = dest_of(j, P.row_off, G), p = P.sel[j];
+      u64 *dst = (u64 *)(D.base[d] + D.lay[d].slab + (P.slab_scan[j] - P.slab_scan[P.row_off[d]]));
+      for (int c = 0; c < n_str; c++) {
+        gar_str r = src.str[c][p];
+        const u8 *s = src.slab + GAR_STR_OFF(r);
+        u32 words = sh_pad8((u32)GAR_STR_LEN(r)) >> 3;
+        for (u32 w = SH_LONG_WORDS + lane; w < words; w += SH_COPY_LANES) dst[w] = ld64u(s + 8 * (size_t)w);
+        dst += words;
+      }
     }
   }
 };
@@ -512,35 +559,22 @@ struct FShAnswer {
   DevTables T;  // directory tables: lbi_* = probes, lb_* and acc_* = rows routed here
   Work W;
   const u32 *home;
-  u32 n;
-  u32 *lb_keys, *lb_vals;      // [n]
-  u32 *stub_keys, *stub_vals;  // [2n]
+  u32 *lb_mask, *stub_mask;  // [n_lbs], [n_accels]: bit d = the row is an answer for a probe whose object lives on shard d
   GAR_HD void operator()(u32 p) const {
-    u32 d = home[p];
-    u32 lk = SH_DROP, lv = 0;
+    const u32 bit = 1u << home[p];
     if (W.tok_code[p] <= GAR_TOK_NLB) {
       u32 st;
       u32 lb = find_lb(T, W, mkstr(T.o.slab, W.tok_region[p]), mkstr(T.o.slab, W.tok_name[p]), &st);
-      if (lb != GAR_NONE) {
-        lk = d;
-        lv = lb;
-      }
+      if (lb != GAR_NONE && !(lb_mask[lb] & bit)) GAR_ATOMIC_OR(&lb_mask[lb], bit);
     }
-    lb_keys[p] = lk;
-    lb_vals[p] = lv;
     Str host = mkstr(T.o.slab, T.o.lbi_hostname[p]);
     Cursor c = idx_open(W.ix_thost, key_hash_str(host));
     IdxEntry e;
     u32 k = 0;
     while (k < 2 && idx_next(W.ix_thost, c, &e)) {
       if (!streq(mkstr(T.a.slab, e.s0), host)) continue;
-      stub_keys[2 * p + k] = d;
-      stub_vals[2 * p + k] = e.row;
+      if (!(stub_mask[e.row] & bit)) GAR_ATOMIC_OR(&stub_mask[e.row], bit);
       k++;
-    }
-    for (; k < 2; k++) {
-      stub_keys[2 * p + k] = SH_DROP;
-      stub_vals[2 * p + k] = 0;
     }
   }
 };
@@ -656,10 +690,11 @@ struct Sharder {
   void plan_children_and_strings(int l) {
     const LevelSchema &Sc = SH_SCHEMA[l];
     LevelPlan &P = plan[l];
+    for (int c = 0; c < Sc.n_child; c++) P.cnt[c] = alloc<u32>(SH_ARENA_PLAN, (size_t)P.cap + 1);
+    P.slab_scan = alloc<u32>(SH_ARENA_PLAN, (size_t)P.cap + 1);
+    be.for_each("shard_row_sizes", P.cap + 1, FShRowSizes{src[l], Sc, P, G});
     for (int c = 0; c < Sc.n_child; c++) {
       int ch = Sc.child[c];
-      P.cnt[c] = alloc<u32>(SH_ARENA_PLAN, (size_t)P.cap + 1);
-      be.for_each("shard_child_count", P.cap + 1, FShChildCount{src[l], c, P, G, P.cnt[c]});
       be.exclusive_scan(P.cnt[c], P.cap + 1);
       active[ch] = true;
       plan[ch].cap = src[ch].n;
@@ -672,13 +707,7 @@ struct Sharder {
       if (P.cap) be.for_each("shard_child_fill", P.cap, FShChildFill{src[l], c, P, G, plan[ch].sel});
       be.for_each("shard_child_bounds", G + 1, FShDerivedBounds{P.row_off, P.cnt[c], G, plan[ch].row_off, plan[ch].m});
     }
-    P.slab_scan = alloc<u32>(SH_ARENA_PLAN, (size_t)P.cap + 1);
-    if (Sc.n_str) {
-      be.for_each("shard_strlen", P.cap + 1, FShStrLen{src[l], Sc.n_str, P, P.slab_scan});
-      be.exclusive_scan(P.slab_scan, P.cap + 1);
-    } else {
-      be.fill32(P.slab_scan, 0, (size_t)P.cap + 1);
-    }
+    if (Sc.n_str) be.exclusive_scan(P.slab_scan, P.cap + 1);
     be.for_each("shard_slab_bounds", G + 1, FShDerivedBounds{P.row_off, P.slab_scan, G, P.slab_off, nullptr});
   }
   // after every level is planned: bring the boundaries to the host and fill the meta rows
@@ -775,35 +804,34 @@ struct Sharder {
       if (nz) be.for_each("shard_keys", nz, FShIota{keys, vals, c.rank});
       set_top(L_ZONE, keys, vals, nz);
     }
-    {  // records: (destination, record) pairs, sorted and de-duplicated
-      u32 nv = A.n_values;
-      u32 *counts = alloc<u32>(SH_ARENA_PLAN, (size_t)nv + 1);
-      be.fill32(counts, 0, (size_t)nv + 1);
-      if (nv) be.for_each("shard_rec_pairs_count", nv, FShRecPairs{S, W, val_dest, counts, nullptr, nullptr});
-      be.exclusive_scan(counts, nv + 1);
-      u32 np = 0;
-      be.download(&np, counts + nv, 4);
-      u32 *keys = alloc<u32>(SH_ARENA_PLAN, np), *vals = alloc<u32>(SH_ARENA_PLAN, np);
-      u32 *k2 = alloc<u32>(SH_ARENA_PLAN, np), *v2 = alloc<u32>(SH_ARENA_PLAN, np);
-      if (np) be.for_each("shard_rec_pairs_fill", nv, FShRecPairs{S, W, val_dest, counts, keys, vals});
-      sorted_unique_top(L_REC, keys, vals, k2, v2, np, A.n_records);
+    {  // records: destination masks (a record can be needed on several shards), then the (destination, record) list
+      u32 *mask = alloc<u32>(SH_ARENA_PLAN, A.n_records);
+      be.fill32(mask, 0, (size_t)A.n_records + 1);
+      if (A.n_values) be.for_each("shard_rec_mask", A.n_values, FShRecMask{S, W, val_dest, mask});
+      mask_top(L_REC, mask, A.n_records);
     }
     plan_finish(meta, send_bytes);
   }
-  // (keys, vals) in any order -> sorted by (key, val), duplicates and SH_DROP removed -> top-level selection of level l
-  void sorted_unique_top(int l, u32 *keys, u32 *vals, u32 *k2, u32 *v2, u32 np, u32 val_range) {
-    if (np) {
-      // LSD: by row, then (stable) by destination.  sort_pairs orders by its first array.
-      be.sort_pairs(vals, keys, v2, k2, np, ilog2(next_pow2(val_range + 1)) + 1);
-      be.sort_pairs(keys, vals, k2, v2, np, 8);
-    }
-    u32 *flag = alloc<u32>(SH_ARENA_PLAN, (size_t)np + 1);
-    be.for_each("shard_unique_flag", np + 1, FShUniqueFlag{keys, vals, np, flag});
-    be.exclusive_scan(flag, np + 1);
-    if (np) be.for_each("shard_compact", np, FShCompact{keys, vals, flag, k2, v2});
+  // mask[row] = set of destinations (bits below G) -> top-level selection of level l: rows by (destination, row), a row once per
+  // destination.  No sort: the tiles are in row order and the counts are laid out destination-major.
+  void mask_top(int l, const u32 *mask, u32 n_rows) {
+    const u32 T = (n_rows + SH_MASK_TILE - 1) / SH_MASK_TILE;
+    u32 *counts = alloc<u32>(SH_ARENA_PLAN, (size_t)G * T + 1);
+    be.fill32(counts + (size_t)G * T, 0, 1);
+    if (T) be.for_each("shard_mask_count", T, FShMaskCount{mask, n_rows, G, T, counts});
+    be.exclusive_scan(counts, G * T + 1);
     u32 nu = 0;
-    be.download(&nu, flag + np, 4);
-    set_top(l, k2, v2, nu, true);
+    be.download(&nu, counts + (size_t)G * T, 4);
+    u32 *sel = alloc<u32>(SH_ARENA_PLAN, nu);
+    if (T && nu) be.for_each("shard_mask_fill", T, FShMaskFill{mask, n_rows, G, T, counts, sel});
+    active[l] = true;
+    plan[l].multi = true;
+    plan[l].sel = sel;
+    plan[l].cap = nu;
+    plan[l].m = m_dev(l);
+    plan[l].row_off = row_off_dev(l);
+    plan[l].slab_off = slab_off_dev(l);
+    be.for_each("shard_bounds", G + 1, FShMaskBounds{counts, G, T, plan[l].row_off, plan[l].m});
   }
 
   // ---- pack the current plan into `send` (n_ranks blobs back to back, sizes as reported by the route call)
@@ -829,6 +857,8 @@ struct Sharder {
   template <class Done>
   void pack_to(u8 *const bases[SH_MAX_RANKS], Done level_done) {
     u64 lvl_off[SH_MAX_RANKS] = {0};
+    u32 *any_long = alloc<u32>(SH_ARENA_PLAN, 1);
+    be.fill32(any_long, 0, 1);
     for (int l = 0; l < L_NLEVELS; l++) {
       PackDst D{};
       for (u32 d = 0; d < G; d++) {
@@ -839,8 +869,9 @@ struct Sharder {
       }
       u32 m = h_row_off[l][G];
       if (!active[l] || !m) continue;
-      be.for_each("shard_pack_columns", m, FShPackCols{src[l], SH_SCHEMA[l], plan[l], G, D});
-      if (SH_SCHEMA[l].n_str && h_slab_off[l][G]) be.for_each("shard_pack_strings", m * SH_COPY_LANES, FShPackBytes{src[l], SH_SCHEMA[l].n_str, plan[l], G, D});
+      be.for_each("shard_pack_rows", m, FShPackRows{src[l], SH_SCHEMA[l], plan[l], G, D, any_long});
+      if (SH_SCHEMA[l].n_str && h_slab_off[l][G])
+        be.for_each("shard_pack_long", SH_LONG_WORKERS, FShPackLong{src[l], SH_SCHEMA[l].n_str, plan[l], G, m, D, any_long});
       level_done(l, (const u64 *)lvl_off);
     }
     level_done((int)L_NLEVELS, (const u64 *)lvl_off);
@@ -1010,12 +1041,12 @@ struct Sharder {
     x.slab = A.slab; x.n = A.n_accels; src[L_STUB] = x;
     x = LevelSrc{}; x.str[0] = A.tag_key; x.str[1] = A.tag_val; x.slab = A.slab; x.n = A.n_tags; src[L_STUBTAG] = x;
     u32 np = Dt.o.n_lbi;
-    u32 *lk = alloc<u32>(SH_ARENA_PLAN, np), *lv = alloc<u32>(SH_ARENA_PLAN, np), *lk2 = alloc<u32>(SH_ARENA_PLAN, np), *lv2 = alloc<u32>(SH_ARENA_PLAN, np);
-    u32 *sk = alloc<u32>(SH_ARENA_PLAN, 2 * (size_t)np), *sv = alloc<u32>(SH_ARENA_PLAN, 2 * (size_t)np);
-    u32 *sk2 = alloc<u32>(SH_ARENA_PLAN, 2 * (size_t)np), *sv2 = alloc<u32>(SH_ARENA_PLAN, 2 * (size_t)np);
-    if (np) be.for_each("shard_answer_probes", np, FShAnswer{Dt, W, dir_home, np, lk, lv, sk, sv});
-    sorted_unique_top(L_LB, lk, lv, lk2, lv2, np, A.n_lbs);
-    sorted_unique_top(L_STUB, sk, sv, sk2, sv2, 2 * np, A.n_accels);
+    u32 *lb_mask = alloc<u32>(SH_ARENA_PLAN, A.n_lbs), *stub_mask = alloc<u32>(SH_ARENA_PLAN, A.n_accels);
+    be.fill32(lb_mask, 0, (size_t)A.n_lbs + 1);
+    be.fill32(stub_mask, 0, (size_t)A.n_accels + 1);
+    if (np) be.for_each("shard_answer_probes", np, FShAnswer{Dt, W, dir_home, lb_mask, stub_mask});
+    mask_top(L_LB, lb_mask, A.n_lbs);
+    mask_top(L_STUB, stub_mask, A.n_accels);
     plan_finish(meta, send_bytes);
   }
 

@@ -118,6 +118,38 @@ def test_sharded_hot_keys(garecon, oracle, hostlib):
     assert sum(p.n_objects for p in parts) == len(objects)
 
 
+def long_string_model():
+    ANN = "aws-global-accelerator-controller.h3poteto.dev/"
+    M, O, H, C = ("aws-global-accelerator-controller-managed", "aws-global-accelerator-owner", "aws-global-accelerator-target-hostname", "aws-global-accelerator-cluster")
+    objects, lbs, accs, want_update = [], [], [], []
+    for k in range(14):
+        lbname = f"{k:032x}"
+        host = f"{lbname}-0123456789abcdef.elb.us-west-2.amazonaws.com"
+        long_v = "".join(chr(65 + (i * 5 + k) % 26) for i in range(3001 + 17 * k))
+        ann = {ANN + "global-accelerator-managed": "true", "service.beta.kubernetes.io/aws-load-balancer-type": "nlb", ANN + "global-accelerator-tags": "k=" + long_v,
+               "example.com/blob": "".join(chr(97 + (i * 7 + k) % 26) for i in range(5000 + 13 * k))}
+        objects.append(dict(kind="service", ns="default", name=f"s{k}", spec_type="LoadBalancer", annotations=ann, ports=[(80, "TCP")], lb_ingress=[host]))
+        lbs.append({"region": "us-west-2", "name": lbname, "dns": host, "arn": f"arn:lb{k}", "state": "active"})
+        off = k % 2 == 1
+        want_update.append(off)
+        accs.append({"arn": f"a{k}", "name": f"service-default-s{k}", "dns": f"a{k}.awsglobalaccelerator.com", "enabled": True,
+                     "tags": [(M, "true"), (O, f"service/default/s{k}"), (H, host), (C, "default"), ("k", long_v[:-1] + "!" if off else long_v)],
+                     "listeners": [{"arn": f"l{k}", "proto": "TCP", "ports": [80], "egs": [{"arn": f"e{k}", "endpoints": [f"arn:lb{k}"]}]}]})
+    return objects, {"lbs": lbs, "accelerators": accs, "zones": []}, want_update
+
+
+def test_sharded_long_strings(garecon, oracle, hostlib):
+    """Strings longer than the pack kernel's per-thread cut (2 KB) are finished by the strided second pass; every byte must
+    arrive: a Service whose 3 KB user tag is already on its accelerator needs no op, one whose LAST byte differs needs an update."""
+    objects, actual, want_update = long_string_model()
+    for n_ranks in (2, 3):
+        got, _ = check(garecon, oracle, hostlib, objects, actual, n_ranks)
+        sb = [int(x) for x in got["section_begin"]]
+        ops = got["ops"][sb[0]:sb[1]]
+        assert [int(o["obj"]) for o in ops] == [k for k in range(14) if want_update[k]]
+        assert all(int(o["head"]) & 0xFF == 2 for o in ops)  # GA_UPDATE_ACCEL
+
+
 def test_sharded_other_cluster_name(garecon, oracle, hostlib):
     objects, actual = randmodel.make(3, n_objects=40, cluster="prod-1")
     check(garecon, oracle, hostlib, objects, actual, 3, cluster="prod-1")
@@ -342,6 +374,28 @@ def test_gpu_sharded_hot_keys(garecon, oracle):
     for e in engines:
         e.close()
     check_slices(garecon, oracle.diff(garecon.pack(objects, actual), "default", mode=1), parts, len(objects))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("peers", [False, True])
+def test_gpu_sharded_long_strings(garecon, oracle, peers):
+    objects, actual, want_update = long_string_model()
+    slices = shard.slice_model(objects, actual, 3)
+    engines, keep = [], []
+    for objs_r, act_r, _ in slices:
+        e = garecon.Engine(cluster_name="default")
+        e.load(garecon.pack(objs_r, act_r))
+        engines.append(e)
+    if peers:
+        shard.exchange_local_peers(engines, [s[2] for s in slices])
+    else:
+        shard.exchange_local(engines, [s[2] for s in slices], keep, device="cuda:0")
+    parts = [e.diff() for e in engines]
+    for e in engines:
+        e.close()
+    want = oracle.diff(garecon.pack(objects, actual), "default", mode=1)
+    assert sorted(int(o["obj"]) for o in want.ops) == [k for k in range(14) if want_update[k]]
+    check_slices(garecon, want, parts, len(objects))
 
 
 @pytest.mark.gpu
