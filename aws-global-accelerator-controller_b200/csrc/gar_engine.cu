@@ -451,6 +451,30 @@ struct StateError {
 
 static std::string g_create_error = "";
 
+// Peer push (sharded mode, gar_shard_pack_peers): finished level groups of the staged blobs go to the other GPUs' receive arenas
+// over NVLink as 16-byte coalesced stores, one grid row per destination.  Runs on a high-priority stream beside the pack
+// kernels of the later levels.  (The copy engines moved the same bytes at 340 GB/s aggregate to 7 peers; NCCL's all-to-all 677.)
+struct PushDesc {
+  const uint4 *src[GAR_SHARD_MAX_RANKS];
+  uint4 *dst[GAR_SHARD_MAX_RANKS];
+  unsigned long long n16[GAR_SHARD_MAX_RANKS];
+};
+constexpr int PUSH_BLOCKS = 24, PUSH_THREADS = 512;
+__global__ void __launch_bounds__(PUSH_THREADS) k_peer_push(const __grid_constant__ PushDesc d) {
+  const uint4 *__restrict__ s = d.src[blockIdx.y];
+  uint4 *__restrict__ t = d.dst[blockIdx.y];
+  const unsigned long long n = d.n16[blockIdx.y], stride = (unsigned long long)gridDim.x * blockDim.x;
+  unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + 3 * stride < n; i += 4 * stride) {
+    uint4 a = __ldcs(s + i), b = __ldcs(s + i + stride), c = __ldcs(s + i + 2 * stride), e = __ldcs(s + i + 3 * stride);
+    t[i] = a;
+    t[i + stride] = b;
+    t[i + 2 * stride] = c;
+    t[i + 3 * stride] = e;
+  }
+  for (; i < n; i += stride) t[i] = __ldcs(s + i);
+}
+
 struct gar_engine {
   int device = 0;
   std::string cluster;
@@ -501,6 +525,8 @@ struct gar_engine {
   // straight into the mapped arenas instead — one step, but 8-byte scattered stores over NVLink: 138 GB/s at 8 GPUs)
   DBuf peer_stage;
   cudaStream_t peer_copy_stream[GAR_SHARD_MAX_RANKS] = {};
+  cudaStream_t peer_push_stream = nullptr;  // high priority: its blocks are placed before the pack kernels' next ones
+  bool peer_ce = false;                     // GAR_PEER_CE=1: move the staged blobs with cudaMemcpyAsync (copy engines) instead of k_peer_push
   std::vector<cudaEvent_t> peer_ev;
   bool peer_direct = false;
   void peers_close() {
@@ -1209,6 +1235,7 @@ int gar_engine_create(const gar_config *cfg, gar_engine **out) {
   if (const char *ta = getenv("GAR_TMA_ALL")) e->staged_all = ta[0] == '1';
   if (const char *ng = getenv("GAR_NO_GRAPH")) e->use_graphs = ng[0] != '1';
   if (const char *pd = getenv("GAR_PEER_DIRECT")) e->peer_direct = pd[0] == '1';
+  if (const char *pc = getenv("GAR_PEER_CE")) e->peer_ce = pc[0] == '1';
   e->no_orphans = (cfg->flags & GAR_FLAG_NO_ORPHANS) != 0;
   e->allow_empty_cache = (cfg->flags & GAR_FLAG_ALLOW_EMPTY_CACHE) != 0;
   try {
@@ -1242,6 +1269,7 @@ void gar_engine_destroy(gar_engine *e) {
   cudaFree(e->peer_stage.p);
   for (auto &cs : e->peer_copy_stream)
     if (cs) cudaStreamDestroy(cs);
+  if (e->peer_push_stream) cudaStreamDestroy(e->peer_push_stream);
   for (auto ev : e->peer_ev) cudaEventDestroy(ev);
   for (auto &ar : e->arena)
     for (auto &b : ar) cudaFree(b.p);
@@ -1474,10 +1502,23 @@ int gar_shard_pack_peers(gar_engine *e, int round, const uint64_t *all_meta) {
       for (u32 d = 0; d < G; d++) {
         peer_base[d] = bases[d];
         if (d != me) bases[d] = (u8 *)st.p + stage_off[d];
-        if (d != me && !e->peer_copy_stream[d]) CK(cudaStreamCreateWithFlags(&e->peer_copy_stream[d], cudaStreamNonBlocking));
+        if (e->peer_ce && d != me && !e->peer_copy_stream[d]) CK(cudaStreamCreateWithFlags(&e->peer_copy_stream[d], cudaStreamNonBlocking));
+      }
+      if (!e->peer_ce && !e->peer_push_stream) {
+        int lo = 0, hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CK(cudaStreamCreateWithPriority(&e->peer_push_stream, cudaStreamNonBlocking, hi));
       }
       u64 sent[GAR_SHARD_MAX_RANKS] = {0};
       size_t ev_used = 0;
+      // GAR_PEER_TRACE=1: where the time of this call goes (stderr): pack kernels, first byte on the wire, last byte per destination
+      static const bool trace = getenv("GAR_PEER_TRACE") && getenv("GAR_PEER_TRACE")[0] == '1';
+      cudaEvent_t tr_begin = nullptr, tr_pack_end = nullptr, tr_first[GAR_SHARD_MAX_RANKS] = {}, tr_last[GAR_SHARD_MAX_RANKS] = {};
+      if (trace) {
+        CK(cudaEventCreate(&tr_begin));
+        CK(cudaEventCreate(&tr_pack_end));
+        CK(cudaEventRecord(tr_begin, e->stream));
+      }
       const u64 kGroupBytes = 48ull << 20;  // start a transfer once this much (over all destinations) is packed
       e->sharder->pack_to(bases, [&](int lvl, const u64 *end) {
         u64 pending = 0;
@@ -1491,16 +1532,71 @@ int gar_shard_pack_peers(gar_engine *e, int round, const uint64_t *all_meta) {
         }
         cudaEvent_t ev = e->peer_ev[ev_used++];
         CK(cudaEventRecord(ev, e->stream));
-        for (u32 k = 1; k < G; k++) {  // rank r starts with r+1: no destination is everybody's first
+        if (!e->peer_ce) {
+          PushDesc pd{};
+          u32 cnt = 0;
+          for (u32 k = 1; k < G; k++) {  // rank r starts with r+1: no destination is everybody's first
+            u32 d = (me + k) % G;
+            if (end[d] == sent[d]) continue;
+            pd.src[cnt] = (const uint4 *)(bases[d] + sent[d]);
+            pd.dst[cnt] = (uint4 *)(peer_base[d] + sent[d]);
+            pd.n16[cnt] = (end[d] - sent[d]) >> 4;  // blob sections are multiples of 16 bytes (sh_align)
+            sent[d] = end[d];
+            cnt++;
+          }
+          CK(cudaStreamWaitEvent(e->peer_push_stream, ev, 0));
+          if (trace && !tr_first[0]) {
+            CK(cudaEventCreate(&tr_first[0]));
+            CK(cudaEventRecord(tr_first[0], e->peer_push_stream));
+          }
+          k_peer_push<<<dim3(PUSH_BLOCKS, cnt), PUSH_THREADS, 0, e->peer_push_stream>>>(pd);
+          e->launches++;
+          return;
+        }
+        for (u32 k = 1; k < G; k++) {
           u32 d = (me + k) % G;
           if (end[d] == sent[d]) continue;
           CK(cudaStreamWaitEvent(e->peer_copy_stream[d], ev, 0));
+          if (trace && !tr_first[d]) {
+            CK(cudaEventCreate(&tr_first[d]));
+            CK(cudaEventRecord(tr_first[d], e->peer_copy_stream[d]));
+          }
           CK(cudaMemcpyAsync(peer_base[d] + sent[d], bases[d] + sent[d], end[d] - sent[d], cudaMemcpyDefault, e->peer_copy_stream[d]));
           sent[d] = end[d];
         }
       });
+      auto copy_stream = [&](u32 d) { return e->peer_ce ? e->peer_copy_stream[d] : e->peer_push_stream; };
+      if (trace) {
+        CK(cudaEventRecord(tr_pack_end, e->stream));
+        for (u32 d = 0; d < G; d++)
+          if (d != me) {
+            CK(cudaEventCreate(&tr_last[d]));
+            CK(cudaEventRecord(tr_last[d], copy_stream(d)));
+          }
+      }
       for (u32 d = 0; d < G; d++)
-        if (d != me) CK(cudaStreamSynchronize(e->peer_copy_stream[d]));
+        if (d != me) CK(cudaStreamSynchronize(copy_stream(d)));
+      if (trace) {
+        CK(cudaStreamSynchronize(e->stream));
+        float pack_ms = 0;
+        CK(cudaEventElapsedTime(&pack_ms, tr_begin, tr_pack_end));
+        std::string line = "[peer trace] rank " + std::to_string(me) + " round " + std::to_string(round) + " groups " + std::to_string(ev_used) +
+                           " pack_end " + std::to_string(pack_ms) + " ms;";
+        for (u32 d = 0; d < G; d++)
+          if (d != me) {
+            float a = 0, b = 0;
+            cudaEvent_t first = e->peer_ce ? tr_first[d] : tr_first[0];
+            if (first) CK(cudaEventElapsedTime(&a, tr_begin, first));
+            CK(cudaEventElapsedTime(&b, tr_begin, tr_last[d]));
+            line += " ->" + std::to_string(d) + " " + std::to_string(sent[d] >> 20) + "MB first " + std::to_string(a).substr(0, 5) + " last " + std::to_string(b).substr(0, 5) + ";";
+            cudaEventDestroy(tr_last[d]);
+          }
+        for (auto &f : tr_first)
+          if (f) cudaEventDestroy(f);
+        fprintf(stderr, "%s\n", line.c_str());
+        cudaEventDestroy(tr_begin);
+        cudaEventDestroy(tr_pack_end);
+      }
     }
     e->shard_launches += e->launches - l0;
     CK(cudaStreamSynchronize(e->stream));  // the stores are performed: after the ranks' barrier every arena is complete

@@ -16,7 +16,7 @@ with_bindings = len(sys.argv) > 5 and sys.argv[5] == "bindings"
 pkg = importlib.import_module("aws-global-accelerator-controller_b200")
 synth = importlib.import_module("aws-global-accelerator-controller_b200.synth")
 shard = importlib.import_module("aws-global-accelerator-controller_b200.shard")
-slices = synth.cluster_slices(cfg, n, g)
+slices = synth.cluster_slices(cfg, n, g, layout=1, threads=8)  # column-major slabs, as the packer writes them
 bases = pkg.tables.shard_bases(slices)
 engines = []
 for o, a in slices:
