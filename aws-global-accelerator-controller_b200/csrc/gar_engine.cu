@@ -19,6 +19,7 @@
 #include <thread>
 #include <string>
 #include <vector>
+#include <type_traits>
 #include <utility>
 
 #include "gar_pipeline.h"
@@ -451,6 +452,52 @@ struct StateError {
 
 static std::string g_create_error = "";
 
+// Sharded-mode pack (gar_shard.h FShPackRows): one thread per selected row.  The 256 rows of a block own one contiguous byte
+// range of their destination's slab, so the block assembles it in shared memory and one thread writes it with a bulk store
+// (cp.async.bulk.global.shared::cta): full-width packets whether the destination is this GPU's memory or a peer's arena over
+// NVLink — per-thread 8-byte stores reach 138 GB/s there.  Blocks that straddle two destinations or exceed the tile store directly.
+constexpr u32 PACK_TILE = 40 * 1024;
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, u32 bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_addr(src)), "r"(bytes) : "memory");
+}
+__global__ void __launch_bounds__(256) k_shard_pack_rows(const __grid_constant__ FShPackRows f, u32 m) {
+  __shared__ alignas(128) u8 tile[PACK_TILE + 16];
+  __shared__ u32 s_staged, s_lo, s_bytes, s_d;
+  const u32 j0 = blockIdx.x * blockDim.x, j1 = min(j0 + blockDim.x, m), j = j0 + threadIdx.x;
+  if (threadIdx.x == 0) {
+    const u32 d0 = dest_of(j0, f.P.row_off, f.G), d1 = dest_of(j1 - 1, f.P.row_off, f.G);
+    const u32 lo = f.P.slab_scan[j0], hi = f.P.slab_scan[j1];
+    s_staged = f.S.n_str && d0 == d1 && hi > lo && hi - lo <= PACK_TILE;
+    s_lo = lo;
+    s_bytes = hi - lo;
+    s_d = d0;
+  }
+  __syncthreads();
+  if (!s_staged) {
+    if (j < m) f(j);
+    return;
+  }
+  const u32 d = s_d;
+  u8 *dst = f.D.base[d] + f.D.lay[d].slab + (s_lo - f.P.slab_scan[f.P.row_off[d]]);  // 8-byte aligned
+  u8 *t = tile + ((uintptr_t)dst & 15);                                               // same phase inside a 16-byte line as dst
+  if (j < m) f.row(j, t, s_lo);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the tile was written through the generic proxy, the bulk store reads it through the async one
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const u32 bytes = s_bytes;                                  // multiple of 8
+    u32 head = ((uintptr_t)dst & 15) ? 8u : 0u;
+    if (head > bytes) head = bytes;
+    const u32 body = (bytes - head) & ~15u, tail = bytes - head - body;
+    if (head) *(u64 *)dst = *(const u64 *)t;
+    if (tail) *(u64 *)(dst + head + body) = *(const u64 *)(t + head + body);
+    if (body) {
+      bulk_s2g(dst + head, t + head, body);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the tile must stay until it has been read
+    }
+  }
+}
+
 // Peer push (sharded mode, gar_shard_pack_peers): finished level groups of the staged blobs go to the other GPUs' receive arenas
 // over NVLink as 16-byte coalesced stores, one grid row per destination.  Runs on a high-priority stream beside the pack
 // kernels of the later levels.  (The copy engines moved the same bytes at 340 GB/s aggregate to 7 peers; NCCL's all-to-all 677.)
@@ -608,10 +655,19 @@ struct gar_engine {
   }
 
   // ---- Backend interface (gar_pipeline.h)
+  bool pack_tma = true;  // GAR_PACK_TMA=0: the sharded pack stores every row straight from its thread
   template <class F>
   void for_each(const char *name, u32 n, const F &f) {
     if (!n) return;
     stage_begin(name);
+    if constexpr (std::is_same<F, FShPackRows>::value) {
+      if (pack_tma) {
+        k_shard_pack_rows<<<(n + 255) / 256, 256, 0, stream>>>(f, n);
+        launches++;
+        stage_end();
+        return;
+      }
+    }
     k_for_each<F><<<(n + 255) / 256, 256, 0, stream>>>(f, n);
     launches++;
     stage_end();
@@ -1236,6 +1292,7 @@ int gar_engine_create(const gar_config *cfg, gar_engine **out) {
   if (const char *ng = getenv("GAR_NO_GRAPH")) e->use_graphs = ng[0] != '1';
   if (const char *pd = getenv("GAR_PEER_DIRECT")) e->peer_direct = pd[0] == '1';
   if (const char *pc = getenv("GAR_PEER_CE")) e->peer_ce = pc[0] == '1';
+  if (const char *pt = getenv("GAR_PACK_TMA")) e->pack_tma = pt[0] != '0';
   e->no_orphans = (cfg->flags & GAR_FLAG_NO_ORPHANS) != 0;
   e->allow_empty_cache = (cfg->flags & GAR_FLAG_ALLOW_EMPTY_CACHE) != 0;
   try {

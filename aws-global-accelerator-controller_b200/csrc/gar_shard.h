@@ -409,7 +409,13 @@ struct FShPackRows {
   u32 G;
   PackDst D;
   u32 *any_long;  // device flag: some string was cut
-  GAR_HD void operator()(u32 j) const {
+  // CUDA backend (gar_engine.cu k_shard_pack_rows): a block's 256 consecutive rows own ONE contiguous byte range of the
+  // destination slab, so the block assembles that range in shared memory and writes it with one bulk store
+  // (cp.async.bulk shared -> global: full-width packets, also over NVLink into a peer's arena); row(j, tile, lo) puts row j's
+  // bytes at tile + (its slab position - lo).  tile == nullptr: straight to the destination, long strings cut.
+  static constexpr bool kBlockStagedStore = true;
+  GAR_HD void operator()(u32 j) const { row(j, nullptr, 0); }
+  GAR_HD void row(u32 j, u8 *tile, u32 tile_lo) const {
     u32 d = dest_of(j, P.row_off, G), k = j - P.row_off[d], p = P.sel[j];
     u8 *b = D.base[d];
     const LevelLayout &L = D.lay[d];
@@ -427,8 +433,12 @@ struct FShPackRows {
       u64 len = GAR_STR_LEN(ref[c]);
       ((gar_str *)(b + L.str[c]))[k] = GAR_STR(off, len);
       u32 words = sh_pad8((u32)len) >> 3;
-      cut |= words > SH_LONG_WORDS;
-      sh_copy_words((u64 *)(b + L.slab + off), src.slab + GAR_STR_OFF(ref[c]), words > SH_LONG_WORDS ? SH_LONG_WORDS : words);
+      if (tile) {
+        sh_copy_words((u64 *)(tile + (P.slab_scan[P.row_off[d]] + off - tile_lo)), src.slab + GAR_STR_OFF(ref[c]), words);
+      } else {
+        cut |= words > SH_LONG_WORDS;
+        sh_copy_words((u64 *)(b + L.slab + off), src.slab + GAR_STR_OFF(ref[c]), words > SH_LONG_WORDS ? SH_LONG_WORDS : words);
+      }
       off += (u64)words << 3;
     }
     if (cut) *any_long = 1;
