@@ -452,10 +452,10 @@ struct StateError {
 
 static std::string g_create_error = "";
 
-// Sharded-mode pack (gar_shard.h FShPackRows): one thread per selected row.  The 256 rows of a block own one contiguous byte
-// range of their destination's slab, so the block assembles it in shared memory and one thread writes it with a bulk store
-// (cp.async.bulk.global.shared::cta): full-width packets whether the destination is this GPU's memory or a peer's arena over
-// NVLink — per-thread 8-byte stores reach 138 GB/s there.  Blocks that straddle two destinations or exceed the tile store directly.
+// Sharded-mode pack, shared-memory variant (gar_shard.h FShPackRows; optional, GAR_PACK_TMA=1): one thread per selected row.  The
+// 256 rows of a block own one contiguous byte range of their destination's slab, so the block assembles it in shared memory and
+// one thread writes it with a bulk store (cp.async.bulk.global.shared::cta).  Blocks that straddle two destinations or exceed
+// the tile store directly.  Kept for the record: it lost against plain per-thread stores both locally and over NVLink.
 constexpr u32 PACK_TILE = 40 * 1024;
 __device__ __forceinline__ void bulk_s2g(void *dst, const void *src, u32 bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_addr(src)), "r"(bytes) : "memory");
@@ -500,7 +500,8 @@ __global__ void __launch_bounds__(256) k_shard_pack_rows(const __grid_constant__
 
 // Peer push (sharded mode, gar_shard_pack_peers): finished level groups of the staged blobs go to the other GPUs' receive arenas
 // over NVLink as 16-byte coalesced stores, one grid row per destination.  Runs on a high-priority stream beside the pack
-// kernels of the later levels.  (The copy engines moved the same bytes at 340 GB/s aggregate to 7 peers; NCCL's all-to-all 677.)
+// kernels of the later levels.  (Measured at 8 GPUs, 2.6 GB to 7 peers per rank: copy engines 340 GB/s aggregate, last byte at
+// 7.8 ms; this kernel: last byte 0.2 ms after the last pack kernel, at 6.8 ms; NCCL all-to-all after a separate pack: 7.9 ms.)
 struct PushDesc {
   const uint4 *src[GAR_SHARD_MAX_RANKS];
   uint4 *dst[GAR_SHARD_MAX_RANKS];
@@ -655,7 +656,10 @@ struct gar_engine {
   }
 
   // ---- Backend interface (gar_pipeline.h)
-  bool pack_tma = true;  // GAR_PACK_TMA=0: the sharded pack stores every row straight from its thread
+  // GAR_PACK_TMA=1: the sharded pack assembles each block's slab range in shared memory and bulk-stores it (k_shard_pack_rows).
+  // Measured on the B200 (profiles/r02_pack_tma_ab.json): 10 % slower than per-thread stores into local memory (5.54 vs 5.02 ms,
+  // 2*10^6 objects) and 2.4x slower straight into peer arenas over NVLink (16.6 vs 6.8 ms per round-1 pack at 8 GPUs) — off.
+  bool pack_tma = false;
   template <class F>
   void for_each(const char *name, u32 n, const F &f) {
     if (!n) return;
@@ -1292,7 +1296,7 @@ int gar_engine_create(const gar_config *cfg, gar_engine **out) {
   if (const char *ng = getenv("GAR_NO_GRAPH")) e->use_graphs = ng[0] != '1';
   if (const char *pd = getenv("GAR_PEER_DIRECT")) e->peer_direct = pd[0] == '1';
   if (const char *pc = getenv("GAR_PEER_CE")) e->peer_ce = pc[0] == '1';
-  if (const char *pt = getenv("GAR_PACK_TMA")) e->pack_tma = pt[0] != '0';
+  if (const char *pt = getenv("GAR_PACK_TMA")) e->pack_tma = pt[0] == '1';
   e->no_orphans = (cfg->flags & GAR_FLAG_NO_ORPHANS) != 0;
   e->allow_empty_cache = (cfg->flags & GAR_FLAG_ALLOW_EMPTY_CACHE) != 0;
   try {

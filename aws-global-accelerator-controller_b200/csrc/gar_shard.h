@@ -409,10 +409,10 @@ struct FShPackRows {
   u32 G;
   PackDst D;
   u32 *any_long;  // device flag: some string was cut
-  // CUDA backend (gar_engine.cu k_shard_pack_rows): a block's 256 consecutive rows own ONE contiguous byte range of the
-  // destination slab, so the block assembles that range in shared memory and writes it with one bulk store
-  // (cp.async.bulk shared -> global: full-width packets, also over NVLink into a peer's arena); row(j, tile, lo) puts row j's
-  // bytes at tile + (its slab position - lo).  tile == nullptr: straight to the destination, long strings cut.
+  // Optional CUDA variant (gar_engine.cu k_shard_pack_rows, GAR_PACK_TMA=1): a block's 256 consecutive rows own ONE contiguous
+  // byte range of the destination slab, so the block can assemble that range in shared memory and write it with one bulk store;
+  // row(j, tile, lo) puts row j's bytes at tile + (its slab position - lo).  tile == nullptr (the default path): straight to
+  // the destination, long strings cut.
   static constexpr bool kBlockStagedStore = true;
   GAR_HD void operator()(u32 j) const { row(j, nullptr, 0); }
   GAR_HD void row(u32 j, u8 *tile, u32 tile_lo) const {

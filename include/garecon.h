@@ -471,10 +471,11 @@ uint64_t gar_shard_blob_bytes(const uint64_t *meta_row);
 
 /* Peer-memory exchange (one process per GPU on one NVLink / NVSwitch node): no collective on the data path.  Every rank maps the
    RECEIVE arenas of the other GPUs through CUDA IPC; gar_shard_pack_peers packs the rank's own blob in place and the others into a
-   local stage from which the copy engines push them into the peers' arenas over NVLink, one stream per destination, level group by
-   level group while the later levels are still being packed (transfer and partitioning overlap).  GAR_PEER_DIRECT=1 makes the pack
-   kernels store straight into the mapped arenas instead (one step, but 8-byte scattered stores over NVLink: 2.4x slower on 8
-   GPUs).  Per round:
+   local stage from which a copy kernel on a high-priority stream pushes them into the peers' arenas over NVLink (16-byte coalesced
+   stores), level group by level group while the later levels are still being packed (transfer and partitioning overlap).
+   Alternatives kept behind environment switches because they were measured and lost on 8 B200s: GAR_PEER_CE=1 (copy engines
+   instead of the copy kernel), GAR_PEER_DIRECT=1 (the pack kernels store straight into the mapped arenas: 8-byte scattered
+   stores over NVLink), GAR_PACK_TMA=1 (bulk stores from shared memory).  Per round:
 
      gar_shard_route(e, &shard, round, meta, send_bytes)
      all-gather the meta rows                                  -> all_meta[s][d] = row of source s for destination d
