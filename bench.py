@@ -218,7 +218,13 @@ def _cpu_arm(ob, snap, threads_list, reps=1, mode=CPU_TUNED):
 
 
 def _thread_ladder(cores):
-    return sorted({t for t in (1, 8, 32, 128, cores) if t <= cores})
+    return sorted({t for t in (1, 8, 32, 64, 128, cores) if t <= cores})
+
+
+def _best_threads(scaling):
+    """The thread count the CPU arm is reported at: the fastest of the ladder (on an SMT box all hardware threads can be slower
+    than half of them; the baseline is the best the host can do, not a fixed count)."""
+    return max(scaling, key=lambda t: scaling[t])
 
 
 def run_reference(args, rank, world):
@@ -237,24 +243,25 @@ def run_reference(args, rank, world):
     cfg.layout = 1 if args.layout == "column" else 0
     snap = synth.SynthSnapshot(cfg)
     cl = snap.cluster.encode()
-    for _ in range(min(args.warmup, 1)):
-        ob.diff_raw(snap.objects, snap.actual, cl, CPU_TUNED, cores)
+    scaling = _cpu_arm(ob, snap, _thread_ladder(cores))  # one untimed pass per thread count: warm-up and the choice of the count
+    best_t = _best_threads(scaling)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        ob.diff_raw(snap.objects, snap.actual, cl, CPU_TUNED, cores)
+        ob.diff_raw(snap.objects, snap.actual, cl, CPU_TUNED, best_t)
     dt = time.perf_counter() - t0
     value = n * args.steps / dt
-    scaling = _cpu_arm(ob, snap, [t for t in _thread_ladder(cores) if t != cores])
-    scaling[cores] = value
+    scaling[best_t] = value
     literal = _cpu_arm(ob, snap, [cores], mode=CPU_LITERAL)[cores]
+    cores_used = best_t
     sample = (f"the whole workload: config {args.config} generator at {n} objects (seed {int(cfg.seed)}, {args.layout}-major slabs); oracle mode 2 "
-              f"(tuned: flat hash indexes, tag digests, thread pool; bit-identical to the literal port, tests/test_synth_configs.py), {cores} threads")
+              f"(tuned: flat hash indexes, tag digests, thread pool; bit-identical to the literal port, tests/test_synth_configs.py), {best_t} threads "
+              f"= the fastest of the ladder in `scaling` on this host ({cores} hardware threads)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32 (bytes and indices)",
         "data": "synthetic", "config": {"workload": _workload_name(args.config, args.objects), "sample_objects": n, "same_config": n == args.objects,
                                         "slab_layout": args.layout, "seed": int(cfg.seed)},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores_used, "kind": "port", "sample": sample,
                          "scaling": {str(k): round(v, 1) for k, v in sorted(scaling.items())},
                          "literal_port": {"value": literal, "cores": cores, "what": "oracle mode 1: the function-by-function restatement over unordered_map indexes"}},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -759,12 +766,13 @@ def main():
                 faithful.append({"objects": fn, "seconds": round(fdt, 3), "objects_per_s": round(fn / fdt, 1)})
             line["cpu_faithful"] = {"kind": "port", "cores": 1, "runs": faithful,
                                     "note": "literal per-object linear scans as in the reference (quadratic); indexed multi-thread figure is cpu_baseline"}
-            line["cpu_baseline"] = {"value": scaling[cores], "unit": UNIT, "cores": cores, "kind": "port", "same_config": same,
+            best_t = _best_threads(scaling)
+            line["cpu_baseline"] = {"value": scaling[best_t], "unit": UNIT, "cores": best_t, "kind": "port", "same_config": same,
                                     "scaling": {str(k): round(v, 1) for k, v in sorted(scaling.items())},
                                     "literal_port": {"scaling": {str(k): round(v, 1) for k, v in sorted(literal.items())},
                                                      "what": "oracle mode 1: the function-by-function restatement over unordered_map indexes (the parity arbiter)"},
                                     "sample": f"{'the timed workload itself' if same else 'a sample'}: config {args.config} generator at {cn} objects, oracle mode 2 (tuned: flat "
-                                              f"hash indexes, tag digests, thread pool; bit-identical to the literal port), {cores} threads (thread ladder in `scaling`); "
+                                              f"hash indexes, tag digests, thread pool; bit-identical to the literal port), {best_t} threads = the fastest of the ladder in `scaling` ({cores} hardware threads); "
                                               f"Go reference not timed (no toolchain)"}
     _unpin(torch, pinned_addrs)
     del snap, o, a, hcs, flush_buf
