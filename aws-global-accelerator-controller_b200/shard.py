@@ -99,6 +99,16 @@ def exchange_local_peers(engines, shards):
             e.shard_unpack(rnd, arenas[d], np.ascontiguousarray(all_meta[:, d]))
 
 
+_MAX_BLOB_BYTES = 1 << 40  # what a 40-bit string offset can address: a meta row that claims more is corrupt, not big
+
+
+def _check_blob_sizes(sizes, what):
+    """Sizes derived from meta rows another rank sent: refuse nonsense before it becomes an allocation or a collective."""
+    for s, n in enumerate(sizes):
+        if n < 0 or n % 16 or n >= _MAX_BLOB_BYTES:
+            raise ValueError(f"sharded exchange: implausible blob size {n} in the meta row of rank {s} ({what})")
+
+
 class DistExchange:
     """torch.distributed data path of one rank.  Buffers are torch uint8 tensors on `device` (cuda:N or cpu)."""
 
@@ -159,6 +169,7 @@ class DistExchange:
         recv_meta = m_in.cpu().numpy().view(np.uint64)
         in_sizes = [int(x) for x in nbytes]
         out_sizes = [self.e.blob_bytes(recv_meta[s]) for s in range(self.g)]
+        self._guard(lambda: _check_blob_sizes(out_sizes, "received"))
         send = torch.empty(sum(in_sizes) + 64, dtype=torch.uint8, device=self.device)
         if str(self.device) != "cpu":
             torch.cuda.current_stream().synchronize()  # the allocation (and any fill) is on torch's stream, the engine packs on its own
@@ -302,6 +313,7 @@ class PeerExchange(DistExchange):
             all_meta = np.ascontiguousarray(gathered[:, :meta.nbytes]).view(np.uint64).reshape((g,) + meta.shape)  # [source][destination][words]
             handles = np.ascontiguousarray(gathered[:, meta.nbytes:meta.nbytes + abi.SHARD_HANDLE_BYTES])
             caps = [int(np.ascontiguousarray(gathered[d, meta.nbytes + abi.SHARD_HANDLE_BYTES:]).view(np.uint64)[0]) for d in range(g)]
+            _check_blob_sizes([self.e.blob_bytes(all_meta[s][d]) for s in range(g) for d in range(g)], "all-gathered")
             need = [sum(self.e.blob_bytes(all_meta[s][d]) for s in range(g)) for d in range(g)]
             if any(caps[d] < need[d] + 64 for d in range(g)):  # every rank sees the same numbers: all of them take this branch or none
                 arena, handle, _ = self._guard(lambda: self.e.shard_arena(rnd, need[me]))
