@@ -1060,6 +1060,9 @@ static void do_diff(gar_engine *e, gar_changeset *out, bool to_host, const gar_k
   e->shard_reported = true;
   e->stage_depth = 0;
   if (e->shard_home && (ks || bd)) throw InvalidError{"incremental / binding diffs are not available on a sharded sub-snapshot"};
+  if (e->shard_home && e->shard_round != 4)
+    throw StateError{"a new exchange has started: the previous sub-snapshot's strings live in receive buffers that are being refilled; "
+                     "finish both rounds (gar_shard_unpack(.., 2, ..)) before the next diff"};
   if (!e->pipe) {
     e->graph_drop();  // recorded launches belong to the previous pipeline's buffers and tables
     e->pipe = new Pipeline<gar_engine>(*e, e->T);

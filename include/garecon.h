@@ -451,7 +451,8 @@ int gar_bindings_diff(gar_engine *e, const gar_bindings *bindings, gar_changeset
                                                               copied: the sub-snapshot's strings live in BOTH rounds' receive
                                                               buffers, which must stay alive and unchanged until the last
                                                               diff of this exchange (the next gar_shard_route(.., 1) or
-                                                              gar_snapshot_load ends their use)
+                                                              gar_snapshot_load ends their use; between that route call
+                                                              and its second unpack gar_diff returns GAR_E_STATE)
    Round 1 moves every row to the shard its own key hashes to and one probe per lbIngress hostname to the "directory"
    shard of that hostname; round 2 returns the load balancer / by-hostname accelerators each probe resolves to.  After the
    second unpack the engine holds a self-contained sub-snapshot: gar_diff / gar_diff_device work as usual, n_objects is

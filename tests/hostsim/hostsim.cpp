@@ -228,6 +228,7 @@ int gar_snapshot_attach_device(gar_engine *e, const gar_objects *o, const gar_ac
 static int diff_impl(gar_engine *e, gar_changeset *out, const gar_keyset *ks, const gar_bindings *bd = nullptr) {
   memset(out, 0, sizeof(*out));
   e->launches = 0;
+  if (e->shard_home && e->shard_round != 4) return GAR_E_STATE;  // mid-exchange: the old sub-snapshot's receive buffers are being refilled
   if (!e->pipe) {
     e->pipe = new Pipeline<gar_engine>(*e, e->T);
     if (const char *tc = getenv("GAR_TINY_CAPS")) e->pipe->tiny_caps = tc[0] == '1';

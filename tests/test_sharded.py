@@ -163,6 +163,36 @@ def test_sharded_empty_and_lopsided(garecon, oracle, hostlib):
     check(garecon, oracle, hostlib, [], actual, 3)
 
 
+def test_diff_in_the_middle_of_a_new_exchange_is_refused(garecon, hostlib):
+    """The sub-snapshot's strings stay in the receive buffers (no copy): once the next exchange has started they are being
+    refilled, so a diff must wait for both rounds — GAR_E_STATE instead of decisions about half-overwritten strings."""
+    objects, actual = randmodel.make(7, n_objects=40)
+    slices = shard.slice_model(objects, actual, 2)
+    engines, keep, snaps = [], [], []
+    for objs_r, act_r, _ in slices:
+        e = garecon.Engine(cluster_name="default", lib=hostlib)
+        snaps.append(garecon.pack(objs_r, act_r))
+        e.load(snaps[-1])
+        engines.append(e)
+    shards = [s[2] for s in slices]
+    assert engines[0].diff().n_objects == len(slices[0][0])  # before any exchange: the slice itself is diffed
+    shard.exchange_local(engines, shards, keep)
+    first = [e.diff() for e in engines]
+    engines[0].shard_route(shards[0], 1)                     # a new exchange starts on rank 0 ...
+    with pytest.raises(garecon.abi.GarError) as ei:
+        engines[0].diff()                                    # ... its old sub-snapshot is no longer readable
+    assert ei.value.rc == garecon.abi.GAR_E_STATE
+    engines[1].shard_route(shards[1], 1)
+    keep2 = []
+    # finish the exchange properly (route is idempotent: exchange_local routes again) and compare with the first result
+    shard.exchange_local(engines, shards, keep2)
+    second = [e.diff() for e in engines]
+    for a, b in zip(first, second):
+        assert a.ops.tolist() == b.ops.tolist() and a.status_ga.tolist() == b.status_ga.tolist()
+    for e in engines:
+        e.close()
+
+
 def test_contract_violations_are_errors(garecon, hostlib):
     """The two layout rules of sharded mode are checked on the device: same zone table everywhere, whole zones per rank in
     ascending ranges."""
