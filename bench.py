@@ -122,6 +122,31 @@ def _np_col(ptr, n, dtype):
     return np.frombuffer((C.c_char * (n * np.dtype(dtype).itemsize)).from_address(addr), dtype=dtype, count=n)
 
 
+def _key_is(col, slab_ptr, slab_len, literal: bytes):
+    """Boolean mask over a gar_str column: rows whose string equals `literal` (length AND bytes, chunked so that the gathered
+    candidates stay small)."""
+    import numpy as np
+    lens = (col >> np.uint64(40)).astype(np.int64)
+    mask = lens == len(literal)
+    cand = np.flatnonzero(mask)
+    if not len(cand) or not literal:
+        return mask
+    slab = _np_col(slab_ptr, slab_len, np.uint8)
+    want = np.frombuffer(literal, dtype=np.uint8)
+    offs = (col[cand] & np.uint64((1 << 40) - 1)).astype(np.int64)
+    step = 1 << 16
+    for b in range(0, len(cand), step):
+        o = offs[b:b + step]
+        same = (slab[o[:, None] + np.arange(len(literal))[None, :]] == want[None, :]).all(axis=1)
+        mask[cand[b:b + step][~same]] = False
+    return mask
+
+
+TAG_OWNER_KEY, TAG_THOST_KEY = b"aws-global-accelerator-owner", b"aws-global-accelerator-target-hostname"
+TAG_MANAGED_KEY, TAG_CLUSTER_KEY = b"aws-global-accelerator-controller-managed", b"aws-global-accelerator-cluster"
+ANN_R53_KEY = b"aws-global-accelerator-controller.h3poteto.dev/route53-hostname"
+
+
 def kernel_byte_models(o, a, n_ops_ga_obj: int, n_pairs: int, frac_ga: float):
     """Algorithmic bytes of the two decide kernels (DESIGN.md "Per-kernel byte model"): the unique input bytes each must
     read at least once + what it must write.  Index/digest structures it reads are counted (they are its inputs);
@@ -132,10 +157,12 @@ def kernel_byte_models(o, a, n_ops_ga_obj: int, n_pairs: int, frac_ga: float):
     key_bytes = L(o.obj_ns, n) + L(o.obj_name, n) + n
     host_bytes = L(o.lbi_hostname, o.n_lbi)
     lb_strings = L(a.lb_region, a.n_lbs) + L(a.lb_name, a.n_lbs) + L(a.lb_dns, a.n_lbs) + L(a.lb_arn, a.n_lbs)
-    tk = _np_col(a.tag_key, a.n_tags, np.uint64) >> np.uint64(40)
+    tkc = _np_col(a.tag_key, a.n_tags, np.uint64)
     tv = _np_col(a.tag_val, a.n_tags, np.uint64) >> np.uint64(40)
-    thost_bytes = int(tv[tk == 38].sum())   # aws-global-accelerator-target-hostname
-    owner_bytes = int(tv[tk == 28].sum())   # aws-global-accelerator-owner
+    is_owner, is_thost = _key_is(tkc, a.slab, a.slab_len, TAG_OWNER_KEY), _key_is(tkc, a.slab, a.slab_len, TAG_THOST_KEY)
+    is_managed, is_cluster = _key_is(tkc, a.slab, a.slab_len, TAG_MANAGED_KEY), _key_is(tkc, a.slab, a.slab_len, TAG_CLUSTER_KEY)
+    thost_bytes = int(tv[is_thost].sum())
+    owner_bytes = int(tv[is_owner].sum())
     acc_strings = L(a.acc_name, a.n_accels) + thost_bytes + owner_bytes + L(a.ep_id, a.n_endpoints)
     ga = frac_ga * (host_bytes + 17 * o.n_lbi + lb_strings + (32 + 16) * a.n_lbs + acc_strings + (32 + 64) * a.n_accels) \
         + n * (4 + 8 + 16 + 8 + 1) + key_bytes + 4 * o.n_ports * frac_ga + n * 8 + 24 * n_ops_ga_obj
@@ -147,9 +174,9 @@ def kernel_byte_models(o, a, n_ops_ga_obj: int, n_pairs: int, frac_ga: float):
     zone_name_per = L(a.zone_name, a.n_zones) / max(a.n_zones, 1)
     # per pair: hostname piece, pair row, zone entry + name, the object's value entries (32 B each, ~1 per pair) with the
     # owner-key bytes of the in-zone one, its record name, the value->alias link, the alias DNS name, the accelerator DNS name
-    ak = _np_col(o.ann_key, o.n_ann, np.uint64) >> np.uint64(40)
+    is_r53 = _key_is(_np_col(o.ann_key, o.n_ann, np.uint64), o.slab, o.slab_len, ANN_R53_KEY)
     av = _np_col(o.ann_val, o.n_ann, np.uint64) >> np.uint64(40)
-    ann_r53 = int(av[ak == 63].sum())  # aws-global-accelerator-controller.h3poteto.dev/route53-hostname (63 bytes)
+    ann_r53 = int(av[is_r53].sum())
     r53 = ann_r53 + n_pairs * ((4 + 8) + (1 + 4 + 4) + 32 + zone_name_per + 32 + key_bytes / max(n, 1) + name_bytes_per_rec + 16 + alias_bytes_per_rec + acc_dns_per + 8 + 8 + 1 + 16)
     models = {"ga_objects": int(ga), "r53_pairs": int(r53)}
     # ---- the other stages: input bytes each must read once + output bytes it writes (same rules: no re-reads, no scratch)
@@ -157,7 +184,7 @@ def kernel_byte_models(o, a, n_ops_ga_obj: int, n_pairs: int, frac_ga: float):
     known_key_bytes = 1024  # interned annotation keys: a handful of distinct strings
     models["classify_objects"] = int(n * (3 + 3 * 8 + 3 * 4) + ann_key_refs + 8 * o.n_ann + known_key_bytes + key_bytes + n * (4 + 8 + 4 * 8 + 4))
     models["tokenise_hostnames"] = int(host_bytes + 8 * o.n_lbi + 17 * o.n_lbi)
-    sys_tag_bytes = int(tv[(tk == 28) | (tk == 38) | (tk == 41) | (tk == 30)].sum())  # owner, target-hostname, managed, cluster
+    sys_tag_bytes = int(tv[is_owner | is_thost | is_managed | is_cluster].sum())
     models["digest_accelerators"] = int(a.n_accels * (2 * 4 + 2 * 8 + 1) + 16 * a.n_tags + sys_tag_bytes + a.n_listeners * (1 + 8) + 4 * a.n_port_ranges
                                         + 4 * a.n_egs + 8 * a.n_endpoints + a.n_accels * (64 + 5 * 8 + 2 * 8 + 4))
     name_bytes = L(a.rec_name, nrec)
@@ -170,7 +197,7 @@ def kernel_byte_models(o, a, n_ops_ga_obj: int, n_pairs: int, frac_ga: float):
     models["idx_place"] = int(idx_rows_total * (28 + 32 + 4) + 4 * idx_rows_total)
     models["idx_order"] = int(idx_rows_total * 0.25 * (4 + 2.5 * 32 * 2))  # ~a quarter of the buckets hold 2-3 entries: read + written back
     models["hash_load_balancers"] = int(L(a.lb_region, a.n_lbs) + L(a.lb_name, a.n_lbs) + a.n_lbs * (16 + 8 + 4))
-    n_annotated = int((ak == 63).sum())
+    n_annotated = int(is_r53.sum())
     models["r53_prepare"] = int(n * (4 + 8 + 1) + host_bytes + n_annotated * (32 + 8 + acc_dns_per) + ann_r53 + n * (1 + 4 + 8 + 4))
     models["r53_objects"] = int(n * (1 + 4 + 4 + 4) + n_pairs * (1 + 4 + 4) + n * 8)
     models["r53_fill_pairs"] = int(n * (4 + 8) + ann_r53 + n_pairs * (4 + 8))
